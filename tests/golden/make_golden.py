@@ -1,0 +1,204 @@
+"""Generate golden vectors by executing the REAL reference code on seeded synthetic inputs.
+
+Run in the authoring container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+What is executed is the unmodified reference: `Sam2MatchingBaselineNoAMG.forward_test`,
+`.forward_fill_memory`, `._process_sam_masks`, `MemoryBank.postprocess`, `compute_sim_global_avg`,
+`compute_semantic_ios`, `batched_mask_to_box`, `calculate_stability_score` — bound to a light-weight
+stand-in for `self` that supplies synthetic tensors at the encoder seams (`_forward_sam`,
+`_extract_target_features`, `_forward_encoder`), because the frozen encoders are out of scope and
+random-init SAM-2 emits degenerate masks.  Intermediate values are captured by wrapping
+the functions `forward_test` looks up in its module globals.
+
+Outputs: tests/golden/<case>.npz (inputs are NOT stored — they are regenerated from the seed by
+`synth.make_stage_inputs`; a sha256 of the inputs is stored to detect generator drift).
+"""
+import hashlib
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import ref_shim  # noqa: E402
+
+synth = importlib.import_module("no-time-to-train_b200.synth")
+
+# name -> (n, c, n_cls, shots, ori_hw, seed, degenerate, num_out_instance, clustered)
+STAGE_CASES = {
+    "stage_a_1024_degenerate": (64, 384, 5, 2, (1024, 1024), 101, True, 10, True),
+    "stage_b_480x640": (48, 384, 5, 2, (480, 640), 102, False, 10, True),
+    "stage_c_427x640_degenerate": (48, 384, 4, 3, (427, 640), 103, True, 10, True),
+    "stage_d_200x180_downscale": (40, 384, 5, 2, (200, 180), 104, False, 10, True),
+    "stage_e_config1_1cls_1shot": (100, 384, 1, 1, (1024, 1024), 105, True, 100, False),
+    "stage_f_truncate_333x500": (96, 64, 3, 2, (333, 500), 106, False, 4, True),
+    "stage_g_iid_80cls": (128, 256, 80, 10, (512, 512), 107, True, 100, False),
+}
+
+# name -> (n_cls, shots, filled_per_class, c, seed)
+FILL_CASES = {
+    "fill_a_3cls_2shot": (3, 2, [2, 2, 1], 32, 201),
+    "fill_b_5cls_3shot": (5, 3, [3, 3, 3, 3, 0], 48, 202),
+}
+
+
+def sha(*tensors) -> str:
+    h = hashlib.sha256()
+    for t in tensors:
+        h.update(np.ascontiguousarray(t.detach().cpu().numpy()).tobytes())
+    return h.hexdigest()
+
+
+def run_stage_case(ref, name, spec):
+    n, c, n_cls, shots, ori_hw, seed, degenerate, num_out, clustered = spec
+    inp = synth.make_stage_inputs(n, c, n_cls, shots, ori_hw, seed=seed, clustered=clustered,
+                                  degenerate=degenerate)
+    model_mod = sys.modules[ref.Model.__module__]
+    cap = {}
+
+    def wrap(fn_name, rec):
+        orig = getattr(model_mod, fn_name)
+
+        def inner(*a, **k):
+            out = orig(*a, **k)
+            rec(a, k, out)
+            return out
+        setattr(model_mod, fn_name, inner)
+        return orig
+
+    boxes_calls = []
+    origs = {
+        "compute_sim_global_avg": wrap("compute_sim_global_avg",
+                                       lambda a, k, o: cap.update(sim=o[0].clone(), obj_feats=o[1].clone())),
+        "batched_nms": wrap("batched_nms", lambda a, k, o: cap.update(nms_keep_full=o.clone())),
+        "compute_semantic_ios": wrap("compute_semantic_ios",
+                                     lambda a, k, o: cap.update(ios=o.clone(), full_masks=a[0].clone(),
+                                                                labels_sel=a[1].clone())),
+        "batched_mask_to_box": wrap("batched_mask_to_box", lambda a, k, o: boxes_calls.append(o.clone())),
+    }
+    try:
+        fake = types.SimpleNamespace()
+        fake.predictor = types.SimpleNamespace(device=torch.device("cpu"))
+        fake.encoder_h, fake.encoder_w = 37, 37
+        fake.cls_num_per_mask = 1
+        fake.num_out_instance = num_out
+        fake.nms_thr = 0.5
+        fake.online_vis = False
+        fake.memory_bank = types.SimpleNamespace(feats_ins_avg=inp.feats_ins_avg, n_classes=n_cls)
+        fake.sam_transform = lambda x: x
+        fake._extract_target_features = lambda img, device: (inp.tar_feat, img)
+        fake._forward_sam = lambda imgs: (inp.lr_masks, inp.pred_ious, None)
+        fake._process_sam_masks = types.MethodType(ref.Model._process_sam_masks, fake)
+        fake._reset = lambda: None
+        info = dict(ori_height=ori_hw[0], ori_width=ori_hw[1], file_name="synthetic", id=0)
+        with torch.inference_mode():
+            out = ref.Model.forward_test(
+                fake, [dict(target_img=torch.zeros(3, 8, 8), target_img_info=info)], False)[0]
+            stab = ref.calculate_stability_score(inp.lr_masks, 0.0, 1.0)
+    finally:
+        for k, v in origs.items():
+            setattr(model_mod, k, v)
+
+    full = cap.get("full_masks")
+    g = dict(
+        spec=np.array([n, c, n_cls, shots, ori_hw[0], ori_hw[1], seed, int(degenerate), num_out,
+                       int(clustered)], dtype=np.int64),
+        inputs_sha=np.array(sha(inp.lr_masks, inp.pred_ious, inp.tar_feat, inp.feats_ins_avg)),
+        sim=cap["sim"].numpy(),
+        obj_feats=cap["obj_feats"].numpy(),
+        lr_boxes=boxes_calls[0].numpy(),
+        nms_keep_full=cap["nms_keep_full"].numpy(),
+        stability=stab.numpy(),
+        out_scores=out["scores"].numpy(),
+        out_labels=out["labels"].numpy(),
+        out_bboxes=out["bboxes"].numpy(),
+        out_masks_packed=np.packbits(out["binary_masks"].numpy().reshape(out["binary_masks"].shape[0], -1),
+                                     axis=-1),
+    )
+    if full is not None:
+        g.update(
+            ios=cap["ios"].numpy(),
+            labels_sel=cap["labels_sel"].numpy(),
+            full_area=full.reshape(full.shape[0], -1).sum(-1).numpy(),
+            full_boxes=boxes_calls[1].numpy(),
+            full_masks_sha=np.array(sha(full)),
+        )
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **g)
+    print(f"{name}: K_sel={0 if full is None else full.shape[0]} K_out={out['scores'].shape[0]} "
+          f"nan_scores={int(torch.isnan(out['scores']).sum())} labels_used={len(set(out['labels'].tolist()))}")
+
+
+def run_fill_case(ref, name, spec):
+    n_cls, shots, filled, c, seed = spec
+    e_side, img_side = 37, 74
+    e = e_side * e_side
+    feats, _ = synth.make_ref_shots(n_cls, shots, e, c, seed=seed)
+    gen = torch.Generator().manual_seed(seed + 1)
+    bank = ref.MemoryBank(dict(category_num=n_cls, length=shots, feat_shape=(e, c)), 2, 2)
+    order = [(ci, li) for li in range(shots) for ci in range(n_cls) if li < filled[ci]]
+    calls = {"i": 0}
+
+    def fake_encoder(imgs):
+        ci, li = order[calls["i"]]
+        calls["i"] += 1
+        return feats[ci, li].reshape(1, e, c)
+
+    fake = types.SimpleNamespace()
+    fake.predictor = types.SimpleNamespace(device=torch.device("cpu"))
+    fake.encoder_img_size = img_side
+    fake.encoder_transform = lambda x: x
+    fake.encoder_dim = c
+    fake.encoder_h, fake.encoder_w = e_side, e_side
+    fake._forward_encoder = fake_encoder
+    fake.memory_bank = bank
+    fake.memory_bank_neg = None
+    soft_masks = []
+    for ci, li in order:
+        m = torch.zeros(1, img_side, img_side)
+        y0, x0 = torch.randint(0, img_side // 2, (2,), generator=gen).tolist()
+        hh, ww = torch.randint(6, img_side // 2, (2,), generator=gen).tolist()
+        m[0, y0:y0 + hh, x0:x0 + ww] = 1.0
+        m[0, y0:y0 + 3, x0:x0 + ww] = torch.rand(3, ww, generator=gen)
+        soft_masks.append(m)
+        img = torch.rand(1, 3, img_side, img_side, generator=gen)
+        ref.Model.forward_fill_memory(fake, [dict(refs_by_cat={ci: dict(imgs=img, masks=m)})], True)
+    masks_lowres = bank.masks.clone()
+    bank.postprocess()
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"),
+        spec=np.array([n_cls, shots, c, seed, e_side, img_side], dtype=np.int64),
+        filled=np.array(filled, dtype=np.int64),
+        order=np.array(order, dtype=np.int64),
+        soft_masks=torch.cat(soft_masks).numpy(),
+        masks_lowres=masks_lowres.numpy(),
+        fill_counts=bank.fill_counts.numpy(),
+        feats_avg=bank.feats_avg.numpy(),
+        feats_ins_avg=bank.feats_ins_avg.numpy(),
+        postprocessed=bank.postprocessed.numpy(),
+    )
+    print(f"{name}: fill_counts={bank.fill_counts.tolist()}")
+
+
+def main():
+    torch.manual_seed(0)
+    ref = ref_shim.load()
+    only = sys.argv[1:]
+    for name, spec in STAGE_CASES.items():
+        if not only or name in only:
+            run_stage_case(ref, name, spec)
+    for name, spec in FILL_CASES.items():
+        if not only or name in only:
+            run_fill_case(ref, name, spec)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,57 @@
+"""Helpers shared by the oracle-vs-golden (CPU) and CUDA-vs-golden (GPU) tests."""
+import hashlib
+import importlib
+import os
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STAGE_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith("stage_") and f.endswith(".npz"))
+FILL_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith("fill_") and f.endswith(".npz"))
+
+RTOL = 1e-3  # BASELINE.json north_star: pooled features / prototypes / similarities within 1e-3 relative
+
+
+def load_case(name):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
+    n, c, n_cls, shots, oh, ow, seed, degenerate, num_out, clustered = g["spec"].tolist()
+    synth = importlib.import_module("no-time-to-train_b200.synth")
+    inp = synth.make_stage_inputs(n, c, n_cls, shots, (oh, ow), seed=seed, clustered=bool(clustered),
+                                  degenerate=bool(degenerate))
+    h = hashlib.sha256()
+    for t in (inp.lr_masks, inp.pred_ious, inp.tar_feat, inp.feats_ins_avg):
+        h.update(np.ascontiguousarray(t.numpy()).tobytes())
+    assert h.hexdigest() == str(g["inputs_sha"]), "synthetic generator drifted from the golden inputs"
+    return g, inp, dict(num_out_instance=num_out, n_cls=n_cls)
+
+
+def sha_bool(t) -> str:
+    a = t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+    return hashlib.sha256(np.ascontiguousarray(a.astype(np.bool_)).tobytes()).hexdigest()
+
+
+def assert_close_rel(actual, expected, rtol=RTOL, what=""):
+    """|a-e| <= rtol * max|e| row-wise scale (vectors are unit-norm or cosine-valued), NaN == NaN."""
+    a = np.asarray(actual, dtype=np.float64)
+    e = np.asarray(expected, dtype=np.float64)
+    assert a.shape == e.shape, f"{what}: shape {a.shape} vs {e.shape}"
+    assert np.array_equal(np.isnan(a), np.isnan(e)), f"{what}: NaN pattern differs"
+    scale = max(np.nanmax(np.abs(e)), 1e-30) if e.size else 1.0
+    err = np.nanmax(np.abs(a - e)) / scale if e.size else 0.0
+    assert err <= rtol, f"{what}: max relative error {err:.3e} > {rtol}"
+
+
+def assert_same_ranking(scores_a, labels_a, scores_e, labels_e, rtol=RTOL, what=""):
+    """Final per-image rankings must be identical; permutations are tolerated only inside groups whose
+    reference scores tie within the float tolerance (argsort is unstable in the reference, :674-675)."""
+    sa, se = np.asarray(scores_a, np.float64), np.asarray(scores_e, np.float64)
+    la, le = np.asarray(labels_a), np.asarray(labels_e)
+    assert sa.shape == se.shape, f"{what}: K_out {sa.shape} vs {se.shape}"
+    assert_close_rel(sa, se, rtol, what + " scores")
+    if np.array_equal(la, le):
+        return
+    bad = np.nonzero(la != le)[0]
+    for i in bad:
+        near = np.abs(se - se[i]) <= rtol * max(abs(se[i]), 1e-6)
+        assert le[i] in la[near] and la[i] in le[near], f"{what}: label order differs at rank {i} outside a tie group"
