@@ -1,0 +1,208 @@
+/*
+ * nttt_b200.h — C-ABI of libnttt_b200.so: the B200-native (sm_100a) reference-matching stage of
+ * DogRog/no-time-to-train.
+ *
+ * The reference has no FFI: its seam is the Python class `Sam2MatchingBaselineNoAMG`
+ * (no_time_to_train/models/Sam2MatchingBaseline_noAMG.py:128-765).  Each entry point below replaces the
+ * library calls of one section of that class; the reference file:line it replaces is cited per function.
+ * `no-time-to-train_b200/model.py` is the host-side mirror that binds these with ctypes (see
+ * INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless the name ends in `_host`;
+ *   - the caller owns every buffer (inputs, outputs, workspace); nothing is allocated per call;
+ *   - `stream` is a `cudaStream_t` passed as `void*`; every call is stream-ordered and never
+ *     synchronises the device; data-dependent counts are returned in device memory;
+ *   - return value: 0 on success, a negative `NTTT_E*` code otherwise (never throws);
+ *   - there is no CPU path: on a machine without an sm_100 device the compute entries return
+ *     NTTT_ENODEVICE / the CUDA launch error.
+ *
+ * Bit-packed masks: one `uint32_t` word holds 32 consecutive pixels of ONE row, bit b = pixel x0+b
+ * (LSB first).  A row of W pixels occupies `words = (W+31)/32` words; pad bits are zero.
+ */
+#ifndef NTTT_B200_H
+#define NTTT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NTTT_VERSION 100
+
+enum {
+  NTTT_OK = 0,
+  NTTT_EINVAL = -1,     /* bad argument (null pointer, non-positive size, unsupported shape) */
+  NTTT_ENODEVICE = -2,  /* no CUDA device / not an sm_100 device */
+  NTTT_ECUDA = -3,      /* a CUDA runtime / driver call failed; see nttt_last_cuda_error() */
+  NTTT_EWORKSPACE = -4, /* workspace too small */
+  NTTT_EUNSUPPORTED = -5
+};
+
+typedef struct nttt_ctx nttt_ctx;
+
+int nttt_version(void);
+const char* nttt_error_string(int code);
+/* text of the last CUDA error seen by this thread's calls ("" if none) */
+const char* nttt_last_cuda_error(void);
+
+/* Per-device context: caches the antialias weight tables, TMA descriptors and the normalised
+ * prototypes.  Not thread-safe; use one per host thread/stream set. */
+int nttt_ctx_create(nttt_ctx** out, int device);
+void nttt_ctx_destroy(nttt_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------------
+ * a6 / a9 / a15 — low-res threshold, bit-pack, area, box, stability counts
+ * replaces: `lr_masks > 0` (Sam2MatchingBaseline_noAMG.py:548-549), `batched_mask_to_box(lr_masks > 0)`
+ * (:614, sam2/utils/amg.py:305-348) and `calculate_stability_score` (sam2/utils/amg.py:158-178).
+ *   logits [n, h, w] f32 (h*w multiple of 128; SAM-2 emits 256x256)
+ *   bits   [n, h*w/32] u32          area [n] i32            box [n,4] i32 (x1,y1,x2,y2 inclusive; empty->0)
+ *   stab   [n,2] i32 = {count(logit > thr+off), count(logit > thr-off)}
+ *   flags  [n] i32: bit0 = every positive logit is finite and in (2^-100, 2^100) (lets the full-res
+ *          resize skip uniformly-positive footprints without evaluating them)
+ */
+int nttt_threshold_pack(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits,
+                        int32_t* area, int32_t* box, int32_t* stab, int32_t* flags, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * a6 (feature half) + a7 — mask-average pooling and cosine similarity
+ * replaces: F.interpolate(tar_feat, 256x256, antialias) (:551-558) and compute_sim_global_avg
+ * (matching_baseline_utils.py:869-904).
+ *
+ * Factored form: masks @ upsample(feat) == (Uy^T M Ux) @ feat.  nttt_project_masks computes the
+ * [n, E] projection of each packed mask onto the encoder grid with the exact antialias weights;
+ * nttt_pool_normalize contracts it with feat [E, C] on the tensor cores (split-bf16 operands, fp32
+ * accumulate), divides by the area (0 -> 1) and L2-normalises (eps 1e-12).
+ */
+int nttt_project_masks(nttt_ctx* ctx, const uint32_t* bits, int n, int h, int w, int eh, int ew,
+                       float* proj /* [n, eh*ew] */, void* stream);
+size_t nttt_pool_workspace_bytes(int n, int e, int c);
+int nttt_pool_normalize(nttt_ctx* ctx, const float* proj, const float* feat /* [e, c] */,
+                        const int32_t* area, int n, int e, int c, float* obj_feats /* [n, c] */,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* prototypes = normalize(mean over ALL L slots of feats_ins_avg) (matching_baseline_utils.py:893-894),
+ * computed once per memory bank instead of once per image.  proto [n_cls, c] f32. */
+int nttt_proto_prepare(const float* feats_ins_avg, int n_cls, int shots, int c, float* proto, void* stream);
+
+/* a7 (similarity) + a8 (top-1 label; `k == n_cls` branch of :606-609 applies when n_cls == 1)
+ *   sim [n, n_cls] f32 (may be NULL), top_score [n] f32, top_label [n] i32 (lowest index on ties) */
+size_t nttt_similarity_workspace_bytes(int n, int c, int n_cls);
+int nttt_similarity_top1(nttt_ctx* ctx, const float* obj_feats, const float* proto, int n, int c, int n_cls,
+                         float* sim, float* top_score, int32_t* top_label, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * a10 / a11 — class-aware box NMS + positive-score filter
+ * replaces: torchvision batched_nms(boxes.float(), pred_ious, labels, nms_thr)[:out_num] (:621-629) and the
+ * `scores > 0` compaction (:631-641).  Suppression arithmetic is the published torchvision kernel's
+ * (fp32 inter / (areaA + areaB - inter) > thr, areas without +1); order = score desc, index asc on ties.
+ *   keep [max_keep] i32, n_keep [1] i32 : NMS survivors, truncated to max_keep (= out_num)
+ *   sel  [max_keep] i32, n_sel  [1] i32 : those of `keep` whose top_score > 0, same order
+ */
+size_t nttt_nms_workspace_bytes(int n);
+int nttt_box_nms(const int32_t* box, const float* nms_scores, const int32_t* labels, const float* top_score,
+                 int n, float iou_thr, int max_keep, int32_t* keep, int32_t* n_keep, int32_t* sel,
+                 int32_t* n_sel, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * a12 / a9 — antialiased bilinear resize of the selected logits + threshold + bit-pack (+area, +box)
+ * replaces: F.interpolate(lr_masks_out, (H,W), bilinear, antialias=True) > 0 (:657-663) and
+ * batched_mask_to_box (:665).  Bit-exact with aten's arithmetic.
+ *   sel/n_sel: indices into logits (device); processes k < min(*n_sel, max_sel)
+ *   bits_full [max_sel, oh, words(ow)] u32 — only words inside rect[k] are written; everything outside
+ *              rect[k] is zero BY CONTRACT and must not be read
+ *   rect [max_sel,4] i32 = {row0,row1,word0,word1} half-open bound derived from the low-res box
+ *   area_full [max_sel] i32, box_full [max_sel,4] i32
+ */
+int nttt_upsample_threshold_pack(nttt_ctx* ctx, const float* logits, const uint32_t* bits_lr,
+                                 const int32_t* box_lr, const int32_t* flags_lr, int ih, int iw,
+                                 const int32_t* sel, const int32_t* n_sel, int max_sel, int oh, int ow,
+                                 uint32_t* bits_full, int32_t* rect, int32_t* area_full, int32_t* box_full,
+                                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * a13 — intersection-over-self decay term on packed masks (popcount), per class
+ * replaces: obj_sim = clamp(F F^T, 0) (:668-669) and compute_semantic_ios (matching_baseline_utils.py:831-867).
+ *   inter_out (nullable) [max_sel, max_sel] i32 receives the integer intersection counts of same-label
+ *   pairs (0 elsewhere) for parity tests.
+ */
+int nttt_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_t* area_full,
+                  const int32_t* box_full, const int32_t* sel, const int32_t* n_sel, int max_sel, int oh, int ow,
+                  const int32_t* labels, const float* obj_feats, int c, float* ios, int32_t* inter_out,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * a14 — score decay, final top-k, output gather
+ * replaces: scores * pow(1 - ios, 0.5), argsort(descending)[:num_out] and the output dict (:671-683).
+ * NaN sorts first (torch semantics); ties keep selection order.
+ *   out_masks [num_out, oh, ow] u8 (torch.bool layout), out_boxes [num_out,4] i64, out_scores [num_out] f32,
+ *   out_labels [num_out] i64, n_out [1] i32, out_index [num_out] i32 (index into logits),
+ *   out_slot [num_out] i32 (position in the selected list `sel`)
+ */
+int nttt_decay_topk(const float* top_score, const int32_t* labels, const float* ios, const int32_t* sel,
+                    const int32_t* n_sel, int max_sel, int num_out, const uint32_t* bits_full,
+                    const int32_t* rect, const int32_t* box_full, int oh, int ow, uint8_t* out_masks,
+                    int64_t* out_boxes, float* out_scores, int64_t* out_labels, int32_t* out_index,
+                    int32_t* out_slot, int32_t* n_out, void* stream);
+
+/* unpack all selected masks (tests / debugging): masks_u8 [max_sel, oh, ow] */
+int nttt_unpack_masks(const uint32_t* bits_full, const int32_t* rect, const int32_t* n_sel, int max_sel, int oh,
+                      int ow, uint8_t* masks_u8, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * a2 / a5 — memory-bank fill and post-process
+ * replaces: the raw-feature slot writes of forward_fill_memory (:465-485) and MemoryBank.postprocess
+ * (matching_baseline_utils.py:574-599).  Instead of storing raw [n_cls,L,E,C] features the bank keeps the
+ * mask-weighted sums: sum[c,l,:] = sum_e mask[e] * feat[e,:], wsum[c,l] = sum_e mask[e].
+ *   soft_mask [mh, mw] f32 is nearest-resized to (eh, ew) exactly like F.interpolate(mode="nearest") (:465-469)
+ *   mask_lowres_out (nullable) [eh*ew] receives the resized mask
+ */
+int nttt_fill_pool_accumulate(const float* feat /* [eh*ew, c] */, const float* soft_mask, int mh, int mw,
+                              int eh, int ew, int c, float* sum_slot /* [c] */, float* wsum_slot /* [1] */,
+                              float* mask_lowres_out, void* stream);
+int nttt_fill_finalize(const float* sum /* [n_cls, L, c] */, const float* wsum /* [n_cls, L] */, int n_cls,
+                       int shots, int c, float* feats_ins_avg, float* feats_avg, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * The whole matching stage of one image, enqueued on one stream with no host synchronisation
+ * (Sam2MatchingBaseline_noAMG.py:582-683).
+ */
+typedef struct nttt_match_args {
+  /* inputs */
+  const float* logits;    /* [n, 256, 256] */
+  const float* pred_ious; /* [n] */
+  const float* tar_feat;  /* [eh*ew, c] */
+  const float* proto;     /* [n_cls, c] from nttt_proto_prepare */
+  int32_t n, lr_h, lr_w, eh, ew, c, n_cls;
+  int32_t ori_h, ori_w;
+  float nms_thr;
+  int32_t num_out_instance; /* outputs capacity */
+  int32_t max_sel;          /* = min(8 * num_out_instance, n) */
+  /* outputs (capacity num_out_instance) */
+  uint8_t* out_masks;
+  int64_t* out_boxes;
+  float* out_scores;
+  int64_t* out_labels;
+  int32_t* out_index;
+  int32_t* counts; /* [4] i32: n_keep, n_sel, n_out, reserved */
+  /* optional taps for tests (nullable) */
+  float* sim;       /* [n, n_cls] */
+  float* obj_feats; /* [n, c] — if NULL, kept in workspace */
+  /* workspace */
+  void* workspace;
+  size_t workspace_bytes;
+} nttt_match_args;
+
+size_t nttt_match_workspace_bytes(int n, int lr_h, int lr_w, int eh, int ew, int c, int n_cls, int ori_h,
+                                  int ori_w, int max_sel);
+int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* args, void* stream);
+/* sizeof(nttt_match_args) as compiled, so FFI mirrors can verify their layout */
+size_t nttt_sizeof_match_args(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTTT_B200_H */

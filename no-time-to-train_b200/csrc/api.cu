@@ -1,0 +1,409 @@
+// C-ABI of libnttt_b200.so (see include/nttt_b200.h).  Host-side only: argument checks, workspace carving,
+// kernel launches.  No allocation per call, no device synchronisation (except one-time table builds).
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace nttt {
+
+// launchers implemented in the kernel translation units
+int launch_lowres_pack(const float*, int, int, int, float, float, uint32_t*, int32_t*, int32_t*, int32_t*, int32_t*,
+                       cudaStream_t);
+int launch_project_masks(const AxisTable&, const AxisTable&, const uint32_t*, int, int, int, int, int, float*, int,
+                         cudaStream_t);
+int launch_sgemm(bool, const float*, int, const float*, int, float*, int, int, int, int, cudaStream_t);
+int launch_normalize_rows(const float*, const int32_t*, int, int, float*, cudaStream_t);
+int launch_proto_prepare(const float*, int, int, int, float*, cudaStream_t);
+int launch_top1(const float*, int, int, int, float*, int32_t*, cudaStream_t);
+size_t nms_workspace_bytes(int n);
+int launch_box_nms(const int32_t*, const float*, const int32_t*, const float*, int, float, int, int32_t*, int32_t*,
+                   int32_t*, int32_t*, void*, size_t, cudaStream_t);
+int launch_upsample_pack(const AxisTable&, const AxisTable&, const float*, const uint32_t*, const int32_t*,
+                         const int32_t*, int, int, const int32_t*, const int32_t*, int, int, int, uint32_t*, int32_t*,
+                         int32_t*, int32_t*, int32_t*, cudaStream_t);
+size_t upsample_scratch_bytes(int max_sel);
+int launch_unpack(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, uint8_t*,
+                  cudaStream_t);
+int launch_mask_ios(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
+                    int, int, int, const int32_t*, const float*, int, float*, int32_t*, cudaStream_t);
+int launch_decay_rank(const float*, const int32_t*, const float*, const int32_t*, const int32_t*, int, int,
+                      const int32_t*, int64_t*, float*, int64_t*, int32_t*, int32_t*, int32_t*, float*, cudaStream_t);
+int launch_fill_pool(const float*, const float*, int, int, int, int, int, float*, float*, float*, cudaStream_t);
+int launch_fill_finalize(const float*, const float*, int, int, int, float*, float*, cudaStream_t);
+
+static thread_local char g_cuda_err[512] = "";
+
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? NTTT_ENODEVICE : NTTT_ECUDA;
+}
+
+// bump allocator over the caller's workspace
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = align_up(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += sizeof(T) * count;
+    return p;
+  }
+};
+
+}  // namespace nttt
+
+using namespace nttt;
+
+const nttt::AxisTable* nttt_ctx::axis(int in_size, int out_size, cudaStream_t s, int* err) {
+  *err = NTTT_OK;
+  for (int i = 0; i < n_tables; ++i)
+    if (tables[i].in_size == in_size && tables[i].out_size == out_size) return &tables[i];
+  if (n_tables == kMaxTables) {  // evict the oldest (sizes rarely change within a run)
+    cudaStreamSynchronize(s);
+    free_axis_table(tables[0]);
+    for (int i = 1; i < n_tables; ++i) tables[i - 1] = tables[i];
+    --n_tables;
+  }
+  AxisTable& t = tables[n_tables];
+  t = AxisTable{};
+  *err = build_axis_table(t, in_size, out_size, s);
+  if (*err != NTTT_OK) return nullptr;
+  // the tables are read by kernels on any stream afterwards: make them visible once, here
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { *err = cuda_fail(e, "axis table build"); return nullptr; }
+  ++n_tables;
+  return &t;
+}
+
+extern "C" {
+
+int nttt_version(void) { return NTTT_VERSION; }
+
+size_t nttt_sizeof_match_args(void) { return sizeof(nttt_match_args); }
+
+const char* nttt_error_string(int code) {
+  switch (code) {
+    case NTTT_OK: return "ok";
+    case NTTT_EINVAL: return "invalid argument";
+    case NTTT_ENODEVICE: return "no CUDA device";
+    case NTTT_ECUDA: return "CUDA error";
+    case NTTT_EWORKSPACE: return "workspace too small";
+    case NTTT_EUNSUPPORTED: return "unsupported shape";
+    default: return "unknown error";
+  }
+}
+
+const char* nttt_last_cuda_error(void) { return g_cuda_err; }
+
+int nttt_ctx_create(nttt_ctx** out, int device) {
+  if (!out) return NTTT_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    if (e != cudaSuccess) cuda_fail(e, "cudaGetDeviceCount");
+    return NTTT_ENODEVICE;
+  }
+  if (device < 0 || device >= count) return NTTT_EINVAL;
+  cudaDeviceProp prop;
+  NTTT_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d is sm_%d%d; libnttt_b200 is built for sm_100a only", device,
+             prop.major, prop.minor);
+    return NTTT_ENODEVICE;
+  }
+  NTTT_CUDA(cudaSetDevice(device));
+  nttt_ctx* ctx = new nttt_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return NTTT_OK;
+}
+
+void nttt_ctx_destroy(nttt_ctx* ctx) {
+  if (!ctx) return;
+  for (int i = 0; i < ctx->n_tables; ++i) free_axis_table(ctx->tables[i]);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  delete ctx;
+}
+
+int nttt_threshold_pack(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits, int32_t* area,
+                        int32_t* box, int32_t* stab, int32_t* flags, void* stream) {
+  if (n < 0 || h <= 0 || w <= 0) return NTTT_EINVAL;
+  if (n > 0 && (!logits || !bits || !area || !box || !stab || !flags)) return NTTT_EINVAL;
+  return launch_lowres_pack(logits, n, h, w, thr, off, bits, area, box, stab, flags, (cudaStream_t)stream);
+}
+
+int nttt_project_masks(nttt_ctx* ctx, const uint32_t* bits, int n, int h, int w, int eh, int ew, float* proj,
+                       void* stream) {
+  if (!ctx || n < 0 || h <= 0 || w <= 0 || eh <= 0 || ew <= 0) return NTTT_EINVAL;
+  if (n > 0 && (!bits || !proj)) return NTTT_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  int err;
+  const AxisTable* tx = ctx->axis(ew, w, s, &err);
+  if (!tx) return err;
+  const AxisTable* ty = ctx->axis(eh, h, s, &err);
+  if (!ty) return err;
+  return launch_project_masks(*tx, *ty, bits, n, h, w, eh, ew, proj, eh * ew, s);
+}
+
+size_t nttt_pool_workspace_bytes(int n, int e, int c) {
+  (void)e;
+  return align_up(sizeof(float) * (size_t)n * c, 256);
+}
+
+int nttt_pool_normalize(nttt_ctx* ctx, const float* proj, const float* feat, const int32_t* area, int n, int e, int c,
+                        float* obj_feats, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!ctx || n < 0 || e <= 0 || c <= 0) return NTTT_EINVAL;
+  if (n == 0) return NTTT_OK;
+  if (!proj || !feat || !area || !obj_feats || !workspace) return NTTT_EINVAL;
+  if (workspace_bytes < nttt_pool_workspace_bytes(n, e, c)) return NTTT_EWORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* sums = static_cast<float*>(workspace);
+  int err = launch_sgemm(false, proj, e, feat, c, sums, c, n, c, e, s);
+  if (err) return err;
+  return launch_normalize_rows(sums, area, n, c, obj_feats, s);
+}
+
+int nttt_proto_prepare(const float* feats_ins_avg, int n_cls, int shots, int c, float* proto, void* stream) {
+  if (n_cls <= 0 || shots <= 0 || c <= 0 || !feats_ins_avg || !proto) return NTTT_EINVAL;
+  return launch_proto_prepare(feats_ins_avg, n_cls, shots, c, proto, (cudaStream_t)stream);
+}
+
+size_t nttt_similarity_workspace_bytes(int n, int c, int n_cls) {
+  (void)c;
+  return align_up(sizeof(float) * (size_t)n * n_cls, 256);
+}
+
+int nttt_similarity_top1(nttt_ctx* ctx, const float* obj_feats, const float* proto, int n, int c, int n_cls,
+                         float* sim, float* top_score, int32_t* top_label, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  if (!ctx || n < 0 || c <= 0 || n_cls <= 0) return NTTT_EINVAL;
+  if (n == 0) return NTTT_OK;
+  if (!obj_feats || !proto || !top_score || !top_label) return NTTT_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* simbuf = sim;
+  if (!simbuf) {
+    if (!workspace || workspace_bytes < nttt_similarity_workspace_bytes(n, c, n_cls)) return NTTT_EWORKSPACE;
+    simbuf = static_cast<float*>(workspace);
+  }
+  int err = launch_sgemm(true, obj_feats, c, proto, c, simbuf, n_cls, n, n_cls, c, s);
+  if (err) return err;
+  return launch_top1(simbuf, n_cls, n, n_cls, top_score, top_label, s);
+}
+
+size_t nttt_nms_workspace_bytes(int n) { return nms_workspace_bytes(n > 0 ? n : 1); }
+
+int nttt_box_nms(const int32_t* box, const float* nms_scores, const int32_t* labels, const float* top_score, int n,
+                 float iou_thr, int max_keep, int32_t* keep, int32_t* n_keep, int32_t* sel, int32_t* n_sel,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (n < 0 || !keep || !n_keep || !sel || !n_sel) return NTTT_EINVAL;
+  if (n > 0 && (!box || !nms_scores || !labels || !top_score || !workspace)) return NTTT_EINVAL;
+  return launch_box_nms(box, nms_scores, labels, top_score, n, iou_thr, max_keep, keep, n_keep, sel, n_sel, workspace,
+                        workspace_bytes, (cudaStream_t)stream);
+}
+
+// scratch for the cross-CTA per-mask statistics of the stand-alone resize entry is owned by the ctx
+static int ensure_scratch(nttt_ctx* ctx, int max_sel, int32_t** out) {
+  if (max_sel > ctx->scratch_cap) {
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_cap = 0;
+    NTTT_CUDA(cudaMalloc(&ctx->scratch, upsample_scratch_bytes(max_sel)));
+    ctx->scratch_cap = max_sel;
+  }
+  *out = ctx->scratch;
+  return NTTT_OK;
+}
+
+int nttt_upsample_threshold_pack(nttt_ctx* ctx, const float* logits, const uint32_t* bits_lr, const int32_t* box_lr,
+                                 const int32_t* flags_lr, int ih, int iw, const int32_t* sel, const int32_t* n_sel,
+                                 int max_sel, int oh, int ow, uint32_t* bits_full, int32_t* rect, int32_t* area_full,
+                                 int32_t* box_full, void* stream) {
+  if (!ctx || max_sel < 0 || ih <= 0 || iw <= 0 || oh <= 0 || ow <= 0) return NTTT_EINVAL;
+  if (max_sel == 0) return NTTT_OK;
+  if (!logits || !bits_lr || !box_lr || !flags_lr || !sel || !n_sel || !bits_full || !rect || !area_full || !box_full)
+    return NTTT_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  int err;
+  const AxisTable* tx = ctx->axis(iw, ow, s, &err);
+  if (!tx) return err;
+  const AxisTable* ty = ctx->axis(ih, oh, s, &err);
+  if (!ty) return err;
+  int32_t* scratch = nullptr;
+  err = ensure_scratch(ctx, max_sel, &scratch);
+  if (err) return err;
+  return launch_upsample_pack(*tx, *ty, logits, bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, oh, ow,
+                              bits_full, rect, area_full, box_full, scratch, s);
+}
+
+int nttt_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_t* area_full, const int32_t* box_full,
+                  const int32_t* sel, const int32_t* n_sel, int max_sel, int oh, int ow, const int32_t* labels,
+                  const float* obj_feats, int c, float* ios, int32_t* inter_out, void* stream) {
+  if (max_sel < 0 || oh <= 0 || ow <= 0 || c <= 0) return NTTT_EINVAL;
+  if (max_sel == 0) return NTTT_OK;
+  if (!bits_full || !rect || !area_full || !box_full || !sel || !n_sel || !labels || !obj_feats || !ios)
+    return NTTT_EINVAL;
+  return launch_mask_ios(bits_full, rect, area_full, box_full, sel, n_sel, max_sel, oh, ow, labels, obj_feats, c, ios,
+                         inter_out, (cudaStream_t)stream);
+}
+
+int nttt_decay_topk(const float* top_score, const int32_t* labels, const float* ios, const int32_t* sel,
+                    const int32_t* n_sel, int max_sel, int num_out, const uint32_t* bits_full, const int32_t* rect,
+                    const int32_t* box_full, int oh, int ow, uint8_t* out_masks, int64_t* out_boxes, float* out_scores,
+                    int64_t* out_labels, int32_t* out_index, int32_t* out_slot, int32_t* n_out, void* stream) {
+  if (max_sel < 0 || num_out < 0 || oh <= 0 || ow <= 0) return NTTT_EINVAL;
+  if (!n_out) return NTTT_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (max_sel == 0 || num_out == 0) {
+    NTTT_CUDA(cudaMemsetAsync(n_out, 0, sizeof(int32_t), s));
+    return NTTT_OK;
+  }
+  if (!top_score || !labels || !ios || !sel || !n_sel || !bits_full || !rect || !box_full || !out_masks || !out_boxes ||
+      !out_scores || !out_labels || !out_index || !out_slot)
+    return NTTT_EINVAL;
+  int err = launch_decay_rank(top_score, labels, ios, sel, n_sel, max_sel, num_out, box_full, out_boxes, out_scores,
+                              out_labels, out_index, out_slot, n_out, nullptr, s);
+  if (err) return err;
+  return launch_unpack(bits_full, rect, out_slot, n_out, num_out, oh, ow, out_masks, s);
+}
+
+int nttt_unpack_masks(const uint32_t* bits_full, const int32_t* rect, const int32_t* n_sel, int max_sel, int oh, int ow,
+                      uint8_t* masks_u8, void* stream) {
+  if (max_sel < 0 || oh <= 0 || ow <= 0) return NTTT_EINVAL;
+  if (max_sel == 0) return NTTT_OK;
+  if (!bits_full || !rect || !n_sel || !masks_u8) return NTTT_EINVAL;
+  return launch_unpack(bits_full, rect, nullptr, n_sel, max_sel, oh, ow, masks_u8, (cudaStream_t)stream);
+}
+
+int nttt_fill_pool_accumulate(const float* feat, const float* soft_mask, int mh, int mw, int eh, int ew, int c,
+                              float* sum_slot, float* wsum_slot, float* mask_lowres_out, void* stream) {
+  if (!feat || !soft_mask || !sum_slot || !wsum_slot || mh <= 0 || mw <= 0 || eh <= 0 || ew <= 0 || c <= 0)
+    return NTTT_EINVAL;
+  return launch_fill_pool(feat, soft_mask, mh, mw, eh, ew, c, sum_slot, wsum_slot, mask_lowres_out,
+                          (cudaStream_t)stream);
+}
+
+int nttt_fill_finalize(const float* sum, const float* wsum, int n_cls, int shots, int c, float* feats_ins_avg,
+                       float* feats_avg, void* stream) {
+  if (!sum || !wsum || !feats_ins_avg || !feats_avg || n_cls <= 0 || shots <= 0 || c <= 0) return NTTT_EINVAL;
+  return launch_fill_finalize(sum, wsum, n_cls, shots, c, feats_ins_avg, feats_avg, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// whole-image pipeline
+// ---------------------------------------------------------------------------------------------------
+struct MatchLayout {
+  uint32_t* bits_lr; int32_t* area_lr; int32_t* box_lr; int32_t* stab; int32_t* flags;
+  float* proj; float* sums; float* obj_feats; float* sim; float* top_score; int32_t* top_label;
+  void* nms_ws; size_t nms_ws_bytes; int32_t* keep; int32_t* sel;
+  uint32_t* bits_full; int32_t* rect; int32_t* area_full; int32_t* box_full; int32_t* scratch;
+  float* ios; int32_t* out_slot;
+  size_t total;
+};
+
+static MatchLayout carve(void* ws, int n, int lr_h, int lr_w, int eh, int ew, int c, int n_cls, int oh, int ow,
+                         int max_sel, int num_out) {
+  Carver cv(ws);
+  MatchLayout L;
+  const size_t p = (size_t)lr_h * lr_w;
+  L.bits_lr = cv.take<uint32_t>((size_t)n * (p / 32));
+  L.area_lr = cv.take<int32_t>(n);
+  L.box_lr = cv.take<int32_t>((size_t)n * 4);
+  L.stab = cv.take<int32_t>((size_t)n * 2);
+  L.flags = cv.take<int32_t>(n);
+  L.proj = cv.take<float>((size_t)n * eh * ew);
+  L.sums = cv.take<float>((size_t)n * c);
+  L.obj_feats = cv.take<float>((size_t)n * c);
+  L.sim = cv.take<float>((size_t)n * n_cls);
+  L.top_score = cv.take<float>(n);
+  L.top_label = cv.take<int32_t>(n);
+  L.nms_ws_bytes = nms_workspace_bytes(n > 0 ? n : 1);
+  L.nms_ws = cv.take<char>(L.nms_ws_bytes);
+  L.keep = cv.take<int32_t>(max_sel > 0 ? max_sel : 1);
+  L.sel = cv.take<int32_t>(max_sel > 0 ? max_sel : 1);
+  L.bits_full = cv.take<uint32_t>((size_t)max_sel * oh * ((ow + 31) / 32));
+  L.rect = cv.take<int32_t>((size_t)max_sel * 4);
+  L.area_full = cv.take<int32_t>(max_sel > 0 ? max_sel : 1);
+  L.box_full = cv.take<int32_t>((size_t)max_sel * 4);
+  L.scratch = cv.take<int32_t>(upsample_scratch_bytes(max_sel > 0 ? max_sel : 1) / sizeof(int32_t));
+  L.ios = cv.take<float>(max_sel > 0 ? max_sel : 1);
+  L.out_slot = cv.take<int32_t>(num_out > 0 ? num_out : 1);
+  L.total = align_up(cv.off, 256);
+  return L;
+}
+
+size_t nttt_match_workspace_bytes(int n, int lr_h, int lr_w, int eh, int ew, int c, int n_cls, int ori_h, int ori_w,
+                                  int max_sel) {
+  if (n < 0 || lr_h <= 0 || lr_w <= 0 || eh <= 0 || ew <= 0 || c <= 0 || n_cls <= 0 || ori_h <= 0 || ori_w <= 0 ||
+      max_sel < 0)
+    return 0;
+  return carve(nullptr, n, lr_h, lr_w, eh, ew, c, n_cls, ori_h, ori_w, max_sel, max_sel).total;
+}
+
+int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
+  if (!ctx || !a) return NTTT_EINVAL;
+  if (a->n < 0 || a->lr_h <= 0 || a->lr_w <= 0 || a->eh <= 0 || a->ew <= 0 || a->c <= 0 || a->n_cls <= 0 ||
+      a->ori_h <= 0 || a->ori_w <= 0 || a->num_out_instance < 0 || a->max_sel < 0)
+    return NTTT_EINVAL;
+  if (!a->counts || !a->workspace) return NTTT_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = a->n, max_sel = a->max_sel, num_out = a->num_out_instance;
+  if (n == 0 || max_sel == 0) {
+    NTTT_CUDA(cudaMemsetAsync(a->counts, 0, 4 * sizeof(int32_t), s));
+    return NTTT_OK;
+  }
+  if (!a->logits || !a->pred_ious || !a->tar_feat || !a->proto || !a->out_masks || !a->out_boxes || !a->out_scores ||
+      !a->out_labels || !a->out_index)
+    return NTTT_EINVAL;
+  MatchLayout L = carve(a->workspace, n, a->lr_h, a->lr_w, a->eh, a->ew, a->c, a->n_cls, a->ori_h, a->ori_w, max_sel,
+                        num_out);
+  if (a->workspace_bytes < L.total) return NTTT_EWORKSPACE;
+  float* obj_feats = a->obj_feats ? a->obj_feats : L.obj_feats;
+  float* sim = a->sim ? a->sim : L.sim;
+  int err;
+  const AxisTable* px = ctx->axis(a->ew, a->lr_w, s, &err);
+  if (!px) return err;
+  const AxisTable* py = ctx->axis(a->eh, a->lr_h, s, &err);
+  if (!py) return err;
+  const AxisTable* ux = ctx->axis(a->lr_w, a->ori_w, s, &err);
+  if (!ux) return err;
+  const AxisTable* uy = ctx->axis(a->lr_h, a->ori_h, s, &err);
+  if (!uy) return err;
+  const int e = a->eh * a->ew;
+
+#define NTTT_STEP(call) do { err = (call); if (err) return err; } while (0)
+  // a6/a9/a15: one pass over the logits
+  NTTT_STEP(launch_lowres_pack(a->logits, n, a->lr_h, a->lr_w, 0.0f, 1.0f, L.bits_lr, L.area_lr, L.box_lr, L.stab,
+                               L.flags, s));
+  // a6/a7: projection + pooling contraction + normalisation
+  NTTT_STEP(launch_project_masks(*px, *py, L.bits_lr, n, a->lr_h, a->lr_w, a->eh, a->ew, L.proj, e, s));
+  NTTT_STEP(launch_sgemm(false, L.proj, e, a->tar_feat, a->c, L.sums, a->c, n, a->c, e, s));
+  NTTT_STEP(launch_normalize_rows(L.sums, L.area_lr, n, a->c, obj_feats, s));
+  // a7/a8: similarity + top-1
+  NTTT_STEP(launch_sgemm(true, obj_feats, a->c, a->proto, a->c, sim, a->n_cls, n, a->n_cls, a->c, s));
+  NTTT_STEP(launch_top1(sim, a->n_cls, n, a->n_cls, L.top_score, L.top_label, s));
+  // a10/a11
+  NTTT_STEP(launch_box_nms(L.box_lr, a->pred_ious, L.top_label, L.top_score, n, a->nms_thr, max_sel, L.keep,
+                           a->counts + 0, L.sel, a->counts + 1, L.nms_ws, L.nms_ws_bytes, s));
+  // a12/a9
+  NTTT_STEP(launch_upsample_pack(*ux, *uy, a->logits, L.bits_lr, L.box_lr, L.flags, a->lr_h, a->lr_w, L.sel,
+                                 a->counts + 1, max_sel, a->ori_h, a->ori_w, L.bits_full, L.rect, L.area_full,
+                                 L.box_full, L.scratch, s));
+  // a13
+  NTTT_STEP(launch_mask_ios(L.bits_full, L.rect, L.area_full, L.box_full, L.sel, a->counts + 1, max_sel, a->ori_h,
+                            a->ori_w, L.top_label, obj_feats, a->c, L.ios, nullptr, s));
+  // a14
+  NTTT_STEP(launch_decay_rank(L.top_score, L.top_label, L.ios, L.sel, a->counts + 1, max_sel, num_out, L.box_full,
+                              a->out_boxes, a->out_scores, a->out_labels, a->out_index, L.out_slot, a->counts + 2,
+                              nullptr, s));
+  NTTT_STEP(launch_unpack(L.bits_full, L.rect, L.out_slot, a->counts + 2, num_out, a->ori_h, a->ori_w, a->out_masks,
+                          s));
+#undef NTTT_STEP
+  return NTTT_OK;
+}
+
+}  // extern "C"

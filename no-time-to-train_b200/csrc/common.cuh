@@ -1,0 +1,93 @@
+// Shared device/host helpers for libnttt_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nttt_b200.h"
+
+namespace nttt {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// launch-site error capture: records the CUDA error text for nttt_last_cuda_error()
+int cuda_fail(cudaError_t e, const char* what);
+#define NTTT_CUDA(expr)                                        \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) return ::nttt::cuda_fail(_e, #expr); \
+  } while (0)
+#define NTTT_LAUNCH_CHECK() NTTT_CUDA(cudaGetLastError())
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_min(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+
+// streaming 128-bit load that does not pollute L1 (data is touched once)
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Antialias (Pillow-style) bilinear weight tables for one axis, shared by the full-res resize kernel
+// and the mask projection.  Built on the device with the exact fp32 recipe of aten's
+// _upsample_bilinear2d_aa.
+// ---------------------------------------------------------------------------------------------------
+struct AxisTable {
+  int in_size = 0, out_size = 0, taps = 0;
+  int32_t* xmin = nullptr;   // [out]
+  int32_t* xsize = nullptr;  // [out]
+  float* w = nullptr;        // [out, taps]
+  // transposed (scatter) view: for input coordinate e, the contiguous output range whose span holds e
+  int32_t* t_lo = nullptr;   // [in]
+  int32_t* t_len = nullptr;  // [in]
+  float* t_w = nullptr;      // [in, kMaxScatter]
+};
+constexpr int kMaxScatter = 24;
+
+int aa_max_taps(int in_size, int out_size);
+
+// internal launchers (defined in the .cu files, called by api.cu)
+int build_axis_table(AxisTable& t, int in_size, int out_size, cudaStream_t s);
+void free_axis_table(AxisTable& t);
+
+}  // namespace nttt
+
+struct nttt_ctx {
+  int device = 0;
+  int sm_count = 0;
+  static constexpr int kMaxTables = 16;
+  nttt::AxisTable tables[kMaxTables];
+  int n_tables = 0;
+  int32_t* scratch = nullptr;  // per-mask statistics scratch of the stand-alone resize entry
+  int scratch_cap = 0;
+  const nttt::AxisTable* axis(int in_size, int out_size, cudaStream_t s, int* err);
+};

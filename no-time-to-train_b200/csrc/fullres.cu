@@ -1,0 +1,240 @@
+// Full-resolution mask pass: antialiased bilinear resize of the selected low-res logits to the original
+// image size, strict > 0, bit-pack, area and box — without materialising the fp32 [K,H,W] tensor.
+//
+// Reference: Sam2MatchingBaseline_noAMG.py:657-665 (F.interpolate(..., antialias=True) > 0,
+// batched_mask_to_box).  Arithmetic: horizontal pass on each contributing input row, then vertical
+// pass, each `acc = s0*w0; acc = fma(s_j, w_j, acc)` in fp32 — the association of aten's
+// upsample_gen2d_aa kernel (ATen/native/cuda/UpSample.cuh interpolate_aa_single_dim).
+//
+// Two exact shortcuts keep the kernel off the instruction roofline:
+//   1. rect bound: an output sample whose footprint lies outside the low-res box sees only
+//      non-positive logits and non-negative weights, so it is not > 0.  Only the rect is computed/stored.
+//   2. uniform footprints: if every low-res bit under the footprint of a 32-pixel output word is 0 the
+//      word is 0; if every bit is 1 (and the mask's positives are finite, flags bit0) the word is all
+//      ones.  Only words whose footprint crosses the mask boundary evaluate the interpolation.
+#include "common.cuh"
+
+namespace nttt {
+
+constexpr int kUpThreads = 256;
+constexpr int kUpSplit = 4;  // CTAs per mask (rows interleaved)
+
+struct UpTables {
+  const int32_t* xmin; const int32_t* xsize; const float* wx; int tx;
+  const int32_t* ymin; const int32_t* ysize; const float* wy; int ty;
+  const int32_t* x_tlo; const int32_t* x_tlen;  // input col -> output range
+  const int32_t* y_tlo; const int32_t* y_tlen;  // input row -> output range
+};
+
+// acc = s0*w0; acc = fma(s_j, w_j, acc)
+__device__ __forceinline__ float aa_dot(const float* __restrict__ src, int stride, const float* __restrict__ w, int n) {
+  float acc = __fmul_rn(__ldg(src), __ldg(w));
+  for (int j = 1; j < n; ++j) acc = __fmaf_rn(__ldg(src + (size_t)j * stride), __ldg(w + j), acc);
+  return acc;
+}
+
+// scratch per mask (zero-initialised by the launcher): {area, maxx+1, maxy+1, BIG-minx, BIG-miny, done}
+constexpr int kScratchInts = 8;
+constexpr int kBig = 1 << 30;
+
+__global__ void __launch_bounds__(kUpThreads)
+upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restrict__ bits_lr,
+                     const int32_t* __restrict__ box_lr, const int32_t* __restrict__ flags_lr, int ih, int iw,
+                     const int32_t* __restrict__ sel, const int32_t* __restrict__ n_sel, int max_sel, int oh, int ow,
+                     UpTables t, uint32_t* __restrict__ bits_full, int32_t* __restrict__ rect,
+                     int32_t* __restrict__ area_full, int32_t* __restrict__ box_full, int32_t* __restrict__ scratch) {
+  extern __shared__ uint32_t s_lr[];  // ih * iw/32 packed low-res bits of this mask
+  __shared__ int s_red[5];
+  const int k = blockIdx.y;
+  const int nsel = min(*n_sel, max_sel);
+  if (k >= nsel) return;
+  const int src_idx = sel[k];
+  const int lr_wpr = iw >> 5;
+  const int ow_words = (ow + 31) >> 5;
+  const int lane = lane_id(), warp = warp_id();
+  constexpr int kWarps = kUpThreads / 32;
+
+  const uint32_t* lr = bits_lr + (size_t)src_idx * ih * lr_wpr;
+  for (int i = threadIdx.x; i < ih * lr_wpr; i += kUpThreads) s_lr[i] = lr[i];
+  if (threadIdx.x < 5) s_red[threadIdx.x] = 0;
+
+  const int4 b = reinterpret_cast<const int4*>(box_lr)[src_idx];
+  // empty low-res mask <=> box all zero AND bit (0,0) clear
+  const bool lr_empty = (b.x | b.y | b.z | b.w) == 0 && (lr[0] & 1u) == 0;
+  int r0 = 0, r1 = 0, w0 = 0, w1 = 0;
+  if (!lr_empty) {
+    r0 = t.y_tlo[b.y];
+    r1 = t.y_tlo[b.w] + t.y_tlen[b.w];
+    const int c0 = t.x_tlo[b.x];
+    const int c1 = t.x_tlo[b.z] + t.x_tlen[b.z];
+    w0 = c0 >> 5;
+    w1 = (c1 + 31) >> 5;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<int4*>(rect)[k] = make_int4(r0, r1, w0, w1);
+  const bool safe = (flags_lr[src_idx] & 1) != 0;
+  const float* src = logits + (size_t)src_idx * ih * iw;
+  uint32_t* dst = bits_full + (size_t)k * oh * ow_words;
+  __syncthreads();
+
+  int area = 0, minx = kBig, maxx = -1, miny = kBig, maxy = -1;
+  for (int y = r0 + blockIdx.x * kWarps + warp; y < r1; y += kUpSplit * kWarps) {
+    const int ry0 = t.ymin[y], rys = t.ysize[y];
+    const float* wy = t.wy + (size_t)y * t.ty;
+    for (int wbase = w0; wbase < w1; wbase += 32) {
+      const int wi = wbase + lane;
+      const bool active = wi < w1;
+      uint32_t word = 0;
+      bool mixed = false;
+      uint32_t valid = 0;
+      if (active) {
+        const int x0 = wi << 5;
+        const int x1 = min(x0 + 31, ow - 1);
+        valid = (x1 - x0 == 31) ? 0xffffffffu : ((1u << (x1 - x0 + 1)) - 1u);
+        const int c0 = t.xmin[x0];
+        const int c1 = t.xmin[x1] + t.xsize[x1];  // exclusive
+        bool all0 = true, all1 = true;
+        for (int r = 0; r < rys; ++r) {
+          const uint32_t* row = s_lr + (ry0 + r) * lr_wpr;
+          for (int cw = c0 >> 5; cw <= (c1 - 1) >> 5; ++cw) {
+            const int lo = max(c0 - (cw << 5), 0), hi = min(c1 - (cw << 5), 32);
+            const uint32_t m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+            const uint32_t v = row[cw] & m;
+            all0 = all0 && (v == 0);
+            all1 = all1 && (v == m);
+          }
+        }
+        if (all0) word = 0;
+        else if (all1 && safe) word = valid;
+        else mixed = true;
+      }
+      uint32_t todo = __ballot_sync(kFull, mixed);
+      while (todo) {
+        const int src_lane = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int x = ((wbase + src_lane) << 5) + lane;
+        bool bit = false;
+        if (x < ow) {
+          const int cx = t.xmin[x], cs = t.xsize[x];
+          const float* wx = t.wx + (size_t)x * t.tx;
+          const float* p = src + (size_t)ry0 * iw + cx;
+          float acc = __fmul_rn(aa_dot(p, 1, wx, cs), __ldg(wy));
+          for (int r = 1; r < rys; ++r) acc = __fmaf_rn(aa_dot(p + (size_t)r * iw, 1, wx, cs), __ldg(wy + r), acc);
+          bit = acc > 0.0f;
+        }
+        const uint32_t res = __ballot_sync(kFull, bit);
+        if (lane == src_lane) word = res;
+      }
+      if (active) {
+        dst[(size_t)y * ow_words + wi] = word;
+        if (word) {
+          area += __popc(word);
+          minx = min(minx, (wi << 5) + __ffs(word) - 1);
+          maxx = max(maxx, (wi << 5) + 31 - __clz(word));
+          miny = min(miny, y);
+          maxy = max(maxy, y);
+        }
+      }
+    }
+  }
+  area = warp_sum(area);
+  minx = warp_min(minx); miny = warp_min(miny); maxx = warp_max(maxx); maxy = warp_max(maxy);
+  if (lane == 0) {
+    atomicAdd(&s_red[0], area);
+    atomicMax(&s_red[1], maxx + 1);
+    atomicMax(&s_red[2], maxy + 1);
+    atomicMax(&s_red[3], kBig - minx);
+    atomicMax(&s_red[4], kBig - miny);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t* sc = scratch + (size_t)k * kScratchInts;
+    atomicAdd(&sc[0], s_red[0]);
+    atomicMax(&sc[1], s_red[1]);
+    atomicMax(&sc[2], s_red[2]);
+    atomicMax(&sc[3], s_red[3]);
+    atomicMax(&sc[4], s_red[4]);
+    __threadfence();
+    const int prev = atomicAdd(&sc[5], 1);
+    if (prev == kUpSplit - 1) {  // last CTA of this mask publishes the final statistics
+      __threadfence();
+      const int a = atomicAdd(&sc[0], 0);
+      const int mx1 = atomicMax(&sc[1], 0), my1 = atomicMax(&sc[2], 0);
+      const int bx = atomicMax(&sc[3], 0), by = atomicMax(&sc[4], 0);
+      area_full[k] = a;
+      int4 o = make_int4(0, 0, 0, 0);
+      if (a > 0) o = make_int4(kBig - bx, kBig - by, mx1 - 1, my1 - 1);
+      reinterpret_cast<int4*>(box_full)[k] = o;
+    }
+  }
+}
+
+int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* logits, const uint32_t* bits_lr,
+                         const int32_t* box_lr, const int32_t* flags_lr, int ih, int iw, const int32_t* sel,
+                         const int32_t* n_sel, int max_sel, int oh, int ow, uint32_t* bits_full, int32_t* rect,
+                         int32_t* area_full, int32_t* box_full, int32_t* scratch, cudaStream_t s) {
+  if (max_sel <= 0) return NTTT_OK;
+  if (iw % 32 != 0) return NTTT_EUNSUPPORTED;
+  const size_t smem = (size_t)ih * (iw / 32) * 4;
+  if (smem > 160 * 1024) return NTTT_EUNSUPPORTED;
+  if (smem > 48 * 1024)
+    NTTT_CUDA(cudaFuncSetAttribute(upsample_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NTTT_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int32_t) * kScratchInts * (size_t)max_sel, s));
+  UpTables t{tx.xmin, tx.xsize, tx.w, tx.taps, ty.xmin, ty.xsize, ty.w, ty.taps, tx.t_lo, tx.t_len, ty.t_lo, ty.t_len};
+  dim3 grid(kUpSplit, max_sel);
+  upsample_pack_kernel<<<grid, kUpThreads, smem, s>>>(logits, bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel,
+                                                      oh, ow, t, bits_full, rect, area_full, box_full, scratch);
+  NTTT_LAUNCH_CHECK();
+  return NTTT_OK;
+}
+size_t upsample_scratch_bytes(int max_sel) { return sizeof(int32_t) * kScratchInts * (size_t)max_sel; }
+
+// ---------------------------------------------------------------------------------------------------
+// unpack: packed words -> torch.bool bytes.  `index` (nullable) maps output slot j -> packed mask k.
+// HBM-bound: oh*ow bytes written per mask.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+unpack_masks_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restrict__ rect,
+                    const int32_t* __restrict__ index, const int32_t* __restrict__ count, int max_count, int oh, int ow,
+                    uint8_t* __restrict__ out) {
+  const int j = blockIdx.y;
+  if (j >= min(*count, max_count)) return;
+  const int k = index ? index[j] : j;
+  const int ow_words = (ow + 31) >> 5;
+  const int4 rc = reinterpret_cast<const int4*>(rect)[k];
+  const uint32_t* src = bits_full + (size_t)k * oh * ow_words;
+  uint8_t* dst = out + (size_t)j * oh * ow;
+  const int segs = (ow + 15) >> 4;  // 16-pixel segments per row
+  const long total = (long)oh * segs;
+  const bool vec = (ow & 15) == 0;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const int y = (int)(g / segs), sx = (int)(g - (long)y * segs);
+    const int x = sx << 4, wi = x >> 5;
+    uint32_t half = 0;
+    if (y >= rc.x && y < rc.y && wi >= rc.z && wi < rc.w) half = (src[(size_t)y * ow_words + wi] >> (x & 31)) & 0xffffu;
+    if (vec) {
+      uint32_t o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t nb = (half >> (4 * q)) & 0xfu;
+        o[q] = (nb & 1u) | ((nb & 2u) << 7) | ((nb & 4u) << 14) | ((nb & 8u) << 21);
+      }
+      *reinterpret_cast<uint4*>(dst + (size_t)y * ow + x) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+      for (int q = 0; q < 16 && x + q < ow; ++q) dst[(size_t)y * ow + x + q] = (half >> q) & 1u;
+    }
+  }
+}
+
+int launch_unpack(const uint32_t* bits_full, const int32_t* rect, const int32_t* index, const int32_t* count,
+                  int max_count, int oh, int ow, uint8_t* out, cudaStream_t s) {
+  if (max_count <= 0) return NTTT_OK;
+  const long total = (long)oh * ((ow + 15) >> 4);
+  const long want = (total + 255) / 256;
+  const int bx = (int)(want < 1024 ? want : 1024);
+  dim3 grid(bx, max_count);
+  unpack_masks_kernel<<<grid, 256, 0, s>>>(bits_full, rect, index, count, max_count, oh, ow, out);
+  NTTT_LAUNCH_CHECK();
+  return NTTT_OK;
+}
+
+}  // namespace nttt

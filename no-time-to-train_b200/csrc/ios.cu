@@ -1,0 +1,178 @@
+// Intersection-over-self score decay on bit-packed full-resolution masks, final top-k and output gather.
+//
+// Reference: obj_sim = clamp(F F^T, 0) (Sam2MatchingBaseline_noAMG.py:668-669), compute_semantic_ios
+// (matching_baseline_utils.py:831-867), scores * pow(1-ios, 0.5) and argsort/top-k (:671-683).
+//
+// The reference casts [K,H*W] bool to fp32 and runs one SGEMM per class; the counts it produces are exact
+// integers, so AND+popcount over the packed words gives the same numbers.  Only same-label pairs whose
+// full-res boxes overlap can intersect, and only inside the intersection of their rects.
+#include "common.cuh"
+
+namespace nttt {
+
+constexpr int kIosThreads = 256;
+
+// one CTA per selected mask i; warps stride over candidate partners j.
+__global__ void __launch_bounds__(kIosThreads)
+mask_ios_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restrict__ rect,
+                const int32_t* __restrict__ area_full, const int32_t* __restrict__ box_full,
+                const int32_t* __restrict__ sel, const int32_t* __restrict__ n_sel, int max_sel, int oh, int ow,
+                const int32_t* __restrict__ labels, const float* __restrict__ obj_feats, int c,
+                float* __restrict__ ios, int32_t* __restrict__ inter_out) {
+  __shared__ float s_best[kIosThreads / 32];
+  const int i = blockIdx.x;
+  const int nsel = min(*n_sel, max_sel);
+  if (i >= nsel) return;
+  const int lane = lane_id(), warp = warp_id();
+  constexpr int kWarps = kIosThreads / 32;
+  const int ow_words = (ow + 31) >> 5;
+  const int src_i = sel[i];
+  const int lab_i = labels[src_i];
+  const int area_i = area_full[i];
+  const int4 bi = reinterpret_cast<const int4*>(box_full)[i];
+  const int4 ri = reinterpret_cast<const int4*>(rect)[i];
+  const uint32_t* mi = bits_full + (size_t)i * oh * ow_words;
+  const float* fi = obj_feats + (size_t)src_i * c;
+  const float area_f = (float)area_i;
+
+  float best = 0.0f;  // the zeroed diagonal takes part in the row max (area_i > 0 case)
+  for (int j = warp; j < nsel; j += kWarps) {
+    if (j == i) continue;
+    const int src_j = sel[j];
+    if (labels[src_j] != lab_i) continue;
+    int inter = 0;
+    if (area_i > 0 && area_full[j] > 0) {
+      const int4 bj = reinterpret_cast<const int4*>(box_full)[j];
+      // inclusive boxes -> overlap window in pixels
+      const int x0 = max(bi.x, bj.x), x1 = min(bi.z, bj.z), y0 = max(bi.y, bj.y), y1 = min(bi.w, bj.w);
+      if (x0 <= x1 && y0 <= y1) {
+        const int4 rj = reinterpret_cast<const int4*>(rect)[j];
+        const int wlo = max(max(ri.z, rj.z), x0 >> 5), whi = min(min(ri.w, rj.w), (x1 >> 5) + 1);
+        const int ylo = max(max(ri.x, rj.x), y0), yhi = min(min(ri.y, rj.y), y1 + 1);
+        const uint32_t* mj = bits_full + (size_t)j * oh * ow_words;
+        const int nw = whi - wlo;
+        if (nw > 0 && yhi > ylo) {
+          const int total = (yhi - ylo) * nw;
+          for (int t = lane; t < total; t += 32) {
+            const int y = ylo + t / nw, w = wlo + t % nw;
+            const size_t o = (size_t)y * ow_words + w;
+            inter += __popc(mi[o] & mj[o]);
+          }
+        }
+      }
+    }
+    inter = warp_sum(inter);
+    if (inter_out && lane == 0) inter_out[(size_t)i * max_sel + j] = inter;
+    if (inter > 0) {
+      const float* fj = obj_feats + (size_t)src_j * c;
+      float dot = 0.0f;
+      for (int q = lane; q < c; q += 32) dot = fmaf(fi[q], fj[q], dot);
+      dot = warp_sum(dot);
+      const float s = fmaxf(dot, 0.0f);
+      // ((inter * s) / area_i) * s  — the reference's association
+      const float v = __fmul_rn(__fdiv_rn(__fmul_rn((float)inter, s), area_f), s);
+      best = fmaxf(best, v);
+    }
+  }
+  if (lane == 0) s_best[warp] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = s_best[0];
+    for (int w = 1; w < kWarps; ++w) b = fmaxf(b, s_best[w]);
+    // empty full-res mask: 0/0 on the diagonal -> NaN, and torch.max propagates it
+    ios[i] = area_i == 0 ? __int_as_float(0x7fc00000) : b;
+  }
+}
+
+int launch_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_t* area_full, const int32_t* box_full,
+                    const int32_t* sel, const int32_t* n_sel, int max_sel, int oh, int ow, const int32_t* labels,
+                    const float* obj_feats, int c, float* ios, int32_t* inter_out, cudaStream_t s) {
+  if (max_sel <= 0) return NTTT_OK;
+  if (inter_out) NTTT_CUDA(cudaMemsetAsync(inter_out, 0, sizeof(int32_t) * (size_t)max_sel * max_sel, s));
+  mask_ios_kernel<<<max_sel, kIosThreads, 0, s>>>(bits_full, rect, area_full, box_full, sel, n_sel, max_sel, oh, ow,
+                                                  labels, obj_feats, c, ios, inter_out);
+  NTTT_LAUNCH_CHECK();
+  return NTTT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// decay + final ranking: decayed = score * sqrt(1 - ios); order = argsort(desc), NaN first, stable.
+// Single CTA bitonic sort on (key, position) over <= 1024 entries (max_sel <= 8*num_out_instance).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t desc_key_nanfirst(float f) {
+  if (f != f) return 0u;  // every NaN first
+  uint32_t u = __float_as_uint(f);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  u = ~u;
+  return u == 0u ? 1u : u;  // keep 0 reserved for NaN (only +NaN patterns could map to 0 anyway)
+}
+
+__global__ void __launch_bounds__(1024)
+decay_rank_kernel(const float* __restrict__ top_score, const int32_t* __restrict__ labels,
+                  const float* __restrict__ ios, const int32_t* __restrict__ sel, const int32_t* __restrict__ n_sel,
+                  int max_sel, int n_pad, int num_out, const int32_t* __restrict__ box_full,
+                  int64_t* __restrict__ out_boxes, float* __restrict__ out_scores, int64_t* __restrict__ out_labels,
+                  int32_t* __restrict__ out_index, int32_t* __restrict__ out_slot, int32_t* __restrict__ n_out,
+                  float* __restrict__ decayed_out) {
+  extern __shared__ unsigned long long s_keys[];
+  float* s_val = reinterpret_cast<float*>(s_keys + n_pad);
+  const int nsel = min(*n_sel, max_sel);
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (i < nsel) {
+      const float d = __fmul_rn(top_score[sel[i]], sqrtf(__fsub_rn(1.0f, ios[i])));
+      s_val[i] = d;
+      if (decayed_out) decayed_out[i] = d;
+      key = ((unsigned long long)desc_key_nanfirst(d) << 32) | (uint32_t)i;
+    }
+    s_keys[i] = key;
+  }
+  __syncthreads();
+  for (int k = 2; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = s_keys[i], b = s_keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { s_keys[i] = b; s_keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const int nout = min(num_out, nsel);
+  for (int r = threadIdx.x; r < nout; r += blockDim.x) {
+    const int k = (int)(s_keys[r] & 0xffffffffu);  // slot in the selected list
+    const int src = sel[k];
+    out_slot[r] = k;
+    out_index[r] = src;
+    out_scores[r] = s_val[k];
+    out_labels[r] = (int64_t)labels[src];
+    const int4 b = reinterpret_cast<const int4*>(box_full)[k];
+    out_boxes[4 * r + 0] = b.x; out_boxes[4 * r + 1] = b.y; out_boxes[4 * r + 2] = b.z; out_boxes[4 * r + 3] = b.w;
+  }
+  if (threadIdx.x == 0) *n_out = nout;
+}
+
+int launch_decay_rank(const float* top_score, const int32_t* labels, const float* ios, const int32_t* sel,
+                      const int32_t* n_sel, int max_sel, int num_out, const int32_t* box_full, int64_t* out_boxes,
+                      float* out_scores, int64_t* out_labels, int32_t* out_index, int32_t* out_slot, int32_t* n_out,
+                      float* decayed_out, cudaStream_t s) {
+  if (max_sel <= 0 || num_out <= 0) {
+    NTTT_CUDA(cudaMemsetAsync(n_out, 0, sizeof(int32_t), s));
+    return NTTT_OK;
+  }
+  int n_pad = 1;
+  while (n_pad < max_sel) n_pad <<= 1;
+  const size_t smem = (sizeof(unsigned long long) + sizeof(float)) * (size_t)n_pad;
+  if (smem > 200 * 1024) return NTTT_EUNSUPPORTED;
+  if (smem > 48 * 1024)
+    NTTT_CUDA(cudaFuncSetAttribute(decay_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  decay_rank_kernel<<<1, 1024, smem, s>>>(top_score, labels, ios, sel, n_sel, max_sel, n_pad, num_out, box_full,
+                                          out_boxes, out_scores, out_labels, out_index, out_slot, n_out, decayed_out);
+  NTTT_LAUNCH_CHECK();
+  return NTTT_OK;
+}
+
+}  // namespace nttt

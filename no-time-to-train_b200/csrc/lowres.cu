@@ -1,0 +1,266 @@
+// Low-resolution mask pass: threshold + bit-pack + area + box + stability counts (one HBM pass over the
+// SAM-2 logits), the antialias weight tables, and the projection of packed masks onto the encoder grid.
+//
+// Reference: Sam2MatchingBaseline_noAMG.py:548-549 (lr_masks > 0), :551-558 (feature upsample),
+// sam2/utils/amg.py:158-178 (stability), :305-348 (boxes).
+#include "common.cuh"
+
+namespace nttt {
+
+// ---------------------------------------------------------------------------------------------------
+// K1: lowres_pack — HBM-bound streaming kernel, one CTA per mask.
+//   algorithmic bytes per mask: 4*P read (+ P/8 written)
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPackThreads = 512;
+constexpr int kPackUnroll = 4;
+
+__global__ void __launch_bounds__(kPackThreads)
+lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mask */, int words_per_row,
+                   float thr_hi, float thr_lo, uint32_t* __restrict__ bits, int32_t* __restrict__ area,
+                   int32_t* __restrict__ box, int32_t* __restrict__ stab, int32_t* __restrict__ flags) {
+  extern __shared__ uint32_t s_bits[];  // p4/8 words
+  __shared__ int s_red[8];              // area, hi, lo, unsafe, minx, miny, maxx, maxy
+  const int n = blockIdx.x;
+  const float4* src = logits + (size_t)n * p4;
+  const int lane = lane_id();
+  if (threadIdx.x < 8) s_red[threadIdx.x] = (threadIdx.x == 4 || threadIdx.x == 5) ? 0x7fffffff : (threadIdx.x >= 6 ? -1 : 0);
+
+  int a = 0, hi = 0, lo = 0, unsafe = 0;
+  int minx = 0x7fffffff, miny = 0x7fffffff, maxx = -1, maxy = -1;
+  const float kTiny = 7.888609052210118e-31f;   // 2^-100
+  const float kHuge = 1.2676506002282294e30f;   // 2^100
+
+  for (int base = 0; base < p4; base += kPackThreads * kPackUnroll) {
+    float4 v[kPackUnroll];
+#pragma unroll
+    for (int u = 0; u < kPackUnroll; ++u) {
+      const int q = base + u * kPackThreads + threadIdx.x;
+      v[u] = q < p4 ? ld_stream(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kPackUnroll; ++u) {
+      const int q = base + u * kPackThreads + threadIdx.x;
+      const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      uint32_t nib = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool pos = e[k] > 0.0f;
+        nib |= (uint32_t)pos << k;
+        hi += e[k] > thr_hi;
+        lo += e[k] > thr_lo;
+        unsafe |= pos && !(e[k] > kTiny && e[k] < kHuge);
+      }
+      uint32_t word = nib << (4 * (lane & 7));
+      word |= __shfl_xor_sync(kFull, word, 1);
+      word |= __shfl_xor_sync(kFull, word, 2);
+      word |= __shfl_xor_sync(kFull, word, 4);
+      if ((lane & 7) == 0 && q < p4) {
+        const int wi = q >> 3;
+        s_bits[wi] = word;
+        if (word) {
+          a += __popc(word);
+          const int row = wi / words_per_row;
+          const int x0 = (wi - row * words_per_row) * 32;
+          minx = min(minx, x0 + __ffs(word) - 1);
+          maxx = max(maxx, x0 + 31 - __clz(word));
+          miny = min(miny, row);
+          maxy = max(maxy, row);
+        }
+      }
+    }
+  }
+  a = warp_sum(a); hi = warp_sum(hi); lo = warp_sum(lo); unsafe = warp_max(unsafe);
+  minx = warp_min(minx); miny = warp_min(miny); maxx = warp_max(maxx); maxy = warp_max(maxy);
+  __syncthreads();  // s_red initialised, s_bits complete
+  if (lane == 0) {
+    atomicAdd(&s_red[0], a); atomicAdd(&s_red[1], hi); atomicAdd(&s_red[2], lo); atomicMax(&s_red[3], unsafe);
+    atomicMin(&s_red[4], minx); atomicMin(&s_red[5], miny); atomicMax(&s_red[6], maxx); atomicMax(&s_red[7], maxy);
+  }
+  // packed words out, coalesced 128-bit stores
+  const int n_words = p4 >> 3;
+  uint4* dst = reinterpret_cast<uint4*>(bits + (size_t)n * n_words);
+  const uint4* s4 = reinterpret_cast<const uint4*>(s_bits);
+  for (int i = threadIdx.x; i < (n_words >> 2); i += kPackThreads) dst[i] = s4[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    area[n] = s_red[0];
+    stab[2 * n] = s_red[1];
+    stab[2 * n + 1] = s_red[2];
+    flags[n] = s_red[3] ? 0 : 1;
+    const bool empty = s_red[6] < s_red[4] || s_red[7] < s_red[5];
+    int4 b = empty ? make_int4(0, 0, 0, 0) : make_int4(s_red[4], s_red[5], s_red[6], s_red[7]);
+    reinterpret_cast<int4*>(box)[n] = b;
+  }
+}
+
+int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits,
+                       int32_t* area, int32_t* box, int32_t* stab, int32_t* flags, cudaStream_t s) {
+  const long p = (long)h * w;
+  if (n <= 0) return NTTT_OK;
+  if (w % 32 != 0 || p % 128 != 0 || p / 32 * 4 > 160 * 1024) return NTTT_EUNSUPPORTED;
+  const size_t smem = (size_t)(p / 32) * sizeof(uint32_t);
+  if (smem > 48 * 1024)
+    NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  lowres_pack_kernel<<<n, kPackThreads, smem, s>>>(reinterpret_cast<const float4*>(logits), (int)(p / 4), w / 32,
+                                                   thr + off, thr - off, bits, area, box, stab, flags);
+  NTTT_LAUNCH_CHECK();
+  return NTTT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Antialias weight tables.  Exact fp32 recipe (every operation individually rounded, no contraction):
+//   scale = in/out; support = scale>=1 ? scale : 1; invscale = scale>=1 ? float(1.0/double(scale)) : 1
+//   center = scale*(i+0.5); xmin = max(int(center-support+0.5),0); xsize = min(int(center+support+0.5),in)-xmin
+//   w_j = tri((j + (xmin-center) + 0.5)*invscale); w_j /= sum_j w_j (sequential sum)
+// ---------------------------------------------------------------------------------------------------
+int aa_max_taps(int in_size, int out_size) {
+  const float scale = (float)in_size / (float)out_size;
+  const float support = scale >= 1.0f ? scale : 1.0f;
+  return (int)ceilf(support) * 2 + 1;
+}
+
+__global__ void aa_table_kernel(int in_size, int out_size, int taps, int32_t* xmin, int32_t* xsize, float* w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= out_size) return;
+  const float scale = __fdiv_rn((float)in_size, (float)out_size);
+  const float support = scale >= 1.0f ? scale : 1.0f;
+  const float invscale = scale >= 1.0f ? (float)(1.0 / (double)scale) : 1.0f;
+  const float center = __fmul_rn(scale, __fadd_rn((float)i, 0.5f));
+  int lo = (int)__fadd_rn(__fsub_rn(center, support), 0.5f);
+  lo = max(lo, 0);
+  int hi = (int)__fadd_rn(__fadd_rn(center, support), 0.5f);
+  hi = min(hi, in_size);
+  const int size = hi - lo;
+  const float lo_m_center = __fsub_rn((float)lo, center);
+  float total = 0.0f;
+  float* wi = w + (size_t)i * taps;
+  for (int j = 0; j < size; ++j) {
+    float x = __fmul_rn(__fadd_rn(__fadd_rn((float)j, lo_m_center), 0.5f), invscale);
+    x = fabsf(x);
+    const float v = x < 1.0f ? __fsub_rn(1.0f, x) : 0.0f;
+    wi[j] = v;
+    total = __fadd_rn(total, v);
+  }
+  if (total != 0.0f)
+    for (int j = 0; j < size; ++j) wi[j] = __fdiv_rn(wi[j], total);
+  for (int j = size; j < taps; ++j) wi[j] = 0.0f;
+  xmin[i] = lo;
+  xsize[i] = size;
+}
+
+// transposed view: for input coordinate e, outputs [t_lo, t_lo+t_len) are those whose span contains e
+__global__ void aa_transpose_kernel(int in_size, int out_size, int taps, const int32_t* xmin, const int32_t* xsize,
+                                    const float* w, int32_t* t_lo, int32_t* t_len, float* t_w) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= in_size) return;
+  int lo = -1, hi = -1;
+  for (int x = 0; x < out_size; ++x) {
+    if (e >= xmin[x] && e < xmin[x] + xsize[x]) {
+      if (lo < 0) lo = x;
+      hi = x;
+    }
+  }
+  const int len = lo < 0 ? 0 : hi - lo + 1;  // true length; t_w only holds the first kMaxScatter weights
+  t_lo[e] = max(lo, 0);
+  t_len[e] = len;
+  for (int t = 0; t < kMaxScatter; ++t) {
+    const int x = lo + t;
+    float v = 0.0f;
+    if (lo >= 0 && x <= hi && e >= xmin[x] && e < xmin[x] + xsize[x]) v = w[(size_t)x * taps + (e - xmin[x])];
+    t_w[(size_t)e * kMaxScatter + t] = v;
+  }
+}
+
+int build_axis_table(AxisTable& t, int in_size, int out_size, cudaStream_t s) {
+  t.in_size = in_size;
+  t.out_size = out_size;
+  t.taps = aa_max_taps(in_size, out_size);
+  NTTT_CUDA(cudaMalloc(&t.xmin, sizeof(int32_t) * out_size));
+  NTTT_CUDA(cudaMalloc(&t.xsize, sizeof(int32_t) * out_size));
+  NTTT_CUDA(cudaMalloc(&t.w, sizeof(float) * (size_t)out_size * t.taps));
+  NTTT_CUDA(cudaMalloc(&t.t_lo, sizeof(int32_t) * in_size));
+  NTTT_CUDA(cudaMalloc(&t.t_len, sizeof(int32_t) * in_size));
+  NTTT_CUDA(cudaMalloc(&t.t_w, sizeof(float) * (size_t)in_size * kMaxScatter));
+  aa_table_kernel<<<ceil_div(out_size, 128), 128, 0, s>>>(in_size, out_size, t.taps, t.xmin, t.xsize, t.w);
+  NTTT_LAUNCH_CHECK();
+  aa_transpose_kernel<<<ceil_div(in_size, 128), 128, 0, s>>>(in_size, out_size, t.taps, t.xmin, t.xsize, t.w, t.t_lo,
+                                                            t.t_len, t.t_w);
+  NTTT_LAUNCH_CHECK();
+  return NTTT_OK;
+}
+
+void free_axis_table(AxisTable& t) {
+  cudaFree(t.xmin); cudaFree(t.xsize); cudaFree(t.w); cudaFree(t.t_lo); cudaFree(t.t_len); cudaFree(t.t_w);
+  t = AxisTable{};
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: project_masks — proj[n, ey, ex] = sum_{y,x} Uy[y,ey] * bit(y,x) * Ux[x,ex]
+// (Uy, Ux = antialias upsample matrices encoder grid -> mask grid).  With it
+//   masks @ upsample(feat)  ==  proj @ feat           (linearity + separability of the resize)
+// so the 2*N*P*C contraction of the reference collapses to 2*N*E*C.  Reads only the packed bits
+// (P/8 bytes per mask, L2 resident); compute-bound on the set-bit walk.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kProjThreads = 256;
+
+__global__ void __launch_bounds__(kProjThreads)
+project_masks_kernel(const uint32_t* __restrict__ bits, int h, int words_per_row, int eh, int ew,
+                     const int32_t* __restrict__ x_lo, const int32_t* __restrict__ x_len,
+                     const float* __restrict__ x_w, const int32_t* __restrict__ y_lo,
+                     const int32_t* __restrict__ y_len, const float* __restrict__ y_w,
+                     float* __restrict__ proj, int proj_stride) {
+  extern __shared__ uint32_t smem[];
+  uint32_t* s_bits = smem;                                            // h * words_per_row
+  float* s_row = reinterpret_cast<float*>(smem + h * words_per_row);  // h * ew
+  const int n = blockIdx.x;
+  const int n_words = h * words_per_row;
+  const uint32_t* src = bits + (size_t)n * n_words;
+  for (int i = threadIdx.x; i < n_words; i += kProjThreads) s_bits[i] = src[i];
+  __syncthreads();
+  // row pass: s_row[y, ex] = sum_x bit(y,x) * Ux[x,ex]
+  for (int item = threadIdx.x; item < h * ew; item += kProjThreads) {
+    const int y = item / ew, ex = item - y * ew;
+    const int lo = x_lo[ex], len = x_len[ex];
+    const uint32_t* row = s_bits + y * words_per_row;
+    const int w0 = lo >> 5, sh = lo & 31;
+    const uint32_t a = row[w0];
+    const uint32_t b = (w0 + 1 < words_per_row) ? row[w0 + 1] : 0u;
+    uint32_t f = __funnelshift_r(a, b, sh);
+    f &= (len >= 32) ? 0xffffffffu : ((1u << len) - 1u);
+    float acc = 0.0f;
+    const float* wv = x_w + ex * kMaxScatter;
+    while (f) {
+      const int t = __ffs(f) - 1;
+      acc += wv[t];
+      f &= f - 1;
+    }
+    s_row[item] = acc;
+  }
+  __syncthreads();
+  // column pass: proj[ey, ex] = sum_y Uy[y,ey] * s_row[y, ex]
+  float* out = proj + (size_t)n * proj_stride;
+  for (int item = threadIdx.x; item < eh * ew; item += kProjThreads) {
+    const int ey = item / ew, ex = item - ey * ew;
+    const int lo = y_lo[ey], len = y_len[ey];
+    const float* wv = y_w + ey * kMaxScatter;
+    float acc = 0.0f;
+    for (int t = 0; t < len; ++t) acc = fmaf(wv[t], s_row[(lo + t) * ew + ex], acc);
+    out[item] = acc;
+  }
+}
+
+int launch_project_masks(const AxisTable& tx, const AxisTable& ty, const uint32_t* bits, int n, int h, int w, int eh,
+                         int ew, float* proj, int proj_stride, cudaStream_t s) {
+  if (n <= 0) return NTTT_OK;
+  if (w % 32 != 0) return NTTT_EUNSUPPORTED;
+  const size_t smem = (size_t)h * (w / 32) * 4 + (size_t)h * ew * 4;
+  if (smem > 200 * 1024) return NTTT_EUNSUPPORTED;
+  if (smem > 48 * 1024)
+    NTTT_CUDA(cudaFuncSetAttribute(project_masks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  project_masks_kernel<<<n, kProjThreads, smem, s>>>(bits, h, w / 32, eh, ew, tx.t_lo, tx.t_len, tx.t_w, ty.t_lo,
+                                                     ty.t_len, ty.t_w, proj, proj_stride);
+  NTTT_LAUNCH_CHECK();
+  return NTTT_OK;
+}
+
+}  // namespace nttt

@@ -1,0 +1,178 @@
+// Class-aware box NMS on the low-res mask boxes + positive-score compaction.
+//
+// Reference: torchvision.ops.batched_nms(lr_bboxes.float(), pred_ious, labels, nms_thr)[:out_num]
+// (Sam2MatchingBaseline_noAMG.py:621-629) and the `scores_out > 0` filter (:631-641).
+// torchvision (third-party, pinned 0.19.1 by pyproject.toml:57) adds label*(max_coord+1) to every box and
+// runs plain NMS; with integer-valued fp32 coordinates that is exactly "same label AND IoU > thr", which
+// is what is evaluated here: inter/(areaA+areaB-inter) in fp32, areas (x2-x1)*(y2-y1), strict >.
+#include "common.cuh"
+
+namespace nttt {
+
+// float -> uint key whose ascending order is the float's DESCENDING order (positive NaN first, like torch)
+__device__ __forceinline__ uint32_t desc_key(float f) {
+  uint32_t u = __float_as_uint(f);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending-orderable
+  return ~u;
+}
+
+// single-CTA bitonic sort of (score desc, index asc); n_pad = next pow2 >= n
+__global__ void __launch_bounds__(1024)
+nms_sort_kernel(const float* __restrict__ scores, int n, int n_pad, int32_t* __restrict__ order) {
+  extern __shared__ unsigned long long s_keys[];
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x)
+    s_keys[i] = i < n ? (((unsigned long long)desc_key(scores[i]) << 32) | (uint32_t)i) : ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = s_keys[i], b = s_keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { s_keys[i] = b; s_keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) order[i] = (int32_t)(s_keys[i] & 0xffffffffu);
+}
+
+// suppression bit matrix in sorted order: bit j of row i set iff j > i, same label, IoU(i,j) > thr
+__global__ void __launch_bounds__(256)
+nms_mask_kernel(const int32_t* __restrict__ box, const int32_t* __restrict__ labels,
+                const int32_t* __restrict__ order, int n, float thr, uint32_t* __restrict__ mask, int row_words) {
+  __shared__ float4 s_box[8][32];
+  __shared__ int s_lab[8][32];
+  const int i = blockIdx.y * 32 + threadIdx.x;  // sorted position of the row box
+  const int cw = blockIdx.x * 8 + threadIdx.y;  // column word
+  {
+    const int j = cw * 32 + threadIdx.x;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    int l = -1;
+    if (j < n && cw < row_words) {
+      const int oj = order[j];
+      const int4 bi = reinterpret_cast<const int4*>(box)[oj];
+      b = make_float4((float)bi.x, (float)bi.y, (float)bi.z, (float)bi.w);
+      l = labels[oj];
+    }
+    s_box[threadIdx.y][threadIdx.x] = b;
+    s_lab[threadIdx.y][threadIdx.x] = l;
+  }
+  __syncthreads();
+  if (i >= n || cw >= row_words) return;
+  uint32_t bits = 0;
+  if (cw * 32 + 31 > i) {
+    const int oi = order[i];
+    const int4 bi = reinterpret_cast<const int4*>(box)[oi];
+    const float ax1 = (float)bi.x, ay1 = (float)bi.y, ax2 = (float)bi.z, ay2 = (float)bi.w;
+    const float area_a = __fmul_rn(ax2 - ax1, ay2 - ay1);
+    const int la = labels[oi];
+    for (int t = 0; t < 32; ++t) {
+      const int j = cw * 32 + t;
+      if (j <= i || j >= n || s_lab[threadIdx.y][t] != la) continue;
+      const float4 b = s_box[threadIdx.y][t];
+      const float w = fmaxf(fminf(ax2, b.z) - fmaxf(ax1, b.x), 0.0f);
+      const float h = fmaxf(fminf(ay2, b.w) - fmaxf(ay1, b.y), 0.0f);
+      const float inter = __fmul_rn(w, h);
+      const float area_b = __fmul_rn(b.z - b.x, b.w - b.y);
+      const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+      if (ovr > thr) bits |= 1u << t;
+    }
+  }
+  mask[(size_t)i * row_words + cw] = bits;
+}
+
+// greedy scan over the sorted list, one warp.  32 boxes per step: the in-chunk dependencies are resolved
+// on the diagonal word, then the rows of the kept boxes are OR-ed into the removed set.
+constexpr int kScanMaxWords = 8;  // per lane -> n <= 8192
+__global__ void __launch_bounds__(32)
+nms_scan_kernel(const uint32_t* __restrict__ mask, int row_words, const int32_t* __restrict__ order,
+                const float* __restrict__ top_score, int n, int max_keep, int32_t* __restrict__ keep,
+                int32_t* __restrict__ n_keep, int32_t* __restrict__ sel, int32_t* __restrict__ n_sel) {
+  const int lane = threadIdx.x;
+  uint32_t removed[kScanMaxWords];
+#pragma unroll
+  for (int q = 0; q < kScanMaxWords; ++q) removed[q] = 0;
+  int kept = 0, selected = 0;
+  for (int c = 0; c < row_words && kept < max_keep; ++c) {
+    // removed word of this chunk lives in lane (c & 31), slot (c >> 5)
+    uint32_t cur = 0;
+#pragma unroll
+    for (int q = 0; q < kScanMaxWords; ++q)
+      if (q == (c >> 5)) cur = __shfl_sync(kFull, removed[q], c & 31);
+    const int i = c * 32 + lane;
+    const uint32_t diag = i < n ? mask[(size_t)i * row_words + c] : 0u;
+    const int n_here = min(32, n - c * 32);
+    uint32_t keepbits = 0;
+    for (int b = 0; b < n_here; ++b) {
+      const uint32_t d = __shfl_sync(kFull, diag, b);
+      if (!((cur >> b) & 1u)) { keepbits |= 1u << b; cur |= d; }
+    }
+    // truncate to max_keep
+    int cnt = __popc(keepbits);
+    if (kept + cnt > max_keep) {
+      int excess = kept + cnt - max_keep;
+      while (excess--) keepbits &= ~(1u << (31 - __clz(keepbits)));
+      cnt = max_keep - kept;
+    }
+    // emit kept indices (+ positive-score compaction), in sorted order
+    const bool mine = (keepbits >> lane) & 1u;
+    const int oi = (i < n) ? order[i] : 0;
+    const bool pos = mine && (top_score[oi] > 0.0f);
+    const uint32_t posbits = __ballot_sync(kFull, pos);
+    if (mine) keep[kept + __popc(keepbits & ((1u << lane) - 1u))] = oi;
+    if (pos) sel[selected + __popc(posbits & ((1u << lane) - 1u))] = oi;
+    kept += cnt;
+    selected += __popc(posbits);
+    // OR the rows of kept boxes into the removed set (words > c only matter)
+    uint32_t kb = keepbits;
+    while (kb) {
+      const int b = __ffs(kb) - 1;
+      kb &= kb - 1;
+      const uint32_t* row = mask + (size_t)(c * 32 + b) * row_words;
+#pragma unroll
+      for (int q = 0; q < kScanMaxWords; ++q) {
+        const int w = q * 32 + lane;
+        if (w > c && w < row_words) removed[q] |= row[w];
+      }
+    }
+  }
+  if (lane == 0) { *n_keep = kept; *n_sel = selected; }
+}
+
+size_t nms_workspace_bytes(int n) {
+  const size_t row_words = (size_t)ceil_div(n, 32);
+  return align_up(sizeof(int32_t) * (size_t)n, 256) + align_up(sizeof(uint32_t) * row_words * (size_t)n, 256);
+}
+
+int launch_box_nms(const int32_t* box, const float* nms_scores, const int32_t* labels, const float* top_score, int n,
+                   float thr, int max_keep, int32_t* keep, int32_t* n_keep, int32_t* sel, int32_t* n_sel, void* ws,
+                   size_t ws_bytes, cudaStream_t s) {
+  if (n <= 0 || max_keep <= 0) {
+    NTTT_CUDA(cudaMemsetAsync(n_keep, 0, sizeof(int32_t), s));
+    NTTT_CUDA(cudaMemsetAsync(n_sel, 0, sizeof(int32_t), s));
+    return NTTT_OK;
+  }
+  if (n > 32 * 32 * kScanMaxWords) return NTTT_EUNSUPPORTED;
+  if (ws_bytes < nms_workspace_bytes(n)) return NTTT_EWORKSPACE;
+  int32_t* order = static_cast<int32_t*>(ws);
+  uint32_t* mask = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + align_up(sizeof(int32_t) * (size_t)n, 256));
+  int n_pad = 1;
+  while (n_pad < n) n_pad <<= 1;
+  const size_t smem = sizeof(unsigned long long) * (size_t)n_pad;
+  if (smem > 48 * 1024)
+    NTTT_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nms_sort_kernel<<<1, 1024, smem, s>>>(nms_scores, n, n_pad, order);
+  NTTT_LAUNCH_CHECK();
+  const int row_words = ceil_div(n, 32);
+  dim3 grid(ceil_div(row_words, 8), ceil_div(n, 32));
+  nms_mask_kernel<<<grid, dim3(32, 8), 0, s>>>(box, labels, order, n, thr, mask, row_words);
+  NTTT_LAUNCH_CHECK();
+  nms_scan_kernel<<<1, 32, 0, s>>>(mask, row_words, order, top_score, n, max_keep, keep, n_keep, sel, n_sel);
+  NTTT_LAUNCH_CHECK();
+  return NTTT_OK;
+}
+
+}  // namespace nttt

@@ -1,0 +1,142 @@
+"""Host driver of the matching stage: one `nttt_match_image` call per image, no host synchronisation until
+the caller asks for the result.
+
+Mirrors the part of `Sam2MatchingBaselineNoAMG.forward_test` between the `_forward_sam` seam and the output
+dict (`no_time_to_train/models/Sam2MatchingBaseline_noAMG.py:582-683`).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib, ops
+
+
+@dataclass
+class StageConfig:
+    """The `sam2_infer_cfgs` constants the stage reads (`Sam2MatchingBaseline_noAMG.py:185-194`)."""
+    nms_thr: float = 0.5
+    num_out_instance: int = 100
+    cls_num_per_mask: int = 1
+    enc_hw: tuple = (37, 37)
+    expand_ratio: int = 8  # literal at :621
+
+
+class PendingResult:
+    """Device-side result of one image; `.get()` does the single D2H read of the counts and slices."""
+
+    def __init__(self, stage, masks, boxes, scores, labels, index, counts, taps, ori_hw, keepalive):
+        self._stage = stage
+        self.masks, self.boxes, self.scores, self.labels, self.index = masks, boxes, scores, labels, index
+        self.counts = counts
+        self.taps = taps
+        self.ori_hw = ori_hw
+        self._keepalive = keepalive
+        self._event = torch.cuda.Event()
+        self._event.record(torch.cuda.current_stream(masks.device))
+
+    def get(self) -> dict:
+        counts = self.counts.cpu()  # synchronises with the producing stream
+        n_keep, n_sel, n_out = int(counts[0]), int(counts[1]), int(counts[2])
+        dev = self.masks.device
+        oh, ow = self.ori_hw
+        if n_sel == 0:
+            # the reference's empty early-return uses float32 zero boxes (:647-655)
+            out = dict(binary_masks=torch.zeros((0, oh, ow), device=dev, dtype=torch.bool),
+                       bboxes=torch.zeros((0, 4), device=dev, dtype=torch.float32),
+                       scores=torch.zeros((0,), device=dev, dtype=torch.float32),
+                       labels=torch.zeros((0,), device=dev, dtype=torch.long))
+        else:
+            out = dict(binary_masks=self.masks[:n_out], bboxes=self.boxes[:n_out], scores=self.scores[:n_out],
+                       labels=self.labels[:n_out])
+        out["counts"] = dict(n_keep=n_keep, n_sel=n_sel, n_out=n_out)
+        out["index"] = self.index[:n_out]
+        if self.taps:
+            out["taps"] = self.taps
+        return out
+
+
+class MatchingStage:
+    """Per-device matching stage.  Holds the normalised prototypes and the reusable workspace."""
+
+    def __init__(self, device, cfg: StageConfig):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("MatchingStage needs a CUDA device: the matching stage has no CPU path")
+        if cfg.cls_num_per_mask not in (1,):
+            # The reference's k>1 branch passes N scores with N*k boxes to batched_nms
+            # (Sam2MatchingBaseline_noAMG.py:614-629) and only works for k == 1 (k == -1 with one class).
+            raise NotImplementedError("cls_num_per_mask must be 1 (or -1 with a single class)")
+        self.cfg = cfg
+        self.lib = _lib.load()
+        self.ctx = ops.context(self.device)
+        self.proto = None
+        self.n_cls = 0
+        self._ws = {}
+
+    def set_prototypes(self, feats_ins_avg: torch.Tensor) -> None:
+        """normalize(mean over all L slots) once per bank (`matching_baseline_utils.py:893-894`)."""
+        f = feats_ins_avg.to(device=self.device, dtype=torch.float32).contiguous()
+        self.proto = ops.proto_prepare(f)
+        self.n_cls = f.shape[0]
+
+    def _workspace(self, key, nbytes: int) -> torch.Tensor:
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    def match_async(self, lr_masks: torch.Tensor, pred_ious: torch.Tensor, tar_feat: torch.Tensor, ori_hw,
+                    taps: bool = False, slot: int = 0) -> PendingResult:
+        """Enqueue the whole stage for one image on the current stream.  `slot` selects which reusable
+        workspace to use (callers that keep several images in flight on different streams use one slot per
+        stream)."""
+        if self.proto is None:
+            raise RuntimeError("Memory is not ready!")  # same text as Sam2MatchingBaseline_noAMG.py:752
+        ops._need(lr_masks, torch.float32, "lr_masks")
+        ops._need(pred_ious, torch.float32, "pred_ious")
+        ops._need(tar_feat, torch.float32, "tar_feat")
+        n, lh, lw = lr_masks.shape
+        eh, ew = self.cfg.enc_hw
+        e, c = tar_feat.shape
+        if e != eh * ew:
+            raise ValueError(f"tar_feat has {e} patches, expected {eh}x{ew}")
+        oh, ow = int(ori_hw[0]), int(ori_hw[1])
+        num_out = int(self.cfg.num_out_instance)
+        max_sel = int(min(num_out * self.cfg.expand_ratio, n))
+        dev = self.device
+        masks = torch.empty((max(num_out, 1), oh, ow), dtype=torch.uint8, device=dev)
+        boxes = torch.zeros((max(num_out, 1), 4), dtype=torch.int64, device=dev)
+        scores = torch.zeros((max(num_out, 1),), dtype=torch.float32, device=dev)
+        labels = torch.zeros((max(num_out, 1),), dtype=torch.int64, device=dev)
+        index = torch.zeros((max(num_out, 1),), dtype=torch.int32, device=dev)
+        counts = torch.zeros((4,), dtype=torch.int32, device=dev)
+        tap_t = {}
+        if taps:
+            tap_t["sim"] = torch.empty((n, self.n_cls), dtype=torch.float32, device=dev)
+            tap_t["obj_feats"] = torch.empty((n, c), dtype=torch.float32, device=dev)
+        ws_bytes = self.lib.nttt_match_workspace_bytes(n, lh, lw, eh, ew, c, self.n_cls, oh, ow, max_sel)
+        ws = self._workspace(("match", slot), ws_bytes)
+        a = _lib.MatchArgs()
+        a.logits, a.pred_ious, a.tar_feat, a.proto = (lr_masks.data_ptr(), pred_ious.data_ptr(), tar_feat.data_ptr(),
+                                                      self.proto.data_ptr())
+        a.n, a.lr_h, a.lr_w, a.eh, a.ew, a.c, a.n_cls = n, lh, lw, eh, ew, c, self.n_cls
+        a.ori_h, a.ori_w = oh, ow
+        a.nms_thr = float(self.cfg.nms_thr)
+        a.num_out_instance, a.max_sel = num_out, max_sel
+        a.out_masks, a.out_boxes, a.out_scores, a.out_labels = (masks.data_ptr(), boxes.data_ptr(),
+                                                                scores.data_ptr(), labels.data_ptr())
+        a.out_index, a.counts = index.data_ptr(), counts.data_ptr()
+        a.sim = tap_t["sim"].data_ptr() if taps else None
+        a.obj_feats = tap_t["obj_feats"].data_ptr() if taps else None
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(self.lib.nttt_match_image(self.ctx, ctypes.byref(a), stream), "nttt_match_image")
+        return PendingResult(self, masks.view(torch.bool), boxes, scores, labels, index, counts, tap_t, (oh, ow),
+                             keepalive=(lr_masks, pred_ious, tar_feat, ws))
+
+    def match(self, lr_masks, pred_ious, tar_feat, ori_hw, taps: bool = False) -> dict:
+        return self.match_async(lr_masks, pred_ious, tar_feat, ori_hw, taps=taps).get()

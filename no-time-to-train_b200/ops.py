@@ -1,0 +1,228 @@
+"""Per-operator Python entry points over the C-ABI (one function per `nttt_*` entry).
+
+torch is used for device memory and streams only: every function allocates its outputs with torch, passes
+raw device pointers and the current CUDA stream to libnttt_b200.so, and returns torch tensors.  Nothing here
+synchronises the device.  All inputs must be contiguous CUDA tensors of the documented dtype.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+_ctx_by_device = {}
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (the matching stage has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def context(device) -> int:
+    """The per-device `nttt_ctx*` (created on first use)."""
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _ctx_by_device:
+        lib = _lib.load()
+        out = ctypes.c_void_p()
+        with torch.cuda.device(idx):
+            _lib.check(lib.nttt_ctx_create(ctypes.byref(out), idx), "nttt_ctx_create")
+        _ctx_by_device[idx] = out.value
+    return _ctx_by_device[idx]
+
+
+def threshold_pack(logits: torch.Tensor, thr: float = 0.0, off: float = 1.0):
+    """-> bits [n, h*w/32] int32 (bit pattern of uint32), area [n], box [n,4], stab [n,2], flags [n]."""
+    _need(logits, torch.float32, "logits")
+    n, h, w = logits.shape
+    dev = logits.device
+    bits = torch.empty((n, h * w // 32), dtype=torch.int32, device=dev)
+    area = torch.empty((n,), dtype=torch.int32, device=dev)
+    box = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    stab = torch.empty((n, 2), dtype=torch.int32, device=dev)
+    flags = torch.empty((n,), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.nttt_threshold_pack(_ptr(logits), n, h, w, thr, off, _ptr(bits), _ptr(area), _ptr(box), _ptr(stab),
+                                       _ptr(flags), _stream(dev)), "nttt_threshold_pack")
+    return bits, area, box, stab, flags
+
+
+def project_masks(bits: torch.Tensor, hw, enc_hw):
+    _need(bits, torch.int32, "bits")
+    n = bits.shape[0]
+    proj = torch.empty((n, enc_hw[0] * enc_hw[1]), dtype=torch.float32, device=bits.device)
+    lib = _lib.load()
+    _lib.check(lib.nttt_project_masks(context(bits.device), _ptr(bits), n, hw[0], hw[1], enc_hw[0], enc_hw[1],
+                                      _ptr(proj), _stream(bits.device)), "nttt_project_masks")
+    return proj
+
+
+def pool_normalize(proj: torch.Tensor, feat: torch.Tensor, area: torch.Tensor):
+    _need(proj, torch.float32, "proj")
+    _need(feat, torch.float32, "feat")
+    _need(area, torch.int32, "area")
+    n, e = proj.shape
+    c = feat.shape[1]
+    lib = _lib.load()
+    ws_bytes = lib.nttt_pool_workspace_bytes(n, e, c)
+    ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=proj.device)
+    out = torch.empty((n, c), dtype=torch.float32, device=proj.device)
+    _lib.check(lib.nttt_pool_normalize(context(proj.device), _ptr(proj), _ptr(feat), _ptr(area), n, e, c, _ptr(out),
+                                       _ptr(ws), ws_bytes, _stream(proj.device)), "nttt_pool_normalize")
+    return out
+
+
+def proto_prepare(feats_ins_avg: torch.Tensor):
+    _need(feats_ins_avg, torch.float32, "feats_ins_avg")
+    n_cls, shots, c = feats_ins_avg.shape
+    proto = torch.empty((n_cls, c), dtype=torch.float32, device=feats_ins_avg.device)
+    lib = _lib.load()
+    _lib.check(lib.nttt_proto_prepare(_ptr(feats_ins_avg), n_cls, shots, c, _ptr(proto),
+                                      _stream(feats_ins_avg.device)), "nttt_proto_prepare")
+    return proto
+
+
+def similarity_top1(obj_feats: torch.Tensor, proto: torch.Tensor, want_sim: bool = True):
+    _need(obj_feats, torch.float32, "obj_feats")
+    _need(proto, torch.float32, "proto")
+    n, c = obj_feats.shape
+    n_cls = proto.shape[0]
+    dev = obj_feats.device
+    lib = _lib.load()
+    sim = torch.empty((n, n_cls), dtype=torch.float32, device=dev) if want_sim else None
+    ws_bytes = 0 if want_sim else lib.nttt_similarity_workspace_bytes(n, c, n_cls)
+    ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
+    top_score = torch.empty((n,), dtype=torch.float32, device=dev)
+    top_label = torch.empty((n,), dtype=torch.int32, device=dev)
+    _lib.check(lib.nttt_similarity_top1(context(dev), _ptr(obj_feats), _ptr(proto), n, c, n_cls, _ptr(sim),
+                                        _ptr(top_score), _ptr(top_label), _ptr(ws), ws_bytes, _stream(dev)),
+               "nttt_similarity_top1")
+    return sim, top_score, top_label
+
+
+def box_nms(box: torch.Tensor, nms_scores: torch.Tensor, labels: torch.Tensor, top_score: torch.Tensor,
+            iou_thr: float, max_keep: int):
+    """-> keep [max_keep] i32, sel [max_keep] i32, counts [2] i32 = (n_keep, n_sel); all on device."""
+    _need(box, torch.int32, "box")
+    _need(nms_scores, torch.float32, "nms_scores")
+    _need(labels, torch.int32, "labels")
+    _need(top_score, torch.float32, "top_score")
+    n = box.shape[0]
+    dev = box.device
+    lib = _lib.load()
+    ws_bytes = lib.nttt_nms_workspace_bytes(n)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    keep = torch.zeros((max(max_keep, 1),), dtype=torch.int32, device=dev)
+    sel = torch.zeros((max(max_keep, 1),), dtype=torch.int32, device=dev)
+    counts = torch.zeros((2,), dtype=torch.int32, device=dev)
+    _lib.check(lib.nttt_box_nms(_ptr(box), _ptr(nms_scores), _ptr(labels), _ptr(top_score), n, iou_thr, max_keep,
+                                _ptr(keep), counts.data_ptr(), _ptr(sel), counts.data_ptr() + 4, _ptr(ws), ws_bytes,
+                                _stream(dev)), "nttt_box_nms")
+    return keep, sel, counts
+
+
+def upsample_threshold_pack(logits, bits_lr, box_lr, flags_lr, sel, n_sel, max_sel: int, ori_hw):
+    """-> bits_full [max_sel, oh, words] i32, rect [max_sel,4], area_full [max_sel], box_full [max_sel,4]."""
+    _need(logits, torch.float32, "logits")
+    _need(bits_lr, torch.int32, "bits_lr")
+    _need(sel, torch.int32, "sel")
+    _need(n_sel, torch.int32, "n_sel")
+    _, ih, iw = logits.shape
+    oh, ow = ori_hw
+    dev = logits.device
+    words = (ow + 31) // 32
+    bits_full = torch.empty((max_sel, oh, words), dtype=torch.int32, device=dev)
+    rect = torch.zeros((max_sel, 4), dtype=torch.int32, device=dev)
+    area_full = torch.zeros((max_sel,), dtype=torch.int32, device=dev)
+    box_full = torch.zeros((max_sel, 4), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.nttt_upsample_threshold_pack(context(dev), _ptr(logits), _ptr(bits_lr), _ptr(box_lr),
+                                                _ptr(flags_lr), ih, iw, _ptr(sel), _ptr(n_sel), max_sel, oh, ow,
+                                                _ptr(bits_full), _ptr(rect), _ptr(area_full), _ptr(box_full),
+                                                _stream(dev)), "nttt_upsample_threshold_pack")
+    return bits_full, rect, area_full, box_full
+
+
+def unpack_masks(bits_full, rect, n_sel, ori_hw):
+    max_sel = bits_full.shape[0]
+    oh, ow = ori_hw
+    out = torch.zeros((max_sel, oh, ow), dtype=torch.uint8, device=bits_full.device)
+    lib = _lib.load()
+    _lib.check(lib.nttt_unpack_masks(_ptr(bits_full), _ptr(rect), _ptr(n_sel), max_sel, oh, ow, _ptr(out),
+                                     _stream(bits_full.device)), "nttt_unpack_masks")
+    return out.view(torch.bool)
+
+
+def mask_ios(bits_full, rect, area_full, box_full, sel, n_sel, ori_hw, labels, obj_feats, want_inter=False):
+    max_sel = bits_full.shape[0]
+    oh, ow = ori_hw
+    dev = bits_full.device
+    c = obj_feats.shape[1]
+    ios = torch.zeros((max_sel,), dtype=torch.float32, device=dev)
+    inter = torch.zeros((max_sel, max_sel), dtype=torch.int32, device=dev) if want_inter else None
+    lib = _lib.load()
+    _lib.check(lib.nttt_mask_ios(_ptr(bits_full), _ptr(rect), _ptr(area_full), _ptr(box_full), _ptr(sel), _ptr(n_sel),
+                                 max_sel, oh, ow, _ptr(labels), _ptr(obj_feats), c, _ptr(ios), _ptr(inter),
+                                 _stream(dev)), "nttt_mask_ios")
+    return (ios, inter) if want_inter else ios
+
+
+def decay_topk(top_score, labels, ios, sel, n_sel, num_out: int, bits_full, rect, box_full, ori_hw):
+    max_sel = bits_full.shape[0]
+    oh, ow = ori_hw
+    dev = bits_full.device
+    out_masks = torch.empty((num_out, oh, ow), dtype=torch.uint8, device=dev)
+    out_boxes = torch.zeros((num_out, 4), dtype=torch.int64, device=dev)
+    out_scores = torch.zeros((num_out,), dtype=torch.float32, device=dev)
+    out_labels = torch.zeros((num_out,), dtype=torch.int64, device=dev)
+    out_index = torch.zeros((num_out,), dtype=torch.int32, device=dev)
+    out_slot = torch.zeros((num_out,), dtype=torch.int32, device=dev)
+    n_out = torch.zeros((1,), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.nttt_decay_topk(_ptr(top_score), _ptr(labels), _ptr(ios), _ptr(sel), _ptr(n_sel), max_sel, num_out,
+                                   _ptr(bits_full), _ptr(rect), _ptr(box_full), oh, ow, _ptr(out_masks),
+                                   _ptr(out_boxes), _ptr(out_scores), _ptr(out_labels), _ptr(out_index),
+                                   _ptr(out_slot), _ptr(n_out), _stream(dev)), "nttt_decay_topk")
+    return out_masks.view(torch.bool), out_boxes, out_scores, out_labels, out_index, out_slot, n_out
+
+
+def fill_pool_accumulate(feat, soft_mask, enc_hw, sum_slot, wsum_slot, want_mask=False):
+    """sum_slot [c] and wsum_slot [1] are accumulated IN PLACE (views into the bank's sum buffers)."""
+    _need(feat, torch.float32, "feat")
+    _need(soft_mask, torch.float32, "soft_mask")
+    mh, mw = soft_mask.shape[-2:]
+    eh, ew = enc_hw
+    c = feat.shape[-1]
+    mask_out = torch.empty((eh * ew,), dtype=torch.float32, device=feat.device) if want_mask else None
+    lib = _lib.load()
+    _lib.check(lib.nttt_fill_pool_accumulate(_ptr(feat), _ptr(soft_mask), mh, mw, eh, ew, c, _ptr(sum_slot),
+                                             _ptr(wsum_slot), _ptr(mask_out), _stream(feat.device)),
+               "nttt_fill_pool_accumulate")
+    return mask_out
+
+
+def fill_finalize(sums, wsum):
+    _need(sums, torch.float32, "sums")
+    _need(wsum, torch.float32, "wsum")
+    n_cls, shots, c = sums.shape
+    ins_avg = torch.empty_like(sums)
+    avg = torch.empty((n_cls, c), dtype=torch.float32, device=sums.device)
+    lib = _lib.load()
+    _lib.check(lib.nttt_fill_finalize(_ptr(sums), _ptr(wsum), n_cls, shots, c, _ptr(ins_avg), _ptr(avg),
+                                      _stream(sums.device)), "nttt_fill_finalize")
+    return ins_avg, avg

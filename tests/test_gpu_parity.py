@@ -1,0 +1,327 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the oracle and the golden vectors.
+
+Bit-exact: thresholded masks, areas, boxes, stability counts, NMS keep indices, intersection counts.
+1e-3 relative (BASELINE.json north_star): pooled features, prototypes, similarities, IoS, scores.
+"""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import (FILL_CASES, GOLDEN_DIR, RTOL, STAGE_CASES, assert_close_rel, assert_same_ranking, load_case,
+                         sha_bool)
+from oracle import nttt_oracle as orc
+from oracle import ref_torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def P():
+    return importlib.import_module("no-time-to-train_b200")
+
+
+@pytest.fixture(scope="module")
+def ops(P):
+    return importlib.import_module("no-time-to-train_b200.ops")
+
+
+def _unpack_lr(bits, h, w):
+    b = bits.cpu().numpy().view(np.uint32)
+    return np.unpackbits(b.view(np.uint8), bitorder="little").reshape(b.shape[0], h, w)
+
+
+# ------------------------------------------------------------------------------------------------ per-op
+@pytest.mark.parametrize("n", [1, 7, 64])
+def test_threshold_pack_bit_exact(ops, synth, n):
+    gen = torch.Generator().manual_seed(5 + n)
+    logits = synth.make_masks(n, gen)
+    if n >= 7:
+        bank = torch.zeros(2, 2, 4)
+        logits = torch.cat([logits, logits[:1]])[:max(n, 8)]
+        synth.inject_degenerate_cases(logits, bank)
+    logits[0, 3, 5] = float("nan")
+    logits[0, 9, 9] = float("inf")
+    bits, area, box, stab, flags = ops.threshold_pack(logits.to(DEV), 0.0, 1.0)
+    mask, o_area, o_box, o_hi, o_lo = orc.threshold_stats(logits.numpy(), 0.0, 1.0)
+    assert np.array_equal(_unpack_lr(bits, 256, 256), mask)
+    assert np.array_equal(area.cpu().numpy(), o_area)
+    assert np.array_equal(box.cpu().numpy().astype(np.int64), o_box)
+    assert np.array_equal(stab.cpu().numpy()[:, 0], o_hi)
+    assert np.array_equal(stab.cpu().numpy()[:, 1], o_lo)
+    assert flags.cpu().numpy()[0] == 0 and (flags.cpu().numpy()[1:] == 1).all()  # the inf makes mask 0 unsafe
+
+
+def test_threshold_pack_empty_batch(ops):
+    bits, area, *_ = ops.threshold_pack(torch.zeros((0, 256, 256), device=DEV))
+    assert bits.shape[0] == 0 and area.shape[0] == 0
+
+
+@pytest.mark.parametrize("c", [64, 384])
+def test_project_pool_matches_dense_reference(ops, synth, c):
+    """Factored pooling == the reference's literal masks @ upsample(feat) within 1e-3 (measured ~1e-6)."""
+    inp = synth.make_stage_inputs(n=40, c=c, n_cls=5, shots=2, seed=21, degenerate=True)
+    bits, area, *_ = ops.threshold_pack(inp.lr_masks.to(DEV))
+    proj = ops.project_masks(bits, (256, 256), (37, 37))
+    obj = ops.pool_normalize(proj, inp.tar_feat.to(DEV), area)
+    feat_pc = ref_torch.upsample_features(inp.tar_feat, (37, 37), (256, 256))
+    _, want = ref_torch.pool_and_score(feat_pc, ref_torch.threshold_lowres(inp.lr_masks), inp.feats_ins_avg)
+    assert_close_rel(obj.cpu().numpy(), want.numpy(), what="obj_feats")
+    assert float(obj[0].abs().max()) == 0.0  # empty mask -> zero row (F.normalize eps clamp)
+
+
+def test_proto_similarity_top1(ops, synth):
+    inp = synth.make_stage_inputs(n=33, c=384, n_cls=7, shots=3, seed=22, degenerate=True)
+    proto = ops.proto_prepare(inp.feats_ins_avg.to(DEV))
+    assert_close_rel(proto.cpu().numpy(), ref_torch.prototypes(inp.feats_ins_avg).numpy(), what="prototypes")
+    obj = torch.nn.functional.normalize(torch.randn(33, 384, generator=torch.Generator().manual_seed(1)), dim=-1)
+    obj[4] = 0.0  # all-equal row -> lowest index
+    sim, top_score, top_label = ops.similarity_top1(obj.to(DEV), proto)
+    want = obj @ ref_torch.prototypes(inp.feats_ins_avg).t()
+    assert_close_rel(sim.cpu().numpy(), want.numpy(), what="sim")
+    got_lab = top_label.cpu().numpy()
+    assert got_lab[4] == 0
+    # labels must be the argmax of OUR sim exactly, and agree with the reference except on float ties
+    assert np.array_equal(got_lab, sim.cpu().numpy().argmax(1))
+    wl = want.numpy().argmax(1)
+    for i in np.nonzero(got_lab != wl)[0]:
+        assert abs(want[i, got_lab[i]] - want[i, wl[i]]) <= RTOL
+
+
+@pytest.mark.parametrize("n,n_cls", [(1, 1), (17, 2), (300, 4), (1000, 3), (4096, 80)])
+def test_box_nms_matches_oracle_and_torchvision(ops, n, n_cls):
+    from torchvision.ops import batched_nms
+    gen = torch.Generator().manual_seed(n)
+    xy = torch.randint(0, 200, (n, 2), generator=gen)
+    wh = torch.randint(0, 56, (n, 2), generator=gen)
+    box = torch.cat([xy, xy + wh], 1).int()
+    if n > 4:
+        box[3] = box[2]                       # identical boxes
+        box[1] = torch.tensor([5, 5, 5, 40])  # zero-width box
+    scores = torch.rand(n, generator=gen)
+    if n > 4:
+        scores[3] = scores[2]                 # tie -> lower index first
+    labels = torch.randint(0, n_cls, (n,), generator=gen).int()
+    top = torch.rand(n, generator=gen) - 0.2   # some non-positive
+    max_keep = min(800, n)
+    keep, sel, counts = ops.box_nms(box.to(DEV), scores.to(DEV), labels.to(DEV), top.to(DEV), 0.5, max_keep)
+    nk, ns = counts.cpu().tolist()
+    want = orc.box_nms(box.float().numpy(), scores.numpy(), labels.long().numpy(), 0.5)[:max_keep]
+    assert np.array_equal(keep.cpu().numpy()[:nk], want)
+    tv = batched_nms(box.float(), scores, labels.long(), 0.5)[:max_keep].numpy()
+    assert np.array_equal(want, tv)
+    want_sel = want[top.numpy()[want] > 0]
+    assert ns == len(want_sel) and np.array_equal(sel.cpu().numpy()[:ns], want_sel)
+
+
+@pytest.mark.parametrize("ori_hw", [(1024, 1024), (480, 640), (427, 640), (333, 500), (200, 180), (100, 700), (1500, 2040)])
+def test_upsample_threshold_pack_bit_exact(ops, synth, ori_hw):
+    n = 24
+    gen = torch.Generator().manual_seed(ori_hw[0] * 7 + ori_hw[1])
+    logits = synth.make_masks(n, gen)
+    synth.inject_degenerate_cases(logits, torch.zeros(2, 2, 4))
+    logits[9] = 5.0          # all-positive mask exercises the uniform-ones shortcut
+    logits[10, :, :] = -1.0
+    logits[10, 100:140, 90:200] = float("inf")  # non-finite positives: shortcut must be disabled (flags)
+    d = logits.to(DEV)
+    bits, area, box, stab, flags = ops.threshold_pack(d)
+    sel = torch.tensor([5, 0, 1, 2, 3, 9, 10, 11, 12, 20, 23, 7], dtype=torch.int32, device=DEV)
+    n_sel = torch.tensor([sel.numel()], dtype=torch.int32, device=DEV)
+    bits_full, rect, area_full, box_full = ops.upsample_threshold_pack(d, bits, box, flags, sel, n_sel, 16, ori_hw)
+    got = ops.unpack_masks(bits_full, rect, n_sel, ori_hw)[:sel.numel()].cpu().numpy()
+    want = orc.aa_resize_threshold(logits.numpy()[sel.cpu().numpy()], ori_hw).astype(bool)
+    assert np.array_equal(got, want), f"{(got != want).sum()} pixels differ"
+    o_box, o_area = orc.mask_boxes(want.astype(np.uint8))
+    assert np.array_equal(area_full.cpu().numpy()[:sel.numel()], o_area)
+    assert np.array_equal(box_full.cpu().numpy()[:sel.numel()].astype(np.int64), o_box)
+    # informational cross-check against aten's CUDA kernel (the op the reference itself would run on this GPU)
+    aten = torch.nn.functional.interpolate(d[sel.long()].unsqueeze(1), size=ori_hw, mode="bilinear",
+                                           align_corners=False, antialias=True).squeeze(1) > 0
+    diff = int((aten.cpu().numpy() != got).sum())
+    print(f"[aten-cuda cross-check] {ori_hw}: {diff} differing pixels of {got.size}")
+    assert diff == 0
+
+
+def test_mask_ios_counts_bit_exact(ops, synth):
+    inp = synth.make_stage_inputs(n=48, c=64, n_cls=3, shots=2, ori_hw=(333, 500), seed=31, degenerate=True)
+    d = inp.lr_masks.to(DEV)
+    bits, area, box, stab, flags = ops.threshold_pack(d)
+    k = 40
+    sel = torch.arange(k, dtype=torch.int32, device=DEV)
+    n_sel = torch.tensor([k], dtype=torch.int32, device=DEV)
+    bits_full, rect, area_full, box_full = ops.upsample_threshold_pack(d, bits, box, flags, sel, n_sel, k, inp.ori_hw)
+    gen = torch.Generator().manual_seed(2)
+    labels = torch.randint(0, 3, (48,), generator=gen).int()
+    feats = torch.nn.functional.normalize(torch.randn(48, 64, generator=gen), dim=-1)
+    ios, inter = ops.mask_ios(bits_full, rect, area_full, box_full, sel, n_sel, inp.ori_hw, labels.to(DEV),
+                              feats.to(DEV), want_inter=True)
+    full = orc.aa_resize_threshold(inp.lr_masks.numpy()[:k], inp.ori_hw)
+    obj_sim = np.maximum(feats[:k].numpy() @ feats[:k].numpy().T, 0)
+    o_ios, o_inter = orc.semantic_ios(full, labels[:k].long().numpy(), obj_sim, want_inter=True)
+    assert np.array_equal(inter.cpu().numpy(), o_inter)
+    assert_close_rel(ios.cpu().numpy(), o_ios, what="ios")
+
+
+# ------------------------------------------------------------------------------------------------ pipeline
+def _run_stage(P, inp, num_out):
+    stage = P.MatchingStage(DEV, P.StageConfig(nms_thr=0.5, num_out_instance=num_out, enc_hw=(37, 37)))
+    stage.set_prototypes(inp.feats_ins_avg)
+    return stage.match(inp.lr_masks.to(DEV), inp.pred_ious.to(DEV), inp.tar_feat.to(DEV), inp.ori_hw, taps=True)
+
+
+@pytest.mark.parametrize("name", STAGE_CASES)
+def test_pipeline_matches_reference_golden(P, name):
+    g, inp, cfg = load_case(name)
+    out = _run_stage(P, inp, cfg["num_out_instance"])
+    assert_close_rel(out["taps"]["sim"].cpu().numpy(), g["sim"], what="sim")
+    assert_close_rel(out["taps"]["obj_feats"].cpu().numpy(), g["obj_feats"], what="obj_feats")
+    scores, labels = out["scores"].cpu().numpy(), out["labels"].cpu().numpy()
+    assert_same_ranking(scores, labels, g["out_scores"], g["out_labels"], what=name)
+    assert out["bboxes"].dtype == torch.int64 and out["binary_masks"].dtype == torch.bool
+    assert out["labels"].dtype == torch.int64 and out["scores"].dtype == torch.float32
+    masks = out["binary_masks"].cpu().numpy()
+    packed = np.packbits(masks.reshape(masks.shape[0], -1).astype(np.uint8), axis=-1)
+    # identical ranking (NaN-first, then score): compare masks and boxes row by row
+    same_order = np.array_equal(labels, g["out_labels"])
+    if same_order:
+        rows_equal = [np.array_equal(packed[i], g["out_masks_packed"][i]) for i in range(packed.shape[0])]
+        boxes_equal = np.array_equal(out["bboxes"].cpu().numpy(), g["out_bboxes"])
+        if not (all(rows_equal) and boxes_equal):
+            # only legal when two outputs tie in score (unstable argsort in the reference)
+            bad = [i for i, e in enumerate(rows_equal) if not e]
+            for i in bad:
+                assert np.sum(np.abs(g["out_scores"] - g["out_scores"][i]) <= RTOL * abs(g["out_scores"][i])) > 1
+    assert out["counts"]["n_sel"] == (len(g["labels_sel"]) if "labels_sel" in g else 0)
+
+
+@pytest.mark.parametrize("name", STAGE_CASES)
+def test_pipeline_matches_c_oracle(P, name):
+    g, inp, cfg = load_case(name)
+    out = _run_stage(P, inp, cfg["num_out_instance"])
+    ref = orc.match_image(inp.lr_masks.numpy(), inp.pred_ious.numpy(), inp.tar_feat.numpy(),
+                          inp.feats_ins_avg.numpy(), inp.ori_hw, num_out_instance=cfg["num_out_instance"])
+    assert out["counts"]["n_keep"] == len(ref["keep"])
+    assert out["counts"]["n_sel"] == len(ref["sel_index"])
+    assert_same_ranking(out["scores"].cpu().numpy(), out["labels"].cpu().numpy(), ref["scores"], ref["labels"], what=name)
+    if np.array_equal(out["index"].cpu().numpy(), ref["sel_index"][ref["order"]] if "order" in ref else []):
+        assert np.array_equal(out["binary_masks"].cpu().numpy(), ref["binary_masks"].astype(bool))
+        assert np.array_equal(out["bboxes"].cpu().numpy(), ref["bboxes"])
+
+
+def test_pipeline_empty_selection(P, synth):
+    """All scores <= 0 -> the reference's empty early return (float32 zero boxes, :647-655)."""
+    inp = synth.make_stage_inputs(n=16, c=64, n_cls=2, shots=1, ori_hw=(64, 96), seed=41)
+    inp.lr_masks[:] = -1.0
+    out = _run_stage(P, inp, 5)
+    assert out["binary_masks"].shape == (0, 64, 96) and out["bboxes"].dtype == torch.float32
+    assert out["scores"].shape == (0,) and out["labels"].dtype == torch.int64
+
+
+def test_pipeline_not_ready(P):
+    stage = P.MatchingStage(DEV, P.StageConfig())
+    with pytest.raises(RuntimeError, match="Memory is not ready"):
+        stage.match_async(torch.zeros(1, 256, 256, device=DEV), torch.zeros(1, device=DEV),
+                          torch.zeros(1369, 8, device=DEV), (8, 8))
+
+
+@pytest.mark.parametrize("n,c,n_cls,shots,ori_hw", [
+    (1024, 1024, 80, 10, (1024, 1024)),     # BASELINE config 2
+    (256, 1024, 1203, 10, (512, 512)),      # config 4 (LVIS-shape similarity)
+    (4096, 384, 80, 10, (1024, 1024)),      # config 5 (64x64 grid NMS / IoU stress)
+])
+def test_full_size_against_torch_port_on_gpu(P, synth, n, c, n_cls, shots, ori_hw):
+    """BASELINE.json's full sizes: the CUDA path against the torch restatement run on the same GPU (the
+    reference's own op sequence), plus size-independent properties."""
+    inp = synth.make_stage_inputs(n, c, n_cls, shots, ori_hw, seed=77, clustered=True, degenerate=True)
+    out = _run_stage(P, inp, 100)
+    with torch.inference_mode():
+        ref = ref_torch.match_image(inp.lr_masks.to(DEV), inp.pred_ious.to(DEV), inp.tar_feat.to(DEV),
+                                    inp.feats_ins_avg.to(DEV), ref_torch.StageConfig(num_out_instance=100), ori_hw)
+    aux = ref["aux"]
+    assert out["counts"]["n_keep"] == aux["keep"].numel()
+    assert out["counts"]["n_sel"] == aux["sel_index"].numel()
+    assert_close_rel(out["taps"]["sim"].cpu().numpy(), aux["sim"].cpu().numpy(), what="sim")
+    assert_same_ranking(out["scores"].cpu().numpy(), out["labels"].cpu().numpy(), ref["scores"].cpu().numpy(),
+                        ref["labels"].cpu().numpy(), what="full size")
+    # properties: areas/boxes agree with the emitted masks; masks are exactly the torch-CUDA thresholded resize
+    m = out["binary_masks"]
+    idx = out["index"].long()
+    want = ref_torch.upsample_threshold(inp.lr_masks.to(DEV)[idx], ori_hw)
+    assert torch.equal(m, want)
+    assert torch.equal(out["bboxes"], ref_torch.mask_boxes(m))
+    s = out["scores"].cpu().numpy()
+    key = np.where(np.isnan(s), np.inf, s)
+    assert np.all(key[:-1] >= key[1:]), "scores not sorted (NaN first, then descending)"
+
+
+# ------------------------------------------------------------------------------------------------ bank
+@pytest.mark.parametrize("name", FILL_CASES)
+def test_bank_fill_postprocess_matches_reference(P, synth, name):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    n_cls, shots, c, seed, e_side, img_side = g["spec"].tolist()
+    feats, _ = synth.make_ref_shots(n_cls, shots, e_side * e_side, c, seed=seed)
+    bank = P.MemoryBank(dict(category_num=n_cls, length=shots, feat_shape=(e_side * e_side, c))).to(DEV)
+    for (ci, li), soft in zip(g["order"].tolist(), g["soft_masks"]):
+        bank.fill(ci, feats[ci, li].to(DEV), torch.from_numpy(soft).to(DEV), (e_side, e_side))
+    assert np.array_equal(bank.fill_counts.cpu().numpy(), g["fill_counts"])
+    assert np.array_equal(bank.masks.cpu().numpy(), g["masks_lowres"])  # nearest resize is exact
+    bank.postprocess()
+    assert bool(bank.postprocessed[0])
+    assert_close_rel(bank.feats_ins_avg.cpu().numpy(), g["feats_ins_avg"], what="feats_ins_avg")
+    assert_close_rel(bank.feats_avg.cpu().numpy(), g["feats_avg"], what="feats_avg")
+
+
+def test_model_boundary_modes(P, synth):
+    """fill_memory -> postprocess_memory -> test through the reference's forward(input_dicts) boundary, with
+    seam objects standing in for the frozen encoders."""
+    n_cls, shots, c = 3, 2, 64
+    feats, masks = synth.make_ref_shots(n_cls, shots, 1369, c, seed=9)
+    inp = synth.make_stage_inputs(n=32, c=c, n_cls=n_cls, shots=shots, ori_hw=(120, 160), seed=10)
+
+    class Model(P.Sam2MatchingBaselineNoAMG):
+        def _forward_encoder(self, imgs):
+            ci, li = self._next
+            return feats[ci, li].to(imgs.device)[None]
+
+        def _extract_target_features(self, tar_img, device):
+            return inp.tar_feat.to(device), tar_img.to(device)
+
+        def _forward_sam(self, imgs):
+            return inp.lr_masks.to(imgs.device), inp.pred_ious.to(imgs.device), None
+
+    m = Model(sam2_infer_cfgs=dict(points_per_side=32, testing_point_bs=256, iou_thr=0.4, nms_thr=0.5,
+                                   num_out_instance=10, kmeans_k=2, n_pca_components=2, cls_num_per_mask=1),
+              memory_bank_cfg=dict(enable=True, category_num=n_cls, length=shots),
+              encoder_geometry=(518, 14, c), device=DEV)
+    with pytest.raises(RuntimeError, match="Memory is not ready"):
+        m([dict(data_mode="test", target_img=torch.zeros(3, 32, 32),
+                target_img_info=dict(ori_height=120, ori_width=160, file_name="x", id=0))])
+    for li in range(shots):
+        for ci in range(n_cls):
+            m._next = (ci, li)
+            soft = masks[ci, li].reshape(1, 37, 37)
+            r = m([dict(data_mode="fill_memory", refs_by_cat={ci: dict(imgs=torch.rand(1, 3, 64, 64), masks=soft)})])
+            assert r == {}
+    m.postprocess_memory()
+    raw = ref_torch.RawBank(n_cls, shots, 1369, c)
+    for li in range(shots):
+        for ci in range(n_cls):
+            ref_torch.bank_fill(raw, [ci], feats[ci, li][None], masks[ci, li][None])
+    _, want_ins = ref_torch.bank_postprocess(raw)
+    assert_close_rel(m.memory_bank.feats_ins_avg.cpu().numpy(), want_ins.numpy(), what="feats_ins_avg")
+    out = m([dict(data_mode="test", target_img=torch.zeros(3, 32, 32),
+                  target_img_info=dict(ori_height=120, ori_width=160, file_name="x", id=0))])[0]
+    ref = ref_torch.match_image(inp.lr_masks, inp.pred_ious, inp.tar_feat, want_ins,
+                                ref_torch.StageConfig(num_out_instance=10), (120, 160))
+    assert_same_ranking(out["scores"].cpu().numpy(), out["labels"].cpu().numpy(), ref["scores"].numpy(),
+                        ref["labels"].numpy(), what="model")
+    assert set(out) == {"binary_masks", "bboxes", "scores", "labels", "image_info"}
+    # checkpoint round trip keeps the reference's buffer names
+    sd = m.state_dict()
+    for k in ("memory_bank.fill_counts", "memory_bank.feats_avg", "memory_bank.feats_ins_avg", "memory_bank.postprocessed",
+              "memory_bank.masks"):
+        assert k in sd
