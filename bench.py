@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 reference-matching stage (BASELINE.json metric: matching-stage images/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One process per GPU (the driver launches torchrun for N>1; RANK/LOCAL_RANK/WORLD_SIZE from the env).
+A "step" = one pass of the matching stage over one batch of `--batch` synthetic images per GPU at the
+BASELINE config-2 shape (80 classes x 10 shots, 1024 candidate masks of 256x256 logits, DINOv2 ViT-L/14
+features 37x37x1024, 1024x1024 output, top-100 instances).  Images shard over ranks with no data-path
+collective (weak scaling: per-GPU work is fixed).
+
+Printed JSON (rank 0, one line):
+  value      images/s, inputs already resident in HBM, max-over-ranks device time (CUDA events)
+  e2e        images/s through the public API with PINNED HOST inputs and outputs: every step copies its
+             logits / IoUs / features host->device and the result dict device->host inside the timed region
+  roofline   dominant kernel (lowres_pack: the single pass over the 268 MB of logits) vs measured HBM peak
+  cpu_baseline  the oracle's torch port of the reference stage on the host cores (bounded sample)
+`--impl reference` times that same port as the reference arm (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "matching_stage_images_per_s"
+UNIT = "images/s"
+WORKLOAD = dict(workload="coco80x10_sam2L_dinov2L_1024masks_1024x1024", n_masks=1024, lowres=256, feat_hw=37,
+                feat_dim=1024, n_classes=80, shots=10, ori_hw=[1024, 1024], num_out_instance=100, nms_thr=0.5)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="images per step per GPU")
+    ap.add_argument("--streams", type=int, default=4, help="images in flight per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=2, help="images timed for cpu_baseline (0 = skip)")
+    ap.add_argument("--n-masks", type=int, default=WORKLOAD["n_masks"])
+    return ap.parse_args()
+
+
+def make_pool(n_images, n_masks, rank):
+    """`n_images` distinct synthetic images for this rank (seed = 1234 + global image index)."""
+    synth = importlib.import_module("no-time-to-train_b200.synth")
+    pool = []
+    for i in range(n_images):
+        pool.append(synth.make_stage_inputs(n_masks, WORKLOAD["feat_dim"], WORKLOAD["n_classes"], WORKLOAD["shots"],
+                                            tuple(WORKLOAD["ori_hw"]), seed=1234 + rank * 1000 + i, clustered=True))
+    return pool
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            parts = [p.strip() for p in r.split(",")]
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except Exception:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_port_seconds(pool, n_images, timings=None):
+    """The oracle's torch port of the reference stage on the host cores; returns seconds per image."""
+    from oracle import ref_torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = ref_torch.StageConfig(num_out_instance=WORKLOAD["num_out_instance"], nms_thr=WORKLOAD["nms_thr"])
+    ts = []
+    with torch.inference_mode():
+        for i in range(n_images):
+            inp = pool[i % len(pool)]
+            t0 = time.perf_counter()
+            ref_torch.match_image(inp.lr_masks, inp.pred_ious, inp.tar_feat, inp.feats_ins_avg, cfg, inp.ori_hw,
+                                  timings=timings)
+            ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def run_reference(args, rank):
+    """Reference arm: the reference's CPU implementation of the path (oracle port; the reference is Python and
+    cannot travel to the GPU box), all host threads, one image per step."""
+    if rank != 0:
+        return
+    pool = make_pool(1, args.n_masks, 0)
+    cpu_port_seconds(pool, max(args.warmup, 0) and 1)  # one warm-up image is enough on the CPU
+    ts = cpu_port_seconds(pool, args.steps)
+    total = sum(ts)
+    value = args.steps / total
+    cores = os.cpu_count() or 1
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference",
+                config=dict(WORKLOAD, n_masks=args.n_masks, images_per_step=1),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
+                                  sample=f"{args.steps} images, one per step, torch CPU ops with {cores} threads"),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    pkg = importlib.import_module("no-time-to-train_b200")
+    ops = importlib.import_module("no-time-to-train_b200.ops")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, S = args.batch, max(1, min(args.streams, args.batch))
+    pool = make_pool(B, args.n_masks, rank)
+    stage = pkg.MatchingStage(dev, pkg.StageConfig(nms_thr=WORKLOAD["nms_thr"],
+                                                   num_out_instance=WORKLOAD["num_out_instance"],
+                                                   enc_hw=(WORKLOAD["feat_hw"], WORKLOAD["feat_hw"])))
+    stage.set_prototypes(pool[0].feats_ins_avg)
+    lib = stage.lib
+
+    # pinned host copies (e2e) and device-resident copies (value)
+    host = [(p.lr_masks.pin_memory(), p.pred_ious.pin_memory(), p.tar_feat.pin_memory()) for p in pool]
+    resident = [(h[0].to(dev), h[1].to(dev), h[2].to(dev)) for h in host]
+    streams = [torch.cuda.Stream(dev) for _ in range(S)]
+    ori_hw = tuple(WORKLOAD["ori_hw"])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def resident_step():
+        pend = []
+        for i in range(B):
+            s = streams[i % S]
+            with torch.cuda.stream(s):
+                pend.append(stage.match_async(*resident[i], ori_hw, slot=i % S))
+        return pend
+
+    def timed(step_fn, steps):
+        barrier()
+        cur = torch.cuda.current_stream(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(cur)
+        for s in streams:
+            s.wait_event(e0)
+        for _ in range(steps):
+            step_fn()
+        for s in streams:
+            cur.wait_stream(s)
+        e1.record(cur)
+        barrier()
+        t1 = time.perf_counter()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), t0, t1
+
+    # ---- value: device-resident throughput -------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
+    torch.cuda.synchronize(dev)
+    launches0 = lib.nttt_launch_count()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms_total, t0, t1 = timed(resident_step, args.steps)
+    clock_info = clocks.stop(t0, t1) if rank == 0 else None
+    launches = lib.nttt_launch_count() - launches0
+    images = world * args.steps * B
+    value = images / (ms_total / 1e3)
+
+    # ---- e2e: pinned host inputs -> device -> stage -> pinned host outputs, every step ----------------------
+    n_out = WORKLOAD["num_out_instance"]
+    out_host = [dict(masks=torch.empty((n_out, *ori_hw), dtype=torch.bool).pin_memory(),
+                     boxes=torch.empty((n_out, 4), dtype=torch.int64).pin_memory(),
+                     scores=torch.empty((n_out,), dtype=torch.float32).pin_memory(),
+                     labels=torch.empty((n_out,), dtype=torch.int64).pin_memory(),
+                     counts=torch.empty((4,), dtype=torch.int32).pin_memory()) for _ in range(S)]
+    dev_in = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(S)]
+    h2d = sum(t.numel() * t.element_size() for t in host[0]) * B
+    d2h = sum(t.numel() * t.element_size() for t in out_host[0].values()) * B
+
+    def e2e_step():
+        for i in range(B):
+            k = i % S
+            s = streams[k]
+            with torch.cuda.stream(s):
+                for dst, src in zip(dev_in[k], host[i]):
+                    dst.copy_(src, non_blocking=True)
+                p = stage.match_async(*dev_in[k], ori_hw, slot=k)
+                oh = out_host[k]
+                oh["masks"].copy_(p.masks, non_blocking=True)
+                oh["boxes"].copy_(p.boxes, non_blocking=True)
+                oh["scores"].copy_(p.scores, non_blocking=True)
+                oh["labels"].copy_(p.labels, non_blocking=True)
+                oh["counts"].copy_(p.counts, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    e2e_steps = max(2, min(args.steps, 10))
+    ms_e2e, _, _ = timed(e2e_step, e2e_steps)
+    e2e_value = world * e2e_steps * B / (ms_e2e / 1e3)
+
+    # ---- per-stage share (single stream, CUDA events between the stage's kernels) and the roofline kernel --
+    stage_ms = {}
+    roofline = None
+    if rank == 0:
+        stage.profile(True)
+        for rep in range(2 * B):
+            stage.match_async(*resident[rep % B], ori_hw, slot=0)
+            for k, v in stage.profile_read().items():
+                if rep >= B:
+                    stage_ms[k] = stage_ms.get(k, 0.0) + v / B
+        stage.profile(False)
+        # dominant kernel alone, over inputs larger than L2 (B x 268 MB rotate), events on the launching stream
+        reps = max(3 * B, 24)
+        for i in range(B):
+            ops.threshold_pack(resident[i][0])
+        torch.cuda.synchronize(dev)
+        cur = torch.cuda.current_stream(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        keep = []
+        e0.record(cur)
+        for i in range(reps):
+            keep.append(ops.threshold_pack(resident[i % B][0]))
+        e1.record(cur)
+        torch.cuda.synchronize(dev)
+        k_ms = e0.elapsed_time(e1) / reps
+        alg_bytes = 4 * args.n_masks * WORKLOAD["lowres"] ** 2
+        peak, peak_src = 6650.0, "fallback"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        roofline = dict(bound="hbm", kernel="lowres_pack_kernel", achieved=achieved, peak=peak, unit="GB/s",
+                        frac=achieved / peak, traffic=None, peak_source=peak_src, alg_bytes_per_launch=alg_bytes,
+                        us_per_launch=1e3 * k_ms)
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle's torch port on a bounded sample -------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and args.cpu_sample > 0:
+        cpu_pool = pool[:1]
+        cpu_port_seconds(cpu_pool, 1)
+        tm = {}
+        ts = cpu_port_seconds(cpu_pool, args.cpu_sample, timings=tm)
+        cores = os.cpu_count() or 1
+        cpu_baseline = dict(value=len(ts) / sum(ts), unit=UNIT, cores=cores, kind="port",
+                            sample=f"{len(ts)} image(s) of the same workload after 1 warm-up, torch CPU ops, "
+                                   f"{cores} threads",
+                            ms_per_stage={k: 1e3 * v / len(ts) for k, v in tm.items()})
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f32", data="synthetic",
+                    config=dict(WORKLOAD, n_masks=args.n_masks, images_per_step_per_gpu=B, streams=S,
+                                l2_policy=f"inputs larger than L2: {B} images x 268 MB of logits rotate"),
+                    us_per_image=1e3 * ms_total / (args.steps * B),
+                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                             steps=e2e_steps),
+                    gpu_launches=int(launches), clocks=clock_info, roofline=roofline, cpu_baseline=cpu_baseline,
+                    stage_us_per_image={k: 1e3 * v for k, v in stage_ms.items()})
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -53,6 +53,17 @@ const char* nttt_last_cuda_error(void);
 int nttt_ctx_create(nttt_ctx** out, int device);
 void nttt_ctx_destroy(nttt_ctx* ctx);
 
+/* number of kernels this library has launched in this process (bench.py's `gpu_launches`) */
+unsigned long long nttt_launch_count(void);
+
+/* Optional per-stage CUDA-event profile of nttt_match_image: when enabled, an event is recorded on the
+ * launching stream between the stage's kernels; nttt_ctx_profile_read synchronises on the last one and
+ * writes the elapsed milliseconds of each stage of the most recent image to HOST memory. */
+int nttt_profile_num_stages(void);
+const char* nttt_profile_stage_name(int i);
+int nttt_ctx_profile(nttt_ctx* ctx, int enable);
+int nttt_ctx_profile_read(nttt_ctx* ctx, float* ms_host, int capacity);
+
 /* ---------------------------------------------------------------------------------------------------
  * a6 / a9 / a15 — low-res threshold, bit-pack, area, box, stability counts
  * replaces: `lr_masks > 0` (Sam2MatchingBaseline_noAMG.py:548-549), `batched_mask_to_box(lr_masks > 0)`

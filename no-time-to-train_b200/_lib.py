@@ -64,6 +64,11 @@ SIGNATURES = {
     "nttt_match_workspace_bytes": (c_size_t, [c_int] * 10),
     "nttt_match_image": (c_int, [_P, POINTER(MatchArgs), _P]),
     "nttt_sizeof_match_args": (c_size_t, []),
+    "nttt_launch_count": (ctypes.c_ulonglong, []),
+    "nttt_profile_num_stages": (c_int, []),
+    "nttt_profile_stage_name": (c_char_p, [c_int]),
+    "nttt_ctx_profile": (c_int, [_P, c_int]),
+    "nttt_ctx_profile_read": (c_int, [_P, POINTER(c_float), c_int]),
 }
 
 _lib = None

@@ -33,6 +33,7 @@ int launch_fill_pool(const float*, const float*, int, int, int, int, int, float*
 int launch_fill_finalize(const float*, const float*, int, int, int, float*, float*, cudaStream_t);
 
 static thread_local char g_cuda_err[512] = "";
+unsigned long long g_launches = 0;
 
 int cuda_fail(cudaError_t e, const char* what) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
@@ -57,25 +58,35 @@ struct Carver {
 
 using namespace nttt;
 
-const nttt::AxisTable* nttt_ctx::axis(int in_size, int out_size, cudaStream_t s, int* err) {
-  *err = NTTT_OK;
+int nttt_ctx::axis(int in_size, int out_size, cudaStream_t s, nttt::AxisTable* out) {
   for (int i = 0; i < n_tables; ++i)
-    if (tables[i].in_size == in_size && tables[i].out_size == out_size) return &tables[i];
-  if (n_tables == kMaxTables) {  // evict the oldest (sizes rarely change within a run)
-    cudaStreamSynchronize(s);
-    free_axis_table(tables[0]);
-    for (int i = 1; i < n_tables; ++i) tables[i - 1] = tables[i];
-    --n_tables;
+    if (tables[i].in_size == in_size && tables[i].out_size == out_size) {
+      last_use[i] = epoch;
+      *out = tables[i];
+      return NTTT_OK;
+    }
+  int slot = n_tables;
+  if (n_tables == kMaxTables) {
+    // evict the least recently used table that the current call has not taken; kernels of earlier calls
+    // (possibly on other streams) may still read it, so drain the device first.  Rare: sizes seldom change.
+    slot = -1;
+    for (int i = 0; i < n_tables; ++i)
+      if (last_use[i] < epoch && (slot < 0 || last_use[i] < last_use[slot])) slot = i;
+    if (slot < 0) return NTTT_EUNSUPPORTED;
+    NTTT_CUDA(cudaDeviceSynchronize());
+    free_axis_table(tables[slot]);
   }
-  AxisTable& t = tables[n_tables];
-  t = AxisTable{};
-  *err = build_axis_table(t, in_size, out_size, s);
-  if (*err != NTTT_OK) return nullptr;
+  AxisTable t{};
+  int err = build_axis_table(t, in_size, out_size, s);
+  if (err != NTTT_OK) { free_axis_table(t); return err; }
   // the tables are read by kernels on any stream afterwards: make them visible once, here
   cudaError_t e = cudaStreamSynchronize(s);
-  if (e != cudaSuccess) { *err = cuda_fail(e, "axis table build"); return nullptr; }
-  ++n_tables;
-  return &t;
+  if (e != cudaSuccess) { free_axis_table(t); return cuda_fail(e, "axis table build"); }
+  tables[slot] = t;
+  last_use[slot] = epoch;
+  if (slot == n_tables) ++n_tables;
+  *out = t;
+  return NTTT_OK;
 }
 
 extern "C" {
@@ -83,6 +94,33 @@ extern "C" {
 int nttt_version(void) { return NTTT_VERSION; }
 
 size_t nttt_sizeof_match_args(void) { return sizeof(nttt_match_args); }
+
+unsigned long long nttt_launch_count(void) { return g_launches; }
+
+static const char* const kStageNames[] = {"lowres_pack", "project_masks", "pool_gemm", "normalize_rows", "sim_gemm",
+                                          "top1", "box_nms", "upsample_pack", "mask_ios", "decay_rank", "unpack"};
+static constexpr int kNumStages = sizeof(kStageNames) / sizeof(kStageNames[0]);
+
+int nttt_profile_num_stages(void) { return kNumStages; }
+const char* nttt_profile_stage_name(int i) { return (i >= 0 && i < kNumStages) ? kStageNames[i] : ""; }
+
+int nttt_ctx_profile(nttt_ctx* ctx, int enable) {
+  if (!ctx) return NTTT_EINVAL;
+  if (enable)
+    for (int i = 0; i <= kNumStages; ++i)
+      if (!ctx->ev[i]) NTTT_CUDA(cudaEventCreate(&ctx->ev[i]));
+  ctx->profile = enable != 0;
+  ctx->n_ev = 0;
+  return NTTT_OK;
+}
+
+int nttt_ctx_profile_read(nttt_ctx* ctx, float* ms_host, int capacity) {
+  if (!ctx || !ms_host || capacity < kNumStages) return NTTT_EINVAL;
+  if (ctx->n_ev != kNumStages + 1) return NTTT_EINVAL;  // no complete image recorded
+  NTTT_CUDA(cudaEventSynchronize(ctx->ev[kNumStages]));
+  for (int i = 0; i < kNumStages; ++i) NTTT_CUDA(cudaEventElapsedTime(&ms_host[i], ctx->ev[i], ctx->ev[i + 1]));
+  return kNumStages;
+}
 
 const char* nttt_error_string(int code) {
   switch (code) {
@@ -127,6 +165,8 @@ void nttt_ctx_destroy(nttt_ctx* ctx) {
   if (!ctx) return;
   for (int i = 0; i < ctx->n_tables; ++i) free_axis_table(ctx->tables[i]);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  for (int i = 0; i <= nttt_ctx::kMaxStages; ++i)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   delete ctx;
 }
 
@@ -142,12 +182,13 @@ int nttt_project_masks(nttt_ctx* ctx, const uint32_t* bits, int n, int h, int w,
   if (!ctx || n < 0 || h <= 0 || w <= 0 || eh <= 0 || ew <= 0) return NTTT_EINVAL;
   if (n > 0 && (!bits || !proj)) return NTTT_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
-  int err;
-  const AxisTable* tx = ctx->axis(ew, w, s, &err);
-  if (!tx) return err;
-  const AxisTable* ty = ctx->axis(eh, h, s, &err);
-  if (!ty) return err;
-  return launch_project_masks(*tx, *ty, bits, n, h, w, eh, ew, proj, eh * ew, s);
+  ++ctx->epoch;
+  AxisTable tx, ty;
+  int err = ctx->axis(ew, w, s, &tx);
+  if (err) return err;
+  err = ctx->axis(eh, h, s, &ty);
+  if (err) return err;
+  return launch_project_masks(tx, ty, bits, n, h, w, eh, ew, proj, eh * ew, s);
 }
 
 size_t nttt_pool_workspace_bytes(int n, int e, int c) {
@@ -228,15 +269,16 @@ int nttt_upsample_threshold_pack(nttt_ctx* ctx, const float* logits, const uint3
   if (!logits || !bits_lr || !box_lr || !flags_lr || !sel || !n_sel || !bits_full || !rect || !area_full || !box_full)
     return NTTT_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
-  int err;
-  const AxisTable* tx = ctx->axis(iw, ow, s, &err);
-  if (!tx) return err;
-  const AxisTable* ty = ctx->axis(ih, oh, s, &err);
-  if (!ty) return err;
+  ++ctx->epoch;
+  AxisTable tx, ty;
+  int err = ctx->axis(iw, ow, s, &tx);
+  if (err) return err;
+  err = ctx->axis(ih, oh, s, &ty);
+  if (err) return err;
   int32_t* scratch = nullptr;
   err = ensure_scratch(ctx, max_sel, &scratch);
   if (err) return err;
-  return launch_upsample_pack(*tx, *ty, logits, bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, oh, ow,
+  return launch_upsample_pack(tx, ty, logits, bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, oh, ow,
                               bits_full, rect, area_full, box_full, scratch, s);
 }
 
@@ -364,23 +406,27 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   if (a->workspace_bytes < L.total) return NTTT_EWORKSPACE;
   float* obj_feats = a->obj_feats ? a->obj_feats : L.obj_feats;
   float* sim = a->sim ? a->sim : L.sim;
-  int err;
-  const AxisTable* px = ctx->axis(a->ew, a->lr_w, s, &err);
-  if (!px) return err;
-  const AxisTable* py = ctx->axis(a->eh, a->lr_h, s, &err);
-  if (!py) return err;
-  const AxisTable* ux = ctx->axis(a->lr_w, a->ori_w, s, &err);
-  if (!ux) return err;
-  const AxisTable* uy = ctx->axis(a->lr_h, a->ori_h, s, &err);
-  if (!uy) return err;
+  ++ctx->epoch;
+  AxisTable px, py, ux, uy;
+  int err = ctx->axis(a->ew, a->lr_w, s, &px);
+  if (err) return err;
+  if ((err = ctx->axis(a->eh, a->lr_h, s, &py))) return err;
+  if ((err = ctx->axis(a->lr_w, a->ori_w, s, &ux))) return err;
+  if ((err = ctx->axis(a->lr_h, a->ori_h, s, &uy))) return err;
   const int e = a->eh * a->ew;
 
-#define NTTT_STEP(call) do { err = (call); if (err) return err; } while (0)
+  ctx->n_ev = 0;
+#define NTTT_MARK()                                                              \
+  do {                                                                           \
+    if (ctx->profile) { NTTT_CUDA(cudaEventRecord(ctx->ev[ctx->n_ev], s)); ++ctx->n_ev; } \
+  } while (0)
+#define NTTT_STEP(call) do { err = (call); if (err) return err; NTTT_MARK(); } while (0)
+  NTTT_MARK();
   // a6/a9/a15: one pass over the logits
   NTTT_STEP(launch_lowres_pack(a->logits, n, a->lr_h, a->lr_w, 0.0f, 1.0f, L.bits_lr, L.area_lr, L.box_lr, L.stab,
                                L.flags, s));
   // a6/a7: projection + pooling contraction + normalisation
-  NTTT_STEP(launch_project_masks(*px, *py, L.bits_lr, n, a->lr_h, a->lr_w, a->eh, a->ew, L.proj, e, s));
+  NTTT_STEP(launch_project_masks(px, py, L.bits_lr, n, a->lr_h, a->lr_w, a->eh, a->ew, L.proj, e, s));
   NTTT_STEP(launch_sgemm(false, L.proj, e, a->tar_feat, a->c, L.sums, a->c, n, a->c, e, s));
   NTTT_STEP(launch_normalize_rows(L.sums, L.area_lr, n, a->c, obj_feats, s));
   // a7/a8: similarity + top-1
@@ -390,7 +436,7 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   NTTT_STEP(launch_box_nms(L.box_lr, a->pred_ious, L.top_label, L.top_score, n, a->nms_thr, max_sel, L.keep,
                            a->counts + 0, L.sel, a->counts + 1, L.nms_ws, L.nms_ws_bytes, s));
   // a12/a9
-  NTTT_STEP(launch_upsample_pack(*ux, *uy, a->logits, L.bits_lr, L.box_lr, L.flags, a->lr_h, a->lr_w, L.sel,
+  NTTT_STEP(launch_upsample_pack(ux, uy, a->logits, L.bits_lr, L.box_lr, L.flags, a->lr_h, a->lr_w, L.sel,
                                  a->counts + 1, max_sel, a->ori_h, a->ori_w, L.bits_full, L.rect, L.area_full,
                                  L.box_full, L.scratch, s));
   // a13
@@ -403,6 +449,7 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   NTTT_STEP(launch_unpack(L.bits_full, L.rect, L.out_slot, a->counts + 2, num_out, a->ori_h, a->ori_w, a->out_masks,
                           s));
 #undef NTTT_STEP
+#undef NTTT_MARK
   return NTTT_OK;
 }
 

@@ -18,7 +18,13 @@ int cuda_fail(cudaError_t e, const char* what);
     cudaError_t _e = (expr);                                   \
     if (_e != cudaSuccess) return ::nttt::cuda_fail(_e, #expr); \
   } while (0)
-#define NTTT_LAUNCH_CHECK() NTTT_CUDA(cudaGetLastError())
+// every kernel launch of the library passes through here; the counter backs nttt_launch_count()
+extern unsigned long long g_launches;
+#define NTTT_LAUNCH_CHECK()          \
+  do {                               \
+    ++::nttt::g_launches;            \
+    NTTT_CUDA(cudaGetLastError());   \
+  } while (0)
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -84,10 +90,19 @@ void free_axis_table(AxisTable& t);
 struct nttt_ctx {
   int device = 0;
   int sm_count = 0;
-  static constexpr int kMaxTables = 16;
+  // cache of antialias tables keyed by (in,out); least-recently-used entry of an EARLIER call is evicted
+  static constexpr int kMaxTables = 32;
   nttt::AxisTable tables[kMaxTables];
+  unsigned long long last_use[kMaxTables] = {};
+  unsigned long long epoch = 0;  // bumped once per API call that takes tables
   int n_tables = 0;
   int32_t* scratch = nullptr;  // per-mask statistics scratch of the stand-alone resize entry
   int scratch_cap = 0;
-  const nttt::AxisTable* axis(int in_size, int out_size, cudaStream_t s, int* err);
+  // optional per-stage CUDA-event profile of nttt_match_image (off by default)
+  static constexpr int kMaxStages = 16;
+  bool profile = false;
+  cudaEvent_t ev[kMaxStages + 1] = {};
+  int n_ev = 0;
+  // returns the table BY VALUE (device pointers stay valid until evicted by a later call)
+  int axis(int in_size, int out_size, cudaStream_t s, nttt::AxisTable* out);
 };

@@ -138,5 +138,18 @@ class MatchingStage:
         return PendingResult(self, masks.view(torch.bool), boxes, scores, labels, index, counts, tap_t, (oh, ow),
                              keepalive=(lr_masks, pred_ious, tar_feat, ws))
 
+    def profile(self, enable: bool) -> None:
+        """Per-stage CUDA-event timing of the next `match_async` calls (see nttt_ctx_profile)."""
+        _lib.check(self.lib.nttt_ctx_profile(self.ctx, int(enable)), "nttt_ctx_profile")
+
+    def profile_read(self) -> dict:
+        """Stage name -> milliseconds of the most recent image (synchronises on its last event)."""
+        n = self.lib.nttt_profile_num_stages()
+        buf = (ctypes.c_float * n)()
+        got = self.lib.nttt_ctx_profile_read(self.ctx, buf, n)
+        if got < 0:
+            _lib.check(got, "nttt_ctx_profile_read")
+        return {self.lib.nttt_profile_stage_name(i).decode(): float(buf[i]) for i in range(got)}
+
     def match(self, lr_masks, pred_ious, tar_feat, ori_hw, taps: bool = False) -> dict:
         return self.match_async(lr_masks, pred_ious, tar_feat, ori_hw, taps=taps).get()
