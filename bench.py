@@ -274,15 +274,15 @@ def main():
         stage.profile(False)
         # dominant kernel alone, over inputs larger than L2 (B x 268 MB rotate), events on the launching stream
         reps = max(3 * B, 24)
+        outs = ops.threshold_pack(resident[0][0])
         for i in range(B):
-            ops.threshold_pack(resident[i][0])
+            ops.threshold_pack(resident[i][0], out=outs)
         torch.cuda.synchronize(dev)
         cur = torch.cuda.current_stream(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        keep = []
         e0.record(cur)
         for i in range(reps):
-            keep.append(ops.threshold_pack(resident[i % B][0]))
+            ops.threshold_pack(resident[i % B][0], out=outs)
         e1.record(cur)
         torch.cuda.synchronize(dev)
         k_ms = e0.elapsed_time(e1) / reps

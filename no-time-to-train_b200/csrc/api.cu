@@ -12,7 +12,9 @@ int launch_lowres_pack(const float*, int, int, int, float, float, uint32_t*, int
                        cudaStream_t);
 int launch_project_masks(const AxisTable&, const AxisTable&, const uint32_t*, int, int, int, int, int, float*, int,
                          cudaStream_t);
-int launch_sgemm(bool, const float*, int, const float*, int, float*, int, int, int, int, cudaStream_t);
+int launch_gemm_tc(const void*, int, const void*, int, float*, int, int, int, int, cudaStream_t);
+int launch_split_rows(const float*, int, int, int, int, int, void*, cudaStream_t);
+int launch_split_transpose(const float*, int, int, int, int, int, void*, cudaStream_t);
 int launch_normalize_rows(const float*, const int32_t*, int, int, float*, cudaStream_t);
 int launch_proto_prepare(const float*, int, int, int, float*, cudaStream_t);
 int launch_top1(const float*, int, int, int, float*, int32_t*, cudaStream_t);
@@ -53,6 +55,31 @@ struct Carver {
     return p;
   }
 };
+
+inline int pad64(int k) { return (k + 63) / 64 * 64; }
+
+// sums[n, c] = proj[n, e] * feat[e, c] on the tensor cores (split-bf16, K' = 3 * pad64(e))
+// scratch: a_split [n, 3*ep] bf16, b_split [c, 3*ep] bf16
+static int pool_contract(const float* proj, const float* feat, int n, int e, int c, float* sums, void* a_split,
+                         void* b_split, cudaStream_t s) {
+  const int ep = pad64(e);
+  int err = launch_split_rows(proj, e, n, e, ep, 0, a_split, s);
+  if (err) return err;
+  err = launch_split_transpose(feat, c, c, e, ep, 1, b_split, s);
+  if (err) return err;
+  return launch_gemm_tc(a_split, 3 * ep, b_split, 3 * ep, sums, c, n, c, 3 * ep, s);
+}
+
+// sim[n, n_cls] = obj_feats[n, c] * proto[n_cls, c]^T
+static int sim_contract(const float* obj_feats, const float* proto, int n, int c, int n_cls, float* sim, void* a_split,
+                        void* b_split, cudaStream_t s) {
+  const int cp = pad64(c);
+  int err = launch_split_rows(obj_feats, c, n, c, cp, 0, a_split, s);
+  if (err) return err;
+  err = launch_split_rows(proto, c, n_cls, c, cp, 1, b_split, s);
+  if (err) return err;
+  return launch_gemm_tc(a_split, 3 * cp, b_split, 3 * cp, sim, n_cls, n, n_cls, 3 * cp, s);
+}
 
 }  // namespace nttt
 
@@ -192,8 +219,9 @@ int nttt_project_masks(nttt_ctx* ctx, const uint32_t* bits, int n, int h, int w,
 }
 
 size_t nttt_pool_workspace_bytes(int n, int e, int c) {
-  (void)e;
-  return align_up(sizeof(float) * (size_t)n * c, 256);
+  const size_t ep = pad64(e);
+  return align_up(sizeof(float) * (size_t)n * c, 256) + align_up(2 * (size_t)n * 3 * ep, 256) +
+         align_up(2 * (size_t)c * 3 * ep, 256);
 }
 
 int nttt_pool_normalize(nttt_ctx* ctx, const float* proj, const float* feat, const int32_t* area, int n, int e, int c,
@@ -203,8 +231,11 @@ int nttt_pool_normalize(nttt_ctx* ctx, const float* proj, const float* feat, con
   if (!proj || !feat || !area || !obj_feats || !workspace) return NTTT_EINVAL;
   if (workspace_bytes < nttt_pool_workspace_bytes(n, e, c)) return NTTT_EWORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
-  float* sums = static_cast<float*>(workspace);
-  int err = launch_sgemm(false, proj, e, feat, c, sums, c, n, c, e, s);
+  char* ws = static_cast<char*>(workspace);
+  float* sums = reinterpret_cast<float*>(ws);
+  char* a_split = ws + align_up(sizeof(float) * (size_t)n * c, 256);
+  char* b_split = a_split + align_up(2 * (size_t)n * 3 * pad64(e), 256);
+  int err = pool_contract(proj, feat, n, e, c, sums, a_split, b_split, s);
   if (err) return err;
   return launch_normalize_rows(sums, area, n, c, obj_feats, s);
 }
@@ -215,8 +246,9 @@ int nttt_proto_prepare(const float* feats_ins_avg, int n_cls, int shots, int c, 
 }
 
 size_t nttt_similarity_workspace_bytes(int n, int c, int n_cls) {
-  (void)c;
-  return align_up(sizeof(float) * (size_t)n * n_cls, 256);
+  const size_t cp = pad64(c);
+  return align_up(sizeof(float) * (size_t)n * n_cls, 256) + align_up(2 * (size_t)n * 3 * cp, 256) +
+         align_up(2 * (size_t)n_cls * 3 * cp, 256);
 }
 
 int nttt_similarity_top1(nttt_ctx* ctx, const float* obj_feats, const float* proto, int n, int c, int n_cls,
@@ -226,12 +258,12 @@ int nttt_similarity_top1(nttt_ctx* ctx, const float* obj_feats, const float* pro
   if (n == 0) return NTTT_OK;
   if (!obj_feats || !proto || !top_score || !top_label) return NTTT_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
-  float* simbuf = sim;
-  if (!simbuf) {
-    if (!workspace || workspace_bytes < nttt_similarity_workspace_bytes(n, c, n_cls)) return NTTT_EWORKSPACE;
-    simbuf = static_cast<float*>(workspace);
-  }
-  int err = launch_sgemm(true, obj_feats, c, proto, c, simbuf, n_cls, n, n_cls, c, s);
+  if (!workspace || workspace_bytes < nttt_similarity_workspace_bytes(n, c, n_cls)) return NTTT_EWORKSPACE;
+  char* ws = static_cast<char*>(workspace);
+  float* simbuf = sim ? sim : reinterpret_cast<float*>(ws);
+  char* a_split = ws + align_up(sizeof(float) * (size_t)n * n_cls, 256);
+  char* b_split = a_split + align_up(2 * (size_t)n * 3 * pad64(c), 256);
+  int err = sim_contract(obj_feats, proto, n, c, n_cls, simbuf, a_split, b_split, s);
   if (err) return err;
   return launch_top1(simbuf, n_cls, n, n_cls, top_score, top_label, s);
 }
@@ -341,6 +373,7 @@ int nttt_fill_finalize(const float* sum, const float* wsum, int n_cls, int shots
 struct MatchLayout {
   uint32_t* bits_lr; int32_t* area_lr; int32_t* box_lr; int32_t* stab; int32_t* flags;
   float* proj; float* sums; float* obj_feats; float* sim; float* top_score; int32_t* top_label;
+  char* a_split; char* b_split;
   void* nms_ws; size_t nms_ws_bytes; int32_t* keep; int32_t* sel;
   uint32_t* bits_full; int32_t* rect; int32_t* area_full; int32_t* box_full; int32_t* scratch;
   float* ios; int32_t* out_slot;
@@ -361,6 +394,12 @@ static MatchLayout carve(void* ws, int n, int lr_h, int lr_w, int eh, int ew, in
   L.sums = cv.take<float>((size_t)n * c);
   L.obj_feats = cv.take<float>((size_t)n * c);
   L.sim = cv.take<float>((size_t)n * n_cls);
+  {
+    const size_t kmax = (size_t)3 * (pad64(eh * ew) > pad64(c) ? pad64(eh * ew) : pad64(c));
+    const size_t rows_b = (size_t)(c > n_cls ? c : n_cls);
+    L.a_split = cv.take<char>(2 * (size_t)n * kmax);
+    L.b_split = cv.take<char>(2 * rows_b * kmax);
+  }
   L.top_score = cv.take<float>(n);
   L.top_label = cv.take<int32_t>(n);
   L.nms_ws_bytes = nms_workspace_bytes(n > 0 ? n : 1);
@@ -427,10 +466,10 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
                                L.flags, s));
   // a6/a7: projection + pooling contraction + normalisation
   NTTT_STEP(launch_project_masks(px, py, L.bits_lr, n, a->lr_h, a->lr_w, a->eh, a->ew, L.proj, e, s));
-  NTTT_STEP(launch_sgemm(false, L.proj, e, a->tar_feat, a->c, L.sums, a->c, n, a->c, e, s));
+  NTTT_STEP(pool_contract(L.proj, a->tar_feat, n, e, a->c, L.sums, L.a_split, L.b_split, s));
   NTTT_STEP(launch_normalize_rows(L.sums, L.area_lr, n, a->c, obj_feats, s));
   // a7/a8: similarity + top-1
-  NTTT_STEP(launch_sgemm(true, obj_feats, a->c, a->proto, a->c, sim, a->n_cls, n, a->n_cls, a->c, s));
+  NTTT_STEP(sim_contract(obj_feats, a->proto, n, a->c, a->n_cls, sim, L.a_split, L.b_split, s));
   NTTT_STEP(launch_top1(sim, a->n_cls, n, a->n_cls, L.top_score, L.top_label, s));
   // a10/a11
   NTTT_STEP(launch_box_nms(L.box_lr, a->pred_ious, L.top_label, L.top_score, n, a->nms_thr, max_sel, L.keep,

@@ -1,0 +1,344 @@
+// tcgen05 / TMEM / TMA GEMM for the two contractions of the matching stage:
+//   pooling     sums[N, C]     = proj[N, E]      * feat[E, C]            (matching_baseline_utils.py:890)
+//   similarity  sim [N, n_cls] = obj_feats[N, C] * proto[n_cls, C]^T     (matching_baseline_utils.py:896)
+//
+// D[M, N] (fp32) = A[M, K'] * B[N, K']^T with bf16 operands, K-major, staged by TMA into 128B-swizzled shared
+// memory and multiplied by tcgen05.mma (cta_group::1, UMMA 128 x BN x 16) into a TMEM accumulator.
+//
+// fp32 accuracy on bf16 tensor cores: each fp32 operand x is split into hi = bf16(x), lo = bf16(x - hi) and the
+// three significant partial products are laid side by side along K,
+//     A' = [A_hi | A_hi | A_lo],  B' = [B_hi | B_lo | B_hi]   =>   A'B'^T = A_hi B_hi + A_hi B_lo + A_lo B_hi,
+// so one ordinary bf16 GEMM with K' = 3*Kp yields ~2^-17 relative error (the dropped lo*lo term), far inside
+// the 1e-3 parity bound and small enough not to disturb score rankings.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..5 = epilogue (TMEM -> registers -> global), one TMEM lane quarter each.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace nttt {
+
+constexpr int kBM = 128;      // UMMA_M
+constexpr int kBK = 64;       // bf16 elements per k-block = 128 bytes = one swizzle atom row
+constexpr int kUmmaK = 16;    // bf16
+constexpr int kGemmThreads = 192;
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a lost arrive traps (CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major, 128-byte swizzle: atoms of 8 rows x 128 B, SBO = 1024 B between 8-row groups, LBO unused
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                             // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                             // layout type: SWIZZLE_128B
+  return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn
+__host__ __device__ constexpr uint32_t umma_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the kernel: one CTA per 128 x BN output tile
+// ---------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct GemmSmem {
+  alignas(1024) __nv_bfloat16 a[STAGES][kBM * kBK];
+  alignas(1024) __nv_bfloat16 b[STAGES][BN * kBK];
+  alignas(8) uint64_t full[STAGES];
+  alignas(8) uint64_t empty[STAGES];
+  alignas(8) uint64_t acc_ready;
+  uint32_t tmem_base;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               float* __restrict__ D, int ldd, int M, int N, int num_k_blocks) {
+  extern __shared__ uint8_t smem_raw[];
+  auto& sm = *reinterpret_cast<GemmSmem<BN, STAGES>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
+  constexpr uint32_t kStageBytes = (kBM + BN) * kBK * sizeof(__nv_bfloat16);
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    mbar_init(&sm.acc_ready, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)),
+                 "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_acc = sm.tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&sm.empty[s], ph ^ 1);
+        mbar_expect_tx(&sm.full[s], kStageBytes);
+        tma_load_2d(sm.a[s], &map_a, &sm.full[s], kb * kBK, m0);
+        tma_load_2d(sm.b[s], &map_b, &sm.full[s], kb * kBK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(BN);
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&sm.full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = smem_u32(sm.a[s]), b_addr = smem_u32(sm.b[s]);
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          const uint64_t ad = umma_smem_desc(a_addr + k * kUmmaK * 2);
+          const uint64_t bd = umma_smem_desc(b_addr + k * kUmmaK * 2);
+          umma_f16(tmem_acc, ad, bd, idesc, (kb | k) != 0);
+        }
+        umma_commit(&sm.empty[s]);  // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(&sm.acc_ready);   // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    mbar_wait(&sm.acc_ready, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + q * 32 + lane;
+#pragma unroll
+    for (int cb = 0; cb < BN; cb += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + cb, r);
+      if (row < M) {
+        float* dst = D + (size_t)row * ldd + n0 + cb;
+        if (n0 + cb + 32 <= N && (ldd & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + cb + j < N) dst[j] = __uint_as_float(r[j]);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(kTmemCols));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host: tensor maps + launch
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// row-major bf16 [rows, k] with k contiguous; box = [box_rows, 64]
+static int make_map(CUtensorMap* map, const void* base, int rows, int k, int ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return NTTT_ECUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled");
+    return NTTT_ECUDA;
+  }
+  return NTTT_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, float* D, int ldd, int M, int N,
+                     int K, cudaStream_t s) {
+  CUtensorMap ma, mb;
+  int err = make_map(&ma, A, M, K, lda, kBM);
+  if (err) return err;
+  err = make_map(&mb, B, N, K, ldb, BN);
+  if (err) return err;
+  const size_t smem = sizeof(GemmSmem<BN, STAGES>) + 1024;
+  auto kern = gemm_tc_kernel<BN, STAGES>;
+  NTTT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(N, BN), ceil_div(M, kBM));
+  kern<<<grid, kGemmThreads, smem, s>>>(ma, mb, D, ldd, M, N, K / kBK);
+  NTTT_LAUNCH_CHECK();
+  return NTTT_OK;
+}
+
+// A [M, K] and B [N, K] bf16, K a multiple of 64, rows 16-byte aligned (lda, ldb multiples of 8)
+int launch_gemm_tc(const void* A, int lda, const void* B, int ldb, float* D, int ldd, int M, int N, int K,
+                   cudaStream_t s) {
+  if (M <= 0 || N <= 0) return NTTT_OK;
+  if (K <= 0 || K % kBK != 0 || lda % 8 != 0 || ldb % 8 != 0) return NTTT_EINVAL;
+  return launch_tc<64, 6>(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(B), ldb, D, ldd,
+                          M, N, K, s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// operand preparation: fp32 -> split bf16, three K-segments of width kp (zero padded)
+//   mode 0 (A operand): [hi | hi | lo]      mode 1 (B operand): [hi | lo | hi]
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+__global__ void __launch_bounds__(256)
+split_rows_kernel(const float* __restrict__ X, int ld, int rows, int k, int kp, int mode,
+                  __nv_bfloat16* __restrict__ out) {
+  const int r = blockIdx.y;
+  const float* src = X + (size_t)r * ld;
+  __nv_bfloat16* dst = out + (size_t)r * 3 * kp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kp; i += gridDim.x * blockDim.x) {
+    __nv_bfloat16 hi = __float2bfloat16_rn(0.0f), lo = hi;
+    if (i < k) split_bf16(src[i], hi, lo);
+    dst[i] = hi;
+    dst[kp + i] = mode == 0 ? hi : lo;
+    dst[2 * kp + i] = mode == 0 ? lo : hi;
+  }
+}
+
+// X [k, rows] (row-major, ld) -> out [rows, 3*kp]: transpose + split (for feat [E, C] -> [C, 3*Ep])
+__global__ void __launch_bounds__(256)
+split_transpose_kernel(const float* __restrict__ X, int ld, int rows, int k, int kp, int mode,
+                       __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int kk = k0 + j, rr = r0 + tx;
+    tile[j][tx] = (kk < k && rr < rows) ? X[(size_t)kk * ld + rr] : 0.0f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int rr = r0 + j, kk = k0 + tx;
+    if (rr < rows && kk < kp) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(tile[tx][j], hi, lo);
+      __nv_bfloat16* dst = out + (size_t)rr * 3 * kp;
+      dst[kk] = hi;
+      dst[kp + kk] = mode == 0 ? hi : lo;
+      dst[2 * kp + kk] = mode == 0 ? lo : hi;
+    }
+  }
+}
+
+int launch_split_rows(const float* X, int ld, int rows, int k, int kp, int mode, void* out, cudaStream_t s) {
+  if (rows <= 0) return NTTT_OK;
+  dim3 grid(ceil_div(kp, 256), rows);
+  split_rows_kernel<<<grid, 256, 0, s>>>(X, ld, rows, k, kp, mode, static_cast<__nv_bfloat16*>(out));
+  NTTT_LAUNCH_CHECK();
+  return NTTT_OK;
+}
+
+int launch_split_transpose(const float* X, int ld, int rows, int k, int kp, int mode, void* out, cudaStream_t s) {
+  if (rows <= 0) return NTTT_OK;
+  dim3 grid(ceil_div(kp, 32), ceil_div(rows, 32));
+  split_transpose_kernel<<<grid, 256, 0, s>>>(X, ld, rows, k, kp, mode, static_cast<__nv_bfloat16*>(out));
+  NTTT_LAUNCH_CHECK();
+  return NTTT_OK;
+}
+
+}  // namespace nttt

@@ -7,70 +7,6 @@
 namespace nttt {
 
 // ---------------------------------------------------------------------------------------------------
-// fp32 tiled GEMM on the CUDA cores (first correct path; the tcgen05 kernel in gemm_tc.cu replaces it
-// for the hot contractions).  C[M,N] = A[M,K] * op(B), op(B) = B[K,N] (kBT=false) or B[N,K]^T (kBT=true).
-// ---------------------------------------------------------------------------------------------------
-template <bool kBT>
-__global__ void __launch_bounds__(256)
-sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C,
-             int ldc, int M, int N, int K) {
-  constexpr int BM = 64, BN = 64, BK = 16;
-  __shared__ float sA[BK][BM + 4];
-  __shared__ float sB[BK][BN + 4];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += BK) {
-    for (int i = threadIdx.x; i < BM * BK; i += 256) {
-      const int m = i / BK, k = i % BK;
-      sA[k][m] = (m0 + m < M && k0 + k < K) ? A[(size_t)(m0 + m) * lda + k0 + k] : 0.0f;
-    }
-    if (kBT) {
-      for (int i = threadIdx.x; i < BN * BK; i += 256) {
-        const int n = i / BK, k = i % BK;
-        sB[k][n] = (n0 + n < N && k0 + k < K) ? B[(size_t)(n0 + n) * ldb + k0 + k] : 0.0f;
-      }
-    } else {
-      for (int i = threadIdx.x; i < BN * BK; i += 256) {
-        const int k = i / BN, n = i % BN;
-        sB[k][n] = (n0 + n < N && k0 + k < K) ? B[(size_t)(k0 + k) * ldb + n0 + n] : 0.0f;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sA[k][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = sB[k][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
-      if (m < M && n < N) C[(size_t)m * ldc + n] = acc[i][j];
-    }
-}
-
-int launch_sgemm(bool b_transposed, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N,
-                 int K, cudaStream_t s) {
-  if (M <= 0 || N <= 0) return NTTT_OK;
-  dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
-  if (b_transposed) sgemm_kernel<true><<<grid, 256, 0, s>>>(A, lda, B, ldb, C, ldc, M, N, K);
-  else sgemm_kernel<false><<<grid, 256, 0, s>>>(A, lda, B, ldb, C, ldc, M, N, K);
-  NTTT_LAUNCH_CHECK();
-  return NTTT_OK;
-}
-
-// ---------------------------------------------------------------------------------------------------
 // rows: x = sums / max(area,1)  (area==0 -> 1, matching_baseline_utils.py:887-888); x /= max(||x||, 1e-12)
 // one warp per row.
 // ---------------------------------------------------------------------------------------------------

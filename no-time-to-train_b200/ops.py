@@ -46,16 +46,20 @@ def context(device) -> int:
     return _ctx_by_device[idx]
 
 
-def threshold_pack(logits: torch.Tensor, thr: float = 0.0, off: float = 1.0):
-    """-> bits [n, h*w/32] int32 (bit pattern of uint32), area [n], box [n,4], stab [n,2], flags [n]."""
+def threshold_pack(logits: torch.Tensor, thr: float = 0.0, off: float = 1.0, out=None):
+    """-> bits [n, h*w/32] int32 (bit pattern of uint32), area [n], box [n,4], stab [n,2], flags [n].
+    `out` may carry the five preallocated outputs of an earlier call (no allocation inside a timed loop)."""
     _need(logits, torch.float32, "logits")
     n, h, w = logits.shape
     dev = logits.device
-    bits = torch.empty((n, h * w // 32), dtype=torch.int32, device=dev)
-    area = torch.empty((n,), dtype=torch.int32, device=dev)
-    box = torch.empty((n, 4), dtype=torch.int32, device=dev)
-    stab = torch.empty((n, 2), dtype=torch.int32, device=dev)
-    flags = torch.empty((n,), dtype=torch.int32, device=dev)
+    if out is not None:
+        bits, area, box, stab, flags = out
+    else:
+        bits = torch.empty((n, h * w // 32), dtype=torch.int32, device=dev)
+        area = torch.empty((n,), dtype=torch.int32, device=dev)
+        box = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        stab = torch.empty((n, 2), dtype=torch.int32, device=dev)
+        flags = torch.empty((n,), dtype=torch.int32, device=dev)
     lib = _lib.load()
     _lib.check(lib.nttt_threshold_pack(_ptr(logits), n, h, w, thr, off, _ptr(bits), _ptr(area), _ptr(box), _ptr(stab),
                                        _ptr(flags), _stream(dev)), "nttt_threshold_pack")
@@ -105,7 +109,7 @@ def similarity_top1(obj_feats: torch.Tensor, proto: torch.Tensor, want_sim: bool
     dev = obj_feats.device
     lib = _lib.load()
     sim = torch.empty((n, n_cls), dtype=torch.float32, device=dev) if want_sim else None
-    ws_bytes = 0 if want_sim else lib.nttt_similarity_workspace_bytes(n, c, n_cls)
+    ws_bytes = lib.nttt_similarity_workspace_bytes(n, c, n_cls)
     ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
     top_score = torch.empty((n,), dtype=torch.float32, device=dev)
     top_label = torch.empty((n,), dtype=torch.int32, device=dev)
