@@ -125,11 +125,15 @@ def semantic_ios(masks_bool: torch.Tensor, labels: torch.Tensor, obj_sim: torch.
     return ios
 
 
-def match_image(lr_masks, pred_ious, tar_feat, feats_ins_avg, cfg: StageConfig, ori_hw, timings=None):
+def match_image(lr_masks, pred_ious, tar_feat, feats_ins_avg, cfg: StageConfig, ori_hw, timings=None,
+                override=None):
     """The matching stage of `forward_test(with_negative=False)`
     (`Sam2MatchingBaseline_noAMG.py:582-683`), from the `_forward_sam` seam to the output dict.
 
-    `timings`, if a dict, receives per-section wall-clock seconds (CPU baseline reporting)."""
+    `timings`, if a dict, receives per-section wall-clock seconds (CPU baseline reporting).
+    `override`, if a dict with `sim` and `obj_feats`, replaces the pooled features / similarities so that a
+    test can check everything downstream of the float contractions exactly (label near-ties otherwise
+    cascade through NMS)."""
     import time
 
     def lap(name, t0):
@@ -144,6 +148,8 @@ def match_image(lr_masks, pred_ious, tar_feat, feats_ins_avg, cfg: StageConfig, 
     feat_pc = upsample_features(tar_feat, cfg.enc_hw, lr_masks.shape[-2:])
     t = lap("process_sam_masks", t)
     sim, obj_feats = pool_and_score(feat_pc, masks_bool, feats_ins_avg)
+    if override is not None:
+        sim, obj_feats = override["sim"], override["obj_feats"]
     t = lap("pool_and_score", t)
     scores_all, labels, k = select_labels(sim, cfg.cls_num_per_mask)
     t = lap("topk", t)
