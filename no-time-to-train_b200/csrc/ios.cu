@@ -12,13 +12,26 @@ namespace nttt {
 
 constexpr int kIosThreads = 256;
 
-// one CTA per selected mask i; warps stride over candidate partners j.
+// one CTA per selected mask i; warps stride over candidate partners j.  The per-partner metadata (label, area,
+// box, rect) is staged in shared memory once per CTA so the partner loop never waits on dependent global loads.
+struct IosMeta {
+  int4 box;
+  int4 rect;
+  int label;
+  int area;
+  int src;
+  int pad;
+};
+
+template <bool kStaged>
 __global__ void __launch_bounds__(kIosThreads)
 mask_ios_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restrict__ rect,
                 const int32_t* __restrict__ area_full, const int32_t* __restrict__ box_full,
                 const int32_t* __restrict__ sel, const int32_t* __restrict__ n_sel, int max_sel, int oh, int ow,
                 const int32_t* __restrict__ labels, const float* __restrict__ obj_feats, int c,
                 float* __restrict__ ios, int32_t* __restrict__ inter_out) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  IosMeta* s_meta = reinterpret_cast<IosMeta*>(s_raw);
   __shared__ float s_best[kIosThreads / 32];
   const int i = blockIdx.x;
   const int nsel = min(*n_sel, max_sel);
@@ -26,37 +39,48 @@ mask_ios_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restric
   const int lane = lane_id(), warp = warp_id();
   constexpr int kWarps = kIosThreads / 32;
   const int ow_words = (ow + 31) >> 5;
-  const int src_i = sel[i];
-  const int lab_i = labels[src_i];
-  const int area_i = area_full[i];
-  const int4 bi = reinterpret_cast<const int4*>(box_full)[i];
-  const int4 ri = reinterpret_cast<const int4*>(rect)[i];
+  auto load_meta = [&](int j) {
+    IosMeta m;
+    m.src = sel[j];
+    m.label = labels[m.src];
+    m.area = area_full[j];
+    m.box = reinterpret_cast<const int4*>(box_full)[j];
+    m.rect = reinterpret_cast<const int4*>(rect)[j];
+    m.pad = 0;
+    return m;
+  };
+  if (kStaged) {
+    for (int j = threadIdx.x; j < nsel; j += kIosThreads) s_meta[j] = load_meta(j);
+    __syncthreads();
+  }
+  const IosMeta me = kStaged ? s_meta[i] : load_meta(i);
   const uint32_t* mi = bits_full + (size_t)i * oh * ow_words;
-  const float* fi = obj_feats + (size_t)src_i * c;
-  const float area_f = (float)area_i;
+  const float* fi = obj_feats + (size_t)me.src * c;
+  const float area_f = (float)me.area;
 
   float best = 0.0f;  // the zeroed diagonal takes part in the row max (area_i > 0 case)
   for (int j = warp; j < nsel; j += kWarps) {
     if (j == i) continue;
-    const int src_j = sel[j];
-    if (labels[src_j] != lab_i) continue;
+    int lab_j;
+    if (kStaged) lab_j = s_meta[j].label; else lab_j = labels[sel[j]];
+    if (lab_j != me.label) continue;
+    const IosMeta mj = kStaged ? s_meta[j] : load_meta(j);
     int inter = 0;
-    if (area_i > 0 && area_full[j] > 0) {
-      const int4 bj = reinterpret_cast<const int4*>(box_full)[j];
+    if (me.area > 0 && mj.area > 0) {
       // inclusive boxes -> overlap window in pixels
-      const int x0 = max(bi.x, bj.x), x1 = min(bi.z, bj.z), y0 = max(bi.y, bj.y), y1 = min(bi.w, bj.w);
+      const int x0 = max(me.box.x, mj.box.x), x1 = min(me.box.z, mj.box.z);
+      const int y0 = max(me.box.y, mj.box.y), y1 = min(me.box.w, mj.box.w);
       if (x0 <= x1 && y0 <= y1) {
-        const int4 rj = reinterpret_cast<const int4*>(rect)[j];
-        const int wlo = max(max(ri.z, rj.z), x0 >> 5), whi = min(min(ri.w, rj.w), (x1 >> 5) + 1);
-        const int ylo = max(max(ri.x, rj.x), y0), yhi = min(min(ri.y, rj.y), y1 + 1);
-        const uint32_t* mj = bits_full + (size_t)j * oh * ow_words;
+        const int wlo = max(max(me.rect.z, mj.rect.z), x0 >> 5), whi = min(min(me.rect.w, mj.rect.w), (x1 >> 5) + 1);
+        const int ylo = max(max(me.rect.x, mj.rect.x), y0), yhi = min(min(me.rect.y, mj.rect.y), y1 + 1);
+        const uint32_t* pj = bits_full + (size_t)j * oh * ow_words;
         const int nw = whi - wlo;
         if (nw > 0 && yhi > ylo) {
           const int total = (yhi - ylo) * nw;
           for (int t = lane; t < total; t += 32) {
             const int y = ylo + t / nw, w = wlo + t % nw;
             const size_t o = (size_t)y * ow_words + w;
-            inter += __popc(mi[o] & mj[o]);
+            inter += __popc(mi[o] & pj[o]);
           }
         }
       }
@@ -64,7 +88,7 @@ mask_ios_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restric
     inter = warp_sum(inter);
     if (inter_out && lane == 0) inter_out[(size_t)i * max_sel + j] = inter;
     if (inter > 0) {
-      const float* fj = obj_feats + (size_t)src_j * c;
+      const float* fj = obj_feats + (size_t)mj.src * c;
       float dot = 0.0f;
       for (int q = lane; q < c; q += 32) dot = fmaf(fi[q], fj[q], dot);
       dot = warp_sum(dot);
@@ -80,7 +104,7 @@ mask_ios_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restric
     float b = s_best[0];
     for (int w = 1; w < kWarps; ++w) b = fmaxf(b, s_best[w]);
     // empty full-res mask: 0/0 on the diagonal -> NaN, and torch.max propagates it
-    ios[i] = area_i == 0 ? __int_as_float(0x7fc00000) : b;
+    ios[i] = me.area == 0 ? __int_as_float(0x7fc00000) : b;
   }
 }
 
@@ -89,8 +113,16 @@ int launch_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_
                     const float* obj_feats, int c, float* ios, int32_t* inter_out, cudaStream_t s) {
   if (max_sel <= 0) return NTTT_OK;
   if (inter_out) NTTT_CUDA(cudaMemsetAsync(inter_out, 0, sizeof(int32_t) * (size_t)max_sel * max_sel, s));
-  mask_ios_kernel<<<max_sel, kIosThreads, 0, s>>>(bits_full, rect, area_full, box_full, sel, n_sel, max_sel, oh, ow,
-                                                  labels, obj_feats, c, ios, inter_out);
+  const size_t smem = sizeof(IosMeta) * (size_t)max_sel;
+  if (smem <= 160 * 1024) {
+    if (smem > 48 * 1024)
+      NTTT_CUDA(cudaFuncSetAttribute(mask_ios_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mask_ios_kernel<true><<<max_sel, kIosThreads, smem, s>>>(bits_full, rect, area_full, box_full, sel, n_sel, max_sel,
+                                                            oh, ow, labels, obj_feats, c, ios, inter_out);
+  } else {
+    mask_ios_kernel<false><<<max_sel, kIosThreads, 0, s>>>(bits_full, rect, area_full, box_full, sel, n_sel, max_sel,
+                                                          oh, ow, labels, obj_feats, c, ios, inter_out);
+  }
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }

@@ -84,62 +84,74 @@ nms_mask_kernel(const int32_t* __restrict__ box, const int32_t* __restrict__ lab
   mask[(size_t)i * row_words + cw] = bits;
 }
 
-// greedy scan over the sorted list, one warp.  32 boxes per step: the in-chunk dependencies are resolved
-// on the diagonal word, then the rows of the kept boxes are OR-ed into the removed set.
-constexpr int kScanMaxWords = 8;  // per lane -> n <= 8192
-__global__ void __launch_bounds__(32)
+// Greedy scan over the sorted list by one CTA of 32 warps, 32 boxes (one chunk) per step:
+//   warp 0 resolves the in-chunk dependencies on the diagonal word and emits the survivors,
+//   then warp j ORs the suppression row of survivor j into the shared `removed` set (all rows in parallel).
+// The bit matrix is staged in shared memory when it fits (n <= ~1100), otherwise read from L2.
+constexpr int kScanThreads = 1024;
+constexpr int kScanMaxN = 8192;
+
+template <bool kStaged>
+__global__ void __launch_bounds__(kScanThreads)
 nms_scan_kernel(const uint32_t* __restrict__ mask, int row_words, const int32_t* __restrict__ order,
                 const float* __restrict__ top_score, int n, int max_keep, int32_t* __restrict__ keep,
                 int32_t* __restrict__ n_keep, int32_t* __restrict__ sel, int32_t* __restrict__ n_sel) {
-  const int lane = threadIdx.x;
-  uint32_t removed[kScanMaxWords];
-#pragma unroll
-  for (int q = 0; q < kScanMaxWords; ++q) removed[q] = 0;
-  int kept = 0, selected = 0;
-  for (int c = 0; c < row_words && kept < max_keep; ++c) {
-    // removed word of this chunk lives in lane (c & 31), slot (c >> 5)
-    uint32_t cur = 0;
-#pragma unroll
-    for (int q = 0; q < kScanMaxWords; ++q)
-      if (q == (c >> 5)) cur = __shfl_sync(kFull, removed[q], c & 31);
-    const int i = c * 32 + lane;
-    const uint32_t diag = i < n ? mask[(size_t)i * row_words + c] : 0u;
-    const int n_here = min(32, n - c * 32);
-    uint32_t keepbits = 0;
-    for (int b = 0; b < n_here; ++b) {
-      const uint32_t d = __shfl_sync(kFull, diag, b);
-      if (!((cur >> b) & 1u)) { keepbits |= 1u << b; cur |= d; }
+  extern __shared__ uint32_t s_dyn[];
+  __shared__ uint32_t s_removed[kScanMaxN / 32];
+  __shared__ uint32_t s_keepbits;
+  __shared__ int s_stop;
+  const int lane = lane_id(), warp = warp_id();
+  const uint32_t* M = mask;
+  if (kStaged) {
+    const int total = n * row_words;
+    for (int i = threadIdx.x; i < total; i += kScanThreads) s_dyn[i] = mask[i];
+    M = s_dyn;
+  }
+  for (int i = threadIdx.x; i < row_words; i += kScanThreads) s_removed[i] = 0;
+  if (threadIdx.x == 0) s_stop = 0;
+  __syncthreads();
+  int kept = 0, selected = 0;  // tracked by warp 0
+  for (int c = 0; c < row_words; ++c) {
+    if (warp == 0) {
+      uint32_t cur = s_removed[c];
+      const int i = c * 32 + lane;
+      const uint32_t diag = i < n ? M[(size_t)i * row_words + c] : 0u;
+      const int n_here = min(32, n - c * 32);
+      uint32_t keepbits = 0;
+      for (int b = 0; b < n_here; ++b) {
+        const uint32_t d = __shfl_sync(kFull, diag, b);
+        if (!((cur >> b) & 1u)) { keepbits |= 1u << b; cur |= d; }
+      }
+      int cnt = __popc(keepbits);
+      if (kept + cnt > max_keep) {  // truncate to max_keep (= out_num)
+        int excess = kept + cnt - max_keep;
+        while (excess--) keepbits &= ~(1u << (31 - __clz(keepbits)));
+        cnt = max_keep - kept;
+      }
+      const bool mine = (keepbits >> lane) & 1u;
+      const int oi = (i < n) ? order[i] : 0;
+      const bool pos = mine && (top_score[oi] > 0.0f);
+      const uint32_t posbits = __ballot_sync(kFull, pos);
+      if (mine) keep[kept + __popc(keepbits & ((1u << lane) - 1u))] = oi;
+      if (pos) sel[selected + __popc(posbits & ((1u << lane) - 1u))] = oi;
+      kept += cnt;
+      selected += __popc(posbits);
+      if (lane == 0) { s_keepbits = keepbits; s_stop = kept >= max_keep; }
     }
-    // truncate to max_keep
-    int cnt = __popc(keepbits);
-    if (kept + cnt > max_keep) {
-      int excess = kept + cnt - max_keep;
-      while (excess--) keepbits &= ~(1u << (31 - __clz(keepbits)));
-      cnt = max_keep - kept;
-    }
-    // emit kept indices (+ positive-score compaction), in sorted order
-    const bool mine = (keepbits >> lane) & 1u;
-    const int oi = (i < n) ? order[i] : 0;
-    const bool pos = mine && (top_score[oi] > 0.0f);
-    const uint32_t posbits = __ballot_sync(kFull, pos);
-    if (mine) keep[kept + __popc(keepbits & ((1u << lane) - 1u))] = oi;
-    if (pos) sel[selected + __popc(posbits & ((1u << lane) - 1u))] = oi;
-    kept += cnt;
-    selected += __popc(posbits);
-    // OR the rows of kept boxes into the removed set (words > c only matter)
-    uint32_t kb = keepbits;
-    while (kb) {
-      const int b = __ffs(kb) - 1;
-      kb &= kb - 1;
-      const uint32_t* row = mask + (size_t)(c * 32 + b) * row_words;
-#pragma unroll
-      for (int q = 0; q < kScanMaxWords; ++q) {
-        const int w = q * 32 + lane;
-        if (w > c && w < row_words) removed[q] |= row[w];
+    __syncthreads();
+    const uint32_t kb = s_keepbits;
+    const int stop = s_stop;
+    if (stop) break;
+    if ((kb >> warp) & 1u) {
+      const uint32_t* row = M + (size_t)(c * 32 + warp) * row_words;
+      for (int w = c + 1 + lane; w < row_words; w += 32) {
+        const uint32_t v = row[w];
+        if (v) atomicOr(&s_removed[w], v);
       }
     }
+    __syncthreads();
   }
-  if (lane == 0) { *n_keep = kept; *n_sel = selected; }
+  if (threadIdx.x == 0) { *n_keep = kept; *n_sel = selected; }
 }
 
 size_t nms_workspace_bytes(int n) {
@@ -155,7 +167,7 @@ int launch_box_nms(const int32_t* box, const float* nms_scores, const int32_t* l
     NTTT_CUDA(cudaMemsetAsync(n_sel, 0, sizeof(int32_t), s));
     return NTTT_OK;
   }
-  if (n > 32 * 32 * kScanMaxWords) return NTTT_EUNSUPPORTED;
+  if (n > kScanMaxN) return NTTT_EUNSUPPORTED;
   if (ws_bytes < nms_workspace_bytes(n)) return NTTT_EWORKSPACE;
   int32_t* order = static_cast<int32_t*>(ws);
   uint32_t* mask = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + align_up(sizeof(int32_t) * (size_t)n, 256));
@@ -170,7 +182,16 @@ int launch_box_nms(const int32_t* box, const float* nms_scores, const int32_t* l
   dim3 grid(ceil_div(row_words, 8), ceil_div(n, 32));
   nms_mask_kernel<<<grid, dim3(32, 8), 0, s>>>(box, labels, order, n, thr, mask, row_words);
   NTTT_LAUNCH_CHECK();
-  nms_scan_kernel<<<1, 32, 0, s>>>(mask, row_words, order, top_score, n, max_keep, keep, n_keep, sel, n_sel);
+  const size_t stage_bytes = sizeof(uint32_t) * (size_t)n * row_words;
+  if (stage_bytes <= 160 * 1024) {
+    NTTT_CUDA(cudaFuncSetAttribute(nms_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)stage_bytes));
+    nms_scan_kernel<true><<<1, kScanThreads, stage_bytes, s>>>(mask, row_words, order, top_score, n, max_keep, keep,
+                                                              n_keep, sel, n_sel);
+  } else {
+    nms_scan_kernel<false><<<1, kScanThreads, 0, s>>>(mask, row_words, order, top_score, n, max_keep, keep, n_keep,
+                                                      sel, n_sel);
+  }
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }
