@@ -87,8 +87,8 @@ int nttt_threshold_pack(const float* logits, int n, int h, int w, float thr, flo
  * nttt_pool_normalize contracts it with feat [E, C] on the tensor cores (split-bf16 operands, fp32
  * accumulate), divides by the area (0 -> 1) and L2-normalises (eps 1e-12).
  */
-int nttt_project_masks(nttt_ctx* ctx, const uint32_t* bits, int n, int h, int w, int eh, int ew,
-                       float* proj /* [n, eh*ew] */, void* stream);
+int nttt_project_masks(nttt_ctx* ctx, const uint32_t* bits, const int32_t* box /* [n,4] from threshold_pack */,
+                       int n, int h, int w, int eh, int ew, float* proj /* [n, eh*ew] */, void* stream);
 size_t nttt_pool_workspace_bytes(int n, int e, int c);
 int nttt_pool_normalize(nttt_ctx* ctx, const float* proj, const float* feat /* [e, c] */,
                         const int32_t* area, int n, int e, int c, float* obj_feats /* [n, c] */,

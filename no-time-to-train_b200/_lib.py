@@ -45,7 +45,7 @@ SIGNATURES = {
     "nttt_ctx_create": (c_int, [POINTER(c_void_p), c_int]),
     "nttt_ctx_destroy": (None, [c_void_p]),
     "nttt_threshold_pack": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P]),
-    "nttt_project_masks": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "nttt_project_masks": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "nttt_pool_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "nttt_pool_normalize": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "nttt_proto_prepare": (c_int, [_P, c_int, c_int, c_int, _P, _P]),

@@ -10,8 +10,9 @@ namespace nttt {
 // launchers implemented in the kernel translation units
 int launch_lowres_pack(const float*, int, int, int, float, float, uint32_t*, int32_t*, int32_t*, int32_t*, int32_t*,
                        cudaStream_t);
-int launch_project_masks(const AxisTable&, const AxisTable&, const uint32_t*, int, int, int, int, int, float*, int,
-                         cudaStream_t);
+int launch_project_masks(const AxisTable&, const AxisTable&, const uint32_t*, const int32_t*, int, int, int, int, int,
+                         void*, int, bool, cudaStream_t);
+int launch_normalize_split(const float*, const int32_t*, int, int, int, float*, void*, cudaStream_t);
 int launch_gemm_tc(const void*, int, const void*, int, float*, int, int, int, int, cudaStream_t);
 int launch_split_rows(const float*, int, int, int, int, int, void*, cudaStream_t);
 int launch_split_transpose(const float*, int, int, int, int, int, void*, cudaStream_t);
@@ -60,21 +61,37 @@ inline int pad64(int k) { return (k + 63) / 64 * 64; }
 
 // sums[n, c] = proj[n, e] * feat[e, c] on the tensor cores (split-bf16, K' = 3 * pad64(e))
 // scratch: a_split [n, 3*ep] bf16, b_split [c, 3*ep] bf16
+// (proj == nullptr: a_split already holds the split projection, written by project_masks_kernel<true>)
 static int pool_contract(const float* proj, const float* feat, int n, int e, int c, float* sums, void* a_split,
                          void* b_split, cudaStream_t s) {
   const int ep = pad64(e);
-  int err = launch_split_rows(proj, e, n, e, ep, 0, a_split, s);
+  int err = proj ? launch_split_rows(proj, e, n, e, ep, 0, a_split, s) : NTTT_OK;
   if (err) return err;
   err = launch_split_transpose(feat, c, c, e, ep, 1, b_split, s);
   if (err) return err;
   return launch_gemm_tc(a_split, 3 * ep, b_split, 3 * ep, sums, c, n, c, 3 * ep, s);
 }
 
+// rows of `sums` -> /area -> L2-normalise -> obj_feats (+ split-bf16 copy when the vector path applies).
+// Returns through *split_done whether a_split now holds the similarity GEMM's A operand.
+static int normalize_rows(const float* sums, const int32_t* area, int n, int c, float* obj_feats, void* a_split,
+                          bool* split_done, cudaStream_t s) {
+  *split_done = a_split && launch_normalize_split(sums, area, n, c, pad64(c), obj_feats, a_split, s) == 1;
+  if (*split_done) return NTTT_OK;
+  return launch_normalize_rows(sums, area, n, c, obj_feats, s);
+}
+
+// the scatter tables hold kMaxScatter weights per encoder cell: enough while out/in <= ~11
+static bool projection_supported(int in_size, int out_size) {
+  return in_size > 0 && 2 * ((out_size + in_size - 1) / in_size) + 2 <= kMaxScatter;
+}
+
 // sim[n, n_cls] = obj_feats[n, c] * proto[n_cls, c]^T
+// (a_ready: a_split already holds the split obj_feats, written by normalize_split_kernel)
 static int sim_contract(const float* obj_feats, const float* proto, int n, int c, int n_cls, float* sim, void* a_split,
-                        void* b_split, cudaStream_t s) {
+                        void* b_split, bool a_ready, cudaStream_t s) {
   const int cp = pad64(c);
-  int err = launch_split_rows(obj_feats, c, n, c, cp, 0, a_split, s);
+  int err = a_ready ? NTTT_OK : launch_split_rows(obj_feats, c, n, c, cp, 0, a_split, s);
   if (err) return err;
   err = launch_split_rows(proto, c, n_cls, c, cp, 1, b_split, s);
   if (err) return err;
@@ -204,10 +221,11 @@ int nttt_threshold_pack(const float* logits, int n, int h, int w, float thr, flo
   return launch_lowres_pack(logits, n, h, w, thr, off, bits, area, box, stab, flags, (cudaStream_t)stream);
 }
 
-int nttt_project_masks(nttt_ctx* ctx, const uint32_t* bits, int n, int h, int w, int eh, int ew, float* proj,
-                       void* stream) {
+int nttt_project_masks(nttt_ctx* ctx, const uint32_t* bits, const int32_t* box, int n, int h, int w, int eh, int ew,
+                       float* proj, void* stream) {
   if (!ctx || n < 0 || h <= 0 || w <= 0 || eh <= 0 || ew <= 0) return NTTT_EINVAL;
-  if (n > 0 && (!bits || !proj)) return NTTT_EINVAL;
+  if (n > 0 && (!bits || !box || !proj)) return NTTT_EINVAL;
+  if (!projection_supported(ew, w) || !projection_supported(eh, h)) return NTTT_EUNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   ++ctx->epoch;
   AxisTable tx, ty;
@@ -215,7 +233,7 @@ int nttt_project_masks(nttt_ctx* ctx, const uint32_t* bits, int n, int h, int w,
   if (err) return err;
   err = ctx->axis(eh, h, s, &ty);
   if (err) return err;
-  return launch_project_masks(tx, ty, bits, n, h, w, eh, ew, proj, eh * ew, s);
+  return launch_project_masks(tx, ty, bits, box, n, h, w, eh, ew, proj, eh * ew, false, s);
 }
 
 size_t nttt_pool_workspace_bytes(int n, int e, int c) {
@@ -237,7 +255,8 @@ int nttt_pool_normalize(nttt_ctx* ctx, const float* proj, const float* feat, con
   char* b_split = a_split + align_up(2 * (size_t)n * 3 * pad64(e), 256);
   int err = pool_contract(proj, feat, n, e, c, sums, a_split, b_split, s);
   if (err) return err;
-  return launch_normalize_rows(sums, area, n, c, obj_feats, s);
+  bool split_done;
+  return normalize_rows(sums, area, n, c, obj_feats, nullptr, &split_done, s);
 }
 
 int nttt_proto_prepare(const float* feats_ins_avg, int n_cls, int shots, int c, float* proto, void* stream) {
@@ -263,7 +282,7 @@ int nttt_similarity_top1(nttt_ctx* ctx, const float* obj_feats, const float* pro
   float* simbuf = sim ? sim : reinterpret_cast<float*>(ws);
   char* a_split = ws + align_up(sizeof(float) * (size_t)n * n_cls, 256);
   char* b_split = a_split + align_up(2 * (size_t)n * 3 * pad64(c), 256);
-  int err = sim_contract(obj_feats, proto, n, c, n_cls, simbuf, a_split, b_split, s);
+  int err = sim_contract(obj_feats, proto, n, c, n_cls, simbuf, a_split, b_split, false, s);
   if (err) return err;
   return launch_top1(simbuf, n_cls, n, n_cls, top_score, top_label, s);
 }
@@ -465,11 +484,14 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   NTTT_STEP(launch_lowres_pack(a->logits, n, a->lr_h, a->lr_w, 0.0f, 1.0f, L.bits_lr, L.area_lr, L.box_lr, L.stab,
                                L.flags, s));
   // a6/a7: projection + pooling contraction + normalisation
-  NTTT_STEP(launch_project_masks(px, py, L.bits_lr, n, a->lr_h, a->lr_w, a->eh, a->ew, L.proj, e, s));
-  NTTT_STEP(pool_contract(L.proj, a->tar_feat, n, e, a->c, L.sums, L.a_split, L.b_split, s));
-  NTTT_STEP(launch_normalize_rows(L.sums, L.area_lr, n, a->c, obj_feats, s));
+  if (!projection_supported(a->ew, a->lr_w) || !projection_supported(a->eh, a->lr_h)) return NTTT_EUNSUPPORTED;
+  NTTT_STEP(launch_project_masks(px, py, L.bits_lr, L.box_lr, n, a->lr_h, a->lr_w, a->eh, a->ew, L.a_split, pad64(e),
+                                 true, s));
+  NTTT_STEP(pool_contract(nullptr, a->tar_feat, n, e, a->c, L.sums, L.a_split, L.b_split, s));
+  bool a_ready = false;
+  NTTT_STEP(normalize_rows(L.sums, L.area_lr, n, a->c, obj_feats, L.a_split, &a_ready, s));
   // a7/a8: similarity + top-1
-  NTTT_STEP(sim_contract(obj_feats, a->proto, n, a->c, a->n_cls, sim, L.a_split, L.b_split, s));
+  NTTT_STEP(sim_contract(obj_feats, a->proto, n, a->c, a->n_cls, sim, L.a_split, L.b_split, a_ready, s));
   NTTT_STEP(launch_top1(sim, a->n_cls, n, a->n_cls, L.top_score, L.top_label, s));
   // a10/a11
   NTTT_STEP(launch_box_nms(L.box_lr, a->pred_ious, L.top_label, L.top_score, n, a->nms_thr, max_sel, L.keep,

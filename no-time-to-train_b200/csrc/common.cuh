@@ -76,7 +76,12 @@ struct AxisTable {
   int32_t* t_lo = nullptr;   // [in]
   int32_t* t_len = nullptr;  // [in]
   float* t_w = nullptr;      // [in, kMaxScatter]
+  // output coordinates grouped into runs (<= kGrpMax long) that share the same input span (xmin, xsize):
+  // rows of one group read the same input rows, so the horizontal pass and the footprint test are shared
+  int32_t* grp_of = nullptr;     // [out]  group index of each output coordinate
+  int32_t* grp_start = nullptr;  // [out + 1] first coordinate of each group, grp_start[n_groups] = out
 };
+constexpr int kGrpMax = 4;
 constexpr int kMaxScatter = 24;
 
 int aa_max_taps(int in_size, int out_size);

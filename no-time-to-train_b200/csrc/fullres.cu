@@ -24,6 +24,7 @@ struct UpTables {
   const int32_t* ymin; const int32_t* ysize; const float* wy; int ty;
   const int32_t* x_tlo; const int32_t* x_tlen;  // input col -> output range
   const int32_t* y_tlo; const int32_t* y_tlen;  // input row -> output range
+  const int32_t* y_grp_of; const int32_t* y_grp_start;  // output rows grouped by identical input span
 };
 
 // acc = s0*w0; acc = fma(s_j, w_j, acc)
@@ -36,6 +37,7 @@ __device__ __forceinline__ float aa_dot(const float* __restrict__ src, int strid
 // scratch per mask (zero-initialised by the launcher): {area, maxx+1, maxy+1, BIG-minx, BIG-miny, done}
 constexpr int kScratchInts = 8;
 constexpr int kBig = 1 << 30;
+constexpr int kTapsReg = 4;  // footprints of up to 4 input rows keep their horizontal-pass values in registers
 
 __global__ void __launch_bounds__(kUpThreads)
 upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restrict__ bits_lr,
@@ -77,19 +79,24 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
   __syncthreads();
 
   int area = 0, minx = kBig, maxx = -1, miny = kBig, maxy = -1;
-  for (int y = r0 + blockIdx.x * kWarps + warp; y < r1; y += kUpSplit * kWarps) {
-    const int ry0 = t.ymin[y], rys = t.ysize[y];
-    const float* wy = t.wy + (size_t)y * t.ty;
+  const int g0 = r1 > r0 ? t.y_grp_of[r0] : 0;
+  const int g1 = r1 > r0 ? t.y_grp_of[r1 - 1] + 1 : 0;
+  for (int g = g0 + blockIdx.x * kWarps + warp; g < g1; g += kUpSplit * kWarps) {
+    // rows [ya, yb) of this group share the input rows [ry0, ry0 + rys)
+    const int ya = max(t.y_grp_start[g], r0), yb = min(t.y_grp_start[g + 1], r1);
+    const int nrows = yb - ya;
+    const int ry0 = t.ymin[ya], rys = t.ysize[ya];
     for (int wbase = w0; wbase < w1; wbase += 32) {
       const int wi = wbase + lane;
       const bool active = wi < w1;
-      uint32_t word = 0;
+      uint32_t words[kGrpMax];
+#pragma unroll
+      for (int j = 0; j < kGrpMax; ++j) words[j] = 0;
       bool mixed = false;
-      uint32_t valid = 0;
       if (active) {
         const int x0 = wi << 5;
         const int x1 = min(x0 + 31, ow - 1);
-        valid = (x1 - x0 == 31) ? 0xffffffffu : ((1u << (x1 - x0 + 1)) - 1u);
+        const uint32_t valid = (x1 - x0 == 31) ? 0xffffffffu : ((1u << (x1 - x0 + 1)) - 1u);
         const int c0 = t.xmin[x0];
         const int c1 = t.xmin[x1] + t.xsize[x1];  // exclusive
         bool all0 = true, all1 = true;
@@ -103,35 +110,69 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
             all1 = all1 && (v == m);
           }
         }
-        if (all0) word = 0;
-        else if (all1 && safe) word = valid;
-        else mixed = true;
+        if (all1 && safe && !all0) {
+#pragma unroll
+          for (int j = 0; j < kGrpMax; ++j) words[j] = valid;
+        } else if (!all0) {
+          mixed = true;
+        }
       }
       uint32_t todo = __ballot_sync(kFull, mixed);
       while (todo) {
         const int src_lane = __ffs(todo) - 1;
         todo &= todo - 1;
         const int x = ((wbase + src_lane) << 5) + lane;
-        bool bit = false;
-        if (x < ow) {
-          const int cx = t.xmin[x], cs = t.xsize[x];
-          const float* wx = t.wx + (size_t)x * t.tx;
-          const float* p = src + (size_t)ry0 * iw + cx;
-          float acc = __fmul_rn(aa_dot(p, 1, wx, cs), __ldg(wy));
-          for (int r = 1; r < rys; ++r) acc = __fmaf_rn(aa_dot(p + (size_t)r * iw, 1, wx, cs), __ldg(wy + r), acc);
-          bit = acc > 0.0f;
+        const bool inb = x < ow;
+        const int cx = inb ? t.xmin[x] : 0, cs = inb ? t.xsize[x] : 1;
+        const float* wx = t.wx + (size_t)(inb ? x : 0) * t.tx;
+        const float* p = src + (size_t)ry0 * iw + cx;
+        if (rys <= kTapsReg) {
+          // horizontal pass once per group, vertical pass per row
+          float T[kTapsReg];
+#pragma unroll
+          for (int r = 0; r < kTapsReg; ++r) T[r] = (r < rys && inb) ? aa_dot(p + (size_t)r * iw, 1, wx, cs) : 0.0f;
+#pragma unroll
+          for (int j = 0; j < kGrpMax; ++j) {
+            if (j < nrows) {
+              const float* wy = t.wy + (size_t)(ya + j) * t.ty;
+              float acc = __fmul_rn(T[0], __ldg(wy));
+#pragma unroll
+              for (int r = 1; r < kTapsReg; ++r)
+                if (r < rys) acc = __fmaf_rn(T[r], __ldg(wy + r), acc);
+              const uint32_t res = __ballot_sync(kFull, inb && acc > 0.0f);
+              if (lane == src_lane) words[j] = res;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < kGrpMax; ++j) {
+            if (j < nrows) {
+              const float* wy = t.wy + (size_t)(ya + j) * t.ty;
+              float acc = 0.0f;
+              if (inb) {
+                acc = __fmul_rn(aa_dot(p, 1, wx, cs), __ldg(wy));
+                for (int r = 1; r < rys; ++r) acc = __fmaf_rn(aa_dot(p + (size_t)r * iw, 1, wx, cs), __ldg(wy + r), acc);
+              }
+              const uint32_t res = __ballot_sync(kFull, inb && acc > 0.0f);
+              if (lane == src_lane) words[j] = res;
+            }
+          }
         }
-        const uint32_t res = __ballot_sync(kFull, bit);
-        if (lane == src_lane) word = res;
       }
       if (active) {
-        dst[(size_t)y * ow_words + wi] = word;
-        if (word) {
-          area += __popc(word);
-          minx = min(minx, (wi << 5) + __ffs(word) - 1);
-          maxx = max(maxx, (wi << 5) + 31 - __clz(word));
-          miny = min(miny, y);
-          maxy = max(maxy, y);
+#pragma unroll
+        for (int j = 0; j < kGrpMax; ++j) {
+          if (j < nrows) {
+            const uint32_t word = words[j];
+            dst[(size_t)(ya + j) * ow_words + wi] = word;
+            if (word) {
+              area += __popc(word);
+              minx = min(minx, (wi << 5) + __ffs(word) - 1);
+              maxx = max(maxx, (wi << 5) + 31 - __clz(word));
+              miny = min(miny, ya + j);
+              maxy = max(maxy, ya + j);
+            }
+          }
         }
       }
     }
@@ -179,7 +220,8 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
   if (smem > 48 * 1024)
     NTTT_CUDA(cudaFuncSetAttribute(upsample_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   NTTT_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int32_t) * kScratchInts * (size_t)max_sel, s));
-  UpTables t{tx.xmin, tx.xsize, tx.w, tx.taps, ty.xmin, ty.xsize, ty.w, ty.taps, tx.t_lo, tx.t_len, ty.t_lo, ty.t_len};
+  UpTables t{tx.xmin, tx.xsize, tx.w, tx.taps, ty.xmin, ty.xsize, ty.w, ty.taps, tx.t_lo, tx.t_len, ty.t_lo, ty.t_len,
+             ty.grp_of, ty.grp_start};
   dim3 grid(kUpSplit, max_sel);
   upsample_pack_kernel<<<grid, kUpThreads, smem, s>>>(logits, bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel,
                                                       oh, ow, t, bits_full, rect, area_full, box_full, scratch);

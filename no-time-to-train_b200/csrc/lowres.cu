@@ -3,6 +3,8 @@
 //
 // Reference: Sam2MatchingBaseline_noAMG.py:548-549 (lr_masks > 0), :551-558 (feature upsample),
 // sam2/utils/amg.py:158-178 (stability), :305-348 (boxes).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace nttt {
@@ -171,6 +173,20 @@ __global__ void aa_transpose_kernel(int in_size, int out_size, int taps, const i
   }
 }
 
+// runs of output coordinates with identical (xmin, xsize), at most kGrpMax long
+__global__ void aa_group_kernel(int out_size, const int32_t* xmin, const int32_t* xsize, int32_t* grp_of,
+                                int32_t* grp_start) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int g = -1, run = 0;
+  for (int i = 0; i < out_size; ++i) {
+    const bool same = i > 0 && xmin[i] == xmin[i - 1] && xsize[i] == xsize[i - 1] && run < kGrpMax;
+    if (!same) { ++g; grp_start[g] = i; run = 0; }
+    grp_of[i] = g;
+    ++run;
+  }
+  for (int k = g + 1; k <= out_size; ++k) grp_start[k] = out_size;
+}
+
 int build_axis_table(AxisTable& t, int in_size, int out_size, cudaStream_t s) {
   t.in_size = in_size;
   t.out_size = out_size;
@@ -181,16 +197,21 @@ int build_axis_table(AxisTable& t, int in_size, int out_size, cudaStream_t s) {
   NTTT_CUDA(cudaMalloc(&t.t_lo, sizeof(int32_t) * in_size));
   NTTT_CUDA(cudaMalloc(&t.t_len, sizeof(int32_t) * in_size));
   NTTT_CUDA(cudaMalloc(&t.t_w, sizeof(float) * (size_t)in_size * kMaxScatter));
+  NTTT_CUDA(cudaMalloc(&t.grp_of, sizeof(int32_t) * out_size));
+  NTTT_CUDA(cudaMalloc(&t.grp_start, sizeof(int32_t) * ((size_t)out_size + 1)));
   aa_table_kernel<<<ceil_div(out_size, 128), 128, 0, s>>>(in_size, out_size, t.taps, t.xmin, t.xsize, t.w);
   NTTT_LAUNCH_CHECK();
   aa_transpose_kernel<<<ceil_div(in_size, 128), 128, 0, s>>>(in_size, out_size, t.taps, t.xmin, t.xsize, t.w, t.t_lo,
                                                             t.t_len, t.t_w);
+  NTTT_LAUNCH_CHECK();
+  aa_group_kernel<<<1, 32, 0, s>>>(out_size, t.xmin, t.xsize, t.grp_of, t.grp_start);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }
 
 void free_axis_table(AxisTable& t) {
   cudaFree(t.xmin); cudaFree(t.xsize); cudaFree(t.w); cudaFree(t.t_lo); cudaFree(t.t_len); cudaFree(t.t_w);
+  cudaFree(t.grp_of); cudaFree(t.grp_start);
   t = AxisTable{};
 }
 
@@ -203,62 +224,121 @@ void free_axis_table(AxisTable& t) {
 // ---------------------------------------------------------------------------------------------------
 constexpr int kProjThreads = 256;
 
+struct ProjTables {
+  const int32_t* x_lo; const int32_t* x_len; const float* x_w;
+  const int32_t* y_lo; const int32_t* y_len; const float* y_w;
+};
+
+__device__ __forceinline__ void split_bf16_pair(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// One CTA per mask.  Work is confined to the mask's low-res box: rows [top,bottom] for the horizontal pass and
+// the encoder cells whose spans touch the box for the vertical pass; everything else is written as zero.
+// kSplit=false: proj f32 [n, stride];  kSplit=true: bf16 [n, 3*kp] laid out [hi | hi | lo] (the A operand of
+// the tcgen05 pooling GEMM), zero padded to kp.
+template <bool kSplit>
 __global__ void __launch_bounds__(kProjThreads)
-project_masks_kernel(const uint32_t* __restrict__ bits, int h, int words_per_row, int eh, int ew,
-                     const int32_t* __restrict__ x_lo, const int32_t* __restrict__ x_len,
-                     const float* __restrict__ x_w, const int32_t* __restrict__ y_lo,
-                     const int32_t* __restrict__ y_len, const float* __restrict__ y_w,
-                     float* __restrict__ proj, int proj_stride) {
+project_masks_kernel(const uint32_t* __restrict__ bits, const int32_t* __restrict__ box, int h, int words_per_row,
+                     int eh, int ew, ProjTables t, void* __restrict__ out, int stride_or_kp) {
   extern __shared__ uint32_t smem[];
-  uint32_t* s_bits = smem;                                            // h * words_per_row
-  float* s_row = reinterpret_cast<float*>(smem + h * words_per_row);  // h * ew
+  // layout: x_lo[ew] x_len[ew] y_lo[eh] y_len[eh] | x_w[ew*S] y_w[eh*S] | bits[h*wpr] | row[h*ew]
+  int* s_xlo = reinterpret_cast<int*>(smem);
+  int* s_xlen = s_xlo + ew;
+  int* s_ylo = s_xlen + ew;
+  int* s_ylen = s_ylo + eh;
+  float* s_xw = reinterpret_cast<float*>(s_ylen + eh);
+  float* s_yw = s_xw + ew * kMaxScatter;
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_yw + eh * kMaxScatter);
+  float* s_row = reinterpret_cast<float*>(s_bits + h * words_per_row);
   const int n = blockIdx.x;
-  const int n_words = h * words_per_row;
-  const uint32_t* src = bits + (size_t)n * n_words;
-  for (int i = threadIdx.x; i < n_words; i += kProjThreads) s_bits[i] = src[i];
-  __syncthreads();
-  // row pass: s_row[y, ex] = sum_x bit(y,x) * Ux[x,ex]
-  for (int item = threadIdx.x; item < h * ew; item += kProjThreads) {
-    const int y = item / ew, ex = item - y * ew;
-    const int lo = x_lo[ex], len = x_len[ex];
-    const uint32_t* row = s_bits + y * words_per_row;
-    const int w0 = lo >> 5, sh = lo & 31;
-    const uint32_t a = row[w0];
-    const uint32_t b = (w0 + 1 < words_per_row) ? row[w0 + 1] : 0u;
-    uint32_t f = __funnelshift_r(a, b, sh);
-    f &= (len >= 32) ? 0xffffffffu : ((1u << len) - 1u);
-    float acc = 0.0f;
-    const float* wv = x_w + ex * kMaxScatter;
-    while (f) {
-      const int t = __ffs(f) - 1;
-      acc += wv[t];
-      f &= f - 1;
+  const int e_total = eh * ew;
+  const int4 b = reinterpret_cast<const int4*>(box)[n];
+  const uint32_t* src = bits + (size_t)n * h * words_per_row;
+  const bool empty = (b.x | b.y | b.z | b.w) == 0 && (src[0] & 1u) == 0;
+  const int top = b.y, bottom = b.w, left = b.x, right = b.z;
+
+  if (!empty) {
+    for (int i = threadIdx.x; i < ew; i += kProjThreads) { s_xlo[i] = t.x_lo[i]; s_xlen[i] = min(t.x_len[i], kMaxScatter); }
+    for (int i = threadIdx.x; i < eh; i += kProjThreads) { s_ylo[i] = t.y_lo[i]; s_ylen[i] = min(t.y_len[i], kMaxScatter); }
+    for (int i = threadIdx.x; i < ew * kMaxScatter; i += kProjThreads) s_xw[i] = t.x_w[i];
+    for (int i = threadIdx.x; i < eh * kMaxScatter; i += kProjThreads) s_yw[i] = t.y_w[i];
+    const int nrows = bottom - top + 1;
+    for (int i = threadIdx.x; i < nrows * words_per_row; i += kProjThreads) s_bits[i] = src[top * words_per_row + i];
+    __syncthreads();
+    // horizontal pass over the box rows: s_row[y - top, ex] = sum_x bit(y, x) * Ux[x, ex]
+    for (int item = threadIdx.x; item < nrows * ew; item += kProjThreads) {
+      const int yy = item / ew, ex = item - yy * ew;
+      const int lo = s_xlo[ex], len = s_xlen[ex];
+      float acc = 0.0f;
+      if (lo <= right && lo + len > left) {
+        const uint32_t* row = s_bits + yy * words_per_row;
+        const int w0 = lo >> 5, sh = lo & 31;
+        const uint32_t wa = row[w0];
+        const uint32_t wb = (w0 + 1 < words_per_row) ? row[w0 + 1] : 0u;
+        uint32_t f = __funnelshift_r(wa, wb, sh);
+        f &= (len >= 32) ? 0xffffffffu : ((1u << len) - 1u);
+        const float* wv = s_xw + ex * kMaxScatter;
+        while (f) {
+          const int q = __ffs(f) - 1;
+          acc += wv[q];
+          f &= f - 1;
+        }
+      }
+      s_row[item] = acc;
     }
-    s_row[item] = acc;
   }
   __syncthreads();
-  // column pass: proj[ey, ex] = sum_y Uy[y,ey] * s_row[y, ex]
-  float* out = proj + (size_t)n * proj_stride;
-  for (int item = threadIdx.x; item < eh * ew; item += kProjThreads) {
-    const int ey = item / ew, ex = item - ey * ew;
-    const int lo = y_lo[ey], len = y_len[ey];
-    const float* wv = y_w + ey * kMaxScatter;
+  // vertical pass + output (zeros outside the box's reach and in the K padding)
+  const int out_n = kSplit ? stride_or_kp : e_total;
+  for (int item = threadIdx.x; item < out_n; item += kProjThreads) {
     float acc = 0.0f;
-    for (int t = 0; t < len; ++t) acc = fmaf(wv[t], s_row[(lo + t) * ew + ex], acc);
-    out[item] = acc;
+    if (!empty && item < e_total) {
+      const int ey = item / ew, ex = item - ey * ew;
+      const int lo = s_ylo[ey], len = s_ylen[ey];
+      const int xl = s_xlo[ex], xn = s_xlen[ex];
+      if (lo <= bottom && lo + len > top && xl <= right && xl + xn > left) {
+        const float* wv = s_yw + ey * kMaxScatter;
+        const int ta = max(top - lo, 0), tb = min(bottom - lo + 1, len);
+        for (int q = ta; q < tb; ++q) acc = fmaf(wv[q], s_row[(lo + q - top) * ew + ex], acc);
+      }
+    }
+    if (kSplit) {
+      __nv_bfloat16 hi, lo16;
+      split_bf16_pair(acc, hi, lo16);
+      __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + (size_t)n * 3 * stride_or_kp;
+      o[item] = hi;
+      o[stride_or_kp + item] = hi;
+      o[2 * stride_or_kp + item] = lo16;
+    } else {
+      static_cast<float*>(out)[(size_t)n * stride_or_kp + item] = acc;
+    }
   }
 }
 
-int launch_project_masks(const AxisTable& tx, const AxisTable& ty, const uint32_t* bits, int n, int h, int w, int eh,
-                         int ew, float* proj, int proj_stride, cudaStream_t s) {
+static size_t project_smem_bytes(int h, int w, int eh, int ew) {
+  return sizeof(int) * 2 * (size_t)(ew + eh) + sizeof(float) * kMaxScatter * (size_t)(ew + eh) +
+         sizeof(uint32_t) * (size_t)h * (w / 32) + sizeof(float) * (size_t)h * ew;
+}
+
+// split=false: out = float [n, out_stride];  split=true: out = bf16 [n, 3*out_stride] with out_stride = kp
+int launch_project_masks(const AxisTable& tx, const AxisTable& ty, const uint32_t* bits, const int32_t* box, int n,
+                         int h, int w, int eh, int ew, void* out, int out_stride, bool split, cudaStream_t s) {
   if (n <= 0) return NTTT_OK;
   if (w % 32 != 0) return NTTT_EUNSUPPORTED;
-  const size_t smem = (size_t)h * (w / 32) * 4 + (size_t)h * ew * 4;
+  const size_t smem = project_smem_bytes(h, w, eh, ew);
   if (smem > 200 * 1024) return NTTT_EUNSUPPORTED;
-  if (smem > 48 * 1024)
-    NTTT_CUDA(cudaFuncSetAttribute(project_masks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  project_masks_kernel<<<n, kProjThreads, smem, s>>>(bits, h, w / 32, eh, ew, tx.t_lo, tx.t_len, tx.t_w, ty.t_lo,
-                                                     ty.t_len, ty.t_w, proj, proj_stride);
+  ProjTables t{tx.t_lo, tx.t_len, tx.t_w, ty.t_lo, ty.t_len, ty.t_w};
+  if (split) {
+    if (smem > 48 * 1024)
+      NTTT_CUDA(cudaFuncSetAttribute(project_masks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    project_masks_kernel<true><<<n, kProjThreads, smem, s>>>(bits, box, h, w / 32, eh, ew, t, out, out_stride);
+  } else {
+    if (smem > 48 * 1024)
+      NTTT_CUDA(cudaFuncSetAttribute(project_masks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    project_masks_kernel<false><<<n, kProjThreads, smem, s>>>(bits, box, h, w / 32, eh, ew, t, out, out_stride);
+  }
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }

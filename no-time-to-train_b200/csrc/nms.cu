@@ -98,6 +98,7 @@ nms_scan_kernel(const uint32_t* __restrict__ mask, int row_words, const int32_t*
                 int32_t* __restrict__ n_keep, int32_t* __restrict__ sel, int32_t* __restrict__ n_sel) {
   extern __shared__ uint32_t s_dyn[];
   __shared__ uint32_t s_removed[kScanMaxN / 32];
+  __shared__ uint32_t s_posbits[kScanMaxN / 32];  // bit i: top_score of sorted box i is > 0
   __shared__ uint32_t s_keepbits;
   __shared__ int s_stop;
   const int lane = lane_id(), warp = warp_id();
@@ -108,6 +109,12 @@ nms_scan_kernel(const uint32_t* __restrict__ mask, int row_words, const int32_t*
     M = s_dyn;
   }
   for (int i = threadIdx.x; i < row_words; i += kScanThreads) s_removed[i] = 0;
+  for (int base = 0; base < row_words * 32; base += kScanThreads) {  // positive-score flags, one ballot per warp
+    const int i = base + threadIdx.x;
+    const bool pos = i < n && top_score[order[i]] > 0.0f;
+    const uint32_t bits = __ballot_sync(kFull, pos);
+    if (lane == 0 && (i >> 5) < row_words) s_posbits[i >> 5] = bits;
+  }
   if (threadIdx.x == 0) s_stop = 0;
   __syncthreads();
   int kept = 0, selected = 0;  // tracked by warp 0
@@ -118,10 +125,12 @@ nms_scan_kernel(const uint32_t* __restrict__ mask, int row_words, const int32_t*
       const uint32_t diag = i < n ? M[(size_t)i * row_words + c] : 0u;
       const int n_here = min(32, n - c * 32);
       uint32_t keepbits = 0;
-      for (int b = 0; b < n_here; ++b) {
+#pragma unroll
+      for (int b = 0; b < 32; ++b) {  // rows past n have diag == 0 and are masked out below
         const uint32_t d = __shfl_sync(kFull, diag, b);
         if (!((cur >> b) & 1u)) { keepbits |= 1u << b; cur |= d; }
       }
+      if (n_here < 32) keepbits &= (1u << n_here) - 1u;
       int cnt = __popc(keepbits);
       if (kept + cnt > max_keep) {  // truncate to max_keep (= out_num)
         int excess = kept + cnt - max_keep;
@@ -129,11 +138,13 @@ nms_scan_kernel(const uint32_t* __restrict__ mask, int row_words, const int32_t*
         cnt = max_keep - kept;
       }
       const bool mine = (keepbits >> lane) & 1u;
-      const int oi = (i < n) ? order[i] : 0;
-      const bool pos = mine && (top_score[oi] > 0.0f);
-      const uint32_t posbits = __ballot_sync(kFull, pos);
-      if (mine) keep[kept + __popc(keepbits & ((1u << lane) - 1u))] = oi;
-      if (pos) sel[selected + __popc(posbits & ((1u << lane) - 1u))] = oi;
+      const uint32_t posbits = keepbits & s_posbits[c];
+      const bool pos = (posbits >> lane) & 1u;
+      if (mine) {
+        const int oi = order[i];
+        keep[kept + __popc(keepbits & ((1u << lane) - 1u))] = oi;
+        if (pos) sel[selected + __popc(posbits & ((1u << lane) - 1u))] = oi;
+      }
       kept += cnt;
       selected += __popc(posbits);
       if (lane == 0) { s_keepbits = keepbits; s_stop = kept >= max_keep; }

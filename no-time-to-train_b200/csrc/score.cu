@@ -2,6 +2,8 @@
 //
 // Reference: compute_sim_global_avg (matching_baseline_utils.py:869-904) and the top-k section
 // (Sam2MatchingBaseline_noAMG.py:602-612).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace nttt {
@@ -25,6 +27,80 @@ normalize_rows_kernel(const float* __restrict__ sums, const int32_t* __restrict_
   const float nrm = fmaxf(sqrtf(ss), 1e-12f);
   float* dst = out + (size_t)row * c;
   for (int i = lane; i < c; i += 32) dst[i] = __fdiv_rn(__fdiv_rn(src[i], denom), nrm);
+}
+
+// Vector path for encoder widths that are multiples of 128 (384, 768, 1024, 1536): one warp per row keeps the
+// whole row in registers (one pass over HBM), and also emits the split-bf16 A operand [hi | hi | lo] of the
+// similarity GEMM so no separate conversion pass is needed.
+template <int kVec>  // float4 per lane, c = 128 * kVec
+__global__ void __launch_bounds__(256)
+normalize_split_kernel(const float* __restrict__ sums, const int32_t* __restrict__ area, int n, int cp,
+                       float* __restrict__ out, __nv_bfloat16* __restrict__ split) {
+  constexpr int c = 128 * kVec;
+  const int row = blockIdx.x * 8 + warp_id();
+  if (row >= n) return;
+  const int lane = lane_id();
+  float denom = 1.0f;
+  if (area) { const int a = area[row]; denom = a == 0 ? 1.0f : (float)a; }
+  const float4* src = reinterpret_cast<const float4*>(sums + (size_t)row * c);
+  float4 v[kVec];
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) v[i] = src[i * 32 + lane];
+  float ss = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    v[i].x = __fdiv_rn(v[i].x, denom); v[i].y = __fdiv_rn(v[i].y, denom);
+    v[i].z = __fdiv_rn(v[i].z, denom); v[i].w = __fdiv_rn(v[i].w, denom);
+    ss = fmaf(v[i].x, v[i].x, ss); ss = fmaf(v[i].y, v[i].y, ss);
+    ss = fmaf(v[i].z, v[i].z, ss); ss = fmaf(v[i].w, v[i].w, ss);
+  }
+  ss = warp_sum(ss);
+  const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+  float4* dst = reinterpret_cast<float4*>(out + (size_t)row * c);
+  __nv_bfloat16* sp = split ? split + (size_t)row * 3 * cp : nullptr;
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    float4 o;
+    o.x = __fdiv_rn(v[i].x, nrm); o.y = __fdiv_rn(v[i].y, nrm);
+    o.z = __fdiv_rn(v[i].z, nrm); o.w = __fdiv_rn(v[i].w, nrm);
+    dst[i * 32 + lane] = o;
+    if (sp) {
+      const float e[4] = {o.x, o.y, o.z, o.w};
+      __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        hi[k] = __float2bfloat16_rn(e[k]);
+        lo[k] = __float2bfloat16_rn(e[k] - __bfloat162float(hi[k]));
+      }
+      const int col = (i * 32 + lane) * 4;
+      const uint2 h2 = make_uint2((uint32_t)__bfloat16_as_ushort(hi[0]) | ((uint32_t)__bfloat16_as_ushort(hi[1]) << 16),
+                                  (uint32_t)__bfloat16_as_ushort(hi[2]) | ((uint32_t)__bfloat16_as_ushort(hi[3]) << 16));
+      const uint2 l2 = make_uint2((uint32_t)__bfloat16_as_ushort(lo[0]) | ((uint32_t)__bfloat16_as_ushort(lo[1]) << 16),
+                                  (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16));
+      *reinterpret_cast<uint2*>(sp + col) = h2;
+      *reinterpret_cast<uint2*>(sp + cp + col) = h2;
+      *reinterpret_cast<uint2*>(sp + 2 * cp + col) = l2;
+    }
+  }
+}
+
+// returns 1 if the fused vector path ran (split written), 0 if the caller must use the generic kernels
+int launch_normalize_split(const float* sums, const int32_t* area, int n, int c, int cp, float* out, void* split,
+                           cudaStream_t s) {
+  if (n <= 0) return 1;
+  if (c % 128 != 0 || cp != c) return 0;
+  const int grid = ceil_div(n, 8);
+  __nv_bfloat16* sp = static_cast<__nv_bfloat16*>(split);
+  switch (c / 128) {
+    case 3: normalize_split_kernel<3><<<grid, 256, 0, s>>>(sums, area, n, cp, out, sp); break;
+    case 6: normalize_split_kernel<6><<<grid, 256, 0, s>>>(sums, area, n, cp, out, sp); break;
+    case 8: normalize_split_kernel<8><<<grid, 256, 0, s>>>(sums, area, n, cp, out, sp); break;
+    case 12: normalize_split_kernel<12><<<grid, 256, 0, s>>>(sums, area, n, cp, out, sp); break;
+    default: return 0;
+  }
+  ++g_launches;
+  if (cudaGetLastError() != cudaSuccess) return 0;
+  return 1;
 }
 
 int launch_normalize_rows(const float* sums, const int32_t* area, int n, int c, float* out, cudaStream_t s) {

@@ -66,12 +66,13 @@ def threshold_pack(logits: torch.Tensor, thr: float = 0.0, off: float = 1.0, out
     return bits, area, box, stab, flags
 
 
-def project_masks(bits: torch.Tensor, hw, enc_hw):
+def project_masks(bits: torch.Tensor, box: torch.Tensor, hw, enc_hw):
     _need(bits, torch.int32, "bits")
+    _need(box, torch.int32, "box")
     n = bits.shape[0]
     proj = torch.empty((n, enc_hw[0] * enc_hw[1]), dtype=torch.float32, device=bits.device)
     lib = _lib.load()
-    _lib.check(lib.nttt_project_masks(context(bits.device), _ptr(bits), n, hw[0], hw[1], enc_hw[0], enc_hw[1],
+    _lib.check(lib.nttt_project_masks(context(bits.device), _ptr(bits), _ptr(box), n, hw[0], hw[1], enc_hw[0], enc_hw[1],
                                       _ptr(proj), _stream(bits.device)), "nttt_project_masks")
     return proj
 

@@ -65,8 +65,8 @@ def test_threshold_pack_empty_batch(ops):
 def test_project_pool_matches_dense_reference(ops, synth, c):
     """Factored pooling == the reference's literal masks @ upsample(feat) within 1e-3 (measured ~1e-6)."""
     inp = synth.make_stage_inputs(n=40, c=c, n_cls=5, shots=2, seed=21, degenerate=True)
-    bits, area, *_ = ops.threshold_pack(inp.lr_masks.to(DEV))
-    proj = ops.project_masks(bits, (256, 256), (37, 37))
+    bits, area, box, *_ = ops.threshold_pack(inp.lr_masks.to(DEV))
+    proj = ops.project_masks(bits, box, (256, 256), (37, 37))
     obj = ops.pool_normalize(proj, inp.tar_feat.to(DEV), area)
     feat_pc = ref_torch.upsample_features(inp.tar_feat, (37, 37), (256, 256))
     _, want = ref_torch.pool_and_score(feat_pc, ref_torch.threshold_lowres(inp.lr_masks), inp.feats_ins_avg)
