@@ -70,7 +70,7 @@ int nttt_ctx_profile_read(nttt_ctx* ctx, float* ms_host, int capacity);
  * (:614, sam2/utils/amg.py:305-348) and `calculate_stability_score` (sam2/utils/amg.py:158-178).
  *   logits [n, h, w] f32 (h*w multiple of 128; SAM-2 emits 256x256)
  *   bits   [n, h*w/32] u32          area [n] i32            box [n,4] i32 (x1,y1,x2,y2 inclusive; empty->0)
- *   stab   [n,2] i32 = {count(logit > thr+off), count(logit > thr-off)}
+ *   stab   [n,2] i32 = {count(logit > thr+off), count(logit > thr-off)}; may be NULL (counts skipped)
  *   flags  [n] i32: bit0 = every positive logit is finite and in (2^-100, 2^100) (lets the full-res
  *          resize skip uniformly-positive footprints without evaluating them)
  */

@@ -217,7 +217,7 @@ void nttt_ctx_destroy(nttt_ctx* ctx) {
 int nttt_threshold_pack(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits, int32_t* area,
                         int32_t* box, int32_t* stab, int32_t* flags, void* stream) {
   if (n < 0 || h <= 0 || w <= 0) return NTTT_EINVAL;
-  if (n > 0 && (!logits || !bits || !area || !box || !stab || !flags)) return NTTT_EINVAL;
+  if (n > 0 && (!logits || !bits || !area || !box || !flags)) return NTTT_EINVAL;  // stab may be NULL
   return launch_lowres_pack(logits, n, h, w, thr, off, bits, area, box, stab, flags, (cudaStream_t)stream);
 }
 
@@ -481,7 +481,8 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
 #define NTTT_STEP(call) do { err = (call); if (err) return err; NTTT_MARK(); } while (0)
   NTTT_MARK();
   // a6/a9/a15: one pass over the logits
-  NTTT_STEP(launch_lowres_pack(a->logits, n, a->lr_h, a->lr_w, 0.0f, 1.0f, L.bits_lr, L.area_lr, L.box_lr, L.stab,
+  // (the stability counts of a15 are not read on this path, so the pipeline does not pay for them)
+  NTTT_STEP(launch_lowres_pack(a->logits, n, a->lr_h, a->lr_w, 0.0f, 1.0f, L.bits_lr, L.area_lr, L.box_lr, nullptr,
                                L.flags, s));
   // a6/a7: projection + pooling contraction + normalisation
   if (!projection_supported(a->ew, a->lr_w) || !projection_supported(a->eh, a->lr_h)) return NTTT_EUNSUPPORTED;

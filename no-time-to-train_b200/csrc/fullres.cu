@@ -232,8 +232,13 @@ size_t upsample_scratch_bytes(int max_sel) { return sizeof(int32_t) * kScratchIn
 
 // ---------------------------------------------------------------------------------------------------
 // unpack: packed words -> torch.bool bytes.  `index` (nullable) maps output slot j -> packed mask k.
-// HBM-bound: oh*ow bytes written per mask.
+// HBM-bound: oh*ow bytes written per mask.  One thread expands one 32-pixel word into two 128-bit stores
+// (nibble -> 4 bytes is one multiply and one mask); rows outside the mask's rect are zero-filled unread.
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t nb) { return (nb * 0x00204081u) & 0x01010101u; }
+
+constexpr int kUnpackRows = 8;  // output rows per CTA
+
 __global__ void __launch_bounds__(256)
 unpack_masks_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restrict__ rect,
                     const int32_t* __restrict__ index, const int32_t* __restrict__ count, int max_count, int oh, int ow,
@@ -245,24 +250,26 @@ unpack_masks_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __res
   const int4 rc = reinterpret_cast<const int4*>(rect)[k];
   const uint32_t* src = bits_full + (size_t)k * oh * ow_words;
   uint8_t* dst = out + (size_t)j * oh * ow;
-  const int segs = (ow + 15) >> 4;  // 16-pixel segments per row
-  const long total = (long)oh * segs;
-  const bool vec = (ow & 15) == 0;
-  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
-    const int y = (int)(g / segs), sx = (int)(g - (long)y * segs);
-    const int x = sx << 4, wi = x >> 5;
-    uint32_t half = 0;
-    if (y >= rc.x && y < rc.y && wi >= rc.z && wi < rc.w) half = (src[(size_t)y * ow_words + wi] >> (x & 31)) & 0xffffu;
+  const int y0 = blockIdx.x * kUnpackRows;
+  const int rows = min(kUnpackRows, oh - y0);
+  const bool vec = (ow & 15) == 0;  // every 16-pixel half word starts 16-byte aligned
+  for (int it = threadIdx.x; it < rows * ow_words; it += 256) {
+    const int ry = it / ow_words, wi = it - ry * ow_words;
+    const int y = y0 + ry, x = wi << 5;
+    uint32_t word = 0;
+    if (y >= rc.x && y < rc.y && wi >= rc.z && wi < rc.w) word = src[(size_t)y * ow_words + wi];
+    uint8_t* p = dst + (size_t)y * ow + x;
     if (vec) {
-      uint32_t o[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t nb = (half >> (4 * q)) & 0xfu;
-        o[q] = (nb & 1u) | ((nb & 2u) << 7) | ((nb & 4u) << 14) | ((nb & 8u) << 21);
+      uint4 lo4 = make_uint4(nibble_to_bytes(word & 15u), nibble_to_bytes((word >> 4) & 15u),
+                             nibble_to_bytes((word >> 8) & 15u), nibble_to_bytes((word >> 12) & 15u));
+      *reinterpret_cast<uint4*>(p) = lo4;
+      if (x + 16 < ow) {
+        uint4 hi4 = make_uint4(nibble_to_bytes((word >> 16) & 15u), nibble_to_bytes((word >> 20) & 15u),
+                               nibble_to_bytes((word >> 24) & 15u), nibble_to_bytes(word >> 28));
+        *reinterpret_cast<uint4*>(p + 16) = hi4;
       }
-      *reinterpret_cast<uint4*>(dst + (size_t)y * ow + x) = make_uint4(o[0], o[1], o[2], o[3]);
     } else {
-      for (int q = 0; q < 16 && x + q < ow; ++q) dst[(size_t)y * ow + x + q] = (half >> q) & 1u;
+      for (int q = 0; q < 32 && x + q < ow; ++q) p[q] = (word >> q) & 1u;
     }
   }
 }
@@ -270,10 +277,7 @@ unpack_masks_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __res
 int launch_unpack(const uint32_t* bits_full, const int32_t* rect, const int32_t* index, const int32_t* count,
                   int max_count, int oh, int ow, uint8_t* out, cudaStream_t s) {
   if (max_count <= 0) return NTTT_OK;
-  const long total = (long)oh * ((ow + 15) >> 4);
-  const long want = (total + 255) / 256;
-  const int bx = (int)(want < 1024 ? want : 1024);
-  dim3 grid(bx, max_count);
+  dim3 grid(ceil_div(oh, kUnpackRows), max_count);
   unpack_masks_kernel<<<grid, 256, 0, s>>>(bits_full, rect, index, count, max_count, oh, ow, out);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;

@@ -13,10 +13,14 @@ namespace nttt {
 // K1: lowres_pack — HBM-bound streaming kernel, one CTA per mask.
 //   algorithmic bytes per mask: 4*P read (+ P/8 written)
 // ---------------------------------------------------------------------------------------------------
-constexpr int kPackThreads = 512;
+constexpr int kPackThreads = 256;
 constexpr int kPackUnroll = 4;
 
-__global__ void __launch_bounds__(kPackThreads)
+// The loop is issue-bound before it is HBM-bound (5-10 ALU ops per logit), so it carries only what has to be
+// done per element: the sign bit, the finite-range check, and (only if asked, kStab) the two stability counts.
+// Area and box are derived afterwards from the packed words in shared memory.
+template <bool kStab>
+__global__ void __launch_bounds__(kPackThreads, 6)
 lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mask */, int words_per_row,
                    float thr_hi, float thr_lo, uint32_t* __restrict__ bits, int32_t* __restrict__ area,
                    int32_t* __restrict__ box, int32_t* __restrict__ stab, int32_t* __restrict__ flags) {
@@ -27,10 +31,10 @@ lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mas
   const int lane = lane_id();
   if (threadIdx.x < 8) s_red[threadIdx.x] = (threadIdx.x == 4 || threadIdx.x == 5) ? 0x7fffffff : (threadIdx.x >= 6 ? -1 : 0);
 
-  int a = 0, hi = 0, lo = 0, unsafe = 0;
-  int minx = 0x7fffffff, miny = 0x7fffffff, maxx = -1, maxy = -1;
-  const float kTiny = 7.888609052210118e-31f;   // 2^-100
-  const float kHuge = 1.2676506002282294e30f;   // 2^100
+  int hi = 0, lo = 0;
+  uint32_t unsafe = 0;
+  // a positive logit is "safe" iff 2^-100 < v < 2^100: bit pattern strictly between 0x0D800000 and 0x71800000
+  constexpr uint32_t kLoBits = 0x0D800000u, kSpan = 0x71800000u - 0x0D800001u;
 
   for (int base = 0; base < p4; base += kPackThreads * kPackUnroll) {
     float4 v[kPackUnroll];
@@ -48,46 +52,52 @@ lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mas
       for (int k = 0; k < 4; ++k) {
         const bool pos = e[k] > 0.0f;
         nib |= (uint32_t)pos << k;
-        hi += e[k] > thr_hi;
-        lo += e[k] > thr_lo;
-        unsafe |= pos && !(e[k] > kTiny && e[k] < kHuge);
+        const bool in_range = (__float_as_uint(e[k]) - (kLoBits + 1u)) < kSpan;
+        unsafe |= (uint32_t)(pos && !in_range);
+        if (kStab) {
+          hi += e[k] > thr_hi;
+          lo += e[k] > thr_lo;
+        }
       }
       uint32_t word = nib << (4 * (lane & 7));
       word |= __shfl_xor_sync(kFull, word, 1);
       word |= __shfl_xor_sync(kFull, word, 2);
       word |= __shfl_xor_sync(kFull, word, 4);
-      if ((lane & 7) == 0 && q < p4) {
-        const int wi = q >> 3;
-        s_bits[wi] = word;
-        if (word) {
-          a += __popc(word);
-          const int row = wi / words_per_row;
-          const int x0 = (wi - row * words_per_row) * 32;
-          minx = min(minx, x0 + __ffs(word) - 1);
-          maxx = max(maxx, x0 + 31 - __clz(word));
-          miny = min(miny, row);
-          maxy = max(maxy, row);
-        }
-      }
+      if ((lane & 7) == 0 && q < p4) s_bits[q >> 3] = word;
     }
   }
-  a = warp_sum(a); hi = warp_sum(hi); lo = warp_sum(lo); unsafe = warp_max(unsafe);
-  minx = warp_min(minx); miny = warp_min(miny); maxx = warp_max(maxx); maxy = warp_max(maxy);
-  __syncthreads();  // s_red initialised, s_bits complete
-  if (lane == 0) {
-    atomicAdd(&s_red[0], a); atomicAdd(&s_red[1], hi); atomicAdd(&s_red[2], lo); atomicMax(&s_red[3], unsafe);
-    atomicMin(&s_red[4], minx); atomicMin(&s_red[5], miny); atomicMax(&s_red[6], maxx); atomicMax(&s_red[7], maxy);
-  }
-  // packed words out, coalesced 128-bit stores
+  __syncthreads();  // s_bits complete, s_red initialised
+  // area and box from the packed words; 128-bit stores of the words
   const int n_words = p4 >> 3;
+  int a = 0, minx = 0x7fffffff, miny = 0x7fffffff, maxx = -1, maxy = -1;
+  for (int wi = threadIdx.x; wi < n_words; wi += kPackThreads) {
+    const uint32_t word = s_bits[wi];
+    if (word) {
+      a += __popc(word);
+      const int row = wi / words_per_row;
+      const int x0 = (wi - row * words_per_row) * 32;
+      minx = min(minx, x0 + __ffs(word) - 1);
+      maxx = max(maxx, x0 + 31 - __clz(word));
+      miny = min(miny, row);
+      maxy = max(maxy, row);
+    }
+  }
   uint4* dst = reinterpret_cast<uint4*>(bits + (size_t)n * n_words);
   const uint4* s4 = reinterpret_cast<const uint4*>(s_bits);
   for (int i = threadIdx.x; i < (n_words >> 2); i += kPackThreads) dst[i] = s4[i];
+  a = warp_sum(a);
+  unsafe = (uint32_t)warp_max((int)unsafe);
+  minx = warp_min(minx); miny = warp_min(miny); maxx = warp_max(maxx); maxy = warp_max(maxy);
+  if (kStab) { hi = warp_sum(hi); lo = warp_sum(lo); }
+  if (lane == 0) {
+    atomicAdd(&s_red[0], a); atomicMax(&s_red[3], (int)unsafe);
+    atomicMin(&s_red[4], minx); atomicMin(&s_red[5], miny); atomicMax(&s_red[6], maxx); atomicMax(&s_red[7], maxy);
+    if (kStab) { atomicAdd(&s_red[1], hi); atomicAdd(&s_red[2], lo); }
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     area[n] = s_red[0];
-    stab[2 * n] = s_red[1];
-    stab[2 * n + 1] = s_red[2];
+    if (kStab) { stab[2 * n] = s_red[1]; stab[2 * n + 1] = s_red[2]; }
     flags[n] = s_red[3] ? 0 : 1;
     const bool empty = s_red[6] < s_red[4] || s_red[7] < s_red[5];
     int4 b = empty ? make_int4(0, 0, 0, 0) : make_int4(s_red[4], s_red[5], s_red[6], s_red[7]);
@@ -95,16 +105,20 @@ lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mas
   }
 }
 
+// stab may be NULL: the stability counts (sam2/utils/amg.py:158-178) are not read on the noAMG path
 int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits,
                        int32_t* area, int32_t* box, int32_t* stab, int32_t* flags, cudaStream_t s) {
   const long p = (long)h * w;
   if (n <= 0) return NTTT_OK;
-  if (w % 32 != 0 || p % 128 != 0 || p / 32 * 4 > 160 * 1024) return NTTT_EUNSUPPORTED;
+  if (w % 32 != 0 || p % 128 != 0 || p / 32 * 4 > 32 * 1024) return NTTT_EUNSUPPORTED;
   const size_t smem = (size_t)(p / 32) * sizeof(uint32_t);
-  if (smem > 48 * 1024)
-    NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  lowres_pack_kernel<<<n, kPackThreads, smem, s>>>(reinterpret_cast<const float4*>(logits), (int)(p / 4), w / 32,
-                                                   thr + off, thr - off, bits, area, box, stab, flags);
+  const float4* src = reinterpret_cast<const float4*>(logits);
+  if (stab)
+    lowres_pack_kernel<true><<<n, kPackThreads, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area,
+                                                          box, stab, flags);
+  else
+    lowres_pack_kernel<false><<<n, kPackThreads, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits,
+                                                           area, box, stab, flags);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }

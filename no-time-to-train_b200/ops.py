@@ -46,9 +46,10 @@ def context(device) -> int:
     return _ctx_by_device[idx]
 
 
-def threshold_pack(logits: torch.Tensor, thr: float = 0.0, off: float = 1.0, out=None):
+def threshold_pack(logits: torch.Tensor, thr: float = 0.0, off: float = 1.0, out=None, want_stab: bool = True):
     """-> bits [n, h*w/32] int32 (bit pattern of uint32), area [n], box [n,4], stab [n,2], flags [n].
-    `out` may carry the five preallocated outputs of an earlier call (no allocation inside a timed loop)."""
+    `out` may carry the five preallocated outputs of an earlier call (no allocation inside a timed loop).
+    want_stab=False skips the stability counts (the variant `nttt_match_image` launches)."""
     _need(logits, torch.float32, "logits")
     n, h, w = logits.shape
     dev = logits.device
@@ -61,8 +62,9 @@ def threshold_pack(logits: torch.Tensor, thr: float = 0.0, off: float = 1.0, out
         stab = torch.empty((n, 2), dtype=torch.int32, device=dev)
         flags = torch.empty((n,), dtype=torch.int32, device=dev)
     lib = _lib.load()
-    _lib.check(lib.nttt_threshold_pack(_ptr(logits), n, h, w, thr, off, _ptr(bits), _ptr(area), _ptr(box), _ptr(stab),
-                                       _ptr(flags), _stream(dev)), "nttt_threshold_pack")
+    _lib.check(lib.nttt_threshold_pack(_ptr(logits), n, h, w, thr, off, _ptr(bits), _ptr(area), _ptr(box),
+                                       _ptr(stab) if want_stab else None, _ptr(flags), _stream(dev)),
+               "nttt_threshold_pack")
     return bits, area, box, stab, flags
 
 
