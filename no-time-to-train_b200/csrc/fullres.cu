@@ -237,7 +237,8 @@ size_t upsample_scratch_bytes(int max_sel) { return sizeof(int32_t) * kScratchIn
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t nb) { return (nb * 0x00204081u) & 0x01010101u; }
 
-constexpr int kUnpackRows = 8;  // output rows per CTA
+constexpr int kUnpackRows = 32;   // output rows per CTA
+constexpr int kUnpackUnroll = 4;  // words per thread in flight
 
 __global__ void __launch_bounds__(256)
 unpack_masks_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restrict__ rect,
@@ -253,23 +254,36 @@ unpack_masks_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __res
   const int y0 = blockIdx.x * kUnpackRows;
   const int rows = min(kUnpackRows, oh - y0);
   const bool vec = (ow & 15) == 0;  // every 16-pixel half word starts 16-byte aligned
-  for (int it = threadIdx.x; it < rows * ow_words; it += 256) {
-    const int ry = it / ow_words, wi = it - ry * ow_words;
-    const int y = y0 + ry, x = wi << 5;
-    uint32_t word = 0;
-    if (y >= rc.x && y < rc.y && wi >= rc.z && wi < rc.w) word = src[(size_t)y * ow_words + wi];
-    uint8_t* p = dst + (size_t)y * ow + x;
-    if (vec) {
-      uint4 lo4 = make_uint4(nibble_to_bytes(word & 15u), nibble_to_bytes((word >> 4) & 15u),
-                             nibble_to_bytes((word >> 8) & 15u), nibble_to_bytes((word >> 12) & 15u));
-      *reinterpret_cast<uint4*>(p) = lo4;
-      if (x + 16 < ow) {
-        uint4 hi4 = make_uint4(nibble_to_bytes((word >> 16) & 15u), nibble_to_bytes((word >> 20) & 15u),
-                               nibble_to_bytes((word >> 24) & 15u), nibble_to_bytes(word >> 28));
-        *reinterpret_cast<uint4*>(p + 16) = hi4;
+  const int total = rows * ow_words;
+  for (int base = 0; base < total; base += 256 * kUnpackUnroll) {
+    uint32_t word[kUnpackUnroll];
+    int yy[kUnpackUnroll], ww[kUnpackUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnpackUnroll; ++u) {  // all loads first
+      const int it = base + u * 256 + threadIdx.x;
+      const int ry = it / ow_words;
+      yy[u] = y0 + ry;
+      ww[u] = it - ry * ow_words;
+      word[u] = 0;
+      if (it < total && yy[u] >= rc.x && yy[u] < rc.y && ww[u] >= rc.z && ww[u] < rc.w)
+        word[u] = __ldg(src + (size_t)yy[u] * ow_words + ww[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnpackUnroll; ++u) {
+      const int it = base + u * 256 + threadIdx.x;
+      if (it >= total) continue;
+      const int x = ww[u] << 5;
+      const uint32_t w = word[u];
+      uint8_t* p = dst + (size_t)yy[u] * ow + x;
+      if (vec) {
+        *reinterpret_cast<uint4*>(p) = make_uint4(nibble_to_bytes(w & 15u), nibble_to_bytes((w >> 4) & 15u),
+                                                   nibble_to_bytes((w >> 8) & 15u), nibble_to_bytes((w >> 12) & 15u));
+        if (x + 16 < ow)
+          *reinterpret_cast<uint4*>(p + 16) = make_uint4(nibble_to_bytes((w >> 16) & 15u), nibble_to_bytes((w >> 20) & 15u),
+                                                        nibble_to_bytes((w >> 24) & 15u), nibble_to_bytes(w >> 28));
+      } else {
+        for (int q = 0; q < 32 && x + q < ow; ++q) p[q] = (w >> q) & 1u;
       }
-    } else {
-      for (int q = 0; q < 32 && x + q < ow; ++q) p[q] = (word >> q) & 1u;
     }
   }
 }

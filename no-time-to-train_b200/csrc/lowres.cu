@@ -20,7 +20,7 @@ constexpr int kPackUnroll = 4;
 // done per element: the sign bit, the finite-range check, and (only if asked, kStab) the two stability counts.
 // Area and box are derived afterwards from the packed words in shared memory.
 template <bool kStab>
-__global__ void __launch_bounds__(kPackThreads, 6)
+__global__ void __launch_bounds__(kPackThreads, 5)
 lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mask */, int words_per_row,
                    float thr_hi, float thr_lo, uint32_t* __restrict__ bits, int32_t* __restrict__ area,
                    int32_t* __restrict__ box, int32_t* __restrict__ stab, int32_t* __restrict__ flags) {
@@ -36,12 +36,21 @@ lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mas
   // a positive logit is "safe" iff 2^-100 < v < 2^100: bit pattern strictly between 0x0D800000 and 0x71800000
   constexpr uint32_t kLoBits = 0x0D800000u, kSpan = 0x71800000u - 0x0D800001u;
 
+  // software pipeline: the loads of the next batch are in flight while this batch is reduced
+  float4 nxt[kPackUnroll];
+#pragma unroll
+  for (int u = 0; u < kPackUnroll; ++u) {
+    const int q = u * kPackThreads + threadIdx.x;
+    nxt[u] = q < p4 ? ld_stream(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int base = 0; base < p4; base += kPackThreads * kPackUnroll) {
     float4 v[kPackUnroll];
 #pragma unroll
+    for (int u = 0; u < kPackUnroll; ++u) v[u] = nxt[u];
+#pragma unroll
     for (int u = 0; u < kPackUnroll; ++u) {
-      const int q = base + u * kPackThreads + threadIdx.x;
-      v[u] = q < p4 ? ld_stream(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int q = base + kPackThreads * kPackUnroll + u * kPackThreads + threadIdx.x;
+      nxt[u] = q < p4 ? ld_stream(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < kPackUnroll; ++u) {
@@ -250,89 +259,124 @@ __device__ __forceinline__ void split_bf16_pair(float x, __nv_bfloat16& hi, __nv
 
 // One CTA per mask.  Work is confined to the mask's low-res box: rows [top,bottom] for the horizontal pass and
 // the encoder cells whose spans touch the box for the vertical pass; everything else is written as zero.
+// The horizontal pass walks RUNS of set bits (masks are blobs: one or two runs per row) against prefix sums of
+// the weights, one warp per row and one lane per encoder column, so there is no per-bit loop and no division.
 // kSplit=false: proj f32 [n, stride];  kSplit=true: bf16 [n, 3*kp] laid out [hi | hi | lo] (the A operand of
 // the tcgen05 pooling GEMM), zero padded to kp.
+constexpr int kCum = kMaxScatter + 1;
+
+// first and last index e in [0, n) with flag(e) true, evaluated by one warp (n <= 64); returns lo > hi if none
+template <typename F>
+__device__ __forceinline__ void warp_range(int n, F flag, int& lo, int& hi) {
+  const int lane = lane_id();
+  const uint32_t b0 = __ballot_sync(kFull, lane < n && flag(lane));
+  const uint32_t b1 = __ballot_sync(kFull, lane + 32 < n && flag(lane + 32));
+  lo = b0 ? __ffs(b0) - 1 : (b1 ? 32 + __ffs(b1) - 1 : 1);
+  hi = b1 ? 63 - __clz(b1) : (b0 ? 31 - __clz(b0) : 0);
+}
+
 template <bool kSplit>
 __global__ void __launch_bounds__(kProjThreads)
 project_masks_kernel(const uint32_t* __restrict__ bits, const int32_t* __restrict__ box, int h, int words_per_row,
                      int eh, int ew, ProjTables t, void* __restrict__ out, int stride_or_kp) {
   extern __shared__ uint32_t smem[];
-  // layout: x_lo[ew] x_len[ew] y_lo[eh] y_len[eh] | x_w[ew*S] y_w[eh*S] | bits[h*wpr] | row[h*ew]
+  // layout: x_lo[ew] x_len[ew] y_lo[eh] y_len[eh] | x_cum[ew*kCum] y_w[eh*S] | bits[h*wpr] | row[h*ew]
   int* s_xlo = reinterpret_cast<int*>(smem);
   int* s_xlen = s_xlo + ew;
   int* s_ylo = s_xlen + ew;
   int* s_ylen = s_ylo + eh;
-  float* s_xw = reinterpret_cast<float*>(s_ylen + eh);
-  float* s_yw = s_xw + ew * kMaxScatter;
+  float* s_xc = reinterpret_cast<float*>(s_ylen + eh);
+  float* s_yw = s_xc + ew * kCum;
   uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_yw + eh * kMaxScatter);
   float* s_row = reinterpret_cast<float*>(s_bits + h * words_per_row);
   const int n = blockIdx.x;
+  const int lane = lane_id(), warp = warp_id();
+  constexpr int kWarps = kProjThreads / 32;
   const int e_total = eh * ew;
   const int4 b = reinterpret_cast<const int4*>(box)[n];
   const uint32_t* src = bits + (size_t)n * h * words_per_row;
   const bool empty = (b.x | b.y | b.z | b.w) == 0 && (src[0] & 1u) == 0;
   const int top = b.y, bottom = b.w, left = b.x, right = b.z;
 
-  if (!empty) {
-    for (int i = threadIdx.x; i < ew; i += kProjThreads) { s_xlo[i] = t.x_lo[i]; s_xlen[i] = min(t.x_len[i], kMaxScatter); }
-    for (int i = threadIdx.x; i < eh; i += kProjThreads) { s_ylo[i] = t.y_lo[i]; s_ylen[i] = min(t.y_len[i], kMaxScatter); }
-    for (int i = threadIdx.x; i < ew * kMaxScatter; i += kProjThreads) s_xw[i] = t.x_w[i];
-    for (int i = threadIdx.x; i < eh * kMaxScatter; i += kProjThreads) s_yw[i] = t.y_w[i];
-    const int nrows = bottom - top + 1;
-    for (int i = threadIdx.x; i < nrows * words_per_row; i += kProjThreads) s_bits[i] = src[top * words_per_row + i];
-    __syncthreads();
-    // horizontal pass over the box rows: s_row[y - top, ex] = sum_x bit(y, x) * Ux[x, ex]
-    for (int item = threadIdx.x; item < nrows * ew; item += kProjThreads) {
-      const int yy = item / ew, ex = item - yy * ew;
+  // zero the whole output row first (128-bit stores); the cells the box reaches are overwritten below
+  {
+    const size_t row_bytes = kSplit ? (size_t)3 * stride_or_kp * 2 : (size_t)stride_or_kp * 4;
+    char* o = static_cast<char*>(out) + (size_t)n * row_bytes;
+    if ((row_bytes & 15) == 0) {
+      for (int i = threadIdx.x; i < (int)(row_bytes >> 4); i += kProjThreads)
+        reinterpret_cast<uint4*>(o)[i] = make_uint4(0, 0, 0, 0);
+    } else {
+      for (int i = threadIdx.x; i < (int)(row_bytes >> 2); i += kProjThreads) reinterpret_cast<uint32_t*>(o)[i] = 0;
+    }
+  }
+  if (empty || eh > 64 || ew > 64) return;  // (eh, ew <= 64 is checked by the launcher)
+
+  for (int i = threadIdx.x; i < ew; i += kProjThreads) { s_xlo[i] = t.x_lo[i]; s_xlen[i] = min(t.x_len[i], kMaxScatter); }
+  for (int i = threadIdx.x; i < eh; i += kProjThreads) { s_ylo[i] = t.y_lo[i]; s_ylen[i] = min(t.y_len[i], kMaxScatter); }
+  for (int i = threadIdx.x; i < eh * kMaxScatter; i += kProjThreads) s_yw[i] = t.y_w[i];
+  for (int ex = threadIdx.x; ex < ew; ex += kProjThreads) {  // prefix sums of the column weights
+    float c = 0.0f;
+    s_xc[ex * kCum] = 0.0f;
+    for (int q = 0; q < kMaxScatter; ++q) { c += t.x_w[ex * kMaxScatter + q]; s_xc[ex * kCum + q + 1] = c; }
+  }
+  const int nrows = bottom - top + 1;
+  for (int i = threadIdx.x; i < nrows * words_per_row; i += kProjThreads) s_bits[i] = src[top * words_per_row + i];
+  __syncthreads();
+  // encoder cells whose spans touch the box
+  int ex_lo, ex_hi, ey_lo, ey_hi;
+  warp_range(ew, [&](int e) { return s_xlo[e] <= right && s_xlo[e] + s_xlen[e] > left; }, ex_lo, ex_hi);
+  warp_range(eh, [&](int e) { return s_ylo[e] <= bottom && s_ylo[e] + s_ylen[e] > top; }, ey_lo, ey_hi);
+  const int nex = ex_hi - ex_lo + 1;
+  if (nex <= 0 || ey_hi < ey_lo) return;
+
+  // horizontal pass: s_row[yy, ex - ex_lo] = sum_x bit(top + yy, x) * Ux[x, ex], one warp per row
+  for (int yy = warp; yy < nrows; yy += kWarps) {
+    const uint32_t* row = s_bits + yy * words_per_row;
+    for (int ex = ex_lo + lane; ex <= ex_hi; ex += 32) {
       const int lo = s_xlo[ex], len = s_xlen[ex];
+      const int w0 = lo >> 5, sh = lo & 31;
+      const uint32_t wa = row[w0];
+      const uint32_t wb = (w0 + 1 < words_per_row) ? row[w0 + 1] : 0u;
+      uint32_t f = __funnelshift_r(wa, wb, sh);
+      f &= (len >= 32) ? 0xffffffffu : ((1u << len) - 1u);
+      const float* cw = s_xc + ex * kCum;
       float acc = 0.0f;
-      if (lo <= right && lo + len > left) {
-        const uint32_t* row = s_bits + yy * words_per_row;
-        const int w0 = lo >> 5, sh = lo & 31;
-        const uint32_t wa = row[w0];
-        const uint32_t wb = (w0 + 1 < words_per_row) ? row[w0 + 1] : 0u;
-        uint32_t f = __funnelshift_r(wa, wb, sh);
-        f &= (len >= 32) ? 0xffffffffu : ((1u << len) - 1u);
-        const float* wv = s_xw + ex * kMaxScatter;
-        while (f) {
-          const int q = __ffs(f) - 1;
-          acc += wv[q];
-          f &= f - 1;
-        }
+      while (f) {  // one iteration per run of set bits
+        const int a = __ffs(f) - 1;
+        const uint32_t g = ~(f >> a);
+        const int run = g ? __ffs(g) - 1 : 32 - a;
+        acc += cw[a + run] - cw[a];
+        f = (a + run >= 32) ? 0u : (f >> (a + run)) << (a + run);
       }
-      s_row[item] = acc;
+      s_row[yy * nex + (ex - ex_lo)] = acc;
     }
   }
   __syncthreads();
-  // vertical pass + output (zeros outside the box's reach and in the K padding)
-  const int out_n = kSplit ? stride_or_kp : e_total;
-  for (int item = threadIdx.x; item < out_n; item += kProjThreads) {
-    float acc = 0.0f;
-    if (!empty && item < e_total) {
-      const int ey = item / ew, ex = item - ey * ew;
-      const int lo = s_ylo[ey], len = s_ylen[ey];
-      const int xl = s_xlo[ex], xn = s_xlen[ex];
-      if (lo <= bottom && lo + len > top && xl <= right && xl + xn > left) {
-        const float* wv = s_yw + ey * kMaxScatter;
-        const int ta = max(top - lo, 0), tb = min(bottom - lo + 1, len);
-        for (int q = ta; q < tb; ++q) acc = fmaf(wv[q], s_row[(lo + q - top) * ew + ex], acc);
+  // vertical pass over the reachable cells + output
+  for (int ey = ey_lo + warp; ey <= ey_hi; ey += kWarps) {
+    const int lo = s_ylo[ey], len = s_ylen[ey];
+    const float* wv = s_yw + ey * kMaxScatter;
+    const int ta = max(top - lo, 0), tb = min(bottom - lo + 1, len);
+    for (int ex = ex_lo + lane; ex <= ex_hi; ex += 32) {
+      float acc = 0.0f;
+      for (int q = ta; q < tb; ++q) acc = fmaf(wv[q], s_row[(lo + q - top) * nex + (ex - ex_lo)], acc);
+      const int item = ey * ew + ex;
+      if (kSplit) {
+        __nv_bfloat16 hi, lo16;
+        split_bf16_pair(acc, hi, lo16);
+        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + (size_t)n * 3 * stride_or_kp;
+        o[item] = hi;
+        o[stride_or_kp + item] = hi;
+        o[2 * stride_or_kp + item] = lo16;
+      } else {
+        static_cast<float*>(out)[(size_t)n * stride_or_kp + item] = acc;
       }
-    }
-    if (kSplit) {
-      __nv_bfloat16 hi, lo16;
-      split_bf16_pair(acc, hi, lo16);
-      __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + (size_t)n * 3 * stride_or_kp;
-      o[item] = hi;
-      o[stride_or_kp + item] = hi;
-      o[2 * stride_or_kp + item] = lo16;
-    } else {
-      static_cast<float*>(out)[(size_t)n * stride_or_kp + item] = acc;
     }
   }
 }
 
 static size_t project_smem_bytes(int h, int w, int eh, int ew) {
-  return sizeof(int) * 2 * (size_t)(ew + eh) + sizeof(float) * kMaxScatter * (size_t)(ew + eh) +
+  return sizeof(int) * 2 * (size_t)(ew + eh) + sizeof(float) * ((size_t)kCum * ew + (size_t)kMaxScatter * eh) +
          sizeof(uint32_t) * (size_t)h * (w / 32) + sizeof(float) * (size_t)h * ew;
 }
 
@@ -340,7 +384,7 @@ static size_t project_smem_bytes(int h, int w, int eh, int ew) {
 int launch_project_masks(const AxisTable& tx, const AxisTable& ty, const uint32_t* bits, const int32_t* box, int n,
                          int h, int w, int eh, int ew, void* out, int out_stride, bool split, cudaStream_t s) {
   if (n <= 0) return NTTT_OK;
-  if (w % 32 != 0) return NTTT_EUNSUPPORTED;
+  if (w % 32 != 0 || eh > 64 || ew > 64) return NTTT_EUNSUPPORTED;
   const size_t smem = project_smem_bytes(h, w, eh, ew);
   if (smem > 200 * 1024) return NTTT_EUNSUPPORTED;
   ProjTables t{tx.t_lo, tx.t_len, tx.t_w, ty.t_lo, ty.t_len, ty.t_w};

@@ -34,8 +34,6 @@ class PendingResult:
         self.taps = taps
         self.ori_hw = ori_hw
         self._keepalive = keepalive
-        self._event = torch.cuda.Event()
-        self._event.record(torch.cuda.current_stream(masks.device))
 
     def get(self) -> dict:
         counts = self.counts.cpu()  # synchronises with the producing stream
@@ -109,11 +107,12 @@ class MatchingStage:
         max_sel = int(min(num_out * self.cfg.expand_ratio, n))
         dev = self.device
         masks = torch.empty((max(num_out, 1), oh, ow), dtype=torch.uint8, device=dev)
-        boxes = torch.zeros((max(num_out, 1), 4), dtype=torch.int64, device=dev)
-        scores = torch.zeros((max(num_out, 1),), dtype=torch.float32, device=dev)
-        labels = torch.zeros((max(num_out, 1),), dtype=torch.int64, device=dev)
-        index = torch.zeros((max(num_out, 1),), dtype=torch.int32, device=dev)
-        counts = torch.zeros((4,), dtype=torch.int32, device=dev)
+        # (no fills: only the first n_out rows are ever read, and the pipeline writes the counts itself)
+        boxes = torch.empty((max(num_out, 1), 4), dtype=torch.int64, device=dev)
+        scores = torch.empty((max(num_out, 1),), dtype=torch.float32, device=dev)
+        labels = torch.empty((max(num_out, 1),), dtype=torch.int64, device=dev)
+        index = torch.empty((max(num_out, 1),), dtype=torch.int32, device=dev)
+        counts = torch.empty((4,), dtype=torch.int32, device=dev)
         tap_t = {}
         if taps:
             tap_t["sim"] = torch.empty((n, self.n_cls), dtype=torch.float32, device=dev)
