@@ -140,10 +140,11 @@ int nttt_upsample_threshold_pack(nttt_ctx* ctx, const float* logits, const uint3
  *   inter_out (nullable) [max_sel, max_sel] i32 receives the integer intersection counts of same-label
  *   pairs (0 elsewhere) for parity tests.
  */
+size_t nttt_mask_ios_workspace_bytes(int max_sel);
 int nttt_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_t* area_full,
                   const int32_t* box_full, const int32_t* sel, const int32_t* n_sel, int max_sel, int oh, int ow,
                   const int32_t* labels, const float* obj_feats, int c, float* ios, int32_t* inter_out,
-                  void* stream);
+                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * a14 — score decay, final top-k, output gather

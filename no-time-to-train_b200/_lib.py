@@ -55,7 +55,8 @@ SIGNATURES = {
     "nttt_box_nms": (c_int, [_P, _P, _P, _P, c_int, c_float, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "nttt_upsample_threshold_pack": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, _P, _P,
                                              _P, _P, _P]),
-    "nttt_mask_ios": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P]),
+    "nttt_mask_ios_workspace_bytes": (c_size_t, [c_int]),
+    "nttt_mask_ios": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, c_size_t, _P]),
     "nttt_decay_topk": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P,
                                 _P, _P]),
     "nttt_unpack_masks": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P]),

@@ -28,10 +28,12 @@ int launch_upsample_pack(const AxisTable&, const AxisTable&, const float*, const
 size_t upsample_scratch_bytes(int max_sel);
 int launch_unpack(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, uint8_t*,
                   cudaStream_t);
+size_t ios_workspace_bytes(int max_sel);
 int launch_mask_ios(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
-                    int, int, int, const int32_t*, const float*, int, float*, int32_t*, cudaStream_t);
+                    int, int, int, const int32_t*, const float*, int, float*, int32_t*, void*, bool, cudaStream_t);
 int launch_decay_rank(const float*, const int32_t*, const float*, const int32_t*, const int32_t*, int, int,
-                      const int32_t*, int64_t*, float*, int64_t*, int32_t*, int32_t*, int32_t*, float*, cudaStream_t);
+                      const int32_t*, const int32_t*, int64_t*, float*, int64_t*, int32_t*, int32_t*, int32_t*, float*,
+                      cudaStream_t);
 int launch_fill_pool(const float*, const float*, int, int, int, int, int, float*, float*, float*, cudaStream_t);
 int launch_fill_finalize(const float*, const float*, int, int, int, float*, float*, cudaStream_t);
 
@@ -333,15 +335,19 @@ int nttt_upsample_threshold_pack(nttt_ctx* ctx, const float* logits, const uint3
                               bits_full, rect, area_full, box_full, scratch, s);
 }
 
+size_t nttt_mask_ios_workspace_bytes(int max_sel) { return ios_workspace_bytes(max_sel > 0 ? max_sel : 1); }
+
 int nttt_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_t* area_full, const int32_t* box_full,
                   const int32_t* sel, const int32_t* n_sel, int max_sel, int oh, int ow, const int32_t* labels,
-                  const float* obj_feats, int c, float* ios, int32_t* inter_out, void* stream) {
+                  const float* obj_feats, int c, float* ios, int32_t* inter_out, void* workspace,
+                  size_t workspace_bytes, void* stream) {
   if (max_sel < 0 || oh <= 0 || ow <= 0 || c <= 0) return NTTT_EINVAL;
   if (max_sel == 0) return NTTT_OK;
   if (!bits_full || !rect || !area_full || !box_full || !sel || !n_sel || !labels || !obj_feats || !ios)
     return NTTT_EINVAL;
+  if (!workspace || workspace_bytes < ios_workspace_bytes(max_sel)) return NTTT_EWORKSPACE;
   return launch_mask_ios(bits_full, rect, area_full, box_full, sel, n_sel, max_sel, oh, ow, labels, obj_feats, c, ios,
-                         inter_out, (cudaStream_t)stream);
+                         inter_out, workspace, true, (cudaStream_t)stream);
 }
 
 int nttt_decay_topk(const float* top_score, const int32_t* labels, const float* ios, const int32_t* sel,
@@ -358,7 +364,7 @@ int nttt_decay_topk(const float* top_score, const int32_t* labels, const float* 
   if (!top_score || !labels || !ios || !sel || !n_sel || !bits_full || !rect || !box_full || !out_masks || !out_boxes ||
       !out_scores || !out_labels || !out_index || !out_slot)
     return NTTT_EINVAL;
-  int err = launch_decay_rank(top_score, labels, ios, sel, n_sel, max_sel, num_out, box_full, out_boxes, out_scores,
+  int err = launch_decay_rank(top_score, labels, ios, sel, n_sel, max_sel, num_out, box_full, nullptr, out_boxes, out_scores,
                               out_labels, out_index, out_slot, n_out, nullptr, s);
   if (err) return err;
   return launch_unpack(bits_full, rect, out_slot, n_out, num_out, oh, ow, out_masks, s);
@@ -395,7 +401,7 @@ struct MatchLayout {
   char* a_split; char* b_split;
   void* nms_ws; size_t nms_ws_bytes; int32_t* keep; int32_t* sel;
   uint32_t* bits_full; int32_t* rect; int32_t* area_full; int32_t* box_full; int32_t* scratch;
-  float* ios; int32_t* out_slot;
+  float* ios; void* ios_ws; int32_t* out_slot;
   size_t total;
 };
 
@@ -431,6 +437,7 @@ static MatchLayout carve(void* ws, int n, int lr_h, int lr_w, int eh, int ew, in
   L.box_full = cv.take<int32_t>((size_t)max_sel * 4);
   L.scratch = cv.take<int32_t>(upsample_scratch_bytes(max_sel > 0 ? max_sel : 1) / sizeof(int32_t));
   L.ios = cv.take<float>(max_sel > 0 ? max_sel : 1);
+  L.ios_ws = cv.take<char>(ios_workspace_bytes(max_sel > 0 ? max_sel : 1));
   L.out_slot = cv.take<int32_t>(num_out > 0 ? num_out : 1);
   L.total = align_up(cv.off, 256);
   return L;
@@ -503,9 +510,10 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
                                  L.box_full, L.scratch, s));
   // a13
   NTTT_STEP(launch_mask_ios(L.bits_full, L.rect, L.area_full, L.box_full, L.sel, a->counts + 1, max_sel, a->ori_h,
-                            a->ori_w, L.top_label, obj_feats, a->c, L.ios, nullptr, s));
+                            a->ori_w, L.top_label, obj_feats, a->c, L.ios, nullptr, L.ios_ws, false, s));
   // a14
   NTTT_STEP(launch_decay_rank(L.top_score, L.top_label, L.ios, L.sel, a->counts + 1, max_sel, num_out, L.box_full,
+                              L.area_full,
                               a->out_boxes, a->out_scores, a->out_labels, a->out_index, L.out_slot, a->counts + 2,
                               nullptr, s));
   NTTT_STEP(launch_unpack(L.bits_full, L.rect, L.out_slot, a->counts + 2, num_out, a->ori_h, a->ori_w, a->out_masks,

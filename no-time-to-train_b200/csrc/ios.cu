@@ -12,8 +12,10 @@ namespace nttt {
 
 constexpr int kIosThreads = 256;
 
-// one CTA per selected mask i; warps stride over candidate partners j.  The per-partner metadata (label, area,
-// box, rect) is staged in shared memory once per CTA so the partner loop never waits on dependent global loads.
+// Pair work is symmetric (inter(i,j) and the pair similarity are shared by v_ij and v_ji), so each unordered
+// same-label pair is evaluated once, by the CTA of the lower index, and both row maxima are updated with an
+// integer atomicMax on the float bits (all values are >= 0).  A first tiny kernel compacts the per-mask
+// metadata so the pair kernel never chases sel[] -> labels[] pointers.
 struct IosMeta {
   int4 box;
   int4 rect;
@@ -23,107 +25,149 @@ struct IosMeta {
   int pad;
 };
 
-template <bool kStaged>
+size_t ios_workspace_bytes(int max_sel) {
+  return align_up(sizeof(IosMeta) * (size_t)max_sel, 256) + align_up(sizeof(int32_t) * (size_t)max_sel, 256);
+}
+
+__global__ void __launch_bounds__(256)
+ios_meta_kernel(const int32_t* __restrict__ rect, const int32_t* __restrict__ area_full,
+                const int32_t* __restrict__ box_full, const int32_t* __restrict__ sel,
+                const int32_t* __restrict__ n_sel, int max_sel, const int32_t* __restrict__ labels,
+                IosMeta* __restrict__ meta, int32_t* __restrict__ label_sel, float* __restrict__ ios) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= max_sel) return;
+  ios[j] = 0.0f;  // identity of the row max (the zeroed diagonal, area > 0 case)
+  if (j >= min(*n_sel, max_sel)) { label_sel[j] = -1; return; }
+  IosMeta m;
+  m.src = sel[j];
+  m.label = labels[m.src];
+  m.area = area_full[j];
+  m.box = reinterpret_cast<const int4*>(box_full)[j];
+  m.rect = reinterpret_cast<const int4*>(rect)[j];
+  m.pad = 0;
+  meta[j] = m;
+  label_sel[j] = m.label;
+}
+
+template <int kRegs>  // feature elements per lane held in registers (c <= 32 * kRegs), 0 = read from memory
 __global__ void __launch_bounds__(kIosThreads)
-mask_ios_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restrict__ rect,
-                const int32_t* __restrict__ area_full, const int32_t* __restrict__ box_full,
-                const int32_t* __restrict__ sel, const int32_t* __restrict__ n_sel, int max_sel, int oh, int ow,
-                const int32_t* __restrict__ labels, const float* __restrict__ obj_feats, int c,
-                float* __restrict__ ios, int32_t* __restrict__ inter_out) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  IosMeta* s_meta = reinterpret_cast<IosMeta*>(s_raw);
-  __shared__ float s_best[kIosThreads / 32];
+mask_ios_kernel(const uint32_t* __restrict__ bits_full, const IosMeta* __restrict__ meta,
+                const int32_t* __restrict__ label_sel, const int32_t* __restrict__ n_sel, int max_sel, int oh, int ow,
+                const float* __restrict__ obj_feats, int c, float* __restrict__ ios, int32_t* __restrict__ inter_out) {
+  extern __shared__ int s_label[];
   const int i = blockIdx.x;
   const int nsel = min(*n_sel, max_sel);
   if (i >= nsel) return;
   const int lane = lane_id(), warp = warp_id();
   constexpr int kWarps = kIosThreads / 32;
   const int ow_words = (ow + 31) >> 5;
-  auto load_meta = [&](int j) {
-    IosMeta m;
-    m.src = sel[j];
-    m.label = labels[m.src];
-    m.area = area_full[j];
-    m.box = reinterpret_cast<const int4*>(box_full)[j];
-    m.rect = reinterpret_cast<const int4*>(rect)[j];
-    m.pad = 0;
-    return m;
-  };
-  if (kStaged) {
-    for (int j = threadIdx.x; j < nsel; j += kIosThreads) s_meta[j] = load_meta(j);
-    __syncthreads();
-  }
-  const IosMeta me = kStaged ? s_meta[i] : load_meta(i);
+  for (int j = i + 1 + threadIdx.x; j < nsel; j += kIosThreads) s_label[j] = label_sel[j];
+  const IosMeta me = meta[i];
   const uint32_t* mi = bits_full + (size_t)i * oh * ow_words;
   const float* fi = obj_feats + (size_t)me.src * c;
-  const float area_f = (float)me.area;
+  float freg[kRegs > 0 ? kRegs : 1];
+  if (kRegs > 0) {
+#pragma unroll
+    for (int q = 0; q < kRegs; ++q) freg[q] = (q * 32 + lane < c) ? fi[q * 32 + lane] : 0.0f;
+  }
+  __syncthreads();
+  if (me.area == 0) return;  // NaN row: finalised by the caller (0/0 on the diagonal)
 
-  float best = 0.0f;  // the zeroed diagonal takes part in the row max (area_i > 0 case)
-  for (int j = warp; j < nsel; j += kWarps) {
-    if (j == i) continue;
-    int lab_j;
-    if (kStaged) lab_j = s_meta[j].label; else lab_j = labels[sel[j]];
-    if (lab_j != me.label) continue;
-    const IosMeta mj = kStaged ? s_meta[j] : load_meta(j);
+  float best = 0.0f;
+  for (int j = i + 1 + warp; j < nsel; j += kWarps) {
+    if (s_label[j] != me.label) continue;
+    const IosMeta mj = meta[j];
+    if (mj.area == 0) continue;
+    // inclusive boxes -> overlap window in pixels
+    const int x0 = max(me.box.x, mj.box.x), x1 = min(me.box.z, mj.box.z);
+    const int y0 = max(me.box.y, mj.box.y), y1 = min(me.box.w, mj.box.w);
+    if (x0 > x1 || y0 > y1) continue;
+    const int wlo = max(max(me.rect.z, mj.rect.z), x0 >> 5), whi = min(min(me.rect.w, mj.rect.w), (x1 >> 5) + 1);
+    const int ylo = max(max(me.rect.x, mj.rect.x), y0), yhi = min(min(me.rect.y, mj.rect.y), y1 + 1);
+    const int nw = whi - wlo;
+    if (nw <= 0 || yhi <= ylo) continue;
+    const uint32_t* pj = bits_full + (size_t)j * oh * ow_words;
     int inter = 0;
-    if (me.area > 0 && mj.area > 0) {
-      // inclusive boxes -> overlap window in pixels
-      const int x0 = max(me.box.x, mj.box.x), x1 = min(me.box.z, mj.box.z);
-      const int y0 = max(me.box.y, mj.box.y), y1 = min(me.box.w, mj.box.w);
-      if (x0 <= x1 && y0 <= y1) {
-        const int wlo = max(max(me.rect.z, mj.rect.z), x0 >> 5), whi = min(min(me.rect.w, mj.rect.w), (x1 >> 5) + 1);
-        const int ylo = max(max(me.rect.x, mj.rect.x), y0), yhi = min(min(me.rect.y, mj.rect.y), y1 + 1);
-        const uint32_t* pj = bits_full + (size_t)j * oh * ow_words;
-        const int nw = whi - wlo;
-        if (nw > 0 && yhi > ylo) {
-          const int total = (yhi - ylo) * nw;
-          for (int t = lane; t < total; t += 32) {
-            const int y = ylo + t / nw, w = wlo + t % nw;
-            const size_t o = (size_t)y * ow_words + w;
-            inter += __popc(mi[o] & pj[o]);
-          }
+    if (nw <= 32) {
+      // lanes across the words of a row, 32/nw... simple and coalesced: one row per step, lanes over words
+      const int rows_per_step = 32 / nw;
+      const int ry = lane / nw, wx = lane - ry * nw;
+      if (ry < rows_per_step)
+        for (int y = ylo + ry; y < yhi; y += rows_per_step) {
+          const size_t o = (size_t)y * ow_words + wlo + wx;
+          inter += __popc(__ldg(mi + o) & __ldg(pj + o));
         }
-      }
+    } else {
+      for (int y = ylo; y < yhi; ++y)
+        for (int w = wlo + lane; w < whi; w += 32) {
+          const size_t o = (size_t)y * ow_words + w;
+          inter += __popc(__ldg(mi + o) & __ldg(pj + o));
+        }
     }
     inter = warp_sum(inter);
-    if (inter_out && lane == 0) inter_out[(size_t)i * max_sel + j] = inter;
-    if (inter > 0) {
-      const float* fj = obj_feats + (size_t)mj.src * c;
-      float dot = 0.0f;
-      for (int q = lane; q < c; q += 32) dot = fmaf(fi[q], fj[q], dot);
-      dot = warp_sum(dot);
-      const float s = fmaxf(dot, 0.0f);
-      // ((inter * s) / area_i) * s  — the reference's association
-      const float v = __fmul_rn(__fdiv_rn(__fmul_rn((float)inter, s), area_f), s);
-      best = fmaxf(best, v);
+    if (inter_out && lane == 0) {
+      inter_out[(size_t)i * max_sel + j] = inter;
+      inter_out[(size_t)j * max_sel + i] = inter;
     }
+    if (inter == 0) continue;
+    const float* fj = obj_feats + (size_t)mj.src * c;
+    float dot = 0.0f;
+    if (kRegs > 0) {
+#pragma unroll
+      for (int q = 0; q < kRegs; ++q) dot = fmaf(freg[q], (q * 32 + lane < c) ? __ldg(fj + q * 32 + lane) : 0.0f, dot);
+    } else {
+      for (int q = lane; q < c; q += 32) dot = fmaf(fi[q], fj[q], dot);
+    }
+    dot = warp_sum(dot);
+    const float sim = fmaxf(dot, 0.0f);
+    // ((inter * s) / area) * s  — the reference's association, for both rows of the pair
+    const float num = __fmul_rn((float)inter, sim);
+    const float v_ij = __fmul_rn(__fdiv_rn(num, (float)me.area), sim);
+    const float v_ji = __fmul_rn(__fdiv_rn(num, (float)mj.area), sim);
+    best = fmaxf(best, v_ij);
+    if (lane == 0) atomicMax(reinterpret_cast<int*>(ios + j), __float_as_int(v_ji));
   }
-  if (lane == 0) s_best[warp] = best;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float b = s_best[0];
-    for (int w = 1; w < kWarps; ++w) b = fmaxf(b, s_best[w]);
-    // empty full-res mask: 0/0 on the diagonal -> NaN, and torch.max propagates it
-    ios[i] = me.area == 0 ? __int_as_float(0x7fc00000) : b;
-  }
+  if (lane == 0 && best > 0.0f) atomicMax(reinterpret_cast<int*>(ios + i), __float_as_int(best));
 }
 
+// rows of empty full-res masks: 0/0 on the diagonal -> NaN, and torch.max propagates it
+__global__ void __launch_bounds__(256)
+ios_finalize_kernel(const int32_t* __restrict__ area_full, const int32_t* __restrict__ n_sel, int max_sel,
+                    float* __restrict__ ios) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < min(*n_sel, max_sel) && area_full[j] == 0) ios[j] = __int_as_float(0x7fc00000);
+}
+
+// finalize=false leaves the NaN rows to the consumer (decay_rank_kernel applies the same rule)
 int launch_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_t* area_full, const int32_t* box_full,
                     const int32_t* sel, const int32_t* n_sel, int max_sel, int oh, int ow, const int32_t* labels,
-                    const float* obj_feats, int c, float* ios, int32_t* inter_out, cudaStream_t s) {
+                    const float* obj_feats, int c, float* ios, int32_t* inter_out, void* ws, bool finalize,
+                    cudaStream_t s) {
   if (max_sel <= 0) return NTTT_OK;
   if (inter_out) NTTT_CUDA(cudaMemsetAsync(inter_out, 0, sizeof(int32_t) * (size_t)max_sel * max_sel, s));
-  const size_t smem = sizeof(IosMeta) * (size_t)max_sel;
-  if (smem <= 160 * 1024) {
-    if (smem > 48 * 1024)
-      NTTT_CUDA(cudaFuncSetAttribute(mask_ios_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mask_ios_kernel<true><<<max_sel, kIosThreads, smem, s>>>(bits_full, rect, area_full, box_full, sel, n_sel, max_sel,
-                                                            oh, ow, labels, obj_feats, c, ios, inter_out);
-  } else {
-    mask_ios_kernel<false><<<max_sel, kIosThreads, 0, s>>>(bits_full, rect, area_full, box_full, sel, n_sel, max_sel,
-                                                          oh, ow, labels, obj_feats, c, ios, inter_out);
-  }
+  IosMeta* meta = static_cast<IosMeta*>(ws);
+  int32_t* label_sel = reinterpret_cast<int32_t*>(static_cast<char*>(ws) + align_up(sizeof(IosMeta) * (size_t)max_sel, 256));
+  ios_meta_kernel<<<ceil_div(max_sel, 256), 256, 0, s>>>(rect, area_full, box_full, sel, n_sel, max_sel, labels, meta,
+                                                         label_sel, ios);
   NTTT_LAUNCH_CHECK();
+  const size_t smem = sizeof(int) * (size_t)max_sel;
+  if (smem > 160 * 1024) return NTTT_EUNSUPPORTED;
+#define NTTT_IOS_LAUNCH(R)                                                                                          \
+  do {                                                                                                              \
+    if (smem > 48 * 1024)                                                                                           \
+      NTTT_CUDA(cudaFuncSetAttribute(mask_ios_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mask_ios_kernel<R><<<max_sel, kIosThreads, smem, s>>>(bits_full, meta, label_sel, n_sel, max_sel, oh, ow,      \
+                                                          obj_feats, c, ios, inter_out);                            \
+  } while (0)
+  if (c <= 384) NTTT_IOS_LAUNCH(12);
+  else if (c <= 1024) NTTT_IOS_LAUNCH(32);
+  else NTTT_IOS_LAUNCH(0);
+#undef NTTT_IOS_LAUNCH
+  NTTT_LAUNCH_CHECK();
+  if (finalize) {
+    ios_finalize_kernel<<<ceil_div(max_sel, 256), 256, 0, s>>>(area_full, n_sel, max_sel, ios);
+    NTTT_LAUNCH_CHECK();
+  }
   return NTTT_OK;
 }
 
@@ -143,6 +187,7 @@ __global__ void __launch_bounds__(1024)
 decay_rank_kernel(const float* __restrict__ top_score, const int32_t* __restrict__ labels,
                   const float* __restrict__ ios, const int32_t* __restrict__ sel, const int32_t* __restrict__ n_sel,
                   int max_sel, int n_pad, int num_out, const int32_t* __restrict__ box_full,
+                  const int32_t* __restrict__ area_full,
                   int64_t* __restrict__ out_boxes, float* __restrict__ out_scores, int64_t* __restrict__ out_labels,
                   int32_t* __restrict__ out_index, int32_t* __restrict__ out_slot, int32_t* __restrict__ n_out,
                   float* __restrict__ decayed_out) {
@@ -152,7 +197,9 @@ decay_rank_kernel(const float* __restrict__ top_score, const int32_t* __restrict
   for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
     unsigned long long key = ~0ull;
     if (i < nsel) {
-      const float d = __fmul_rn(top_score[sel[i]], sqrtf(__fsub_rn(1.0f, ios[i])));
+      // empty full-res mask: the reference's 0/0 on the IoS diagonal -> NaN (torch.max propagates it)
+      const float io = (area_full && area_full[i] == 0) ? __int_as_float(0x7fc00000) : ios[i];
+      const float d = __fmul_rn(top_score[sel[i]], sqrtf(__fsub_rn(1.0f, io)));
       s_val[i] = d;
       if (decayed_out) decayed_out[i] = d;
       key = ((unsigned long long)desc_key_nanfirst(d) << 32) | (uint32_t)i;
@@ -188,7 +235,8 @@ decay_rank_kernel(const float* __restrict__ top_score, const int32_t* __restrict
 }
 
 int launch_decay_rank(const float* top_score, const int32_t* labels, const float* ios, const int32_t* sel,
-                      const int32_t* n_sel, int max_sel, int num_out, const int32_t* box_full, int64_t* out_boxes,
+                      const int32_t* n_sel, int max_sel, int num_out, const int32_t* box_full,
+                      const int32_t* area_full, int64_t* out_boxes,
                       float* out_scores, int64_t* out_labels, int32_t* out_index, int32_t* out_slot, int32_t* n_out,
                       float* decayed_out, cudaStream_t s) {
   if (max_sel <= 0 || num_out <= 0) {
@@ -202,7 +250,7 @@ int launch_decay_rank(const float* top_score, const int32_t* labels, const float
   if (smem > 48 * 1024)
     NTTT_CUDA(cudaFuncSetAttribute(decay_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   decay_rank_kernel<<<1, 1024, smem, s>>>(top_score, labels, ios, sel, n_sel, max_sel, n_pad, num_out, box_full,
-                                          out_boxes, out_scores, out_labels, out_index, out_slot, n_out, decayed_out);
+                                          area_full, out_boxes, out_scores, out_labels, out_index, out_slot, n_out, decayed_out);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }

@@ -183,9 +183,11 @@ def mask_ios(bits_full, rect, area_full, box_full, sel, n_sel, ori_hw, labels, o
     ios = torch.zeros((max_sel,), dtype=torch.float32, device=dev)
     inter = torch.zeros((max_sel, max_sel), dtype=torch.int32, device=dev) if want_inter else None
     lib = _lib.load()
+    ws_bytes = lib.nttt_mask_ios_workspace_bytes(max_sel)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     _lib.check(lib.nttt_mask_ios(_ptr(bits_full), _ptr(rect), _ptr(area_full), _ptr(box_full), _ptr(sel), _ptr(n_sel),
-                                 max_sel, oh, ow, _ptr(labels), _ptr(obj_feats), c, _ptr(ios), _ptr(inter),
-                                 _stream(dev)), "nttt_mask_ios")
+                                 max_sel, oh, ow, _ptr(labels), _ptr(obj_feats), c, _ptr(ios), _ptr(inter), _ptr(ws),
+                                 ws_bytes, _stream(dev)), "nttt_mask_ios")
     return (ios, inter) if want_inter else ios
 
 
