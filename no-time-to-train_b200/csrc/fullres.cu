@@ -86,12 +86,6 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
     const int ya = max(t.y_grp_start[g], r0), yb = min(t.y_grp_start[g + 1], r1);
     const int nrows = yb - ya;
     const int ry0 = t.ymin[ya], rys = t.ysize[ya];
-    float wyv[kGrpMax][kTapsReg];  // vertical weights of the group's rows (uniform across the warp)
-#pragma unroll
-    for (int j = 0; j < kGrpMax; ++j)
-#pragma unroll
-      for (int r = 0; r < kTapsReg; ++r)
-        wyv[j][r] = (j < nrows && r < rys) ? __ldg(t.wy + (size_t)(ya + j) * t.ty + r) : 0.0f;
     for (int wbase = w0; wbase < w1; wbase += 32) {
       const int wi = wbase + lane;
       const bool active = wi < w1;
@@ -132,37 +126,7 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
         const int cx = inb ? t.xmin[x] : 0, cs = inb ? t.xsize[x] : 1;
         const float* wx = t.wx + (size_t)(inb ? x : 0) * t.tx;
         const float* p = src + (size_t)ry0 * iw + cx;
-        if (rys <= kTapsReg && t.tx <= 3) {
-          // horizontal pass once per group (all of its loads issued back to back: one exposed latency per
-          // mixed word instead of one per tap), vertical pass per row.  Taps beyond `cs` are never loaded,
-          // so the arithmetic is exactly acc = s0*w0; acc = fma(s_j, w_j, acc) for j < cs.
-          float wv[3], sv[kTapsReg][3];
-#pragma unroll
-          for (int q = 0; q < 3; ++q) wv[q] = (inb && q < cs) ? __ldg(wx + q) : 0.0f;
-#pragma unroll
-          for (int r = 0; r < kTapsReg; ++r)
-#pragma unroll
-            for (int q = 0; q < 3; ++q) sv[r][q] = (inb && r < rys && q < cs) ? __ldg(p + (size_t)r * iw + q) : 0.0f;
-          float T[kTapsReg];
-#pragma unroll
-          for (int r = 0; r < kTapsReg; ++r) {
-            float acc = __fmul_rn(sv[r][0], wv[0]);
-            if (cs > 1) acc = __fmaf_rn(sv[r][1], wv[1], acc);
-            if (cs > 2) acc = __fmaf_rn(sv[r][2], wv[2], acc);
-            T[r] = acc;
-          }
-#pragma unroll
-          for (int j = 0; j < kGrpMax; ++j) {
-            if (j < nrows) {
-              float acc = __fmul_rn(T[0], wyv[j][0]);
-#pragma unroll
-              for (int r = 1; r < kTapsReg; ++r)
-                if (r < rys) acc = __fmaf_rn(T[r], wyv[j][r], acc);
-              const uint32_t res = __ballot_sync(kFull, inb && acc > 0.0f);
-              if (lane == src_lane) words[j] = res;
-            }
-          }
-        } else if (rys <= kTapsReg) {
+        if (rys <= kTapsReg) {
           // horizontal pass once per group, vertical pass per row
           float T[kTapsReg];
 #pragma unroll
