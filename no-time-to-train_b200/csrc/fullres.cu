@@ -39,41 +39,69 @@ constexpr int kScratchInts = 8;
 constexpr int kBig = 1 << 30;
 constexpr int kTapsReg = 4;  // footprints of up to 4 input rows keep their horizontal-pass values in registers
 
+// per selected mask, resolved once by a tiny pre-kernel so that the four CTAs of a mask do not each chase
+// sel[] -> box_lr[] -> span tables; scratch[kScratchInts*k + 6..7] is unused padding
+struct UpMeta {
+  int src;           // index into logits / bits_lr
+  int r0, r1;        // output rows [r0, r1)
+  int w0, w1;        // output words [w0, w1)
+  int lr0, lr1;      // low-res rows [lr0, lr1) under those output rows
+  int safe;          // flags bit0
+};
+
+__global__ void __launch_bounds__(256)
+upsample_meta_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __restrict__ box_lr,
+                     const int32_t* __restrict__ flags_lr, int ih, int iw, const int32_t* __restrict__ sel,
+                     const int32_t* __restrict__ n_sel, int max_sel, UpTables t, UpMeta* __restrict__ meta,
+                     int32_t* __restrict__ rect, int32_t* __restrict__ scratch) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= max_sel) return;
+#pragma unroll
+  for (int q = 0; q < kScratchInts; ++q) scratch[(size_t)k * kScratchInts + q] = 0;
+  if (k >= min(*n_sel, max_sel)) return;
+  UpMeta m;
+  m.src = sel[k];
+  const int4 b = reinterpret_cast<const int4*>(box_lr)[m.src];
+  // empty low-res mask <=> box all zero AND bit (0,0) clear
+  const bool lr_empty = (b.x | b.y | b.z | b.w) == 0 && (bits_lr[(size_t)m.src * ih * (iw >> 5)] & 1u) == 0;
+  m.r0 = m.r1 = m.w0 = m.w1 = m.lr0 = m.lr1 = 0;
+  if (!lr_empty) {
+    m.r0 = t.y_tlo[b.y];
+    m.r1 = t.y_tlo[b.w] + t.y_tlen[b.w];
+    const int c0 = t.x_tlo[b.x];
+    const int c1 = t.x_tlo[b.z] + t.x_tlen[b.z];
+    m.w0 = c0 >> 5;
+    m.w1 = (c1 + 31) >> 5;
+    m.lr0 = t.ymin[m.r0];
+    m.lr1 = t.ymin[m.r1 - 1] + t.ysize[m.r1 - 1];
+  }
+  m.safe = flags_lr[m.src] & 1;
+  meta[k] = m;
+  reinterpret_cast<int4*>(rect)[k] = make_int4(m.r0, m.r1, m.w0, m.w1);
+}
+
 __global__ void __launch_bounds__(kUpThreads)
 upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restrict__ bits_lr,
-                     const int32_t* __restrict__ box_lr, const int32_t* __restrict__ flags_lr, int ih, int iw,
-                     const int32_t* __restrict__ sel, const int32_t* __restrict__ n_sel, int max_sel, int oh, int ow,
-                     UpTables t, uint32_t* __restrict__ bits_full, int32_t* __restrict__ rect,
-                     int32_t* __restrict__ area_full, int32_t* __restrict__ box_full, int32_t* __restrict__ scratch) {
-  extern __shared__ uint32_t s_lr[];  // ih * iw/32 packed low-res bits of this mask
+                     const UpMeta* __restrict__ meta, int ih, int iw, const int32_t* __restrict__ n_sel, int max_sel,
+                     int oh, int ow, UpTables t, uint32_t* __restrict__ bits_full, int32_t* __restrict__ area_full,
+                     int32_t* __restrict__ box_full, int32_t* __restrict__ scratch) {
+  extern __shared__ uint32_t s_lr[];  // packed low-res bits of this mask, rows [lr0, lr1) only
   __shared__ int s_red[5];
   const int k = blockIdx.y;
   const int nsel = min(*n_sel, max_sel);
   if (k >= nsel) return;
-  const int src_idx = sel[k];
+  const UpMeta mt = meta[k];
+  const int src_idx = mt.src;
   const int lr_wpr = iw >> 5;
   const int ow_words = (ow + 31) >> 5;
   const int lane = lane_id(), warp = warp_id();
   constexpr int kWarps = kUpThreads / 32;
+  const int r0 = mt.r0, r1 = mt.r1, w0 = mt.w0, w1 = mt.w1;
 
-  const uint32_t* lr = bits_lr + (size_t)src_idx * ih * lr_wpr;
-  for (int i = threadIdx.x; i < ih * lr_wpr; i += kUpThreads) s_lr[i] = lr[i];
+  const uint32_t* lr = bits_lr + ((size_t)src_idx * ih + mt.lr0) * lr_wpr;
+  for (int i = threadIdx.x; i < (mt.lr1 - mt.lr0) * lr_wpr; i += kUpThreads) s_lr[i] = lr[i];
   if (threadIdx.x < 5) s_red[threadIdx.x] = 0;
-
-  const int4 b = reinterpret_cast<const int4*>(box_lr)[src_idx];
-  // empty low-res mask <=> box all zero AND bit (0,0) clear
-  const bool lr_empty = (b.x | b.y | b.z | b.w) == 0 && (lr[0] & 1u) == 0;
-  int r0 = 0, r1 = 0, w0 = 0, w1 = 0;
-  if (!lr_empty) {
-    r0 = t.y_tlo[b.y];
-    r1 = t.y_tlo[b.w] + t.y_tlen[b.w];
-    const int c0 = t.x_tlo[b.x];
-    const int c1 = t.x_tlo[b.z] + t.x_tlen[b.z];
-    w0 = c0 >> 5;
-    w1 = (c1 + 31) >> 5;
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<int4*>(rect)[k] = make_int4(r0, r1, w0, w1);
-  const bool safe = (flags_lr[src_idx] & 1) != 0;
+  const bool safe = mt.safe != 0;
   const float* src = logits + (size_t)src_idx * ih * iw;
   uint32_t* dst = bits_full + (size_t)k * oh * ow_words;
   __syncthreads();
@@ -101,7 +129,7 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
         const int c1 = t.xmin[x1] + t.xsize[x1];  // exclusive
         bool all0 = true, all1 = true;
         for (int r = 0; r < rys; ++r) {
-          const uint32_t* row = s_lr + (ry0 + r) * lr_wpr;
+          const uint32_t* row = s_lr + (ry0 + r - mt.lr0) * lr_wpr;
           for (int cw = c0 >> 5; cw <= (c1 - 1) >> 5; ++cw) {
             const int lo = max(c0 - (cw << 5), 0), hi = min(c1 - (cw << 5), 32);
             const uint32_t m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
@@ -219,16 +247,21 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
   if (smem > 160 * 1024) return NTTT_EUNSUPPORTED;
   if (smem > 48 * 1024)
     NTTT_CUDA(cudaFuncSetAttribute(upsample_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  NTTT_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int32_t) * kScratchInts * (size_t)max_sel, s));
   UpTables t{tx.xmin, tx.xsize, tx.w, tx.taps, ty.xmin, ty.xsize, ty.w, ty.taps, tx.t_lo, tx.t_len, ty.t_lo, ty.t_len,
              ty.grp_of, ty.grp_start};
+  UpMeta* meta = reinterpret_cast<UpMeta*>(scratch + (size_t)kScratchInts * max_sel);
+  upsample_meta_kernel<<<ceil_div(max_sel, 256), 256, 0, s>>>(bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, t,
+                                                              meta, rect, scratch);
+  NTTT_LAUNCH_CHECK();
   dim3 grid(kUpSplit, max_sel);
-  upsample_pack_kernel<<<grid, kUpThreads, smem, s>>>(logits, bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel,
-                                                      oh, ow, t, bits_full, rect, area_full, box_full, scratch);
+  upsample_pack_kernel<<<grid, kUpThreads, smem, s>>>(logits, bits_lr, meta, ih, iw, n_sel, max_sel, oh, ow, t, bits_full,
+                                                      area_full, box_full, scratch);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }
-size_t upsample_scratch_bytes(int max_sel) { return sizeof(int32_t) * kScratchInts * (size_t)max_sel; }
+size_t upsample_scratch_bytes(int max_sel) {
+  return (sizeof(int32_t) * kScratchInts + sizeof(UpMeta)) * (size_t)max_sel;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // unpack: packed words -> torch.bool bytes.  `index` (nullable) maps output slot j -> packed mask k.

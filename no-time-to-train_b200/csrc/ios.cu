@@ -49,85 +49,106 @@ ios_meta_kernel(const int32_t* __restrict__ rect, const int32_t* __restrict__ ar
   label_sel[j] = m.label;
 }
 
-template <int kRegs>  // feature elements per lane held in registers (c <= 32 * kRegs), 0 = read from memory
+// One CTA per selected mask i.  Phase 1: all threads scan the partners j > i (label, non-empty, overlapping
+// boxes) and append the survivors to a shared candidate list.  Phase 2: the WHOLE CTA evaluates one candidate at
+// a time — popcount of the AND over the overlap window plus the 1024-wide feature dot product, both spread over
+// all threads with several loads in flight, one block reduction per candidate.  (One warp per pair left the
+// big windows — thousands of words — latency-bound on a single warp.)
+constexpr int kIosMaxCand = 1024;
+
 __global__ void __launch_bounds__(kIosThreads)
 mask_ios_kernel(const uint32_t* __restrict__ bits_full, const IosMeta* __restrict__ meta,
                 const int32_t* __restrict__ label_sel, const int32_t* __restrict__ n_sel, int max_sel, int oh, int ow,
                 const float* __restrict__ obj_feats, int c, float* __restrict__ ios, int32_t* __restrict__ inter_out) {
-  extern __shared__ int s_label[];
+  __shared__ int s_cand[kIosMaxCand];
+  __shared__ int s_ncand;
+  __shared__ int s_inter[kIosThreads / 32];
+  __shared__ float s_dot[kIosThreads / 32];
   const int i = blockIdx.x;
   const int nsel = min(*n_sel, max_sel);
   if (i >= nsel) return;
   const int lane = lane_id(), warp = warp_id();
   constexpr int kWarps = kIosThreads / 32;
   const int ow_words = (ow + 31) >> 5;
-  for (int j = i + 1 + threadIdx.x; j < nsel; j += kIosThreads) s_label[j] = label_sel[j];
   const IosMeta me = meta[i];
+  if (me.area == 0) return;  // NaN row: finalised by the caller (0/0 on the diagonal)
   const uint32_t* mi = bits_full + (size_t)i * oh * ow_words;
   const float* fi = obj_feats + (size_t)me.src * c;
-  float freg[kRegs > 0 ? kRegs : 1];
-  if (kRegs > 0) {
-#pragma unroll
-    for (int q = 0; q < kRegs; ++q) freg[q] = (q * 32 + lane < c) ? fi[q * 32 + lane] : 0.0f;
-  }
-  __syncthreads();
-  if (me.area == 0) return;  // NaN row: finalised by the caller (0/0 on the diagonal)
+  float best = 0.0f;  // tracked by thread 0
 
-  float best = 0.0f;
-  for (int j = i + 1 + warp; j < nsel; j += kWarps) {
-    if (s_label[j] != me.label) continue;
-    const IosMeta mj = meta[j];
-    if (mj.area == 0) continue;
-    // inclusive boxes -> overlap window in pixels
-    const int x0 = max(me.box.x, mj.box.x), x1 = min(me.box.z, mj.box.z);
-    const int y0 = max(me.box.y, mj.box.y), y1 = min(me.box.w, mj.box.w);
-    if (x0 > x1 || y0 > y1) continue;
-    const int wlo = max(max(me.rect.z, mj.rect.z), x0 >> 5), whi = min(min(me.rect.w, mj.rect.w), (x1 >> 5) + 1);
-    const int ylo = max(max(me.rect.x, mj.rect.x), y0), yhi = min(min(me.rect.y, mj.rect.y), y1 + 1);
-    const int nw = whi - wlo;
-    if (nw <= 0 || yhi <= ylo) continue;
-    const uint32_t* pj = bits_full + (size_t)j * oh * ow_words;
-    int inter = 0;
-    if (nw <= 32) {
-      // lanes across the words of a row, 32/nw... simple and coalesced: one row per step, lanes over words
-      const int rows_per_step = 32 / nw;
-      const int ry = lane / nw, wx = lane - ry * nw;
-      if (ry < rows_per_step)
-        for (int y = ylo + ry; y < yhi; y += rows_per_step) {
-          const size_t o = (size_t)y * ow_words + wlo + wx;
-          inter += __popc(__ldg(mi + o) & __ldg(pj + o));
-        }
-    } else {
-      for (int y = ylo; y < yhi; ++y)
-        for (int w = wlo + lane; w < whi; w += 32) {
-          const size_t o = (size_t)y * ow_words + w;
-          inter += __popc(__ldg(mi + o) & __ldg(pj + o));
-        }
+  for (int base = i + 1; base < nsel; base += kIosMaxCand) {
+    if (threadIdx.x == 0) s_ncand = 0;
+    __syncthreads();
+    const int end = min(base + kIosMaxCand, nsel);
+    for (int j = base + threadIdx.x; j < end; j += kIosThreads) {
+      if (label_sel[j] != me.label) continue;
+      const IosMeta mj = meta[j];
+      if (mj.area == 0) continue;
+      if (max(me.box.x, mj.box.x) > min(me.box.z, mj.box.z) || max(me.box.y, mj.box.y) > min(me.box.w, mj.box.w)) continue;
+      s_cand[atomicAdd(&s_ncand, 1)] = j;
     }
-    inter = warp_sum(inter);
-    if (inter_out && lane == 0) {
-      inter_out[(size_t)i * max_sel + j] = inter;
-      inter_out[(size_t)j * max_sel + i] = inter;
-    }
-    if (inter == 0) continue;
-    const float* fj = obj_feats + (size_t)mj.src * c;
-    float dot = 0.0f;
-    if (kRegs > 0) {
+    __syncthreads();
+    const int ncand = s_ncand;
+    for (int q = 0; q < ncand; ++q) {
+      const int j = s_cand[q];
+      const IosMeta mj = meta[j];
+      const int x0 = max(me.box.x, mj.box.x), x1 = min(me.box.z, mj.box.z);
+      const int y0 = max(me.box.y, mj.box.y), y1 = min(me.box.w, mj.box.w);
+      const int wlo = max(max(me.rect.z, mj.rect.z), x0 >> 5), whi = min(min(me.rect.w, mj.rect.w), (x1 >> 5) + 1);
+      const int ylo = max(max(me.rect.x, mj.rect.x), y0), yhi = min(min(me.rect.y, mj.rect.y), y1 + 1);
+      const int nw = whi - wlo;
+      const uint32_t* pj = bits_full + (size_t)j * oh * ow_words;
+      int inter = 0;
+      if (nw > 0 && yhi > ylo) {
+        // threads tile the window: tx over words, ty over rows (tx extent = next pow2 >= nw, <= 32)
+        int txn = 1;
+        while (txn < nw && txn < 32) txn <<= 1;
+        const int tx = threadIdx.x & (txn - 1), ty = threadIdx.x / txn, tyn = kIosThreads / txn;
+        for (int w = wlo + tx; w < whi; w += txn) {
+          int y = ylo + ty;
+          for (; y + 3 * tyn < yhi; y += 4 * tyn) {  // four independent load pairs in flight
+            const size_t o0 = (size_t)y * ow_words + w, o1 = o0 + (size_t)tyn * ow_words;
+            const size_t o2 = o1 + (size_t)tyn * ow_words, o3 = o2 + (size_t)tyn * ow_words;
+            const uint32_t a0 = __ldg(mi + o0), b0 = __ldg(pj + o0), a1 = __ldg(mi + o1), b1 = __ldg(pj + o1);
+            const uint32_t a2 = __ldg(mi + o2), b2 = __ldg(pj + o2), a3 = __ldg(mi + o3), b3 = __ldg(pj + o3);
+            inter += __popc(a0 & b0) + __popc(a1 & b1) + __popc(a2 & b2) + __popc(a3 & b3);
+          }
+          for (; y < yhi; y += tyn) {
+            const size_t o = (size_t)y * ow_words + w;
+            inter += __popc(__ldg(mi + o) & __ldg(pj + o));
+          }
+        }
+      }
+      // feature dot product, spread over the CTA (needed only if the masks intersect, but computing it in the
+      // same pass saves a second reduction round)
+      const float* fj = obj_feats + (size_t)mj.src * c;
+      float dot = 0.0f;
+      for (int e = threadIdx.x; e < c; e += kIosThreads) dot = fmaf(__ldg(fi + e), __ldg(fj + e), dot);
+      inter = warp_sum(inter);
+      dot = warp_sum(dot);
+      if (lane == 0) { s_inter[warp] = inter; s_dot[warp] = dot; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int it = 0;
+        float dt = 0.0f;
 #pragma unroll
-      for (int q = 0; q < kRegs; ++q) dot = fmaf(freg[q], (q * 32 + lane < c) ? __ldg(fj + q * 32 + lane) : 0.0f, dot);
-    } else {
-      for (int q = lane; q < c; q += 32) dot = fmaf(fi[q], fj[q], dot);
+        for (int w = 0; w < kWarps; ++w) { it += s_inter[w]; dt += s_dot[w]; }
+        if (inter_out) {
+          inter_out[(size_t)i * max_sel + j] = it;
+          inter_out[(size_t)j * max_sel + i] = it;
+        }
+        if (it > 0) {
+          const float sim = fmaxf(dt, 0.0f);
+          // ((inter * s) / area) * s  — the reference's association, for both rows of the pair
+          const float num = __fmul_rn((float)it, sim);
+          best = fmaxf(best, __fmul_rn(__fdiv_rn(num, (float)me.area), sim));
+          atomicMax(reinterpret_cast<int*>(ios + j), __float_as_int(__fmul_rn(__fdiv_rn(num, (float)mj.area), sim)));
+        }
+      }
+      __syncthreads();
     }
-    dot = warp_sum(dot);
-    const float sim = fmaxf(dot, 0.0f);
-    // ((inter * s) / area) * s  — the reference's association, for both rows of the pair
-    const float num = __fmul_rn((float)inter, sim);
-    const float v_ij = __fmul_rn(__fdiv_rn(num, (float)me.area), sim);
-    const float v_ji = __fmul_rn(__fdiv_rn(num, (float)mj.area), sim);
-    best = fmaxf(best, v_ij);
-    if (lane == 0) atomicMax(reinterpret_cast<int*>(ios + j), __float_as_int(v_ji));
   }
-  if (lane == 0 && best > 0.0f) atomicMax(reinterpret_cast<int*>(ios + i), __float_as_int(best));
+  if (threadIdx.x == 0 && best > 0.0f) atomicMax(reinterpret_cast<int*>(ios + i), __float_as_int(best));
 }
 
 // rows of empty full-res masks: 0/0 on the diagonal -> NaN, and torch.max propagates it
@@ -150,19 +171,8 @@ int launch_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_
   ios_meta_kernel<<<ceil_div(max_sel, 256), 256, 0, s>>>(rect, area_full, box_full, sel, n_sel, max_sel, labels, meta,
                                                          label_sel, ios);
   NTTT_LAUNCH_CHECK();
-  const size_t smem = sizeof(int) * (size_t)max_sel;
-  if (smem > 160 * 1024) return NTTT_EUNSUPPORTED;
-#define NTTT_IOS_LAUNCH(R)                                                                                          \
-  do {                                                                                                              \
-    if (smem > 48 * 1024)                                                                                           \
-      NTTT_CUDA(cudaFuncSetAttribute(mask_ios_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    mask_ios_kernel<R><<<max_sel, kIosThreads, smem, s>>>(bits_full, meta, label_sel, n_sel, max_sel, oh, ow,      \
-                                                          obj_feats, c, ios, inter_out);                            \
-  } while (0)
-  if (c <= 384) NTTT_IOS_LAUNCH(12);
-  else if (c <= 1024) NTTT_IOS_LAUNCH(32);
-  else NTTT_IOS_LAUNCH(0);
-#undef NTTT_IOS_LAUNCH
+  mask_ios_kernel<<<max_sel, kIosThreads, 0, s>>>(bits_full, meta, label_sel, n_sel, max_sel, oh, ow, obj_feats, c, ios,
+                                                  inter_out);
   NTTT_LAUNCH_CHECK();
   if (finalize) {
     ios_finalize_kernel<<<ceil_div(max_sel, 256), 256, 0, s>>>(area_full, n_sel, max_sel, ios);
