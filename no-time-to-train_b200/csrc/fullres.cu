@@ -109,33 +109,55 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
   int area = 0, minx = kBig, maxx = -1, miny = kBig, maxy = -1;
   const int g0 = r1 > r0 ? t.y_grp_of[r0] : 0;
   const int g1 = r1 > r0 ? t.y_grp_of[r1 - 1] + 1 : 0;
+  for (int wbase = w0; wbase < w1; wbase += 32) {
+    // per-lane (= per output word) constants, hoisted out of the row-group loop
+    const int wi = wbase + lane;
+    const bool active = wi < w1;
+    const int x0 = min(wi << 5, ow - 1);
+    const int x1 = min(x0 + 31, ow - 1);
+    const uint32_t valid = (x1 - x0 == 31) ? 0xffffffffu : ((1u << (x1 - x0 + 1)) - 1u);
+    const int c0 = t.xmin[x0];
+    const int c1 = t.xmin[x1] + t.xsize[x1];  // exclusive
+    const int cw0 = c0 >> 5;
+    const bool two_words = ((c1 - 1) >> 5) <= cw0 + 1;  // the footprint columns span at most two low-res words
+    uint32_t m0, m1 = 0;
+    {
+      const int lo = c0 - (cw0 << 5), hi = min(c1 - (cw0 << 5), 32);
+      m0 = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+      const int hi1 = c1 - ((cw0 + 1) << 5);
+      if (hi1 > 0) m1 = hi1 >= 32 ? 0xffffffffu : ((1u << hi1) - 1u);
+    }
+    uint32_t colbits = 0;
   for (int g = g0 + blockIdx.x * kWarps + warp; g < g1; g += kUpSplit * kWarps) {
     // rows [ya, yb) of this group share the input rows [ry0, ry0 + rys)
     const int ya = max(t.y_grp_start[g], r0), yb = min(t.y_grp_start[g + 1], r1);
     const int nrows = yb - ya;
     const int ry0 = t.ymin[ya], rys = t.ysize[ya];
-    for (int wbase = w0; wbase < w1; wbase += 32) {
-      const int wi = wbase + lane;
-      const bool active = wi < w1;
+    {
       uint32_t words[kGrpMax];
 #pragma unroll
       for (int j = 0; j < kGrpMax; ++j) words[j] = 0;
       bool mixed = false;
       if (active) {
-        const int x0 = wi << 5;
-        const int x1 = min(x0 + 31, ow - 1);
-        const uint32_t valid = (x1 - x0 == 31) ? 0xffffffffu : ((1u << (x1 - x0 + 1)) - 1u);
-        const int c0 = t.xmin[x0];
-        const int c1 = t.xmin[x1] + t.xsize[x1];  // exclusive
         bool all0 = true, all1 = true;
-        for (int r = 0; r < rys; ++r) {
-          const uint32_t* row = s_lr + (ry0 + r - mt.lr0) * lr_wpr;
-          for (int cw = c0 >> 5; cw <= (c1 - 1) >> 5; ++cw) {
-            const int lo = max(c0 - (cw << 5), 0), hi = min(c1 - (cw << 5), 32);
-            const uint32_t m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-            const uint32_t v = row[cw] & m;
-            all0 = all0 && (v == 0);
-            all1 = all1 && (v == m);
+        if (two_words) {
+          for (int r = 0; r < rys; ++r) {
+            const uint32_t* row = s_lr + (ry0 + r - mt.lr0) * lr_wpr + cw0;
+            const uint32_t v0 = row[0] & m0;
+            const uint32_t v1 = m1 ? (row[1] & m1) : 0u;
+            all0 = all0 && ((v0 | v1) == 0);
+            all1 = all1 && (v0 == m0) && (v1 == m1);
+          }
+        } else {
+          for (int r = 0; r < rys; ++r) {
+            const uint32_t* row = s_lr + (ry0 + r - mt.lr0) * lr_wpr;
+            for (int cw = cw0; cw <= (c1 - 1) >> 5; ++cw) {
+              const int lo = max(c0 - (cw << 5), 0), hi = min(c1 - (cw << 5), 32);
+              const uint32_t m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+              const uint32_t v = row[cw] & m;
+              all0 = all0 && (v == 0);
+              all1 = all1 && (v == m);
+            }
           }
         }
         if (all1 && safe && !all0) {
@@ -187,22 +209,24 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
           }
         }
       }
-      if (active) {
 #pragma unroll
-        for (int j = 0; j < kGrpMax; ++j) {
-          if (j < nrows) {
-            const uint32_t word = words[j];
-            dst[(size_t)(ya + j) * ow_words + wi] = word;
-            if (word) {
-              area += __popc(word);
-              minx = min(minx, (wi << 5) + __ffs(word) - 1);
-              maxx = max(maxx, (wi << 5) + 31 - __clz(word));
-              miny = min(miny, ya + j);
-              maxy = max(maxy, ya + j);
-            }
+      for (int j = 0; j < kGrpMax; ++j) {
+        if (j < nrows) {
+          const uint32_t word = active ? words[j] : 0u;
+          if (active) dst[(size_t)(ya + j) * ow_words + wi] = word;
+          area += __popc(word);
+          colbits |= word;
+          if (__any_sync(kFull, word != 0)) {  // warp-uniform row extent
+            miny = min(miny, ya + j);
+            maxy = max(maxy, ya + j);
           }
         }
       }
+    }
+  }
+    if (colbits) {
+      minx = min(minx, (wi << 5) + __ffs(colbits) - 1);
+      maxx = max(maxx, (wi << 5) + 31 - __clz(colbits));
     }
   }
   area = warp_sum(area);

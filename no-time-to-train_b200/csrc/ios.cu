@@ -25,16 +25,21 @@ struct IosMeta {
   int pad;
 };
 
+static size_t ios_max_pairs(int max_sel) { return (size_t)max_sel * (max_sel > 1 ? max_sel - 1 : 1) / 2 + 1; }
+
 size_t ios_workspace_bytes(int max_sel) {
-  return align_up(sizeof(IosMeta) * (size_t)max_sel, 256) + align_up(sizeof(int32_t) * (size_t)max_sel, 256);
+  return align_up(sizeof(IosMeta) * (size_t)max_sel, 256) + align_up(sizeof(int32_t) * (size_t)max_sel, 256) +
+         align_up(sizeof(int2) * ios_max_pairs(max_sel), 256) + 256;
 }
 
 __global__ void __launch_bounds__(256)
 ios_meta_kernel(const int32_t* __restrict__ rect, const int32_t* __restrict__ area_full,
                 const int32_t* __restrict__ box_full, const int32_t* __restrict__ sel,
                 const int32_t* __restrict__ n_sel, int max_sel, const int32_t* __restrict__ labels,
-                IosMeta* __restrict__ meta, int32_t* __restrict__ label_sel, float* __restrict__ ios) {
+                IosMeta* __restrict__ meta, int32_t* __restrict__ label_sel, float* __restrict__ ios,
+                int32_t* __restrict__ n_pairs) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) *n_pairs = 0;
   if (j >= max_sel) return;
   ios[j] = 0.0f;  // identity of the row max (the zeroed diagonal, area > 0 case)
   if (j >= min(*n_sel, max_sel)) { label_sel[j] = -1; return; }
@@ -49,106 +54,109 @@ ios_meta_kernel(const int32_t* __restrict__ rect, const int32_t* __restrict__ ar
   label_sel[j] = m.label;
 }
 
-// One CTA per selected mask i.  Phase 1: all threads scan the partners j > i (label, non-empty, overlapping
-// boxes) and append the survivors to a shared candidate list.  Phase 2: the WHOLE CTA evaluates one candidate at
-// a time — popcount of the AND over the overlap window plus the 1024-wide feature dot product, both spread over
-// all threads with several loads in flight, one block reduction per candidate.  (One warp per pair left the
-// big windows — thousands of words — latency-bound on a single warp.)
-constexpr int kIosMaxCand = 1024;
-
-__global__ void __launch_bounds__(kIosThreads)
-mask_ios_kernel(const uint32_t* __restrict__ bits_full, const IosMeta* __restrict__ meta,
-                const int32_t* __restrict__ label_sel, const int32_t* __restrict__ n_sel, int max_sel, int oh, int ow,
-                const float* __restrict__ obj_feats, int c, float* __restrict__ ios, int32_t* __restrict__ inter_out) {
-  __shared__ int s_cand[kIosMaxCand];
-  __shared__ int s_ncand;
-  __shared__ int s_inter[kIosThreads / 32];
-  __shared__ float s_dot[kIosThreads / 32];
+// Pair generation: CTA i scans the partners j > i (same label, both non-empty, overlapping boxes) and appends
+// (i, j) to a global list (warp-aggregated atomics).  The work per image is a few thousand pairs.
+__global__ void __launch_bounds__(256)
+ios_pairs_kernel(const IosMeta* __restrict__ meta, const int32_t* __restrict__ label_sel,
+                 const int32_t* __restrict__ n_sel, int max_sel, int2* __restrict__ pairs,
+                 int32_t* __restrict__ n_pairs, int max_pairs) {
   const int i = blockIdx.x;
   const int nsel = min(*n_sel, max_sel);
   if (i >= nsel) return;
+  const IosMeta me = meta[i];
+  if (me.area == 0) return;
+  const int lane = lane_id();
+  for (int base = i + 1; base < nsel; base += 256) {
+    const int j = base + threadIdx.x;
+    bool hit = false;
+    if (j < nsel && label_sel[j] == me.label) {
+      const IosMeta mj = meta[j];
+      hit = mj.area > 0 && max(me.box.x, mj.box.x) <= min(me.box.z, mj.box.z) &&
+            max(me.box.y, mj.box.y) <= min(me.box.w, mj.box.w);
+    }
+    const uint32_t m = __ballot_sync(kFull, hit);
+    if (m) {
+      int slot = 0;
+      if (lane == 0) slot = atomicAdd(n_pairs, __popc(m));
+      slot = __shfl_sync(kFull, slot, 0) + __popc(m & ((1u << lane) - 1u));
+      if (hit && slot < max_pairs) pairs[slot] = make_int2(i, j);
+    }
+  }
+}
+
+// Pair evaluation: one CTA per pair (grid-stride over the list): popcount of the AND over the overlap window and
+// the feature dot product, spread over all threads with four load pairs in flight, one block reduction.
+__global__ void __launch_bounds__(kIosThreads)
+ios_eval_kernel(const uint32_t* __restrict__ bits_full, const IosMeta* __restrict__ meta,
+                const int2* __restrict__ pairs, const int32_t* __restrict__ n_pairs, int max_pairs, int max_sel, int oh,
+                int ow, const float* __restrict__ obj_feats, int c, float* __restrict__ ios,
+                int32_t* __restrict__ inter_out) {
+  __shared__ int s_inter[kIosThreads / 32];
+  __shared__ float s_dot[kIosThreads / 32];
   const int lane = lane_id(), warp = warp_id();
   constexpr int kWarps = kIosThreads / 32;
   const int ow_words = (ow + 31) >> 5;
-  const IosMeta me = meta[i];
-  if (me.area == 0) return;  // NaN row: finalised by the caller (0/0 on the diagonal)
-  const uint32_t* mi = bits_full + (size_t)i * oh * ow_words;
-  const float* fi = obj_feats + (size_t)me.src * c;
-  float best = 0.0f;  // tracked by thread 0
-
-  for (int base = i + 1; base < nsel; base += kIosMaxCand) {
-    if (threadIdx.x == 0) s_ncand = 0;
-    __syncthreads();
-    const int end = min(base + kIosMaxCand, nsel);
-    for (int j = base + threadIdx.x; j < end; j += kIosThreads) {
-      if (label_sel[j] != me.label) continue;
-      const IosMeta mj = meta[j];
-      if (mj.area == 0) continue;
-      if (max(me.box.x, mj.box.x) > min(me.box.z, mj.box.z) || max(me.box.y, mj.box.y) > min(me.box.w, mj.box.w)) continue;
-      s_cand[atomicAdd(&s_ncand, 1)] = j;
-    }
-    __syncthreads();
-    const int ncand = s_ncand;
-    for (int q = 0; q < ncand; ++q) {
-      const int j = s_cand[q];
-      const IosMeta mj = meta[j];
-      const int x0 = max(me.box.x, mj.box.x), x1 = min(me.box.z, mj.box.z);
-      const int y0 = max(me.box.y, mj.box.y), y1 = min(me.box.w, mj.box.w);
-      const int wlo = max(max(me.rect.z, mj.rect.z), x0 >> 5), whi = min(min(me.rect.w, mj.rect.w), (x1 >> 5) + 1);
-      const int ylo = max(max(me.rect.x, mj.rect.x), y0), yhi = min(min(me.rect.y, mj.rect.y), y1 + 1);
-      const int nw = whi - wlo;
-      const uint32_t* pj = bits_full + (size_t)j * oh * ow_words;
-      int inter = 0;
-      if (nw > 0 && yhi > ylo) {
-        // threads tile the window: tx over words, ty over rows (tx extent = next pow2 >= nw, <= 32)
-        int txn = 1;
-        while (txn < nw && txn < 32) txn <<= 1;
-        const int tx = threadIdx.x & (txn - 1), ty = threadIdx.x / txn, tyn = kIosThreads / txn;
-        for (int w = wlo + tx; w < whi; w += txn) {
-          int y = ylo + ty;
-          for (; y + 3 * tyn < yhi; y += 4 * tyn) {  // four independent load pairs in flight
-            const size_t o0 = (size_t)y * ow_words + w, o1 = o0 + (size_t)tyn * ow_words;
-            const size_t o2 = o1 + (size_t)tyn * ow_words, o3 = o2 + (size_t)tyn * ow_words;
-            const uint32_t a0 = __ldg(mi + o0), b0 = __ldg(pj + o0), a1 = __ldg(mi + o1), b1 = __ldg(pj + o1);
-            const uint32_t a2 = __ldg(mi + o2), b2 = __ldg(pj + o2), a3 = __ldg(mi + o3), b3 = __ldg(pj + o3);
-            inter += __popc(a0 & b0) + __popc(a1 & b1) + __popc(a2 & b2) + __popc(a3 & b3);
-          }
-          for (; y < yhi; y += tyn) {
-            const size_t o = (size_t)y * ow_words + w;
-            inter += __popc(__ldg(mi + o) & __ldg(pj + o));
-          }
+  const int np = min(*n_pairs, max_pairs);
+  for (int p = blockIdx.x; p < np; p += gridDim.x) {
+    const int2 pr = pairs[p];
+    const int i = pr.x, j = pr.y;
+    const IosMeta me = meta[i], mj = meta[j];
+    const int x0 = max(me.box.x, mj.box.x), x1 = min(me.box.z, mj.box.z);
+    const int y0 = max(me.box.y, mj.box.y), y1 = min(me.box.w, mj.box.w);
+    const int wlo = max(max(me.rect.z, mj.rect.z), x0 >> 5), whi = min(min(me.rect.w, mj.rect.w), (x1 >> 5) + 1);
+    const int ylo = max(max(me.rect.x, mj.rect.x), y0), yhi = min(min(me.rect.y, mj.rect.y), y1 + 1);
+    const int nw = whi - wlo;
+    const uint32_t* mi = bits_full + (size_t)i * oh * ow_words;
+    const uint32_t* pj = bits_full + (size_t)j * oh * ow_words;
+    int inter = 0;
+    if (nw > 0 && yhi > ylo) {
+      // threads tile the window: tx over words (next pow2 >= nw, <= 32), ty over rows
+      int txn = 1;
+      while (txn < nw && txn < 32) txn <<= 1;
+      const int tx = threadIdx.x & (txn - 1), ty = threadIdx.x / txn, tyn = kIosThreads / txn;
+      for (int w = wlo + tx; w < whi; w += txn) {
+        int y = ylo + ty;
+        for (; y + 3 * tyn < yhi; y += 4 * tyn) {
+          const size_t o0 = (size_t)y * ow_words + w, o1 = o0 + (size_t)tyn * ow_words;
+          const size_t o2 = o1 + (size_t)tyn * ow_words, o3 = o2 + (size_t)tyn * ow_words;
+          const uint32_t a0 = __ldg(mi + o0), b0 = __ldg(pj + o0), a1 = __ldg(mi + o1), b1 = __ldg(pj + o1);
+          const uint32_t a2 = __ldg(mi + o2), b2 = __ldg(pj + o2), a3 = __ldg(mi + o3), b3 = __ldg(pj + o3);
+          inter += __popc(a0 & b0) + __popc(a1 & b1) + __popc(a2 & b2) + __popc(a3 & b3);
+        }
+        for (; y < yhi; y += tyn) {
+          const size_t o = (size_t)y * ow_words + w;
+          inter += __popc(__ldg(mi + o) & __ldg(pj + o));
         }
       }
-      // feature dot product, spread over the CTA (needed only if the masks intersect, but computing it in the
-      // same pass saves a second reduction round)
-      const float* fj = obj_feats + (size_t)mj.src * c;
-      float dot = 0.0f;
-      for (int e = threadIdx.x; e < c; e += kIosThreads) dot = fmaf(__ldg(fi + e), __ldg(fj + e), dot);
-      inter = warp_sum(inter);
-      dot = warp_sum(dot);
-      if (lane == 0) { s_inter[warp] = inter; s_dot[warp] = dot; }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        int it = 0;
-        float dt = 0.0f;
+    }
+    const float* fi = obj_feats + (size_t)me.src * c;
+    const float* fj = obj_feats + (size_t)mj.src * c;
+    float dot = 0.0f;
+    for (int e = threadIdx.x; e < c; e += kIosThreads) dot = fmaf(__ldg(fi + e), __ldg(fj + e), dot);
+    inter = warp_sum(inter);
+    dot = warp_sum(dot);
+    if (lane == 0) { s_inter[warp] = inter; s_dot[warp] = dot; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int it = 0;
+      float dt = 0.0f;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) { it += s_inter[w]; dt += s_dot[w]; }
-        if (inter_out) {
-          inter_out[(size_t)i * max_sel + j] = it;
-          inter_out[(size_t)j * max_sel + i] = it;
-        }
-        if (it > 0) {
-          const float sim = fmaxf(dt, 0.0f);
-          // ((inter * s) / area) * s  — the reference's association, for both rows of the pair
-          const float num = __fmul_rn((float)it, sim);
-          best = fmaxf(best, __fmul_rn(__fdiv_rn(num, (float)me.area), sim));
-          atomicMax(reinterpret_cast<int*>(ios + j), __float_as_int(__fmul_rn(__fdiv_rn(num, (float)mj.area), sim)));
-        }
+      for (int w = 0; w < kWarps; ++w) { it += s_inter[w]; dt += s_dot[w]; }
+      if (inter_out) {
+        inter_out[(size_t)i * max_sel + j] = it;
+        inter_out[(size_t)j * max_sel + i] = it;
       }
-      __syncthreads();
+      if (it > 0) {
+        const float sim = fmaxf(dt, 0.0f);
+        // ((inter * s) / area) * s  — the reference's association, for both rows of the pair; all values are
+        // >= 0, so the row max is an integer atomicMax on the float bits
+        const float num = __fmul_rn((float)it, sim);
+        atomicMax(reinterpret_cast<int*>(ios + i), __float_as_int(__fmul_rn(__fdiv_rn(num, (float)me.area), sim)));
+        atomicMax(reinterpret_cast<int*>(ios + j), __float_as_int(__fmul_rn(__fdiv_rn(num, (float)mj.area), sim)));
+      }
     }
+    __syncthreads();
   }
-  if (threadIdx.x == 0 && best > 0.0f) atomicMax(reinterpret_cast<int*>(ios + i), __float_as_int(best));
 }
 
 // rows of empty full-res masks: 0/0 on the diagonal -> NaN, and torch.max propagates it
@@ -166,13 +174,19 @@ int launch_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_
                     cudaStream_t s) {
   if (max_sel <= 0) return NTTT_OK;
   if (inter_out) NTTT_CUDA(cudaMemsetAsync(inter_out, 0, sizeof(int32_t) * (size_t)max_sel * max_sel, s));
-  IosMeta* meta = static_cast<IosMeta*>(ws);
-  int32_t* label_sel = reinterpret_cast<int32_t*>(static_cast<char*>(ws) + align_up(sizeof(IosMeta) * (size_t)max_sel, 256));
+  char* w8 = static_cast<char*>(ws);
+  IosMeta* meta = reinterpret_cast<IosMeta*>(w8);
+  int32_t* label_sel = reinterpret_cast<int32_t*>(w8 + align_up(sizeof(IosMeta) * (size_t)max_sel, 256));
+  int2* pairs = reinterpret_cast<int2*>(reinterpret_cast<char*>(label_sel) + align_up(sizeof(int32_t) * (size_t)max_sel, 256));
+  const int max_pairs = (int)ios_max_pairs(max_sel);
+  int32_t* n_pairs = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(pairs) + align_up(sizeof(int2) * (size_t)max_pairs, 256));
   ios_meta_kernel<<<ceil_div(max_sel, 256), 256, 0, s>>>(rect, area_full, box_full, sel, n_sel, max_sel, labels, meta,
-                                                         label_sel, ios);
+                                                         label_sel, ios, n_pairs);
   NTTT_LAUNCH_CHECK();
-  mask_ios_kernel<<<max_sel, kIosThreads, 0, s>>>(bits_full, meta, label_sel, n_sel, max_sel, oh, ow, obj_feats, c, ios,
-                                                  inter_out);
+  ios_pairs_kernel<<<max_sel, 256, 0, s>>>(meta, label_sel, n_sel, max_sel, pairs, n_pairs, max_pairs);
+  NTTT_LAUNCH_CHECK();
+  ios_eval_kernel<<<148 * 8, kIosThreads, 0, s>>>(bits_full, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats,
+                                                  c, ios, inter_out);
   NTTT_LAUNCH_CHECK();
   if (finalize) {
     ios_finalize_kernel<<<ceil_div(max_sel, 256), 256, 0, s>>>(area_full, n_sel, max_sel, ios);
