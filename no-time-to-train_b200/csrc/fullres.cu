@@ -80,7 +80,7 @@ upsample_meta_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
   reinterpret_cast<int4*>(rect)[k] = make_int4(m.r0, m.r1, m.w0, m.w1);
 }
 
-__global__ void __launch_bounds__(kUpThreads)
+__global__ void __launch_bounds__(kUpThreads, 4)
 upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restrict__ bits_lr,
                      const UpMeta* __restrict__ meta, int ih, int iw, const int32_t* __restrict__ n_sel, int max_sel,
                      int oh, int ow, UpTables t, uint32_t* __restrict__ bits_full, int32_t* __restrict__ area_full,
