@@ -294,7 +294,8 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
   if (iw % 32 != 0) return NTTT_EUNSUPPORTED;
   const size_t smem = (size_t)ih * (iw / 32) * 4 + sizeof(float) * kLogFloats;
   if (smem > 160 * 1024) return NTTT_EUNSUPPORTED;
-  NTTT_CUDA(cudaFuncSetAttribute(upsample_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024)
+    NTTT_CUDA(cudaFuncSetAttribute(upsample_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   UpTables t{tx.xmin, tx.xsize, tx.w, tx.taps, ty.xmin, ty.xsize, ty.w, ty.taps, tx.t_lo, tx.t_len, ty.t_lo, ty.t_len,
              ty.grp_of, ty.grp_start, ow};
   UpMeta* meta = reinterpret_cast<UpMeta*>(scratch + (size_t)kScratchInts * max_sel);
