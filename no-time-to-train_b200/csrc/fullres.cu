@@ -25,13 +25,12 @@ struct UpTables {
   const int32_t* x_tlo; const int32_t* x_tlen;  // input col -> output range
   const int32_t* y_tlo; const int32_t* y_tlen;  // input row -> output range
   const int32_t* y_grp_of; const int32_t* y_grp_start;  // output rows grouped by identical input span
-  int ow;
 };
 
 // acc = s0*w0; acc = fma(s_j, w_j, acc)
 __device__ __forceinline__ float aa_dot(const float* __restrict__ src, int stride, const float* __restrict__ w, int n) {
-  float acc = __fmul_rn(src[0], __ldg(w));  // src may point to shared memory: generic loads
-  for (int j = 1; j < n; ++j) acc = __fmaf_rn(src[(size_t)j * stride], __ldg(w + j), acc);
+  float acc = __fmul_rn(__ldg(src), __ldg(w));
+  for (int j = 1; j < n; ++j) acc = __fmaf_rn(__ldg(src + (size_t)j * stride), __ldg(w + j), acc);
   return acc;
 }
 
@@ -47,11 +46,8 @@ struct UpMeta {
   int r0, r1;        // output rows [r0, r1)
   int w0, w1;        // output words [w0, w1)
   int lr0, lr1;      // low-res rows [lr0, lr1) under those output rows
-  int cl0, cl1;      // low-res columns [cl0, cl1) under those output words
-  int g0, g1;        // row groups [g0, g1) covering the output rows
   int safe;          // flags bit0
 };
-constexpr int kLogFloats = 10240;  // per-CTA shared-memory window of logits (40 KB)
 
 __global__ void __launch_bounds__(256)
 upsample_meta_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __restrict__ box_lr,
@@ -68,7 +64,7 @@ upsample_meta_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
   const int4 b = reinterpret_cast<const int4*>(box_lr)[m.src];
   // empty low-res mask <=> box all zero AND bit (0,0) clear
   const bool lr_empty = (b.x | b.y | b.z | b.w) == 0 && (bits_lr[(size_t)m.src * ih * (iw >> 5)] & 1u) == 0;
-  m.r0 = m.r1 = m.w0 = m.w1 = m.lr0 = m.lr1 = m.cl0 = m.cl1 = m.g0 = m.g1 = 0;
+  m.r0 = m.r1 = m.w0 = m.w1 = m.lr0 = m.lr1 = 0;
   if (!lr_empty) {
     m.r0 = t.y_tlo[b.y];
     m.r1 = t.y_tlo[b.w] + t.y_tlen[b.w];
@@ -78,11 +74,6 @@ upsample_meta_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
     m.w1 = (c1 + 31) >> 5;
     m.lr0 = t.ymin[m.r0];
     m.lr1 = t.ymin[m.r1 - 1] + t.ysize[m.r1 - 1];
-    const int xa = min(m.w0 << 5, t.ow - 1), xb = min(m.w1 << 5, t.ow) - 1;
-    m.cl0 = t.xmin[xa];
-    m.cl1 = t.xmin[xb] + t.xsize[xb];
-    m.g0 = t.y_grp_of[m.r0];
-    m.g1 = t.y_grp_of[m.r1 - 1] + 1;
   }
   m.safe = flags_lr[m.src] & 1;
   meta[k] = m;
@@ -107,33 +98,17 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
   constexpr int kWarps = kUpThreads / 32;
   const int r0 = mt.r0, r1 = mt.r1, w0 = mt.w0, w1 = mt.w1;
 
-  // this CTA's contiguous share of the mask's row groups, and the low-res rows under it
-  const int per = (mt.g1 - mt.g0 + kUpSplit - 1) / kUpSplit;
-  const int gb = mt.g0 + blockIdx.x * per, ge = min(gb + per, mt.g1);
-  int lrA = 0, lrB = 0;
-  if (gb < ge) {
-    const int ya_first = max(t.y_grp_start[gb], r0), y_last = min(t.y_grp_start[ge], r1) - 1;
-    lrA = t.ymin[ya_first];
-    lrB = t.ymin[y_last] + t.ysize[y_last];
-  }
-  const int ncols = mt.cl1 - mt.cl0, nlr = lrB - lrA;
-  const bool staged = nlr * ncols <= kLogFloats;  // window of logits fits in shared memory
-  float* s_log = reinterpret_cast<float*>(s_lr + ih * lr_wpr);
-  const float* src = logits + (size_t)src_idx * ih * iw;
-
-  const uint32_t* lr = bits_lr + ((size_t)src_idx * ih + lrA) * lr_wpr;
-  for (int i = threadIdx.x; i < nlr * lr_wpr; i += kUpThreads) s_lr[i] = lr[i];
-  if (staged)  // all loads of the window are in flight at once; later reads are LDS, not dependent L2 round trips
-    for (int r = warp; r < nlr; r += kWarps)
-      for (int cc = lane; cc < ncols; cc += 32) s_log[r * ncols + cc] = src[(size_t)(lrA + r) * iw + mt.cl0 + cc];
+  const uint32_t* lr = bits_lr + ((size_t)src_idx * ih + mt.lr0) * lr_wpr;
+  for (int i = threadIdx.x; i < (mt.lr1 - mt.lr0) * lr_wpr; i += kUpThreads) s_lr[i] = lr[i];
   if (threadIdx.x < 5) s_red[threadIdx.x] = 0;
   const bool safe = mt.safe != 0;
-  const float* pbase = staged ? s_log : src;
-  const int pstride = staged ? ncols : iw, row_off = staged ? lrA : 0, col_off = staged ? mt.cl0 : 0;
+  const float* src = logits + (size_t)src_idx * ih * iw;
   uint32_t* dst = bits_full + (size_t)k * oh * ow_words;
   __syncthreads();
 
   int area = 0, minx = kBig, maxx = -1, miny = kBig, maxy = -1;
+  const int g0 = r1 > r0 ? t.y_grp_of[r0] : 0;
+  const int g1 = r1 > r0 ? t.y_grp_of[r1 - 1] + 1 : 0;
   for (int wbase = w0; wbase < w1; wbase += 32) {
     // per-lane (= per output word) constants, hoisted out of the row-group loop
     const int wi = wbase + lane;
@@ -153,7 +128,7 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
       if (hi1 > 0) m1 = hi1 >= 32 ? 0xffffffffu : ((1u << hi1) - 1u);
     }
     uint32_t colbits = 0;
-  for (int g = gb + warp; g < ge; g += kWarps) {
+  for (int g = g0 + blockIdx.x * kWarps + warp; g < g1; g += kUpSplit * kWarps) {
     // rows [ya, yb) of this group share the input rows [ry0, ry0 + rys)
     const int ya = max(t.y_grp_start[g], r0), yb = min(t.y_grp_start[g + 1], r1);
     const int nrows = yb - ya;
@@ -167,7 +142,7 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
         bool all0 = true, all1 = true;
         if (two_words) {
           for (int r = 0; r < rys; ++r) {
-            const uint32_t* row = s_lr + (ry0 + r - lrA) * lr_wpr + cw0;
+            const uint32_t* row = s_lr + (ry0 + r - mt.lr0) * lr_wpr + cw0;
             const uint32_t v0 = row[0] & m0;
             const uint32_t v1 = m1 ? (row[1] & m1) : 0u;
             all0 = all0 && ((v0 | v1) == 0);
@@ -175,7 +150,7 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
           }
         } else {
           for (int r = 0; r < rys; ++r) {
-            const uint32_t* row = s_lr + (ry0 + r - lrA) * lr_wpr;
+            const uint32_t* row = s_lr + (ry0 + r - mt.lr0) * lr_wpr;
             for (int cw = cw0; cw <= (c1 - 1) >> 5; ++cw) {
               const int lo = max(c0 - (cw << 5), 0), hi = min(c1 - (cw << 5), 32);
               const uint32_t m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
@@ -200,12 +175,12 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
         const bool inb = x < ow;
         const int cx = inb ? t.xmin[x] : 0, cs = inb ? t.xsize[x] : 1;
         const float* wx = t.wx + (size_t)(inb ? x : 0) * t.tx;
-        const float* p = pbase + (size_t)(ry0 - row_off) * pstride + (cx - col_off);
+        const float* p = src + (size_t)ry0 * iw + cx;
         if (rys <= kTapsReg) {
           // horizontal pass once per group, vertical pass per row
           float T[kTapsReg];
 #pragma unroll
-          for (int r = 0; r < kTapsReg; ++r) T[r] = (r < rys && inb) ? aa_dot(p + (size_t)r * pstride, 1, wx, cs) : 0.0f;
+          for (int r = 0; r < kTapsReg; ++r) T[r] = (r < rys && inb) ? aa_dot(p + (size_t)r * iw, 1, wx, cs) : 0.0f;
 #pragma unroll
           for (int j = 0; j < kGrpMax; ++j) {
             if (j < nrows) {
@@ -226,7 +201,7 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
               float acc = 0.0f;
               if (inb) {
                 acc = __fmul_rn(aa_dot(p, 1, wx, cs), __ldg(wy));
-                for (int r = 1; r < rys; ++r) acc = __fmaf_rn(aa_dot(p + (size_t)r * pstride, 1, wx, cs), __ldg(wy + r), acc);
+                for (int r = 1; r < rys; ++r) acc = __fmaf_rn(aa_dot(p + (size_t)r * iw, 1, wx, cs), __ldg(wy + r), acc);
               }
               const uint32_t res = __ballot_sync(kFull, inb && acc > 0.0f);
               if (lane == src_lane) words[j] = res;
@@ -292,12 +267,12 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
                          int32_t* area_full, int32_t* box_full, int32_t* scratch, cudaStream_t s) {
   if (max_sel <= 0) return NTTT_OK;
   if (iw % 32 != 0) return NTTT_EUNSUPPORTED;
-  const size_t smem = (size_t)ih * (iw / 32) * 4 + sizeof(float) * kLogFloats;
+  const size_t smem = (size_t)ih * (iw / 32) * 4;
   if (smem > 160 * 1024) return NTTT_EUNSUPPORTED;
   if (smem > 48 * 1024)
     NTTT_CUDA(cudaFuncSetAttribute(upsample_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   UpTables t{tx.xmin, tx.xsize, tx.w, tx.taps, ty.xmin, ty.xsize, ty.w, ty.taps, tx.t_lo, tx.t_len, ty.t_lo, ty.t_len,
-             ty.grp_of, ty.grp_start, ow};
+             ty.grp_of, ty.grp_start};
   UpMeta* meta = reinterpret_cast<UpMeta*>(scratch + (size_t)kScratchInts * max_sel);
   upsample_meta_kernel<<<ceil_div(max_sel, 256), 256, 0, s>>>(bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, t,
                                                               meta, rect, scratch);
