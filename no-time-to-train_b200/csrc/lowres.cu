@@ -13,73 +13,130 @@ namespace nttt {
 // K1: lowres_pack — HBM-bound streaming kernel, one CTA per mask.
 //   algorithmic bytes per mask: 4*P read (+ P/8 written)
 // ---------------------------------------------------------------------------------------------------
-constexpr int kPackThreads = 256;
-constexpr int kPackUnroll = 4;
+constexpr int kPackThreads = 256;                  // consumer threads (8 warps)
+constexpr int kPackBlock = kPackThreads + 32;      // + one producer warp
+constexpr int kPackStages = 4;
+constexpr int kPackStageF4 = 4 * kPackThreads;     // float4 per stage: 4 per consumer thread = 16 KB
+constexpr int kPackStageBytes = kPackStageF4 * 16;
 
-// The loop is issue-bound before it is HBM-bound (5-10 ALU ops per logit), so it carries only what has to be
-// done per element: the sign bit, the finite-range check, and (only if asked, kStab) the two stability counts.
-// Area and box are derived afterwards from the packed words in shared memory.
+__device__ __forceinline__ uint32_t pk_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pk_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pk_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void pk_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pk_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pk_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pk_smem_u32(bar)) : "memory");
+}
+// bounded wait: a lost arrive traps (CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void pk_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = pk_smem_u32(bar);
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void pk_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   pk_smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(pk_smem_u32(bar))
+               : "memory");
+}
+
+// One CTA per mask.  A producer warp streams the 256 KB of logits through a 4-stage ring of 16 KB TMA bulk
+// copies (48 KB in flight per CTA without holding registers); eight consumer warps read each stage with
+// conflict-free 128-bit LDS and do the per-element work.  That work is issue-bound before it is HBM-bound
+// (5-10 ALU ops per logit), so the loop carries only what has to be done per element: the sign bit, the
+// finite-range check and (only if asked, kStab) the two stability counts.  Area and box are derived afterwards
+// from the packed words in shared memory.
 template <bool kStab>
-__global__ void __launch_bounds__(kPackThreads, 5)
+__global__ void __launch_bounds__(kPackBlock, 3)
 lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mask */, int words_per_row,
                    float thr_hi, float thr_lo, uint32_t* __restrict__ bits, int32_t* __restrict__ area,
                    int32_t* __restrict__ box, int32_t* __restrict__ stab, int32_t* __restrict__ flags) {
-  extern __shared__ uint32_t s_bits[];  // p4/8 words
-  __shared__ int s_red[8];              // area, hi, lo, unsafe, minx, miny, maxx, maxy
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  float4* s_stage = reinterpret_cast<float4*>(s_raw);                                        // ring
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_raw + (size_t)kPackStages * kPackStageBytes);  // p4/8 words
+  __shared__ uint64_t s_full[kPackStages], s_empty[kPackStages];
+  __shared__ int s_red[8];  // area, hi, lo, unsafe, minx, miny, maxx, maxy
   const int n = blockIdx.x;
   const float4* src = logits + (size_t)n * p4;
-  const int lane = lane_id();
+  const int lane = lane_id(), warp = warp_id();
+  const int n_stages = (p4 + kPackStageF4 - 1) / kPackStageF4;
   if (threadIdx.x < 8) s_red[threadIdx.x] = (threadIdx.x == 4 || threadIdx.x == 5) ? 0x7fffffff : (threadIdx.x >= 6 ? -1 : 0);
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < kPackStages; ++q) { pk_mbar_init(&s_full[q], 1); pk_mbar_init(&s_empty[q], kPackThreads / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 
   int hi = 0, lo = 0;
   uint32_t unsafe = 0;
-  // a positive logit is "safe" iff 2^-100 < v < 2^100: bit pattern strictly between 0x0D800000 and 0x71800000
-  constexpr uint32_t kLoBits = 0x0D800000u, kSpan = 0x71800000u - 0x0D800001u;
-
-  // software pipeline: the loads of the next batch are in flight while this batch is reduced
-  float4 nxt[kPackUnroll];
-#pragma unroll
-  for (int u = 0; u < kPackUnroll; ++u) {
-    const int q = u * kPackThreads + threadIdx.x;
-    nxt[u] = q < p4 ? ld_stream(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  for (int base = 0; base < p4; base += kPackThreads * kPackUnroll) {
-    float4 v[kPackUnroll];
-#pragma unroll
-    for (int u = 0; u < kPackUnroll; ++u) v[u] = nxt[u];
-#pragma unroll
-    for (int u = 0; u < kPackUnroll; ++u) {
-      const int q = base + kPackThreads * kPackUnroll + u * kPackThreads + threadIdx.x;
-      nxt[u] = q < p4 ? ld_stream(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < kPackUnroll; ++u) {
-      const int q = base + u * kPackThreads + threadIdx.x;
-      const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-      uint32_t nib = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const bool pos = e[k] > 0.0f;
-        nib |= (uint32_t)pos << k;
-        const bool in_range = (__float_as_uint(e[k]) - (kLoBits + 1u)) < kSpan;
-        unsafe |= (uint32_t)(pos && !in_range);
-        if (kStab) {
-          hi += e[k] > thr_hi;
-          lo += e[k] > thr_lo;
-        }
+  if (warp == kPackThreads / 32) {
+    // ===== producer warp =====
+    if (lane == 0) {
+      for (int st = 0; st < n_stages; ++st) {
+        const int q = st % kPackStages;
+        pk_mbar_wait(&s_empty[q], ((st / kPackStages) & 1) ^ 1);
+        const int f4 = min(kPackStageF4, p4 - st * kPackStageF4);
+        pk_mbar_expect_tx(&s_full[q], (uint32_t)f4 * 16u);
+        pk_bulk_load(s_stage + (size_t)q * kPackStageF4, src + (size_t)st * kPackStageF4, (uint32_t)f4 * 16u, &s_full[q]);
       }
-      uint32_t word = nib << (4 * (lane & 7));
-      word |= __shfl_xor_sync(kFull, word, 1);
-      word |= __shfl_xor_sync(kFull, word, 2);
-      word |= __shfl_xor_sync(kFull, word, 4);
-      if ((lane & 7) == 0 && q < p4) s_bits[q >> 3] = word;
+    }
+  } else {
+    // ===== consumer warps =====
+    // a positive logit is "safe" iff 2^-100 < v < 2^100: bit pattern strictly between 0x0D800000 and 0x71800000
+    constexpr uint32_t kLoBits = 0x0D800000u, kSpan = 0x71800000u - 0x0D800001u;
+    for (int st = 0; st < n_stages; ++st) {
+      const int q = st % kPackStages;
+      pk_mbar_wait(&s_full[q], (st / kPackStages) & 1);
+      const float4* buf = s_stage + (size_t)q * kPackStageF4;
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)  // (a short last stage leaves the tail of the slot stale: read zeros instead)
+        v[u] = (st * kPackStageF4 + u * kPackThreads + (int)threadIdx.x < p4) ? buf[u * kPackThreads + threadIdx.x]
+                                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+      if (lane == 0) pk_mbar_arrive(&s_empty[q]);  // this warp has copied its share out of the slot
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int qi = st * kPackStageF4 + u * kPackThreads + threadIdx.x;
+        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        uint32_t nib = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool pos = e[k] > 0.0f;
+          nib |= (uint32_t)pos << k;
+          const bool in_range = (__float_as_uint(e[k]) - (kLoBits + 1u)) < kSpan;
+          unsafe |= (uint32_t)(pos && !in_range);
+          if (kStab) {
+            hi += e[k] > thr_hi;
+            lo += e[k] > thr_lo;
+          }
+        }
+        uint32_t word = nib << (4 * (lane & 7));
+        word |= __shfl_xor_sync(kFull, word, 1);
+        word |= __shfl_xor_sync(kFull, word, 2);
+        word |= __shfl_xor_sync(kFull, word, 4);
+        if ((lane & 7) == 0 && qi < p4) s_bits[qi >> 3] = word;
+      }
     }
   }
-  __syncthreads();  // s_bits complete, s_red initialised
+  __syncthreads();  // s_bits complete
   // area and box from the packed words; 128-bit stores of the words
   const int n_words = p4 >> 3;
   int a = 0, minx = 0x7fffffff, miny = 0x7fffffff, maxx = -1, maxy = -1;
-  for (int wi = threadIdx.x; wi < n_words; wi += kPackThreads) {
+  for (int wi = threadIdx.x; wi < n_words; wi += kPackBlock) {
     const uint32_t word = s_bits[wi];
     if (word) {
       a += __popc(word);
@@ -93,7 +150,7 @@ lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mas
   }
   uint4* dst = reinterpret_cast<uint4*>(bits + (size_t)n * n_words);
   const uint4* s4 = reinterpret_cast<const uint4*>(s_bits);
-  for (int i = threadIdx.x; i < (n_words >> 2); i += kPackThreads) dst[i] = s4[i];
+  for (int i = threadIdx.x; i < (n_words >> 2); i += kPackBlock) dst[i] = s4[i];
   a = warp_sum(a);
   unsafe = (uint32_t)warp_max((int)unsafe);
   minx = warp_min(minx); miny = warp_min(miny); maxx = warp_max(maxx); maxy = warp_max(maxy);
@@ -120,14 +177,18 @@ int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, floa
   const long p = (long)h * w;
   if (n <= 0) return NTTT_OK;
   if (w % 32 != 0 || p % 128 != 0 || p / 32 * 4 > 32 * 1024) return NTTT_EUNSUPPORTED;
-  const size_t smem = (size_t)(p / 32) * sizeof(uint32_t);
+  if ((reinterpret_cast<uintptr_t>(logits) & 15) != 0) return NTTT_EINVAL;  // TMA bulk copies need 16-byte alignment
+  const size_t smem = (size_t)kPackStages * kPackStageBytes + (size_t)(p / 32) * sizeof(uint32_t);
   const float4* src = reinterpret_cast<const float4*>(logits);
-  if (stab)
-    lowres_pack_kernel<true><<<n, kPackThreads, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area,
-                                                          box, stab, flags);
-  else
-    lowres_pack_kernel<false><<<n, kPackThreads, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits,
-                                                           area, box, stab, flags);
+  if (stab) {
+    NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lowres_pack_kernel<true><<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area, box,
+                                                        stab, flags);
+  } else {
+    NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lowres_pack_kernel<false><<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area,
+                                                         box, stab, flags);
+  }
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }
