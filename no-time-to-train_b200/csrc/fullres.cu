@@ -39,16 +39,18 @@ constexpr int kScratchInts = 8;
 constexpr int kBig = 1 << 30;
 constexpr int kTapsReg = 4;  // footprints of up to 4 input rows keep their horizontal-pass values in registers
 
-// Work decomposition: the unit of work is one ROW GROUP of one selected mask (<= kGrpMax output rows sharing
-// their input rows).  A single-CTA pre-kernel resolves every mask's rect / group range once and builds the
-// exclusive prefix of the group counts; the main kernel is a fixed grid whose warps take items
-// item = warp_id, warp_id + n_warps, ... and locate (mask, group) by binary search in the prefix.  No per-CTA
-// prologue, no intra-CTA imbalance between small and large masks, no shared memory.
+// Work decomposition: the unit of work is one STRIP = one 32-pixel word column of one selected mask, walked top
+// to bottom by one warp with lane = pixel.  Everything that depends only on the column (input span, horizontal
+// weights, footprint bit masks) is loaded once per strip and lives in registers; per row group the warp tests the
+// footprint bits, and only if they are mixed loads the 2-3 taps x 2-4 input rows, runs the horizontal pass once
+// and the vertical pass per output row, each output word being one ballot.  A single-CTA pre-kernel resolves
+// every mask's rect once and builds the exclusive prefix of the strip counts; the main kernel is a fixed grid
+// whose warps take strips item = warp_id, warp_id + n_warps, ... and locate (mask, word) by binary search.
 struct UpMeta {
   int src;      // index into logits / bits_lr
   int r0, r1;   // output rows [r0, r1)
   int w0, w1;   // output words [w0, w1)
-  int g0, cnt;  // first row group and number of row groups
+  int g0, g1;   // row groups [g0, g1)
   int safe;     // flags bit0
 };
 
@@ -77,7 +79,7 @@ upsample_meta_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
       const int4 b = reinterpret_cast<const int4*>(box_lr)[m.src];
       // empty low-res mask <=> box all zero AND bit (0,0) clear
       const bool lr_empty = (b.x | b.y | b.z | b.w) == 0 && (bits_lr[(size_t)m.src * ih * (iw >> 5)] & 1u) == 0;
-      m.r0 = m.r1 = m.w0 = m.w1 = m.g0 = m.cnt = 0;
+      m.r0 = m.r1 = m.w0 = m.w1 = m.g0 = m.g1 = 0;
       if (!lr_empty) {
         m.r0 = t.y_tlo[b.y];
         m.r1 = t.y_tlo[b.w] + t.y_tlen[b.w];
@@ -86,11 +88,11 @@ upsample_meta_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
         m.w0 = c0 >> 5;
         m.w1 = (c1 + 31) >> 5;
         m.g0 = t.y_grp_of[m.r0];
-        m.cnt = t.y_grp_of[m.r1 - 1] + 1 - m.g0;
+        m.g1 = t.y_grp_of[m.r1 - 1] + 1;
       }
       m.safe = flags_lr[m.src] & 1;
       meta[k] = m;
-      cnt = m.cnt;
+      cnt = (m.r1 > m.r0) ? (m.w1 - m.w0) : 0;  // strips of this mask
       reinterpret_cast<int4*>(rect)[k] = make_int4(m.r0, m.r1, m.w0, m.w1);
       if (cnt == 0) {  // nothing to compute: publish the empty statistics here
         area_full[k] = 0;
@@ -137,7 +139,7 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
   const int total = prefix[max_sel];
   const int n_warps = gridDim.x * kWarps;
   for (int item = blockIdx.x * kWarps + warp_id(); item < total; item += n_warps) {
-    // (mask, group) of this item: last k with prefix[k] <= item
+    // (mask, word) of this strip: last k with prefix[k] <= item
     int klo = 0, khi = max_sel;
     while (khi - klo > 1) {
       const int mid = (klo + khi) >> 1;
@@ -145,135 +147,137 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
     }
     const int k = klo;
     const UpMeta mt = meta[k];
-    const int g = mt.g0 + (item - __ldg(prefix + k));
-    const int r0 = mt.r0, r1 = mt.r1, w0 = mt.w0, w1 = mt.w1;
+    const int wi = mt.w0 + (item - __ldg(prefix + k));
+    const int r0 = mt.r0, r1 = mt.r1;
     const bool safe = mt.safe != 0;
     const float* src = logits + (size_t)mt.src * ih * iw;
     const uint32_t* lr = bits_lr + (size_t)mt.src * ih * lr_wpr;
-    uint32_t* dst = bits_full + (size_t)k * oh * ow_words;
-    // rows [ya, yb) of this group share the input rows [ry0, ry0 + rys)
-    const int ya = max(t.y_grp_start[g], r0), yb = min(t.y_grp_start[g + 1], r1);
-    const int nrows = yb - ya;
-    const int ry0 = t.ymin[ya], rys = t.ysize[ya];
-    int area = 0, minx = kBig, maxx = -1, miny = kBig, maxy = -1;
+    uint32_t* dst = bits_full + (size_t)k * oh * ow_words + wi;
 
-    for (int wbase = w0; wbase < w1; wbase += 32) {
-      const int wi = wbase + lane;
-      const bool active = wi < w1;
-      const int x0 = min(wi << 5, ow - 1);
-      const int x1 = min(x0 + 31, ow - 1);
-      const uint32_t valid = (x1 - x0 == 31) ? 0xffffffffu : ((1u << (x1 - x0 + 1)) - 1u);
-      const int c0 = t.xmin[x0];
-      const int c1 = t.xmin[x1] + t.xsize[x1];  // exclusive
-      const int cw0 = c0 >> 5;
+    // ---- column constants (registers for the whole strip) ----
+    const int x = (wi << 5) + lane;
+    const bool inb = x < ow;
+    const int xc = inb ? x : ow - 1;
+    const int cx = t.xmin[xc], cs = t.xsize[xc];
+    const float* wxp = t.wx + (size_t)xc * t.tx;
+    const bool fast_x = t.tx <= 3;
+    float wx0 = 0.f, wx1 = 0.f, wx2 = 0.f;
+    if (fast_x) {
+      wx0 = __ldg(wxp);
+      if (cs > 1) wx1 = __ldg(wxp + 1);
+      if (cs > 2) wx2 = __ldg(wxp + 2);
+    }
+    const int x0 = wi << 5, x1 = min(x0 + 31, ow - 1);
+    const uint32_t valid = (x1 - x0 == 31) ? 0xffffffffu : ((1u << (x1 - x0 + 1)) - 1u);
+    const int c0 = t.xmin[x0];
+    const int c1 = t.xmin[x1] + t.xsize[x1];  // exclusive: low-res columns [c0, c1) feed this word
+    const int cw0 = c0 >> 5, cw1 = (c1 - 1) >> 5;
+    const float* pcol = src + cx;
+
+    int area = 0, miny = kBig, maxy = -1;
+    uint32_t colbits = 0;
+    for (int g = mt.g0; g < mt.g1; ++g) {
+      // rows [ya, yb) of this group share the input rows [ry0, ry0 + rys)
+      const int ya = max(__ldg(t.y_grp_start + g), r0), yb = min(__ldg(t.y_grp_start + g + 1), r1);
+      const int nrows = yb - ya;
+      const int ry0 = __ldg(t.ymin + ya), rys = __ldg(t.ysize + ya);
+      // footprint test: lane r looks at input row ry0 + r (rys <= 32 always holds for supported scales)
+      bool z = true, o = true;
+      for (int rr = lane; rr < rys; rr += 32) {
+        const uint32_t* row = lr + (size_t)(ry0 + rr) * lr_wpr;
+        for (int cw = cw0; cw <= cw1; ++cw) {
+          const int lo = max(c0 - (cw << 5), 0), hi = min(c1 - (cw << 5), 32);
+          const uint32_t m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+          const uint32_t v = __ldg(row + cw) & m;
+          z = z && (v == 0);
+          o = o && (v == m);
+        }
+      }
+      const bool all0 = __all_sync(kFull, z), all1 = __all_sync(kFull, o);
       uint32_t words[kGrpMax];
 #pragma unroll
       for (int j = 0; j < kGrpMax; ++j) words[j] = 0;
-      bool mixed = false;
-      if (active) {
-        bool all0 = true, all1 = true;
-        for (int r = 0; r < rys; ++r) {
-          const uint32_t* row = lr + (size_t)(ry0 + r) * lr_wpr;
-          for (int cw = cw0; cw <= (c1 - 1) >> 5; ++cw) {
-            const int lo = max(c0 - (cw << 5), 0), hi = min(c1 - (cw << 5), 32);
-            const uint32_t m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-            const uint32_t v = __ldg(row + cw) & m;
-            all0 = all0 && (v == 0);
-            all1 = all1 && (v == m);
+      if (all0) {
+        // stays zero
+      } else if (all1 && safe) {
+#pragma unroll
+        for (int j = 0; j < kGrpMax; ++j) words[j] = valid;
+      } else if (rys <= kTapsReg && fast_x) {
+        // horizontal pass once per group (taps beyond cs are never read), vertical pass per output row
+        float T[kTapsReg];
+#pragma unroll
+        for (int r = 0; r < kTapsReg; ++r) {
+          float acc = 0.0f;
+          if (r < rys && inb) {
+            const float* p = pcol + (size_t)(ry0 + r) * iw;
+            acc = __fmul_rn(__ldg(p), wx0);
+            if (cs > 1) acc = __fmaf_rn(__ldg(p + 1), wx1, acc);
+            if (cs > 2) acc = __fmaf_rn(__ldg(p + 2), wx2, acc);
+          }
+          T[r] = acc;
+        }
+#pragma unroll
+        for (int j = 0; j < kGrpMax; ++j) {
+          if (j < nrows) {
+            const float* wy = t.wy + (size_t)(ya + j) * t.ty;
+            float acc = __fmul_rn(T[0], __ldg(wy));
+#pragma unroll
+            for (int r = 1; r < kTapsReg; ++r)
+              if (r < rys) acc = __fmaf_rn(T[r], __ldg(wy + r), acc);
+            words[j] = __ballot_sync(kFull, inb && acc > 0.0f);
           }
         }
-        if (all1 && safe && !all0) {
+      } else {
+        // long footprints (down-scaling): evaluate each output row directly
 #pragma unroll
-          for (int j = 0; j < kGrpMax; ++j) words[j] = valid;
-        } else if (!all0) {
-          mixed = true;
-        }
-      }
-      uint32_t todo = __ballot_sync(kFull, mixed);
-      while (todo) {
-        const int src_lane = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int x = ((wbase + src_lane) << 5) + lane;
-        const bool inb = x < ow;
-        const int cx = inb ? t.xmin[x] : 0, cs = inb ? t.xsize[x] : 1;
-        const float* wx = t.wx + (size_t)(inb ? x : 0) * t.tx;
-        const float* p = src + (size_t)ry0 * iw + cx;
-        if (rys <= kTapsReg) {
-          // horizontal pass once per group, vertical pass per row
-          float T[kTapsReg];
-#pragma unroll
-          for (int r = 0; r < kTapsReg; ++r) T[r] = (r < rys && inb) ? aa_dot(p + (size_t)r * iw, 1, wx, cs) : 0.0f;
-#pragma unroll
-          for (int j = 0; j < kGrpMax; ++j) {
-            if (j < nrows) {
-              const float* wy = t.wy + (size_t)(ya + j) * t.ty;
-              float acc = __fmul_rn(T[0], __ldg(wy));
-#pragma unroll
-              for (int r = 1; r < kTapsReg; ++r)
-                if (r < rys) acc = __fmaf_rn(T[r], __ldg(wy + r), acc);
-              const uint32_t res = __ballot_sync(kFull, inb && acc > 0.0f);
-              if (lane == src_lane) words[j] = res;
+        for (int j = 0; j < kGrpMax; ++j) {
+          if (j < nrows) {
+            const float* wy = t.wy + (size_t)(ya + j) * t.ty;
+            float acc = 0.0f;
+            if (inb) {
+              const float* p = pcol + (size_t)ry0 * iw;
+              acc = __fmul_rn(aa_dot(p, 1, wxp, cs), __ldg(wy));
+              for (int r = 1; r < rys; ++r) acc = __fmaf_rn(aa_dot(p + (size_t)r * iw, 1, wxp, cs), __ldg(wy + r), acc);
             }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < kGrpMax; ++j) {
-            if (j < nrows) {
-              const float* wy = t.wy + (size_t)(ya + j) * t.ty;
-              float acc = 0.0f;
-              if (inb) {
-                acc = __fmul_rn(aa_dot(p, 1, wx, cs), __ldg(wy));
-                for (int r = 1; r < rys; ++r) acc = __fmaf_rn(aa_dot(p + (size_t)r * iw, 1, wx, cs), __ldg(wy + r), acc);
-              }
-              const uint32_t res = __ballot_sync(kFull, inb && acc > 0.0f);
-              if (lane == src_lane) words[j] = res;
-            }
+            words[j] = __ballot_sync(kFull, inb && acc > 0.0f);
           }
         }
       }
-      uint32_t colbits = 0;
+      // the words are warp-uniform: lane j stores row j
 #pragma unroll
       for (int j = 0; j < kGrpMax; ++j) {
         if (j < nrows) {
-          const uint32_t word = active ? words[j] : 0u;
-          if (active) dst[(size_t)(ya + j) * ow_words + wi] = word;
-          area += __popc(word);
-          colbits |= word;
-          if (__any_sync(kFull, word != 0)) {  // warp-uniform row extent
+          if (lane == j) dst[(size_t)(ya + j) * ow_words] = words[j];
+          if (words[j]) {
+            area += __popc(words[j]);
+            colbits |= words[j];
             miny = min(miny, ya + j);
             maxy = max(maxy, ya + j);
           }
         }
       }
-      if (colbits) {
-        minx = min(minx, (wi << 5) + __ffs(colbits) - 1);
-        maxx = max(maxx, (wi << 5) + 31 - __clz(colbits));
-      }
     }
-    // per-mask statistics: atomics into the scratch; the last group of a mask publishes area and box
-    area = warp_sum(area);
-    minx = warp_min(minx);
-    maxx = warp_max(maxx);
+    // per-mask statistics (all values are warp-uniform): atomics into the scratch; the last strip publishes
     if (lane == 0) {
       int32_t* sc = scratch + (size_t)k * kScratchInts;
       if (area > 0) {
         atomicAdd(&sc[0], area);
-        atomicMax(&sc[1], maxx + 1);
+        atomicMax(&sc[1], (wi << 5) + 31 - __clz(colbits) + 1);
         atomicMax(&sc[2], maxy + 1);
-        atomicMax(&sc[3], kBig - minx);
+        atomicMax(&sc[3], kBig - ((wi << 5) + __ffs(colbits) - 1));
         atomicMax(&sc[4], kBig - miny);
       }
       __threadfence();
       const int prev = atomicAdd(&sc[5], 1);
-      if (prev == mt.cnt - 1) {
+      if (prev == (mt.w1 - mt.w0) - 1) {
         __threadfence();
         const int a = atomicAdd(&sc[0], 0);
         const int mx1 = atomicMax(&sc[1], 0), my1 = atomicMax(&sc[2], 0);
         const int bx = atomicMax(&sc[3], 0), by = atomicMax(&sc[4], 0);
         area_full[k] = a;
-        int4 o = make_int4(0, 0, 0, 0);
-        if (a > 0) o = make_int4(kBig - bx, kBig - by, mx1 - 1, my1 - 1);
-        reinterpret_cast<int4*>(box_full)[k] = o;
+        int4 o4 = make_int4(0, 0, 0, 0);
+        if (a > 0) o4 = make_int4(kBig - bx, kBig - by, mx1 - 1, my1 - 1);
+        reinterpret_cast<int4*>(box_full)[k] = o4;
       }
     }
   }
