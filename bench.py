@@ -181,7 +181,19 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL may print its version banner on fd 1 at communicator creation; stdout must carry exactly one JSON
+        # line, so route fd 1 to stderr until the first collective has run.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     B, S = args.batch, max(1, min(args.streams, args.batch))
     pool = make_pool(B, args.n_masks, rank)
