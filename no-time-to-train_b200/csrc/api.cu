@@ -13,12 +13,13 @@ int launch_lowres_pack(const float*, int, int, int, float, float, uint32_t*, int
 int launch_project_masks(const AxisTable&, const AxisTable&, const uint32_t*, const int32_t*, int, int, int, int, int,
                          void*, int, bool, cudaStream_t);
 int launch_normalize_split(const float*, const int32_t*, int, int, int, float*, void*, cudaStream_t);
-int launch_gemm_tc(const void*, int, const void*, int, float*, int, int, int, int, cudaStream_t);
+int launch_gemm_tc(const void*, int, const void*, int, float*, int, int, int, int, int, size_t, int*, cudaStream_t);
+int gemm_tc_pick_splits(int, int, int, int);
 int launch_split_rows(const float*, int, int, int, int, int, void*, cudaStream_t);
 int launch_split_transpose(const float*, int, int, int, int, int, void*, cudaStream_t);
 int launch_normalize_rows(const float*, const int32_t*, int, int, float*, cudaStream_t);
 int launch_proto_prepare(const float*, int, int, int, float*, cudaStream_t);
-int launch_top1(const float*, int, int, int, float*, int32_t*, cudaStream_t);
+int launch_top1(const float*, int, size_t, float*, int, int, int, float*, int32_t*, cudaStream_t);
 size_t nms_workspace_bytes(int n);
 int launch_box_nms(const int32_t*, const float*, const int32_t*, const float*, int, float, int, int32_t*, int32_t*,
                    int32_t*, int32_t*, void*, size_t, cudaStream_t);
@@ -71,7 +72,7 @@ static int pool_contract(const float* proj, const float* feat, int n, int e, int
   if (err) return err;
   err = launch_split_transpose(feat, c, c, e, ep, 1, b_split, s);
   if (err) return err;
-  return launch_gemm_tc(a_split, 3 * ep, b_split, 3 * ep, sums, c, n, c, 3 * ep, s);
+  return launch_gemm_tc(a_split, 3 * ep, b_split, 3 * ep, sums, c, n, c, 3 * ep, 1, 0, nullptr, s);
 }
 
 // rows of `sums` -> /area -> L2-normalise -> obj_feats (+ split-bf16 copy when the vector path applies).
@@ -90,14 +91,24 @@ static bool projection_supported(int in_size, int out_size) {
 
 // sim[n, n_cls] = obj_feats[n, c] * proto[n_cls, c]^T
 // (a_ready: a_split already holds the split obj_feats, written by normalize_split_kernel)
-static int sim_contract(const float* obj_feats, const float* proto, int n, int c, int n_cls, float* sim, void* a_split,
-                        void* b_split, bool a_ready, cudaStream_t s) {
+// The similarity GEMM has few output tiles (n_cls is small), so it runs split-K into `partials`
+// [splits, n, n_cls]; top1_kernel sums them in a fixed order, writes `sim` (nullable) and the row arg-max.
+constexpr int kMaxSimSplits = 8;
+static int sim_top1(const float* obj_feats, const float* proto, int n, int c, int n_cls, float* sim, float* partials,
+                    float* top_score, int32_t* top_label, void* a_split, void* b_split, bool a_ready, int sm_count,
+                    cudaStream_t s) {
   const int cp = pad64(c);
   int err = a_ready ? NTTT_OK : launch_split_rows(obj_feats, c, n, c, cp, 0, a_split, s);
   if (err) return err;
   err = launch_split_rows(proto, c, n_cls, c, cp, 1, b_split, s);
   if (err) return err;
-  return launch_gemm_tc(a_split, 3 * cp, b_split, 3 * cp, sim, n_cls, n, n_cls, 3 * cp, s);
+  const int want = gemm_tc_pick_splits(n, n_cls, 3 * cp, sm_count);
+  const size_t stride = (size_t)n * n_cls;
+  int splits = 1;
+  err = launch_gemm_tc(a_split, 3 * cp, b_split, 3 * cp, partials, n_cls, n, n_cls, 3 * cp,
+                       want < kMaxSimSplits ? want : kMaxSimSplits, stride, &splits, s);
+  if (err) return err;
+  return launch_top1(partials, splits, stride, sim, n_cls, n, n_cls, top_score, top_label, s);
 }
 
 }  // namespace nttt
@@ -143,8 +154,8 @@ size_t nttt_sizeof_match_args(void) { return sizeof(nttt_match_args); }
 
 unsigned long long nttt_launch_count(void) { return g_launches; }
 
-static const char* const kStageNames[] = {"lowres_pack", "project_masks", "pool_gemm", "normalize_rows", "sim_gemm",
-                                          "top1", "box_nms", "upsample_pack", "mask_ios", "decay_rank", "unpack"};
+static const char* const kStageNames[] = {"lowres_pack", "project_masks", "pool_gemm", "normalize_rows", "sim_top1",
+                                          "box_nms", "upsample_pack", "mask_ios", "decay_rank", "unpack"};
 static constexpr int kNumStages = sizeof(kStageNames) / sizeof(kStageNames[0]);
 
 int nttt_profile_num_stages(void) { return kNumStages; }
@@ -268,7 +279,7 @@ int nttt_proto_prepare(const float* feats_ins_avg, int n_cls, int shots, int c, 
 
 size_t nttt_similarity_workspace_bytes(int n, int c, int n_cls) {
   const size_t cp = pad64(c);
-  return align_up(sizeof(float) * (size_t)n * n_cls, 256) + align_up(2 * (size_t)n * 3 * cp, 256) +
+  return align_up(sizeof(float) * (size_t)kMaxSimSplits * n * n_cls, 256) + align_up(2 * (size_t)n * 3 * cp, 256) +
          align_up(2 * (size_t)n_cls * 3 * cp, 256);
 }
 
@@ -281,12 +292,11 @@ int nttt_similarity_top1(nttt_ctx* ctx, const float* obj_feats, const float* pro
   cudaStream_t s = (cudaStream_t)stream;
   if (!workspace || workspace_bytes < nttt_similarity_workspace_bytes(n, c, n_cls)) return NTTT_EWORKSPACE;
   char* ws = static_cast<char*>(workspace);
-  float* simbuf = sim ? sim : reinterpret_cast<float*>(ws);
-  char* a_split = ws + align_up(sizeof(float) * (size_t)n * n_cls, 256);
+  float* partials = reinterpret_cast<float*>(ws);
+  char* a_split = ws + align_up(sizeof(float) * (size_t)kMaxSimSplits * n * n_cls, 256);
   char* b_split = a_split + align_up(2 * (size_t)n * 3 * pad64(c), 256);
-  int err = sim_contract(obj_feats, proto, n, c, n_cls, simbuf, a_split, b_split, false, s);
-  if (err) return err;
-  return launch_top1(simbuf, n_cls, n, n_cls, top_score, top_label, s);
+  return sim_top1(obj_feats, proto, n, c, n_cls, sim, partials, top_score, top_label, a_split, b_split, false,
+                  ctx->sm_count, s);
 }
 
 size_t nttt_nms_workspace_bytes(int n) { return nms_workspace_bytes(n > 0 ? n : 1); }
@@ -397,7 +407,7 @@ int nttt_fill_finalize(const float* sum, const float* wsum, int n_cls, int shots
 // ---------------------------------------------------------------------------------------------------
 struct MatchLayout {
   uint32_t* bits_lr; int32_t* area_lr; int32_t* box_lr; int32_t* stab; int32_t* flags;
-  float* proj; float* sums; float* obj_feats; float* sim; float* top_score; int32_t* top_label;
+  float* proj; float* sums; float* obj_feats; float* sim; float* sim_part; float* top_score; int32_t* top_label;
   char* a_split; char* b_split;
   void* nms_ws; size_t nms_ws_bytes; int32_t* keep; int32_t* sel;
   uint32_t* bits_full; int32_t* rect; int32_t* area_full; int32_t* box_full; int32_t* scratch;
@@ -419,6 +429,7 @@ static MatchLayout carve(void* ws, int n, int lr_h, int lr_w, int eh, int ew, in
   L.sums = cv.take<float>((size_t)n * c);
   L.obj_feats = cv.take<float>((size_t)n * c);
   L.sim = cv.take<float>((size_t)n * n_cls);
+  L.sim_part = cv.take<float>((size_t)kMaxSimSplits * n * n_cls);
   {
     const size_t kmax = (size_t)3 * (pad64(eh * ew) > pad64(c) ? pad64(eh * ew) : pad64(c));
     const size_t rows_b = (size_t)(c > n_cls ? c : n_cls);
@@ -499,8 +510,8 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   bool a_ready = false;
   NTTT_STEP(normalize_rows(L.sums, L.area_lr, n, a->c, obj_feats, L.a_split, &a_ready, s));
   // a7/a8: similarity + top-1
-  NTTT_STEP(sim_contract(obj_feats, a->proto, n, a->c, a->n_cls, sim, L.a_split, L.b_split, a_ready, s));
-  NTTT_STEP(launch_top1(sim, a->n_cls, n, a->n_cls, L.top_score, L.top_label, s));
+  NTTT_STEP(sim_top1(obj_feats, a->proto, n, a->c, a->n_cls, a->sim, L.sim_part, L.top_score, L.top_label, L.a_split,
+                     L.b_split, a_ready, ctx->sm_count, s));
   // a10/a11
   NTTT_STEP(launch_box_nms(L.box_lr, a->pred_ious, L.top_label, L.top_score, n, a->nms_thr, max_sel, L.keep,
                            a->counts + 0, L.sel, a->counts + 1, L.nms_ws, L.nms_ws_bytes, s));

@@ -53,6 +53,30 @@ __device__ __forceinline__ int warp_max(int v) {
   return v;
 }
 
+// Bitonic sort of 1024 64-bit keys held one per thread (blockDim.x == 1024), ascending: thread i returns the
+// i-th smallest key.  Exchanges at distance < 32 are warp shuffles; only the 15 stages at distance >= 32 go
+// through shared memory (s_x: 1024 keys).  Keys must be distinct (callers put the index in the low bits).
+__device__ __forceinline__ unsigned long long block_bitonic_sort_1024(unsigned long long key,
+                                                                      unsigned long long* s_x) {
+  const int i = threadIdx.x;
+  for (int k = 2; k <= 1024; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      unsigned long long other;
+      if (j >= 32) {
+        s_x[i] = key;
+        __syncthreads();
+        other = s_x[i ^ j];
+        __syncthreads();
+      } else {
+        other = __shfl_xor_sync(kFull, key, j);
+      }
+      const bool take_min = ((i & j) == 0) == ((i & k) == 0);
+      key = (take_min == (other < key)) ? other : key;
+    }
+  }
+  return key;
+}
+
 // streaming 128-bit load that does not pollute L1 (data is touched once)
 __device__ __forceinline__ float4 ld_stream(const float4* p) {
   float4 r;

@@ -123,11 +123,16 @@ struct GemmSmem {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               float* __restrict__ D, int ldd, int M, int N, int num_k_blocks) {
+               float* __restrict__ D, int ldd, int M, int N, int total_k_blocks, int kb_per_split,
+               size_t split_stride) {
   extern __shared__ uint8_t smem_raw[];
   auto& sm = *reinterpret_cast<GemmSmem<BN, STAGES>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
+  // split-K: blockIdx.z owns k-blocks [kb0, kb0 + num_k_blocks) and writes its partial tile to D + z*split_stride
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int num_k_blocks = min(kb_per_split, total_k_blocks - kb0);
+  D += (size_t)blockIdx.z * split_stride;
   constexpr uint32_t kStageBytes = (kBM + BN) * kBK * sizeof(__nv_bfloat16);
   constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
 
@@ -156,8 +161,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&sm.empty[s], ph ^ 1);
         mbar_expect_tx(&sm.full[s], kStageBytes);
-        tma_load_2d(sm.a[s], &map_a, &sm.full[s], kb * kBK, m0);
-        tma_load_2d(sm.b[s], &map_b, &sm.full[s], kb * kBK, n0);
+        tma_load_2d(sm.a[s], &map_a, &sm.full[s], (kb0 + kb) * kBK, m0);
+        tma_load_2d(sm.b[s], &map_b, &sm.full[s], (kb0 + kb) * kBK, n0);
       }
     }
   } else if (warp == 1) {
@@ -252,7 +257,7 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int k, int ld,
 
 template <int BN, int STAGES>
 static int launch_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, float* D, int ldd, int M, int N,
-                     int K, cudaStream_t s) {
+                     int K, int splits, size_t split_stride, cudaStream_t s) {
   CUtensorMap ma, mb;
   int err = make_map(&ma, A, M, K, lda, kBM);
   if (err) return err;
@@ -261,19 +266,38 @@ static int launch_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, in
   const size_t smem = sizeof(GemmSmem<BN, STAGES>) + 1024;
   auto kern = gemm_tc_kernel<BN, STAGES>;
   NTTT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(ceil_div(N, BN), ceil_div(M, kBM));
-  kern<<<grid, kGemmThreads, smem, s>>>(ma, mb, D, ldd, M, N, K / kBK);
+  const int total_kb = K / kBK;
+  const int kb_per = ceil_div(total_kb, splits);
+  dim3 grid(ceil_div(N, BN), ceil_div(M, kBM), ceil_div(total_kb, kb_per));
+  kern<<<grid, kGemmThreads, smem, s>>>(ma, mb, D, ldd, M, N, total_kb, kb_per, split_stride);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }
 
 // A [M, K] and B [N, K] bf16, K a multiple of 64, rows 16-byte aligned (lda, ldb multiples of 8)
-int launch_gemm_tc(const void* A, int lda, const void* B, int ldb, float* D, int ldd, int M, int N, int K,
-                   cudaStream_t s) {
+// splits > 1: split-K, partial tile z is written to D + z*split_stride (the caller sums the partials in a fixed
+// order); *splits_out receives the number of partials actually produced.
+int launch_gemm_tc(const void* A, int lda, const void* B, int ldb, float* D, int ldd, int M, int N, int K, int splits,
+                   size_t split_stride, int* splits_out, cudaStream_t s) {
+  if (splits_out) *splits_out = 1;
   if (M <= 0 || N <= 0) return NTTT_OK;
-  if (K <= 0 || K % kBK != 0 || lda % 8 != 0 || ldb % 8 != 0) return NTTT_EINVAL;
+  if (K <= 0 || K % kBK != 0 || lda % 8 != 0 || ldb % 8 != 0 || splits < 1) return NTTT_EINVAL;
+  const int total_kb = K / kBK;
+  const int kb_per = ceil_div(total_kb, splits);
+  if (splits_out) *splits_out = ceil_div(total_kb, kb_per);
   return launch_tc<64, 6>(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(B), ldb, D, ldd,
-                          M, N, K, s);
+                          M, N, K, splits, split_stride, s);
+}
+
+// how many K splits fill the machine for an M x N output of 128 x 64 tiles (1 when the tiles already do)
+int gemm_tc_pick_splits(int M, int N, int K, int sm_count) {
+  const int tiles = ceil_div(N, 64) * ceil_div(M, kBM);
+  const int total_kb = K / kBK;
+  int splits = sm_count / (tiles > 0 ? tiles : 1);
+  if (splits < 1) splits = 1;
+  if (splits > 8) splits = 8;
+  if (splits > total_kb) splits = total_kb;
+  return splits;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -218,30 +218,37 @@ decay_rank_kernel(const float* __restrict__ top_score, const int32_t* __restrict
   extern __shared__ unsigned long long s_keys[];
   float* s_val = reinterpret_cast<float*>(s_keys + n_pad);
   const int nsel = min(*n_sel, max_sel);
-  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
-    unsigned long long key = ~0ull;
-    if (i < nsel) {
-      // empty full-res mask: the reference's 0/0 on the IoS diagonal -> NaN (torch.max propagates it)
-      const float io = (area_full && area_full[i] == 0) ? __int_as_float(0x7fc00000) : ios[i];
-      const float d = __fmul_rn(top_score[sel[i]], sqrtf(__fsub_rn(1.0f, io)));
-      s_val[i] = d;
-      if (decayed_out) decayed_out[i] = d;
-      key = ((unsigned long long)desc_key_nanfirst(d) << 32) | (uint32_t)i;
-    }
-    s_keys[i] = key;
-  }
-  __syncthreads();
-  for (int k = 2; k <= n_pad; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long a = s_keys[i], b = s_keys[ixj];
-          const bool up = (i & k) == 0;
-          if ((a > b) == up) { s_keys[i] = b; s_keys[ixj] = a; }
+  auto make_key = [&](int i) -> unsigned long long {
+    if (i >= nsel) return ~0ull;
+    // empty full-res mask: the reference's 0/0 on the IoS diagonal -> NaN (torch.max propagates it)
+    const float io = (area_full && area_full[i] == 0) ? __int_as_float(0x7fc00000) : ios[i];
+    const float d = __fmul_rn(top_score[sel[i]], sqrtf(__fsub_rn(1.0f, io)));
+    s_val[i] = d;
+    if (decayed_out) decayed_out[i] = d;
+    return ((unsigned long long)desc_key_nanfirst(d) << 32) | (uint32_t)i;
+  };
+  if (n_pad <= 1024) {
+    // one key per thread, warp shuffles for the short exchanges (n_pad == 1024 by construction of the launcher)
+    unsigned long long key = make_key(threadIdx.x);
+    __syncthreads();  // s_val complete before s_keys is reused as the exchange buffer? (distinct regions) - keep order
+    key = block_bitonic_sort_1024(key, s_keys);
+    s_keys[threadIdx.x] = key;
+    __syncthreads();
+  } else {
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) s_keys[i] = make_key(i);
+    __syncthreads();
+    for (int k = 2; k <= n_pad; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const unsigned long long a = s_keys[i], b = s_keys[ixj];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) { s_keys[i] = b; s_keys[ixj] = a; }
+          }
         }
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
   const int nout = min(num_out, nsel);
@@ -267,7 +274,7 @@ int launch_decay_rank(const float* top_score, const int32_t* labels, const float
     NTTT_CUDA(cudaMemsetAsync(n_out, 0, sizeof(int32_t), s));
     return NTTT_OK;
   }
-  int n_pad = 1;
+  int n_pad = 1024;  // the register sort always runs the 1024-key network
   while (n_pad < max_sel) n_pad <<= 1;
   const size_t smem = (sizeof(unsigned long long) + sizeof(float)) * (size_t)n_pad;
   if (smem > 200 * 1024) return NTTT_EUNSUPPORTED;

@@ -16,10 +16,28 @@ __device__ __forceinline__ uint32_t desc_key(float f) {
   return ~u;
 }
 
-// single-CTA bitonic sort of (score desc, index asc); n_pad = next pow2 >= n
+// single-CTA bitonic sort of (score desc, index asc); also gathers the boxes / labels into sorted order so the
+// matrix kernel reads them coalesced instead of chasing order[] -> box[] pointers.
+// kReg: n_pad <= 1024, one key per thread in registers (warp shuffles for the short exchanges)
+template <bool kReg>
 __global__ void __launch_bounds__(1024)
-nms_sort_kernel(const float* __restrict__ scores, int n, int n_pad, int32_t* __restrict__ order) {
+nms_sort_kernel(const float* __restrict__ scores, const int32_t* __restrict__ box, const int32_t* __restrict__ labels,
+                int n, int n_pad, int32_t* __restrict__ order, float4* __restrict__ sorted_box,
+                int32_t* __restrict__ sorted_label) {
   extern __shared__ unsigned long long s_keys[];
+  if (kReg) {
+    const int i = threadIdx.x;
+    unsigned long long key = i < n ? (((unsigned long long)desc_key(scores[i]) << 32) | (uint32_t)i) : ~0ull;
+    key = block_bitonic_sort_1024(key, s_keys);
+    if (i < n) {
+      const int o = (int)(key & 0xffffffffu);
+      order[i] = o;
+      const int4 bi = reinterpret_cast<const int4*>(box)[o];
+      sorted_box[i] = make_float4((float)bi.x, (float)bi.y, (float)bi.z, (float)bi.w);
+      sorted_label[i] = labels[o];
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < n_pad; i += blockDim.x)
     s_keys[i] = i < n ? (((unsigned long long)desc_key(scores[i]) << 32) | (uint32_t)i) : ~0ull;
   __syncthreads();
@@ -36,45 +54,42 @@ nms_sort_kernel(const float* __restrict__ scores, int n, int n_pad, int32_t* __r
       __syncthreads();
     }
   }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) order[i] = (int32_t)(s_keys[i] & 0xffffffffu);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int o = (int)(s_keys[i] & 0xffffffffu);
+    order[i] = o;
+    const int4 bi = reinterpret_cast<const int4*>(box)[o];
+    sorted_box[i] = make_float4((float)bi.x, (float)bi.y, (float)bi.z, (float)bi.w);
+    sorted_label[i] = labels[o];
+  }
 }
 
 // suppression bit matrix in sorted order: bit j of row i set iff j > i, same label, IoU(i,j) > thr
 __global__ void __launch_bounds__(256)
-nms_mask_kernel(const int32_t* __restrict__ box, const int32_t* __restrict__ labels,
-                const int32_t* __restrict__ order, int n, float thr, uint32_t* __restrict__ mask, int row_words) {
+nms_mask_kernel(const float4* __restrict__ sorted_box, const int32_t* __restrict__ sorted_label, int n, float thr,
+                uint32_t* __restrict__ mask, int row_words) {
   __shared__ float4 s_box[8][32];
   __shared__ int s_lab[8][32];
   const int i = blockIdx.y * 32 + threadIdx.x;  // sorted position of the row box
   const int cw = blockIdx.x * 8 + threadIdx.y;  // column word
   {
     const int j = cw * 32 + threadIdx.x;
-    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-    int l = -1;
-    if (j < n && cw < row_words) {
-      const int oj = order[j];
-      const int4 bi = reinterpret_cast<const int4*>(box)[oj];
-      b = make_float4((float)bi.x, (float)bi.y, (float)bi.z, (float)bi.w);
-      l = labels[oj];
-    }
-    s_box[threadIdx.y][threadIdx.x] = b;
-    s_lab[threadIdx.y][threadIdx.x] = l;
+    const bool ok = j < n && cw < row_words;
+    s_box[threadIdx.y][threadIdx.x] = ok ? sorted_box[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s_lab[threadIdx.y][threadIdx.x] = ok ? sorted_label[j] : -1;
   }
   __syncthreads();
   if (i >= n || cw >= row_words) return;
   uint32_t bits = 0;
   if (cw * 32 + 31 > i) {
-    const int oi = order[i];
-    const int4 bi = reinterpret_cast<const int4*>(box)[oi];
-    const float ax1 = (float)bi.x, ay1 = (float)bi.y, ax2 = (float)bi.z, ay2 = (float)bi.w;
-    const float area_a = __fmul_rn(ax2 - ax1, ay2 - ay1);
-    const int la = labels[oi];
+    const float4 a = sorted_box[i];
+    const float area_a = __fmul_rn(a.z - a.x, a.w - a.y);
+    const int la = sorted_label[i];
     for (int t = 0; t < 32; ++t) {
       const int j = cw * 32 + t;
       if (j <= i || j >= n || s_lab[threadIdx.y][t] != la) continue;
       const float4 b = s_box[threadIdx.y][t];
-      const float w = fmaxf(fminf(ax2, b.z) - fmaxf(ax1, b.x), 0.0f);
-      const float h = fmaxf(fminf(ay2, b.w) - fmaxf(ay1, b.y), 0.0f);
+      const float w = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.0f);
+      const float h = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.0f);
       const float inter = __fmul_rn(w, h);
       const float area_b = __fmul_rn(b.z - b.x, b.w - b.y);
       const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
@@ -167,7 +182,8 @@ nms_scan_kernel(const uint32_t* __restrict__ mask, int row_words, const int32_t*
 
 size_t nms_workspace_bytes(int n) {
   const size_t row_words = (size_t)ceil_div(n, 32);
-  return align_up(sizeof(int32_t) * (size_t)n, 256) + align_up(sizeof(uint32_t) * row_words * (size_t)n, 256);
+  return align_up(sizeof(int32_t) * (size_t)n, 256) + align_up(sizeof(uint32_t) * row_words * (size_t)n, 256) +
+         align_up(sizeof(float4) * (size_t)n, 256) + align_up(sizeof(int32_t) * (size_t)n, 256);
 }
 
 int launch_box_nms(const int32_t* box, const float* nms_scores, const int32_t* labels, const float* top_score, int n,
@@ -180,18 +196,28 @@ int launch_box_nms(const int32_t* box, const float* nms_scores, const int32_t* l
   }
   if (n > kScanMaxN) return NTTT_EUNSUPPORTED;
   if (ws_bytes < nms_workspace_bytes(n)) return NTTT_EWORKSPACE;
-  int32_t* order = static_cast<int32_t*>(ws);
-  uint32_t* mask = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + align_up(sizeof(int32_t) * (size_t)n, 256));
+  char* w8 = static_cast<char*>(ws);
+  int32_t* order = reinterpret_cast<int32_t*>(w8);
+  uint32_t* mask = reinterpret_cast<uint32_t*>(w8 + align_up(sizeof(int32_t) * (size_t)n, 256));
+  const int row_words = ceil_div(n, 32);
+  float4* sorted_box = reinterpret_cast<float4*>(reinterpret_cast<char*>(mask) +
+                                                 align_up(sizeof(uint32_t) * (size_t)row_words * n, 256));
+  int32_t* sorted_label = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(sorted_box) +
+                                                     align_up(sizeof(float4) * (size_t)n, 256));
   int n_pad = 1;
   while (n_pad < n) n_pad <<= 1;
-  const size_t smem = sizeof(unsigned long long) * (size_t)n_pad;
-  if (smem > 48 * 1024)
-    NTTT_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  nms_sort_kernel<<<1, 1024, smem, s>>>(nms_scores, n, n_pad, order);
+  if (n_pad <= 1024) {
+    nms_sort_kernel<true><<<1, 1024, sizeof(unsigned long long) * 1024, s>>>(nms_scores, box, labels, n, 1024, order,
+                                                                             sorted_box, sorted_label);
+  } else {
+    const size_t smem = sizeof(unsigned long long) * (size_t)n_pad;
+    if (smem > 48 * 1024)
+      NTTT_CUDA(cudaFuncSetAttribute(nms_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_sort_kernel<false><<<1, 1024, smem, s>>>(nms_scores, box, labels, n, n_pad, order, sorted_box, sorted_label);
+  }
   NTTT_LAUNCH_CHECK();
-  const int row_words = ceil_div(n, 32);
   dim3 grid(ceil_div(row_words, 8), ceil_div(n, 32));
-  nms_mask_kernel<<<grid, dim3(32, 8), 0, s>>>(box, labels, order, n, thr, mask, row_words);
+  nms_mask_kernel<<<grid, dim3(32, 8), 0, s>>>(sorted_box, sorted_label, n, thr, mask, row_words);
   NTTT_LAUNCH_CHECK();
   const size_t stage_bytes = sizeof(uint32_t) * (size_t)n * row_words;
   if (stage_bytes <= 160 * 1024) {

@@ -142,17 +142,21 @@ int launch_proto_prepare(const float* ins_avg, int n_cls, int shots, int c, floa
 
 // top-1 over classes (lowest index on ties == torch.topk/argmax on CPU); when n_cls == 1 the reference's
 // `k == n_cls` branch applies: score *= (score > 0.6*score)  (Sam2MatchingBaseline_noAMG.py:606-609).
+// `part` holds n_splits split-K partial similarity matrices (stride split_stride floats); they are summed here
+// in a fixed order and the sum is written to `sim` (if non-null).
 __global__ void __launch_bounds__(256)
-top1_kernel(const float* __restrict__ sim, int ld, int n, int n_cls, float* __restrict__ top_score,
-            int32_t* __restrict__ top_label) {
+top1_kernel(const float* __restrict__ part, int n_splits, size_t split_stride, float* __restrict__ sim, int ld, int n,
+            int n_cls, float* __restrict__ top_score, int32_t* __restrict__ top_label) {
   const int row = blockIdx.x * 8 + warp_id();
   if (row >= n) return;
   const int lane = lane_id();
-  const float* src = sim + (size_t)row * ld;
+  const float* src = part + (size_t)row * ld;
   float best = -INFINITY;
   int arg = 0x7fffffff;
   for (int i = lane; i < n_cls; i += 32) {
-    const float v = src[i];
+    float v = src[i];
+    for (int z = 1; z < n_splits; ++z) v += src[(size_t)z * split_stride + i];
+    if (sim) sim[(size_t)row * ld + i] = v;
     if (v > best || (v == best && i < arg)) { best = v; arg = i; }
   }
 #pragma unroll
@@ -168,9 +172,10 @@ top1_kernel(const float* __restrict__ sim, int ld, int n, int n_cls, float* __re
   }
 }
 
-int launch_top1(const float* sim, int ld, int n, int n_cls, float* top_score, int32_t* top_label, cudaStream_t s) {
+int launch_top1(const float* part, int n_splits, size_t split_stride, float* sim, int ld, int n, int n_cls,
+                float* top_score, int32_t* top_label, cudaStream_t s) {
   if (n <= 0) return NTTT_OK;
-  top1_kernel<<<ceil_div(n, 8), 256, 0, s>>>(sim, ld, n, n_cls, top_score, top_label);
+  top1_kernel<<<ceil_div(n, 8), 256, 0, s>>>(part, n_splits, split_stride, sim, ld, n, n_cls, top_score, top_label);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }
