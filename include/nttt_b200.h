@@ -105,6 +105,15 @@ int nttt_similarity_top1(nttt_ctx* ctx, const float* obj_feats, const float* pro
                          float* sim, float* top_score, int32_t* top_label, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* negative-reference variant of the similarity (compute_sim_global_avg_with_neg,
+ * matching_baseline_utils.py:906-941): sim = sp * exp(-max(sn - sp, 0) / sigma) with sp = max(obj.proto_pos[c], 0),
+ * sn = max_l max(obj.proto_neg[c,l], 0).  proto_pos [n_cls, c] and proto_neg [n_cls*l_neg, c] are unit rows
+ * (nttt_proto_prepare with shots = 1 normalises rows). */
+size_t nttt_similarity_neg_workspace_bytes(int n, int c, int n_cls, int l_neg);
+int nttt_similarity_neg_top1(nttt_ctx* ctx, const float* obj_feats, const float* proto_pos, const float* proto_neg,
+                             int n, int c, int n_cls, int l_neg, float sigma, float* sim, float* top_score,
+                             int32_t* top_label, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * a10 / a11 — class-aware box NMS + positive-score filter
  * replaces: torchvision batched_nms(boxes.float(), pred_ious, labels, nms_thr)[:out_num] (:621-629) and the
@@ -206,10 +215,18 @@ typedef struct nttt_match_args {
   /* workspace */
   void* workspace;
   size_t workspace_bytes;
+  /* negative-reference scoring (with_negative_refs, matching_baseline_utils.py:906-941); proto_neg == NULL: off.
+   * With it, `proto` must be the normalised CLASS-level average (feats_avg) and proto_neg the normalised
+   * negative instance averages [n_cls * l_neg, c]; workspace from nttt_match_workspace_bytes_neg. */
+  const float* proto_neg;
+  int32_t l_neg;
+  float sigma;
 } nttt_match_args;
 
 size_t nttt_match_workspace_bytes(int n, int lr_h, int lr_w, int eh, int ew, int c, int n_cls, int ori_h,
                                   int ori_w, int max_sel);
+size_t nttt_match_workspace_bytes_neg(int n, int lr_h, int lr_w, int eh, int ew, int c, int n_cls, int ori_h,
+                                      int ori_w, int max_sel, int l_neg);
 int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* args, void* stream);
 /* sizeof(nttt_match_args) as compiled, so FFI mirrors can verify their layout */
 size_t nttt_sizeof_match_args(void);

@@ -33,6 +33,7 @@ class MatchArgs(ctypes.Structure):
         ("out_index", c_void_p), ("counts", c_void_p),
         ("sim", c_void_p), ("obj_feats", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("proto_neg", c_void_p), ("l_neg", c_int32), ("sigma", c_float),
     ]
 
 
@@ -63,6 +64,10 @@ SIGNATURES = {
     "nttt_fill_pool_accumulate": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "nttt_fill_finalize": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "nttt_match_workspace_bytes": (c_size_t, [c_int] * 10),
+    "nttt_match_workspace_bytes_neg": (c_size_t, [c_int] * 11),
+    "nttt_similarity_neg_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "nttt_similarity_neg_top1": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_size_t,
+                                          _P]),
     "nttt_match_image": (c_int, [_P, POINTER(MatchArgs), _P]),
     "nttt_sizeof_match_args": (c_size_t, []),
     "nttt_launch_count": (ctypes.c_ulonglong, []),

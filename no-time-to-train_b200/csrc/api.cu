@@ -20,6 +20,8 @@ int launch_split_transpose(const float*, int, int, int, int, int, void*, cudaStr
 int launch_normalize_rows(const float*, const int32_t*, int, int, float*, cudaStream_t);
 int launch_proto_prepare(const float*, int, int, int, float*, cudaStream_t);
 int launch_top1(const float*, int, size_t, float*, int, int, int, float*, int32_t*, cudaStream_t);
+int launch_neg_top1(const float*, int, size_t, const float*, int, size_t, int, int, int, float, float*, float*, int32_t*,
+                    cudaStream_t);
 size_t nms_workspace_bytes(int n);
 int launch_box_nms(const int32_t*, const float*, const int32_t*, const float*, int, float, int, int32_t*, int32_t*,
                    int32_t*, int32_t*, void*, size_t, cudaStream_t);
@@ -94,21 +96,42 @@ static bool projection_supported(int in_size, int out_size) {
 // The similarity GEMM has few output tiles (n_cls is small), so it runs split-K into `partials`
 // [splits, n, n_cls]; top1_kernel sums them in a fixed order, writes `sim` (nullable) and the row arg-max.
 constexpr int kMaxSimSplits = 8;
-static int sim_top1(const float* obj_feats, const float* proto, int n, int c, int n_cls, float* sim, float* partials,
-                    float* top_score, int32_t* top_label, void* a_split, void* b_split, bool a_ready, int sm_count,
-                    cudaStream_t s) {
+// floats needed for the split-K partials of an [n, cols] similarity matrix (sized for a 148-SM part)
+static size_t sim_partial_floats(int n, int cols, int c) {
+  int sp = gemm_tc_pick_splits(n, cols, 3 * pad64(c), 148);
+  if (sp > kMaxSimSplits) sp = kMaxSimSplits;
+  return (size_t)sp * n * cols;
+}
+
+// proto_neg == nullptr: plain cosine scoring.  Otherwise negative-reference scoring: proto is the normalised
+// class-level average, proto_neg [n_cls * l_neg, c] the normalised negative instance averages.
+static int sim_top1(const float* obj_feats, const float* proto, const float* proto_neg, int l_neg, float sigma, int n,
+                    int c, int n_cls, float* sim, float* partials, float* partials_neg, float* top_score,
+                    int32_t* top_label, void* a_split, void* b_split, bool a_ready, int sm_count, cudaStream_t s) {
   const int cp = pad64(c);
   int err = a_ready ? NTTT_OK : launch_split_rows(obj_feats, c, n, c, cp, 0, a_split, s);
   if (err) return err;
   err = launch_split_rows(proto, c, n_cls, c, cp, 1, b_split, s);
   if (err) return err;
-  const int want = gemm_tc_pick_splits(n, n_cls, 3 * cp, sm_count);
+  int want = gemm_tc_pick_splits(n, n_cls, 3 * cp, sm_count < 148 ? sm_count : 148);
+  if (want > kMaxSimSplits) want = kMaxSimSplits;
   const size_t stride = (size_t)n * n_cls;
   int splits = 1;
-  err = launch_gemm_tc(a_split, 3 * cp, b_split, 3 * cp, partials, n_cls, n, n_cls, 3 * cp,
-                       want < kMaxSimSplits ? want : kMaxSimSplits, stride, &splits, s);
+  err = launch_gemm_tc(a_split, 3 * cp, b_split, 3 * cp, partials, n_cls, n, n_cls, 3 * cp, want, stride, &splits, s);
   if (err) return err;
-  return launch_top1(partials, splits, stride, sim, n_cls, n, n_cls, top_score, top_label, s);
+  if (!proto_neg) return launch_top1(partials, splits, stride, sim, n_cls, n, n_cls, top_score, top_label, s);
+  const int cols = n_cls * l_neg;
+  err = launch_split_rows(proto_neg, c, cols, c, cp, 1, b_split, s);  // stream-ordered after the GEMM that read b_split
+  if (err) return err;
+  int want_n = gemm_tc_pick_splits(n, cols, 3 * cp, sm_count < 148 ? sm_count : 148);
+  if (want_n > kMaxSimSplits) want_n = kMaxSimSplits;
+  const size_t stride_n = (size_t)n * cols;
+  int splits_n = 1;
+  err = launch_gemm_tc(a_split, 3 * cp, b_split, 3 * cp, partials_neg, cols, n, cols, 3 * cp, want_n, stride_n, &splits_n,
+                       s);
+  if (err) return err;
+  return launch_neg_top1(partials, splits, stride, partials_neg, splits_n, stride_n, n, n_cls, l_neg, sigma, sim,
+                         top_score, top_label, s);
 }
 
 }  // namespace nttt
@@ -279,7 +302,7 @@ int nttt_proto_prepare(const float* feats_ins_avg, int n_cls, int shots, int c, 
 
 size_t nttt_similarity_workspace_bytes(int n, int c, int n_cls) {
   const size_t cp = pad64(c);
-  return align_up(sizeof(float) * (size_t)kMaxSimSplits * n * n_cls, 256) + align_up(2 * (size_t)n * 3 * cp, 256) +
+  return align_up(sizeof(float) * sim_partial_floats(n, n_cls, c), 256) + align_up(2 * (size_t)n * 3 * cp, 256) +
          align_up(2 * (size_t)n_cls * 3 * cp, 256);
 }
 
@@ -293,10 +316,35 @@ int nttt_similarity_top1(nttt_ctx* ctx, const float* obj_feats, const float* pro
   if (!workspace || workspace_bytes < nttt_similarity_workspace_bytes(n, c, n_cls)) return NTTT_EWORKSPACE;
   char* ws = static_cast<char*>(workspace);
   float* partials = reinterpret_cast<float*>(ws);
-  char* a_split = ws + align_up(sizeof(float) * (size_t)kMaxSimSplits * n * n_cls, 256);
+  char* a_split = ws + align_up(sizeof(float) * sim_partial_floats(n, n_cls, c), 256);
   char* b_split = a_split + align_up(2 * (size_t)n * 3 * pad64(c), 256);
-  return sim_top1(obj_feats, proto, n, c, n_cls, sim, partials, top_score, top_label, a_split, b_split, false,
-                  ctx->sm_count, s);
+  return sim_top1(obj_feats, proto, nullptr, 0, 1.0f, n, c, n_cls, sim, partials, nullptr, top_score, top_label, a_split,
+                  b_split, false, ctx->sm_count, s);
+}
+
+size_t nttt_similarity_neg_workspace_bytes(int n, int c, int n_cls, int l_neg) {
+  const size_t cp = pad64(c);
+  const size_t cols = (size_t)n_cls * l_neg;
+  return align_up(sizeof(float) * sim_partial_floats(n, n_cls, c), 256) +
+         align_up(sizeof(float) * sim_partial_floats(n, (int)cols, c), 256) + align_up(2 * (size_t)n * 3 * cp, 256) +
+         align_up(2 * cols * 3 * cp, 256);
+}
+
+int nttt_similarity_neg_top1(nttt_ctx* ctx, const float* obj_feats, const float* proto_pos, const float* proto_neg,
+                             int n, int c, int n_cls, int l_neg, float sigma, float* sim, float* top_score,
+                             int32_t* top_label, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!ctx || n < 0 || c <= 0 || n_cls <= 0 || l_neg <= 0 || !(sigma > 0.0f)) return NTTT_EINVAL;
+  if (n == 0) return NTTT_OK;
+  if (!obj_feats || !proto_pos || !proto_neg || !top_score || !top_label) return NTTT_EINVAL;
+  if (!workspace || workspace_bytes < nttt_similarity_neg_workspace_bytes(n, c, n_cls, l_neg)) return NTTT_EWORKSPACE;
+  char* ws = static_cast<char*>(workspace);
+  float* partials = reinterpret_cast<float*>(ws);
+  float* partials_neg = reinterpret_cast<float*>(ws + align_up(sizeof(float) * sim_partial_floats(n, n_cls, c), 256));
+  char* a_split = reinterpret_cast<char*>(partials_neg) +
+                  align_up(sizeof(float) * sim_partial_floats(n, n_cls * l_neg, c), 256);
+  char* b_split = a_split + align_up(2 * (size_t)n * 3 * pad64(c), 256);
+  return sim_top1(obj_feats, proto_pos, proto_neg, l_neg, sigma, n, c, n_cls, sim, partials, partials_neg, top_score,
+                  top_label, a_split, b_split, false, ctx->sm_count, (cudaStream_t)stream);
 }
 
 size_t nttt_nms_workspace_bytes(int n) { return nms_workspace_bytes(n > 0 ? n : 1); }
@@ -407,7 +455,7 @@ int nttt_fill_finalize(const float* sum, const float* wsum, int n_cls, int shots
 // ---------------------------------------------------------------------------------------------------
 struct MatchLayout {
   uint32_t* bits_lr; int32_t* area_lr; int32_t* box_lr; int32_t* stab; int32_t* flags;
-  float* proj; float* sums; float* obj_feats; float* sim; float* sim_part; float* top_score; int32_t* top_label;
+  float* proj; float* sums; float* obj_feats; float* sim; float* sim_part; float* sim_part_neg; float* top_score; int32_t* top_label;
   char* a_split; char* b_split;
   void* nms_ws; size_t nms_ws_bytes; int32_t* keep; int32_t* sel;
   uint32_t* bits_full; int32_t* rect; int32_t* area_full; int32_t* box_full; int32_t* scratch;
@@ -416,7 +464,7 @@ struct MatchLayout {
 };
 
 static MatchLayout carve(void* ws, int n, int lr_h, int lr_w, int eh, int ew, int c, int n_cls, int oh, int ow,
-                         int max_sel, int num_out) {
+                         int max_sel, int num_out, int l_neg) {
   Carver cv(ws);
   MatchLayout L;
   const size_t p = (size_t)lr_h * lr_w;
@@ -429,10 +477,12 @@ static MatchLayout carve(void* ws, int n, int lr_h, int lr_w, int eh, int ew, in
   L.sums = cv.take<float>((size_t)n * c);
   L.obj_feats = cv.take<float>((size_t)n * c);
   L.sim = cv.take<float>((size_t)n * n_cls);
-  L.sim_part = cv.take<float>((size_t)kMaxSimSplits * n * n_cls);
+  L.sim_part = cv.take<float>(sim_partial_floats(n, n_cls, c));
+  L.sim_part_neg = cv.take<float>(l_neg > 0 ? sim_partial_floats(n, n_cls * l_neg, c) : 1);
   {
     const size_t kmax = (size_t)3 * (pad64(eh * ew) > pad64(c) ? pad64(eh * ew) : pad64(c));
-    const size_t rows_b = (size_t)(c > n_cls ? c : n_cls);
+    size_t rows_b = (size_t)(c > n_cls ? c : n_cls);
+    if ((size_t)n_cls * (l_neg > 0 ? l_neg : 0) > rows_b) rows_b = (size_t)n_cls * l_neg;
     L.a_split = cv.take<char>(2 * (size_t)n * kmax);
     L.b_split = cv.take<char>(2 * rows_b * kmax);
   }
@@ -459,7 +509,15 @@ size_t nttt_match_workspace_bytes(int n, int lr_h, int lr_w, int eh, int ew, int
   if (n < 0 || lr_h <= 0 || lr_w <= 0 || eh <= 0 || ew <= 0 || c <= 0 || n_cls <= 0 || ori_h <= 0 || ori_w <= 0 ||
       max_sel < 0)
     return 0;
-  return carve(nullptr, n, lr_h, lr_w, eh, ew, c, n_cls, ori_h, ori_w, max_sel, max_sel).total;
+  return carve(nullptr, n, lr_h, lr_w, eh, ew, c, n_cls, ori_h, ori_w, max_sel, max_sel, 0).total;
+}
+
+size_t nttt_match_workspace_bytes_neg(int n, int lr_h, int lr_w, int eh, int ew, int c, int n_cls, int ori_h, int ori_w,
+                                      int max_sel, int l_neg) {
+  if (n < 0 || lr_h <= 0 || lr_w <= 0 || eh <= 0 || ew <= 0 || c <= 0 || n_cls <= 0 || ori_h <= 0 || ori_w <= 0 ||
+      max_sel < 0 || l_neg < 0)
+    return 0;
+  return carve(nullptr, n, lr_h, lr_w, eh, ew, c, n_cls, ori_h, ori_w, max_sel, max_sel, l_neg).total;
 }
 
 int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
@@ -477,8 +535,10 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   if (!a->logits || !a->pred_ious || !a->tar_feat || !a->proto || !a->out_masks || !a->out_boxes || !a->out_scores ||
       !a->out_labels || !a->out_index)
     return NTTT_EINVAL;
+  const int l_neg = a->proto_neg ? a->l_neg : 0;
+  if (a->proto_neg && (a->l_neg <= 0 || !(a->sigma > 0.0f))) return NTTT_EINVAL;
   MatchLayout L = carve(a->workspace, n, a->lr_h, a->lr_w, a->eh, a->ew, a->c, a->n_cls, a->ori_h, a->ori_w, max_sel,
-                        num_out);
+                        num_out, l_neg);
   if (a->workspace_bytes < L.total) return NTTT_EWORKSPACE;
   float* obj_feats = a->obj_feats ? a->obj_feats : L.obj_feats;
   float* sim = a->sim ? a->sim : L.sim;
@@ -510,8 +570,8 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   bool a_ready = false;
   NTTT_STEP(normalize_rows(L.sums, L.area_lr, n, a->c, obj_feats, L.a_split, &a_ready, s));
   // a7/a8: similarity + top-1
-  NTTT_STEP(sim_top1(obj_feats, a->proto, n, a->c, a->n_cls, a->sim, L.sim_part, L.top_score, L.top_label, L.a_split,
-                     L.b_split, a_ready, ctx->sm_count, s));
+  NTTT_STEP(sim_top1(obj_feats, a->proto, a->proto_neg, l_neg, a->sigma, n, a->c, a->n_cls, a->sim, L.sim_part,
+                     L.sim_part_neg, L.top_score, L.top_label, L.a_split, L.b_split, a_ready, ctx->sm_count, s));
   // a10/a11
   NTTT_STEP(launch_box_nms(L.box_lr, a->pred_ious, L.top_label, L.top_score, n, a->nms_thr, max_sel, L.keep,
                            a->counts + 0, L.sel, a->counts + 1, L.nms_ws, L.nms_ws_bytes, s));

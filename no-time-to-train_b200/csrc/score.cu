@@ -180,4 +180,56 @@ int launch_top1(const float* part, int n_splits, size_t split_stride, float* sim
   return NTTT_OK;
 }
 
+// Negative-reference scoring (compute_sim_global_avg_with_neg, matching_baseline_utils.py:906-941) + top-1:
+//   sim_pos = clamp(obj . proto_pos[c], 0);  sim_neg = max_l clamp(obj . proto_neg[c, l], 0)
+//   sim     = sim_pos * exp(-clamp(sim_neg - sim_pos, 0) / sigma)
+// Both similarity matrices arrive as split-K partials and are summed here in a fixed order.
+__global__ void __launch_bounds__(256)
+neg_top1_kernel(const float* __restrict__ part_pos, int splits_pos, size_t stride_pos,
+                const float* __restrict__ part_neg, int splits_neg, size_t stride_neg, int n, int n_cls, int l_neg,
+                float sigma, float* __restrict__ sim, float* __restrict__ top_score, int32_t* __restrict__ top_label) {
+  const int row = blockIdx.x * 8 + warp_id();
+  if (row >= n) return;
+  const int lane = lane_id();
+  const float* pp = part_pos + (size_t)row * n_cls;
+  const float* pn = part_neg + (size_t)row * n_cls * l_neg;
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int i = lane; i < n_cls; i += 32) {
+    float sp = pp[i];
+    for (int z = 1; z < splits_pos; ++z) sp += pp[(size_t)z * stride_pos + i];
+    sp = fmaxf(sp, 0.0f);
+    float sn = 0.0f;  // clamp(min=0) before the max: the max of clamped values is >= 0
+    for (int l = 0; l < l_neg; ++l) {
+      float v = pn[i * l_neg + l];
+      for (int z = 1; z < splits_neg; ++z) v += pn[(size_t)z * stride_neg + i * l_neg + l];
+      sn = fmaxf(sn, v);
+    }
+    const float v = __fmul_rn(sp, expf(__fdiv_rn(__fmul_rn(-1.0f, fmaxf(__fsub_rn(sn, sp), 0.0f)), sigma)));
+    if (sim) sim[(size_t)row * n_cls + i] = v;
+    if (v > best || (v == best && i < arg)) { best = v; arg = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(kFull, best, o);
+    const int oa = __shfl_xor_sync(kFull, arg, o);
+    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  if (lane == 0) {
+    if (n_cls == 1) best = best * (float)(best > __fmul_rn(best, 0.6f));
+    top_score[row] = best;
+    top_label[row] = arg == 0x7fffffff ? 0 : arg;
+  }
+}
+
+int launch_neg_top1(const float* part_pos, int splits_pos, size_t stride_pos, const float* part_neg, int splits_neg,
+                    size_t stride_neg, int n, int n_cls, int l_neg, float sigma, float* sim, float* top_score,
+                    int32_t* top_label, cudaStream_t s) {
+  if (n <= 0) return NTTT_OK;
+  neg_top1_kernel<<<ceil_div(n, 8), 256, 0, s>>>(part_pos, splits_pos, stride_pos, part_neg, splits_neg, stride_neg, n,
+                                                 n_cls, l_neg, sigma, sim, top_score, top_label);
+  NTTT_LAUNCH_CHECK();
+  return NTTT_OK;
+}
+
 }  // namespace nttt

@@ -22,6 +22,7 @@ class StageConfig:
     cls_num_per_mask: int = 1
     enc_hw: tuple = (37, 37)
     expand_ratio: int = 8  # literal at :621
+    neg_sigma: float = 0.8  # literal at :596 (compute_sim_global_avg_with_neg(..., sigma=0.8))
 
 
 class PendingResult:
@@ -71,6 +72,8 @@ class MatchingStage:
         self.lib = _lib.load()
         self.ctx = ops.context(self.device)
         self.proto = None
+        self.proto_neg = None
+        self.l_neg = 0
         self.n_cls = 0
         self._ws = {}
 
@@ -78,7 +81,20 @@ class MatchingStage:
         """normalize(mean over all L slots) once per bank (`matching_baseline_utils.py:893-894`)."""
         f = feats_ins_avg.to(device=self.device, dtype=torch.float32).contiguous()
         self.proto = ops.proto_prepare(f)
+        self.proto_neg, self.l_neg = None, 0
         self.n_cls = f.shape[0]
+
+    def set_prototypes_with_negatives(self, feats_avg: torch.Tensor, feats_ins_avg_neg: torch.Tensor) -> None:
+        """Negative-reference scoring (`compute_sim_global_avg_with_neg`, `matching_baseline_utils.py:906-941`):
+        positive prototypes = normalize(class-level feats_avg), negatives = normalize(every negative slot)."""
+        pos = feats_avg.to(device=self.device, dtype=torch.float32).contiguous()
+        neg = feats_ins_avg_neg.to(device=self.device, dtype=torch.float32).contiguous()
+        n_cls, l_neg, c = neg.shape
+        assert pos.shape == (n_cls, c)
+        self.proto = ops.proto_prepare(pos.reshape(n_cls, 1, c))
+        self.proto_neg = ops.proto_prepare(neg.reshape(n_cls * l_neg, 1, c))
+        self.l_neg = l_neg
+        self.n_cls = n_cls
 
     def _workspace(self, key, nbytes: int) -> torch.Tensor:
         ws = self._ws.get(key)
@@ -117,7 +133,7 @@ class MatchingStage:
         if taps:
             tap_t["sim"] = torch.empty((n, self.n_cls), dtype=torch.float32, device=dev)
             tap_t["obj_feats"] = torch.empty((n, c), dtype=torch.float32, device=dev)
-        ws_bytes = self.lib.nttt_match_workspace_bytes(n, lh, lw, eh, ew, c, self.n_cls, oh, ow, max_sel)
+        ws_bytes = self.lib.nttt_match_workspace_bytes_neg(n, lh, lw, eh, ew, c, self.n_cls, oh, ow, max_sel, self.l_neg)
         ws = self._workspace(("match", slot), ws_bytes)
         a = _lib.MatchArgs()
         a.logits, a.pred_ious, a.tar_feat, a.proto = (lr_masks.data_ptr(), pred_ious.data_ptr(), tar_feat.data_ptr(),
@@ -132,6 +148,8 @@ class MatchingStage:
         a.sim = tap_t["sim"].data_ptr() if taps else None
         a.obj_feats = tap_t["obj_feats"].data_ptr() if taps else None
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        a.proto_neg = self.proto_neg.data_ptr() if self.proto_neg is not None else None
+        a.l_neg, a.sigma = self.l_neg, float(self.cfg.neg_sigma)
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(self.lib.nttt_match_image(self.ctx, ctypes.byref(a), stream), "nttt_match_image")
         return PendingResult(self, masks.view(torch.bool), boxes, scores, labels, index, counts, tap_t, (oh, ow),

@@ -61,9 +61,6 @@ class Sam2MatchingBaselineNoAMG(nn.Module):
         self.n_pca_components = sam2_infer_cfgs.get("n_pca_components")
         self.cls_num_per_mask = sam2_infer_cfgs.get("cls_num_per_mask")
         self.with_negative_refs = sam2_infer_cfgs.get("with_negative_refs", False)
-        if self.with_negative_refs:
-            # negative-reference scoring is a "next" row, not built yet
-            raise NotImplementedError("with_negative_refs=True is not supported by the B200 matching stage yet")
 
         if device is None:
             if not torch.cuda.is_available():
@@ -87,7 +84,12 @@ class Sam2MatchingBaselineNoAMG(nn.Module):
         memory_bank_cfg["feat_shape"] = (self.encoder_h * self.encoder_w, self.encoder_dim)
         self.model_cfg_memory = copy.deepcopy(memory_bank_cfg)
         self.memory_bank = MemoryBank(memory_bank_cfg, self.kmeans_k, self.n_pca_components).to(self._device)
-        self.memory_bank_neg = None
+        if self.with_negative_refs:  # (:225-230)
+            neg_cfg = copy.deepcopy(memory_bank_cfg)
+            neg_cfg["length"] = memory_bank_cfg.get("length_negative")
+            self.memory_bank_neg = MemoryBank(neg_cfg, self.kmeans_k, self.n_pca_components).to(self._device)
+        else:
+            self.memory_bank_neg = None
 
         k = self.cls_num_per_mask
         if k == -1 and self.memory_bank.n_classes == 1:
@@ -127,36 +129,45 @@ class Sam2MatchingBaselineNoAMG(nn.Module):
         """(:435-487) one reference shot: encoder forward, then pooled into its (class, slot)."""
         with torch.inference_mode():
             assert len(input_dicts) == 1
-            assert is_positive
+            target_bank = self.memory_bank if is_positive else self.memory_bank_neg
             refs = input_dicts[0]["refs_by_cat"]
             cat_ind = list(refs.keys())[0]
             imgs = refs[cat_ind]["imgs"].to(device=self._device)
             masks = refs[cat_ind]["masks"].to(dtype=imgs.dtype)
             imgs = F.interpolate(imgs, size=(self.encoder_img_size, self.encoder_img_size), mode="bicubic")
             feats = self._forward_encoder(_normalize(imgs)).reshape(1, -1, self.encoder_dim)
-            self.memory_bank.fill(int(cat_ind), feats[0].float(), masks[0], (self.encoder_h, self.encoder_w))
+            target_bank.fill(int(cat_ind), feats[0].float(), masks[0], (self.encoder_h, self.encoder_w))
             return {}
 
     def postprocess_memory(self):
         """(:700-704)"""
         self.memory_bank.postprocess()
 
-    def _ensure_prototypes(self):
-        ver = self.memory_bank.feats_ins_avg._version
-        if self._proto_version != ver:
-            self.stage.set_prototypes(self.memory_bank.feats_ins_avg)
-            self._proto_version = ver
+    def postprocess_memory_negative(self):
+        """(:706-710)"""
+        self.memory_bank_neg.postprocess()
+
+    def _ensure_prototypes(self, with_negative):
+        if with_negative:
+            ver = ("neg", self.memory_bank.feats_avg._version, self.memory_bank_neg.feats_ins_avg._version)
+            if self._proto_version != ver:
+                self.stage.set_prototypes_with_negatives(self.memory_bank.feats_avg, self.memory_bank_neg.feats_ins_avg)
+                self._proto_version = ver
+        else:
+            ver = ("pos", self.memory_bank.feats_ins_avg._version)
+            if self._proto_version != ver:
+                self.stage.set_prototypes(self.memory_bank.feats_ins_avg)
+                self._proto_version = ver
 
     def forward_test(self, input_dicts, with_negative=False):
         """(:562-698) encoders as-is, then the whole matching stage in one `nttt_match_image` call."""
         assert len(input_dicts) == 1
-        assert not with_negative
         device = self._device
         with torch.inference_mode():
             tar_feat, tar_img = self._extract_target_features(input_dicts[0]["target_img"], device)
             lr_masks, pred_ious, _ = self._forward_sam(_normalize(tar_img.unsqueeze(0)))
             info = input_dicts[0]["target_img_info"]
-            self._ensure_prototypes()
+            self._ensure_prototypes(with_negative)
             out = self.stage.match(lr_masks.float().contiguous(), pred_ious.float().contiguous().reshape(-1),
                                    tar_feat.float().contiguous(), (info["ori_height"], info["ori_width"]))
         self._reset()
@@ -168,17 +179,33 @@ class Sam2MatchingBaselineNoAMG(nn.Module):
         data_mode = input_dicts[0].pop("data_mode", None)
         assert data_mode is not None
         assert not self.training
+        def ready(bank, what):
+            if not bank.ready:
+                if bank.postprocessed[0].item():
+                    bank.ready = True
+                else:
+                    raise RuntimeError(what)
+
         if data_mode == "fill_memory":
             return self.forward_fill_memory(input_dicts, is_positive=True)
+        if data_mode == "fill_memory_neg":
+            assert self.with_negative_refs
+            assert not self.memory_bank_neg.postprocessed[0].item()
+            return self.forward_fill_memory(input_dicts, is_positive=False)
         if data_mode == "test":
-            if not self.memory_bank.ready:
-                if self.memory_bank.postprocessed[0].item():
-                    self.memory_bank.ready = True
-                else:
-                    raise RuntimeError("Memory is not ready!")
+            ready(self.memory_bank, "Memory is not ready!")
+            if self.with_negative_refs:
+                ready(self.memory_bank_neg, "Negative memory is not ready!")
+                return self.forward_test(input_dicts, with_negative=True)
             return self.forward_test(input_dicts, with_negative=False)
-        if data_mode in ("fill_memory_neg", "test_support", "vis_memory"):
-            raise NotImplementedError(f"data mode {data_mode} is outside the B200 hot-path scope (SURVEY.md §8f)")
+        if data_mode == "test_support":
+            assert self.with_negative_refs
+            ready(self.memory_bank, "Memory is not ready!")
+            assert not self.memory_bank_neg.ready
+            assert not self.memory_bank_neg.postprocessed[0].item()
+            return self.forward_test(input_dicts, with_negative=False)
+        if data_mode == "vis_memory":
+            raise NotImplementedError("vis_memory is visualisation, outside the B200 hot-path scope (SURVEY.md §2)")
         raise NotImplementedError(f"Unrecognized data mode during inference: {data_mode}")
 
 

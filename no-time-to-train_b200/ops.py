@@ -122,6 +122,27 @@ def similarity_top1(obj_feats: torch.Tensor, proto: torch.Tensor, want_sim: bool
     return sim, top_score, top_label
 
 
+def similarity_neg_top1(obj_feats: torch.Tensor, proto_pos: torch.Tensor, proto_neg: torch.Tensor, l_neg: int,
+                        sigma: float = 0.8):
+    """Negative-reference scoring: proto_pos [n_cls, c], proto_neg [n_cls*l_neg, c], all unit rows."""
+    _need(obj_feats, torch.float32, "obj_feats")
+    _need(proto_pos, torch.float32, "proto_pos")
+    _need(proto_neg, torch.float32, "proto_neg")
+    n, c = obj_feats.shape
+    n_cls = proto_pos.shape[0]
+    dev = obj_feats.device
+    lib = _lib.load()
+    sim = torch.empty((n, n_cls), dtype=torch.float32, device=dev)
+    ws_bytes = lib.nttt_similarity_neg_workspace_bytes(n, c, n_cls, l_neg)
+    ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
+    top_score = torch.empty((n,), dtype=torch.float32, device=dev)
+    top_label = torch.empty((n,), dtype=torch.int32, device=dev)
+    _lib.check(lib.nttt_similarity_neg_top1(context(dev), _ptr(obj_feats), _ptr(proto_pos), _ptr(proto_neg), n, c, n_cls,
+                                            l_neg, sigma, _ptr(sim), _ptr(top_score), _ptr(top_label), _ptr(ws),
+                                            ws_bytes, _stream(dev)), "nttt_similarity_neg_top1")
+    return sim, top_score, top_label
+
+
 def box_nms(box: torch.Tensor, nms_scores: torch.Tensor, labels: torch.Tensor, top_score: torch.Tensor,
             iou_thr: float, max_keep: int):
     """-> keep [max_keep] i32, sel [max_keep] i32, counts [2] i32 = (n_keep, n_sel); all on device."""

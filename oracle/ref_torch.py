@@ -60,6 +60,21 @@ def pool_and_score(feat_pc: torch.Tensor, masks_bool: torch.Tensor, feats_ins_av
     return sim / 1.0, pooled
 
 
+def pool_and_score_neg(feat_pc, masks_bool, feats_avg, feats_ins_avg_neg, sigma=0.8):
+    """`compute_sim_global_avg_with_neg` (`matching_baseline_utils.py:906-941`) + the obj_feats the caller
+    recomputes (`Sam2MatchingBaseline_noAMG.py:597-600`).  No zero guard on the area here: empty masks give NaN."""
+    n = masks_bool.shape[0]
+    n_cls, c = feats_avg.shape
+    m = masks_bool.to(feat_pc.dtype)
+    pooled = F.normalize((m @ feat_pc) / m.sum(dim=-1, keepdim=True), p=2, dim=-1)
+    pos = F.normalize(feats_avg, p=2, dim=-1)
+    neg = F.normalize(feats_ins_avg_neg, p=2, dim=-1).reshape(-1, c)
+    sim_pos = (pooled @ pos.t()).clamp(min=0.0)
+    sim_neg = (pooled @ neg.t()).clamp(min=0.0).reshape(n, n_cls, -1).max(dim=-1).values
+    sim = sim_pos * torch.exp(-1.0 * (sim_neg - sim_pos).clamp(min=0.0) / sigma)
+    return sim, pooled
+
+
 def select_labels(sim: torch.Tensor, k: int):
     """top-k / label section (`Sam2MatchingBaseline_noAMG.py:602-612`)."""
     n_cls = sim.shape[1]
@@ -126,7 +141,7 @@ def semantic_ios(masks_bool: torch.Tensor, labels: torch.Tensor, obj_sim: torch.
 
 
 def match_image(lr_masks, pred_ious, tar_feat, feats_ins_avg, cfg: StageConfig, ori_hw, timings=None,
-                override=None):
+                override=None, negative=None):
     """The matching stage of `forward_test(with_negative=False)`
     (`Sam2MatchingBaseline_noAMG.py:582-683`), from the `_forward_sam` seam to the output dict.
 
@@ -143,11 +158,15 @@ def match_image(lr_masks, pred_ious, tar_feat, feats_ins_avg, cfg: StageConfig, 
 
     t = time.perf_counter()
     device = lr_masks.device
-    n_cls = feats_ins_avg.shape[0]
+    n_cls = feats_ins_avg.shape[0] if negative is None else negative["feats_avg"].shape[0]
     masks_bool = threshold_lowres(lr_masks)
     feat_pc = upsample_features(tar_feat, cfg.enc_hw, lr_masks.shape[-2:])
     t = lap("process_sam_masks", t)
-    sim, obj_feats = pool_and_score(feat_pc, masks_bool, feats_ins_avg)
+    if negative is not None:  # dict(feats_avg=..., feats_ins_avg_neg=..., sigma=0.8): with_negative=True path
+        sim, obj_feats = pool_and_score_neg(feat_pc, masks_bool, negative["feats_avg"], negative["feats_ins_avg_neg"],
+                                            negative.get("sigma", 0.8))
+    else:
+        sim, obj_feats = pool_and_score(feat_pc, masks_bool, feats_ins_avg)
     if override is not None:
         sim, obj_feats = override["sim"], override["obj_feats"]
     t = lap("pool_and_score", t)

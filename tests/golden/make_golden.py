@@ -44,6 +44,12 @@ STAGE_CASES = {
     "stage_g_iid_80cls": (128, 256, 80, 10, (512, 512), 107, True, 100, False),
 }
 
+# negative-reference cases: name -> (n, c, n_cls, shots_neg, ori_hw, seed, num_out)
+NEG_CASES = {
+    "stageneg_a_5cls_3neg": (64, 384, 5, 3, (480, 640), 301, 10),
+    "stageneg_b_20cls_2neg": (96, 256, 20, 2, (512, 512), 302, 20),
+}
+
 # name -> (n_cls, shots, filled_per_class, c, seed)
 FILL_CASES = {
     "fill_a_3cls_2shot": (3, 2, [2, 2, 1], 32, 201),
@@ -137,6 +143,54 @@ def run_stage_case(ref, name, spec):
           f"nan_scores={int(torch.isnan(out['scores']).sum())} labels_used={len(set(out['labels'].tolist()))}")
 
 
+def run_neg_case(ref, name, spec):
+    """forward_test(with_negative=True): needs memory_bank.feats_avg and memory_bank_neg.feats_ins_avg."""
+    n, c, n_cls, l_neg, ori_hw, seed, num_out = spec
+    inp = synth.make_stage_inputs(n, c, n_cls, 2, ori_hw, seed=seed, clustered=True, degenerate=False)
+    gen = torch.Generator().manual_seed(seed + 7)
+    feats_avg = inp.feats_ins_avg.mean(dim=1) * 3.0  # un-normalised class averages
+    neg = inp.feats_ins_avg[:, :1].repeat(1, l_neg, 1) * 0.5 + 0.6 * torch.randn(n_cls, l_neg, c, generator=gen) / (c ** 0.5)
+    model_mod = sys.modules[ref.Model.__module__]
+    cap = {}
+    orig = model_mod.compute_sim_global_avg_with_neg
+
+    def rec(*a, **k):
+        out = orig(*a, **k)
+        cap["sim"] = out.clone()
+        return out
+    model_mod.compute_sim_global_avg_with_neg = rec
+    try:
+        fake = types.SimpleNamespace()
+        fake.predictor = types.SimpleNamespace(device=torch.device("cpu"))
+        fake.encoder_h, fake.encoder_w = 37, 37
+        fake.cls_num_per_mask = 1
+        fake.num_out_instance = num_out
+        fake.nms_thr = 0.5
+        fake.online_vis = False
+        fake.memory_bank = types.SimpleNamespace(feats_avg=feats_avg, feats_ins_avg=inp.feats_ins_avg, n_classes=n_cls)
+        fake.memory_bank_neg = types.SimpleNamespace(feats_ins_avg=neg)
+        fake.sam_transform = lambda x: x
+        fake._extract_target_features = lambda img, device: (inp.tar_feat, img)
+        fake._forward_sam = lambda imgs: (inp.lr_masks, inp.pred_ious, None)
+        fake._process_sam_masks = types.MethodType(ref.Model._process_sam_masks, fake)
+        fake._reset = lambda: None
+        info = dict(ori_height=ori_hw[0], ori_width=ori_hw[1], file_name="synthetic", id=0)
+        with torch.inference_mode():
+            out = ref.Model.forward_test(fake, [dict(target_img=torch.zeros(3, 8, 8), target_img_info=info)], True)[0]
+    finally:
+        model_mod.compute_sim_global_avg_with_neg = orig
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"),
+        spec=np.array([n, c, n_cls, l_neg, ori_hw[0], ori_hw[1], seed, num_out], dtype=np.int64),
+        feats_avg=feats_avg.numpy(), feats_ins_avg_neg=neg.numpy(),
+        inputs_sha=np.array(sha(inp.lr_masks, inp.pred_ious, inp.tar_feat, inp.feats_ins_avg)),
+        sim=cap["sim"].numpy(), out_scores=out["scores"].numpy(), out_labels=out["labels"].numpy(),
+        out_bboxes=out["bboxes"].numpy(),
+        out_masks_packed=np.packbits(out["binary_masks"].numpy().reshape(out["binary_masks"].shape[0], -1), axis=-1))
+    print(f"{name}: K_out={out['scores'].shape[0]} labels_used={len(set(out['labels'].tolist()))} "
+          f"sim range [{float(cap['sim'].min()):.3f}, {float(cap['sim'].max()):.3f}]")
+
+
 def run_fill_case(ref, name, spec):
     n_cls, shots, filled, c, seed = spec
     e_side, img_side = 37, 74
@@ -198,6 +252,9 @@ def main():
     for name, spec in FILL_CASES.items():
         if not only or name in only:
             run_fill_case(ref, name, spec)
+    for name, spec in NEG_CASES.items():
+        if not only or name in only:
+            run_neg_case(ref, name, spec)
 
 
 if __name__ == "__main__":
