@@ -139,7 +139,3 @@ def test_model_rejects_unsupported_modes_without_gpu():
         pkg.Sam2MatchingBaselineNoAMG(sam2_infer_cfgs=dict(nms_thr=0.5, num_out_instance=10, cls_num_per_mask=1),
                                       memory_bank_cfg=dict(enable=True, category_num=2, length=1),
                                       encoder_geometry=(518, 14, 8))
-    with pytest.raises(NotImplementedError):
-        pkg.Sam2MatchingBaselineNoAMG(sam2_infer_cfgs=dict(with_negative_refs=True),
-                                      memory_bank_cfg=dict(enable=True, category_num=2, length=1),
-                                      encoder_geometry=(518, 14, 8))
