@@ -221,6 +221,12 @@ typedef struct nttt_match_args {
   const float* proto_neg;
   int32_t l_neg;
   float sigma;
+  /* fused candidate filter (Sam2MatchingBaseline_noAMG.py:428-431, `inds = scores_all > iou_thr`): when
+   * filter_iou != 0, masks with !(pred_ious[i] > iou_thr) are ignored exactly as if they had been removed before the
+   * stage — their logits are never read — so `logits` can be the decoder's full, un-compacted output and `n` a
+   * fixed capacity (static shapes: the whole call can be captured in a CUDA graph). */
+  float iou_thr;
+  int32_t filter_iou;
 } nttt_match_args;
 
 size_t nttt_match_workspace_bytes(int n, int lr_h, int lr_w, int eh, int ew, int c, int n_cls, int ori_h,

@@ -9,7 +9,7 @@ namespace nttt {
 
 // launchers implemented in the kernel translation units
 int launch_lowres_pack(const float*, int, int, int, float, float, uint32_t*, int32_t*, int32_t*, int32_t*, int32_t*,
-                       cudaStream_t);
+                       const float*, float, cudaStream_t);
 int launch_project_masks(const AxisTable&, const AxisTable&, const uint32_t*, const int32_t*, int, int, int, int, int,
                          void*, int, bool, cudaStream_t);
 int launch_normalize_split(const float*, const int32_t*, int, int, int, float*, void*, cudaStream_t);
@@ -24,7 +24,7 @@ int launch_neg_top1(const float*, int, size_t, const float*, int, size_t, int, i
                     cudaStream_t);
 size_t nms_workspace_bytes(int n);
 int launch_box_nms(const int32_t*, const float*, const int32_t*, const float*, int, float, int, int32_t*, int32_t*,
-                   int32_t*, int32_t*, void*, size_t, cudaStream_t);
+                   int32_t*, int32_t*, void*, size_t, float, int, cudaStream_t);
 int launch_upsample_pack(const AxisTable&, const AxisTable&, const float*, const uint32_t*, const int32_t*,
                          const int32_t*, int, int, const int32_t*, const int32_t*, int, int, int, uint32_t*, int32_t*,
                          int32_t*, int32_t*, int32_t*, cudaStream_t);
@@ -254,7 +254,8 @@ int nttt_threshold_pack(const float* logits, int n, int h, int w, float thr, flo
                         int32_t* box, int32_t* stab, int32_t* flags, void* stream) {
   if (n < 0 || h <= 0 || w <= 0) return NTTT_EINVAL;
   if (n > 0 && (!logits || !bits || !area || !box || !flags)) return NTTT_EINVAL;  // stab may be NULL
-  return launch_lowres_pack(logits, n, h, w, thr, off, bits, area, box, stab, flags, (cudaStream_t)stream);
+  return launch_lowres_pack(logits, n, h, w, thr, off, bits, area, box, stab, flags, nullptr, 0.0f,
+                            (cudaStream_t)stream);
 }
 
 int nttt_project_masks(nttt_ctx* ctx, const uint32_t* bits, const int32_t* box, int n, int h, int w, int eh, int ew,
@@ -355,7 +356,7 @@ int nttt_box_nms(const int32_t* box, const float* nms_scores, const int32_t* lab
   if (n < 0 || !keep || !n_keep || !sel || !n_sel) return NTTT_EINVAL;
   if (n > 0 && (!box || !nms_scores || !labels || !top_score || !workspace)) return NTTT_EINVAL;
   return launch_box_nms(box, nms_scores, labels, top_score, n, iou_thr, max_keep, keep, n_keep, sel, n_sel, workspace,
-                        workspace_bytes, (cudaStream_t)stream);
+                        workspace_bytes, 0.0f, 0, (cudaStream_t)stream);
 }
 
 // scratch for the cross-CTA per-mask statistics of the stand-alone resize entry is owned by the ctx
@@ -561,7 +562,7 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   // a6/a9/a15: one pass over the logits
   // (the stability counts of a15 are not read on this path, so the pipeline does not pay for them)
   NTTT_STEP(launch_lowres_pack(a->logits, n, a->lr_h, a->lr_w, 0.0f, 1.0f, L.bits_lr, L.area_lr, L.box_lr, nullptr,
-                               L.flags, s));
+                               L.flags, a->filter_iou ? a->pred_ious : nullptr, a->iou_thr, s));
   // a6/a7: projection + pooling contraction + normalisation
   if (!projection_supported(a->ew, a->lr_w) || !projection_supported(a->eh, a->lr_h)) return NTTT_EUNSUPPORTED;
   NTTT_STEP(launch_project_masks(px, py, L.bits_lr, L.box_lr, n, a->lr_h, a->lr_w, a->eh, a->ew, L.a_split, pad64(e),
@@ -574,7 +575,7 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
                      L.sim_part_neg, L.top_score, L.top_label, L.a_split, L.b_split, a_ready, ctx->sm_count, s));
   // a10/a11
   NTTT_STEP(launch_box_nms(L.box_lr, a->pred_ious, L.top_label, L.top_score, n, a->nms_thr, max_sel, L.keep,
-                           a->counts + 0, L.sel, a->counts + 1, L.nms_ws, L.nms_ws_bytes, s));
+                           a->counts + 0, L.sel, a->counts + 1, L.nms_ws, L.nms_ws_bytes, a->iou_thr, a->filter_iou, s));
   // a12/a9
   NTTT_STEP(launch_upsample_pack(ux, uy, a->logits, L.bits_lr, L.box_lr, L.flags, a->lr_h, a->lr_w, L.sel,
                                  a->counts + 1, max_sel, a->ori_h, a->ori_w, L.bits_full, L.rect, L.area_full,

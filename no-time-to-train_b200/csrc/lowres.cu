@@ -63,8 +63,22 @@ template <bool kStab>
 __global__ void __launch_bounds__(kPackBlock, 3)
 lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mask */, int words_per_row,
                    float thr_hi, float thr_lo, uint32_t* __restrict__ bits, int32_t* __restrict__ area,
-                   int32_t* __restrict__ box, int32_t* __restrict__ stab, int32_t* __restrict__ flags) {
+                   int32_t* __restrict__ box, int32_t* __restrict__ stab, int32_t* __restrict__ flags,
+                   const float* __restrict__ gate, float gate_min) {
   extern __shared__ __align__(128) unsigned char s_raw[];
+  if (gate && !(gate[blockIdx.x] > gate_min)) {
+    // filtered-out candidate (pred_iou <= iou_thr): its logits are never read; publish an empty mask
+    const int nw = p4 >> 3;
+    uint4* d4 = reinterpret_cast<uint4*>(bits + (size_t)blockIdx.x * nw);
+    for (int i = threadIdx.x; i < (nw >> 2); i += kPackBlock) d4[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+      area[blockIdx.x] = 0;
+      if (kStab) { stab[2 * blockIdx.x] = 0; stab[2 * blockIdx.x + 1] = 0; }
+      flags[blockIdx.x] = 1;
+      reinterpret_cast<int4*>(box)[blockIdx.x] = make_int4(0, 0, 0, 0);
+    }
+    return;
+  }
   float4* s_stage = reinterpret_cast<float4*>(s_raw);                                        // ring
   uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_raw + (size_t)kPackStages * kPackStageBytes);  // p4/8 words
   __shared__ uint64_t s_full[kPackStages], s_empty[kPackStages];
@@ -172,8 +186,10 @@ lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mas
 }
 
 // stab may be NULL: the stability counts (sam2/utils/amg.py:158-178) are not read on the noAMG path
+// gate (nullable): per-mask score; masks with !(gate[n] > gate_min) are skipped and published as empty
 int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits,
-                       int32_t* area, int32_t* box, int32_t* stab, int32_t* flags, cudaStream_t s) {
+                       int32_t* area, int32_t* box, int32_t* stab, int32_t* flags, const float* gate, float gate_min,
+                       cudaStream_t s) {
   const long p = (long)h * w;
   if (n <= 0) return NTTT_OK;
   if (w % 32 != 0 || p % 128 != 0 || p / 32 * 4 > 32 * 1024) return NTTT_EUNSUPPORTED;
@@ -183,11 +199,11 @@ int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, floa
   if (stab) {
     NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lowres_pack_kernel<true><<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area, box,
-                                                        stab, flags);
+                                                        stab, flags, gate, gate_min);
   } else {
     NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lowres_pack_kernel<false><<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area,
-                                                         box, stab, flags);
+                                                         box, stab, flags, gate, gate_min);
   }
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;

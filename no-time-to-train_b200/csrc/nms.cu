@@ -22,24 +22,34 @@ __device__ __forceinline__ uint32_t desc_key(float f) {
 template <bool kReg>
 __global__ void __launch_bounds__(1024)
 nms_sort_kernel(const float* __restrict__ scores, const int32_t* __restrict__ box, const int32_t* __restrict__ labels,
-                int n, int n_pad, int32_t* __restrict__ order, float4* __restrict__ sorted_box,
-                int32_t* __restrict__ sorted_label) {
+                int n, int n_pad, float min_score, int filter, int32_t* __restrict__ order,
+                float4* __restrict__ sorted_box, int32_t* __restrict__ sorted_label) {
   extern __shared__ unsigned long long s_keys[];
+  // filter: boxes whose score is not > min_score are not candidates at all (the reference drops them before the
+  // stage, Sam2MatchingBaseline_noAMG.py:428-431): they sort last, get a unique negative label so that they never
+  // match anything in the matrix, and the scan starts with them removed.
+  auto make_key = [&](int i) -> unsigned long long {
+    if (i >= n) return ~0ull;
+    const float sc = scores[i];
+    const uint32_t hi = (filter && !(sc > min_score)) ? 0xffffffffu : desc_key(sc);
+    return ((unsigned long long)hi << 32) | (uint32_t)i;
+  };
+  auto emit = [&](int i, unsigned long long key) {
+    const int o = (int)(key & 0xffffffffu);
+    order[i] = o;
+    const int4 bi = reinterpret_cast<const int4*>(box)[o];
+    sorted_box[i] = make_float4((float)bi.x, (float)bi.y, (float)bi.z, (float)bi.w);
+    sorted_label[i] = ((uint32_t)(key >> 32) == 0xffffffffu && filter) ? (-2 - i) : labels[o];
+  };
   if (kReg) {
     const int i = threadIdx.x;
-    unsigned long long key = i < n ? (((unsigned long long)desc_key(scores[i]) << 32) | (uint32_t)i) : ~0ull;
+    unsigned long long key = make_key(i);
     key = block_bitonic_sort_1024(key, s_keys);
-    if (i < n) {
-      const int o = (int)(key & 0xffffffffu);
-      order[i] = o;
-      const int4 bi = reinterpret_cast<const int4*>(box)[o];
-      sorted_box[i] = make_float4((float)bi.x, (float)bi.y, (float)bi.z, (float)bi.w);
-      sorted_label[i] = labels[o];
-    }
+    if (i < n) emit(i, key);
     return;
   }
   for (int i = threadIdx.x; i < n_pad; i += blockDim.x)
-    s_keys[i] = i < n ? (((unsigned long long)desc_key(scores[i]) << 32) | (uint32_t)i) : ~0ull;
+    s_keys[i] = make_key(i);
   __syncthreads();
   for (int k = 2; k <= n_pad; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -54,13 +64,7 @@ nms_sort_kernel(const float* __restrict__ scores, const int32_t* __restrict__ bo
       __syncthreads();
     }
   }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int o = (int)(s_keys[i] & 0xffffffffu);
-    order[i] = o;
-    const int4 bi = reinterpret_cast<const int4*>(box)[o];
-    sorted_box[i] = make_float4((float)bi.x, (float)bi.y, (float)bi.z, (float)bi.w);
-    sorted_label[i] = labels[o];
-  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) emit(i, s_keys[i]);
 }
 
 // suppression bit matrix in sorted order: bit j of row i set iff j > i, same label, IoU(i,j) > thr
@@ -109,7 +113,8 @@ constexpr int kScanMaxN = 8192;
 template <bool kStaged>
 __global__ void __launch_bounds__(kScanThreads)
 nms_scan_kernel(const uint32_t* __restrict__ mask, int row_words, const int32_t* __restrict__ order,
-                const float* __restrict__ top_score, int n, int max_keep, int32_t* __restrict__ keep,
+                const int32_t* __restrict__ sorted_label, const float* __restrict__ top_score, int n, int max_keep,
+                int32_t* __restrict__ keep,
                 int32_t* __restrict__ n_keep, int32_t* __restrict__ sel, int32_t* __restrict__ n_sel) {
   extern __shared__ uint32_t s_dyn[];
   __shared__ uint32_t s_removed[kScanMaxN / 32];
@@ -123,12 +128,13 @@ nms_scan_kernel(const uint32_t* __restrict__ mask, int row_words, const int32_t*
     for (int i = threadIdx.x; i < total; i += kScanThreads) s_dyn[i] = mask[i];
     M = s_dyn;
   }
-  for (int i = threadIdx.x; i < row_words; i += kScanThreads) s_removed[i] = 0;
-  for (int base = 0; base < row_words * 32; base += kScanThreads) {  // positive-score flags, one ballot per warp
-    const int i = base + threadIdx.x;
+  for (int base = 0; base < row_words * 32; base += kScanThreads) {  // per sorted box, one ballot per warp:
+    const int i = base + threadIdx.x;                               // positive-score flag, filtered-out flag
     const bool pos = i < n && top_score[order[i]] > 0.0f;
+    const bool gone = i < n && sorted_label[i] < -1;
     const uint32_t bits = __ballot_sync(kFull, pos);
-    if (lane == 0 && (i >> 5) < row_words) s_posbits[i >> 5] = bits;
+    const uint32_t gbits = __ballot_sync(kFull, gone);
+    if (lane == 0 && (i >> 5) < row_words) { s_posbits[i >> 5] = bits; s_removed[i >> 5] = gbits; }
   }
   if (threadIdx.x == 0) s_stop = 0;
   __syncthreads();
@@ -188,7 +194,7 @@ size_t nms_workspace_bytes(int n) {
 
 int launch_box_nms(const int32_t* box, const float* nms_scores, const int32_t* labels, const float* top_score, int n,
                    float thr, int max_keep, int32_t* keep, int32_t* n_keep, int32_t* sel, int32_t* n_sel, void* ws,
-                   size_t ws_bytes, cudaStream_t s) {
+                   size_t ws_bytes, float min_score, int filter, cudaStream_t s) {
   if (n <= 0 || max_keep <= 0) {
     NTTT_CUDA(cudaMemsetAsync(n_keep, 0, sizeof(int32_t), s));
     NTTT_CUDA(cudaMemsetAsync(n_sel, 0, sizeof(int32_t), s));
@@ -207,13 +213,14 @@ int launch_box_nms(const int32_t* box, const float* nms_scores, const int32_t* l
   int n_pad = 1;
   while (n_pad < n) n_pad <<= 1;
   if (n_pad <= 1024) {
-    nms_sort_kernel<true><<<1, 1024, sizeof(unsigned long long) * 1024, s>>>(nms_scores, box, labels, n, 1024, order,
+    nms_sort_kernel<true><<<1, 1024, sizeof(unsigned long long) * 1024, s>>>(nms_scores, box, labels, n, 1024, min_score, filter, order,
                                                                              sorted_box, sorted_label);
   } else {
     const size_t smem = sizeof(unsigned long long) * (size_t)n_pad;
     if (smem > 48 * 1024)
       NTTT_CUDA(cudaFuncSetAttribute(nms_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_sort_kernel<false><<<1, 1024, smem, s>>>(nms_scores, box, labels, n, n_pad, order, sorted_box, sorted_label);
+    nms_sort_kernel<false><<<1, 1024, smem, s>>>(nms_scores, box, labels, n, n_pad, min_score, filter, order, sorted_box,
+                                                 sorted_label);
   }
   NTTT_LAUNCH_CHECK();
   dim3 grid(ceil_div(row_words, 8), ceil_div(n, 32));
@@ -223,10 +230,10 @@ int launch_box_nms(const int32_t* box, const float* nms_scores, const int32_t* l
   if (stage_bytes <= 160 * 1024) {
     NTTT_CUDA(cudaFuncSetAttribute(nms_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)stage_bytes));
-    nms_scan_kernel<true><<<1, kScanThreads, stage_bytes, s>>>(mask, row_words, order, top_score, n, max_keep, keep,
+    nms_scan_kernel<true><<<1, kScanThreads, stage_bytes, s>>>(mask, row_words, order, sorted_label, top_score, n, max_keep, keep,
                                                               n_keep, sel, n_sel);
   } else {
-    nms_scan_kernel<false><<<1, kScanThreads, 0, s>>>(mask, row_words, order, top_score, n, max_keep, keep, n_keep,
+    nms_scan_kernel<false><<<1, kScanThreads, 0, s>>>(mask, row_words, order, sorted_label, top_score, n, max_keep, keep, n_keep,
                                                       sel, n_sel);
   }
   NTTT_LAUNCH_CHECK();

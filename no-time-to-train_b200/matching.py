@@ -104,10 +104,11 @@ class MatchingStage:
         return ws
 
     def match_async(self, lr_masks: torch.Tensor, pred_ious: torch.Tensor, tar_feat: torch.Tensor, ori_hw,
-                    taps: bool = False, slot: int = 0) -> PendingResult:
+                    taps: bool = False, slot=0, iou_thr=None) -> PendingResult:
         """Enqueue the whole stage for one image on the current stream.  `slot` selects which reusable
         workspace to use (callers that keep several images in flight on different streams use one slot per
-        stream)."""
+        stream).  `iou_thr`, if given, fuses the reference's candidate filter (`scores_all > iou_thr`,
+        `Sam2MatchingBaseline_noAMG.py:428-431`): pass the decoder's full un-compacted masks and scores."""
         if self.proto is None:
             raise RuntimeError("Memory is not ready!")  # same text as Sam2MatchingBaseline_noAMG.py:752
         ops._need(lr_masks, torch.float32, "lr_masks")
@@ -150,6 +151,7 @@ class MatchingStage:
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         a.proto_neg = self.proto_neg.data_ptr() if self.proto_neg is not None else None
         a.l_neg, a.sigma = self.l_neg, float(self.cfg.neg_sigma)
+        a.iou_thr, a.filter_iou = (float(iou_thr), 1) if iou_thr is not None else (0.0, 0)
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(self.lib.nttt_match_image(self.ctx, ctypes.byref(a), stream), "nttt_match_image")
         return PendingResult(self, masks.view(torch.bool), boxes, scores, labels, index, counts, tap_t, (oh, ow),
@@ -168,5 +170,54 @@ class MatchingStage:
             _lib.check(got, "nttt_ctx_profile_read")
         return {self.lib.nttt_profile_stage_name(i).decode(): float(buf[i]) for i in range(got)}
 
-    def match(self, lr_masks, pred_ious, tar_feat, ori_hw, taps: bool = False) -> dict:
-        return self.match_async(lr_masks, pred_ious, tar_feat, ori_hw, taps=taps).get()
+    def match(self, lr_masks, pred_ious, tar_feat, ori_hw, taps: bool = False, iou_thr=None) -> dict:
+        return self.match_async(lr_masks, pred_ious, tar_feat, ori_hw, taps=taps, iou_thr=iou_thr).get()
+
+    def graphed(self, n: int, c: int, ori_hw, iou_thr=None, key=None) -> "GraphedMatch":
+        """A CUDA-graph capture of the whole stage at fixed shapes with static input/output buffers."""
+        return GraphedMatch(self, n, c, ori_hw, iou_thr, key)
+
+
+class GraphedMatch:
+    """The stage of one image captured once into a CUDA graph and replayed with one launch.
+
+    Shapes are static: `n` is a fixed capacity (e.g. points_per_side**2) and the fused `iou_thr` filter takes the
+    place of the reference's compaction, so the producer writes the decoder's masks / scores and the encoder's
+    features straight into `self.lr_masks`, `self.pred_ious`, `self.tar_feat` (static device buffers) and calls
+    `replay()`.  Outputs live in static buffers too: consume a result (`.get()`) before replaying the same object
+    again.  Replay costs one graph launch on the host instead of ~18 kernel launches."""
+
+    def __init__(self, stage: MatchingStage, n: int, c: int, ori_hw, iou_thr=None, key=None):
+        dev = stage.device
+        eh, ew = stage.cfg.enc_hw
+        self.stage = stage
+        self.lr_masks = torch.zeros((n, 256, 256), dtype=torch.float32, device=dev)
+        self.pred_ious = torch.zeros((n,), dtype=torch.float32, device=dev)
+        self.tar_feat = torch.zeros((eh * ew, c), dtype=torch.float32, device=dev)
+        self.ori_hw = (int(ori_hw[0]), int(ori_hw[1]))
+        self.iou_thr = iou_thr
+        self._slot = ("graph", id(self) if key is None else key)
+        self.graph = None
+        self.pending = None
+
+    def capture(self):
+        """Warm up (workspace allocation, antialias tables) on a side stream, then capture."""
+        side = torch.cuda.Stream(self.stage.device)
+        side.wait_stream(torch.cuda.current_stream(self.stage.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.stage.match_async(self.lr_masks, self.pred_ious, self.tar_feat, self.ori_hw, slot=self._slot,
+                                       iou_thr=self.iou_thr)
+        torch.cuda.current_stream(self.stage.device).wait_stream(side)
+        torch.cuda.synchronize(self.stage.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.pending = self.stage.match_async(self.lr_masks, self.pred_ious, self.tar_feat, self.ori_hw,
+                                                  slot=self._slot, iou_thr=self.iou_thr)
+        return self
+
+    def replay(self) -> PendingResult:
+        if self.graph is None:
+            self.capture()
+        self.graph.replay()
+        return self.pending

@@ -1,0 +1,74 @@
+"""Fused candidate filter (`scores_all > iou_thr`, Sam2MatchingBaseline_noAMG.py:428-431) and CUDA-graph replay of
+the whole stage: both must give exactly what the reference gives on the compacted inputs."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import assert_same_ranking
+from oracle import ref_torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _case(n=96, c=256, n_cls=6, seed=61, ori_hw=(384, 512)):
+    P = importlib.import_module("no-time-to-train_b200")
+    inp = P.synth.make_stage_inputs(n, c, n_cls, 2, ori_hw, seed=seed, clustered=True, degenerate=True)
+    gen = torch.Generator().manual_seed(seed + 1)
+    inp.pred_ious = torch.rand(n, generator=gen)  # about 40 % fall below the 0.4 threshold
+    inp.pred_ious[5] = 0.4                        # exactly the threshold: dropped (strict >)
+    return P, inp
+
+
+def test_fused_iou_filter_equals_compaction():
+    P, inp = _case()
+    thr = 0.4
+    stage = P.MatchingStage(DEV, P.StageConfig(nms_thr=0.5, num_out_instance=12, enc_hw=(37, 37)))
+    stage.set_prototypes(inp.feats_ins_avg)
+    got = stage.match(inp.lr_masks.to(DEV), inp.pred_ious.to(DEV), inp.tar_feat.to(DEV), inp.ori_hw, iou_thr=thr)
+    keep = inp.pred_ious > thr
+    assert 10 < int(keep.sum()) < inp.lr_masks.shape[0] - 10
+    # the reference semantics: compact first, then run the stage
+    ref = ref_torch.match_image(inp.lr_masks[keep], inp.pred_ious[keep], inp.tar_feat, inp.feats_ins_avg,
+                                ref_torch.StageConfig(num_out_instance=12), inp.ori_hw)
+    assert got["counts"]["n_keep"] == ref["aux"]["keep"].numel()
+    assert got["counts"]["n_sel"] == ref["aux"]["sel_index"].numel()
+    assert_same_ranking(got["scores"].cpu().numpy(), got["labels"].cpu().numpy(), ref["scores"].numpy(),
+                        ref["labels"].numpy(), what="filtered")
+    # our indices refer to the un-compacted list
+    orig_index = torch.nonzero(keep).flatten()[ref["aux"]["sel_index"][ref["aux"]["order"]]]
+    if np.array_equal(got["labels"].cpu().numpy(), ref["labels"].numpy()):
+        assert np.array_equal(got["index"].cpu().numpy(), orig_index.numpy())
+        assert torch.equal(got["binary_masks"].cpu(), ref["binary_masks"])
+        assert torch.equal(got["bboxes"].cpu(), ref["bboxes"])
+    # and the same through the compacted call of our own stage
+    own = stage.match(inp.lr_masks[keep].contiguous().to(DEV), inp.pred_ious[keep].contiguous().to(DEV),
+                      inp.tar_feat.to(DEV), inp.ori_hw)
+    assert torch.equal(own["scores"], got["scores"]) and torch.equal(own["binary_masks"], got["binary_masks"])
+
+
+def test_filter_everything_gives_empty_result():
+    P, inp = _case(n=32)
+    stage = P.MatchingStage(DEV, P.StageConfig(nms_thr=0.5, num_out_instance=5, enc_hw=(37, 37)))
+    stage.set_prototypes(inp.feats_ins_avg)
+    got = stage.match(inp.lr_masks.to(DEV), inp.pred_ious.to(DEV), inp.tar_feat.to(DEV), inp.ori_hw, iou_thr=2.0)
+    assert got["counts"]["n_keep"] == 0 and got["binary_masks"].shape[0] == 0
+
+
+def test_graph_replay_matches_eager():
+    P, inp = _case(n=128, c=384, n_cls=9, seed=71, ori_hw=(1024, 1024))
+    stage = P.MatchingStage(DEV, P.StageConfig(nms_thr=0.5, num_out_instance=20, enc_hw=(37, 37)))
+    stage.set_prototypes(inp.feats_ins_avg)
+    g = stage.graphed(128, 384, (1024, 1024), iou_thr=0.4).capture()
+    for seed in (71, 72, 73):  # new inputs written into the static buffers, same graph
+        _, cur = _case(n=128, c=384, n_cls=9, seed=seed, ori_hw=(1024, 1024))
+        g.lr_masks.copy_(cur.lr_masks)
+        g.pred_ious.copy_(cur.pred_ious)
+        g.tar_feat.copy_(cur.tar_feat)
+        out = g.replay().get()
+        eager = stage.match(cur.lr_masks.to(DEV), cur.pred_ious.to(DEV), cur.tar_feat.to(DEV), (1024, 1024), iou_thr=0.4)
+        assert out["counts"] == eager["counts"]
+        assert torch.equal(out["scores"], eager["scores"]) and torch.equal(out["labels"], eager["labels"])
+        assert torch.equal(out["binary_masks"], eager["binary_masks"]) and torch.equal(out["bboxes"], eager["bboxes"])
