@@ -227,6 +227,11 @@ typedef struct nttt_match_args {
    * fixed capacity (static shapes: the whole call can be captured in a CUDA graph). */
   float iou_thr;
   int32_t filter_iou;
+  /* persistent outputs (nullable): out_prev_rect [num_out_instance, 4] i32, zero-initialised together with an
+   * all-zero out_masks by the caller and then passed unchanged to every call that writes the SAME out_masks buffer.
+   * The unpack then rewrites only the bounding box of each slot's previous and new rect instead of oh*ow bytes per
+   * mask; the buffer content after the call is identical to the dense unpack's. */
+  int32_t* out_prev_rect;
 } nttt_match_args;
 
 size_t nttt_match_workspace_bytes(int n, int lr_h, int lr_w, int eh, int ew, int c, int n_cls, int ori_h,

@@ -35,6 +35,7 @@ class MatchArgs(ctypes.Structure):
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("proto_neg", c_void_p), ("l_neg", c_int32), ("sigma", c_float),
         ("iou_thr", c_float), ("filter_iou", c_int32),
+        ("out_prev_rect", c_void_p),
     ]
 
 

@@ -1,6 +1,7 @@
 // C-ABI of libnttt_b200.so (see include/nttt_b200.h).  Host-side only: argument checks, workspace carving,
 // kernel launches.  No allocation per call, no device synchronisation (except one-time table builds).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -29,6 +30,8 @@ int launch_upsample_pack(const AxisTable&, const AxisTable&, const float*, const
                          const int32_t*, int, int, const int32_t*, const int32_t*, int, int, int, uint32_t*, int32_t*,
                          int32_t*, int32_t*, int32_t*, cudaStream_t);
 size_t upsample_scratch_bytes(int max_sel);
+int launch_unpack_sparse(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, uint8_t*,
+                         int32_t*, cudaStream_t);
 int launch_unpack(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, uint8_t*,
                   cudaStream_t);
 size_t ios_workspace_bytes(int max_sel);
@@ -237,6 +240,7 @@ int nttt_ctx_create(nttt_ctx** out, int device) {
   nttt_ctx* ctx = new nttt_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("NTTT_STOP_AFTER")) ctx->stop_after = atoi(e);
   *out = ctx;
   return NTTT_OK;
 }
@@ -557,7 +561,16 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   do {                                                                           \
     if (ctx->profile) { NTTT_CUDA(cudaEventRecord(ctx->ev[ctx->n_ev], s)); ++ctx->n_ev; } \
   } while (0)
-#define NTTT_STEP(call) do { err = (call); if (err) return err; NTTT_MARK(); } while (0)
+  // profiling aid: NTTT_STOP_AFTER=<k> (read once at ctx creation) ends the pipeline after its k-th stage so the
+  // marginal cost of each stage can be measured with several images in flight; unset in normal use.
+  int stage_no = 0;
+#define NTTT_STEP(call)                                        \
+  do {                                                         \
+    err = (call);                                              \
+    if (err) return err;                                       \
+    NTTT_MARK();                                               \
+    if (ctx->stop_after > 0 && ++stage_no >= ctx->stop_after) return NTTT_OK; \
+  } while (0)
   NTTT_MARK();
   // a6/a9/a15: one pass over the logits
   // (the stability counts of a15 are not read on this path, so the pipeline does not pay for them)
@@ -588,8 +601,12 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
                               L.area_full,
                               a->out_boxes, a->out_scores, a->out_labels, a->out_index, L.out_slot, a->counts + 2,
                               nullptr, s));
-  NTTT_STEP(launch_unpack(L.bits_full, L.rect, L.out_slot, a->counts + 2, num_out, a->ori_h, a->ori_w, a->out_masks,
-                          s));
+  if (a->out_prev_rect)
+    NTTT_STEP(launch_unpack_sparse(L.bits_full, L.rect, L.out_slot, a->counts + 2, num_out, a->ori_h, a->ori_w,
+                                   a->out_masks, a->out_prev_rect, s));
+  else
+    NTTT_STEP(launch_unpack(L.bits_full, L.rect, L.out_slot, a->counts + 2, num_out, a->ori_h, a->ori_w, a->out_masks,
+                            s));
 #undef NTTT_STEP
 #undef NTTT_MARK
   return NTTT_OK;

@@ -130,6 +130,7 @@ struct nttt_ctx {
   // optional per-stage CUDA-event profile of nttt_match_image (off by default)
   static constexpr int kMaxStages = 16;
   bool profile = false;
+  int stop_after = 0;  // debugging/profiling: stop nttt_match_image after this many stages (0 = run all)
   cudaEvent_t ev[kMaxStages + 1] = {};
   int n_ev = 0;
   // returns the table BY VALUE (device pointers stay valid until evicted by a later call)

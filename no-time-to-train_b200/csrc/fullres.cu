@@ -345,6 +345,61 @@ unpack_masks_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __res
   }
 }
 
+// Sparse unpack into PERSISTENT output buffers: out[j] still holds the mask the previous call wrote there, whose
+// rect is remembered in prev_rect[j] (all-zero buffers and rects initially).  Only the bounding box of the old and
+// the new rect is rewritten — old pixels outside the new rect become 0 — so a call writes ~2 x the rect area
+// instead of oh*ow bytes per mask (the dense unpack is HBM-write-bound on mostly zeros).  Every slot up to
+// max_count is visited so that slots that fall out of use are cleared.
+__global__ void __launch_bounds__(256)
+unpack_sparse_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restrict__ rect,
+                     const int32_t* __restrict__ index, const int32_t* __restrict__ count, int max_count, int oh, int ow,
+                     uint8_t* __restrict__ out, int32_t* __restrict__ prev_rect) {
+  const int j = blockIdx.y;
+  const int ow_words = (ow + 31) >> 5;
+  const bool live = j < min(*count, max_count);
+  const int k = live ? (index ? index[j] : j) : 0;
+  const int4 nr = live ? reinterpret_cast<const int4*>(rect)[k] : make_int4(0, 0, 0, 0);
+  const int4 pr = reinterpret_cast<const int4*>(prev_rect)[j];
+  const bool has_new = nr.y > nr.x && nr.w > nr.z, has_old = pr.y > pr.x && pr.w > pr.z;
+  __syncthreads();  // every thread has read prev_rect[j] before thread 0 of CTA 0 overwrites it
+  if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<int4*>(prev_rect)[j] = has_new ? nr : make_int4(0, 0, 0, 0);
+  if (!has_new && !has_old) return;
+  const int y0 = has_new ? (has_old ? min(nr.x, pr.x) : nr.x) : pr.x;
+  const int y1 = has_new ? (has_old ? max(nr.y, pr.y) : nr.y) : pr.y;
+  const int w0 = has_new ? (has_old ? min(nr.z, pr.z) : nr.z) : pr.z;
+  const int w1 = has_new ? (has_old ? max(nr.w, pr.w) : nr.w) : pr.w;
+  const int nw = w1 - w0;
+  const int total = (y1 - y0) * nw;
+  const uint32_t* src = bits_full + (size_t)k * oh * ow_words;
+  uint8_t* dst = out + (size_t)j * oh * ow;
+  const bool vec = (ow & 15) == 0;
+  for (int it = blockIdx.x * 256 + threadIdx.x; it < total; it += gridDim.x * 256) {
+    const int ry = it / nw, wi = w0 + (it - ry * nw);
+    const int y = y0 + ry, x = wi << 5;
+    uint32_t w = 0;
+    if (has_new && y >= nr.x && y < nr.y && wi >= nr.z && wi < nr.w) w = __ldg(src + (size_t)y * ow_words + wi);
+    uint8_t* p = dst + (size_t)y * ow + x;
+    if (vec) {
+      *reinterpret_cast<uint4*>(p) = make_uint4(nibble_to_bytes(w & 15u), nibble_to_bytes((w >> 4) & 15u),
+                                                 nibble_to_bytes((w >> 8) & 15u), nibble_to_bytes((w >> 12) & 15u));
+      if (x + 16 < ow)
+        *reinterpret_cast<uint4*>(p + 16) = make_uint4(nibble_to_bytes((w >> 16) & 15u), nibble_to_bytes((w >> 20) & 15u),
+                                                      nibble_to_bytes((w >> 24) & 15u), nibble_to_bytes(w >> 28));
+    } else {
+      for (int q = 0; q < 32 && x + q < ow; ++q) p[q] = (w >> q) & 1u;
+    }
+  }
+}
+
+int launch_unpack_sparse(const uint32_t* bits_full, const int32_t* rect, const int32_t* index, const int32_t* count,
+                         int max_count, int oh, int ow, uint8_t* out, int32_t* prev_rect, cudaStream_t s) {
+  if (max_count <= 0) return NTTT_OK;
+  dim3 grid(1, max_count);  // one CTA per slot: prev_rect[j] is read and rewritten by the same CTA
+  unpack_sparse_kernel<<<grid, 256, 0, s>>>(bits_full, rect, index, count, max_count, oh, ow, out, prev_rect);
+  NTTT_LAUNCH_CHECK();
+  return NTTT_OK;
+}
+
 int launch_unpack(const uint32_t* bits_full, const int32_t* rect, const int32_t* index, const int32_t* count,
                   int max_count, int oh, int ow, uint8_t* out, cudaStream_t s) {
   if (max_count <= 0) return NTTT_OK;

@@ -104,7 +104,7 @@ class MatchingStage:
         return ws
 
     def match_async(self, lr_masks: torch.Tensor, pred_ious: torch.Tensor, tar_feat: torch.Tensor, ori_hw,
-                    taps: bool = False, slot=0, iou_thr=None) -> PendingResult:
+                    taps: bool = False, slot=0, iou_thr=None, persistent_out=None) -> PendingResult:
         """Enqueue the whole stage for one image on the current stream.  `slot` selects which reusable
         workspace to use (callers that keep several images in flight on different streams use one slot per
         stream).  `iou_thr`, if given, fuses the reference's candidate filter (`scores_all > iou_thr`,
@@ -123,7 +123,14 @@ class MatchingStage:
         num_out = int(self.cfg.num_out_instance)
         max_sel = int(min(num_out * self.cfg.expand_ratio, n))
         dev = self.device
-        masks = torch.empty((max(num_out, 1), oh, ow), dtype=torch.uint8, device=dev)
+        prev_rect = None
+        if persistent_out is not None:
+            # outputs owned by the caller and reused call after call: (masks u8 [num_out,oh,ow] zero-initialised,
+            # prev_rect i32 [num_out,4] zero-initialised); only the changed rectangles are rewritten
+            masks, prev_rect = persistent_out
+            assert masks.shape == (max(num_out, 1), oh, ow) and masks.dtype == torch.uint8
+        else:
+            masks = torch.empty((max(num_out, 1), oh, ow), dtype=torch.uint8, device=dev)
         # (no fills: only the first n_out rows are ever read, and the pipeline writes the counts itself)
         boxes = torch.empty((max(num_out, 1), 4), dtype=torch.int64, device=dev)
         scores = torch.empty((max(num_out, 1),), dtype=torch.float32, device=dev)
@@ -152,6 +159,7 @@ class MatchingStage:
         a.proto_neg = self.proto_neg.data_ptr() if self.proto_neg is not None else None
         a.l_neg, a.sigma = self.l_neg, float(self.cfg.neg_sigma)
         a.iou_thr, a.filter_iou = (float(iou_thr), 1) if iou_thr is not None else (0.0, 0)
+        a.out_prev_rect = prev_rect.data_ptr() if prev_rect is not None else None
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(self.lib.nttt_match_image(self.ctx, ctypes.byref(a), stream), "nttt_match_image")
         return PendingResult(self, masks.view(torch.bool), boxes, scores, labels, index, counts, tap_t, (oh, ow),
@@ -197,6 +205,11 @@ class GraphedMatch:
         self.ori_hw = (int(ori_hw[0]), int(ori_hw[1]))
         self.iou_thr = iou_thr
         self._slot = ("graph", id(self) if key is None else key)
+        num_out = max(int(stage.cfg.num_out_instance), 1)
+        # persistent outputs: the mask buffer is zeroed once; afterwards every replay rewrites only the rectangles
+        # that change (nttt_match_args.out_prev_rect)
+        self._out = (torch.zeros((num_out, self.ori_hw[0], self.ori_hw[1]), dtype=torch.uint8, device=dev),
+                     torch.zeros((num_out, 4), dtype=torch.int32, device=dev))
         self.graph = None
         self.pending = None
 
@@ -207,13 +220,13 @@ class GraphedMatch:
         with torch.cuda.stream(side):
             for _ in range(2):
                 self.stage.match_async(self.lr_masks, self.pred_ious, self.tar_feat, self.ori_hw, slot=self._slot,
-                                       iou_thr=self.iou_thr)
+                                       iou_thr=self.iou_thr, persistent_out=self._out)
         torch.cuda.current_stream(self.stage.device).wait_stream(side)
         torch.cuda.synchronize(self.stage.device)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.pending = self.stage.match_async(self.lr_masks, self.pred_ious, self.tar_feat, self.ori_hw,
-                                                  slot=self._slot, iou_thr=self.iou_thr)
+                                                  slot=self._slot, iou_thr=self.iou_thr, persistent_out=self._out)
         return self
 
     def replay(self) -> PendingResult:

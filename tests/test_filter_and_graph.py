@@ -75,3 +75,29 @@ def test_graph_replay_matches_eager():
         assert torch.equal(torch.nan_to_num(out["scores"]), torch.nan_to_num(eager["scores"]))
         assert torch.equal(out["labels"], eager["labels"])
         assert torch.equal(out["binary_masks"], eager["binary_masks"]) and torch.equal(out["bboxes"], eager["bboxes"])
+
+
+def test_persistent_outputs_are_exactly_the_dense_unpack():
+    """Sparse unpack into persistent buffers: after every replay the WHOLE mask buffer (used and unused slots)
+    equals what a dense unpack into a fresh buffer gives, also when the number of outputs shrinks to zero."""
+    P, inp = _case(n=128, c=384, n_cls=9, seed=81, ori_hw=(480, 640))
+    stage = P.MatchingStage(DEV, P.StageConfig(nms_thr=0.5, num_out_instance=16, enc_hw=(37, 37)))
+    stage.set_prototypes(inp.feats_ins_avg)
+    g = stage.graphed(128, 384, (480, 640), iou_thr=0.4).capture()
+    for step, seed in enumerate((81, 82, 83, 84)):
+        _, cur = _case(n=128, c=384, n_cls=9, seed=seed, ori_hw=(480, 640))
+        if step == 2:
+            cur.pred_ious[:] = 0.1  # nothing passes the filter: every slot must be cleared
+        if step == 3:
+            cur.pred_ious[8:] = 0.1  # only a handful of candidates
+        g.lr_masks.copy_(cur.lr_masks)
+        g.pred_ious.copy_(cur.pred_ious)
+        g.tar_feat.copy_(cur.tar_feat)
+        out = g.replay().get()
+        eager = stage.match(cur.lr_masks.to(DEV), cur.pred_ious.to(DEV), cur.tar_feat.to(DEV), (480, 640), iou_thr=0.4)
+        n_out = out["counts"]["n_out"]
+        assert n_out == eager["counts"]["n_out"]
+        full = g._out[0].view(torch.bool)
+        assert torch.equal(full[:n_out], eager["binary_masks"])
+        assert not bool(full[n_out:].any()), "stale pixels left in unused output slots"
+    assert step == 3
