@@ -37,7 +37,8 @@ __device__ __forceinline__ float aa_dot(const float* __restrict__ src, int strid
 // scratch per mask (zero-initialised by the launcher): {area, maxx+1, maxy+1, BIG-minx, BIG-miny, done}
 constexpr int kScratchInts = 8;
 constexpr int kBig = 1 << 30;
-constexpr int kTapsReg = 4;  // footprints of up to 4 input rows keep their horizontal-pass values in registers
+constexpr int kTapsReg = 4;
+constexpr int kXtWords = 32;  // widest rect (in 32-pixel words) whose horizontal constants are staged in smem  // footprints of up to 4 input rows keep their horizontal-pass values in registers
 
 // per selected mask, resolved once by a tiny pre-kernel so that the four CTAs of a mask do not each chase
 // sel[] -> box_lr[] -> span tables; scratch[kScratchInts*k + 6..7] is unused padding
@@ -100,6 +101,24 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
 
   const uint32_t* lr = bits_lr + ((size_t)src_idx * ih + mt.lr0) * lr_wpr;
   for (int i = threadIdx.x; i < (mt.lr1 - mt.lr0) * lr_wpr; i += kUpThreads) s_lr[i] = lr[i];
+  // per-pixel horizontal constants of the mask's columns, one 128-bit LDS per use: {xmin | xsize << 16, w0, w1, w2}
+  // (xsize = 0 marks pixels beyond the image width).  Only when spans have <= 3 taps and the rect is <= 32 words.
+  float4* s_xt = reinterpret_cast<float4*>(s_lr + ih * lr_wpr);
+  const bool fast_x = t.tx <= 3 && (w1 - w0) <= kXtWords;
+  if (fast_x)
+    for (int i = threadIdx.x; i < (w1 - w0) * 32; i += kUpThreads) {
+      const int x = (w0 << 5) + i;
+      float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (x < ow) {
+        const int cs = t.xsize[x];
+        const float* wx = t.wx + (size_t)x * t.tx;
+        e.x = __int_as_float(t.xmin[x] | (cs << 16));
+        e.y = wx[0];
+        e.z = cs > 1 ? wx[1] : 0.0f;
+        e.w = cs > 2 ? wx[2] : 0.0f;
+      }
+      s_xt[i] = e;
+    }
   if (threadIdx.x < 5) s_red[threadIdx.x] = 0;
   const bool safe = mt.safe != 0;
   const float* src = logits + (size_t)src_idx * ih * iw;
@@ -133,6 +152,13 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
     const int ya = max(t.y_grp_start[g], r0), yb = min(t.y_grp_start[g + 1], r1);
     const int nrows = yb - ya;
     const int ry0 = t.ymin[ya], rys = t.ysize[ya];
+    const bool fast = fast_x && rys <= 3;
+    float wyv[kGrpMax][3];  // vertical weights of the group's rows (warp-uniform), fast path only
+#pragma unroll
+    for (int j = 0; j < kGrpMax; ++j)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) wyv[j][r] = (fast && j < nrows && r < rys) ? __ldg(t.wy + (size_t)(ya + j) * t.ty + r) : 0.0f;
+    const float* rowbase = src + (size_t)ry0 * iw;
     {
       uint32_t words[kGrpMax];
 #pragma unroll
@@ -171,6 +197,37 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
       while (todo) {
         const int src_lane = __ffs(todo) - 1;
         todo &= todo - 1;
+        if (fast) {
+          // all horizontal constants in one LDS; taps beyond cs are never read, so the arithmetic is exactly
+          // acc = s0*w0; acc = fma(s_j, w_j, acc) for j < cs, then the same over the rys input rows
+          const float4 xt = s_xt[((wbase + src_lane - w0) << 5) + lane];
+          const int pk = __float_as_int(xt.x);
+          const int cx = pk & 0xffff, cs = pk >> 16;
+          const float* p = rowbase + cx;
+          float T[3];
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            float acc = 0.0f;
+            if (r < rys && cs > 0) {
+              const float* q = p + (size_t)r * iw;
+              acc = __fmul_rn(__ldg(q), xt.y);
+              if (cs > 1) acc = __fmaf_rn(__ldg(q + 1), xt.z, acc);
+              if (cs > 2) acc = __fmaf_rn(__ldg(q + 2), xt.w, acc);
+            }
+            T[r] = acc;
+          }
+#pragma unroll
+          for (int j = 0; j < kGrpMax; ++j) {
+            if (j < nrows) {
+              float acc = __fmul_rn(T[0], wyv[j][0]);
+              if (rys > 1) acc = __fmaf_rn(T[1], wyv[j][1], acc);
+              if (rys > 2) acc = __fmaf_rn(T[2], wyv[j][2], acc);
+              const uint32_t res = __ballot_sync(kFull, cs > 0 && acc > 0.0f);
+              if (lane == src_lane) words[j] = res;
+            }
+          }
+          continue;
+        }
         const int x = ((wbase + src_lane) << 5) + lane;
         const bool inb = x < ow;
         const int cx = inb ? t.xmin[x] : 0, cs = inb ? t.xsize[x] : 1;
@@ -267,7 +324,7 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
                          int32_t* area_full, int32_t* box_full, int32_t* scratch, cudaStream_t s) {
   if (max_sel <= 0) return NTTT_OK;
   if (iw % 32 != 0) return NTTT_EUNSUPPORTED;
-  const size_t smem = (size_t)ih * (iw / 32) * 4;
+  const size_t smem = (size_t)ih * (iw / 32) * 4 + sizeof(float4) * kXtWords * 32;
   if (smem > 160 * 1024) return NTTT_EUNSUPPORTED;
   if (smem > 48 * 1024)
     NTTT_CUDA(cudaFuncSetAttribute(upsample_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
