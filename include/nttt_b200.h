@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NTTT_VERSION 100
+#define NTTT_VERSION 101
 
 enum {
   NTTT_OK = 0,
@@ -76,6 +76,27 @@ int nttt_ctx_profile_read(nttt_ctx* ctx, float* ms_host, int capacity);
  */
 int nttt_threshold_pack(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits,
                         int32_t* area, int32_t* box, int32_t* stab, int32_t* flags, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * candidate selection in front of the stage
+ * replaces: `best = argmax(ious[:, 1:]) + 1; low_res_multimasks[arange, best]; ious[arange, best]`
+ * (Sam2MatchingBaseline_noAMG.py:295-299), the per-batch `cat` (:423-425) and, together with `gate`, the
+ * `scores_all > iou_thr` compaction (:428-431) — without moving a single logit.
+ *   ious  [n, m] f32 : the decoder's predicted IoUs of its m mask planes per prompt (all batches concatenated)
+ *   first            : planes [first, m) compete (the reference skips plane 0: first = 1)
+ *   chunks_host      : HOST array of n_chunks DEVICE pointers (<= 64): the tensors the decoder returned, batch by
+ *                      batch, each [chunk_prompts, m, h, w] f32 and 16-byte aligned (the last may hold fewer prompts)
+ *   mask_ptr [n]     : device array of device pointers; mask_ptr[i] = address of prompt i's best plane
+ *   score [n] f32    : = ious[i, best(i)]      (first maximal value wins; NaN counts as maximal, as torch.argmax)
+ * nttt_threshold_pack_ptrs is nttt_threshold_pack reading mask i from mask_ptr[i] and skipping masks with
+ * !(gate[i] > gate_min) (gate may be NULL = keep all): skipped masks are published as empty and their logits
+ * are never read.
+ */
+int nttt_select_multimask(const float* ious, int n, int m, int first, const float* const* chunks_host, int n_chunks,
+                          int chunk_prompts, int h, int w, const float** mask_ptr, float* score, void* stream);
+int nttt_threshold_pack_ptrs(const float* const* mask_ptr, const float* gate, float gate_min, int n, int h, int w,
+                             float thr, float off, uint32_t* bits, int32_t* area, int32_t* box, int32_t* stab,
+                             int32_t* flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * a6 (feature half) + a7 — mask-average pooling and cosine similarity
@@ -142,6 +163,12 @@ int nttt_upsample_threshold_pack(nttt_ctx* ctx, const float* logits, const uint3
                                  const int32_t* sel, const int32_t* n_sel, int max_sel, int oh, int ow,
                                  uint32_t* bits_full, int32_t* rect, int32_t* area_full, int32_t* box_full,
                                  void* stream);
+/* same, with candidate i's logits at mask_ptr[i] (from nttt_select_multimask) */
+int nttt_upsample_threshold_pack_ptrs(nttt_ctx* ctx, const float* const* mask_ptr, const uint32_t* bits_lr,
+                                      const int32_t* box_lr, const int32_t* flags_lr, int ih, int iw,
+                                      const int32_t* sel, const int32_t* n_sel, int max_sel, int oh, int ow,
+                                      uint32_t* bits_full, int32_t* rect, int32_t* area_full, int32_t* box_full,
+                                      void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * a13 — intersection-over-self decay term on packed masks (popcount), per class
@@ -232,6 +259,18 @@ typedef struct nttt_match_args {
    * The unpack then rewrites only the bounding box of each slot's previous and new rect instead of oh*ow bytes per
    * mask; the buffer content after the call is identical to the dense unpack's. */
   int32_t* out_prev_rect;
+  /* fused multimask selection (Sam2MatchingBaseline_noAMG.py:295-299; nttt_select_multimask): when n_multi > 1,
+   * the decoder's raw output is consumed in place: `multi_ious` [n, n_multi] are its predicted IoUs, `pred_ious` is
+   * ignored (may be NULL); per prompt the best plane among [multi_first, n_multi) is used and its IoU becomes the
+   * NMS / filter score.  The logits are either ONE buffer `logits` [n, n_multi, lr_h, lr_w] (logits_chunks_host ==
+   * NULL) or the decoder's per-batch tensors: logits_chunks_host = HOST array of n_chunks (<= 64) device pointers,
+   * each [chunk_prompts, n_multi, lr_h, lr_w] (`logits` is then ignored).  n_multi <= 1: off. */
+  const float* multi_ious;
+  int32_t n_multi;
+  int32_t multi_first;
+  const float* const* logits_chunks_host;
+  int32_t n_chunks;
+  int32_t chunk_prompts;
 } nttt_match_args;
 
 size_t nttt_match_workspace_bytes(int n, int lr_h, int lr_w, int eh, int ew, int c, int n_cls, int ori_h,

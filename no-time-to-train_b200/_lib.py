@@ -36,6 +36,8 @@ class MatchArgs(ctypes.Structure):
         ("proto_neg", c_void_p), ("l_neg", c_int32), ("sigma", c_float),
         ("iou_thr", c_float), ("filter_iou", c_int32),
         ("out_prev_rect", c_void_p),
+        ("multi_ious", c_void_p), ("n_multi", c_int32), ("multi_first", c_int32),
+        ("logits_chunks_host", POINTER(c_void_p)), ("n_chunks", c_int32), ("chunk_prompts", c_int32),
     ]
 
 
@@ -48,6 +50,10 @@ SIGNATURES = {
     "nttt_ctx_create": (c_int, [POINTER(c_void_p), c_int]),
     "nttt_ctx_destroy": (None, [c_void_p]),
     "nttt_threshold_pack": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P]),
+    "nttt_select_multimask": (c_int, [_P, c_int, c_int, c_int, POINTER(c_void_p), c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "nttt_threshold_pack_ptrs": (c_int, [_P, _P, c_float, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P]),
+    "nttt_upsample_threshold_pack_ptrs": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, _P, _P,
+                                                  _P, _P, _P]),
     "nttt_project_masks": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "nttt_pool_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "nttt_pool_normalize": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),

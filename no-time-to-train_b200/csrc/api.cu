@@ -10,7 +10,9 @@ namespace nttt {
 
 // launchers implemented in the kernel translation units
 int launch_lowres_pack(const float*, int, int, int, float, float, uint32_t*, int32_t*, int32_t*, int32_t*, int32_t*,
-                       const float*, float, cudaStream_t);
+                       const float*, float, const float* const*, cudaStream_t);
+int launch_multimask_select(const float*, int, int, int, const ChunkTable&, int, size_t, const float**, float*,
+                            cudaStream_t);
 int launch_project_masks(const AxisTable&, const AxisTable&, const uint32_t*, const int32_t*, int, int, int, int, int,
                          void*, int, bool, cudaStream_t);
 int launch_normalize_split(const float*, const int32_t*, int, int, int, float*, void*, cudaStream_t);
@@ -28,7 +30,7 @@ int launch_box_nms(const int32_t*, const float*, const int32_t*, const float*, i
                    int32_t*, int32_t*, void*, size_t, float, int, cudaStream_t);
 int launch_upsample_pack(const AxisTable&, const AxisTable&, const float*, const uint32_t*, const int32_t*,
                          const int32_t*, int, int, const int32_t*, const int32_t*, int, int, int, uint32_t*, int32_t*,
-                         int32_t*, int32_t*, int32_t*, cudaStream_t);
+                         int32_t*, int32_t*, int32_t*, const float* const*, cudaStream_t);
 size_t upsample_scratch_bytes(int max_sel);
 int launch_unpack_sparse(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, uint8_t*,
                          int32_t*, cudaStream_t);
@@ -258,7 +260,41 @@ int nttt_threshold_pack(const float* logits, int n, int h, int w, float thr, flo
                         int32_t* box, int32_t* stab, int32_t* flags, void* stream) {
   if (n < 0 || h <= 0 || w <= 0) return NTTT_EINVAL;
   if (n > 0 && (!logits || !bits || !area || !box || !flags)) return NTTT_EINVAL;  // stab may be NULL
-  return launch_lowres_pack(logits, n, h, w, thr, off, bits, area, box, stab, flags, nullptr, 0.0f,
+  return launch_lowres_pack(logits, n, h, w, thr, off, bits, area, box, stab, flags, nullptr, 0.0f, nullptr,
+                            (cudaStream_t)stream);
+}
+
+// host-side check + by-value table of the decoder's per-batch tensors
+static int make_chunk_table(const float* const* chunks_host, int n_chunks, int chunk_prompts, int n, ChunkTable* out) {
+  if (!chunks_host || n_chunks <= 0 || chunk_prompts <= 0) return NTTT_EINVAL;
+  if (n_chunks > kMaxChunks) return NTTT_EUNSUPPORTED;
+  if ((long long)n_chunks * chunk_prompts < n) return NTTT_EINVAL;
+  for (int i = 0; i < kMaxChunks; ++i) out->base[i] = nullptr;
+  for (int i = 0; i < n_chunks; ++i) {
+    if (!chunks_host[i] || (reinterpret_cast<uintptr_t>(chunks_host[i]) & 15) != 0) return NTTT_EINVAL;
+    out->base[i] = chunks_host[i];
+  }
+  return NTTT_OK;
+}
+
+int nttt_select_multimask(const float* ious, int n, int m, int first, const float* const* chunks_host, int n_chunks,
+                          int chunk_prompts, int h, int w, const float** mask_ptr, float* score, void* stream) {
+  if (n < 0 || m <= 0 || first < 0 || first >= m || h <= 0 || w <= 0) return NTTT_EINVAL;
+  if (n == 0) return NTTT_OK;
+  if (!ious || !mask_ptr || !score || ((size_t)h * w) % 4 != 0) return NTTT_EINVAL;
+  ChunkTable t;
+  int err = make_chunk_table(chunks_host, n_chunks, chunk_prompts, n, &t);
+  if (err) return err;
+  return launch_multimask_select(ious, n, m, first, t, chunk_prompts, (size_t)h * w, mask_ptr, score,
+                                 (cudaStream_t)stream);
+}
+
+int nttt_threshold_pack_ptrs(const float* const* mask_ptr, const float* gate, float gate_min, int n, int h, int w,
+                             float thr, float off, uint32_t* bits, int32_t* area, int32_t* box, int32_t* stab,
+                             int32_t* flags, void* stream) {
+  if (n < 0 || h <= 0 || w <= 0) return NTTT_EINVAL;
+  if (n > 0 && (!mask_ptr || !bits || !area || !box || !flags)) return NTTT_EINVAL;
+  return launch_lowres_pack(nullptr, n, h, w, thr, off, bits, area, box, stab, flags, gate, gate_min, mask_ptr,
                             (cudaStream_t)stream);
 }
 
@@ -376,13 +412,14 @@ static int ensure_scratch(nttt_ctx* ctx, int max_sel, int32_t** out) {
   return NTTT_OK;
 }
 
-int nttt_upsample_threshold_pack(nttt_ctx* ctx, const float* logits, const uint32_t* bits_lr, const int32_t* box_lr,
-                                 const int32_t* flags_lr, int ih, int iw, const int32_t* sel, const int32_t* n_sel,
-                                 int max_sel, int oh, int ow, uint32_t* bits_full, int32_t* rect, int32_t* area_full,
-                                 int32_t* box_full, void* stream) {
+static int upsample_entry(nttt_ctx* ctx, const float* logits, const float* const* mask_ptr, const uint32_t* bits_lr,
+                          const int32_t* box_lr, const int32_t* flags_lr, int ih, int iw, const int32_t* sel,
+                          const int32_t* n_sel, int max_sel, int oh, int ow, uint32_t* bits_full, int32_t* rect,
+                          int32_t* area_full, int32_t* box_full, void* stream) {
   if (!ctx || max_sel < 0 || ih <= 0 || iw <= 0 || oh <= 0 || ow <= 0) return NTTT_EINVAL;
   if (max_sel == 0) return NTTT_OK;
-  if (!logits || !bits_lr || !box_lr || !flags_lr || !sel || !n_sel || !bits_full || !rect || !area_full || !box_full)
+  if ((!logits && !mask_ptr) || !bits_lr || !box_lr || !flags_lr || !sel || !n_sel || !bits_full || !rect || !area_full ||
+      !box_full)
     return NTTT_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
   ++ctx->epoch;
@@ -395,7 +432,23 @@ int nttt_upsample_threshold_pack(nttt_ctx* ctx, const float* logits, const uint3
   err = ensure_scratch(ctx, max_sel, &scratch);
   if (err) return err;
   return launch_upsample_pack(tx, ty, logits, bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, oh, ow,
-                              bits_full, rect, area_full, box_full, scratch, s);
+                              bits_full, rect, area_full, box_full, scratch, mask_ptr, s);
+}
+
+int nttt_upsample_threshold_pack(nttt_ctx* ctx, const float* logits, const uint32_t* bits_lr, const int32_t* box_lr,
+                                 const int32_t* flags_lr, int ih, int iw, const int32_t* sel, const int32_t* n_sel,
+                                 int max_sel, int oh, int ow, uint32_t* bits_full, int32_t* rect, int32_t* area_full,
+                                 int32_t* box_full, void* stream) {
+  return upsample_entry(ctx, logits, nullptr, bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, oh, ow, bits_full,
+                        rect, area_full, box_full, stream);
+}
+
+int nttt_upsample_threshold_pack_ptrs(nttt_ctx* ctx, const float* const* mask_ptr, const uint32_t* bits_lr,
+                                      const int32_t* box_lr, const int32_t* flags_lr, int ih, int iw, const int32_t* sel,
+                                      const int32_t* n_sel, int max_sel, int oh, int ow, uint32_t* bits_full,
+                                      int32_t* rect, int32_t* area_full, int32_t* box_full, void* stream) {
+  return upsample_entry(ctx, nullptr, mask_ptr, bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, oh, ow, bits_full,
+                        rect, area_full, box_full, stream);
 }
 
 size_t nttt_mask_ios_workspace_bytes(int max_sel) { return ios_workspace_bytes(max_sel > 0 ? max_sel : 1); }
@@ -465,6 +518,7 @@ struct MatchLayout {
   void* nms_ws; size_t nms_ws_bytes; int32_t* keep; int32_t* sel;
   uint32_t* bits_full; int32_t* rect; int32_t* area_full; int32_t* box_full; int32_t* scratch;
   float* ios; void* ios_ws; int32_t* out_slot;
+  const float** mask_ptr; float* plane_score;
   size_t total;
 };
 
@@ -505,6 +559,8 @@ static MatchLayout carve(void* ws, int n, int lr_h, int lr_w, int eh, int ew, in
   L.ios = cv.take<float>(max_sel > 0 ? max_sel : 1);
   L.ios_ws = cv.take<char>(ios_workspace_bytes(max_sel > 0 ? max_sel : 1));
   L.out_slot = cv.take<int32_t>(num_out > 0 ? num_out : 1);
+  L.mask_ptr = cv.take<const float*>(n > 0 ? n : 1);
+  L.plane_score = cv.take<float>(n > 0 ? n : 1);
   L.total = align_up(cv.off, 256);
   return L;
 }
@@ -537,9 +593,12 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
     NTTT_CUDA(cudaMemsetAsync(a->counts, 0, 4 * sizeof(int32_t), s));
     return NTTT_OK;
   }
-  if (!a->logits || !a->pred_ious || !a->tar_feat || !a->proto || !a->out_masks || !a->out_boxes || !a->out_scores ||
-      !a->out_labels || !a->out_index)
+  const bool multi = a->n_multi > 1;
+  const bool chunked = multi && a->logits_chunks_host;
+  if ((!a->logits && !chunked) || (!multi && !a->pred_ious) || !a->tar_feat || !a->proto || !a->out_masks ||
+      !a->out_boxes || !a->out_scores || !a->out_labels || !a->out_index)
     return NTTT_EINVAL;
+  if (multi && (!a->multi_ious || a->multi_first < 0 || a->multi_first >= a->n_multi)) return NTTT_EINVAL;
   const int l_neg = a->proto_neg ? a->l_neg : 0;
   if (a->proto_neg && (a->l_neg <= 0 || !(a->sigma > 0.0f))) return NTTT_EINVAL;
   MatchLayout L = carve(a->workspace, n, a->lr_h, a->lr_w, a->eh, a->ew, a->c, a->n_cls, a->ori_h, a->ori_w, max_sel,
@@ -571,11 +630,26 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
     NTTT_MARK();                                               \
     if (ctx->stop_after > 0 && ++stage_no >= ctx->stop_after) return NTTT_OK; \
   } while (0)
+  // candidate selection (§8f rank 2): resolve the best decoder plane per prompt; its IoU is the score from here on
+  const float* const* mask_ptr = nullptr;
+  const float* pred_ious = a->pred_ious;
+  if (multi) {
+    ChunkTable ct;
+    const float* one = a->logits;
+    err = chunked ? make_chunk_table(a->logits_chunks_host, a->n_chunks, a->chunk_prompts, n, &ct)
+                  : make_chunk_table(&one, 1, n, n, &ct);
+    if (err) return err;
+    if ((err = launch_multimask_select(a->multi_ious, n, a->n_multi, a->multi_first, ct, chunked ? a->chunk_prompts : n,
+                                       (size_t)a->lr_h * a->lr_w, L.mask_ptr, L.plane_score, s)))
+      return err;
+    mask_ptr = L.mask_ptr;
+    pred_ious = L.plane_score;
+  }
   NTTT_MARK();
   // a6/a9/a15: one pass over the logits
   // (the stability counts of a15 are not read on this path, so the pipeline does not pay for them)
   NTTT_STEP(launch_lowres_pack(a->logits, n, a->lr_h, a->lr_w, 0.0f, 1.0f, L.bits_lr, L.area_lr, L.box_lr, nullptr,
-                               L.flags, a->filter_iou ? a->pred_ious : nullptr, a->iou_thr, s));
+                               L.flags, a->filter_iou ? pred_ious : nullptr, a->iou_thr, mask_ptr, s));
   // a6/a7: projection + pooling contraction + normalisation
   if (!projection_supported(a->ew, a->lr_w) || !projection_supported(a->eh, a->lr_h)) return NTTT_EUNSUPPORTED;
   NTTT_STEP(launch_project_masks(px, py, L.bits_lr, L.box_lr, n, a->lr_h, a->lr_w, a->eh, a->ew, L.a_split, pad64(e),
@@ -587,12 +661,12 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   NTTT_STEP(sim_top1(obj_feats, a->proto, a->proto_neg, l_neg, a->sigma, n, a->c, a->n_cls, a->sim, L.sim_part,
                      L.sim_part_neg, L.top_score, L.top_label, L.a_split, L.b_split, a_ready, ctx->sm_count, s));
   // a10/a11
-  NTTT_STEP(launch_box_nms(L.box_lr, a->pred_ious, L.top_label, L.top_score, n, a->nms_thr, max_sel, L.keep,
+  NTTT_STEP(launch_box_nms(L.box_lr, pred_ious, L.top_label, L.top_score, n, a->nms_thr, max_sel, L.keep,
                            a->counts + 0, L.sel, a->counts + 1, L.nms_ws, L.nms_ws_bytes, a->iou_thr, a->filter_iou, s));
   // a12/a9
   NTTT_STEP(launch_upsample_pack(ux, uy, a->logits, L.bits_lr, L.box_lr, L.flags, a->lr_h, a->lr_w, L.sel,
                                  a->counts + 1, max_sel, a->ori_h, a->ori_w, L.bits_full, L.rect, L.area_full,
-                                 L.box_full, L.scratch, s));
+                                 L.box_full, L.scratch, mask_ptr, s));
   // a13
   NTTT_STEP(launch_mask_ios(L.bits_full, L.rect, L.area_full, L.box_full, L.sel, a->counts + 1, max_sel, a->ori_h,
                             a->ori_w, L.top_label, obj_feats, a->c, L.ios, nullptr, L.ios_ws, false, s));

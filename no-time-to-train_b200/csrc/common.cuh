@@ -110,6 +110,13 @@ constexpr int kMaxScatter = 24;
 
 int aa_max_taps(int in_size, int out_size);
 
+// base pointers of the decoder's per-batch output tensors, passed to multimask_select_kernel BY VALUE (stream-ordered,
+// graph-capturable, no staging copy)
+constexpr int kMaxChunks = 64;
+struct ChunkTable {
+  const float* base[kMaxChunks];
+};
+
 // internal launchers (defined in the .cu files, called by api.cu)
 int build_axis_table(AxisTable& t, int in_size, int out_size, cudaStream_t s);
 void free_axis_table(AxisTable& t);

@@ -42,19 +42,22 @@ constexpr int kXtWords = 32;  // widest rect (in 32-pixel words) whose horizonta
 
 // per selected mask, resolved once by a tiny pre-kernel so that the four CTAs of a mask do not each chase
 // sel[] -> box_lr[] -> span tables; scratch[kScratchInts*k + 6..7] is unused padding
-struct UpMeta {
-  int src;           // index into logits / bits_lr
+struct alignas(16) UpMeta {  // 48 bytes: three 128-bit loads
+  const float* logits;  // the candidate's [ih, iw] logits
+  int src;           // index into bits_lr / box_lr (candidate number)
   int r0, r1;        // output rows [r0, r1)
   int w0, w1;        // output words [w0, w1)
   int lr0, lr1;      // low-res rows [lr0, lr1) under those output rows
   int safe;          // flags bit0
+  int pad_[2];
 };
 
 __global__ void __launch_bounds__(256)
 upsample_meta_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __restrict__ box_lr,
                      const int32_t* __restrict__ flags_lr, int ih, int iw, const int32_t* __restrict__ sel,
                      const int32_t* __restrict__ n_sel, int max_sel, UpTables t, UpMeta* __restrict__ meta,
-                     int32_t* __restrict__ rect, int32_t* __restrict__ scratch) {
+                     int32_t* __restrict__ rect, int32_t* __restrict__ scratch, const float* __restrict__ logits,
+                     const float* const* __restrict__ mask_ptr) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= max_sel) return;
 #pragma unroll
@@ -62,6 +65,7 @@ upsample_meta_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
   if (k >= min(*n_sel, max_sel)) return;
   UpMeta m;
   m.src = sel[k];
+  m.logits = mask_ptr ? mask_ptr[m.src] : logits + (size_t)m.src * ih * iw;
   const int4 b = reinterpret_cast<const int4*>(box_lr)[m.src];
   // empty low-res mask <=> box all zero AND bit (0,0) clear
   const bool lr_empty = (b.x | b.y | b.z | b.w) == 0 && (bits_lr[(size_t)m.src * ih * (iw >> 5)] & 1u) == 0;
@@ -121,7 +125,7 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
     }
   if (threadIdx.x < 5) s_red[threadIdx.x] = 0;
   const bool safe = mt.safe != 0;
-  const float* src = logits + (size_t)src_idx * ih * iw;
+  const float* src = mt.logits;
   uint32_t* dst = bits_full + (size_t)k * oh * ow_words;
   __syncthreads();
 
@@ -321,7 +325,8 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
 int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* logits, const uint32_t* bits_lr,
                          const int32_t* box_lr, const int32_t* flags_lr, int ih, int iw, const int32_t* sel,
                          const int32_t* n_sel, int max_sel, int oh, int ow, uint32_t* bits_full, int32_t* rect,
-                         int32_t* area_full, int32_t* box_full, int32_t* scratch, cudaStream_t s) {
+                         int32_t* area_full, int32_t* box_full, int32_t* scratch, const float* const* mask_ptr,
+                         cudaStream_t s) {
   if (max_sel <= 0) return NTTT_OK;
   if (iw % 32 != 0) return NTTT_EUNSUPPORTED;
   const size_t smem = (size_t)ih * (iw / 32) * 4 + sizeof(float4) * kXtWords * 32;
@@ -332,7 +337,7 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
              ty.grp_of, ty.grp_start};
   UpMeta* meta = reinterpret_cast<UpMeta*>(scratch + (size_t)kScratchInts * max_sel);
   upsample_meta_kernel<<<ceil_div(max_sel, 256), 256, 0, s>>>(bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, t,
-                                                              meta, rect, scratch);
+                                                              meta, rect, scratch, logits, mask_ptr);
   NTTT_LAUNCH_CHECK();
   dim3 grid(kUpSplit, max_sel);
   upsample_pack_kernel<<<grid, kUpThreads, smem, s>>>(logits, bits_lr, meta, ih, iw, n_sel, max_sel, oh, ow, t, bits_full,

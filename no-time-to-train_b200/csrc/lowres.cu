@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kPackBlock, 3)
 lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mask */, int words_per_row,
                    float thr_hi, float thr_lo, uint32_t* __restrict__ bits, int32_t* __restrict__ area,
                    int32_t* __restrict__ box, int32_t* __restrict__ stab, int32_t* __restrict__ flags,
-                   const float* __restrict__ gate, float gate_min) {
+                   const float* __restrict__ gate, float gate_min, const float* const* __restrict__ mask_ptr) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   if (gate && !(gate[blockIdx.x] > gate_min)) {
     // filtered-out candidate (pred_iou <= iou_thr): its logits are never read; publish an empty mask
@@ -84,7 +84,8 @@ lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mas
   __shared__ uint64_t s_full[kPackStages], s_empty[kPackStages];
   __shared__ int s_red[8];  // area, hi, lo, unsafe, minx, miny, maxx, maxy
   const int n = blockIdx.x;
-  const float4* src = logits + (size_t)n * p4;
+  // mask_ptr (nullable): where the decoder left mask n's logits (multimask_select_kernel); else the dense [n,h,w] array
+  const float4* src = mask_ptr ? reinterpret_cast<const float4*>(mask_ptr[n]) : logits + (size_t)n * p4;
   const int lane = lane_id(), warp = warp_id();
   const int n_stages = (p4 + kPackStageF4 - 1) / kPackStageF4;
   if (threadIdx.x < 8) s_red[threadIdx.x] = (threadIdx.x == 4 || threadIdx.x == 5) ? 0x7fffffff : (threadIdx.x >= 6 ? -1 : 0);
@@ -187,24 +188,60 @@ lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mas
 
 // stab may be NULL: the stability counts (sam2/utils/amg.py:158-178) are not read on the noAMG path
 // gate (nullable): per-mask score; masks with !(gate[n] > gate_min) are skipped and published as empty
+// mask_ptr (nullable, device [n]): mask n is read from mask_ptr[n] (16-byte aligned) instead of logits + n*h*w
 int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits,
                        int32_t* area, int32_t* box, int32_t* stab, int32_t* flags, const float* gate, float gate_min,
-                       cudaStream_t s) {
+                       const float* const* mask_ptr, cudaStream_t s) {
   const long p = (long)h * w;
   if (n <= 0) return NTTT_OK;
   if (w % 32 != 0 || p % 128 != 0 || p / 32 * 4 > 32 * 1024) return NTTT_EUNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(logits) & 15) != 0) return NTTT_EINVAL;  // TMA bulk copies need 16-byte alignment
+  if (!mask_ptr && (reinterpret_cast<uintptr_t>(logits) & 15) != 0) return NTTT_EINVAL;  // TMA bulk copies need 16-byte alignment
   const size_t smem = (size_t)kPackStages * kPackStageBytes + (size_t)(p / 32) * sizeof(uint32_t);
   const float4* src = reinterpret_cast<const float4*>(logits);
   if (stab) {
     NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lowres_pack_kernel<true><<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area, box,
-                                                        stab, flags, gate, gate_min);
+                                                        stab, flags, gate, gate_min, mask_ptr);
   } else {
     NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lowres_pack_kernel<false><<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area,
-                                                         box, stab, flags, gate, gate_min);
+                                                         box, stab, flags, gate, gate_min, mask_ptr);
   }
+  NTTT_LAUNCH_CHECK();
+  return NTTT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Candidate selection fused into the stage: the SAM-2 decoder is run on batches of
+// `chunk_prompts` point prompts and returns, per batch, m mask planes [chunk_prompts, m, h, w] and m predicted IoUs
+// per prompt.  The reference keeps `argmax(ious[:, first:]) + first` per prompt
+// (Sam2MatchingBaseline_noAMG.py:295-299, first = 1), gathers that plane, concatenates the batches (:423-425) and
+// filters `score > iou_thr` (:428-431): three full copies of the logits.  Here only the ADDRESS of the chosen plane is
+// resolved; the logits stay in the tensors the decoder returned and are read once, by lowres_pack / upsample_pack,
+// through mask_ptr[].  torch.argmax semantics: the first maximal value wins, NaN counts as maximal.
+// ---------------------------------------------------------------------------------------------------
+__global__ void multimask_select_kernel(const float* __restrict__ ious, int n, int m, int first, ChunkTable chunks,
+                                        int chunk_prompts, size_t plane_elems, const float** __restrict__ mask_ptr,
+                                        float* __restrict__ score) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* row = ious + (size_t)i * m;
+  int best = first;
+  float bv = row[first];
+  for (int j = first + 1; j < m; ++j) {
+    const float v = row[j];
+    if (v > bv || (v != v && bv == bv)) { bv = v; best = j; }
+  }
+  const int ch = i / chunk_prompts;
+  mask_ptr[i] = chunks.base[ch] + ((size_t)(i - ch * chunk_prompts) * m + best) * plane_elems;
+  score[i] = bv;
+}
+
+int launch_multimask_select(const float* ious, int n, int m, int first, const ChunkTable& chunks, int chunk_prompts,
+                            size_t plane_elems, const float** mask_ptr, float* score, cudaStream_t s) {
+  if (n <= 0) return NTTT_OK;
+  multimask_select_kernel<<<ceil_div(n, 256), 256, 0, s>>>(ious, n, m, first, chunks, chunk_prompts, plane_elems, mask_ptr,
+                                                           score);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }

@@ -104,17 +104,36 @@ class MatchingStage:
         return ws
 
     def match_async(self, lr_masks: torch.Tensor, pred_ious: torch.Tensor, tar_feat: torch.Tensor, ori_hw,
-                    taps: bool = False, slot=0, iou_thr=None, persistent_out=None) -> PendingResult:
+                    taps: bool = False, slot=0, iou_thr=None, persistent_out=None, multi_ious=None,
+                    multi_first: int = 1) -> PendingResult:
         """Enqueue the whole stage for one image on the current stream.  `slot` selects which reusable
         workspace to use (callers that keep several images in flight on different streams use one slot per
         stream).  `iou_thr`, if given, fuses the reference's candidate filter (`scores_all > iou_thr`,
-        `Sam2MatchingBaseline_noAMG.py:428-431`): pass the decoder's full un-compacted masks and scores."""
+        `Sam2MatchingBaseline_noAMG.py:428-431`): pass the decoder's full un-compacted masks and scores.
+        `multi_ious` [n, m], if given, fuses the best-of-m plane selection (`:295-299`) as well: `lr_masks` is then
+        the decoder's raw output — one [n, m, 256, 256] tensor, or the LIST of per-batch tensors the decoder returned
+        (each [testing_point_bs, m, 256, 256]; consumed in place, no `cat`) — and `pred_ious` is ignored (pass None)."""
         if self.proto is None:
             raise RuntimeError("Memory is not ready!")  # same text as Sam2MatchingBaseline_noAMG.py:752
-        ops._need(lr_masks, torch.float32, "lr_masks")
-        ops._need(pred_ious, torch.float32, "pred_ious")
         ops._need(tar_feat, torch.float32, "tar_feat")
-        n, lh, lw = lr_masks.shape
+        n_multi, chunks = 0, None
+        if multi_ious is not None:
+            ops._need(multi_ious, torch.float32, "multi_ious")
+            chunks = list(lr_masks) if isinstance(lr_masks, (list, tuple)) else [lr_masks]
+            n, n_multi = multi_ious.shape
+            bs, _, lh, lw = chunks[0].shape
+            for i, ch in enumerate(chunks):
+                ops._need(ch, torch.float32, "lr_masks chunk")
+                if ch.dim() != 4 or tuple(ch.shape[1:]) != (n_multi, lh, lw) or (ch.shape[0] != bs and i + 1 < len(chunks)):
+                    raise ValueError("with multi_ious [n, m], lr_masks must be the decoder's [bs, m, h, w] outputs")
+            if sum(ch.shape[0] for ch in chunks) != n:
+                raise ValueError("multi_ious rows must match the prompts in lr_masks")
+            if n_multi < 2 or not 0 <= multi_first < n_multi:
+                raise ValueError("multi_ious needs m >= 2 planes and 0 <= multi_first < m")
+        else:
+            ops._need(lr_masks, torch.float32, "lr_masks")
+            ops._need(pred_ious, torch.float32, "pred_ious")
+            n, lh, lw = lr_masks.shape
         eh, ew = self.cfg.enc_hw
         e, c = tar_feat.shape
         if e != eh * ew:
@@ -144,8 +163,12 @@ class MatchingStage:
         ws_bytes = self.lib.nttt_match_workspace_bytes_neg(n, lh, lw, eh, ew, c, self.n_cls, oh, ow, max_sel, self.l_neg)
         ws = self._workspace(("match", slot), ws_bytes)
         a = _lib.MatchArgs()
-        a.logits, a.pred_ious, a.tar_feat, a.proto = (lr_masks.data_ptr(), pred_ious.data_ptr(), tar_feat.data_ptr(),
-                                                      self.proto.data_ptr())
+        a.logits, a.pred_ious, a.tar_feat, a.proto = (None if chunks else lr_masks.data_ptr(), ops._ptr(pred_ious),
+                                                      tar_feat.data_ptr(), self.proto.data_ptr())
+        a.multi_ious, a.n_multi, a.multi_first = ops._ptr(multi_ious), n_multi, int(multi_first)
+        if chunks:
+            table = ops.chunk_table(chunks)
+            a.logits_chunks_host, a.n_chunks, a.chunk_prompts = table, len(chunks), int(chunks[0].shape[0])
         a.n, a.lr_h, a.lr_w, a.eh, a.ew, a.c, a.n_cls = n, lh, lw, eh, ew, c, self.n_cls
         a.ori_h, a.ori_w = oh, ow
         a.nms_thr = float(self.cfg.nms_thr)
@@ -163,7 +186,7 @@ class MatchingStage:
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(self.lib.nttt_match_image(self.ctx, ctypes.byref(a), stream), "nttt_match_image")
         return PendingResult(self, masks.view(torch.bool), boxes, scores, labels, index, counts, tap_t, (oh, ow),
-                             keepalive=(lr_masks, pred_ious, tar_feat, ws))
+                             keepalive=(lr_masks, pred_ious, multi_ious, tar_feat, ws))
 
     def profile(self, enable: bool) -> None:
         """Per-stage CUDA-event timing of the next `match_async` calls (see nttt_ctx_profile)."""
@@ -178,12 +201,16 @@ class MatchingStage:
             _lib.check(got, "nttt_ctx_profile_read")
         return {self.lib.nttt_profile_stage_name(i).decode(): float(buf[i]) for i in range(got)}
 
-    def match(self, lr_masks, pred_ious, tar_feat, ori_hw, taps: bool = False, iou_thr=None) -> dict:
-        return self.match_async(lr_masks, pred_ious, tar_feat, ori_hw, taps=taps, iou_thr=iou_thr).get()
+    def match(self, lr_masks, pred_ious, tar_feat, ori_hw, taps: bool = False, iou_thr=None, multi_ious=None,
+              multi_first: int = 1) -> dict:
+        return self.match_async(lr_masks, pred_ious, tar_feat, ori_hw, taps=taps, iou_thr=iou_thr,
+                                multi_ious=multi_ious, multi_first=multi_first).get()
 
-    def graphed(self, n: int, c: int, ori_hw, iou_thr=None, key=None) -> "GraphedMatch":
-        """A CUDA-graph capture of the whole stage at fixed shapes with static input/output buffers."""
-        return GraphedMatch(self, n, c, ori_hw, iou_thr, key)
+    def graphed(self, n: int, c: int, ori_hw, iou_thr=None, key=None, n_multi: int = 0,
+                multi_first: int = 1) -> "GraphedMatch":
+        """A CUDA-graph capture of the whole stage at fixed shapes with static input/output buffers.
+        n_multi > 1: the static mask buffer is the decoder's raw [n, n_multi, 256, 256] output (+ `multi_ious`)."""
+        return GraphedMatch(self, n, c, ori_hw, iou_thr, key, n_multi, multi_first)
 
 
 class GraphedMatch:
@@ -195,12 +222,20 @@ class GraphedMatch:
     `replay()`.  Outputs live in static buffers too: consume a result (`.get()`) before replaying the same object
     again.  Replay costs one graph launch on the host instead of ~18 kernel launches."""
 
-    def __init__(self, stage: MatchingStage, n: int, c: int, ori_hw, iou_thr=None, key=None):
+    def __init__(self, stage: MatchingStage, n: int, c: int, ori_hw, iou_thr=None, key=None, n_multi: int = 0,
+                 multi_first: int = 1):
         dev = stage.device
         eh, ew = stage.cfg.enc_hw
         self.stage = stage
-        self.lr_masks = torch.zeros((n, 256, 256), dtype=torch.float32, device=dev)
-        self.pred_ious = torch.zeros((n,), dtype=torch.float32, device=dev)
+        if n_multi > 1:
+            self.lr_masks = torch.zeros((n, n_multi, 256, 256), dtype=torch.float32, device=dev)
+            self.multi_ious = torch.zeros((n, n_multi), dtype=torch.float32, device=dev)
+            self.pred_ious = None
+        else:
+            self.lr_masks = torch.zeros((n, 256, 256), dtype=torch.float32, device=dev)
+            self.pred_ious = torch.zeros((n,), dtype=torch.float32, device=dev)
+            self.multi_ious = None
+        self.multi_first = multi_first
         self.tar_feat = torch.zeros((eh * ew, c), dtype=torch.float32, device=dev)
         self.ori_hw = (int(ori_hw[0]), int(ori_hw[1]))
         self.iou_thr = iou_thr
@@ -220,13 +255,15 @@ class GraphedMatch:
         with torch.cuda.stream(side):
             for _ in range(2):
                 self.stage.match_async(self.lr_masks, self.pred_ious, self.tar_feat, self.ori_hw, slot=self._slot,
-                                       iou_thr=self.iou_thr, persistent_out=self._out)
+                                       iou_thr=self.iou_thr, persistent_out=self._out, multi_ious=self.multi_ious,
+                                       multi_first=self.multi_first)
         torch.cuda.current_stream(self.stage.device).wait_stream(side)
         torch.cuda.synchronize(self.stage.device)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.pending = self.stage.match_async(self.lr_masks, self.pred_ious, self.tar_feat, self.ori_hw,
-                                                  slot=self._slot, iou_thr=self.iou_thr, persistent_out=self._out)
+                                                  slot=self._slot, iou_thr=self.iou_thr, persistent_out=self._out,
+                                                  multi_ious=self.multi_ious, multi_first=self.multi_first)
         return self
 
     def replay(self) -> PendingResult:

@@ -118,11 +118,27 @@ class Sam2MatchingBaselineNoAMG(nn.Module):
         x = F.interpolate(tar_img.unsqueeze(0), size=(self.encoder_img_size, self.encoder_img_size), mode="bicubic")
         return self._forward_encoder(_normalize(x)).reshape(-1, self.encoder_dim), tar_img
 
-    def _forward_sam(self, imgs):
-        """(:355-433) grid-prompted SAM-2 decoding; returns lr_masks [N,256,256], pred_ious [N], points."""
+    def _forward_sam_raw(self, imgs):
+        """(:355-426) grid-prompted SAM-2 decoding, stopped BEFORE the reference's best-of-3 gather, `cat` and
+        `iou_thr` compaction (:295-299, :423-431) — those are fused into the stage.
+        Returns the decoder's raw per-batch outputs: chunks (list of [bs,4,256,256]), ious [N,4], points."""
         if self.predictor is None or not hasattr(self.predictor, "forward_image"):
             raise RuntimeError("no SAM-2 predictor was provided")
         return _sam2_grid_masks(self, imgs)
+
+    def _forward_sam(self, imgs):
+        """(:355-433) the reference's seam: compacted `lr_masks [N,256,256], pred_ious [N], points`.  `forward_test`
+        only goes through it when a subclass overrides it (tests inject synthetic candidates here) or when
+        `fuse_candidate_selection` is off; otherwise the raw decoder output is handed to the stage in place."""
+        chunks, ious, points = self._forward_sam_raw(imgs)
+        multi = torch.cat(chunks, dim=0)
+        best = torch.argmax(ious[:, 1:], dim=-1) + 1
+        rows = torch.arange(multi.shape[0], device=multi.device)
+        masks, scores = multi[rows, best], ious[rows, best]
+        keep = scores > self.iou_thr
+        return masks[keep], scores[keep], points[:multi.shape[0]][keep]
+
+    fuse_candidate_selection = True
 
     # ------------------------------------------------------------------ modes
     def forward_fill_memory(self, input_dicts, is_positive=True):
@@ -165,11 +181,20 @@ class Sam2MatchingBaselineNoAMG(nn.Module):
         device = self._device
         with torch.inference_mode():
             tar_feat, tar_img = self._extract_target_features(input_dicts[0]["target_img"], device)
-            lr_masks, pred_ious, _ = self._forward_sam(_normalize(tar_img.unsqueeze(0)))
             info = input_dicts[0]["target_img_info"]
+            ori_hw = (info["ori_height"], info["ori_width"])
             self._ensure_prototypes(with_negative)
-            out = self.stage.match(lr_masks.float().contiguous(), pred_ious.float().contiguous().reshape(-1),
-                                   tar_feat.float().contiguous(), (info["ori_height"], info["ori_width"]))
+            sam_in = _normalize(tar_img.unsqueeze(0))
+            seam_overridden = type(self)._forward_sam is not Sam2MatchingBaselineNoAMG._forward_sam
+            if self.fuse_candidate_selection and not seam_overridden:
+                chunks, multi_ious, _ = self._forward_sam_raw(sam_in)
+                out = self.stage.match([c.float().contiguous() for c in chunks], None, tar_feat.float().contiguous(),
+                                       ori_hw, iou_thr=float(self.iou_thr),
+                                       multi_ious=multi_ious.float().contiguous(), multi_first=1)
+            else:
+                lr_masks, pred_ious, _ = self._forward_sam(sam_in)
+                out = self.stage.match(lr_masks.float().contiguous(), pred_ious.float().contiguous().reshape(-1),
+                                       tar_feat.float().contiguous(), ori_hw)
         self._reset()
         return [dict(binary_masks=out["binary_masks"], bboxes=out["bboxes"], scores=out["scores"],
                      labels=out["labels"], image_info=info)]
@@ -230,8 +255,9 @@ def _build_reference_encoder(encoder_cfg, ckpt_path, device):
 
 
 def _sam2_grid_masks(model, imgs):
-    """Grid-point prompting of the frozen SAM-2 decoder: best-of-3 multimask output by predicted IoU per
-    point, then `pred_iou > iou_thr`.  This is encoder-side glue kept in plain PyTorch."""
+    """Grid-point prompting of the frozen SAM-2 decoder (`_forward_sam` / `_compute_masks` / `_forward_sam_decoder`,
+    :259-426), encoder-side glue kept in plain PyTorch.  The decoder's raw outputs are returned batch by batch; the
+    best-of-3 plane choice, the concatenation and the `pred_iou > iou_thr` filter happen inside the stage."""
     pred = model.predictor
     device = imgs.device
     side = imgs.shape[-2]
@@ -244,20 +270,16 @@ def _sam2_grid_masks(model, imgs):
     img_feats = vis_feats[-1].permute(1, 2, 0).reshape(1, -1, *feat_sizes[-1]).expand(bs, -1, -1, -1)
     hr_feats = [x.permute(1, 2, 0).reshape(1, -1, *s).expand(bs, -1, -1, -1)
                 for x, s in zip(vis_feats[:-1], feat_sizes[:-1])]
-    masks, ious = [], []
+    chunks, ious = [], []
     for start in range(0, (points.shape[0] // bs) * bs, bs):
         pts = points[start:start + bs].reshape(bs, 1, 2)
         lbl = torch.ones((bs, 1), dtype=torch.int32, device=device)
         sparse, dense = pred.sam_prompt_encoder(points=(pts, lbl), boxes=None, masks=None)
-        multi, iou, _, _ = pred.sam_mask_decoder(
+        multi, iou, _, _ = pred.sam_mask_decoder(  # same keywords as the reference call (:275-288)
             image_embeddings=img_feats, image_pe=pred.sam_prompt_encoder.get_dense_pe(),
             sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense, multimask_output=True,
-            repeat_image=False, high_res_features=hr_feats)
-        best = torch.argmax(iou[:, 1:], dim=-1) + 1
-        rows = torch.arange(bs, device=device)
-        masks.append(multi[rows, best])
-        ious.append(iou[rows, best])
-    masks = torch.cat(masks, dim=0)
-    ious = torch.cat(ious, dim=0).reshape(-1)
-    keep = ious > model.iou_thr
-    return masks[keep], ious[keep], points[keep]
+            repeat_image=False, high_res_features=hr_feats, return_iou_token_out=False,
+            disable_custom_iou_embed=True, disable_mlp_obj_scores=True, output_all_masks=True)
+        chunks.append(multi)
+        ious.append(iou)
+    return chunks, torch.cat(ious, dim=0), points

@@ -68,6 +68,52 @@ def threshold_pack(logits: torch.Tensor, thr: float = 0.0, off: float = 1.0, out
     return bits, area, box, stab, flags
 
 
+def chunk_table(chunks):
+    """HOST array of the device pointers of the decoder's per-batch tensors (each [prompts, m, h, w] f32)."""
+    arr = (ctypes.c_void_p * len(chunks))()
+    for i, t in enumerate(chunks):
+        _need(t, torch.float32, "logits chunk")
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def select_multimask(ious: torch.Tensor, chunks, first: int = 1):
+    """Best decoder plane per prompt (`argmax(ious[:, first:]) + first`, `Sam2MatchingBaseline_noAMG.py:295-299`).
+    `chunks`: the decoder's per-batch outputs (list of [prompts, m, h, w] tensors, equal prompts except the last).
+    -> mask_ptr [n] int64 (device addresses of the chosen planes), score [n] f32."""
+    _need(ious, torch.float32, "ious")
+    n, m = ious.shape
+    _, m2, h, w = chunks[0].shape
+    assert m2 == m
+    mask_ptr = torch.empty((n,), dtype=torch.int64, device=ious.device)
+    score = torch.empty((n,), dtype=torch.float32, device=ious.device)
+    lib = _lib.load()
+    _lib.check(lib.nttt_select_multimask(_ptr(ious), n, m, first, chunk_table(chunks), len(chunks), chunks[0].shape[0],
+                                         h, w, _ptr(mask_ptr), _ptr(score), _stream(ious.device)),
+               "nttt_select_multimask")
+    return mask_ptr, score
+
+
+def threshold_pack_ptrs(mask_ptr: torch.Tensor, hw, gate=None, gate_min: float = 0.0, thr: float = 0.0,
+                        off: float = 1.0):
+    """`threshold_pack` of mask i read from address mask_ptr[i]; masks with !(gate[i] > gate_min) are published as
+    empty without reading their logits."""
+    _need(mask_ptr, torch.int64, "mask_ptr")
+    h, w = hw
+    n = mask_ptr.shape[0]
+    dev = mask_ptr.device
+    bits = torch.empty((n, h * w // 32), dtype=torch.int32, device=dev)
+    area = torch.empty((n,), dtype=torch.int32, device=dev)
+    box = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    stab = torch.empty((n, 2), dtype=torch.int32, device=dev)
+    flags = torch.empty((n,), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.nttt_threshold_pack_ptrs(_ptr(mask_ptr), _ptr(gate), gate_min, n, h, w, thr, off, _ptr(bits),
+                                            _ptr(area), _ptr(box), _ptr(stab), _ptr(flags), _stream(dev)),
+               "nttt_threshold_pack_ptrs")
+    return bits, area, box, stab, flags
+
+
 def project_masks(bits: torch.Tensor, box: torch.Tensor, hw, enc_hw):
     _need(bits, torch.int32, "bits")
     _need(box, torch.int32, "box")
@@ -164,13 +210,20 @@ def box_nms(box: torch.Tensor, nms_scores: torch.Tensor, labels: torch.Tensor, t
     return keep, sel, counts
 
 
-def upsample_threshold_pack(logits, bits_lr, box_lr, flags_lr, sel, n_sel, max_sel: int, ori_hw):
-    """-> bits_full [max_sel, oh, words] i32, rect [max_sel,4], area_full [max_sel], box_full [max_sel,4]."""
-    _need(logits, torch.float32, "logits")
+def upsample_threshold_pack(logits, bits_lr, box_lr, flags_lr, sel, n_sel, max_sel: int, ori_hw, mask_ptr=None,
+                            lr_hw=None):
+    """-> bits_full [max_sel, oh, words] i32, rect [max_sel,4], area_full [max_sel], box_full [max_sel,4].
+    With `mask_ptr` (from select_multimask) candidate i's logits are read from mask_ptr[i]; pass logits=None and
+    lr_hw=(ih, iw)."""
     _need(bits_lr, torch.int32, "bits_lr")
     _need(sel, torch.int32, "sel")
     _need(n_sel, torch.int32, "n_sel")
-    _, ih, iw = logits.shape
+    if mask_ptr is not None:
+        ih, iw = lr_hw
+        logits = bits_lr  # device handle only
+    else:
+        _need(logits, torch.float32, "logits")
+        _, ih, iw = logits.shape
     oh, ow = ori_hw
     dev = logits.device
     words = (ow + 31) // 32
@@ -179,6 +232,12 @@ def upsample_threshold_pack(logits, bits_lr, box_lr, flags_lr, sel, n_sel, max_s
     area_full = torch.zeros((max_sel,), dtype=torch.int32, device=dev)
     box_full = torch.zeros((max_sel, 4), dtype=torch.int32, device=dev)
     lib = _lib.load()
+    if mask_ptr is not None:
+        _lib.check(lib.nttt_upsample_threshold_pack_ptrs(context(dev), _ptr(mask_ptr), _ptr(bits_lr), _ptr(box_lr),
+                                                         _ptr(flags_lr), ih, iw, _ptr(sel), _ptr(n_sel), max_sel, oh, ow,
+                                                         _ptr(bits_full), _ptr(rect), _ptr(area_full), _ptr(box_full),
+                                                         _stream(dev)), "nttt_upsample_threshold_pack_ptrs")
+        return bits_full, rect, area_full, box_full
     _lib.check(lib.nttt_upsample_threshold_pack(context(dev), _ptr(logits), _ptr(bits_lr), _ptr(box_lr),
                                                 _ptr(flags_lr), ih, iw, _ptr(sel), _ptr(n_sel), max_sel, oh, ow,
                                                 _ptr(bits_full), _ptr(rect), _ptr(area_full), _ptr(box_full),

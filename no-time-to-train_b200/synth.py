@@ -118,3 +118,23 @@ def make_ref_shots(n_cls: int, shots: int, e: int, c: int, seed: int = 4321):
             masks[ci, li, y0, x0:x0 + ww] = 0.5
             masks[ci, li, y0:y0 + hh, x0] = 0.25
     return feats, masks.reshape(n_cls, shots, e)
+
+
+def make_multimask_inputs(n: int, m: int = 4, seed: int = 77, jitter: float = 0.35):
+    """Synthetic RAW decoder output at the `sam_mask_decoder` seam (`Sam2MatchingBaseline_noAMG.py:275-288`):
+    `multi [n, m, 256, 256]` logits (m jittered variants of one blob per prompt) and `ious [n, m]` in (0.2, 1).
+    A few rows carry the edge cases of the selection: a tie between two planes (first wins), plane 0 holding the
+    largest IoU (it never competes), an IoU exactly at a typical threshold."""
+    gen = torch.Generator().manual_seed(seed)
+    base = make_masks(n, gen)
+    multi = torch.empty((n, m, LOWRES, LOWRES), dtype=torch.float32)
+    for j in range(m):
+        shift = jitter * (j + 1) * torch.randn(n, 1, 1, generator=gen)
+        multi[:, j] = base * (1.0 + 0.1 * j) + shift + 0.3 * torch.randn(n, LOWRES, LOWRES, generator=gen)
+    ious = 0.2 + 0.8 * torch.rand(n, m, generator=gen)
+    if n >= 6 and m >= 3:
+        ious[0, 1] = ious[0, 2] = 0.9   # tie: plane 1 wins
+        ious[0, 3:] = 0.3
+        ious[1, 0] = 0.99               # plane 0 is skipped even when it is the best
+        ious[2, 1:] = 0.5               # all equal to the threshold used by the tests: filtered (strict >)
+    return multi.contiguous(), ious.contiguous()

@@ -125,6 +125,25 @@ def semantic_ios(masks_u8, labels, obj_sim, want_inter=False):
     return (ios, inter) if want_inter else ios
 
 
+def select_candidates(multi, ious, iou_thr, first=1):
+    """numpy restatement of the candidate selection (Sam2MatchingBaseline_noAMG.py:295-299, :428-431): per prompt the
+    first maximal IoU among planes [first, m) (NaN counts as maximal, as torch.argmax), then `score > iou_thr`.
+    multi [n, m, h, w], ious [n, m] -> (lr_masks [n', h, w], scores [n'], kept prompt indices [n'])."""
+    multi, ious = np.asarray(multi), np.asarray(ious, dtype=np.float32)
+    n, m = ious.shape
+    best = np.empty(n, dtype=np.int64)
+    for i in range(n):
+        b, bv = first, ious[i, first]
+        for j in range(first + 1, m):
+            v = ious[i, j]
+            if v > bv or (np.isnan(v) and not np.isnan(bv)):
+                b, bv = j, v
+        best[i] = b
+    scores = ious[np.arange(n), best]
+    keep = np.nonzero(scores > np.float32(iou_thr))[0]
+    return multi[keep, best[keep]], scores[keep], keep
+
+
 def l2_normalize(x, eps=1e-12):
     """F.normalize(p=2, dim=-1): x / max(||x||, eps)."""
     x = _f32(x)

@@ -30,6 +30,23 @@ class StageConfig:
     expand_ratio: int = 8  # literal at :621
 
 
+def select_candidates(chunks, ious_chunks, iou_thr: float):
+    """Candidate selection in front of the stage: per decoder batch `best = argmax(ious[:, 1:]) + 1`, gather that
+    plane and its IoU (`_forward_sam_decoder`, :295-299), concatenate the batches (:423-425), keep
+    `scores > iou_thr` (:428-431).  chunks: list of [bs, m, h, w]; ious_chunks: list of [bs, m].
+    -> lr_masks [N', h, w], pred_ious [N'], kept prompt indices [N']."""
+    masks, scores = [], []
+    for multi, ious in zip(chunks, ious_chunks):
+        best = torch.argmax(ious[:, 1:], dim=-1) + 1
+        rows = torch.arange(multi.shape[0])
+        masks.append(multi[rows, best])
+        scores.append(ious[rows, best].reshape(-1))
+    masks = torch.cat(masks, dim=0)
+    scores = torch.cat(scores, dim=0).reshape(-1)
+    inds = scores > iou_thr
+    return masks[inds], scores[inds], torch.nonzero(inds).reshape(-1)
+
+
 def threshold_lowres(lr_masks: torch.Tensor) -> torch.Tensor:
     """`_process_sam_masks`, mask half (:547-549): strict `> 0`, flattened to [N, P]."""
     return (lr_masks > 0).reshape(lr_masks.shape[0], -1)

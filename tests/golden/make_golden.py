@@ -50,6 +50,13 @@ NEG_CASES = {
     "stageneg_b_20cls_2neg": (96, 256, 20, 2, (512, 512), 302, 20),
 }
 
+# candidate-selection cases (real `_forward_sam` over a stand-in predictor that returns synthetic RAW decoder output):
+# name -> (points_per_side, testing_point_bs, m, iou_thr, c, n_cls, shots, ori_hw, seed, num_out)
+MULTI_CASES = {
+    "stagemm_a_64prompts_bs16": (8, 16, 4, 0.5, 128, 5, 2, (480, 640), 401, 10),
+    "stagemm_b_100prompts_bs25": (10, 25, 4, 0.8, 64, 3, 2, (512, 512), 402, 8),
+}
+
 # name -> (n_cls, shots, filled_per_class, c, seed)
 FILL_CASES = {
     "fill_a_3cls_2shot": (3, 2, [2, 2, 1], 32, 201),
@@ -191,6 +198,70 @@ def run_neg_case(ref, name, spec):
           f"sim range [{float(cap['sim'].min()):.3f}, {float(cap['sim'].max()):.3f}]")
 
 
+def run_multimask_case(ref, name, spec):
+    """The reference's own `_forward_sam` (+ `_compute_masks`, `_forward_sam_decoder`: best-of-3 gather, cat,
+    `> iou_thr`) over a stand-in predictor whose decoder returns seeded synthetic multimask logits, followed by the
+    real `forward_test`."""
+    pps, bs, m, iou_thr, c, n_cls, shots, ori_hw, seed, num_out = spec
+    n = pps * pps
+    multi, ious = synth.make_multimask_inputs(n, m, seed=seed)
+    feat_in = synth.make_stage_inputs(8, c, n_cls, shots, ori_hw, seed=seed + 1, clustered=True)
+    calls = {"i": 0}
+
+    def decoder(**kw):
+        assert kw["multimask_output"] is True and kw["output_all_masks"] is True and kw["repeat_image"] is False
+        i = calls["i"]
+        calls["i"] += 1
+        return multi[i * bs:(i + 1) * bs], ious[i * bs:(i + 1) * bs], None, None
+
+    prompt_encoder = lambda points, boxes, masks: (torch.zeros(bs, 2, 4), torch.zeros(bs, 4, 2, 2))
+    prompt_encoder.get_dense_pe = lambda: torch.zeros(1, 4, 2, 2)
+    pred = types.SimpleNamespace(
+        device=torch.device("cpu"),
+        forward_image=lambda imgs: {},
+        _prepare_backbone_features=lambda bo: (None, [torch.zeros(16, 1, 4), torch.zeros(4, 1, 4)], None, [(4, 4), (2, 2)]),
+        sam_prompt_encoder=prompt_encoder, sam_mask_decoder=decoder)
+    cap = {}
+    fake = types.SimpleNamespace()
+    fake.predictor = pred
+    fake.points_per_side, fake.testing_point_bs, fake.iou_thr = pps, bs, iou_thr
+    fake.backbone_features = fake.backbone_hr_features = None
+    fake._get_grid_points = types.MethodType(ref.Model._get_grid_points, fake)
+    fake._compute_masks = types.MethodType(ref.Model._compute_masks, fake)
+    fake._forward_sam_decoder = types.MethodType(ref.Model._forward_sam_decoder, fake)
+    real_forward_sam = types.MethodType(ref.Model._forward_sam, fake)
+
+    def forward_sam(imgs):
+        out = real_forward_sam(imgs)
+        cap["lr_masks"], cap["pred_ious"] = out[0].clone(), out[1].clone()
+        return out
+    fake._forward_sam = forward_sam
+    fake.encoder_h, fake.encoder_w = 37, 37
+    fake.cls_num_per_mask = 1
+    fake.num_out_instance = num_out
+    fake.nms_thr = 0.5
+    fake.online_vis = False
+    fake.memory_bank = types.SimpleNamespace(feats_ins_avg=feat_in.feats_ins_avg, n_classes=n_cls)
+    fake.sam_transform = lambda x: x
+    fake._extract_target_features = lambda img, device: (feat_in.tar_feat, img)
+    fake._process_sam_masks = types.MethodType(ref.Model._process_sam_masks, fake)
+    fake._reset = lambda: None
+    info = dict(ori_height=ori_hw[0], ori_width=ori_hw[1], file_name="synthetic", id=0)
+    with torch.inference_mode():
+        out = ref.Model.forward_test(fake, [dict(target_img=torch.zeros(3, 64, 64), target_img_info=info)], False)[0]
+    assert calls["i"] == n // bs
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"),
+        spec=np.array([pps, bs, m, c, n_cls, shots, ori_hw[0], ori_hw[1], seed, num_out], dtype=np.int64),
+        iou_thr=np.array(iou_thr, dtype=np.float64),
+        inputs_sha=np.array(sha(multi, ious, feat_in.tar_feat, feat_in.feats_ins_avg)),
+        sel_pred_ious=cap["pred_ious"].numpy(), sel_masks_sha=np.array(sha(cap["lr_masks"])),
+        sel_count=np.array(cap["lr_masks"].shape[0], dtype=np.int64),
+        out_scores=out["scores"].numpy(), out_labels=out["labels"].numpy(), out_bboxes=out["bboxes"].numpy(),
+        out_masks_packed=np.packbits(out["binary_masks"].numpy().reshape(out["binary_masks"].shape[0], -1), axis=-1))
+    print(f"{name}: prompts={n} kept={cap['lr_masks'].shape[0]} K_out={out['scores'].shape[0]}")
+
+
 def run_fill_case(ref, name, spec):
     n_cls, shots, filled, c, seed = spec
     e_side, img_side = 37, 74
@@ -255,6 +326,9 @@ def main():
     for name, spec in NEG_CASES.items():
         if not only or name in only:
             run_neg_case(ref, name, spec)
+    for name, spec in MULTI_CASES.items():
+        if not only or name in only:
+            run_multimask_case(ref, name, spec)
 
 
 if __name__ == "__main__":

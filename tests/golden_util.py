@@ -10,6 +10,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 STAGE_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith("stage_") and f.endswith(".npz"))
 FILL_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith("fill_") and f.endswith(".npz"))
 
+MULTI_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith("stagemm_") and f.endswith(".npz"))
+
 RTOL = 1e-3  # BASELINE.json north_star: pooled features / prototypes / similarities within 1e-3 relative
 
 
@@ -24,6 +26,26 @@ def load_case(name):
         h.update(np.ascontiguousarray(t.numpy()).tobytes())
     assert h.hexdigest() == str(g["inputs_sha"]), "synthetic generator drifted from the golden inputs"
     return g, inp, dict(num_out_instance=num_out, n_cls=n_cls)
+
+
+def load_multimask_case(name):
+    """Candidate-selection golden (real `_forward_sam` + `forward_test` over synthetic RAW decoder output)."""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
+    pps, bs, m, c, n_cls, shots, oh, ow, seed, num_out = g["spec"].tolist()
+    synth = importlib.import_module("no-time-to-train_b200.synth")
+    multi, ious = synth.make_multimask_inputs(pps * pps, m, seed=seed)
+    feat = synth.make_stage_inputs(8, c, n_cls, shots, (oh, ow), seed=seed + 1, clustered=True)
+    h = hashlib.sha256()
+    for t in (multi, ious, feat.tar_feat, feat.feats_ins_avg):
+        h.update(np.ascontiguousarray(t.numpy()).tobytes())
+    assert h.hexdigest() == str(g["inputs_sha"]), "synthetic generator drifted from the golden inputs"
+    cfg = dict(bs=bs, iou_thr=float(g["iou_thr"]), num_out_instance=num_out, n_cls=n_cls, ori_hw=(oh, ow))
+    return g, multi, ious, feat, cfg
+
+
+def sha_f32(t) -> str:
+    a = t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+    return hashlib.sha256(np.ascontiguousarray(a.astype(np.float32)).tobytes()).hexdigest()
 
 
 def sha_bool(t) -> str:

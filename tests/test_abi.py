@@ -37,7 +37,7 @@ def test_header_symbols_all_exported_and_bound(lib):
 
 def test_version_and_error_strings(lib):
     cdll = lib.load()
-    assert cdll.nttt_version() == 100
+    assert cdll.nttt_version() == 101
     assert cdll.nttt_error_string(0) == b"ok"
     assert b"workspace" in cdll.nttt_error_string(-4)
 
@@ -55,7 +55,7 @@ def test_workspace_queries_are_pure_host(lib):
 
 def test_match_args_struct_layout(lib):
     """The ctypes mirror must have the size of the C struct as compiled."""
-    assert ctypes.sizeof(lib.MatchArgs) == lib.load().nttt_sizeof_match_args() == 192
+    assert ctypes.sizeof(lib.MatchArgs) == lib.load().nttt_sizeof_match_args() == 224
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

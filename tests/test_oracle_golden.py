@@ -4,8 +4,8 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import (FILL_CASES, STAGE_CASES, assert_close_rel, assert_same_ranking, load_case, sha_bool,
-                         GOLDEN_DIR)
+from golden_util import (FILL_CASES, MULTI_CASES, STAGE_CASES, assert_close_rel, assert_same_ranking, load_case,
+                         load_multimask_case, sha_bool, sha_f32, GOLDEN_DIR)
 from oracle import nttt_oracle as orc
 from oracle import ref_torch
 
@@ -150,3 +150,39 @@ def test_bank_restatement_matches_reference(name):
     feats_avg, feats_ins_avg = ref_torch.bank_postprocess(bank)
     assert_close_rel(feats_avg.numpy(), g["feats_avg"], rtol=1e-6, what="feats_avg")
     assert_close_rel(feats_ins_avg.numpy(), g["feats_ins_avg"], rtol=1e-6, what="feats_ins_avg")
+
+
+@pytest.mark.parametrize("name", MULTI_CASES)
+def test_candidate_selection_restatements_match_reference(name):
+    """Best-of-3 plane choice + cat + `> iou_thr` (the reference's real `_forward_sam`), then the stage."""
+    g, multi, ious, feat, cfg = load_multimask_case(name)
+    bs = cfg["bs"]
+    chunks = [multi[i:i + bs] for i in range(0, multi.shape[0], bs)]
+    iou_chunks = [ious[i:i + bs] for i in range(0, multi.shape[0], bs)]
+    lr, sc, kept = ref_torch.select_candidates(chunks, iou_chunks, cfg["iou_thr"])
+    assert lr.shape[0] == int(g["sel_count"])
+    assert np.array_equal(sc.numpy(), g["sel_pred_ious"])
+    assert sha_f32(lr) == str(g["sel_masks_sha"])
+    lr_c, sc_c, kept_c = orc.select_candidates(multi.numpy(), ious.numpy(), cfg["iou_thr"])
+    assert np.array_equal(kept_c, kept.numpy()) and np.array_equal(sc_c, g["sel_pred_ious"])
+    assert sha_f32(lr_c) == str(g["sel_masks_sha"])
+    with torch.inference_mode():
+        out = ref_torch.match_image(lr, sc, feat.tar_feat, feat.feats_ins_avg,
+                                    ref_torch.StageConfig(num_out_instance=cfg["num_out_instance"]), cfg["ori_hw"])
+    assert_same_ranking(out["scores"].numpy(), out["labels"].numpy(), g["out_scores"], g["out_labels"], what=name)
+    masks = out["binary_masks"].numpy().astype(np.uint8)
+    assert np.array_equal(np.packbits(masks.reshape(masks.shape[0], -1), axis=-1), g["out_masks_packed"])
+    assert np.array_equal(out["bboxes"].numpy(), g["out_bboxes"])
+
+
+def test_candidate_selection_nan_and_ties():
+    """torch.argmax semantics the kernel must share: first maximal value wins, NaN counts as maximal."""
+    ious = torch.tensor([[0.9, 0.5, 0.5, 0.5], [0.1, 0.2, float("nan"), 0.9], [0.0, float("nan"), float("nan"), 1.0],
+                         [0.3, 0.1, 0.7, 0.7]])
+    multi = torch.arange(4 * 4 * 4, dtype=torch.float32).reshape(4, 4, 2, 2)
+    want = torch.argmax(ious[:, 1:], dim=-1) + 1
+    assert want.tolist() == [1, 2, 1, 2]
+    lr_c, sc_c, kept_c = orc.select_candidates(multi.numpy(), ious.numpy(), 0.4)
+    lr_t, sc_t, kept_t = ref_torch.select_candidates([multi], [ious], 0.4)
+    assert np.array_equal(kept_c, kept_t.numpy()) and kept_c.tolist() == [0, 3]  # NaN > thr is False
+    assert np.array_equal(lr_c, lr_t.numpy())
