@@ -201,6 +201,23 @@ int nttt_unpack_masks(const uint32_t* bits_full, const int32_t* rect, const int3
                       int ow, uint8_t* masks_u8, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * result encoding after the path — COCO compressed RLE of the output masks
+ * replaces: `binary_masks.cpu().numpy()` (105 MB D2H per image, pl_wrapper/sam2matcher_pl.py:144-158) followed by
+ * pycocotools `mask_utils.encode(np.asfortranarray(mask))` per mask (dataset/coco_ref_dataset.py:601-604).
+ * Encodes straight from the packed words; the wire format is pycocotools' rleEncode + rleToString (2.0.8):
+ * column-major runs starting with zeros, then x = cnts[i] - (i > 2 ? cnts[i-2] : 0) in 5-bit groups, chars 48..111.
+ *   slot (nullable) [max_count] : output j encodes packed mask slot[j] (out_slot of nttt_decay_topk); NULL: j
+ *   count [1] i32 (device)      : number of live outputs; rows j >= *count get n_counts = n_chars = 0
+ *   counts  [max_count, cap_counts] u32, n_counts [max_count] i32 : the uncompressed counts and their number m
+ *   chars   [max_count, cap_chars]  u8,  n_chars  [max_count] i32 : the `counts` string (no terminator) and length
+ * Overflow: m > cap_counts -> n_counts = m (the size needed), n_chars = -1, nothing written for that mask;
+ *           length > cap_chars -> n_chars = the length needed, the string is truncated to cap_chars.
+ */
+int nttt_rle_encode(const uint32_t* bits_full, const int32_t* rect, const int32_t* slot, const int32_t* count,
+                    int max_count, int oh, int ow, int cap_counts, int cap_chars, uint32_t* counts, int32_t* n_counts,
+                    uint8_t* chars, int32_t* n_chars, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * a2 / a5 — memory-bank fill and post-process
  * replaces: the raw-feature slot writes of forward_fill_memory (:465-485) and MemoryBank.postprocess
  * (matching_baseline_utils.py:574-599).  Instead of storing raw [n_cls,L,E,C] features the bank keeps the
@@ -271,6 +288,15 @@ typedef struct nttt_match_args {
   const float* const* logits_chunks_host;
   int32_t n_chunks;
   int32_t chunk_prompts;
+  /* fused result encoding (nttt_rle_encode): when rle_chars != NULL the top-`num_out_instance` masks are also emitted
+   * as COCO compressed RLE, and `out_masks` may then be NULL (the dense bool masks are not produced at all).
+   * Shapes as in nttt_rle_encode with max_count = num_out_instance. */
+  uint32_t* rle_counts;
+  int32_t* rle_n_counts;
+  uint8_t* rle_chars;
+  int32_t* rle_n_chars;
+  int32_t rle_cap_counts;
+  int32_t rle_cap_chars;
 } nttt_match_args;
 
 size_t nttt_match_workspace_bytes(int n, int lr_h, int lr_w, int eh, int ew, int c, int n_cls, int ori_h,

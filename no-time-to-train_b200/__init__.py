@@ -7,5 +7,6 @@ from . import _lib, synth  # noqa: F401
 from .matching import MatchingStage, StageConfig  # noqa: F401
 from .memory_bank import MemoryBank  # noqa: F401
 from .model import Sam2MatchingBaselineNoAMG  # noqa: F401
+from .results import encode_results  # noqa: F401
 
-__all__ = ["MatchingStage", "StageConfig", "MemoryBank", "Sam2MatchingBaselineNoAMG", "synth"]
+__all__ = ["MatchingStage", "StageConfig", "MemoryBank", "Sam2MatchingBaselineNoAMG", "encode_results", "synth"]

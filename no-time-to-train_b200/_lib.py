@@ -38,6 +38,8 @@ class MatchArgs(ctypes.Structure):
         ("out_prev_rect", c_void_p),
         ("multi_ious", c_void_p), ("n_multi", c_int32), ("multi_first", c_int32),
         ("logits_chunks_host", POINTER(c_void_p)), ("n_chunks", c_int32), ("chunk_prompts", c_int32),
+        ("rle_counts", c_void_p), ("rle_n_counts", c_void_p), ("rle_chars", c_void_p), ("rle_n_chars", c_void_p),
+        ("rle_cap_counts", c_int32), ("rle_cap_chars", c_int32),
     ]
 
 
@@ -69,6 +71,7 @@ SIGNATURES = {
     "nttt_decay_topk": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P,
                                 _P, _P]),
     "nttt_unpack_masks": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "nttt_rle_encode": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "nttt_fill_pool_accumulate": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "nttt_fill_finalize": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "nttt_match_workspace_bytes": (c_size_t, [c_int] * 10),

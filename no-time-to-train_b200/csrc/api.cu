@@ -42,6 +42,8 @@ int launch_mask_ios(const uint32_t*, const int32_t*, const int32_t*, const int32
 int launch_decay_rank(const float*, const int32_t*, const float*, const int32_t*, const int32_t*, int, int,
                       const int32_t*, const int32_t*, int64_t*, float*, int64_t*, int32_t*, int32_t*, int32_t*, float*,
                       cudaStream_t);
+int launch_rle_encode(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, int, uint32_t*,
+                      int32_t*, uint8_t*, int32_t*, cudaStream_t);
 int launch_fill_pool(const float*, const float*, int, int, int, int, int, float*, float*, float*, cudaStream_t);
 int launch_fill_finalize(const float*, const float*, int, int, int, float*, float*, cudaStream_t);
 
@@ -183,7 +185,7 @@ size_t nttt_sizeof_match_args(void) { return sizeof(nttt_match_args); }
 unsigned long long nttt_launch_count(void) { return g_launches; }
 
 static const char* const kStageNames[] = {"lowres_pack", "project_masks", "pool_gemm", "normalize_rows", "sim_top1",
-                                          "box_nms", "upsample_pack", "mask_ios", "decay_rank", "unpack"};
+                                          "box_nms", "upsample_pack", "mask_ios", "decay_rank", "unpack", "rle_encode"};
 static constexpr int kNumStages = sizeof(kStageNames) / sizeof(kStageNames[0]);
 
 int nttt_profile_num_stages(void) { return kNumStages; }
@@ -494,6 +496,16 @@ int nttt_unpack_masks(const uint32_t* bits_full, const int32_t* rect, const int3
   return launch_unpack(bits_full, rect, nullptr, n_sel, max_sel, oh, ow, masks_u8, (cudaStream_t)stream);
 }
 
+int nttt_rle_encode(const uint32_t* bits_full, const int32_t* rect, const int32_t* slot, const int32_t* count,
+                    int max_count, int oh, int ow, int cap_counts, int cap_chars, uint32_t* counts, int32_t* n_counts,
+                    uint8_t* chars, int32_t* n_chars, void* stream) {
+  if (max_count < 0 || oh <= 0 || ow <= 0 || cap_counts <= 0 || cap_chars <= 0) return NTTT_EINVAL;
+  if (max_count == 0) return NTTT_OK;
+  if (!bits_full || !rect || !count || !counts || !n_counts || !chars || !n_chars) return NTTT_EINVAL;
+  return launch_rle_encode(bits_full, rect, slot, count, max_count, oh, ow, cap_counts, cap_chars, counts, n_counts, chars,
+                           n_chars, (cudaStream_t)stream);
+}
+
 int nttt_fill_pool_accumulate(const float* feat, const float* soft_mask, int mh, int mw, int eh, int ew, int c,
                               float* sum_slot, float* wsum_slot, float* mask_lowres_out, void* stream) {
   if (!feat || !soft_mask || !sum_slot || !wsum_slot || mh <= 0 || mw <= 0 || eh <= 0 || ew <= 0 || c <= 0)
@@ -595,8 +607,11 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   }
   const bool multi = a->n_multi > 1;
   const bool chunked = multi && a->logits_chunks_host;
-  if ((!a->logits && !chunked) || (!multi && !a->pred_ious) || !a->tar_feat || !a->proto || !a->out_masks ||
-      !a->out_boxes || !a->out_scores || !a->out_labels || !a->out_index)
+  const bool want_rle = a->rle_chars != nullptr;
+  if ((!a->logits && !chunked) || (!multi && !a->pred_ious) || !a->tar_feat || !a->proto ||
+      (!a->out_masks && !want_rle) || !a->out_boxes || !a->out_scores || !a->out_labels || !a->out_index)
+    return NTTT_EINVAL;
+  if (want_rle && (!a->rle_counts || !a->rle_n_counts || !a->rle_n_chars || a->rle_cap_counts <= 0 || a->rle_cap_chars <= 0))
     return NTTT_EINVAL;
   if (multi && (!a->multi_ious || a->multi_first < 0 || a->multi_first >= a->n_multi)) return NTTT_EINVAL;
   const int l_neg = a->proto_neg ? a->l_neg : 0;
@@ -675,12 +690,21 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
                               L.area_full,
                               a->out_boxes, a->out_scores, a->out_labels, a->out_index, L.out_slot, a->counts + 2,
                               nullptr, s));
-  if (a->out_prev_rect)
+  if (!a->out_masks)
+    NTTT_MARK();  // RLE-only output: the dense bool masks are never produced
+  else if (a->out_prev_rect)
     NTTT_STEP(launch_unpack_sparse(L.bits_full, L.rect, L.out_slot, a->counts + 2, num_out, a->ori_h, a->ori_w,
                                    a->out_masks, a->out_prev_rect, s));
   else
     NTTT_STEP(launch_unpack(L.bits_full, L.rect, L.out_slot, a->counts + 2, num_out, a->ori_h, a->ori_w, a->out_masks,
                             s));
+  // §8f rank 1: COCO RLE of the outputs straight from the packed words
+  if (want_rle)
+    NTTT_STEP(launch_rle_encode(L.bits_full, L.rect, L.out_slot, a->counts + 2, num_out, a->ori_h, a->ori_w,
+                                a->rle_cap_counts, a->rle_cap_chars, a->rle_counts, a->rle_n_counts, a->rle_chars,
+                                a->rle_n_chars, s));
+  else
+    NTTT_MARK();
 #undef NTTT_STEP
 #undef NTTT_MARK
   return NTTT_OK;

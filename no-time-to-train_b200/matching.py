@@ -23,33 +23,56 @@ class StageConfig:
     enc_hw: tuple = (37, 37)
     expand_ratio: int = 8  # literal at :621
     neg_sigma: float = 0.8  # literal at :596 (compute_sim_global_avg_with_neg(..., sigma=0.8))
+    rle_cap_counts: int = 16384  # per-mask capacity of the fused COCO-RLE output (runs / string bytes)
+    rle_cap_chars: int = 32768
 
 
 class PendingResult:
     """Device-side result of one image; `.get()` does the single D2H read of the counts and slices."""
 
-    def __init__(self, stage, masks, boxes, scores, labels, index, counts, taps, ori_hw, keepalive):
+    def __init__(self, stage, masks, boxes, scores, labels, index, counts, taps, ori_hw, keepalive, rle=None):
         self._stage = stage
         self.masks, self.boxes, self.scores, self.labels, self.index = masks, boxes, scores, labels, index
         self.counts = counts
         self.taps = taps
         self.ori_hw = ori_hw
         self._keepalive = keepalive
+        self.rle = rle  # None or (counts [K,cap] i32, n_counts [K], chars [K,cap] u8, n_chars [K])
+
+    def rle_segmentations(self) -> list:
+        """The outputs as COCO `segmentation` dicts ({"size": [h, w], "counts": str}) — what
+        `mask_utils.encode(np.asfortranarray(mask))` + `.decode("utf-8")` gives in `encode_results`
+        (`dataset/coco_ref_dataset.py:601-604`).  One small D2H read instead of the dense masks."""
+        if self.rle is None:
+            raise RuntimeError("the stage was not asked for RLE output (match_async(..., rle=True))")
+        n_out = int(self.counts.cpu()[2])
+        _, n_counts, chars, n_chars = self.rle
+        lens = n_chars[:n_out].cpu().tolist()
+        need = n_counts[:n_out].cpu().tolist()
+        cap = chars.shape[1]
+        for j, ln in enumerate(lens):
+            if ln < 0 or ln > cap:
+                raise RuntimeError(f"RLE of output {j} does not fit (runs needed {need[j]}, bytes needed {ln}): raise "
+                                   "StageConfig.rle_cap_counts / rle_cap_chars")
+        width = max(lens) if lens else 0
+        host = chars[:n_out, :width].cpu().numpy() if width else None
+        oh, ow = self.ori_hw
+        return [dict(size=[oh, ow], counts=host[j, :lens[j]].tobytes().decode("ascii")) for j in range(n_out)]
 
     def get(self) -> dict:
         counts = self.counts.cpu()  # synchronises with the producing stream
         n_keep, n_sel, n_out = int(counts[0]), int(counts[1]), int(counts[2])
-        dev = self.masks.device
+        dev = self.boxes.device
         oh, ow = self.ori_hw
         if n_sel == 0:
             # the reference's empty early-return uses float32 zero boxes (:647-655)
-            out = dict(binary_masks=torch.zeros((0, oh, ow), device=dev, dtype=torch.bool),
+            out = dict(binary_masks=torch.zeros((0, oh, ow), device=dev, dtype=torch.bool) if self.masks is not None else None,
                        bboxes=torch.zeros((0, 4), device=dev, dtype=torch.float32),
                        scores=torch.zeros((0,), device=dev, dtype=torch.float32),
                        labels=torch.zeros((0,), device=dev, dtype=torch.long))
         else:
-            out = dict(binary_masks=self.masks[:n_out], bboxes=self.boxes[:n_out], scores=self.scores[:n_out],
-                       labels=self.labels[:n_out])
+            out = dict(binary_masks=self.masks[:n_out] if self.masks is not None else None, bboxes=self.boxes[:n_out],
+                       scores=self.scores[:n_out], labels=self.labels[:n_out])
         out["counts"] = dict(n_keep=n_keep, n_sel=n_sel, n_out=n_out)
         out["index"] = self.index[:n_out]
         if self.taps:
@@ -105,14 +128,16 @@ class MatchingStage:
 
     def match_async(self, lr_masks: torch.Tensor, pred_ious: torch.Tensor, tar_feat: torch.Tensor, ori_hw,
                     taps: bool = False, slot=0, iou_thr=None, persistent_out=None, multi_ious=None,
-                    multi_first: int = 1) -> PendingResult:
+                    multi_first: int = 1, rle: bool = False, dense_masks: bool = True) -> PendingResult:
         """Enqueue the whole stage for one image on the current stream.  `slot` selects which reusable
         workspace to use (callers that keep several images in flight on different streams use one slot per
         stream).  `iou_thr`, if given, fuses the reference's candidate filter (`scores_all > iou_thr`,
         `Sam2MatchingBaseline_noAMG.py:428-431`): pass the decoder's full un-compacted masks and scores.
         `multi_ious` [n, m], if given, fuses the best-of-m plane selection (`:295-299`) as well: `lr_masks` is then
         the decoder's raw output — one [n, m, 256, 256] tensor, or the LIST of per-batch tensors the decoder returned
-        (each [testing_point_bs, m, 256, 256]; consumed in place, no `cat`) — and `pred_ious` is ignored (pass None)."""
+        (each [testing_point_bs, m, 256, 256]; consumed in place, no `cat`) — and `pred_ious` is ignored (pass None).
+        `rle=True` also emits the outputs as COCO compressed RLE (`PendingResult.rle_segmentations()`);
+        with `dense_masks=False` the bool masks are not produced at all (`binary_masks` is None)."""
         if self.proto is None:
             raise RuntimeError("Memory is not ready!")  # same text as Sam2MatchingBaseline_noAMG.py:752
         ops._need(tar_feat, torch.float32, "tar_feat")
@@ -143,7 +168,11 @@ class MatchingStage:
         max_sel = int(min(num_out * self.cfg.expand_ratio, n))
         dev = self.device
         prev_rect = None
-        if persistent_out is not None:
+        if not dense_masks:
+            if not rle:
+                raise ValueError("dense_masks=False needs rle=True")
+            masks = None
+        elif persistent_out is not None:
             # outputs owned by the caller and reused call after call: (masks u8 [num_out,oh,ow] zero-initialised,
             # prev_rect i32 [num_out,4] zero-initialised); only the changed rectangles are rewritten
             masks, prev_rect = persistent_out
@@ -173,8 +202,15 @@ class MatchingStage:
         a.ori_h, a.ori_w = oh, ow
         a.nms_thr = float(self.cfg.nms_thr)
         a.num_out_instance, a.max_sel = num_out, max_sel
-        a.out_masks, a.out_boxes, a.out_scores, a.out_labels = (masks.data_ptr(), boxes.data_ptr(),
+        a.out_masks, a.out_boxes, a.out_scores, a.out_labels = (ops._ptr(masks), boxes.data_ptr(),
                                                                 scores.data_ptr(), labels.data_ptr())
+        rle_t = None
+        if rle:
+            k, cc, ch = max(num_out, 1), int(self.cfg.rle_cap_counts), int(self.cfg.rle_cap_chars)
+            rle_t = (torch.empty((k, cc), dtype=torch.int32, device=dev), torch.empty((k,), dtype=torch.int32, device=dev),
+                     torch.empty((k, ch), dtype=torch.uint8, device=dev), torch.empty((k,), dtype=torch.int32, device=dev))
+            a.rle_counts, a.rle_n_counts, a.rle_chars, a.rle_n_chars = (t.data_ptr() for t in rle_t)
+            a.rle_cap_counts, a.rle_cap_chars = cc, ch
         a.out_index, a.counts = index.data_ptr(), counts.data_ptr()
         a.sim = tap_t["sim"].data_ptr() if taps else None
         a.obj_feats = tap_t["obj_feats"].data_ptr() if taps else None
@@ -185,8 +221,8 @@ class MatchingStage:
         a.out_prev_rect = prev_rect.data_ptr() if prev_rect is not None else None
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(self.lib.nttt_match_image(self.ctx, ctypes.byref(a), stream), "nttt_match_image")
-        return PendingResult(self, masks.view(torch.bool), boxes, scores, labels, index, counts, tap_t, (oh, ow),
-                             keepalive=(lr_masks, pred_ious, multi_ious, tar_feat, ws))
+        return PendingResult(self, masks.view(torch.bool) if masks is not None else None, boxes, scores, labels, index,
+                             counts, tap_t, (oh, ow), keepalive=(lr_masks, pred_ious, multi_ious, tar_feat, ws), rle=rle_t)
 
     def profile(self, enable: bool) -> None:
         """Per-stage CUDA-event timing of the next `match_async` calls (see nttt_ctx_profile)."""
@@ -202,9 +238,13 @@ class MatchingStage:
         return {self.lib.nttt_profile_stage_name(i).decode(): float(buf[i]) for i in range(got)}
 
     def match(self, lr_masks, pred_ious, tar_feat, ori_hw, taps: bool = False, iou_thr=None, multi_ious=None,
-              multi_first: int = 1) -> dict:
-        return self.match_async(lr_masks, pred_ious, tar_feat, ori_hw, taps=taps, iou_thr=iou_thr,
-                                multi_ious=multi_ious, multi_first=multi_first).get()
+              multi_first: int = 1, rle: bool = False, dense_masks: bool = True) -> dict:
+        pend = self.match_async(lr_masks, pred_ious, tar_feat, ori_hw, taps=taps, iou_thr=iou_thr,
+                                multi_ious=multi_ious, multi_first=multi_first, rle=rle, dense_masks=dense_masks)
+        out = pend.get()
+        if rle:
+            out["segmentations"] = pend.rle_segmentations()
+        return out
 
     def graphed(self, n: int, c: int, ori_hw, iou_thr=None, key=None, n_multi: int = 0,
                 multi_first: int = 1) -> "GraphedMatch":

@@ -290,6 +290,28 @@ def decay_topk(top_score, labels, ios, sel, n_sel, num_out: int, bits_full, rect
     return out_masks.view(torch.bool), out_boxes, out_scores, out_labels, out_index, out_slot, n_out
 
 
+def rle_encode(bits_full, rect, slot, count, ori_hw, cap_counts: int = 16384, cap_chars: int = 32768, max_count=None):
+    """COCO compressed RLE of packed masks (pycocotools `mask_utils.encode` wire format, column-major).
+    -> counts [max_count, cap_counts] int32 (uint32 bit pattern), n_counts [max_count], chars [max_count, cap_chars]
+    uint8, n_chars [max_count]."""
+    _need(bits_full, torch.int32, "bits_full")
+    _need(rect, torch.int32, "rect")
+    _need(count, torch.int32, "count")
+    oh, ow = ori_hw
+    dev = bits_full.device
+    if max_count is None:
+        max_count = slot.shape[0] if slot is not None else bits_full.shape[0]
+    counts = torch.empty((max_count, cap_counts), dtype=torch.int32, device=dev)
+    n_counts = torch.empty((max_count,), dtype=torch.int32, device=dev)
+    chars = torch.empty((max_count, cap_chars), dtype=torch.uint8, device=dev)
+    n_chars = torch.empty((max_count,), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.nttt_rle_encode(_ptr(bits_full), _ptr(rect), _ptr(slot), _ptr(count), max_count, oh, ow, cap_counts,
+                                   cap_chars, _ptr(counts), _ptr(n_counts), _ptr(chars), _ptr(n_chars), _stream(dev)),
+               "nttt_rle_encode")
+    return counts, n_counts, chars, n_chars
+
+
 def fill_pool_accumulate(feat, soft_mask, enc_hw, sum_slot, wsum_slot, want_mask=False):
     """sum_slot [c] and wsum_slot [1] are accumulated IN PLACE (views into the bank's sum buffers)."""
     _need(feat, torch.float32, "feat")

@@ -16,6 +16,14 @@
  *                            (call site Sam2MatchingBaseline_noAMG.py:624-629; torchvision pinned 0.19.1 by
  *                            pyproject.toml:57, 0.26.0 in this image)
  *   orc_semantic_ios         compute_semantic_ios (matching_baseline_utils.py:831-867)
+ *   orc_rle_*                COCO run-length encoding of the result masks: pycocotools mask_utils.encode
+ *                            (call site dataset/coco_ref_dataset.py:601-604; pycocotools pinned 2.0.8 by
+ *                            pyproject.toml:35, NOT installed in this image and not under /root/reference, so its
+ *                            published maskApi.c algorithm — rleEncode, rleToString, rleFrString — is restated).
+ *                            The counts half is pinned by the reference's own mask_to_rle_pytorch
+ *                            (sam2/utils/amg.py:111-140, golden vectors tests/golden/rle_*.npz); the string half has
+ *                            no reference output to pin against here: PARITY UNPINNED for rleToString (checked
+ *                            structurally: alphabet, decode(encode(x)) == x through the restated rleFrString).
  *
  * Parity pinning: tests/test_oracle_golden.py compares every function here with vectors produced by
  * executing the real reference (tests/golden/make_golden.py).
@@ -270,4 +278,71 @@ void orc_semantic_ios(const uint8_t* masks, int k, size_t hw, const int64_t* lab
     ios[i] = best;
   }
   free(area);
+}
+
+
+/* ---------------------------------------------------------------------------------------------------
+ * COCO RLE (pycocotools maskApi.c, restated).  mask is ROW-major [h, w] u8 as the reference holds it; the
+ * encoder walks it in column-major order (np.asfortranarray at coco_ref_dataset.py:602).
+ * --------------------------------------------------------------------------------------------------- */
+/* rleEncode: alternating run lengths starting with zeros; returns the number of counts (may exceed cap: then only
+ * the first cap counts are stored) */
+long orc_rle_counts(const uint8_t* mask, int h, int w, uint32_t* cnts, long cap) {
+  long m = 0;
+  uint32_t run = 0;
+  uint8_t prev = 0;
+  for (int x = 0; x < w; ++x)
+    for (int y = 0; y < h; ++y) {
+      const uint8_t v = mask[(size_t)y * w + x] != 0;
+      if (v != prev) {
+        if (m < cap) cnts[m] = run;
+        ++m;
+        run = 0;
+        prev = v;
+      }
+      ++run;
+    }
+  if (m < cap) cnts[m] = run;
+  return m + 1;
+}
+
+/* rleToString: x = cnts[i] - (i > 2 ? cnts[i-2] : 0), 5 bits per char, low group first, continuation bit 0x20,
+ * sign carried by bit 0x10 of the last group, chars 48..111; returns the string length (no terminator written) */
+long orc_rle_to_string(const uint32_t* cnts, long m, char* s) {
+  long p = 0;
+  for (long i = 0; i < m; ++i) {
+    long long x = (long long)cnts[i];
+    if (i > 2) x -= (long long)cnts[i - 2];
+    int more = 1;
+    while (more) {
+      char c = (char)(x & 0x1f);
+      x >>= 5;
+      more = (c & 0x10) ? x != -1 : x != 0;
+      if (more) c |= 0x20;
+      c += 48;
+      s[p++] = c;
+    }
+  }
+  return p;
+}
+
+/* rleFrString: the inverse; returns the number of counts */
+long orc_rle_from_string(const char* s, long len, uint32_t* cnts, long cap) {
+  long m = 0, p = 0;
+  while (p < len) {
+    long long x = 0;
+    int k = 0, more = 1;
+    while (more) {
+      const char c = s[p] - 48;
+      x |= (long long)(c & 0x1f) << (5 * k);
+      more = c & 0x20;
+      ++p;
+      ++k;
+      if (!more && (c & 0x10)) x |= -1LL << (5 * k);
+    }
+    if (m > 2) x += (long long)cnts[m - 2];
+    if (m < cap) cnts[m] = (uint32_t)x;
+    ++m;
+  }
+  return m;
 }

@@ -33,6 +33,8 @@ def lib():
         _lib = ctypes.CDLL(build())
         _lib.orc_box_nms.restype = ctypes.c_int
         _lib.orc_aa_max_taps.restype = ctypes.c_int
+        for fn in (_lib.orc_rle_counts, _lib.orc_rle_to_string, _lib.orc_rle_from_string):
+            fn.restype = ctypes.c_long
     return _lib
 
 
@@ -142,6 +144,53 @@ def select_candidates(multi, ious, iou_thr, first=1):
     scores = ious[np.arange(n), best]
     keep = np.nonzero(scores > np.float32(iou_thr))[0]
     return multi[keep, best[keep]], scores[keep], keep
+
+
+def rle_counts(mask):
+    """pycocotools rleEncode of one [h, w] mask (column-major runs, zeros first) -> uint32 counts."""
+    mask = np.ascontiguousarray(np.asarray(mask).astype(np.uint8))
+    h, w = mask.shape
+    cap = 1024
+    while True:
+        cnts = np.empty(cap, np.uint32)
+        m = lib().orc_rle_counts(_p(mask), h, w, _p(cnts), ctypes.c_long(cap))
+        if m <= cap:
+            return cnts[:m].copy()
+        cap = int(m)
+
+
+def rle_to_string(cnts) -> bytes:
+    """pycocotools rleToString."""
+    cnts = np.ascontiguousarray(cnts, dtype=np.uint32)
+    buf = ctypes.create_string_buffer(7 * max(len(cnts), 1))
+    n = lib().orc_rle_to_string(_p(cnts), ctypes.c_long(len(cnts)), buf)
+    return buf.raw[:n]
+
+
+def rle_from_string(s: bytes):
+    """pycocotools rleFrString."""
+    cnts = np.empty(max(len(s), 1), np.uint32)
+    m = lib().orc_rle_from_string(ctypes.c_char_p(s), ctypes.c_long(len(s)), _p(cnts), ctypes.c_long(len(cnts)))
+    return cnts[:m].copy()
+
+
+def rle_decode(cnts, hw):
+    """runs -> [h, w] bool mask (column-major), as `rle_to_mask` (sam2/utils/amg.py:143-154)."""
+    h, w = hw
+    flat = np.zeros(h * w, dtype=bool)
+    pos, val = 0, False
+    for c in np.asarray(cnts, dtype=np.int64):
+        flat[pos:pos + c] = val
+        pos += int(c)
+        val = not val
+    assert pos == h * w
+    return flat.reshape(w, h).T
+
+
+def encode_mask(mask) -> dict:
+    """`mask_utils.encode(np.asfortranarray(mask))` with `counts` decoded to str (coco_ref_dataset.py:601-604)."""
+    mask = np.asarray(mask)
+    return dict(size=[int(mask.shape[0]), int(mask.shape[1])], counts=rle_to_string(rle_counts(mask)).decode("ascii"))
 
 
 def l2_normalize(x, eps=1e-12):

@@ -262,6 +262,49 @@ def run_multimask_case(ref, name, spec):
     print(f"{name}: prompts={n} kept={cap['lr_masks'].shape[0]} K_out={out['scores'].shape[0]}")
 
 
+def rle_special_masks():
+    """Small masks covering the run-length edge cases: empty, full, first/last pixel set, runs that wrap from the
+    bottom of one column into the top of the next, a checkerboard (one run per pixel), widths off the 32-pixel grid."""
+    gen = torch.Generator().manual_seed(77)
+    out = {}
+    out["zeros_9x13"] = torch.zeros(9, 13, dtype=torch.bool)
+    out["ones_9x13"] = torch.ones(9, 13, dtype=torch.bool)
+    m = torch.zeros(40, 70, dtype=torch.bool); m[0, 0] = True; out["first_pixel"] = m
+    m = torch.zeros(40, 70, dtype=torch.bool); m[-1, -1] = True; out["last_pixel"] = m
+    m = torch.zeros(64, 96, dtype=torch.bool); m[:, 10:20] = True; m[0:5, 40:45] = True; m[60:, 40:45] = True
+    out["column_wrap"] = m
+    yy, xx = torch.meshgrid(torch.arange(33), torch.arange(47), indexing="ij")
+    out["checker_33x47"] = ((yy + xx) % 2 == 0)
+    out["noise_100x75"] = torch.rand(100, 75, generator=gen) > 0.7
+    m = torch.zeros(300, 500, dtype=torch.bool); m[20:280, 31:470] = True; m[100:120, 200:260] = False
+    out["blob_300x500"] = m
+    return out
+
+
+def run_rle_golden(ref):
+    """Counts from the reference's own uncompressed-RLE encoder `mask_to_rle_pytorch` (sam2/utils/amg.py:111-140),
+    "in the format expected by pycoco tools": on the special masks and on the output masks of the stage cases."""
+    amg = importlib.import_module("sam2.utils.amg")
+    store = {}
+    for name, m in rle_special_masks().items():
+        rle = amg.mask_to_rle_pytorch(m[None])[0]
+        assert np.array_equal(amg.rle_to_mask(rle), m.numpy())
+        store["special__" + name + "__mask"] = np.packbits(m.numpy().reshape(-1))
+        store["special__" + name + "__hw"] = np.array(m.shape, dtype=np.int64)
+        store["special__" + name + "__counts"] = np.array(rle["counts"], dtype=np.int64)
+    for case in ("stage_a_1024_degenerate", "stage_b_480x640", "stage_f_truncate_333x500", "stage_d_200x180_downscale"):
+        g = np.load(os.path.join(HERE, case + ".npz"))
+        oh, ow = int(g["spec"][4]), int(g["spec"][5])
+        k = g["out_masks_packed"].shape[0]
+        masks = np.unpackbits(g["out_masks_packed"], axis=-1)[:, :oh * ow].reshape(k, oh, ow).astype(bool)
+        rles = amg.mask_to_rle_pytorch(torch.from_numpy(masks))
+        flat = np.concatenate([np.array(r["counts"], dtype=np.int64) for r in rles]) if k else np.zeros(0, np.int64)
+        store["stage__" + case + "__counts"] = flat
+        store["stage__" + case + "__lens"] = np.array([len(r["counts"]) for r in rles], dtype=np.int64)
+        print(f"rle {case}: {k} masks, {flat.size} counts")
+    np.savez_compressed(os.path.join(HERE, "rle_counts.npz"), **store)
+
+
 def run_fill_case(ref, name, spec):
     n_cls, shots, filled, c, seed = spec
     e_side, img_side = 37, 74
@@ -329,6 +372,8 @@ def main():
     for name, spec in MULTI_CASES.items():
         if not only or name in only:
             run_multimask_case(ref, name, spec)
+    if not only or "rle" in only:
+        run_rle_golden(ref)
 
 
 if __name__ == "__main__":
