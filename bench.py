@@ -315,6 +315,49 @@ def main():
     ms_e2e, _, _ = timed(e2e_step, e2e_steps)
     e2e_value = world * e2e_steps * B / (ms_e2e / 1e3)
 
+    # ---- e2e_rle: same, but the result leaves the device as COCO RLE strings (fused nttt_rle_encode) instead of the
+    # dense bool masks: what the reference's _output_inqueue/encode_results ultimately produce
+    e2e_rle = None
+    if use_graph:
+        cap_chars = stage.cfg.rle_cap_chars
+        rle_host = [dict(chars=torch.empty((n_out, cap_chars), dtype=torch.uint8).pin_memory(),
+                         n_chars=torch.empty((n_out,), dtype=torch.int32).pin_memory(),
+                         boxes=torch.empty((n_out, 4), dtype=torch.int64).pin_memory(),
+                         scores=torch.empty((n_out,), dtype=torch.float32).pin_memory(),
+                         labels=torch.empty((n_out,), dtype=torch.int64).pin_memory(),
+                         counts=torch.empty((4,), dtype=torch.int32).pin_memory()) for _ in range(S)]
+        rle_graphs = []
+        for k in range(S):
+            g = stage.graphed(args.n_masks, WORKLOAD["feat_dim"], ori_hw, key=("e2e_rle", k), rle=True, dense_masks=False)
+            g.lr_masks, g.pred_ious, g.tar_feat = dev_in[k]
+            rle_graphs.append(g.capture())
+        d2h_rle = sum(t.numel() * t.element_size() for t in rle_host[0].values()) * B
+
+        def e2e_rle_step():
+            for i in range(B):
+                k = i % S
+                with torch.cuda.stream(streams[k]):
+                    for dst, src in zip(dev_in[k], host[i]):
+                        dst.copy_(src, non_blocking=True)
+                    p = rle_graphs[k].replay()
+                    oh = rle_host[k]
+                    oh["chars"].copy_(p.rle[2], non_blocking=True)
+                    oh["n_chars"].copy_(p.rle[3], non_blocking=True)
+                    oh["boxes"].copy_(p.boxes, non_blocking=True)
+                    oh["scores"].copy_(p.scores, non_blocking=True)
+                    oh["labels"].copy_(p.labels, non_blocking=True)
+                    oh["counts"].copy_(p.counts, non_blocking=True)
+
+        for _ in range(2):
+            e2e_rle_step()
+        torch.cuda.synchronize(dev)
+        ms_rle, _, _ = timed(e2e_rle_step, e2e_steps)
+        n_live = int(rle_host[0]["counts"][2])
+        lens = rle_host[0]["n_chars"][:n_live]
+        e2e_rle = dict(value=world * e2e_steps * B / (ms_rle / 1e3), unit=UNIT, h2d_bytes_per_step=h2d,
+                       d2h_bytes_per_step=d2h_rle, steps=e2e_steps,
+                       rle_bytes_per_image=int(lens.sum()), rle_overflow=bool((lens < 0).any() or (lens > cap_chars).any()))
+
     # ---- per-stage share (single stream, CUDA events between the stage's kernels) and the roofline kernel --
     stage_ms = {}
     roofline = None
@@ -389,7 +432,7 @@ def main():
                     us_per_image=1e3 * ms_total / (args.steps * B),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              steps=e2e_steps),
-                    gpu_launches=int(launches), clocks=clock_info, roofline=roofline, cpu_baseline=cpu_baseline,
+                    e2e_rle=e2e_rle, gpu_launches=int(launches), clocks=clock_info, roofline=roofline, cpu_baseline=cpu_baseline,
                     stage_us_per_image={k: 1e3 * v for k, v in stage_ms.items()},
                     stage_roofline=stage_floor(args.n_masks, 1e3 * ms_total / (args.steps * B)))
         print(json.dumps(line))

@@ -247,10 +247,11 @@ class MatchingStage:
         return out
 
     def graphed(self, n: int, c: int, ori_hw, iou_thr=None, key=None, n_multi: int = 0,
-                multi_first: int = 1) -> "GraphedMatch":
+                multi_first: int = 1, rle: bool = False, dense_masks: bool = True) -> "GraphedMatch":
         """A CUDA-graph capture of the whole stage at fixed shapes with static input/output buffers.
-        n_multi > 1: the static mask buffer is the decoder's raw [n, n_multi, 256, 256] output (+ `multi_ious`)."""
-        return GraphedMatch(self, n, c, ori_hw, iou_thr, key, n_multi, multi_first)
+        n_multi > 1: the static mask buffer is the decoder's raw [n, n_multi, 256, 256] output (+ `multi_ious`).
+        rle / dense_masks: as in `match_async`."""
+        return GraphedMatch(self, n, c, ori_hw, iou_thr, key, n_multi, multi_first, rle, dense_masks)
 
 
 class GraphedMatch:
@@ -263,7 +264,7 @@ class GraphedMatch:
     again.  Replay costs one graph launch on the host instead of ~18 kernel launches."""
 
     def __init__(self, stage: MatchingStage, n: int, c: int, ori_hw, iou_thr=None, key=None, n_multi: int = 0,
-                 multi_first: int = 1):
+                 multi_first: int = 1, rle: bool = False, dense_masks: bool = True):
         dev = stage.device
         eh, ew = stage.cfg.enc_hw
         self.stage = stage
@@ -276,6 +277,7 @@ class GraphedMatch:
             self.pred_ious = torch.zeros((n,), dtype=torch.float32, device=dev)
             self.multi_ious = None
         self.multi_first = multi_first
+        self._kw = dict(rle=rle, dense_masks=dense_masks)
         self.tar_feat = torch.zeros((eh * ew, c), dtype=torch.float32, device=dev)
         self.ori_hw = (int(ori_hw[0]), int(ori_hw[1]))
         self.iou_thr = iou_thr
@@ -284,7 +286,7 @@ class GraphedMatch:
         # persistent outputs: the mask buffer is zeroed once; afterwards every replay rewrites only the rectangles
         # that change (nttt_match_args.out_prev_rect)
         self._out = (torch.zeros((num_out, self.ori_hw[0], self.ori_hw[1]), dtype=torch.uint8, device=dev),
-                     torch.zeros((num_out, 4), dtype=torch.int32, device=dev))
+                     torch.zeros((num_out, 4), dtype=torch.int32, device=dev)) if dense_masks else None
         self.graph = None
         self.pending = None
 
@@ -296,14 +298,14 @@ class GraphedMatch:
             for _ in range(2):
                 self.stage.match_async(self.lr_masks, self.pred_ious, self.tar_feat, self.ori_hw, slot=self._slot,
                                        iou_thr=self.iou_thr, persistent_out=self._out, multi_ious=self.multi_ious,
-                                       multi_first=self.multi_first)
+                                       multi_first=self.multi_first, **self._kw)
         torch.cuda.current_stream(self.stage.device).wait_stream(side)
         torch.cuda.synchronize(self.stage.device)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.pending = self.stage.match_async(self.lr_masks, self.pred_ious, self.tar_feat, self.ori_hw,
                                                   slot=self._slot, iou_thr=self.iou_thr, persistent_out=self._out,
-                                                  multi_ious=self.multi_ious, multi_first=self.multi_first)
+                                                  multi_ious=self.multi_ious, multi_first=self.multi_first, **self._kw)
         return self
 
     def replay(self) -> PendingResult:
