@@ -104,6 +104,9 @@ struct AxisTable {
   // rows of one group read the same input rows, so the horizontal pass and the footprint test are shared
   int32_t* grp_of = nullptr;     // [out]  group index of each output coordinate
   int32_t* grp_start = nullptr;  // [out + 1] first coordinate of each group, grp_start[n_groups] = out
+  // one 128-bit record per output coordinate when taps <= 3 (every up-scaling): {xmin | xsize << 16, w0, w1, w2},
+  // weights beyond xsize are 0; padded with all-zero records (xsize = 0) up to a multiple of 32 coordinates
+  float4* pk = nullptr;          // [align32(out)] or nullptr
 };
 constexpr int kGrpMax = 4;
 constexpr int kMaxScatter = 24;

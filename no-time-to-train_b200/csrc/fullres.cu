@@ -17,7 +17,8 @@
 namespace nttt {
 
 constexpr int kUpThreads = 256;
-constexpr int kUpSplit = 4;  // CTAs per mask (rows interleaved)
+constexpr int kUpMaxSplit = 8;       // grid.x: CTAs available per mask; a mask uses ceil(groups / kUpGroupsPerCta) of them
+constexpr int kUpGroupsPerCta = 32;  // row groups per CTA = 4 per warp: amortises the per-CTA / per-warp set-up
 
 struct UpTables {
   const int32_t* xmin; const int32_t* xsize; const float* wx; int tx;
@@ -25,6 +26,7 @@ struct UpTables {
   const int32_t* x_tlo; const int32_t* x_tlen;  // input col -> output range
   const int32_t* y_tlo; const int32_t* y_tlen;  // input row -> output range
   const int32_t* y_grp_of; const int32_t* y_grp_start;  // output rows grouped by identical input span
+  const float4* pk_x; const float4* pk_y;  // packed {min | size << 16, w0, w1, w2} records (taps <= 3), else nullptr
 };
 
 // acc = s0*w0; acc = fma(s_j, w_j, acc)
@@ -34,22 +36,21 @@ __device__ __forceinline__ float aa_dot(const float* __restrict__ src, int strid
   return acc;
 }
 
-// scratch per mask (zero-initialised by the launcher): {area, maxx+1, maxy+1, BIG-minx, BIG-miny, done}
+// scratch per mask (zero-initialised by the meta kernel): {area, maxx+1, maxy+1, BIG-minx, BIG-miny, done}
 constexpr int kScratchInts = 8;
 constexpr int kBig = 1 << 30;
-constexpr int kTapsReg = 4;
-constexpr int kXtWords = 32;  // widest rect (in 32-pixel words) whose horizontal constants are staged in smem  // footprints of up to 4 input rows keep their horizontal-pass values in registers
+constexpr int kTapsReg = 4;  // footprints of up to 4 input rows keep their horizontal-pass values in registers
 
-// per selected mask, resolved once by a tiny pre-kernel so that the four CTAs of a mask do not each chase
+// per selected mask, resolved once by a tiny pre-kernel so that the CTAs of a mask do not each chase
 // sel[] -> box_lr[] -> span tables; scratch[kScratchInts*k + 6..7] is unused padding
 struct alignas(16) UpMeta {  // 48 bytes: three 128-bit loads
   const float* logits;  // the candidate's [ih, iw] logits
-  int src;           // index into bits_lr / box_lr (candidate number)
-  int r0, r1;        // output rows [r0, r1)
-  int w0, w1;        // output words [w0, w1)
-  int lr0, lr1;      // low-res rows [lr0, lr1) under those output rows
-  int safe;          // flags bit0
-  int pad_[2];
+  int src;              // index into bits_lr / box_lr (candidate number)
+  int safe;             // flags bit0
+  int r0, r1;           // output rows [r0, r1)
+  int w0, w1;           // output words [w0, w1)
+  int lr0, lr1;         // low-res rows [lr0, lr1) under those output rows
+  int g0, g1;           // row groups [g0, g1) covering [r0, r1)
 };
 
 __global__ void __launch_bounds__(256)
@@ -69,7 +70,7 @@ upsample_meta_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
   const int4 b = reinterpret_cast<const int4*>(box_lr)[m.src];
   // empty low-res mask <=> box all zero AND bit (0,0) clear
   const bool lr_empty = (b.x | b.y | b.z | b.w) == 0 && (bits_lr[(size_t)m.src * ih * (iw >> 5)] & 1u) == 0;
-  m.r0 = m.r1 = m.w0 = m.w1 = m.lr0 = m.lr1 = 0;
+  m.r0 = m.r1 = m.w0 = m.w1 = m.lr0 = m.lr1 = m.g0 = m.g1 = 0;
   if (!lr_empty) {
     m.r0 = t.y_tlo[b.y];
     m.r1 = t.y_tlo[b.w] + t.y_tlen[b.w];
@@ -77,61 +78,66 @@ upsample_meta_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
     const int c1 = t.x_tlo[b.z] + t.x_tlen[b.z];
     m.w0 = c0 >> 5;
     m.w1 = (c1 + 31) >> 5;
-    m.lr0 = t.ymin[m.r0];
-    m.lr1 = t.ymin[m.r1 - 1] + t.ysize[m.r1 - 1];
+    if (m.r1 > m.r0) {
+      m.lr0 = t.ymin[m.r0];
+      m.lr1 = t.ymin[m.r1 - 1] + t.ysize[m.r1 - 1];
+      m.g0 = t.y_grp_of[m.r0];
+      m.g1 = t.y_grp_of[m.r1 - 1] + 1;
+    }
   }
   m.safe = flags_lr[m.src] & 1;
   meta[k] = m;
   reinterpret_cast<int4*>(rect)[k] = make_int4(m.r0, m.r1, m.w0, m.w1);
 }
 
+__device__ __forceinline__ int up_ctas_needed(int n_groups) {
+  return max(1, min(kUpMaxSplit, (n_groups + kUpGroupsPerCta - 1) / kUpGroupsPerCta));
+}
+
+// grid (kUpMaxSplit, max_sel).  A mask with G row groups is served by ceil(G / 32) CTAs (the others exit at once); a
+// CTA takes 32 consecutive groups, warp w the groups w, w+8, w+16, w+24 of them; a lane owns one 32-pixel output word
+// column.  Per group: the footprint test on the low-res bits (shared memory) classifies each word as all-0, all-1 or
+// mixed; mixed words are evaluated one at a time with lane = pixel: horizontal pass of the shared input rows once,
+// vertical pass per output row, one ballot per row.
 __global__ void __launch_bounds__(kUpThreads, 4)
-upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restrict__ bits_lr,
-                     const UpMeta* __restrict__ meta, int ih, int iw, const int32_t* __restrict__ n_sel, int max_sel,
-                     int oh, int ow, UpTables t, uint32_t* __restrict__ bits_full, int32_t* __restrict__ area_full,
-                     int32_t* __restrict__ box_full, int32_t* __restrict__ scratch) {
-  extern __shared__ uint32_t s_lr[];  // packed low-res bits of this mask, rows [lr0, lr1) only
+upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restrict__ meta, int ih, int iw,
+                     const int32_t* __restrict__ n_sel, int max_sel, int oh, int ow, UpTables t,
+                     uint32_t* __restrict__ bits_full, int32_t* __restrict__ area_full, int32_t* __restrict__ box_full,
+                     int32_t* __restrict__ scratch) {
+  extern __shared__ uint32_t s_lr[];  // packed low-res bits of this mask, rows [clr0, clr1) only
   __shared__ int s_red[5];
   const int k = blockIdx.y;
-  const int nsel = min(*n_sel, max_sel);
-  if (k >= nsel) return;
+  if (k >= min(*n_sel, max_sel)) return;
   const UpMeta mt = meta[k];
-  const int src_idx = mt.src;
+  const int n_groups = mt.g1 - mt.g0;
+  const int needed = up_ctas_needed(n_groups);
+  if ((int)blockIdx.x >= needed) return;
   const int lr_wpr = iw >> 5;
   const int ow_words = (ow + 31) >> 5;
   const int lane = lane_id(), warp = warp_id();
   constexpr int kWarps = kUpThreads / 32;
   const int r0 = mt.r0, r1 = mt.r1, w0 = mt.w0, w1 = mt.w1;
+  const int chunk0 = mt.g0 + blockIdx.x * kUpGroupsPerCta;       // first group of this CTA's first chunk
+  const bool one_chunk = needed * kUpGroupsPerCta >= n_groups;   // (false only beyond 256 groups)
 
-  const uint32_t* lr = bits_lr + ((size_t)src_idx * ih + mt.lr0) * lr_wpr;
-  for (int i = threadIdx.x; i < (mt.lr1 - mt.lr0) * lr_wpr; i += kUpThreads) s_lr[i] = lr[i];
-  // per-pixel horizontal constants of the mask's columns, one 128-bit LDS per use: {xmin | xsize << 16, w0, w1, w2}
-  // (xsize = 0 marks pixels beyond the image width).  Only when spans have <= 3 taps and the rect is <= 32 words.
-  float4* s_xt = reinterpret_cast<float4*>(s_lr + ih * lr_wpr);
-  const bool fast_x = t.tx <= 3 && (w1 - w0) <= kXtWords;
-  if (fast_x)
-    for (int i = threadIdx.x; i < (w1 - w0) * 32; i += kUpThreads) {
-      const int x = (w0 << 5) + i;
-      float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (x < ow) {
-        const int cs = t.xsize[x];
-        const float* wx = t.wx + (size_t)x * t.tx;
-        e.x = __int_as_float(t.xmin[x] | (cs << 16));
-        e.y = wx[0];
-        e.z = cs > 1 ? wx[1] : 0.0f;
-        e.w = cs > 2 ? wx[2] : 0.0f;
-      }
-      s_xt[i] = e;
-    }
+  // low-res rows under this CTA's groups
+  int clr0 = mt.lr0, clr1 = mt.lr1;
+  if (one_chunk && chunk0 < mt.g1) {
+    const int gl = min(chunk0 + kUpGroupsPerCta, mt.g1);
+    const int ya = max(t.y_grp_start[chunk0], r0), yb = min(t.y_grp_start[gl], r1);
+    clr0 = t.ymin[ya];
+    clr1 = t.ymin[yb - 1] + t.ysize[yb - 1];
+  }
+  const uint32_t* lr = bits_lr + ((size_t)mt.src * ih + clr0) * lr_wpr;
+  for (int i = threadIdx.x; i < (clr1 - clr0) * lr_wpr; i += kUpThreads) s_lr[i] = lr[i];
   if (threadIdx.x < 5) s_red[threadIdx.x] = 0;
+  const bool fast_cfg = t.pk_x != nullptr && t.pk_y != nullptr;  // <= 3 taps on both axes
   const bool safe = mt.safe != 0;
   const float* src = mt.logits;
   uint32_t* dst = bits_full + (size_t)k * oh * ow_words;
   __syncthreads();
 
   int area = 0, minx = kBig, maxx = -1, miny = kBig, maxy = -1;
-  const int g0 = r1 > r0 ? t.y_grp_of[r0] : 0;
-  const int g1 = r1 > r0 ? t.y_grp_of[r1 - 1] + 1 : 0;
   for (int wbase = w0; wbase < w1; wbase += 32) {
     // per-lane (= per output word) constants, hoisted out of the row-group loop
     const int wi = wbase + lane;
@@ -151,140 +157,147 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
       if (hi1 > 0) m1 = hi1 >= 32 ? 0xffffffffu : ((1u << hi1) - 1u);
     }
     uint32_t colbits = 0;
-  for (int g = g0 + blockIdx.x * kWarps + warp; g < g1; g += kUpSplit * kWarps) {
-    // rows [ya, yb) of this group share the input rows [ry0, ry0 + rys)
-    const int ya = max(t.y_grp_start[g], r0), yb = min(t.y_grp_start[g + 1], r1);
-    const int nrows = yb - ya;
-    const int ry0 = t.ymin[ya], rys = t.ysize[ya];
-    const bool fast = fast_x && rys <= 3;
-    float wyv[kGrpMax][3];  // vertical weights of the group's rows (warp-uniform), fast path only
+    for (int cb = chunk0; cb < mt.g1; cb += needed * kUpGroupsPerCta) {
+      const int cend = min(cb + kUpGroupsPerCta, mt.g1);
+      for (int g = cb + warp; g < cend; g += kWarps) {
+        // rows [ya, yb) of this group share the input rows [ry0, ry0 + rys)
+        const int ya = max(t.y_grp_start[g], r0), yb = min(t.y_grp_start[g + 1], r1);
+        const int nrows = yb - ya;
+        int ry0, rys;
+        float4 wv[kGrpMax];  // fast path: {., w0, w1, w2} of the group's rows (rows past nrows repeat the last one)
+        if (fast_cfg) {
 #pragma unroll
-    for (int j = 0; j < kGrpMax; ++j)
-#pragma unroll
-      for (int r = 0; r < 3; ++r) wyv[j][r] = (fast && j < nrows && r < rys) ? __ldg(t.wy + (size_t)(ya + j) * t.ty + r) : 0.0f;
-    const float* rowbase = src + (size_t)ry0 * iw;
-    {
-      uint32_t words[kGrpMax];
-#pragma unroll
-      for (int j = 0; j < kGrpMax; ++j) words[j] = 0;
-      bool mixed = false;
-      if (active) {
-        bool all0 = true, all1 = true;
-        if (two_words) {
-          for (int r = 0; r < rys; ++r) {
-            const uint32_t* row = s_lr + (ry0 + r - mt.lr0) * lr_wpr + cw0;
-            const uint32_t v0 = row[0] & m0;
-            const uint32_t v1 = m1 ? (row[1] & m1) : 0u;
-            all0 = all0 && ((v0 | v1) == 0);
-            all1 = all1 && (v0 == m0) && (v1 == m1);
-          }
+          for (int j = 0; j < kGrpMax; ++j) wv[j] = __ldg(t.pk_y + min(ya + j, yb - 1));
+          const int pky = __float_as_int(wv[0].x);
+          ry0 = pky & 0xffff;
+          rys = pky >> 16;
         } else {
-          for (int r = 0; r < rys; ++r) {
-            const uint32_t* row = s_lr + (ry0 + r - mt.lr0) * lr_wpr;
-            for (int cw = cw0; cw <= (c1 - 1) >> 5; ++cw) {
-              const int lo = max(c0 - (cw << 5), 0), hi = min(c1 - (cw << 5), 32);
-              const uint32_t m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-              const uint32_t v = row[cw] & m;
-              all0 = all0 && (v == 0);
-              all1 = all1 && (v == m);
+          ry0 = t.ymin[ya];
+          rys = t.ysize[ya];
+        }
+        const float* rowbase = src + (size_t)ry0 * iw;
+        uint32_t words[kGrpMax];
+#pragma unroll
+        for (int j = 0; j < kGrpMax; ++j) words[j] = 0;
+        bool mixed = false;
+        if (active) {
+          bool all0 = true, all1 = true;
+          if (two_words) {
+            for (int r = 0; r < rys; ++r) {
+              const uint32_t* row = s_lr + (ry0 + r - clr0) * lr_wpr + cw0;
+              const uint32_t v0 = row[0] & m0;
+              const uint32_t v1 = m1 ? (row[1] & m1) : 0u;
+              all0 = all0 && ((v0 | v1) == 0);
+              all1 = all1 && (v0 == m0) && (v1 == m1);
+            }
+          } else {
+            for (int r = 0; r < rys; ++r) {
+              const uint32_t* row = s_lr + (ry0 + r - clr0) * lr_wpr;
+              for (int cw = cw0; cw <= (c1 - 1) >> 5; ++cw) {
+                const int lo = max(c0 - (cw << 5), 0), hi = min(c1 - (cw << 5), 32);
+                const uint32_t m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+                const uint32_t v = row[cw] & m;
+                all0 = all0 && (v == 0);
+                all1 = all1 && (v == m);
+              }
             }
           }
-        }
-        if (all1 && safe && !all0) {
+          if (all1 && safe && !all0) {
 #pragma unroll
-          for (int j = 0; j < kGrpMax; ++j) words[j] = valid;
-        } else if (!all0) {
-          mixed = true;
-        }
-      }
-      uint32_t todo = __ballot_sync(kFull, mixed);
-      while (todo) {
-        const int src_lane = __ffs(todo) - 1;
-        todo &= todo - 1;
-        if (fast) {
-          // all horizontal constants in one LDS; taps beyond cs are never read, so the arithmetic is exactly
-          // acc = s0*w0; acc = fma(s_j, w_j, acc) for j < cs, then the same over the rys input rows
-          const float4 xt = s_xt[((wbase + src_lane - w0) << 5) + lane];
-          const int pk = __float_as_int(xt.x);
-          const int cx = pk & 0xffff, cs = pk >> 16;
-          const float* p = rowbase + cx;
-          float T[3];
-#pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            float acc = 0.0f;
-            if (r < rys && cs > 0) {
-              const float* q = p + (size_t)r * iw;
-              acc = __fmul_rn(__ldg(q), xt.y);
-              if (cs > 1) acc = __fmaf_rn(__ldg(q + 1), xt.z, acc);
-              if (cs > 2) acc = __fmaf_rn(__ldg(q + 2), xt.w, acc);
-            }
-            T[r] = acc;
+            for (int j = 0; j < kGrpMax; ++j) words[j] = valid;
+          } else if (!all0) {
+            mixed = true;
           }
+        }
+        uint32_t todo = __ballot_sync(kFull, mixed);
+        while (todo) {
+          const int src_lane = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int x = ((wbase + src_lane) << 5) + lane;
+          if (fast_cfg) {
+            // Every constant of the pixel in one 128-bit load (records past the width have size 0).  Taps beyond the
+            // span are never read; rows / taps beyond it contribute fma(0, 0, acc) = acc, so the arithmetic is exactly
+            // acc = s0*w0; acc = fma(s_j, w_j, acc) for j < size, horizontally and then vertically.
+            const float4 xt = __ldg(t.pk_x + x);
+            const int pk = __float_as_int(xt.x);
+            const int cx = pk & 0xffff, cs = pk >> 16;
+            const float* p = rowbase + cx;
+            float T[3];
 #pragma unroll
-          for (int j = 0; j < kGrpMax; ++j) {
-            if (j < nrows) {
-              float acc = __fmul_rn(T[0], wyv[j][0]);
-              if (rys > 1) acc = __fmaf_rn(T[1], wyv[j][1], acc);
-              if (rys > 2) acc = __fmaf_rn(T[2], wyv[j][2], acc);
+            for (int r = 0; r < 3; ++r) {
+              float acc = 0.0f;
+              if (r < rys && cs > 0) {
+                const float* q = p + (size_t)r * iw;
+                acc = __fmul_rn(__ldg(q), xt.y);
+                if (cs > 1) acc = __fmaf_rn(__ldg(q + 1), xt.z, acc);
+                if (cs > 2) acc = __fmaf_rn(__ldg(q + 2), xt.w, acc);
+              }
+              T[r] = acc;
+            }
+#pragma unroll
+            for (int j = 0; j < kGrpMax; ++j) {
+              float acc = __fmul_rn(T[0], wv[j].y);
+              acc = __fmaf_rn(T[1], wv[j].z, acc);
+              acc = __fmaf_rn(T[2], wv[j].w, acc);
               const uint32_t res = __ballot_sync(kFull, cs > 0 && acc > 0.0f);
               if (lane == src_lane) words[j] = res;
             }
+            continue;
           }
-          continue;
-        }
-        const int x = ((wbase + src_lane) << 5) + lane;
-        const bool inb = x < ow;
-        const int cx = inb ? t.xmin[x] : 0, cs = inb ? t.xsize[x] : 1;
-        const float* wx = t.wx + (size_t)(inb ? x : 0) * t.tx;
-        const float* p = src + (size_t)ry0 * iw + cx;
-        if (rys <= kTapsReg) {
-          // horizontal pass once per group, vertical pass per row
-          float T[kTapsReg];
+          const bool inb = x < ow;
+          const int cx = inb ? t.xmin[x] : 0, cs = inb ? t.xsize[x] : 1;
+          const float* wx = t.wx + (size_t)(inb ? x : 0) * t.tx;
+          const float* p = rowbase + cx;
+          if (rys <= kTapsReg) {
+            // horizontal pass once per group, vertical pass per row
+            float T[kTapsReg];
 #pragma unroll
-          for (int r = 0; r < kTapsReg; ++r) T[r] = (r < rys && inb) ? aa_dot(p + (size_t)r * iw, 1, wx, cs) : 0.0f;
+            for (int r = 0; r < kTapsReg; ++r) T[r] = (r < rys && inb) ? aa_dot(p + (size_t)r * iw, 1, wx, cs) : 0.0f;
 #pragma unroll
-          for (int j = 0; j < kGrpMax; ++j) {
-            if (j < nrows) {
-              const float* wy = t.wy + (size_t)(ya + j) * t.ty;
-              float acc = __fmul_rn(T[0], __ldg(wy));
+            for (int j = 0; j < kGrpMax; ++j) {
+              if (j < nrows) {
+                const float* wy = t.wy + (size_t)(ya + j) * t.ty;
+                float acc = __fmul_rn(T[0], __ldg(wy));
 #pragma unroll
-              for (int r = 1; r < kTapsReg; ++r)
-                if (r < rys) acc = __fmaf_rn(T[r], __ldg(wy + r), acc);
-              const uint32_t res = __ballot_sync(kFull, inb && acc > 0.0f);
-              if (lane == src_lane) words[j] = res;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < kGrpMax; ++j) {
-            if (j < nrows) {
-              const float* wy = t.wy + (size_t)(ya + j) * t.ty;
-              float acc = 0.0f;
-              if (inb) {
-                acc = __fmul_rn(aa_dot(p, 1, wx, cs), __ldg(wy));
-                for (int r = 1; r < rys; ++r) acc = __fmaf_rn(aa_dot(p + (size_t)r * iw, 1, wx, cs), __ldg(wy + r), acc);
+                for (int r = 1; r < kTapsReg; ++r)
+                  if (r < rys) acc = __fmaf_rn(T[r], __ldg(wy + r), acc);
+                const uint32_t res = __ballot_sync(kFull, inb && acc > 0.0f);
+                if (lane == src_lane) words[j] = res;
               }
-              const uint32_t res = __ballot_sync(kFull, inb && acc > 0.0f);
-              if (lane == src_lane) words[j] = res;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < kGrpMax; ++j) {
+              if (j < nrows) {
+                const float* wy = t.wy + (size_t)(ya + j) * t.ty;
+                float acc = 0.0f;
+                if (inb) {
+                  acc = __fmul_rn(aa_dot(p, 1, wx, cs), __ldg(wy));
+                  for (int r = 1; r < rys; ++r) acc = __fmaf_rn(aa_dot(p + (size_t)r * iw, 1, wx, cs), __ldg(wy + r), acc);
+                }
+                const uint32_t res = __ballot_sync(kFull, inb && acc > 0.0f);
+                if (lane == src_lane) words[j] = res;
+              }
             }
           }
         }
-      }
+        // store + statistics (words[] is zero on inactive lanes and on rows that were not computed)
+        uint32_t* drow = dst + (size_t)ya * ow_words + wi;
 #pragma unroll
-      for (int j = 0; j < kGrpMax; ++j) {
-        if (j < nrows) {
-          const uint32_t word = active ? words[j] : 0u;
-          if (active) dst[(size_t)(ya + j) * ow_words + wi] = word;
-          area += __popc(word);
-          colbits |= word;
-          if (__any_sync(kFull, word != 0)) {  // warp-uniform row extent
-            miny = min(miny, ya + j);
-            maxy = max(maxy, ya + j);
+        for (int j = 0; j < kGrpMax; ++j) {
+          if (j < nrows) {
+            const uint32_t word = words[j];
+            if (active) drow[(size_t)j * ow_words] = word;
+            area += __popc(word);
+            colbits |= word;
+            if (word) {
+              miny = min(miny, ya + j);
+              maxy = max(maxy, ya + j);
+            }
           }
         }
       }
     }
-  }
     if (colbits) {
       minx = min(minx, (wi << 5) + __ffs(colbits) - 1);
       maxx = max(maxx, (wi << 5) + 31 - __clz(colbits));
@@ -309,7 +322,7 @@ upsample_pack_kernel(const float* __restrict__ logits, const uint32_t* __restric
     atomicMax(&sc[4], s_red[4]);
     __threadfence();
     const int prev = atomicAdd(&sc[5], 1);
-    if (prev == kUpSplit - 1) {  // last CTA of this mask publishes the final statistics
+    if (prev == needed - 1) {  // last CTA of this mask publishes the final statistics
       __threadfence();
       const int a = atomicAdd(&sc[0], 0);
       const int mx1 = atomicMax(&sc[1], 0), my1 = atomicMax(&sc[2], 0);
@@ -329,18 +342,18 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
                          cudaStream_t s) {
   if (max_sel <= 0) return NTTT_OK;
   if (iw % 32 != 0) return NTTT_EUNSUPPORTED;
-  const size_t smem = (size_t)ih * (iw / 32) * 4 + sizeof(float4) * kXtWords * 32;
+  const size_t smem = (size_t)ih * (iw / 32) * 4;
   if (smem > 160 * 1024) return NTTT_EUNSUPPORTED;
   if (smem > 48 * 1024)
     NTTT_CUDA(cudaFuncSetAttribute(upsample_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   UpTables t{tx.xmin, tx.xsize, tx.w, tx.taps, ty.xmin, ty.xsize, ty.w, ty.taps, tx.t_lo, tx.t_len, ty.t_lo, ty.t_len,
-             ty.grp_of, ty.grp_start};
+             ty.grp_of, ty.grp_start, tx.pk, ty.pk};
   UpMeta* meta = reinterpret_cast<UpMeta*>(scratch + (size_t)kScratchInts * max_sel);
   upsample_meta_kernel<<<ceil_div(max_sel, 256), 256, 0, s>>>(bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, t,
                                                               meta, rect, scratch, logits, mask_ptr);
   NTTT_LAUNCH_CHECK();
-  dim3 grid(kUpSplit, max_sel);
-  upsample_pack_kernel<<<grid, kUpThreads, smem, s>>>(logits, bits_lr, meta, ih, iw, n_sel, max_sel, oh, ow, t, bits_full,
+  dim3 grid(kUpMaxSplit, max_sel);
+  upsample_pack_kernel<<<grid, kUpThreads, smem, s>>>(bits_lr, meta, ih, iw, n_sel, max_sel, oh, ow, t, bits_full,
                                                       area_full, box_full, scratch);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;

@@ -324,6 +324,23 @@ __global__ void aa_group_kernel(int out_size, const int32_t* xmin, const int32_t
   for (int k = g + 1; k <= out_size; ++k) grp_start[k] = out_size;
 }
 
+// packed records for the resize fast path (see AxisTable::pk)
+__global__ void aa_pack_kernel(int out_size, int out_pad, int taps, const int32_t* xmin, const int32_t* xsize,
+                               const float* w, float4* pk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= out_pad) return;
+  float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < out_size) {
+    const int cs = xsize[i];
+    const float* wi = w + (size_t)i * taps;
+    e.x = __int_as_float(xmin[i] | (cs << 16));
+    e.y = cs > 0 ? wi[0] : 0.0f;
+    e.z = cs > 1 ? wi[1] : 0.0f;
+    e.w = cs > 2 ? wi[2] : 0.0f;
+  }
+  pk[i] = e;
+}
+
 int build_axis_table(AxisTable& t, int in_size, int out_size, cudaStream_t s) {
   t.in_size = in_size;
   t.out_size = out_size;
@@ -343,12 +360,19 @@ int build_axis_table(AxisTable& t, int in_size, int out_size, cudaStream_t s) {
   NTTT_LAUNCH_CHECK();
   aa_group_kernel<<<1, 32, 0, s>>>(out_size, t.xmin, t.xsize, t.grp_of, t.grp_start);
   NTTT_LAUNCH_CHECK();
+  if (t.taps <= 3 && in_size < 65536) {
+    const int out_pad = (out_size + 31) / 32 * 32;
+    NTTT_CUDA(cudaMalloc(&t.pk, sizeof(float4) * (size_t)out_pad));
+    aa_pack_kernel<<<ceil_div(out_pad, 128), 128, 0, s>>>(out_size, out_pad, t.taps, t.xmin, t.xsize, t.w, t.pk);
+    NTTT_LAUNCH_CHECK();
+  }
   return NTTT_OK;
 }
 
 void free_axis_table(AxisTable& t) {
   cudaFree(t.xmin); cudaFree(t.xsize); cudaFree(t.w); cudaFree(t.t_lo); cudaFree(t.t_len); cudaFree(t.t_w);
   cudaFree(t.grp_of); cudaFree(t.grp_start);
+  if (t.pk) cudaFree(t.pk);
   t = AxisTable{};
 }
 
