@@ -16,9 +16,9 @@
 
 namespace nttt {
 
-constexpr int kUpThreads = 256;
+constexpr int kUpThreads = 128;
 constexpr int kUpMaxSplit = 8;       // grid.x: CTAs available per mask; a mask uses ceil(groups / kUpGroupsPerCta) of them
-constexpr int kUpGroupsPerCta = 32;  // row groups per CTA = 4 per warp: amortises the per-CTA / per-warp set-up
+constexpr int kUpGroupsPerCta = 32;  // row groups per CTA = 8 per warp: amortises the per-CTA / per-warp set-up
 
 struct UpTables {
   const int32_t* xmin; const int32_t* xsize; const float* wx; int tx;
@@ -95,11 +95,16 @@ __device__ __forceinline__ int up_ctas_needed(int n_groups) {
 }
 
 // grid (kUpMaxSplit, max_sel).  A mask with G row groups is served by ceil(G / 32) CTAs (the others exit at once); a
-// CTA takes 32 consecutive groups, warp w the groups w, w+8, w+16, w+24 of them; a lane owns one 32-pixel output word
+// CTA (4 warps) takes 32 consecutive groups, warp w the groups w, w+4, ... of them; a lane owns one 32-pixel output word
 // column.  Per group: the footprint test on the low-res bits (shared memory) classifies each word as all-0, all-1 or
 // mixed; mixed words are evaluated one at a time with lane = pixel: horizontal pass of the shared input rows once,
 // vertical pass per output row, one ballot per row.
-__global__ void __launch_bounds__(kUpThreads, 4)
+// All indices inside the loops are 32-bit (one 64-bit base per array): 64-bit index arithmetic was a third of the
+// instructions of an earlier version.
+#ifndef NTTT_UP_MINBLOCKS
+#define NTTT_UP_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(kUpThreads, NTTT_UP_MINBLOCKS)
 upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restrict__ meta, int ih, int iw,
                      const int32_t* __restrict__ n_sel, int max_sel, int oh, int ow, UpTables t,
                      uint32_t* __restrict__ bits_full, int32_t* __restrict__ area_full, int32_t* __restrict__ box_full,
@@ -129,7 +134,8 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
     clr1 = t.ymin[yb - 1] + t.ysize[yb - 1];
   }
   const uint32_t* lr = bits_lr + ((size_t)mt.src * ih + clr0) * lr_wpr;
-  for (int i = threadIdx.x; i < (clr1 - clr0) * lr_wpr; i += kUpThreads) s_lr[i] = lr[i];
+  const int n_lr = (clr1 - clr0) * lr_wpr;
+  for (int i = threadIdx.x; i < n_lr; i += kUpThreads) s_lr[i] = lr[i];
   if (threadIdx.x < 5) s_red[threadIdx.x] = 0;
   const bool fast_cfg = t.pk_x != nullptr && t.pk_y != nullptr;  // <= 3 taps on both axes
   const bool safe = mt.safe != 0;
@@ -175,7 +181,8 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
           ry0 = t.ymin[ya];
           rys = t.ysize[ya];
         }
-        const float* rowbase = src + (size_t)ry0 * iw;
+        const int rb = ry0 * iw;                     // index of the group's first input row
+        const int lrb = (ry0 - clr0) * lr_wpr + cw0;  // this lane's first footprint word in s_lr
         uint32_t words[kGrpMax];
 #pragma unroll
         for (int j = 0; j < kGrpMax; ++j) words[j] = 0;
@@ -183,16 +190,19 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
         if (active) {
           bool all0 = true, all1 = true;
           if (two_words) {
+            // (m1 == 0 when the footprint stays inside one low-res word; s_lr has a spare word at the end)
+            uint32_t any = 0, miss = 0;
             for (int r = 0; r < rys; ++r) {
-              const uint32_t* row = s_lr + (ry0 + r - clr0) * lr_wpr + cw0;
-              const uint32_t v0 = row[0] & m0;
-              const uint32_t v1 = m1 ? (row[1] & m1) : 0u;
-              all0 = all0 && ((v0 | v1) == 0);
-              all1 = all1 && (v0 == m0) && (v1 == m1);
+              const uint32_t v0 = s_lr[lrb + r * lr_wpr] & m0;
+              const uint32_t v1 = s_lr[lrb + r * lr_wpr + 1] & m1;
+              any |= v0 | v1;
+              miss |= (v0 ^ m0) | (v1 ^ m1);
             }
+            all0 = any == 0;
+            all1 = miss == 0;
           } else {
             for (int r = 0; r < rys; ++r) {
-              const uint32_t* row = s_lr + (ry0 + r - clr0) * lr_wpr;
+              const uint32_t* row = s_lr + (lrb - cw0) + r * lr_wpr;
               for (int cw = cw0; cw <= (c1 - 1) >> 5; ++cw) {
                 const int lo = max(c0 - (cw << 5), 0), hi = min(c1 - (cw << 5), 32);
                 const uint32_t m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
@@ -221,13 +231,12 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
             const float4 xt = __ldg(t.pk_x + x);
             const int pk = __float_as_int(xt.x);
             const int cx = pk & 0xffff, cs = pk >> 16;
-            const float* p = rowbase + cx;
             float T[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
               float acc = 0.0f;
               if (r < rys && cs > 0) {
-                const float* q = p + (size_t)r * iw;
+                const float* q = src + (rb + cx + r * iw);
                 acc = __fmul_rn(__ldg(q), xt.y);
                 if (cs > 1) acc = __fmaf_rn(__ldg(q + 1), xt.z, acc);
                 if (cs > 2) acc = __fmaf_rn(__ldg(q + 2), xt.w, acc);
@@ -247,7 +256,7 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
           const bool inb = x < ow;
           const int cx = inb ? t.xmin[x] : 0, cs = inb ? t.xsize[x] : 1;
           const float* wx = t.wx + (size_t)(inb ? x : 0) * t.tx;
-          const float* p = rowbase + cx;
+          const float* p = src + (rb + cx);
           if (rys <= kTapsReg) {
             // horizontal pass once per group, vertical pass per row
             float T[kTapsReg];
@@ -282,18 +291,16 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
           }
         }
         // store + statistics (words[] is zero on inactive lanes and on rows that were not computed)
-        uint32_t* drow = dst + (size_t)ya * ow_words + wi;
+        const int doff = ya * ow_words + wi;
 #pragma unroll
         for (int j = 0; j < kGrpMax; ++j) {
-          if (j < nrows) {
-            const uint32_t word = words[j];
-            if (active) drow[(size_t)j * ow_words] = word;
-            area += __popc(word);
-            colbits |= word;
-            if (word) {
-              miny = min(miny, ya + j);
-              maxy = max(maxy, ya + j);
-            }
+          const uint32_t word = j < nrows ? words[j] : 0u;  // (the fast path computes all kGrpMax rows)
+          if (active && j < nrows) dst[doff + j * ow_words] = word;
+          area += __popc(word);
+          colbits |= word;
+          if (word) {
+            miny = min(miny, ya + j);
+            maxy = max(maxy, ya + j);
           }
         }
       }
@@ -342,7 +349,7 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
                          cudaStream_t s) {
   if (max_sel <= 0) return NTTT_OK;
   if (iw % 32 != 0) return NTTT_EUNSUPPORTED;
-  const size_t smem = (size_t)ih * (iw / 32) * 4;
+  const size_t smem = ((size_t)ih * (iw / 32) + 1) * 4;  // + one spare word read (and masked off) by the footprint test
   if (smem > 160 * 1024) return NTTT_EUNSUPPORTED;
   if (smem > 48 * 1024)
     NTTT_CUDA(cudaFuncSetAttribute(upsample_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
