@@ -46,8 +46,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="images per step per GPU")
-    ap.add_argument("--streams", type=int, default=4, help="images in flight per GPU")
+    ap.add_argument("--batch", type=int, default=16, help="images per step per GPU")
+    ap.add_argument("--streams", type=int, default=8, help="images in flight per GPU")
     ap.add_argument("--cpu-sample", type=int, default=2, help="images timed for cpu_baseline (0 = skip)")
     ap.add_argument("--n-masks", type=int, default=WORKLOAD["n_masks"])
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from the host instead of replaying "

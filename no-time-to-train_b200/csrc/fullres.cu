@@ -173,7 +173,7 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
         float4 wv[kGrpMax];  // fast path: {., w0, w1, w2} of the group's rows (rows past nrows repeat the last one)
         if (fast_cfg) {
 #pragma unroll
-          for (int j = 0; j < kGrpMax; ++j) wv[j] = __ldg(t.pk_y + min(ya + j, yb - 1));
+          for (int j = 0; j < kGrpMax; ++j) wv[j] = __ldg(t.pk_y + (uint32_t)min(ya + j, yb - 1));
           const int pky = __float_as_int(wv[0].x);
           ry0 = pky & 0xffff;
           rys = pky >> 16;
@@ -192,11 +192,23 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
           if (two_words) {
             // (m1 == 0 when the footprint stays inside one low-res word; s_lr has a spare word at the end)
             uint32_t any = 0, miss = 0;
-            for (int r = 0; r < rys; ++r) {
-              const uint32_t v0 = s_lr[lrb + r * lr_wpr] & m0;
-              const uint32_t v1 = s_lr[lrb + r * lr_wpr + 1] & m1;
-              any |= v0 | v1;
-              miss |= (v0 ^ m0) | (v1 ^ m1);
+            if (rys <= 3) {
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                if (r < rys) {
+                  const uint32_t v0 = s_lr[(uint32_t)(lrb + r * lr_wpr)] & m0;
+                  const uint32_t v1 = s_lr[(uint32_t)(lrb + r * lr_wpr + 1)] & m1;
+                  any |= v0 | v1;
+                  miss |= (v0 ^ m0) | (v1 ^ m1);
+                }
+              }
+            } else {
+              for (int r = 0; r < rys; ++r) {
+                const uint32_t v0 = s_lr[lrb + r * lr_wpr] & m0;
+                const uint32_t v1 = s_lr[lrb + r * lr_wpr + 1] & m1;
+                any |= v0 | v1;
+                miss |= (v0 ^ m0) | (v1 ^ m1);
+              }
             }
             all0 = any == 0;
             all1 = miss == 0;
@@ -228,15 +240,17 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
             // Every constant of the pixel in one 128-bit load (records past the width have size 0).  Taps beyond the
             // span are never read; rows / taps beyond it contribute fma(0, 0, acc) = acc, so the arithmetic is exactly
             // acc = s0*w0; acc = fma(s_j, w_j, acc) for j < size, horizontally and then vertically.
-            const float4 xt = __ldg(t.pk_x + x);
+            const float4 xt = __ldg(t.pk_x + (uint32_t)x);
             const int pk = __float_as_int(xt.x);
             const int cx = pk & 0xffff, cs = pk >> 16;
             float T[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
               float acc = 0.0f;
-              if (r < rys && cs > 0) {
-                const float* q = src + (rb + cx + r * iw);
+              if (r < rys) {  // (warp-uniform)
+                // records past the image width have cs = 0, cx = 0 and zero weights: their first tap reads a valid
+                // address and the lane's result is masked by `cs > 0` in the ballot
+                const float* q = src + (uint32_t)(rb + cx + r * iw);
                 acc = __fmul_rn(__ldg(q), xt.y);
                 if (cs > 1) acc = __fmaf_rn(__ldg(q + 1), xt.z, acc);
                 if (cs > 2) acc = __fmaf_rn(__ldg(q + 2), xt.w, acc);
@@ -295,7 +309,7 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
 #pragma unroll
         for (int j = 0; j < kGrpMax; ++j) {
           const uint32_t word = j < nrows ? words[j] : 0u;  // (the fast path computes all kGrpMax rows)
-          if (active && j < nrows) dst[doff + j * ow_words] = word;
+          if (active && j < nrows) dst[(uint32_t)(doff + j * ow_words)] = word;
           area += __popc(word);
           colbits |= word;
           if (word) {
