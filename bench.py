@@ -47,9 +47,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="images per step per GPU")
-    ap.add_argument("--streams", type=int, default=8, help="images in flight per GPU")
+    ap.add_argument("--streams", type=int, default=16, help="images in flight per GPU")
     ap.add_argument("--cpu-sample", type=int, default=2, help="images timed for cpu_baseline (0 = skip)")
     ap.add_argument("--n-masks", type=int, default=WORKLOAD["n_masks"])
+    ap.add_argument("--n-classes", type=int, default=WORKLOAD["n_classes"], help="other BASELINE configs: 1203 = LVIS-shape "
+                    "bank (config 4); --n-masks 4096 = points_per_side 64 (config 5); the default is config 2")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from the host instead of replaying "
                     "the captured CUDA graph of the stage")
     return ap.parse_args()
@@ -168,6 +170,9 @@ def run_reference(args, rank):
 
 def main():
     args = parse()
+    if args.n_classes != WORKLOAD["n_classes"] or args.n_masks != WORKLOAD["n_masks"]:
+        WORKLOAD["n_classes"] = args.n_classes
+        WORKLOAD["workload"] = f"coco-shape_{args.n_classes}x{WORKLOAD['shots']}_sam2L_dinov2L_{args.n_masks}masks_1024x1024"
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
