@@ -131,6 +131,37 @@ def test_image_sharding_is_strided_and_complete():
         assert merged == [f"img{i}" for i in range(n)]
 
 
+def _collect_worker(rank, world, port, n_items, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shard = importlib.import_module("no-time-to-train_b200.sharding")
+        # each rank "scores" its images: one encoded-result list per image, as `_output_inqueue` appends them
+        part = [[dict(image_id=i, category_id=7, score=0.5, segmentation=dict(size=[4, 4], counts="`0"))]
+                for i in shard.shard_indices(n_items, rank, world)]
+        got = shard.collect_results(part, size=n_items)
+        torch.save(got, os.path.join(out_dir, f"collect{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_collect_results_gathers_and_reorders(tmp_path):
+    """`collect_results` == the reference's `collect_results_cpu` (run_lightning.py:23-78): rank 0 gets every image's
+    results in dataset order, truncated to the dataset length (7 images on 2 ranks: one padded repeat); other
+    ranks get None; without a process group the part comes back unchanged."""
+    shard = importlib.import_module("no-time-to-train_b200.sharding")
+    assert shard.collect_results([1, 2, 3], size=2) == [1, 2, 3]
+    n_items, world = 7, 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.start_processes(_collect_worker, args=(world, port, n_items, str(tmp_path)), nprocs=world, join=True,
+                       start_method="spawn")
+    got0 = torch.load(os.path.join(tmp_path, "collect0.pt"))
+    got1 = torch.load(os.path.join(tmp_path, "collect1.pt"))
+    assert got1 is None
+    assert [r[0]["image_id"] for r in got0] == list(range(n_items))
+
+
 def test_model_rejects_unsupported_modes_without_gpu():
     pkg = importlib.import_module("no-time-to-train_b200")
     if torch.cuda.is_available():
