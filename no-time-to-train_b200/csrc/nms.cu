@@ -67,7 +67,10 @@ nms_sort_kernel(const float* __restrict__ scores, const int32_t* __restrict__ bo
   for (int i = threadIdx.x; i < n; i += blockDim.x) emit(i, s_keys[i]);
 }
 
-// suppression bit matrix in sorted order: bit j of row i set iff j > i, same label, IoU(i,j) > thr
+// suppression bit matrix in sorted order.  kByVictim: bit i of row j set iff i < j, same label, IoU(i,j) > thr — row j
+// lists the earlier boxes that would suppress j if they are kept (wavefront scan).  Otherwise by suppressor: bit j of
+// row i set iff j > i (serial scan).  The IoU arithmetic is symmetric in its two boxes (float additions commute exactly).
+template <bool kByVictim>
 __global__ void __launch_bounds__(256)
 nms_mask_kernel(const float4* __restrict__ sorted_box, const int32_t* __restrict__ sorted_label, int n, float thr,
                 uint32_t* __restrict__ mask, int row_words) {
@@ -84,13 +87,13 @@ nms_mask_kernel(const float4* __restrict__ sorted_box, const int32_t* __restrict
   __syncthreads();
   if (i >= n || cw >= row_words) return;
   uint32_t bits = 0;
-  if (cw * 32 + 31 > i) {
+  if (kByVictim ? (cw * 32 < i) : (cw * 32 + 31 > i)) {
     const float4 a = sorted_box[i];
     const float area_a = __fmul_rn(a.z - a.x, a.w - a.y);
     const int la = sorted_label[i];
     for (int t = 0; t < 32; ++t) {
       const int j = cw * 32 + t;
-      if (j <= i || j >= n || s_lab[threadIdx.y][t] != la) continue;
+      if ((kByVictim ? j >= i : (j <= i || j >= n)) || s_lab[threadIdx.y][t] != la) continue;
       const float4 b = s_box[threadIdx.y][t];
       const float w = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.0f);
       const float h = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.0f);
@@ -100,15 +103,119 @@ nms_mask_kernel(const float4* __restrict__ sorted_box, const int32_t* __restrict
       if (ovr > thr) bits |= 1u << t;
     }
   }
-  mask[(size_t)i * row_words + cw] = bits;
+  // by victim: word-major [cw][i] so that the scan's lanes (consecutive boxes) read consecutive addresses
+  if (kByVictim) mask[(size_t)cw * (row_words * 32) + i] = bits;
+  else mask[(size_t)i * row_words + cw] = bits;
 }
 
-// Greedy scan over the sorted list by one CTA of 32 warps, 32 boxes (one chunk) per step:
+// Greedy scan as a wavefront over 32-box chunks, one CTA of 32 warps, no CTA-wide barrier inside the scan.
+// Warp c owns chunk c; lane b owns sorted box j = 32c + b and row j of the matrix (its potential
+// suppressors).  keep[j] = !gone[j] && no kept suppressor:
+//   * suppressors in EARLIER chunks: the lane ANDs each non-zero row word w with the final keep word K[w], waiting on a
+//     per-chunk ready flag only for the words where it actually has suppressor bits (class-aware NMS: few);
+//   * suppressors in the SAME chunk: a warp-local fixed point K' = ballot(cand && !(diag & K)), which reaches the
+//     unique greedy solution in (longest in-chunk chain + 1) ballots, usually 2-4 instead of a 32-step serial chain.
+// Then the warp publishes K[c] and sets the flag.  The critical path is one in-chunk resolve + one flag hand-off per
+// chunk.  All warps of the CTA are resident and a chunk only waits on lower chunks, so the spin-waits cannot deadlock.
+// Used for n <= 1024 (32 chunks = 32 warps, rows in registers); longer lists take the serial scan below.
+constexpr int kScanThreads = 1024;
+constexpr int kScanMaxN = 8192;
+
+__global__ void __launch_bounds__(kScanThreads, 1)
+nms_wave_kernel(const uint32_t* __restrict__ mt, int row_words, const int32_t* __restrict__ order,
+                const int32_t* __restrict__ sorted_label, const float* __restrict__ top_score, int n, int max_keep,
+                int32_t* __restrict__ keep, int32_t* __restrict__ n_keep, int32_t* __restrict__ sel,
+                int32_t* __restrict__ n_sel) {
+  __shared__ uint32_t s_K[kScanMaxN / 32];    // keep bits per chunk, then truncated to max_keep
+  __shared__ uint32_t s_S[kScanMaxN / 32];    // positive-score flags, then `sel` bits
+  __shared__ int s_pre[kScanMaxN / 32 + 1];   // exclusive prefix of popc over the words
+  __shared__ volatile int s_ready[kScanMaxN / 32];
+  const int lane = lane_id(), warp = warp_id();
+  if (threadIdx.x < 32) s_ready[threadIdx.x] = 0;
+  // n <= 1024: warp c owns chunk c, and every lane holds its whole row (<= 32 words) in registers, so no global load
+  // sits on the scan's critical path
+  const int c = warp;
+  const int j = c * 32 + lane;
+  const bool valid = j < n;
+  uint32_t r[32];
+#pragma unroll
+  for (int w = 0; w < 32; ++w) r[w] = (valid && w <= c && w < row_words) ? __ldg(mt + (size_t)w * (row_words * 32) + j) : 0u;
+  const bool gone = !valid || sorted_label[j] < -1;
+  const bool pos = valid && top_score[order[valid ? j : 0]] > 0.0f;
+  const uint32_t pbits = __ballot_sync(kFull, pos);
+  __syncthreads();
+  if (c < row_words) {
+    uint32_t supp = 0, diag = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) {
+      if (w == c) diag = r[w];  // suppressors inside this chunk (bits below the lane)
+      if (w < c && r[w]) {
+        while (s_ready[w] == 0) {}
+        __threadfence_block();
+        supp |= r[w] & s_K[w];
+      }
+    }
+    __syncwarp();
+    const bool cand = !gone && supp == 0;
+    uint32_t K = __ballot_sync(kFull, cand);
+    for (int it = 0; it < 33; ++it) {
+      const uint32_t K2 = __ballot_sync(kFull, cand && (diag & K) == 0);
+      if (K2 == K) break;
+      K = K2;
+    }
+    if (lane == 0) {
+      s_K[c] = K;
+      s_S[c] = pbits;
+      __threadfence_block();
+      s_ready[c] = 1;
+    }
+  }
+  __syncthreads();
+  // survivors in sorted order, truncated to max_keep; those with a positive top score also go to `sel`
+  auto prefix = [&](const uint32_t* bits) {  // s_pre[w] = number of set bits in words < w (warp 0)
+    if (warp == 0) {
+      int run = 0;
+      for (int w0 = 0; w0 < row_words; w0 += 32) {
+        const int w = w0 + lane;
+        const int cnt = w < row_words ? __popc(bits[w]) : 0;
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(kFull, inc, o);
+          if (lane >= o) inc += up;
+        }
+        if (w < row_words) s_pre[w] = run + inc - cnt;
+        run += __shfl_sync(kFull, inc, 31);
+      }
+      if (lane == 0) s_pre[row_words] = run;
+    }
+    __syncthreads();
+  };
+  prefix(s_K);
+  for (int c = warp; c < row_words; c += kScanThreads / 32) {
+    const uint32_t kw = s_K[c];
+    const int rank = s_pre[c] + __popc(kw & ((1u << lane) - 1u));
+    const bool mine = ((kw >> lane) & 1u) && rank < max_keep;
+    if (mine) keep[rank] = order[c * 32 + lane];
+    const uint32_t mbits = __ballot_sync(kFull, mine);
+    __syncwarp();
+    if (lane == 0) { s_K[c] = mbits; s_S[c] &= mbits; }
+  }
+  const int total_kept = min(s_pre[row_words], max_keep);
+  __syncthreads();
+  prefix(s_S);
+  for (int c = warp; c < row_words; c += kScanThreads / 32) {
+    const uint32_t sw = s_S[c];
+    if ((sw >> lane) & 1u) sel[s_pre[c] + __popc(sw & ((1u << lane) - 1u))] = order[c * 32 + lane];
+  }
+  if (threadIdx.x == 0) { *n_keep = total_kept; *n_sel = s_pre[row_words]; }
+}
+
+// Serial greedy scan (lists longer than 1024 boxes; matrix stored by SUPPRESSOR, kByVictim = false) by one CTA of
+// 32 warps, 32 boxes (one chunk) per step:
 //   warp 0 resolves the in-chunk dependencies on the diagonal word and emits the survivors,
 //   then warp j ORs the suppression row of survivor j into the shared `removed` set (all rows in parallel).
 // The bit matrix is staged in shared memory when it fits (n <= ~1100), otherwise read from L2.
-constexpr int kScanThreads = 1024;
-constexpr int kScanMaxN = 8192;
 
 template <bool kStaged>
 __global__ void __launch_bounds__(kScanThreads)
@@ -188,7 +295,7 @@ nms_scan_kernel(const uint32_t* __restrict__ mask, int row_words, const int32_t*
 
 size_t nms_workspace_bytes(int n) {
   const size_t row_words = (size_t)ceil_div(n, 32);
-  return align_up(sizeof(int32_t) * (size_t)n, 256) + align_up(sizeof(uint32_t) * row_words * (size_t)n, 256) +
+  return align_up(sizeof(int32_t) * (size_t)n, 256) + align_up(sizeof(uint32_t) * row_words * (row_words * 32), 256) +
          align_up(sizeof(float4) * (size_t)n, 256) + align_up(sizeof(int32_t) * (size_t)n, 256);
 }
 
@@ -207,7 +314,7 @@ int launch_box_nms(const int32_t* box, const float* nms_scores, const int32_t* l
   uint32_t* mask = reinterpret_cast<uint32_t*>(w8 + align_up(sizeof(int32_t) * (size_t)n, 256));
   const int row_words = ceil_div(n, 32);
   float4* sorted_box = reinterpret_cast<float4*>(reinterpret_cast<char*>(mask) +
-                                                 align_up(sizeof(uint32_t) * (size_t)row_words * n, 256));
+                                                 align_up(sizeof(uint32_t) * (size_t)row_words * (row_words * 32), 256));
   int32_t* sorted_label = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(sorted_box) +
                                                      align_up(sizeof(float4) * (size_t)n, 256));
   int n_pad = 1;
@@ -224,7 +331,15 @@ int launch_box_nms(const int32_t* box, const float* nms_scores, const int32_t* l
   }
   NTTT_LAUNCH_CHECK();
   dim3 grid(ceil_div(row_words, 8), ceil_div(n, 32));
-  nms_mask_kernel<<<grid, dim3(32, 8), 0, s>>>(sorted_box, sorted_label, n, thr, mask, row_words);
+  if (n <= 1024) {
+    nms_mask_kernel<true><<<grid, dim3(32, 8), 0, s>>>(sorted_box, sorted_label, n, thr, mask, row_words);
+    NTTT_LAUNCH_CHECK();
+    nms_wave_kernel<<<1, kScanThreads, 0, s>>>(mask, row_words, order, sorted_label, top_score, n, max_keep, keep, n_keep, sel,
+                                               n_sel);
+    NTTT_LAUNCH_CHECK();
+    return NTTT_OK;
+  }
+  nms_mask_kernel<false><<<grid, dim3(32, 8), 0, s>>>(sorted_box, sorted_label, n, thr, mask, row_words);
   NTTT_LAUNCH_CHECK();
   const size_t stage_bytes = sizeof(uint32_t) * (size_t)n * row_words;
   if (stage_bytes <= 160 * 1024) {

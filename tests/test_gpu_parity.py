@@ -118,6 +118,30 @@ def test_box_nms_matches_oracle_and_torchvision(ops, n, n_cls):
     assert ns == len(want_sel) and np.array_equal(sel.cpu().numpy()[:ns], want_sel)
 
 
+@pytest.mark.parametrize("n,max_keep", [(1000, 800), (1024, 1024), (333, 50)])
+def test_box_nms_long_suppression_chain(ops, n, max_keep):
+    """Worst case for the fixed-point scan: one class, boxes along a line, each overlapping only its neighbours with
+    IoU > thr, so keep/suppress alternates along a dependency chain as long as the list (plus a random tail)."""
+    from torchvision.ops import batched_nms
+    gen = torch.Generator().manual_seed(n)
+    chain = n * 2 // 3
+    x0 = torch.arange(chain) * 3
+    box = torch.stack([x0, torch.zeros(chain, dtype=torch.long), x0 + 10, torch.full((chain,), 10)], 1)  # IoU(i,i+1)=7/13
+    xy = torch.randint(0, 400, (n - chain, 2), generator=gen)
+    wh = torch.randint(1, 60, (n - chain, 2), generator=gen)
+    box = torch.cat([box, torch.cat([xy, xy + wh], 1) + torch.tensor([0, 50, 0, 50])]).int()
+    scores = torch.cat([torch.linspace(1.0, 0.5, chain), 0.4 * torch.rand(n - chain, generator=gen)])  # chain sorted first
+    labels = torch.zeros(n, dtype=torch.int32)
+    top = torch.rand(n, generator=gen) - 0.3
+    keep, sel, counts = ops.box_nms(box.to(DEV), scores.to(DEV), labels.to(DEV), top.to(DEV), 0.5, max_keep)
+    nk, ns = counts.cpu().tolist()
+    want = batched_nms(box.float(), scores, labels.long(), 0.5)[:max_keep].numpy()
+    assert want[:3].tolist() == [0, 2, 4]  # the chain alternates
+    assert nk == len(want) and np.array_equal(keep.cpu().numpy()[:nk], want)
+    want_sel = want[top.numpy()[want] > 0]
+    assert ns == len(want_sel) and np.array_equal(sel.cpu().numpy()[:ns], want_sel)
+
+
 @pytest.mark.parametrize("ori_hw", [(1024, 1024), (480, 640), (427, 640), (333, 500), (200, 180), (100, 700), (1500, 2040)])
 def test_upsample_threshold_pack_bit_exact(ops, synth, ori_hw):
     n = 24
