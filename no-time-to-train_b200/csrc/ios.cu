@@ -11,6 +11,7 @@
 namespace nttt {
 
 constexpr int kIosThreads = 256;
+constexpr int kIosBigWords = 4096;  // overlap windows above this many words go to the CTA-per-pair kernel
 
 // Pair work is symmetric (inter(i,j) and the pair similarity are shared by v_ij and v_ji), so each unordered
 // same-label pair is evaluated once, by the CTA of the lower index, and both row maxima are updated with an
@@ -39,7 +40,7 @@ ios_meta_kernel(const int32_t* __restrict__ rect, const int32_t* __restrict__ ar
                 IosMeta* __restrict__ meta, int32_t* __restrict__ label_sel, float* __restrict__ ios,
                 int32_t* __restrict__ n_pairs) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j == 0) *n_pairs = 0;
+  if (j == 0) { n_pairs[0] = 0; n_pairs[1] = 0; }  // small list (front of the buffer), big list (back)
   if (j >= max_sel) return;
   ios[j] = 0.0f;  // identity of the row max (the zeroed diagonal, area > 0 case)
   if (j >= min(*n_sel, max_sel)) { label_sel[j] = -1; return; }
@@ -68,26 +69,112 @@ ios_pairs_kernel(const IosMeta* __restrict__ meta, const int32_t* __restrict__ l
   const int lane = lane_id();
   for (int base = i + 1; base < nsel; base += 256) {
     const int j = base + threadIdx.x;
-    bool hit = false;
+    bool hit = false, big = false;
     if (j < nsel && label_sel[j] == me.label) {
       const IosMeta mj = meta[j];
-      hit = mj.area > 0 && max(me.box.x, mj.box.x) <= min(me.box.z, mj.box.z) &&
-            max(me.box.y, mj.box.y) <= min(me.box.w, mj.box.w);
+      const int x0 = max(me.box.x, mj.box.x), x1 = min(me.box.z, mj.box.z);
+      const int y0 = max(me.box.y, mj.box.y), y1 = min(me.box.w, mj.box.w);
+      hit = mj.area > 0 && x0 <= x1 && y0 <= y1;
+      big = hit && ((x1 >> 5) - (x0 >> 5) + 1) * (y1 - y0 + 1) > kIosBigWords;
     }
-    const uint32_t m = __ballot_sync(kFull, hit);
+    const uint32_t mb = __ballot_sync(kFull, big);
+    const uint32_t m = __ballot_sync(kFull, hit) & ~mb;
     if (m) {
       int slot = 0;
-      if (lane == 0) slot = atomicAdd(n_pairs, __popc(m));
+      if (lane == 0) slot = atomicAdd(&n_pairs[0], __popc(m));
       slot = __shfl_sync(kFull, slot, 0) + __popc(m & ((1u << lane) - 1u));
-      if (hit && slot < max_pairs) pairs[slot] = make_int2(i, j);
+      if (hit && !big) pairs[slot] = make_int2(i, j);
+    }
+    if (mb) {
+      int slot = 0;
+      if (lane == 0) slot = atomicAdd(&n_pairs[1], __popc(mb));
+      slot = __shfl_sync(kFull, slot, 0) + __popc(mb & ((1u << lane) - 1u));
+      if (big) pairs[max_pairs - 1 - slot] = make_int2(i, j);
     }
   }
 }
 
-// Pair evaluation: one CTA per pair (grid-stride over the list): popcount of the AND over the overlap window and
-// the feature dot product, spread over all threads with four load pairs in flight, one block reduction.
+// Pair evaluation: one WARP per pair (warp-stride over the list): popcount of the AND over the overlap window and the
+// feature dot product, both reduced with shuffles — no shared memory, no CTA barrier.  (One CTA per pair spent most of
+// its instructions on per-thread set-up and the block reduction: a typical window is ~150 words.)  A window is walked
+// row-major with the lanes along the words when it is wide and along the rows when it is narrow.
 __global__ void __launch_bounds__(kIosThreads)
 ios_eval_kernel(const uint32_t* __restrict__ bits_full, const IosMeta* __restrict__ meta,
+                const int2* __restrict__ pairs, const int32_t* __restrict__ n_pairs, int max_pairs, int max_sel, int oh,
+                int ow, const float* __restrict__ obj_feats, int c, float* __restrict__ ios,
+                int32_t* __restrict__ inter_out) {
+  const int lane = lane_id();
+  constexpr int kWarps = kIosThreads / 32;
+  const int ow_words = (ow + 31) >> 5;
+  const int np = min(*n_pairs, max_pairs);
+  const uint32_t mask_words = (uint32_t)oh * (uint32_t)ow_words;
+  for (int p = blockIdx.x * kWarps + warp_id(); p < np; p += gridDim.x * kWarps) {
+    const int2 pr = pairs[p];
+    const int i = pr.x, j = pr.y;
+    const IosMeta me = meta[i], mj = meta[j];
+    const int x0 = max(me.box.x, mj.box.x), x1 = min(me.box.z, mj.box.z);
+    const int y0 = max(me.box.y, mj.box.y), y1 = min(me.box.w, mj.box.w);
+    const int wlo = max(max(me.rect.z, mj.rect.z), x0 >> 5), whi = min(min(me.rect.w, mj.rect.w), (x1 >> 5) + 1);
+    const int ylo = max(max(me.rect.x, mj.rect.x), y0), yhi = min(min(me.rect.y, mj.rect.y), y1 + 1);
+    const int nw = whi - wlo, nr = yhi - ylo;
+    const uint32_t* mi = bits_full + (size_t)i * mask_words;
+    const uint32_t* pj = bits_full + (size_t)j * mask_words;
+    int inter = 0;
+    if (nw > 0 && nr > 0) {
+      // lanes tile the window: tx over words (next pow2 >= nw, <= 32), ty over rows
+      int txn = 1;
+      while (txn < nw && txn < 32) txn <<= 1;
+      const int tx = lane & (txn - 1), ty = lane / txn, tyn = 32 / txn;
+      for (int w = wlo + tx; w < whi; w += txn) {
+        uint32_t o = (uint32_t)(ylo + ty) * (uint32_t)ow_words + (uint32_t)w;
+        const uint32_t step = (uint32_t)tyn * (uint32_t)ow_words;
+        int y = ylo + ty;
+        for (; y + 3 * tyn < yhi; y += 4 * tyn, o += 4 * step) {
+          const uint32_t a0 = __ldg(mi + o), b0 = __ldg(pj + o), a1 = __ldg(mi + o + step), b1 = __ldg(pj + o + step);
+          const uint32_t a2 = __ldg(mi + o + 2 * step), b2 = __ldg(pj + o + 2 * step);
+          const uint32_t a3 = __ldg(mi + o + 3 * step), b3 = __ldg(pj + o + 3 * step);
+          inter += __popc(a0 & b0) + __popc(a1 & b1) + __popc(a2 & b2) + __popc(a3 & b3);
+        }
+        for (; y < yhi; y += tyn, o += step) inter += __popc(__ldg(mi + o) & __ldg(pj + o));
+      }
+    }
+    inter = warp_sum(inter);
+    if (inter_out && lane == 0) {
+      inter_out[(size_t)i * max_sel + j] = inter;
+      inter_out[(size_t)j * max_sel + i] = inter;
+    }
+    if (inter > 0) {  // (warp-uniform) the similarity is only needed for intersecting pairs
+      const float* fi = obj_feats + (size_t)me.src * c;
+      const float* fj = obj_feats + (size_t)mj.src * c;
+      float dot = 0.0f;
+      if ((c & 3) == 0) {
+        const float4* f4i = reinterpret_cast<const float4*>(fi);
+        const float4* f4j = reinterpret_cast<const float4*>(fj);
+        for (int e = lane; e < (c >> 2); e += 32) {
+          const float4 a = __ldg(f4i + e), b = __ldg(f4j + e);
+          dot = fmaf(a.x, b.x, dot); dot = fmaf(a.y, b.y, dot); dot = fmaf(a.z, b.z, dot); dot = fmaf(a.w, b.w, dot);
+        }
+      } else {
+        for (int e = lane; e < c; e += 32) dot = fmaf(__ldg(fi + e), __ldg(fj + e), dot);
+      }
+      dot = warp_sum(dot);
+      if (lane == 0) {
+        const float sim = fmaxf(dot, 0.0f);
+        // ((inter * s) / area) * s  — the reference's association, for both rows of the pair; all values are
+        // >= 0, so the row max is an integer atomicMax on the float bits
+        const float num = __fmul_rn((float)inter, sim);
+        atomicMax(reinterpret_cast<int*>(ios + i), __float_as_int(__fmul_rn(__fdiv_rn(num, (float)me.area), sim)));
+        atomicMax(reinterpret_cast<int*>(ios + j), __float_as_int(__fmul_rn(__fdiv_rn(num, (float)mj.area), sim)));
+      }
+    }
+  }
+}
+
+// Pairs with a LARGE overlap window (> kIosBigWords words): one CTA per pair (grid-stride over the big list, which
+// grows from the back of the pair buffer): the window is spread over all threads with four load pairs in flight,
+// one block reduction.  A single warp would take tens of microseconds on a 1000 x 32-word window.
+__global__ void __launch_bounds__(kIosThreads)
+ios_eval_big_kernel(const uint32_t* __restrict__ bits_full, const IosMeta* __restrict__ meta,
                 const int2* __restrict__ pairs, const int32_t* __restrict__ n_pairs, int max_pairs, int max_sel, int oh,
                 int ow, const float* __restrict__ obj_feats, int c, float* __restrict__ ios,
                 int32_t* __restrict__ inter_out) {
@@ -96,9 +183,9 @@ ios_eval_kernel(const uint32_t* __restrict__ bits_full, const IosMeta* __restric
   const int lane = lane_id(), warp = warp_id();
   constexpr int kWarps = kIosThreads / 32;
   const int ow_words = (ow + 31) >> 5;
-  const int np = min(*n_pairs, max_pairs);
+  const int np = min(n_pairs[1], max_pairs);
   for (int p = blockIdx.x; p < np; p += gridDim.x) {
-    const int2 pr = pairs[p];
+    const int2 pr = pairs[max_pairs - 1 - p];
     const int i = pr.x, j = pr.y;
     const IosMeta me = meta[i], mj = meta[j];
     const int x0 = max(me.box.x, mj.box.x), x1 = min(me.box.z, mj.box.z);
@@ -185,8 +272,11 @@ int launch_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_
   NTTT_LAUNCH_CHECK();
   ios_pairs_kernel<<<max_sel, 256, 0, s>>>(meta, label_sel, n_sel, max_sel, pairs, n_pairs, max_pairs);
   NTTT_LAUNCH_CHECK();
-  ios_eval_kernel<<<148 * 8, kIosThreads, 0, s>>>(bits_full, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats,
+  ios_eval_kernel<<<148 * 4, kIosThreads, 0, s>>>(bits_full, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats,
                                                   c, ios, inter_out);
+  NTTT_LAUNCH_CHECK();
+  ios_eval_big_kernel<<<148, kIosThreads, 0, s>>>(bits_full, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats, c,
+                                                  ios, inter_out);
   NTTT_LAUNCH_CHECK();
   if (finalize) {
     ios_finalize_kernel<<<ceil_div(max_sel, 256), 256, 0, s>>>(area_full, n_sel, max_sel, ios);
