@@ -100,6 +100,7 @@ struct AxisTable {
   int32_t* t_lo = nullptr;   // [in]
   int32_t* t_len = nullptr;  // [in]
   float* t_w = nullptr;      // [in, kMaxScatter]
+  float* t_cum = nullptr;    // [in, kMaxScatter + 1] running sums of t_w (t_cum[e][0] = 0)
   // output coordinates grouped into runs (<= kGrpMax long) that share the same input span (xmin, xsize):
   // rows of one group read the same input rows, so the horizontal pass and the footprint test are shared
   int32_t* grp_of = nullptr;     // [out]  group index of each output coordinate

@@ -289,7 +289,7 @@ __global__ void aa_table_kernel(int in_size, int out_size, int taps, int32_t* xm
 
 // transposed view: for input coordinate e, outputs [t_lo, t_lo+t_len) are those whose span contains e
 __global__ void aa_transpose_kernel(int in_size, int out_size, int taps, const int32_t* xmin, const int32_t* xsize,
-                                    const float* w, int32_t* t_lo, int32_t* t_len, float* t_w) {
+                                    const float* w, int32_t* t_lo, int32_t* t_len, float* t_w, float* t_cum) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= in_size) return;
   int lo = -1, hi = -1;
@@ -307,6 +307,12 @@ __global__ void aa_transpose_kernel(int in_size, int out_size, int taps, const i
     float v = 0.0f;
     if (lo >= 0 && x <= hi && e >= xmin[x] && e < xmin[x] + xsize[x]) v = w[(size_t)x * taps + (e - xmin[x])];
     t_w[(size_t)e * kMaxScatter + t] = v;
+  }
+  float c = 0.0f;  // running sums, in the order project_masks_kernel used to accumulate them per CTA
+  t_cum[(size_t)e * (kMaxScatter + 1)] = 0.0f;
+  for (int t = 0; t < kMaxScatter; ++t) {
+    c += t_w[(size_t)e * kMaxScatter + t];
+    t_cum[(size_t)e * (kMaxScatter + 1) + t + 1] = c;
   }
 }
 
@@ -351,12 +357,13 @@ int build_axis_table(AxisTable& t, int in_size, int out_size, cudaStream_t s) {
   NTTT_CUDA(cudaMalloc(&t.t_lo, sizeof(int32_t) * in_size));
   NTTT_CUDA(cudaMalloc(&t.t_len, sizeof(int32_t) * in_size));
   NTTT_CUDA(cudaMalloc(&t.t_w, sizeof(float) * (size_t)in_size * kMaxScatter));
+  NTTT_CUDA(cudaMalloc(&t.t_cum, sizeof(float) * (size_t)in_size * (kMaxScatter + 1)));
   NTTT_CUDA(cudaMalloc(&t.grp_of, sizeof(int32_t) * out_size));
   NTTT_CUDA(cudaMalloc(&t.grp_start, sizeof(int32_t) * ((size_t)out_size + 1)));
   aa_table_kernel<<<ceil_div(out_size, 128), 128, 0, s>>>(in_size, out_size, t.taps, t.xmin, t.xsize, t.w);
   NTTT_LAUNCH_CHECK();
   aa_transpose_kernel<<<ceil_div(in_size, 128), 128, 0, s>>>(in_size, out_size, t.taps, t.xmin, t.xsize, t.w, t.t_lo,
-                                                            t.t_len, t.t_w);
+                                                            t.t_len, t.t_w, t.t_cum);
   NTTT_LAUNCH_CHECK();
   aa_group_kernel<<<1, 32, 0, s>>>(out_size, t.xmin, t.xsize, t.grp_of, t.grp_start);
   NTTT_LAUNCH_CHECK();
@@ -370,7 +377,7 @@ int build_axis_table(AxisTable& t, int in_size, int out_size, cudaStream_t s) {
 }
 
 void free_axis_table(AxisTable& t) {
-  cudaFree(t.xmin); cudaFree(t.xsize); cudaFree(t.w); cudaFree(t.t_lo); cudaFree(t.t_len); cudaFree(t.t_w);
+  cudaFree(t.xmin); cudaFree(t.xsize); cudaFree(t.w); cudaFree(t.t_lo); cudaFree(t.t_len); cudaFree(t.t_w); cudaFree(t.t_cum);
   cudaFree(t.grp_of); cudaFree(t.grp_start);
   if (t.pk) cudaFree(t.pk);
   t = AxisTable{};
@@ -386,7 +393,7 @@ void free_axis_table(AxisTable& t) {
 constexpr int kProjThreads = 256;
 
 struct ProjTables {
-  const int32_t* x_lo; const int32_t* x_len; const float* x_w;
+  const int32_t* x_lo; const int32_t* x_len; const float* x_cum;  // running sums of the column weights
   const int32_t* y_lo; const int32_t* y_len; const float* y_w;
 };
 
@@ -418,14 +425,14 @@ __global__ void __launch_bounds__(kProjThreads)
 project_masks_kernel(const uint32_t* __restrict__ bits, const int32_t* __restrict__ box, int h, int words_per_row,
                      int eh, int ew, ProjTables t, void* __restrict__ out, int stride_or_kp) {
   extern __shared__ uint32_t smem[];
-  // layout: x_lo[ew] x_len[ew] y_lo[eh] y_len[eh] | x_cum[ew*kCum] y_w[eh*S] | bits[h*wpr] | row[h*ew]
+  // layout: x_lo[ew] x_len[ew] y_lo[eh] y_len[eh] | bits[h*wpr] | row[h*ew]
+  // (the weight tables — running column sums, row weights — are the same for every mask and are read through L1
+  // from the prebuilt global tables instead of being re-staged by each CTA)
   int* s_xlo = reinterpret_cast<int*>(smem);
   int* s_xlen = s_xlo + ew;
   int* s_ylo = s_xlen + ew;
   int* s_ylen = s_ylo + eh;
-  float* s_xc = reinterpret_cast<float*>(s_ylen + eh);
-  float* s_yw = s_xc + ew * kCum;
-  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_yw + eh * kMaxScatter);
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_ylen + eh);
   float* s_row = reinterpret_cast<float*>(s_bits + h * words_per_row);
   const int n = blockIdx.x;
   const int lane = lane_id(), warp = warp_id();
@@ -451,12 +458,6 @@ project_masks_kernel(const uint32_t* __restrict__ bits, const int32_t* __restric
 
   for (int i = threadIdx.x; i < ew; i += kProjThreads) { s_xlo[i] = t.x_lo[i]; s_xlen[i] = min(t.x_len[i], kMaxScatter); }
   for (int i = threadIdx.x; i < eh; i += kProjThreads) { s_ylo[i] = t.y_lo[i]; s_ylen[i] = min(t.y_len[i], kMaxScatter); }
-  for (int i = threadIdx.x; i < eh * kMaxScatter; i += kProjThreads) s_yw[i] = t.y_w[i];
-  for (int ex = threadIdx.x; ex < ew; ex += kProjThreads) {  // prefix sums of the column weights
-    float c = 0.0f;
-    s_xc[ex * kCum] = 0.0f;
-    for (int q = 0; q < kMaxScatter; ++q) { c += t.x_w[ex * kMaxScatter + q]; s_xc[ex * kCum + q + 1] = c; }
-  }
   const int nrows = bottom - top + 1;
   for (int i = threadIdx.x; i < nrows * words_per_row; i += kProjThreads) s_bits[i] = src[top * words_per_row + i];
   __syncthreads();
@@ -477,13 +478,13 @@ project_masks_kernel(const uint32_t* __restrict__ bits, const int32_t* __restric
       const uint32_t wb = (w0 + 1 < words_per_row) ? row[w0 + 1] : 0u;
       uint32_t f = __funnelshift_r(wa, wb, sh);
       f &= (len >= 32) ? 0xffffffffu : ((1u << len) - 1u);
-      const float* cw = s_xc + ex * kCum;
+      const float* cw = t.x_cum + ex * kCum;
       float acc = 0.0f;
       while (f) {  // one iteration per run of set bits
         const int a = __ffs(f) - 1;
         const uint32_t g = ~(f >> a);
         const int run = g ? __ffs(g) - 1 : 32 - a;
-        acc += cw[a + run] - cw[a];
+        acc += __ldg(cw + a + run) - __ldg(cw + a);
         f = (a + run >= 32) ? 0u : (f >> (a + run)) << (a + run);
       }
       s_row[yy * nex + (ex - ex_lo)] = acc;
@@ -493,11 +494,11 @@ project_masks_kernel(const uint32_t* __restrict__ bits, const int32_t* __restric
   // vertical pass over the reachable cells + output
   for (int ey = ey_lo + warp; ey <= ey_hi; ey += kWarps) {
     const int lo = s_ylo[ey], len = s_ylen[ey];
-    const float* wv = s_yw + ey * kMaxScatter;
+    const float* wv = t.y_w + ey * kMaxScatter;
     const int ta = max(top - lo, 0), tb = min(bottom - lo + 1, len);
     for (int ex = ex_lo + lane; ex <= ex_hi; ex += 32) {
       float acc = 0.0f;
-      for (int q = ta; q < tb; ++q) acc = fmaf(wv[q], s_row[(lo + q - top) * nex + (ex - ex_lo)], acc);
+      for (int q = ta; q < tb; ++q) acc = fmaf(__ldg(wv + q), s_row[(lo + q - top) * nex + (ex - ex_lo)], acc);
       const int item = ey * ew + ex;
       if (kSplit) {
         __nv_bfloat16 hi, lo16;
@@ -514,7 +515,7 @@ project_masks_kernel(const uint32_t* __restrict__ bits, const int32_t* __restric
 }
 
 static size_t project_smem_bytes(int h, int w, int eh, int ew) {
-  return sizeof(int) * 2 * (size_t)(ew + eh) + sizeof(float) * ((size_t)kCum * ew + (size_t)kMaxScatter * eh) +
+  return sizeof(int) * 2 * (size_t)(ew + eh) +
          sizeof(uint32_t) * (size_t)h * (w / 32) + sizeof(float) * (size_t)h * ew;
 }
 
@@ -525,7 +526,7 @@ int launch_project_masks(const AxisTable& tx, const AxisTable& ty, const uint32_
   if (w % 32 != 0 || eh > 64 || ew > 64) return NTTT_EUNSUPPORTED;
   const size_t smem = project_smem_bytes(h, w, eh, ew);
   if (smem > 200 * 1024) return NTTT_EUNSUPPORTED;
-  ProjTables t{tx.t_lo, tx.t_len, tx.t_w, ty.t_lo, ty.t_len, ty.t_w};
+  ProjTables t{tx.t_lo, tx.t_len, tx.t_cum, ty.t_lo, ty.t_len, ty.t_w};
   if (split) {
     if (smem > 48 * 1024)
       NTTT_CUDA(cudaFuncSetAttribute(project_masks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
