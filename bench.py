@@ -54,6 +54,8 @@ def parse():
                     "bank (config 4); --n-masks 4096 = points_per_side 64 (config 5); the default is config 2")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from the host instead of replaying "
                     "the captured CUDA graph of the stage")
+    ap.add_argument("--value-only", action="store_true", help="A/B helper: measure `value` only and print a short line "
+                    "(no e2e legs, no roofline / cpu_baseline) - not the driver's contract line")
     return ap.parse_args()
 
 
@@ -279,6 +281,15 @@ def main():
     launches = launches_per_image * args.steps * B
     images = world * args.steps * B
     value = images / (ms_total / 1e3)
+
+    if args.value_only:
+        if rank == 0:
+            print(json.dumps(dict(metric=METRIC, value_only=True, value=value, us_per_image=1e3 * ms_total / (args.steps * B),
+                                  n_gpus=world, steps=args.steps, batch=B, streams=S, clocks=clock_info,
+                                  env={k: v for k, v in os.environ.items() if k.startswith("NTTT_")})))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     # ---- e2e: pinned host inputs -> device -> stage -> pinned host outputs, every step ----------------------
     n_out = WORKLOAD["num_out_instance"]

@@ -4,6 +4,7 @@
 // Reference: Sam2MatchingBaseline_noAMG.py:548-549 (lr_masks > 0), :551-558 (feature upsample),
 // sam2/utils/amg.py:158-178 (stability), :305-348 (boxes).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -186,9 +187,197 @@ lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mas
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K1b: the variant the stage launches (no stability counts).  Same ring, same outputs, a third of the instructions.
+//
+// Per logit the loop above spends ~6 ALU-pipe instructions (compare, select, range test, two ORs).  Here a logit costs
+// two: one funnel shift that appends its SIGN bit to a per-thread bit string, and half of a 3-input integer min plus
+// half of a 3-input integer max over the raw bit patterns (VIMNMX3).  For every float except +0.0 and a positive NaN,
+// `v > 0` is the complement of the sign bit; and the running signed max / unsigned min of the bit patterns are exactly
+// the largest and the smallest positive logit seen, which is all the finite-range ("safe") flag needs.  A thread whose
+// min/max reveal a +0.0 or a positive NaN switches, for the rest of its mask, to the literal per-element arithmetic of
+// the kernel above, so masks, boxes, areas and flags are identical in every case.
+//
+// The 8 lanes that share a 32-pixel word do not OR-reduce four words with 12 shuffles; they run a 3-step
+// reduce-scatter (4 shuffles in total for four words): each step halves the set of words a lane is responsible for
+// and doubles the lanes it has merged.  Which float4 a lane reads for its "slot" j is chosen (addresses are computed
+// once, all reads stay 128-bit and conflict-free) so that every merge is a byte permute or one LOP3:
+//   u* = 2*g2 + g0 is the word lane g = (g2 g1 g0) ends up holding; slot j holds word u = j ^ u*;
+//   slots 2,3 go to lane g^4, then slot 1 to lane g^1 (nibble interleave), then the half word to lane g^2;
+//   words with odd u are held by odd lanes, whose own nibble is the LOW one of a byte, so for those words lane g reads
+//   float4 g^1 of the word instead of g.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pk_exact_negbits(const uint4& v, uint32_t& unsafe) {
+  constexpr uint32_t kLoBits = 0x0D800000u, kSpan = 0x71800000u - 0x0D800001u;
+  const uint32_t e[4] = {v.x, v.y, v.z, v.w};
+  uint32_t nib = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool pos = __uint_as_float(e[k]) > 0.0f;
+    nib |= (uint32_t)(!pos) << k;
+    unsafe |= (uint32_t)(pos && !((e[k] - (kLoBits + 1u)) < kSpan));
+  }
+  return nib;
+}
+
+__device__ __forceinline__ uint32_t pk_sign_chain(uint32_t acc, const uint4& v) {  // appends w,z,y,x: x lands in bit 0
+  acc = __funnelshift_l(v.w, acc, 1);
+  acc = __funnelshift_l(v.z, acc, 1);
+  acc = __funnelshift_l(v.y, acc, 1);
+  acc = __funnelshift_l(v.x, acc, 1);
+  return acc;
+}
+
+__global__ void __launch_bounds__(kPackBlock, 3)
+lowres_pack_fast_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mask */, int words_per_row,
+                        uint32_t* __restrict__ bits, int32_t* __restrict__ area, int32_t* __restrict__ box,
+                        int32_t* __restrict__ flags, const float* __restrict__ gate, float gate_min,
+                        const float* const* __restrict__ mask_ptr) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  if (gate && !(gate[blockIdx.x] > gate_min)) {
+    const int nw = p4 >> 3;
+    uint4* d4 = reinterpret_cast<uint4*>(bits + (size_t)blockIdx.x * nw);
+    for (int i = threadIdx.x; i < (nw >> 2); i += kPackBlock) d4[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+      area[blockIdx.x] = 0;
+      flags[blockIdx.x] = 1;
+      reinterpret_cast<int4*>(box)[blockIdx.x] = make_int4(0, 0, 0, 0);
+    }
+    return;
+  }
+  uint4* s_stage = reinterpret_cast<uint4*>(s_raw);
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_raw + (size_t)kPackStages * kPackStageBytes);
+  __shared__ uint64_t s_full[kPackStages], s_empty[kPackStages];
+  __shared__ int s_red[8];  // area, -, -, unsafe, minx, miny, maxx, maxy
+  const int n = blockIdx.x;
+  const float4* src = mask_ptr ? reinterpret_cast<const float4*>(mask_ptr[n]) : logits + (size_t)n * p4;
+  const int lane = lane_id(), warp = warp_id();
+  const int n_stages = (p4 + kPackStageF4 - 1) / kPackStageF4;
+  if (threadIdx.x < 8) s_red[threadIdx.x] = (threadIdx.x == 4 || threadIdx.x == 5) ? 0x7fffffff : (threadIdx.x >= 6 ? -1 : 0);
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < kPackStages; ++q) { pk_mbar_init(&s_full[q], 1); pk_mbar_init(&s_empty[q], kPackThreads / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  uint32_t unsafe = 0;
+  if (warp == kPackThreads / 32) {
+    if (lane == 0) {
+      for (int st = 0; st < n_stages; ++st) {
+        const int q = st % kPackStages;
+        pk_mbar_wait(&s_empty[q], ((st / kPackStages) & 1) ^ 1);
+        const int f4 = min(kPackStageF4, p4 - st * kPackStageF4);
+        pk_mbar_expect_tx(&s_full[q], (uint32_t)f4 * 16u);
+        pk_bulk_load(s_stage + (size_t)q * kPackStageF4, src + (size_t)st * kPackStageF4, (uint32_t)f4 * 16u, &s_full[q]);
+      }
+    }
+  } else {
+    const int g = lane & 7;
+    const int ustar = ((g >> 2) << 1) | (g & 1);
+    const int grp = threadIdx.x & ~7;  // first float4 of this lane group's word, within one 256-float4 slab
+    int off[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int u = j ^ ustar;
+      off[j] = u * kPackThreads + grp + (g ^ (u & 1));
+    }
+    const uint32_t sel_a = (g & 4) ? 0x04u : 0x40u;        // bytes {mine, partner's} ordered by g2
+    const uint32_t sel_c = (g & 2) ? 0x1504u : 0x5140u;    // half words interleaved by g1
+    const int word_slot = ustar * (kPackThreads / 8) + (threadIdx.x >> 3);
+    int mx = (int)0x80000000;      // largest bit pattern as a signed int  = largest positive logit (or +inf / +NaN)
+    uint32_t mn = 0xffffffffu;     // smallest bit pattern as an unsigned  = smallest non-negative logit (+0.0 -> 0)
+    bool exact = false;
+    for (int st = 0; st < n_stages; ++st) {
+      const int q = st % kPackStages;
+      pk_mbar_wait(&s_full[q], (st / kPackStages) & 1);
+      const uint4* buf = s_stage + (size_t)q * kPackStageF4;
+      const int f0 = st * kPackStageF4;
+      uint4 v[4];
+      if (f0 + kPackStageF4 <= p4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = buf[off[j]];
+      } else {  // short last stage: the tail of the slot is stale, read -1.0f (not positive, invisible to min/max)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          v[j] = (f0 + (off[j] & ~7) < p4) ? buf[off[j]] : make_uint4(0xbf800000u, 0xbf800000u, 0xbf800000u, 0xbf800000u);
+      }
+      __syncwarp();
+      if (lane == 0) pk_mbar_arrive(&s_empty[q]);
+      uint32_t a01 = 0, a23 = 0;  // sign bits: slot 0 in bits 0-3, slot 1 in bits 4-7 (resp. slots 2, 3)
+      if (!exact) {
+        a01 = pk_sign_chain(pk_sign_chain(0u, v[1]), v[0]);
+        a23 = pk_sign_chain(pk_sign_chain(0u, v[3]), v[2]);
+        int mx1 = mx;
+        uint32_t mn1 = mn;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          mx1 = __vimax3_s32(mx1, (int)v[j].x, (int)v[j].y);
+          mx1 = __vimax3_s32(mx1, (int)v[j].z, (int)v[j].w);
+          mn1 = __vimin3_u32(mn1, v[j].x, v[j].y);
+          mn1 = __vimin3_u32(mn1, v[j].z, v[j].w);
+        }
+        if (mn1 == 0u || mx1 > 0x7f800000) exact = true;  // +0.0 or a positive NaN: sign bit != !(v > 0)
+        else { mx = mx1; mn = mn1; }
+      }
+      if (exact) {
+        a01 = pk_exact_negbits(v[0], unsafe) | (pk_exact_negbits(v[1], unsafe) << 4);
+        a23 = pk_exact_negbits(v[2], unsafe) | (pk_exact_negbits(v[3], unsafe) << 4);
+      }
+      const uint32_t r = __shfl_xor_sync(kFull, a23, 4);
+      const uint32_t y = __byte_perm(a01, r, sel_a);
+      const uint32_t z = __shfl_xor_sync(kFull, y, 1);
+      const uint32_t hv = ~((y & 0x0F0Fu) | (z & 0xF0F0u));  // complement: sign bits -> (v > 0) bits
+      const uint32_t z2 = __shfl_xor_sync(kFull, hv, 2);
+      const uint32_t word = __byte_perm(hv, z2, sel_c);
+      if (!(g & 2) && f0 + ustar * kPackThreads + grp < p4) s_bits[st * (kPackStageF4 / 8) + word_slot] = word;
+    }
+    // positives seen by the sign-bit path: safe iff 2^-100 < v < 2^100 for all of them
+    unsafe |= (uint32_t)(mx >= 0x71800000 || mn < 0x0D800001u);
+  }
+  __syncthreads();
+  const int n_words = p4 >> 3;
+  int a = 0, minx = 0x7fffffff, miny = 0x7fffffff, maxx = -1, maxy = -1;
+  for (int wi = threadIdx.x; wi < n_words; wi += kPackBlock) {
+    const uint32_t word = s_bits[wi];
+    if (word) {
+      a += __popc(word);
+      const int row = wi / words_per_row;
+      const int x0 = (wi - row * words_per_row) * 32;
+      minx = min(minx, x0 + __ffs(word) - 1);
+      maxx = max(maxx, x0 + 31 - __clz(word));
+      miny = min(miny, row);
+      maxy = max(maxy, row);
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(bits + (size_t)n * n_words);
+  const uint4* s4 = reinterpret_cast<const uint4*>(s_bits);
+  for (int i = threadIdx.x; i < (n_words >> 2); i += kPackBlock) dst[i] = s4[i];
+  a = warp_sum(a);
+  unsafe = (uint32_t)warp_max((int)unsafe);
+  minx = warp_min(minx); miny = warp_min(miny); maxx = warp_max(maxx); maxy = warp_max(maxy);
+  if (lane == 0) {
+    atomicAdd(&s_red[0], a); atomicMax(&s_red[3], (int)unsafe);
+    atomicMin(&s_red[4], minx); atomicMin(&s_red[5], miny); atomicMax(&s_red[6], maxx); atomicMax(&s_red[7], maxy);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    area[n] = s_red[0];
+    flags[n] = s_red[3] ? 0 : 1;
+    const bool empty = s_red[6] < s_red[4] || s_red[7] < s_red[5];
+    int4 b = empty ? make_int4(0, 0, 0, 0) : make_int4(s_red[4], s_red[5], s_red[6], s_red[7]);
+    reinterpret_cast<int4*>(box)[n] = b;
+  }
+}
+
 // stab may be NULL: the stability counts (sam2/utils/amg.py:158-178) are not read on the noAMG path
 // gate (nullable): per-mask score; masks with !(gate[n] > gate_min) are skipped and published as empty
 // mask_ptr (nullable, device [n]): mask n is read from mask_ptr[n] (16-byte aligned) instead of logits + n*h*w
+// NTTT_PACK_LITERAL=1 keeps the per-element kernel for the no-stability case too (A/B measurements)
+static bool pack_use_literal() {
+  static const bool v = [] { const char* e = getenv("NTTT_PACK_LITERAL"); return e && e[0] == '1'; }();
+  return v;
+}
+
 int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits,
                        int32_t* area, int32_t* box, int32_t* stab, int32_t* flags, const float* gate, float gate_min,
                        const float* const* mask_ptr, cudaStream_t s) {
@@ -202,6 +391,10 @@ int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, floa
     NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lowres_pack_kernel<true><<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area, box,
                                                         stab, flags, gate, gate_min, mask_ptr);
+  } else if (!pack_use_literal()) {
+    NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lowres_pack_fast_kernel<<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, bits, area, box, flags, gate, gate_min,
+                                                        mask_ptr);
   } else {
     NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lowres_pack_kernel<false><<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area,

@@ -56,6 +56,47 @@ def test_threshold_pack_bit_exact(ops, synth, n):
     assert flags.cpu().numpy()[0] == 0 and (flags.cpu().numpy()[1:] == 1).all()  # the inf makes mask 0 unsafe
 
 
+@pytest.mark.parametrize("hw", [(256, 256), (64, 96)])
+def test_threshold_pack_sign_bit_path_special_values(ops, hw):
+    """The variant the stage launches (no stability counts) takes `v > 0` from the sign bit and the safe flag from
+    integer min/max of the bit patterns; +0.0 and positive NaNs switch a thread to the literal arithmetic.  Every
+    special value is planted at every lane / slot position class (random pixels of 64 masks) and the five outputs are
+    compared with the literal kernel (want_stab=True) and with numpy."""
+    h, w = hw
+    gen = torch.Generator().manual_seed(77 + h)
+    n = 64
+    logits = torch.randn((n, h, w), generator=gen) * 4.0 - 1.0
+    specials = [0.0, -0.0, float("nan"), -float("nan"), float("inf"), -float("inf"), 1e-40, -1e-40, 1e-35, 7.0e-31,
+                8.0e-31, 1.26e30, 1.27e30, 3e38, -3e38, 1.1754944e-38]
+    expect_unsafe = np.zeros(n, dtype=bool)
+    lo, hi = np.float32(2.0) ** -100, np.float32(2.0) ** 100
+    for i in range(n):
+        if i < 4:
+            continue  # plain masks
+        k = int(torch.randint(1, 6, (1,), generator=gen))
+        ys = torch.randint(0, h, (k,), generator=gen)
+        xs = torch.randint(0, w, (k,), generator=gen)
+        for y, x in zip(ys.tolist(), xs.tolist()):
+            logits[i, y, x] = specials[(i + y + x) % len(specials)]
+    logits[5] = 0.0                       # a mask of zeros: empty, safe
+    logits[6] = float("nan")              # all NaN: empty
+    logits[7] = torch.where(logits[7] > 0, torch.tensor(float("inf")), logits[7])
+    v = logits.numpy()
+    with np.errstate(invalid="ignore"):
+        pos = v > 0
+        expect_unsafe = (pos & ~((v > lo) & (v < hi))).reshape(n, -1).any(axis=1)
+    d = logits.to(DEV)
+    lit = ops.threshold_pack(d, 0.0, 1.0, want_stab=True)
+    fast = ops.threshold_pack(d, 0.0, 1.0, want_stab=False)
+    for name, a, b in zip(("bits", "area", "box", "stab", "flags"), lit, fast):
+        if name == "stab":
+            continue
+        assert torch.equal(a, b), name
+    assert np.array_equal(_unpack_lr(fast[0], h, w), pos.astype(np.uint8))
+    assert np.array_equal(fast[4].cpu().numpy() == 0, expect_unsafe)
+    assert expect_unsafe.any() and (~expect_unsafe).any()
+
+
 def test_threshold_pack_empty_batch(ops):
     bits, area, *_ = ops.threshold_pack(torch.zeros((0, 256, 256), device=DEV))
     assert bits.shape[0] == 0 and area.shape[0] == 0
