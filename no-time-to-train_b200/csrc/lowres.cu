@@ -372,12 +372,12 @@ lowres_pack_fast_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 pe
 // stab may be NULL: the stability counts (sam2/utils/amg.py:158-178) are not read on the noAMG path
 // gate (nullable): per-mask score; masks with !(gate[n] > gate_min) are skipped and published as empty
 // mask_ptr (nullable, device [n]): mask n is read from mask_ptr[n] (16-byte aligned) instead of logits + n*h*w
-// NTTT_PACK_LITERAL=1 keeps the per-element kernel for the no-stability case too (A/B measurements)
-static bool pack_use_literal() {
-  static const bool v = [] { const char* e = getenv("NTTT_PACK_LITERAL"); return e && e[0] == '1'; }();
+// NTTT_PACK_MODE (A/B measurements): 0/1 = sign-bit kernel (default), 2 = literal per-element kernel.  Requests for the
+// stability counts always take the literal kernel.
+static int pack_mode() {
+  static const int v = [] { const char* e = getenv("NTTT_PACK_MODE"); return e ? atoi(e) : 0; }();
   return v;
 }
-
 int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits,
                        int32_t* area, int32_t* box, int32_t* stab, int32_t* flags, const float* gate, float gate_min,
                        const float* const* mask_ptr, cudaStream_t s) {
@@ -391,7 +391,7 @@ int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, floa
     NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lowres_pack_kernel<true><<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area, box,
                                                         stab, flags, gate, gate_min, mask_ptr);
-  } else if (!pack_use_literal()) {
+  } else if (pack_mode() <= 1) {
     NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lowres_pack_fast_kernel<<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, bits, area, box, flags, gate, gate_min,
                                                         mask_ptr);
