@@ -419,7 +419,7 @@ def main():
                 traffic = prof["traffic_bytes_per_launch"]
         except Exception:
             pass
-        roofline = dict(bound="hbm", kernel="lowres_pack_kernel", achieved=achieved, peak=peak, unit="GB/s",
+        roofline = dict(bound="hbm", kernel="lowres_pack_fast_kernel", achieved=achieved, peak=peak, unit="GB/s",
                         frac=achieved / peak, traffic=traffic, peak_source=peak_src, alg_bytes_per_launch=alg_bytes,
                         us_per_launch=1e3 * k_ms,
                         note="peak is the driver's copy bandwidth (read+write); a read-only stream of the same 268 MB "

@@ -35,7 +35,7 @@ def main() -> None:
         a[0] += 1
         a[1] += us
     ours = {k: v for k, v in agg.items() if "at::" not in k and "cub::" not in k and not k.startswith(SETUP)}
-    images = max(v[0] for k, v in ours.items() if k.startswith("lowres_pack_kernel"))
+    images = max(v[0] for k, v in ours.items() if k.startswith("lowres_pack"))
     stage_us = sum(v[1] for v in ours.values()) / images
     print(f"# ncu launch list (gpu__time_duration.sum, --clock-control none) of `{what}`")
     print("# per-kernel average over the captured launches; cold-cache and serialised: compare SHARES, not absolutes")
