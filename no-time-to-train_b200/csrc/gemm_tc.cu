@@ -329,27 +329,34 @@ split_rows_kernel(const float* __restrict__ X, int ld, int rows, int k, int kp, 
   }
 }
 
-// X [k, rows] (row-major, ld) -> out [rows, 3*kp]: transpose + split (for feat [E, C] -> [C, 3*Ep])
+// X [k, rows] (row-major, ld) -> out [rows, 3*kp]: transpose + split (for feat [E, C] -> [C, 3*Ep]).
+// 64 (k) x 32 (rows) tiles: 128-byte coalesced reads along `rows`, and every thread writes two consecutive k as one
+// bf16x2, so a warp stores 128 contiguous bytes per segment (kp is a multiple of 64).
 __global__ void __launch_bounds__(256)
 split_transpose_kernel(const float* __restrict__ X, int ld, int rows, int k, int kp, int mode,
                        __nv_bfloat16* __restrict__ out) {
-  __shared__ float tile[32][33];
-  const int k0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  __shared__ float tile[64][33];
+  const int k0 = blockIdx.x * 64, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (int j = ty; j < 32; j += 8) {
+#pragma unroll
+  for (int j = ty; j < 64; j += 8) {
     const int kk = k0 + j, rr = r0 + tx;
     tile[j][tx] = (kk < k && rr < rows) ? X[(size_t)kk * ld + rr] : 0.0f;
   }
   __syncthreads();
+  const int kk = k0 + 2 * tx;
+#pragma unroll
   for (int j = ty; j < 32; j += 8) {
-    const int rr = r0 + j, kk = k0 + tx;
-    if (rr < rows && kk < kp) {
-      __nv_bfloat16 hi, lo;
-      split_bf16(tile[tx][j], hi, lo);
-      __nv_bfloat16* dst = out + (size_t)rr * 3 * kp;
-      dst[kk] = hi;
-      dst[kp + kk] = mode == 0 ? hi : lo;
-      dst[2 * kp + kk] = mode == 0 ? lo : hi;
+    const int rr = r0 + j;
+    if (rr < rows && kk + 1 < kp) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(tile[2 * tx][j], h0, l0);
+      split_bf16(tile[2 * tx + 1][j], h1, l1);
+      const __nv_bfloat162 hi = __halves2bfloat162(h0, h1), lo = __halves2bfloat162(l0, l1);
+      __nv_bfloat16* dst = out + (size_t)rr * 3 * kp + kk;
+      *reinterpret_cast<__nv_bfloat162*>(dst) = hi;
+      *reinterpret_cast<__nv_bfloat162*>(dst + kp) = mode == 0 ? hi : lo;
+      *reinterpret_cast<__nv_bfloat162*>(dst + 2 * kp) = mode == 0 ? lo : hi;
     }
   }
 }
@@ -364,7 +371,8 @@ int launch_split_rows(const float* X, int ld, int rows, int k, int kp, int mode,
 
 int launch_split_transpose(const float* X, int ld, int rows, int k, int kp, int mode, void* out, cudaStream_t s) {
   if (rows <= 0) return NTTT_OK;
-  dim3 grid(ceil_div(kp, 32), ceil_div(rows, 32));
+  if (kp % 64 != 0) return NTTT_EINVAL;  // (callers pad K to 64: the GEMM's K block)
+  dim3 grid(kp / 64, ceil_div(rows, 32));
   split_transpose_kernel<<<grid, 256, 0, s>>>(X, ld, rows, k, kp, mode, static_cast<__nv_bfloat16*>(out));
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
