@@ -18,6 +18,8 @@ namespace nttt {
 
 constexpr int kUpThreads = 128;
 constexpr int kUpMaxSplit = 8;       // grid.x: CTAs available per mask; a mask uses ceil(groups / kUpGroupsPerCta) of them
+constexpr int kUpCols = 8;           // word columns per group slot of a warp
+constexpr int kUpSub = 32 / kUpCols;  // group slots per warp
 constexpr int kUpGroupsPerCta = 32;  // row groups per CTA = 8 per warp: amortises the per-CTA / per-warp set-up
 
 struct UpTables {
@@ -144,9 +146,13 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
   __syncthreads();
 
   int area = 0, minx = kBig, maxx = -1, miny = kBig, maxy = -1;
-  for (int wbase = w0; wbase < w1; wbase += 32) {
+  // A warp works on kUpSub row groups at once: lane = (group slot q, word column): a mask is ~7 words wide, so with one
+  // group per warp three lanes in four idled through the per-group part (spans, footprint test, stores, statistics),
+  // which was as many instructions as the evaluation of the boundary words itself.
+  const int q = lane / kUpCols;
+  for (int wbase = w0; wbase < w1; wbase += kUpCols) {
     // per-lane (= per output word) constants, hoisted out of the row-group loop
-    const int wi = wbase + lane;
+    const int wi = wbase + (lane & (kUpCols - 1));
     const bool active = wi < w1;
     const int x0 = min(wi << 5, ow - 1);
     const int x1 = min(x0 + 31, ow - 1);
@@ -165,16 +171,15 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
     uint32_t colbits = 0;
     for (int cb = chunk0; cb < mt.g1; cb += needed * kUpGroupsPerCta) {
       const int cend = min(cb + kUpGroupsPerCta, mt.g1);
-      for (int g = cb + warp; g < cend; g += kWarps) {
-        // rows [ya, yb) of this group share the input rows [ry0, ry0 + rys)
-        const int ya = max(t.y_grp_start[g], r0), yb = min(t.y_grp_start[g + 1], r1);
+      for (int g0 = cb + warp; g0 < cend; g0 += kWarps * kUpSub) {
+        const int g = g0 + kWarps * q;
+        const bool gvalid = g < cend;
+        // rows [ya, yb) of this group share the input rows [ry0, ry0 + rys)   (no group: ya = yb = r0, nrows = 0)
+        const int ya = gvalid ? max(t.y_grp_start[g], r0) : r0, yb = gvalid ? min(t.y_grp_start[g + 1], r1) : r0;
         const int nrows = yb - ya;
         int ry0, rys;
-        float4 wv[kGrpMax];  // fast path: {., w0, w1, w2} of the group's rows (rows past nrows repeat the last one)
         if (fast_cfg) {
-#pragma unroll
-          for (int j = 0; j < kGrpMax; ++j) wv[j] = __ldg(t.pk_y + (uint32_t)min(ya + j, yb - 1));
-          const int pky = __float_as_int(wv[0].x);
+          const int pky = __float_as_int(__ldg(t.pk_y + (uint32_t)ya).x);
           ry0 = pky & 0xffff;
           rys = pky >> 16;
         } else {
@@ -187,7 +192,7 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
 #pragma unroll
         for (int j = 0; j < kGrpMax; ++j) words[j] = 0;
         bool mixed = false;
-        if (active) {
+        if (active && gvalid) {
           bool all0 = true, all1 = true;
           if (two_words) {
             // (m1 == 0 when the footprint stays inside one low-res word; s_lr has a spare word at the end)
@@ -235,7 +240,10 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
         while (todo) {
           const int src_lane = __ffs(todo) - 1;
           todo &= todo - 1;
-          const int x = ((wbase + src_lane) << 5) + lane;
+          // the word's group: its rows and input rows come from the lane that owns the word
+          const int s_ya = __shfl_sync(kFull, ya, src_lane), s_nrows = __shfl_sync(kFull, nrows, src_lane);
+          const int s_rb = __shfl_sync(kFull, rb, src_lane), s_rys = __shfl_sync(kFull, rys, src_lane);
+          const int x = ((wbase + (src_lane & (kUpCols - 1))) << 5) + lane;
           if (fast_cfg) {
             // Every constant of the pixel in one 128-bit load (records past the width have size 0).  Taps beyond the
             // span are never read; rows / taps beyond it contribute fma(0, 0, acc) = acc, so the arithmetic is exactly
@@ -247,21 +255,23 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
               float acc = 0.0f;
-              if (r < rys) {  // (warp-uniform)
+              if (r < s_rys) {  // (warp-uniform)
                 // records past the image width have cs = 0, cx = 0 and zero weights: their first tap reads a valid
                 // address and the lane's result is masked by `cs > 0` in the ballot
-                const float* q = src + (uint32_t)(rb + cx + r * iw);
-                acc = __fmul_rn(__ldg(q), xt.y);
-                if (cs > 1) acc = __fmaf_rn(__ldg(q + 1), xt.z, acc);
-                if (cs > 2) acc = __fmaf_rn(__ldg(q + 2), xt.w, acc);
+                const float* pl = src + (uint32_t)(s_rb + cx + r * iw);
+                acc = __fmul_rn(__ldg(pl), xt.y);
+                if (cs > 1) acc = __fmaf_rn(__ldg(pl + 1), xt.z, acc);
+                if (cs > 2) acc = __fmaf_rn(__ldg(pl + 2), xt.w, acc);
               }
               T[r] = acc;
             }
 #pragma unroll
             for (int j = 0; j < kGrpMax; ++j) {
-              float acc = __fmul_rn(T[0], wv[j].y);
-              acc = __fmaf_rn(T[1], wv[j].z, acc);
-              acc = __fmaf_rn(T[2], wv[j].w, acc);
+              // {., w0, w1, w2} of the group's rows (rows past its last one repeat it and are dropped at the store)
+              const float4 wv = __ldg(t.pk_y + (uint32_t)min(s_ya + j, s_ya + s_nrows - 1));
+              float acc = __fmul_rn(T[0], wv.y);
+              acc = __fmaf_rn(T[1], wv.z, acc);
+              acc = __fmaf_rn(T[2], wv.w, acc);
               const uint32_t res = __ballot_sync(kFull, cs > 0 && acc > 0.0f);
               if (lane == src_lane) words[j] = res;
             }
@@ -270,20 +280,20 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
           const bool inb = x < ow;
           const int cx = inb ? t.xmin[x] : 0, cs = inb ? t.xsize[x] : 1;
           const float* wx = t.wx + (size_t)(inb ? x : 0) * t.tx;
-          const float* p = src + (rb + cx);
-          if (rys <= kTapsReg) {
+          const float* p = src + (s_rb + cx);
+          if (s_rys <= kTapsReg) {
             // horizontal pass once per group, vertical pass per row
             float T[kTapsReg];
 #pragma unroll
-            for (int r = 0; r < kTapsReg; ++r) T[r] = (r < rys && inb) ? aa_dot(p + (size_t)r * iw, 1, wx, cs) : 0.0f;
+            for (int r = 0; r < kTapsReg; ++r) T[r] = (r < s_rys && inb) ? aa_dot(p + (size_t)r * iw, 1, wx, cs) : 0.0f;
 #pragma unroll
             for (int j = 0; j < kGrpMax; ++j) {
-              if (j < nrows) {
-                const float* wy = t.wy + (size_t)(ya + j) * t.ty;
+              if (j < s_nrows) {
+                const float* wy = t.wy + (size_t)(s_ya + j) * t.ty;
                 float acc = __fmul_rn(T[0], __ldg(wy));
 #pragma unroll
                 for (int r = 1; r < kTapsReg; ++r)
-                  if (r < rys) acc = __fmaf_rn(T[r], __ldg(wy + r), acc);
+                  if (r < s_rys) acc = __fmaf_rn(T[r], __ldg(wy + r), acc);
                 const uint32_t res = __ballot_sync(kFull, inb && acc > 0.0f);
                 if (lane == src_lane) words[j] = res;
               }
@@ -291,12 +301,12 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
           } else {
 #pragma unroll
             for (int j = 0; j < kGrpMax; ++j) {
-              if (j < nrows) {
-                const float* wy = t.wy + (size_t)(ya + j) * t.ty;
+              if (j < s_nrows) {
+                const float* wy = t.wy + (size_t)(s_ya + j) * t.ty;
                 float acc = 0.0f;
                 if (inb) {
                   acc = __fmul_rn(aa_dot(p, 1, wx, cs), __ldg(wy));
-                  for (int r = 1; r < rys; ++r) acc = __fmaf_rn(aa_dot(p + (size_t)r * iw, 1, wx, cs), __ldg(wy + r), acc);
+                  for (int r = 1; r < s_rys; ++r) acc = __fmaf_rn(aa_dot(p + (size_t)r * iw, 1, wx, cs), __ldg(wy + r), acc);
                 }
                 const uint32_t res = __ballot_sync(kFull, inb && acc > 0.0f);
                 if (lane == src_lane) words[j] = res;
