@@ -192,6 +192,9 @@ def test_upsample_threshold_pack_bit_exact(ops, synth, ori_hw):
     logits[9] = 5.0          # all-positive mask exercises the uniform-ones shortcut
     logits[10, :, :] = -1.0
     logits[10, 100:140, 90:200] = float("inf")  # non-finite positives: shortcut must be disabled (flags)
+    # salt-and-pepper over the whole frame: every output word of every row group is a boundary word, over the full
+    # width (all word-column chunks of a warp's group slots, all CTAs of a mask)
+    logits[11] = torch.randn(256, 256, generator=gen) + 0.2
     d = logits.to(DEV)
     bits, area, box, stab, flags = ops.threshold_pack(d)
     sel = torch.tensor([5, 0, 1, 2, 3, 9, 10, 11, 12, 20, 23, 7], dtype=torch.int32, device=DEV)
