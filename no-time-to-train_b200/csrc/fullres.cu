@@ -97,10 +97,11 @@ __device__ __forceinline__ int up_ctas_needed(int n_groups) {
 }
 
 // grid (kUpMaxSplit, max_sel).  A mask with G row groups is served by ceil(G / 32) CTAs (the others exit at once); a
-// CTA (4 warps) takes 32 consecutive groups, warp w the groups w, w+4, ... of them; a lane owns one 32-pixel output word
-// column.  Per group: the footprint test on the low-res bits (shared memory) classifies each word as all-0, all-1 or
-// mixed; mixed words are evaluated one at a time with lane = pixel: horizontal pass of the shared input rows once,
-// vertical pass per output row, one ballot per row.
+// CTA (4 warps) takes 32 consecutive groups, warp w the groups w, w+4, ... of them, FOUR at a time: lane = (group slot,
+// word column), 8 columns per slot (wider masks loop over column chunks).  Per group: the footprint test on the low-res
+// bits (shared memory) classifies each word as all-0, all-1 or mixed; mixed words are evaluated one at a time by the
+// whole warp with lane = pixel (the owning lane broadcasts its group's rows): horizontal pass of the shared input rows
+// once, vertical pass per output row, one ballot per row.
 // All indices inside the loops are 32-bit (one 64-bit base per array): 64-bit index arithmetic was a third of the
 // instructions of an earlier version.
 #ifndef NTTT_UP_MINBLOCKS
