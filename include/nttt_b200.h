@@ -77,6 +77,13 @@ int nttt_ctx_profile_read(nttt_ctx* ctx, float* ms_host, int capacity);
 int nttt_threshold_pack(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits,
                         int32_t* area, int32_t* box, int32_t* stab, int32_t* flags, void* stream);
 
+/* same pass, plus the stability score AS A VALUE (`calculate_stability_score`, sam2/utils/amg.py:158-178):
+ *   stab_score [n] f32 = (float)stab[i,0] / (float)stab[i,1] — torch's int32 / int32 true division in float32
+ *   (counts <= h*w are exact in float32); an empty denominator gives 0/0 = NaN exactly as the reference does. */
+int nttt_threshold_pack_stability(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits,
+                                  int32_t* area, int32_t* box, int32_t* stab, float* stab_score, int32_t* flags,
+                                  void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * candidate selection in front of the stage
  * replaces: `best = argmax(ious[:, 1:]) + 1; low_res_multimasks[arange, best]; ious[arange, best]`
@@ -228,6 +235,18 @@ int nttt_rle_encode(const uint32_t* bits_full, const int32_t* rect, const int32_
 int nttt_fill_pool_accumulate(const float* feat /* [eh*ew, c] */, const float* soft_mask, int mh, int mw,
                               int eh, int ew, int c, float* sum_slot /* [c] */, float* wsum_slot /* [1] */,
                               float* mask_lowres_out, void* stream);
+/* Batched form for many reference shots in ONE launch (grid = shots x column strips): feat [b, eh*ew, c],
+ * soft_mask [b, mh, mw] -> sums [b, c], wsums [b], masks_lowres [b, eh*ew] (nullable); plain stores (staging rows,
+ * no accumulation).  A shot pools to the same bits alone or in a batch (fixed reduction order). */
+int nttt_fill_pool_batch(const float* feat, const float* soft_mask, int b, int mh, int mw, int eh, int ew, int c,
+                         float* sums, float* wsums, float* masks_lowres, void* stream);
+/* The slot loop of forward_fill_memory (:478-485) for n staged shots at once: dst = slot[i] (class * L + position,
+ * negative = skip; destinations must be unique within a call)
+ *   feats_sum[dst,:] += sums[i,:]; mask_sum[dst] += wsums[i]; masks[dst,:] += masks_lowres[i,:] (both nullable).
+ * In a multi-GPU fill every rank scatters its own shots into a zero delta buffer that is then summed across ranks
+ * by ONE all-reduce (replaces the three per-step all_gathers of model_utils.py:74-91). */
+int nttt_fill_scatter(const float* sums, const float* wsums, const float* masks_lowres, const int32_t* slot, int n, int c,
+                      int e, float* feats_sum, float* mask_sum, float* masks, void* stream);
 int nttt_fill_finalize(const float* sum /* [n_cls, L, c] */, const float* wsum /* [n_cls, L] */, int n_cls,
                        int shots, int c, float* feats_ins_avg, float* feats_avg, void* stream);
 

@@ -52,6 +52,7 @@ SIGNATURES = {
     "nttt_ctx_create": (c_int, [POINTER(c_void_p), c_int]),
     "nttt_ctx_destroy": (None, [c_void_p]),
     "nttt_threshold_pack": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P]),
+    "nttt_threshold_pack_stability": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P, _P]),
     "nttt_select_multimask": (c_int, [_P, c_int, c_int, c_int, POINTER(c_void_p), c_int, c_int, c_int, c_int, _P, _P, _P]),
     "nttt_threshold_pack_ptrs": (c_int, [_P, _P, c_float, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P]),
     "nttt_upsample_threshold_pack_ptrs": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, _P, _P,
@@ -73,6 +74,8 @@ SIGNATURES = {
     "nttt_unpack_masks": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "nttt_rle_encode": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "nttt_fill_pool_accumulate": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "nttt_fill_pool_batch": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "nttt_fill_scatter": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "nttt_fill_finalize": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "nttt_match_workspace_bytes": (c_size_t, [c_int] * 10),
     "nttt_match_workspace_bytes_neg": (c_size_t, [c_int] * 11),

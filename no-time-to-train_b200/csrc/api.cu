@@ -10,17 +10,17 @@ namespace nttt {
 
 // launchers implemented in the kernel translation units
 int launch_lowres_pack(const float*, int, int, int, float, float, uint32_t*, int32_t*, int32_t*, int32_t*, int32_t*,
-                       const float*, float, const float* const*, cudaStream_t);
+                       const float*, float, const float* const*, cudaStream_t, float* stab_score = nullptr);
 int launch_multimask_select(const float*, int, int, int, const ChunkTable&, int, size_t, const float**, float*,
                             cudaStream_t);
 int launch_project_masks(const AxisTable&, const AxisTable&, const uint32_t*, const int32_t*, int, int, int, int, int,
                          void*, int, bool, cudaStream_t);
-int launch_normalize_split(const float*, const int32_t*, int, int, int, float*, void*, cudaStream_t);
+int launch_normalize_split(const float*, const int32_t*, int, int, int, float*, void*, bool, cudaStream_t);
 int launch_gemm_tc(const void*, int, const void*, int, float*, int, int, int, int, int, size_t, int*, cudaStream_t);
 int gemm_tc_pick_splits(int, int, int, int);
 int launch_split_rows(const float*, int, int, int, int, int, void*, cudaStream_t);
 int launch_split_transpose(const float*, int, int, int, int, int, void*, cudaStream_t);
-int launch_normalize_rows(const float*, const int32_t*, int, int, float*, cudaStream_t);
+int launch_normalize_rows(const float*, const int32_t*, int, int, float*, bool, cudaStream_t);
 int launch_proto_prepare(const float*, int, int, int, float*, cudaStream_t);
 int launch_top1(const float*, int, size_t, float*, int, int, int, float*, int32_t*, cudaStream_t);
 int launch_neg_top1(const float*, int, size_t, const float*, int, size_t, int, int, int, float, float*, float*, int32_t*,
@@ -44,7 +44,9 @@ int launch_decay_rank(const float*, const int32_t*, const float*, const int32_t*
                       cudaStream_t);
 int launch_rle_encode(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, int, uint32_t*,
                       int32_t*, uint8_t*, int32_t*, cudaStream_t);
-int launch_fill_pool(const float*, const float*, int, int, int, int, int, float*, float*, float*, cudaStream_t);
+int launch_fill_pool(const float*, const float*, int, int, int, int, int, int, float*, float*, float*, int, cudaStream_t);
+int launch_fill_scatter(const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*, float*,
+                        cudaStream_t);
 int launch_fill_finalize(const float*, const float*, int, int, int, float*, float*, cudaStream_t);
 
 static thread_local char g_cuda_err[512] = "";
@@ -86,11 +88,12 @@ static int pool_contract(const float* proj, const float* feat, int n, int e, int
 
 // rows of `sums` -> /area -> L2-normalise -> obj_feats (+ split-bf16 copy when the vector path applies).
 // Returns through *split_done whether a_split now holds the similarity GEMM's A operand.
+// nan_empty: negative-reference scoring divides by the raw area (empty mask -> NaN row, as the reference does)
 static int normalize_rows(const float* sums, const int32_t* area, int n, int c, float* obj_feats, void* a_split,
-                          bool* split_done, cudaStream_t s) {
-  *split_done = a_split && launch_normalize_split(sums, area, n, c, pad64(c), obj_feats, a_split, s) == 1;
+                          bool* split_done, bool nan_empty, cudaStream_t s) {
+  *split_done = a_split && launch_normalize_split(sums, area, n, c, pad64(c), obj_feats, a_split, nan_empty, s) == 1;
   if (*split_done) return NTTT_OK;
-  return launch_normalize_rows(sums, area, n, c, obj_feats, s);
+  return launch_normalize_rows(sums, area, n, c, obj_feats, nan_empty, s);
 }
 
 // the scatter tables hold kMaxScatter weights per encoder cell: enough while out/in <= ~11
@@ -266,6 +269,15 @@ int nttt_threshold_pack(const float* logits, int n, int h, int w, float thr, flo
                             (cudaStream_t)stream);
 }
 
+int nttt_threshold_pack_stability(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits,
+                                  int32_t* area, int32_t* box, int32_t* stab, float* stab_score, int32_t* flags,
+                                  void* stream) {
+  if (n < 0 || h <= 0 || w <= 0) return NTTT_EINVAL;
+  if (n > 0 && (!logits || !bits || !area || !box || !stab || !stab_score || !flags)) return NTTT_EINVAL;
+  return launch_lowres_pack(logits, n, h, w, thr, off, bits, area, box, stab, flags, nullptr, 0.0f, nullptr,
+                            (cudaStream_t)stream, stab_score);
+}
+
 // host-side check + by-value table of the decoder's per-batch tensors
 static int make_chunk_table(const float* const* chunks_host, int n_chunks, int chunk_prompts, int n, ChunkTable* out) {
   if (!chunks_host || n_chunks <= 0 || chunk_prompts <= 0) return NTTT_EINVAL;
@@ -335,7 +347,7 @@ int nttt_pool_normalize(nttt_ctx* ctx, const float* proj, const float* feat, con
   int err = pool_contract(proj, feat, n, e, c, sums, a_split, b_split, s);
   if (err) return err;
   bool split_done;
-  return normalize_rows(sums, area, n, c, obj_feats, nullptr, &split_done, s);
+  return normalize_rows(sums, area, n, c, obj_feats, nullptr, &split_done, false, s);
 }
 
 int nttt_proto_prepare(const float* feats_ins_avg, int n_cls, int shots, int c, float* proto, void* stream) {
@@ -510,8 +522,25 @@ int nttt_fill_pool_accumulate(const float* feat, const float* soft_mask, int mh,
                               float* sum_slot, float* wsum_slot, float* mask_lowres_out, void* stream) {
   if (!feat || !soft_mask || !sum_slot || !wsum_slot || mh <= 0 || mw <= 0 || eh <= 0 || ew <= 0 || c <= 0)
     return NTTT_EINVAL;
-  return launch_fill_pool(feat, soft_mask, mh, mw, eh, ew, c, sum_slot, wsum_slot, mask_lowres_out,
+  return launch_fill_pool(feat, soft_mask, 1, mh, mw, eh, ew, c, sum_slot, wsum_slot, mask_lowres_out, 1,
                           (cudaStream_t)stream);
+}
+
+int nttt_fill_pool_batch(const float* feat, const float* soft_mask, int b, int mh, int mw, int eh, int ew, int c,
+                         float* sums, float* wsums, float* masks_lowres, void* stream) {
+  if (b < 0 || mh <= 0 || mw <= 0 || eh <= 0 || ew <= 0 || c <= 0) return NTTT_EINVAL;
+  if (b == 0) return NTTT_OK;
+  if (!feat || !soft_mask || !sums || !wsums) return NTTT_EINVAL;
+  return launch_fill_pool(feat, soft_mask, b, mh, mw, eh, ew, c, sums, wsums, masks_lowres, 0, (cudaStream_t)stream);
+}
+
+int nttt_fill_scatter(const float* sums, const float* wsums, const float* masks_lowres, const int32_t* slot, int n, int c,
+                      int e, float* feats_sum, float* mask_sum, float* masks, void* stream) {
+  if (n < 0 || c <= 0 || e <= 0) return NTTT_EINVAL;
+  if (n == 0) return NTTT_OK;
+  if (!sums || !wsums || !slot || !feats_sum || !mask_sum) return NTTT_EINVAL;
+  if ((masks == nullptr) != (masks_lowres == nullptr)) return NTTT_EINVAL;
+  return launch_fill_scatter(sums, wsums, masks_lowres, slot, n, c, e, feats_sum, mask_sum, masks, (cudaStream_t)stream);
 }
 
 int nttt_fill_finalize(const float* sum, const float* wsum, int n_cls, int shots, int c, float* feats_ins_avg,
@@ -671,7 +700,7 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
                                  true, s));
   NTTT_STEP(pool_contract(nullptr, a->tar_feat, n, e, a->c, L.sums, L.a_split, L.b_split, s));
   bool a_ready = false;
-  NTTT_STEP(normalize_rows(L.sums, L.area_lr, n, a->c, obj_feats, L.a_split, &a_ready, s));
+  NTTT_STEP(normalize_rows(L.sums, L.area_lr, n, a->c, obj_feats, L.a_split, &a_ready, a->proto_neg != nullptr, s));
   // a7/a8: similarity + top-1
   NTTT_STEP(sim_top1(obj_feats, a->proto, a->proto_neg, l_neg, a->sigma, n, a->c, a->n_cls, a->sim, L.sim_part,
                      L.sim_part_neg, L.top_score, L.top_label, L.a_split, L.b_split, a_ready, ctx->sm_count, s));

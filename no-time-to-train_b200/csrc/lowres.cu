@@ -64,8 +64,9 @@ template <bool kStab>
 __global__ void __launch_bounds__(kPackBlock, 3)
 lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mask */, int words_per_row,
                    float thr_hi, float thr_lo, uint32_t* __restrict__ bits, int32_t* __restrict__ area,
-                   int32_t* __restrict__ box, int32_t* __restrict__ stab, int32_t* __restrict__ flags,
-                   const float* __restrict__ gate, float gate_min, const float* const* __restrict__ mask_ptr) {
+                   int32_t* __restrict__ box, int32_t* __restrict__ stab, float* __restrict__ stab_score,
+                   int32_t* __restrict__ flags, const float* __restrict__ gate, float gate_min,
+                   const float* const* __restrict__ mask_ptr) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   if (gate && !(gate[blockIdx.x] > gate_min)) {
     // filtered-out candidate (pred_iou <= iou_thr): its logits are never read; publish an empty mask
@@ -75,6 +76,7 @@ lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mas
     if (threadIdx.x == 0) {
       area[blockIdx.x] = 0;
       if (kStab) { stab[2 * blockIdx.x] = 0; stab[2 * blockIdx.x + 1] = 0; }
+      if (kStab && stab_score) stab_score[blockIdx.x] = __fdiv_rn(0.0f, 0.0f);  // 0 / 0 counts -> NaN, as torch
       flags[blockIdx.x] = 1;
       reinterpret_cast<int4*>(box)[blockIdx.x] = make_int4(0, 0, 0, 0);
     }
@@ -180,6 +182,9 @@ lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mas
   if (threadIdx.x == 0) {
     area[n] = s_red[0];
     if (kStab) { stab[2 * n] = s_red[1]; stab[2 * n + 1] = s_red[2]; }
+    // calculate_stability_score (sam2/utils/amg.py:158-178): int32 / int32 is a true division in float32; both
+    // counts are <= 65 536 (exact), an empty mask divides 0 by 0 -> NaN
+    if (kStab && stab_score) stab_score[n] = __fdiv_rn((float)s_red[1], (float)s_red[2]);
     flags[n] = s_red[3] ? 0 : 1;
     const bool empty = s_red[6] < s_red[4] || s_red[7] < s_red[5];
     int4 b = empty ? make_int4(0, 0, 0, 0) : make_int4(s_red[4], s_red[5], s_red[6], s_red[7]);
@@ -380,7 +385,7 @@ static int pack_mode() {
 }
 int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits,
                        int32_t* area, int32_t* box, int32_t* stab, int32_t* flags, const float* gate, float gate_min,
-                       const float* const* mask_ptr, cudaStream_t s) {
+                       const float* const* mask_ptr, cudaStream_t s, float* stab_score) {
   const long p = (long)h * w;
   if (n <= 0) return NTTT_OK;
   if (w % 32 != 0 || p % 128 != 0 || p / 32 * 4 > 32 * 1024) return NTTT_EUNSUPPORTED;
@@ -390,7 +395,7 @@ int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, floa
   if (stab) {
     NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lowres_pack_kernel<true><<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area, box,
-                                                        stab, flags, gate, gate_min, mask_ptr);
+                                                        stab, stab_score, flags, gate, gate_min, mask_ptr);
   } else if (pack_mode() <= 1) {
     NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lowres_pack_fast_kernel<<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, bits, area, box, flags, gate, gate_min,
@@ -398,7 +403,7 @@ int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, floa
   } else {
     NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lowres_pack_kernel<false><<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area,
-                                                         box, stab, flags, gate, gate_min, mask_ptr);
+                                                         box, stab, nullptr, flags, gate, gate_min, mask_ptr);
   }
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;

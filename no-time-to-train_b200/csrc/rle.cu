@@ -97,12 +97,25 @@ __device__ __forceinline__ uint32_t rle_block_edges(const RleGeom& g, int st, in
   return d;
 }
 
-// value of the pixel that precedes (x, r0) in column-major order, for the first block of a column
-__device__ __forceinline__ uint32_t rle_first_carry(const RleGeom& g, int x) {
-  if (g.r0 > 0 || x == 0 || g.r1 < g.oh) return 0u;  // the pixel above is outside the rect: zero
-  const int xp = x - 1, wp = xp >> 5;                 // wrap: last pixel of the previous column
+// value of the last pixel (row oh-1) of column x-1 — the pixel that precedes (x, 0) in column-major order; zero
+// unless the rect reaches the bottom row and column x-1 lies inside the rect's words
+__device__ __forceinline__ uint32_t rle_prev_column_last(const RleGeom& g, int x) {
+  if (x == 0 || g.r1 < g.oh) return 0u;
+  const int xp = x - 1, wp = xp >> 5;
   if (wp < g.w0 || wp >= g.w1) return 0u;
   return (__ldg(g.src + (size_t)(g.oh - 1) * g.ow_words + wp) >> (xp & 31)) & 1u;
+}
+
+// value of the pixel that precedes (x, r0) in column-major order, for the first block of a column: the wrap from the
+// previous column when the rect starts at row 0, otherwise the (zero) pixel above the rect
+__device__ __forceinline__ uint32_t rle_first_carry(const RleGeom& g, int x) {
+  return g.r0 > 0 ? 0u : rle_prev_column_last(g, x);
+}
+
+// rect reaches the bottom row but not the top one: a run that ends on the last row of column x-1 closes at (x, 0),
+// a row the walk over [r0, rend) never visits.  Returns 1 if column x owes that extra boundary at position x*oh.
+__device__ __forceinline__ uint32_t rle_wrap_edge(const RleGeom& g, int x) {
+  return g.r0 > 0 ? rle_prev_column_last(g, x) : 0u;
 }
 
 __global__ void __launch_bounds__(kRleThreads)
@@ -138,7 +151,7 @@ rle_encode_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restr
   for (int st = warp; st < g.n_strips; st += kRleWarps) {
     const int x = ((g.w0 + st) << 5) + lane;
     uint32_t carry = rle_first_carry(g, x);
-    int cnt = 0;
+    int cnt = (int)rle_wrap_edge(g, x);
     for (int b = 0; b < n_blocks; ++b) {
       const uint32_t d = rle_block_edges(g, st, b, lane, carry);
       cnt += __popc(d);
@@ -171,6 +184,7 @@ rle_encode_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restr
     const int x = ((g.w0 + st) << 5) + lane;
     uint32_t carry = rle_first_carry(g, x);
     int idx = s_col[(st << 5) + lane];
+    if (x < cend && rle_wrap_edge(g, x)) cnts[idx++] = (uint32_t)x * (uint32_t)oh;
     for (int b = 0; b < n_blocks; ++b) {
       uint32_t d = rle_block_edges(g, st, b, lane, carry);
       if (x >= cend) d = 0;

@@ -10,16 +10,17 @@ namespace nttt {
 
 // ---------------------------------------------------------------------------------------------------
 // rows: x = sums / max(area,1)  (area==0 -> 1, matching_baseline_utils.py:887-888); x /= max(||x||, 1e-12)
-// one warp per row.
+// one warp per row.  nan_empty: the negative-reference variant has NO zero guard (matching_baseline_utils.py:925,
+// Sam2MatchingBaseline_noAMG.py:598-600): an empty mask divides 0 by 0 and its whole row is NaN, as in the reference.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 normalize_rows_kernel(const float* __restrict__ sums, const int32_t* __restrict__ area, int n, int c,
-                      float* __restrict__ out) {
+                      float* __restrict__ out, bool nan_empty) {
   const int row = blockIdx.x * 8 + warp_id();
   if (row >= n) return;
   const int lane = lane_id();
   float denom = 1.0f;
-  if (area) { const int a = area[row]; denom = a == 0 ? 1.0f : (float)a; }
+  if (area) { const int a = area[row]; denom = (a == 0 && !nan_empty) ? 1.0f : (float)a; }
   const float* src = sums + (size_t)row * c;
   float ss = 0.0f;
   for (int i = lane; i < c; i += 32) { const float v = __fdiv_rn(src[i], denom); ss = fmaf(v, v, ss); }
@@ -35,13 +36,13 @@ normalize_rows_kernel(const float* __restrict__ sums, const int32_t* __restrict_
 template <int kVec>  // float4 per lane, c = 128 * kVec
 __global__ void __launch_bounds__(256)
 normalize_split_kernel(const float* __restrict__ sums, const int32_t* __restrict__ area, int n, int cp,
-                       float* __restrict__ out, __nv_bfloat16* __restrict__ split) {
+                       float* __restrict__ out, __nv_bfloat16* __restrict__ split, bool nan_empty) {
   constexpr int c = 128 * kVec;
   const int row = blockIdx.x * 8 + warp_id();
   if (row >= n) return;
   const int lane = lane_id();
   float denom = 1.0f;
-  if (area) { const int a = area[row]; denom = a == 0 ? 1.0f : (float)a; }
+  if (area) { const int a = area[row]; denom = (a == 0 && !nan_empty) ? 1.0f : (float)a; }
   const float4* src = reinterpret_cast<const float4*>(sums + (size_t)row * c);
   float4 v[kVec];
 #pragma unroll
@@ -86,16 +87,16 @@ normalize_split_kernel(const float* __restrict__ sums, const int32_t* __restrict
 
 // returns 1 if the fused vector path ran (split written), 0 if the caller must use the generic kernels
 int launch_normalize_split(const float* sums, const int32_t* area, int n, int c, int cp, float* out, void* split,
-                           cudaStream_t s) {
+                           bool nan_empty, cudaStream_t s) {
   if (n <= 0) return 1;
   if (c % 128 != 0 || cp != c) return 0;
   const int grid = ceil_div(n, 8);
   __nv_bfloat16* sp = static_cast<__nv_bfloat16*>(split);
   switch (c / 128) {
-    case 3: normalize_split_kernel<3><<<grid, 256, 0, s>>>(sums, area, n, cp, out, sp); break;
-    case 6: normalize_split_kernel<6><<<grid, 256, 0, s>>>(sums, area, n, cp, out, sp); break;
-    case 8: normalize_split_kernel<8><<<grid, 256, 0, s>>>(sums, area, n, cp, out, sp); break;
-    case 12: normalize_split_kernel<12><<<grid, 256, 0, s>>>(sums, area, n, cp, out, sp); break;
+    case 3: normalize_split_kernel<3><<<grid, 256, 0, s>>>(sums, area, n, cp, out, sp, nan_empty); break;
+    case 6: normalize_split_kernel<6><<<grid, 256, 0, s>>>(sums, area, n, cp, out, sp, nan_empty); break;
+    case 8: normalize_split_kernel<8><<<grid, 256, 0, s>>>(sums, area, n, cp, out, sp, nan_empty); break;
+    case 12: normalize_split_kernel<12><<<grid, 256, 0, s>>>(sums, area, n, cp, out, sp, nan_empty); break;
     default: return 0;
   }
   ++g_launches;
@@ -103,9 +104,10 @@ int launch_normalize_split(const float* sums, const int32_t* area, int n, int c,
   return 1;
 }
 
-int launch_normalize_rows(const float* sums, const int32_t* area, int n, int c, float* out, cudaStream_t s) {
+int launch_normalize_rows(const float* sums, const int32_t* area, int n, int c, float* out, bool nan_empty,
+                          cudaStream_t s) {
   if (n <= 0) return NTTT_OK;
-  normalize_rows_kernel<<<ceil_div(n, 8), 256, 0, s>>>(sums, area, n, c, out);
+  normalize_rows_kernel<<<ceil_div(n, 8), 256, 0, s>>>(sums, area, n, c, out, nan_empty);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }
@@ -140,6 +142,16 @@ int launch_proto_prepare(const float* ins_avg, int n_cls, int shots, int c, floa
   return NTTT_OK;
 }
 
+// torch.topk / argmax ordering: NaN is larger than every number; among equals (and among NaNs) the lowest index wins
+__device__ __forceinline__ bool top1_beats(float v, int i, float best, int arg) {
+  const bool vn = v != v, bn = best != best;
+  if (vn != bn) return vn;
+  if (vn) return i < arg;
+  return v > best || (v == best && i < arg);
+}
+// torch.clamp(min=0) keeps NaN (fmaxf would drop it)
+__device__ __forceinline__ float clamp_min0(float x) { return x < 0.0f ? 0.0f : x; }
+
 // top-1 over classes (lowest index on ties == torch.topk/argmax on CPU); when n_cls == 1 the reference's
 // `k == n_cls` branch applies: score *= (score > 0.6*score)  (Sam2MatchingBaseline_noAMG.py:606-609).
 // `part` holds n_splits split-K partial similarity matrices (stride split_stride floats); they are summed here
@@ -157,13 +169,13 @@ top1_kernel(const float* __restrict__ part, int n_splits, size_t split_stride, f
     float v = src[i];
     for (int z = 1; z < n_splits; ++z) v += src[(size_t)z * split_stride + i];
     if (sim) sim[(size_t)row * ld + i] = v;
-    if (v > best || (v == best && i < arg)) { best = v; arg = i; }
+    if (top1_beats(v, i, best, arg)) { best = v; arg = i; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ob = __shfl_xor_sync(kFull, best, o);
     const int oa = __shfl_xor_sync(kFull, arg, o);
-    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    if (top1_beats(ob, oa, best, arg)) { best = ob; arg = oa; }
   }
   if (lane == 0) {
     if (n_cls == 1) best = best * (float)(best > __fmul_rn(best, 0.6f));
@@ -198,22 +210,22 @@ neg_top1_kernel(const float* __restrict__ part_pos, int splits_pos, size_t strid
   for (int i = lane; i < n_cls; i += 32) {
     float sp = pp[i];
     for (int z = 1; z < splits_pos; ++z) sp += pp[(size_t)z * stride_pos + i];
-    sp = fmaxf(sp, 0.0f);
-    float sn = 0.0f;  // clamp(min=0) before the max: the max of clamped values is >= 0
+    sp = clamp_min0(sp);
+    float sn = 0.0f;  // clamp(min=0) before the max: the max of clamped values is >= 0; NaN propagates (torch.max)
     for (int l = 0; l < l_neg; ++l) {
       float v = pn[i * l_neg + l];
       for (int z = 1; z < splits_neg; ++z) v += pn[(size_t)z * stride_neg + i * l_neg + l];
-      sn = fmaxf(sn, v);
+      if (sn == sn && (v != v || v > sn)) sn = v;
     }
-    const float v = __fmul_rn(sp, expf(__fdiv_rn(__fmul_rn(-1.0f, fmaxf(__fsub_rn(sn, sp), 0.0f)), sigma)));
+    const float v = __fmul_rn(sp, expf(__fdiv_rn(__fmul_rn(-1.0f, clamp_min0(__fsub_rn(sn, sp))), sigma)));
     if (sim) sim[(size_t)row * n_cls + i] = v;
-    if (v > best || (v == best && i < arg)) { best = v; arg = i; }
+    if (top1_beats(v, i, best, arg)) { best = v; arg = i; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ob = __shfl_xor_sync(kFull, best, o);
     const int oa = __shfl_xor_sync(kFull, arg, o);
-    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    if (top1_beats(ob, oa, best, arg)) { best = ob; arg = oa; }
   }
   if (lane == 0) {
     if (n_cls == 1) best = best * (float)(best > __fmul_rn(best, 0.6f));

@@ -68,6 +68,29 @@ def threshold_pack(logits: torch.Tensor, thr: float = 0.0, off: float = 1.0, out
     return bits, area, box, stab, flags
 
 
+def calculate_stability_score(logits: torch.Tensor, mask_threshold: float, threshold_offset: float) -> torch.Tensor:
+    """`calculate_stability_score(masks, mask_threshold, threshold_offset)` (`sam2/utils/amg.py:158-178`) — same name,
+    arguments and result: count(logit > thr+off) / count(logit > thr-off) per mask as float32 (0/0 -> NaN), computed
+    in the same single pass over the logits that packs the masks (`nttt_threshold_pack_stability`).
+    logits [..., h, w] f32 -> [...] f32."""
+    _need(logits, torch.float32, "logits")
+    lead, (h, w) = logits.shape[:-2], logits.shape[-2:]
+    flat = logits.reshape(-1, h, w)
+    n = flat.shape[0]
+    dev = logits.device
+    bits = torch.empty((n, h * w // 32), dtype=torch.int32, device=dev)
+    area = torch.empty((n,), dtype=torch.int32, device=dev)
+    box = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    stab = torch.empty((n, 2), dtype=torch.int32, device=dev)
+    flags = torch.empty((n,), dtype=torch.int32, device=dev)
+    score = torch.empty((n,), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.nttt_threshold_pack_stability(_ptr(flat), n, h, w, float(mask_threshold), float(threshold_offset),
+                                                 _ptr(bits), _ptr(area), _ptr(box), _ptr(stab), _ptr(score), _ptr(flags),
+                                                 _stream(dev)), "nttt_threshold_pack_stability")
+    return score.reshape(lead)
+
+
 def chunk_table(chunks):
     """HOST array of the device pointers of the decoder's per-batch tensors (each [prompts, m, h, w] f32)."""
     arr = (ctypes.c_void_p * len(chunks))()

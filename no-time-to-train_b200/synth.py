@@ -66,13 +66,17 @@ def make_features(e: int, c: int, n_cls: int, shots: int, gen: torch.Generator,
 
 
 def make_stage_inputs(n: int, c: int, n_cls: int, shots: int, ori_hw=(1024, 1024), seed: int = 1234,
-                      e_side: int = 37, clustered: bool = True, degenerate: bool = False) -> StageInputs:
+                      e_side: int = 37, clustered: bool = True, degenerate=False) -> StageInputs:
+    """degenerate: False/0 = plain blobs; True/1 = + the edge cases of `inject_degenerate_cases`;
+    2 = + masks cut by exactly one image border (`inject_border_cases`)."""
     gen = torch.Generator().manual_seed(seed)
     lr_masks = make_masks(n, gen)
     pred_ious = 0.4 + 0.6 * torch.rand(n, generator=gen)
     tar_feat, bank = make_features(e_side * e_side, c, n_cls, shots, gen, clustered=clustered)
     if degenerate:
         inject_degenerate_cases(lr_masks, bank)
+    if int(degenerate) >= 2:
+        inject_border_cases(lr_masks, pred_ious)
     return StageInputs(lr_masks, pred_ious, tar_feat, bank, tuple(ori_hw))
 
 
@@ -99,6 +103,29 @@ def inject_degenerate_cases(lr_masks: torch.Tensor, bank: torch.Tensor) -> None:
     # an unfilled prototype slot: reference averages over ALL L slots, zeros included
     if bank.shape[1] > 1:
         bank[0, -1] = 0.0
+
+
+def inject_border_cases(lr_masks: torch.Tensor, pred_ious: torch.Tensor) -> None:
+    """Masks cut by exactly ONE image border (needs N >= 16): their full-resolution rect reaches the last row / column
+    without reaching the first one, the case in which a column-major run wraps into a column whose top is background.
+    Their SAM scores are raised so that they survive NMS and reach the output."""
+    n = lr_masks.shape[0]
+    assert n >= 16
+    def block(i, ys, xs):
+        lr_masks[i] = -4.0
+        lr_masks[i, ys[0]:ys[1], xs[0]:xs[1]] = 3.0
+        pred_ious[i] = 0.99 - 0.001 * i
+    block(8, (200, 256), (60, 100))     # bottom border only, several columns
+    block(9, (180, 256), (130, 131))    # bottom border only, one low-res column
+    block(10, (230, 256), (220, 256))   # bottom-right corner
+    block(11, (0, 30), (100, 140))      # top border only
+    block(12, (90, 140), (236, 256))    # right border only
+    block(13, (150, 256), (0, 24))      # bottom-left corner
+    # a bottom-border mask with a ragged lower edge: columns alternate between reaching the last row and not
+    lr_masks[14] = -4.0
+    lr_masks[14, 210:250, 150:200] = 3.0
+    lr_masks[14, 250:256, 150:200:2] = 3.0
+    pred_ious[14] = 0.97
 
 
 def make_ref_shots(n_cls: int, shots: int, e: int, c: int, seed: int = 4321):

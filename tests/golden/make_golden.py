@@ -42,12 +42,19 @@ STAGE_CASES = {
     "stage_e_config1_1cls_1shot": (100, 384, 1, 1, (1024, 1024), 105, True, 100, False),
     "stage_f_truncate_333x500": (96, 64, 3, 2, (333, 500), 106, False, 4, True),
     "stage_g_iid_80cls": (128, 256, 80, 10, (512, 512), 107, True, 100, False),
+    # degenerate == 2: + masks cut by exactly one image border (bottom only, corners, ragged bottom edge)
+    "stage_h_borders_640x480": (48, 128, 5, 2, (640, 480), 108, 2, 48, True),
+    "stage_i_borders_1024": (32, 64, 3, 2, (1024, 1024), 109, 2, 32, True),
 }
 
-# negative-reference cases: name -> (n, c, n_cls, shots_neg, ori_hw, seed, num_out)
+# negative-reference cases: name -> (n, c, n_cls, shots_neg, ori_hw, seed, num_out[, degenerate])
+# degenerate: the reference's negative path has NO zero guard (matching_baseline_utils.py:925): the empty low-res
+# mask of `inject_degenerate_cases` gives a NaN feature row, NaN similarities and a top-k over an all-NaN row.
 NEG_CASES = {
     "stageneg_a_5cls_3neg": (64, 384, 5, 3, (480, 640), 301, 10),
     "stageneg_b_20cls_2neg": (96, 256, 20, 2, (512, 512), 302, 20),
+    "stageneg_c_degenerate_80cls": (64, 128, 80, 2, (480, 640), 303, 64, 1),
+    "stageneg_d_degenerate_borders": (48, 384, 40, 3, (427, 640), 304, 48, 2),
 }
 
 # candidate-selection cases (real `_forward_sam` over a stand-in predictor that returns synthetic RAW decoder output):
@@ -74,7 +81,7 @@ def sha(*tensors) -> str:
 def run_stage_case(ref, name, spec):
     n, c, n_cls, shots, ori_hw, seed, degenerate, num_out, clustered = spec
     inp = synth.make_stage_inputs(n, c, n_cls, shots, ori_hw, seed=seed, clustered=clustered,
-                                  degenerate=degenerate)
+                                  degenerate=int(degenerate))
     model_mod = sys.modules[ref.Model.__module__]
     cap = {}
 
@@ -152,8 +159,9 @@ def run_stage_case(ref, name, spec):
 
 def run_neg_case(ref, name, spec):
     """forward_test(with_negative=True): needs memory_bank.feats_avg and memory_bank_neg.feats_ins_avg."""
-    n, c, n_cls, l_neg, ori_hw, seed, num_out = spec
-    inp = synth.make_stage_inputs(n, c, n_cls, 2, ori_hw, seed=seed, clustered=True, degenerate=False)
+    n, c, n_cls, l_neg, ori_hw, seed, num_out = spec[:7]
+    degenerate = spec[7] if len(spec) > 7 else 0
+    inp = synth.make_stage_inputs(n, c, n_cls, 2, ori_hw, seed=seed, clustered=True, degenerate=degenerate)
     gen = torch.Generator().manual_seed(seed + 7)
     feats_avg = inp.feats_ins_avg.mean(dim=1) * 3.0  # un-normalised class averages
     neg = inp.feats_ins_avg[:, :1].repeat(1, l_neg, 1) * 0.5 + 0.6 * torch.randn(n_cls, l_neg, c, generator=gen) / (c ** 0.5)
@@ -165,7 +173,14 @@ def run_neg_case(ref, name, spec):
         out = orig(*a, **k)
         cap["sim"] = out.clone()
         return out
+    orig_nms = model_mod.batched_nms
+
+    def rec_nms(*a, **k):
+        out = orig_nms(*a, **k)
+        cap["nms_keep_full"], cap["labels_all"] = out.clone(), a[2].clone()
+        return out
     model_mod.compute_sim_global_avg_with_neg = rec
+    model_mod.batched_nms = rec_nms
     try:
         fake = types.SimpleNamespace()
         fake.predictor = types.SimpleNamespace(device=torch.device("cpu"))
@@ -186,9 +201,14 @@ def run_neg_case(ref, name, spec):
             out = ref.Model.forward_test(fake, [dict(target_img=torch.zeros(3, 8, 8), target_img_info=info)], True)[0]
     finally:
         model_mod.compute_sim_global_avg_with_neg = orig
+        model_mod.batched_nms = orig_nms
+    extra = {}
+    if degenerate:  # (kept out of the two older files so that they regenerate byte-identically)
+        extra = dict(nms_keep_full=cap["nms_keep_full"].numpy(), labels_all=cap["labels_all"].numpy())
     np.savez_compressed(
-        os.path.join(HERE, name + ".npz"),
-        spec=np.array([n, c, n_cls, l_neg, ori_hw[0], ori_hw[1], seed, num_out], dtype=np.int64),
+        os.path.join(HERE, name + ".npz"), **extra,
+        spec=np.array([n, c, n_cls, l_neg, ori_hw[0], ori_hw[1], seed, num_out] + ([degenerate] if degenerate else []),
+                      dtype=np.int64),
         feats_avg=feats_avg.numpy(), feats_ins_avg_neg=neg.numpy(),
         inputs_sha=np.array(sha(inp.lr_masks, inp.pred_ious, inp.tar_feat, inp.feats_ins_avg)),
         sim=cap["sim"].numpy(), out_scores=out["scores"].numpy(), out_labels=out["labels"].numpy(),
@@ -278,6 +298,17 @@ def rle_special_masks():
     out["noise_100x75"] = torch.rand(100, 75, generator=gen) > 0.7
     m = torch.zeros(300, 500, dtype=torch.bool); m[20:280, 31:470] = True; m[100:120, 200:260] = False
     out["blob_300x500"] = m
+    # masks that reach the LAST row without reaching the first one: the run of a column ends at the bottom border and
+    # the next column starts with background, so the closing boundary sits at (x+1, 0), above a tight rect
+    m = torch.zeros(64, 96, dtype=torch.bool); m[40:, 10:20] = True; out["bottom_only_block"] = m
+    m = torch.zeros(64, 96, dtype=torch.bool); m[50:, 33] = True; out["bottom_only_one_column"] = m
+    m = torch.zeros(64, 96, dtype=torch.bool); m[30:, 80:] = True; out["bottom_right_corner"] = m
+    m = torch.zeros(64, 96, dtype=torch.bool); m[30:, :12] = True; out["bottom_left_corner"] = m
+    m = torch.zeros(70, 130, dtype=torch.bool); m[35:, 20:110] = True; m[60:, 20:110:2] = False
+    out["bottom_ragged_multiword"] = m
+    m = torch.zeros(64, 96, dtype=torch.bool); m[40:, 31] = True; m[40:, 32] = True; m[20:, 63] = True
+    out["bottom_only_word_seams"] = m
+    m = torch.zeros(45, 64, dtype=torch.bool); m[10:, 63] = True; out["bottom_only_last_column"] = m
     return out
 
 
@@ -292,7 +323,8 @@ def run_rle_golden(ref):
         store["special__" + name + "__mask"] = np.packbits(m.numpy().reshape(-1))
         store["special__" + name + "__hw"] = np.array(m.shape, dtype=np.int64)
         store["special__" + name + "__counts"] = np.array(rle["counts"], dtype=np.int64)
-    for case in ("stage_a_1024_degenerate", "stage_b_480x640", "stage_f_truncate_333x500", "stage_d_200x180_downscale"):
+    for case in ("stage_a_1024_degenerate", "stage_b_480x640", "stage_f_truncate_333x500", "stage_d_200x180_downscale",
+                 "stage_h_borders_640x480", "stage_i_borders_1024"):
         g = np.load(os.path.join(HERE, case + ".npz"))
         oh, ow = int(g["spec"][4]), int(g["spec"][5])
         k = g["out_masks_packed"].shape[0]

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import MULTI_CASES, assert_same_ranking, load_multimask_case
+from golden_util import MULTI_CASES, assert_rows_match, assert_same_ranking, load_multimask_case
 from oracle import nttt_oracle as orc
 from oracle import ref_torch
 
@@ -85,10 +85,9 @@ def test_stage_on_raw_decoder_output_matches_reference(P, name, chunked):
                       multi_ious=ious.to(DEV), multi_first=1)
     assert_same_ranking(out["scores"].cpu().numpy(), out["labels"].cpu().numpy(), g["out_scores"], g["out_labels"],
                         what=name)
-    if np.array_equal(out["labels"].cpu().numpy(), g["out_labels"]):
-        masks = out["binary_masks"].cpu().numpy().astype(np.uint8)
-        assert np.array_equal(np.packbits(masks.reshape(masks.shape[0], -1), axis=-1), g["out_masks_packed"])
-        assert np.array_equal(out["bboxes"].cpu().numpy(), g["out_bboxes"])
+    assert_rows_match(dict(scores=out["scores"], labels=out["labels"], bboxes=out["bboxes"], masks=out["binary_masks"]),
+                      dict(scores=g["out_scores"], labels=g["out_labels"], bboxes=g["out_bboxes"],
+                           masks=g["out_masks_packed"]), what=name)
     # `index` refers to prompt numbers of the un-compacted grid
     _, _, kept = orc.select_candidates(multi.numpy(), ious.numpy(), cfg["iou_thr"])
     assert set(out["index"].cpu().tolist()) <= set(kept.tolist())
@@ -157,9 +156,9 @@ def test_model_consumes_decoder_batches_in_place(P, name):
     assert calls["i"] == multi.shape[0] // bs
     assert_same_ranking(out["scores"].cpu().numpy(), out["labels"].cpu().numpy(), g["out_scores"], g["out_labels"],
                         what="model")
-    if np.array_equal(out["labels"].cpu().numpy(), g["out_labels"]):
-        masks = out["binary_masks"].cpu().numpy().astype(np.uint8)
-        assert np.array_equal(np.packbits(masks.reshape(masks.shape[0], -1), axis=-1), g["out_masks_packed"])
+    assert_rows_match(dict(scores=out["scores"], labels=out["labels"], bboxes=out["bboxes"], masks=out["binary_masks"]),
+                      dict(scores=g["out_scores"], labels=g["out_labels"], bboxes=g["out_bboxes"],
+                           masks=g["out_masks_packed"]), what="model")
     # the reference-compatible seam (compacted triple) gives the same candidates
     calls["i"] = 0
     lr, sc, _ = m._forward_sam(torch.zeros(1, 3, 64, 64, device=DEV))

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import assert_same_ranking
+from golden_util import assert_rows_match, assert_same_ranking
 from oracle import ref_torch
 
 pytestmark = pytest.mark.gpu
@@ -39,10 +39,10 @@ def test_fused_iou_filter_equals_compaction():
                         ref["labels"].numpy(), what="filtered")
     # our indices refer to the un-compacted list
     orig_index = torch.nonzero(keep).flatten()[ref["aux"]["sel_index"][ref["aux"]["order"]]]
-    if np.array_equal(got["labels"].cpu().numpy(), ref["labels"].numpy()):
-        assert np.array_equal(got["index"].cpu().numpy(), orig_index.numpy())
-        assert torch.equal(got["binary_masks"].cpu(), ref["binary_masks"])
-        assert torch.equal(got["bboxes"].cpu(), ref["bboxes"])
+    assert_rows_match(dict(scores=got["scores"], labels=got["labels"], bboxes=got["bboxes"], masks=got["binary_masks"],
+                           index=got["index"]),
+                      dict(scores=ref["scores"], labels=ref["labels"], bboxes=ref["bboxes"], masks=ref["binary_masks"],
+                           index=orig_index), what="filtered")
     # and the same through the compacted call of our own stage
     own = stage.match(inp.lr_masks[keep].contiguous().to(DEV), inp.pred_ious[keep].contiguous().to(DEV),
                       inp.tar_feat.to(DEV), inp.ori_hw)

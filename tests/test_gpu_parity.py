@@ -10,8 +10,8 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import (FILL_CASES, GOLDEN_DIR, RTOL, STAGE_CASES, assert_close_rel, assert_same_ranking, load_case,
-                         sha_bool)
+from golden_util import (FILL_CASES, GOLDEN_DIR, RTOL, STAGE_CASES, assert_close_rel, assert_rows_match,
+                         assert_same_ranking, load_case, sha_bool)
 from oracle import nttt_oracle as orc
 from oracle import ref_torch
 
@@ -95,6 +95,22 @@ def test_threshold_pack_sign_bit_path_special_values(ops, hw):
     assert np.array_equal(_unpack_lr(fast[0], h, w), pos.astype(np.uint8))
     assert np.array_equal(fast[4].cpu().numpy() == 0, expect_unsafe)
     assert expect_unsafe.any() and (~expect_unsafe).any()
+
+
+@pytest.mark.parametrize("name", STAGE_CASES)
+def test_stability_score_value_matches_reference(ops, name):
+    """a15 as a VALUE: `calculate_stability_score` (sam2/utils/amg.py:158-178) run by the real reference on the same
+    logits (golden `stability`), bit-for-bit including the 0/0 -> NaN rows."""
+    g, inp, _ = load_case(name)
+    got = ops.calculate_stability_score(inp.lr_masks.to(DEV), 0.0, 1.0)
+    assert got.dtype == torch.float32 and got.shape == (inp.lr_masks.shape[0],)
+    assert np.array_equal(got.cpu().numpy(), g["stability"], equal_nan=True)
+    # other threshold / offset pairs and a leading batch shape, against the torch restatement
+    for thr, off in ((0.5, 0.25), (-1.0, 3.0), (0.0, 0.0)):
+        x = inp.lr_masks[:8].reshape(2, 4, 256, 256)
+        want = ref_torch.stability_score(x, thr, off)
+        got = ops.calculate_stability_score(x.contiguous().to(DEV), thr, off)
+        assert got.shape == (2, 4) and np.array_equal(got.cpu().numpy(), want.numpy(), equal_nan=True)
 
 
 def test_threshold_pack_empty_batch(ops):
@@ -259,18 +275,10 @@ def test_pipeline_matches_reference_golden(P, name):
     assert_same_ranking(scores, labels, g["out_scores"], g["out_labels"], what=name)
     assert out["bboxes"].dtype == torch.int64 and out["binary_masks"].dtype == torch.bool
     assert out["labels"].dtype == torch.int64 and out["scores"].dtype == torch.float32
-    masks = out["binary_masks"].cpu().numpy()
-    packed = np.packbits(masks.reshape(masks.shape[0], -1).astype(np.uint8), axis=-1)
-    # identical ranking (NaN-first, then score): compare masks and boxes row by row
-    same_order = np.array_equal(labels, g["out_labels"])
-    if same_order:
-        rows_equal = [np.array_equal(packed[i], g["out_masks_packed"][i]) for i in range(packed.shape[0])]
-        boxes_equal = np.array_equal(out["bboxes"].cpu().numpy(), g["out_bboxes"])
-        if not (all(rows_equal) and boxes_equal):
-            # only legal when two outputs tie in score (unstable argsort in the reference)
-            bad = [i for i, e in enumerate(rows_equal) if not e]
-            for i in bad:
-                assert np.sum(np.abs(g["out_scores"] - g["out_scores"][i]) <= RTOL * abs(g["out_scores"][i])) > 1
+    # masks and boxes are compared for EVERY output row; rows may be permuted only inside float score ties
+    assert_rows_match(dict(scores=scores, labels=labels, bboxes=out["bboxes"], masks=out["binary_masks"]),
+                      dict(scores=g["out_scores"], labels=g["out_labels"], bboxes=g["out_bboxes"],
+                           masks=g["out_masks_packed"]), what=name)
     assert out["counts"]["n_sel"] == (len(g["labels_sel"]) if "labels_sel" in g else 0)
 
 
@@ -283,9 +291,11 @@ def test_pipeline_matches_c_oracle(P, name):
     assert out["counts"]["n_keep"] == len(ref["keep"])
     assert out["counts"]["n_sel"] == len(ref["sel_index"])
     assert_same_ranking(out["scores"].cpu().numpy(), out["labels"].cpu().numpy(), ref["scores"], ref["labels"], what=name)
-    if np.array_equal(out["index"].cpu().numpy(), ref["sel_index"][ref["order"]] if "order" in ref else []):
-        assert np.array_equal(out["binary_masks"].cpu().numpy(), ref["binary_masks"].astype(bool))
-        assert np.array_equal(out["bboxes"].cpu().numpy(), ref["bboxes"])
+    ref_index = ref["sel_index"][ref["order"]] if "order" in ref else np.zeros(0, np.int64)
+    assert_rows_match(dict(scores=out["scores"], labels=out["labels"], bboxes=out["bboxes"], masks=out["binary_masks"],
+                           index=out["index"]),
+                      dict(scores=ref["scores"], labels=ref["labels"], bboxes=ref["bboxes"],
+                           masks=ref["binary_masks"].astype(bool), index=ref_index), what=name + " vs C oracle")
 
 
 def test_pipeline_empty_selection(P, synth):

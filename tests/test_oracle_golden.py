@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import (FILL_CASES, MULTI_CASES, STAGE_CASES, assert_close_rel, assert_same_ranking, load_case,
+from golden_util import (assert_rows_match, FILL_CASES, MULTI_CASES, STAGE_CASES, assert_close_rel, assert_same_ranking, load_case,
                          load_multimask_case, sha_bool, sha_f32, GOLDEN_DIR)
 from oracle import nttt_oracle as orc
 from oracle import ref_torch
@@ -24,16 +24,10 @@ def _check_against_golden(g, out, aux, what):
         assert np.array_equal(np.asarray(aux["full_boxes"]), g["full_boxes"]), what + " full-res boxes"
         assert_close_rel(aux["ios"], g["ios"], what=what + " ios")
     assert_same_ranking(out["scores"], out["labels"], g["out_scores"], g["out_labels"], what=what)
-    if np.array_equal(np.asarray(out["labels"]), g["out_labels"]) and \
-            np.array_equal(np.argsort(-np.nan_to_num(np.asarray(out["scores"], np.float64), nan=np.inf), kind="stable"),
-                           np.argsort(-np.nan_to_num(g["out_scores"].astype(np.float64), nan=np.inf), kind="stable")):
-        masks = np.asarray(out["binary_masks"]).astype(np.uint8)
-        packed = np.packbits(masks.reshape(masks.shape[0], -1), axis=-1)
-        if packed.shape == g["out_masks_packed"].shape:
-            same_rows = [np.array_equal(packed[i], g["out_masks_packed"][i]) for i in range(packed.shape[0])]
-            # rows can only differ where two outputs swapped inside a tie group
-            assert all(same_rows) or len(set(np.asarray(out["scores"]).tolist())) < len(same_rows), what + " masks"
-        assert np.array_equal(np.asarray(out["bboxes"]), g["out_bboxes"]) or not all(same_rows), what + " out boxes"
+    assert_rows_match(dict(scores=out["scores"], labels=out["labels"], bboxes=out["bboxes"],
+                           masks=np.asarray(out["binary_masks"]).astype(bool)),
+                      dict(scores=g["out_scores"], labels=g["out_labels"], bboxes=g["out_bboxes"],
+                           masks=g["out_masks_packed"]), what=what)
 
 
 @pytest.mark.parametrize("name", STAGE_CASES)

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import GOLDEN_DIR, load_case
+from golden_util import GOLDEN_DIR, assert_rows_match, load_case
 from oracle import nttt_oracle as orc
 
 DEV = "cuda:0"
@@ -68,6 +68,49 @@ def test_oracle_string_roundtrip_and_alphabet():
     assert orc.rle_to_string(np.array([5], np.uint32)) == b"5"
     # the 4th count is stored as a difference to the 2nd: 3 - 7 = -4 -> 0b11100 -> one char, 28 + 48
     assert orc.rle_to_string(np.array([1, 7, 2, 3], np.uint32)) == b"172" + bytes([28 + 48])
+
+
+def _kernel_walk(mask, rect):
+    """Host restatement of the WALK `rle_encode_kernel` (csrc/rle.cu) makes over a mask: only rows [r0, min(r1+1, oh))
+    and columns [32*w0, min(32*w1+1, ow)) are visited, nothing outside the rect is loaded, the carry into the first row
+    of a column is the wrap from the previous column only when the rect starts at row 0, and a rect that reaches the last
+    row without reaching the first owes the boundary at (x, 0) explicitly (`rle_wrap_edge`)."""
+    oh, ow = mask.shape
+    r0, r1, w0, w1 = rect
+    if r1 <= r0 or w1 <= w0:
+        return np.array([oh * ow], dtype=np.int64)
+    rend, cend = min(r1 + 1, oh), min((w1 << 5) + 1, ow)
+
+    def px(y, x):
+        inside = r0 <= y < r1 and w0 <= (x >> 5) < w1 and x < ow
+        return int(mask[y, x]) if inside else 0
+
+    def prev_column_last(x):
+        if x == 0 or r1 < oh or not w0 <= ((x - 1) >> 5) < w1:
+            return 0
+        return int(mask[oh - 1, x - 1])
+
+    edges = []
+    for x in range(w0 << 5, cend):
+        if r0 > 0 and prev_column_last(x):
+            edges.append(x * oh)
+        carry = prev_column_last(x) if r0 == 0 else 0
+        for y in range(r0, rend):
+            v = px(y, x)
+            if v != carry:
+                edges.append(x * oh + y)
+            carry = v
+    return np.diff(np.concatenate([[0], np.array(edges + [oh * ow], dtype=np.int64)]))
+
+
+@pytest.mark.parametrize("name", SPECIAL)
+def test_kernel_walk_over_tight_and_full_rects(name):
+    """The rect-confined walk the CUDA kernel makes gives the reference's counts for tight and full rects (pins the
+    bottom-border case: a tight rect with r1 == oh and r0 > 0)."""
+    mask, want = _special(name)
+    h, w = mask.shape
+    for rect in (_tight_rect(mask), [0, h, 0, (w + 31) // 32]):
+        assert np.array_equal(_kernel_walk(mask, rect), want), (name, rect)
 
 
 # ------------------------------------------------------------------------------------------------ GPU
@@ -155,7 +198,8 @@ def test_gpu_rle_large_random_and_overflow():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["stage_a_1024_degenerate", "stage_f_truncate_333x500", "stage_d_200x180_downscale"])
+@pytest.mark.parametrize("name", ["stage_a_1024_degenerate", "stage_f_truncate_333x500", "stage_d_200x180_downscale",
+                                  "stage_h_borders_640x480", "stage_i_borders_1024"])
 def test_stage_rle_output_matches_dense_masks(name):
     """Fused: the stage's RLE strings decode to exactly its own dense masks and equal the oracle's encoding of the
     reference's masks; with dense_masks=False the result is the same without producing the bool masks."""
@@ -175,12 +219,15 @@ def test_stage_rle_output_matches_dense_masks(name):
     lean = stage.match(*args, rle=True, dense_masks=False)
     assert lean["binary_masks"] is None and lean["segmentations"] == segs
     assert torch.equal(lean["bboxes"], out["bboxes"]) and torch.equal(lean["labels"], out["labels"])
-    # against the reference's masks (golden) when the ranking carries no tie permutation
-    if np.array_equal(out["labels"].cpu().numpy(), g["out_labels"]):
-        oh, ow = inp.ori_hw
-        ref_masks = np.unpackbits(g["out_masks_packed"], axis=-1)[:, :oh * ow].reshape(-1, oh, ow).astype(bool)
-        if np.array_equal(ref_masks, dense):
-            assert segs == [orc.encode_mask(m) for m in ref_masks]
+    # against the reference's masks (golden): every output's string equals the oracle's encoding of the reference mask
+    # it matches (rows may be permuted inside float score ties only)
+    oh, ow = inp.ori_hw
+    ref_masks = np.unpackbits(g["out_masks_packed"], axis=-1)[:, :oh * ow].reshape(-1, oh, ow).astype(bool)
+    assert_rows_match(dict(scores=out["scores"], labels=out["labels"], bboxes=out["bboxes"], masks=dense),
+                      dict(scores=g["out_scores"], labels=g["out_labels"], bboxes=g["out_bboxes"], masks=ref_masks),
+                      what=name)
+    ref_segs = [orc.encode_mask(m) for m in ref_masks]
+    assert sorted(s["counts"] for s in segs) == sorted(s["counts"] for s in ref_segs)
 
 
 @pytest.mark.gpu
