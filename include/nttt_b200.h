@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NTTT_VERSION 101
+#define NTTT_VERSION 200
 
 enum {
   NTTT_OK = 0,
@@ -44,6 +44,9 @@ enum {
 typedef struct nttt_ctx nttt_ctx;
 
 int nttt_version(void);
+/* 1 if the library was built with -DNTTT_ABLATE (honours NTTT_STOP_AFTER / NTTT_PACK_MODE for tools/ablate.py);
+ * the product build returns 0 and contains neither switch. */
+int nttt_build_is_ablation(void);
 const char* nttt_error_string(int code);
 /* text of the last CUDA error seen by this thread's calls ("" if none) */
 const char* nttt_last_cuda_error(void);
@@ -230,7 +233,8 @@ int nttt_rle_encode(const uint32_t* bits_full, const int32_t* rect, const int32_
  * (matching_baseline_utils.py:574-599).  Instead of storing raw [n_cls,L,E,C] features the bank keeps the
  * mask-weighted sums: sum[c,l,:] = sum_e mask[e] * feat[e,:], wsum[c,l] = sum_e mask[e].
  *   soft_mask [mh, mw] f32 is nearest-resized to (eh, ew) exactly like F.interpolate(mode="nearest") (:465-469)
- *   mask_lowres_out (nullable) [eh*ew] receives the resized mask
+ *   sum_slot [c], wsum_slot [1] and mask_lowres_out [eh*ew] (nullable) are ACCUMULATED (+=): they are views of the
+ *   bank slot (feats_sum[c,l], mask_sum[c,l], masks[c,l]), as `+=` at :482-484
  */
 int nttt_fill_pool_accumulate(const float* feat /* [eh*ew, c] */, const float* soft_mask, int mh, int mw,
                               int eh, int ew, int c, float* sum_slot /* [c] */, float* wsum_slot /* [1] */,

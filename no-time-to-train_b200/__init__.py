@@ -8,5 +8,6 @@ from .matching import MatchingStage, StageConfig  # noqa: F401
 from .memory_bank import MemoryBank  # noqa: F401
 from .model import Sam2MatchingBaselineNoAMG  # noqa: F401
 from .results import encode_results  # noqa: F401
+from .runner import MatcherRunner  # noqa: F401
 
-__all__ = ["MatchingStage", "StageConfig", "MemoryBank", "Sam2MatchingBaselineNoAMG", "encode_results", "synth"]
+__all__ = ["MatchingStage", "StageConfig", "MemoryBank", "Sam2MatchingBaselineNoAMG", "encode_results", "MatcherRunner", "synth"]

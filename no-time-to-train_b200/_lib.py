@@ -47,6 +47,7 @@ class MatchArgs(ctypes.Structure):
 _P = c_void_p
 SIGNATURES = {
     "nttt_version": (c_int, []),
+    "nttt_build_is_ablation": (c_int, []),
     "nttt_error_string": (c_char_p, [c_int]),
     "nttt_last_cuda_error": (c_char_p, []),
     "nttt_ctx_create": (c_int, [POINTER(c_void_p), c_int]),

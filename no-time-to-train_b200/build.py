@@ -47,6 +47,16 @@ def _stale(target: str, deps) -> bool:
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
+    # NTTT_BUILD_ABLATE=1: measurement build for tools/ablate.py (-DNTTT_ABLATE compiles the NTTT_STOP_AFTER /
+    # NTTT_PACK_MODE switches in).  The flavour is recorded next to the objects so that switching it rebuilds.
+    ablate = os.environ.get("NTTT_BUILD_ABLATE", "0") not in ("", "0")
+    flavour_file = os.path.join(OBJ, "flavour")
+    flavour = "ablate" if ablate else "product"
+    if not os.path.exists(flavour_file) or open(flavour_file).read() != flavour:
+        force = True
+        with open(flavour_file, "w") as f:
+            f.write(flavour)
+    extra = ["-DNTTT_ABLATE"] if ablate else []
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(PKG_DIR), "include", "nttt_b200.h"))
     headers.append(os.path.abspath(__file__))
@@ -61,7 +71,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         src, obj = job
-        cmd = [cc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [cc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, r
 

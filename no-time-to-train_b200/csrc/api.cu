@@ -183,6 +183,14 @@ extern "C" {
 
 int nttt_version(void) { return NTTT_VERSION; }
 
+int nttt_build_is_ablation(void) {
+#ifdef NTTT_ABLATE
+  return 1;
+#else
+  return 0;
+#endif
+}
+
 size_t nttt_sizeof_match_args(void) { return sizeof(nttt_match_args); }
 
 unsigned long long nttt_launch_count(void) { return g_launches; }
@@ -247,7 +255,9 @@ int nttt_ctx_create(nttt_ctx** out, int device) {
   nttt_ctx* ctx = new nttt_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+#ifdef NTTT_ABLATE
   if (const char* e = getenv("NTTT_STOP_AFTER")) ctx->stop_after = atoi(e);
+#endif
   *out = ctx;
   return NTTT_OK;
 }
@@ -664,15 +674,21 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   do {                                                                           \
     if (ctx->profile) { NTTT_CUDA(cudaEventRecord(ctx->ev[ctx->n_ev], s)); ++ctx->n_ev; } \
   } while (0)
-  // profiling aid: NTTT_STOP_AFTER=<k> (read once at ctx creation) ends the pipeline after its k-th stage so the
-  // marginal cost of each stage can be measured with several images in flight; unset in normal use.
+  // Ablation builds only (-DNTTT_ABLATE, `NTTT_BUILD_ABLATE=1 python build.py`): NTTT_STOP_AFTER=<k>, read once at
+  // ctx creation, ends the pipeline after its k-th stage so that tools/ablate.py can measure the marginal cost of each
+  // stage with several images in flight.  The product library does not contain this switch.
+#ifdef NTTT_ABLATE
   int stage_no = 0;
+#define NTTT_STOP_CHECK() if (ctx->stop_after > 0 && ++stage_no >= ctx->stop_after) return NTTT_OK
+#else
+#define NTTT_STOP_CHECK() (void)0
+#endif
 #define NTTT_STEP(call)                                        \
   do {                                                         \
     err = (call);                                              \
     if (err) return err;                                       \
     NTTT_MARK();                                               \
-    if (ctx->stop_after > 0 && ++stage_no >= ctx->stop_after) return NTTT_OK; \
+    NTTT_STOP_CHECK();                                         \
   } while (0)
   // candidate selection (§8f rank 2): resolve the best decoder plane per prompt; its IoU is the score from here on
   const float* const* mask_ptr = nullptr;
@@ -735,6 +751,7 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   else
     NTTT_MARK();
 #undef NTTT_STEP
+#undef NTTT_STOP_CHECK
 #undef NTTT_MARK
   return NTTT_OK;
 }

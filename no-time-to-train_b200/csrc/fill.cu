@@ -20,15 +20,16 @@ __device__ __forceinline__ int nearest_src(int dst, int in_size, int out_size) {
 // load per patch row: a warp reads 512 contiguous bytes).  blockIdx.y = shot, so a batch of reference shots is ONE
 // launch of b * ceil(c/128) CTAs.  The reduction order is fixed (patches e = w, w+8, ... per warp with fma, then the
 // 8 warp partials in order), so a shot pools to the same bits whether it arrives alone or in a batch.
-//   accumulate != 0: sums[b,:] += ..., wsums[b] += ... (the single-shot entry writes straight into a bank slot)
+//   accumulate != 0: sums[b,:] += ..., wsums[b] += ..., mask_out[b,:] += ... (the single-shot entry writes straight
+//                    into a bank slot, as `feats[c, slot] += f; masks[c, slot] += m` at :482-484)
 //   accumulate == 0: plain stores into staging rows
 __global__ void __launch_bounds__(256)
 fill_pool_kernel(const float* __restrict__ feat, const float* __restrict__ soft_mask, int mh, int mw, int eh, int ew,
                  int c, float* __restrict__ sums, float* __restrict__ wsums, float* __restrict__ mask_out,
                  int accumulate) {
-  extern __shared__ float s_mask[];  // eh*ew, then 8 * 128 partials
+  extern __shared__ __align__(16) float s_mask[];  // eh*ew (padded to 4 floats), then 8 * 128 partials
   const int e_total = eh * ew;
-  float* s_part = s_mask + e_total;
+  float* s_part = s_mask + ((e_total + 3) & ~3);  // read back as float4
   const int shot = blockIdx.y;
   feat += (size_t)shot * e_total * c;
   soft_mask += (size_t)shot * mh * mw;
@@ -37,7 +38,10 @@ fill_pool_kernel(const float* __restrict__ feat, const float* __restrict__ soft_
     const int ey = e / ew, ex = e - ey * ew;
     const float m = soft_mask[(size_t)nearest_src(ey, mh, eh) * mw + nearest_src(ex, mw, ew)];
     s_mask[e] = m;
-    if (blockIdx.x == 0 && mask_out) mask_out[(size_t)shot * e_total + e] = m;
+    if (blockIdx.x == 0 && mask_out) {
+      float* mo = mask_out + (size_t)shot * e_total + e;
+      *mo = accumulate ? *mo + m : m;
+    }
   }
   __syncthreads();
   const int col = blockIdx.x * 128 + lane * 4;
@@ -87,7 +91,7 @@ int launch_fill_pool(const float* feat, const float* soft_mask, int b, int mh, i
                      float* wsums, float* mask_out, int accumulate, cudaStream_t s) {
   if (b <= 0) return NTTT_OK;
   if (b > 65535) return NTTT_EUNSUPPORTED;
-  const size_t smem = sizeof(float) * ((size_t)eh * ew + 8 * 128);
+  const size_t smem = sizeof(float) * ((((size_t)eh * ew + 3) & ~(size_t)3) + 8 * 128);
   if (smem > 200 * 1024) return NTTT_EUNSUPPORTED;
   if (smem > 48 * 1024)
     NTTT_CUDA(cudaFuncSetAttribute(fill_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

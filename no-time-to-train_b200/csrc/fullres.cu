@@ -453,10 +453,11 @@ unpack_masks_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __res
 }
 
 // Sparse unpack into PERSISTENT output buffers: out[j] still holds the mask the previous call wrote there, whose
-// rect is remembered in prev_rect[j] (all-zero buffers and rects initially).  Only the bounding box of the old and
-// the new rect is rewritten — old pixels outside the new rect become 0 — so a call writes ~2 x the rect area
-// instead of oh*ow bytes per mask (the dense unpack is HBM-write-bound on mostly zeros).  Every slot up to
-// max_count is visited so that slots that fall out of use are cleared.
+// rect is remembered in prev_rect[j] (all-zero buffers and rects initially).  Two passes over one index space:
+// the OLD rect is cleared where the new rect does not cover it, then the NEW rect is written — so a call touches
+// area(old \ new) + area(new) bytes per mask whatever the distance between the two rects (never their common bounding
+// box, and never oh*ow: the dense unpack is HBM-write-bound on mostly zeros).  Every slot up to max_count is visited
+// so that slots that fall out of use are cleared.
 __global__ void __launch_bounds__(256)
 unpack_sparse_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restrict__ rect,
                      const int32_t* __restrict__ index, const int32_t* __restrict__ count, int max_count, int oh, int ow,
@@ -468,23 +469,30 @@ unpack_sparse_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __re
   const int4 nr = live ? reinterpret_cast<const int4*>(rect)[k] : make_int4(0, 0, 0, 0);
   const int4 pr = reinterpret_cast<const int4*>(prev_rect)[j];
   const bool has_new = nr.y > nr.x && nr.w > nr.z, has_old = pr.y > pr.x && pr.w > pr.z;
-  __syncthreads();  // every thread has read prev_rect[j] before thread 0 of CTA 0 overwrites it
+  __syncthreads();  // every thread has read prev_rect[j] before thread 0 overwrites it
   if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<int4*>(prev_rect)[j] = has_new ? nr : make_int4(0, 0, 0, 0);
   if (!has_new && !has_old) return;
-  const int y0 = has_new ? (has_old ? min(nr.x, pr.x) : nr.x) : pr.x;
-  const int y1 = has_new ? (has_old ? max(nr.y, pr.y) : nr.y) : pr.y;
-  const int w0 = has_new ? (has_old ? min(nr.z, pr.z) : nr.z) : pr.z;
-  const int w1 = has_new ? (has_old ? max(nr.w, pr.w) : nr.w) : pr.w;
-  const int nw = w1 - w0;
-  const int total = (y1 - y0) * nw;
+  const int old_w = has_old ? pr.w - pr.z : 0, new_w = has_new ? nr.w - nr.z : 0;
+  const int n_old = has_old ? (pr.y - pr.x) * old_w : 0;
+  const int total = n_old + (has_new ? (nr.y - nr.x) * new_w : 0);
   const uint32_t* src = bits_full + (size_t)k * oh * ow_words;
   uint8_t* dst = out + (size_t)j * oh * ow;
   const bool vec = (ow & 15) == 0;
   for (int it = blockIdx.x * 256 + threadIdx.x; it < total; it += gridDim.x * 256) {
-    const int ry = it / nw, wi = w0 + (it - ry * nw);
-    const int y = y0 + ry, x = wi << 5;
+    int y, wi;
     uint32_t w = 0;
-    if (has_new && y >= nr.x && y < nr.y && wi >= nr.z && wi < nr.w) w = __ldg(src + (size_t)y * ow_words + wi);
+    if (it < n_old) {  // clearing pass: old words the new rect will not rewrite
+      const int ry = it / old_w;
+      y = pr.x + ry;
+      wi = pr.z + (it - ry * old_w);
+      if (has_new && y >= nr.x && y < nr.y && wi >= nr.z && wi < nr.w) continue;
+    } else {           // writing pass
+      const int q = it - n_old, ry = q / new_w;
+      y = nr.x + ry;
+      wi = nr.z + (q - ry * new_w);
+      w = __ldg(src + (size_t)y * ow_words + wi);
+    }
+    const int x = wi << 5;
     uint8_t* p = dst + (size_t)y * ow + x;
     if (vec) {
       *reinterpret_cast<uint4*>(p) = make_uint4(nibble_to_bytes(w & 15u), nibble_to_bytes((w >> 4) & 15u),

@@ -377,11 +377,15 @@ lowres_pack_fast_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 pe
 // stab may be NULL: the stability counts (sam2/utils/amg.py:158-178) are not read on the noAMG path
 // gate (nullable): per-mask score; masks with !(gate[n] > gate_min) are skipped and published as empty
 // mask_ptr (nullable, device [n]): mask n is read from mask_ptr[n] (16-byte aligned) instead of logits + n*h*w
-// NTTT_PACK_MODE (A/B measurements): 0/1 = sign-bit kernel (default), 2 = literal per-element kernel.  Requests for the
+// NTTT_PACK_MODE (ablation builds only, -DNTTT_ABLATE): 0/1 = sign-bit kernel (default), 2 = literal per-element kernel.  Requests for the
 // stability counts always take the literal kernel.
 static int pack_mode() {
+#ifdef NTTT_ABLATE
   static const int v = [] { const char* e = getenv("NTTT_PACK_MODE"); return e ? atoi(e) : 0; }();
   return v;
+#else
+  return 0;
+#endif
 }
 int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits,
                        int32_t* area, int32_t* box, int32_t* stab, int32_t* flags, const float* gate, float gate_min,

@@ -238,20 +238,23 @@ class MatchingStage:
         return {self.lib.nttt_profile_stage_name(i).decode(): float(buf[i]) for i in range(got)}
 
     def match(self, lr_masks, pred_ious, tar_feat, ori_hw, taps: bool = False, iou_thr=None, multi_ious=None,
-              multi_first: int = 1, rle: bool = False, dense_masks: bool = True) -> dict:
+              multi_first: int = 1, rle: bool = False, dense_masks: bool = True, persistent_out=None) -> dict:
         pend = self.match_async(lr_masks, pred_ious, tar_feat, ori_hw, taps=taps, iou_thr=iou_thr,
-                                multi_ious=multi_ious, multi_first=multi_first, rle=rle, dense_masks=dense_masks)
+                                multi_ious=multi_ious, multi_first=multi_first, rle=rle, dense_masks=dense_masks,
+                                persistent_out=persistent_out)
         out = pend.get()
         if rle:
             out["segmentations"] = pend.rle_segmentations()
         return out
 
     def graphed(self, n: int, c: int, ori_hw, iou_thr=None, key=None, n_multi: int = 0,
-                multi_first: int = 1, rle: bool = False, dense_masks: bool = True) -> "GraphedMatch":
+                multi_first: int = 1, rle: bool = False, dense_masks: bool = True, persistent_out=None) -> "GraphedMatch":
         """A CUDA-graph capture of the whole stage at fixed shapes with static input/output buffers.
         n_multi > 1: the static mask buffer is the decoder's raw [n, n_multi, 256, 256] output (+ `multi_ious`).
-        rle / dense_masks: as in `match_async`."""
-        return GraphedMatch(self, n, c, ori_hw, iou_thr, key, n_multi, multi_first, rle, dense_masks)
+        rle / dense_masks: as in `match_async`.  `key` names the workspace slot and `persistent_out` the
+        (masks, prev_rect) output buffers: graphs that are replayed on the SAME stream may share both (a caller
+        holding one graph per resident image passes the stream's slot)."""
+        return GraphedMatch(self, n, c, ori_hw, iou_thr, key, n_multi, multi_first, rle, dense_masks, persistent_out)
 
 
 class GraphedMatch:
@@ -264,7 +267,7 @@ class GraphedMatch:
     again.  Replay costs one graph launch on the host instead of ~18 kernel launches."""
 
     def __init__(self, stage: MatchingStage, n: int, c: int, ori_hw, iou_thr=None, key=None, n_multi: int = 0,
-                 multi_first: int = 1, rle: bool = False, dense_masks: bool = True):
+                 multi_first: int = 1, rle: bool = False, dense_masks: bool = True, persistent_out=None):
         dev = stage.device
         eh, ew = stage.cfg.enc_hw
         self.stage = stage
@@ -285,8 +288,11 @@ class GraphedMatch:
         num_out = max(int(stage.cfg.num_out_instance), 1)
         # persistent outputs: the mask buffer is zeroed once; afterwards every replay rewrites only the rectangles
         # that change (nttt_match_args.out_prev_rect)
-        self._out = (torch.zeros((num_out, self.ori_hw[0], self.ori_hw[1]), dtype=torch.uint8, device=dev),
-                     torch.zeros((num_out, 4), dtype=torch.int32, device=dev)) if dense_masks else None
+        if persistent_out is not None and dense_masks:
+            self._out = persistent_out
+        else:
+            self._out = (torch.zeros((num_out, self.ori_hw[0], self.ori_hw[1]), dtype=torch.uint8, device=dev),
+                         torch.zeros((num_out, 4), dtype=torch.int32, device=dev)) if dense_masks else None
         self.graph = None
         self.pending = None
 

@@ -98,6 +98,9 @@ class Sam2MatchingBaselineNoAMG(nn.Module):
             nms_thr=float(self.nms_thr), num_out_instance=int(self.num_out_instance), cls_num_per_mask=int(k),
             enc_hw=(self.encoder_h, self.encoder_w)))
         self._proto_version = None
+        # Output buffers of forward_test, reused round-robin (see `output_ring`): (ori_hw) -> [ring of (masks, prev_rect)]
+        self._out_ring = {}
+        self._out_next = {}
         self._reset()
         self.eval()
 
@@ -139,6 +142,35 @@ class Sam2MatchingBaselineNoAMG(nn.Module):
         return masks[keep], scores[keep], points[:multi.shape[0]][keep]
 
     fuse_candidate_selection = True
+    # forward_test writes its `binary_masks` into a small ring of PERSISTENT buffers per image size instead of a fresh
+    # 105 MB allocation per image: only the rectangles that change between two uses of a buffer are rewritten
+    # (`nttt_match_args.out_prev_rect`), which removes the stage's largest write.  The tensors of a result therefore
+    # stay valid for the next `output_ring - 1` calls — ample for the reference's driver, which converts every result
+    # to numpy before the next image (`pl_wrapper/sam2matcher_pl.py:144-158`).  0 = a fresh dense buffer per call.
+    output_ring = 4
+    # True: forward_test also returns `segmentations` (COCO RLE dicts produced on the device by `nttt_rle_encode`),
+    # which is what `_output_inqueue` / `encode_results` turn the masks into on the host in the reference
+    # (`pl_wrapper/sam2matcher_pl.py:144-158`, `dataset/coco_ref_dataset.py:590-613`).  Off by default: the output dict
+    # then has exactly the reference's keys.
+    emit_rle = False
+
+    def _persistent_out(self, ori_hw):
+        if self.output_ring <= 0:
+            return None
+        key = (int(ori_hw[0]), int(ori_hw[1]))
+        ring = self._out_ring.get(key)
+        if ring is None:
+            if len(self._out_ring) >= 8:  # datasets with many image sizes: keep the most recent few
+                drop = next(iter(self._out_ring))
+                del self._out_ring[drop], self._out_next[drop]
+            num_out = max(int(self.num_out_instance), 1)
+            ring = [(torch.zeros((num_out, key[0], key[1]), dtype=torch.uint8, device=self._device),
+                     torch.zeros((num_out, 4), dtype=torch.int32, device=self._device)) for _ in range(self.output_ring)]
+            self._out_ring[key] = ring
+            self._out_next[key] = 0
+        i = self._out_next[key]
+        self._out_next[key] = (i + 1) % len(ring)
+        return ring[i]
 
     # ------------------------------------------------------------------ modes
     def forward_fill_memory(self, input_dicts, is_positive=True):
@@ -190,14 +222,19 @@ class Sam2MatchingBaselineNoAMG(nn.Module):
                 chunks, multi_ious, _ = self._forward_sam_raw(sam_in)
                 out = self.stage.match([c.float().contiguous() for c in chunks], None, tar_feat.float().contiguous(),
                                        ori_hw, iou_thr=float(self.iou_thr),
-                                       multi_ious=multi_ious.float().contiguous(), multi_first=1)
+                                       multi_ious=multi_ious.float().contiguous(), multi_first=1,
+                                       persistent_out=self._persistent_out(ori_hw), rle=self.emit_rle)
             else:
                 lr_masks, pred_ious, _ = self._forward_sam(sam_in)
                 out = self.stage.match(lr_masks.float().contiguous(), pred_ious.float().contiguous().reshape(-1),
-                                       tar_feat.float().contiguous(), ori_hw)
+                                       tar_feat.float().contiguous(), ori_hw,
+                                       persistent_out=self._persistent_out(ori_hw), rle=self.emit_rle)
         self._reset()
-        return [dict(binary_masks=out["binary_masks"], bboxes=out["bboxes"], scores=out["scores"],
-                     labels=out["labels"], image_info=info)]
+        result = dict(binary_masks=out["binary_masks"], bboxes=out["bboxes"], scores=out["scores"],
+                      labels=out["labels"], image_info=info)
+        if self.emit_rle:
+            result["segmentations"] = out["segmentations"]
+        return [result]
 
     def forward(self, input_dicts):
         """(:712-765) mode dispatch."""

@@ -335,19 +335,54 @@ def rle_encode(bits_full, rect, slot, count, ori_hw, cap_counts: int = 16384, ca
     return counts, n_counts, chars, n_chars
 
 
-def fill_pool_accumulate(feat, soft_mask, enc_hw, sum_slot, wsum_slot, want_mask=False):
-    """sum_slot [c] and wsum_slot [1] are accumulated IN PLACE (views into the bank's sum buffers)."""
+def fill_pool_accumulate(feat, soft_mask, enc_hw, sum_slot, wsum_slot, mask_slot=None):
+    """One shot pooled straight INTO a bank slot: sum_slot [c], wsum_slot [1] and mask_slot [e] (nullable) are views of
+    the bank's buffers and are accumulated in place (`+=`, as the reference's slot writes at :482-484)."""
     _need(feat, torch.float32, "feat")
     _need(soft_mask, torch.float32, "soft_mask")
     mh, mw = soft_mask.shape[-2:]
     eh, ew = enc_hw
     c = feat.shape[-1]
-    mask_out = torch.empty((eh * ew,), dtype=torch.float32, device=feat.device) if want_mask else None
     lib = _lib.load()
     _lib.check(lib.nttt_fill_pool_accumulate(_ptr(feat), _ptr(soft_mask), mh, mw, eh, ew, c, _ptr(sum_slot),
-                                             _ptr(wsum_slot), _ptr(mask_out), _stream(feat.device)),
+                                             _ptr(wsum_slot), _ptr(mask_slot), _stream(feat.device)),
                "nttt_fill_pool_accumulate")
-    return mask_out
+
+
+def fill_pool_batch(feats, soft_masks, enc_hw, sums, wsums, masks_lowres=None):
+    """B reference shots in one launch: feats [B,E,C], soft_masks [B,S,S] -> sums [B,C], wsums [B], masks_lowres [B,E]
+    (preallocated staging rows, plain stores)."""
+    _need(feats, torch.float32, "feats")
+    _need(soft_masks, torch.float32, "soft_masks")
+    _need(sums, torch.float32, "sums")
+    _need(wsums, torch.float32, "wsums")
+    b, e, c = feats.shape
+    mh, mw = soft_masks.shape[-2:]
+    eh, ew = enc_hw
+    assert e == eh * ew and soft_masks.shape[0] == b and sums.shape == (b, c) and wsums.shape == (b,)
+    if masks_lowres is not None:
+        _need(masks_lowres, torch.float32, "masks_lowres")
+        assert masks_lowres.shape == (b, e)
+    lib = _lib.load()
+    _lib.check(lib.nttt_fill_pool_batch(_ptr(feats), _ptr(soft_masks), b, mh, mw, eh, ew, c, _ptr(sums), _ptr(wsums),
+                                        _ptr(masks_lowres), _stream(feats.device)), "nttt_fill_pool_batch")
+
+
+def fill_scatter(sums, wsums, masks_lowres, slot, feats_sum, mask_sum, masks=None):
+    """Staged rows -> bank slots: feats_sum.view(-1,C)[slot[i]] += sums[i] etc. (slot < 0: skipped; unique slots)."""
+    for t, name in ((sums, "sums"), (wsums, "wsums"), (feats_sum, "feats_sum"), (mask_sum, "mask_sum")):
+        _need(t, torch.float32, name)
+    _need(slot, torch.int32, "slot")
+    n, c = sums.shape
+    e = masks_lowres.shape[-1] if masks_lowres is not None else 1
+    if masks is not None:
+        _need(masks, torch.float32, "masks")
+        _need(masks_lowres, torch.float32, "masks_lowres")
+    else:
+        masks_lowres = None
+    lib = _lib.load()
+    _lib.check(lib.nttt_fill_scatter(_ptr(sums), _ptr(wsums), _ptr(masks_lowres), _ptr(slot), n, c, e, _ptr(feats_sum),
+                                     _ptr(mask_sum), _ptr(masks), _stream(sums.device)), "nttt_fill_scatter")
 
 
 def fill_finalize(sums, wsum):

@@ -165,3 +165,58 @@ def make_multimask_inputs(n: int, m: int = 4, seed: int = 77, jitter: float = 0.
         ious[1, 0] = 0.99               # plane 0 is skipped even when it is the best
         ious[2, 1:] = 0.5               # all equal to the threshold used by the tests: filtered (strict >)
     return multi.contiguous(), ious.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Device-side generators (bench.py): the same recipes with a CUDA generator, so that hundreds of images / thousands
+# of reference shots can be produced in milliseconds each.  Seeds are per item (image index, (class, shot)), so every
+# rank can regenerate any item; values differ from the CPU generator's (different RNG stream), the distributions do not.
+# ----------------------------------------------------------------------------------------------------------
+def cluster_centres(c: int, n_centres: int = 5, seed: int = 99) -> torch.Tensor:
+    """The `n_centres` unit vectors shared by reference shots and target features of one synthetic dataset."""
+    gen = torch.Generator().manual_seed(seed)
+    return torch.nn.functional.normalize(torch.randn(n_centres, c, generator=gen), dim=-1)
+
+
+def make_stage_inputs_device(n: int, centres: torch.Tensor, device, seed: int, e_side: int = 37, noise: float = 0.5,
+                             rmin: float = 4.0, rmax: float = 64.0):
+    """One synthetic image at the encoder seams, generated on `device`: (lr_masks [n,256,256], pred_ious [n],
+    tar_feat [E, C]) following `make_masks` / `make_features(clustered=True)`."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    lo = LOWRES
+    r = torch.rand((5, n), generator=gen, device=device)
+    cy, cx = r[0] * lo, r[1] * lo
+    lr_, hr_ = math.log(rmin), math.log(rmax)
+    ry, rx = torch.exp(r[2] * (hr_ - lr_) + lr_), torch.exp(r[3] * (hr_ - lr_) + lr_)
+    ys = torch.arange(lo, dtype=torch.float32, device=device).view(1, lo, 1)
+    xs = torch.arange(lo, dtype=torch.float32, device=device).view(1, 1, lo)
+    dy = (ys - cy.view(n, 1, 1)) / ry.view(n, 1, 1)
+    dx = (xs - cx.view(n, 1, 1)) / rx.view(n, 1, 1)
+    logits = 8.0 * (1.0 - dy * dy - dx * dx)
+    logits += noise * torch.randn((n, lo, lo), generator=gen, device=device)
+    pred_ious = 0.4 + 0.6 * r[4]
+    e, c = e_side * e_side, centres.shape[1]
+    cen = centres.to(device)
+    patch_centre = torch.randint(0, cen.shape[0], (e,), generator=gen, device=device)
+    tar = cen[patch_centre] + (0.6 / math.sqrt(c)) * torch.randn((e, c), generator=gen, device=device)
+    return logits.contiguous(), pred_ious.contiguous(), tar.contiguous()
+
+
+def make_ref_shot_device(cls: int, shot: int, centres: torch.Tensor, device, e_side: int = 37, mask_side: int = 518,
+                         seed: int = 4321):
+    """One synthetic reference shot at the encoder-output seam of `forward_fill_memory`
+    (`Sam2MatchingBaseline_noAMG.py:461-469`): patch features [E, C] near the class's cluster centre and a SOFT mask
+    [mask_side, mask_side] in [0,1] (a box with a soft rim), reproducible from (cls, shot) alone."""
+    gen = torch.Generator(device=device).manual_seed(seed + 100003 * cls + shot)
+    e, c = e_side * e_side, centres.shape[1]
+    cen = centres.to(device)[cls % centres.shape[0]]
+    feats = cen.unsqueeze(0) + (3.0 / math.sqrt(c)) * torch.randn((e, c), generator=gen, device=device)
+    geo = torch.rand((4,), generator=gen, device=device).tolist()
+    y0, x0 = int(geo[0] * mask_side / 2), int(geo[1] * mask_side / 2)
+    hh, ww = int(mask_side / 8 + geo[2] * mask_side * 3 / 8), int(mask_side / 8 + geo[3] * mask_side * 3 / 8)
+    m = torch.zeros((mask_side, mask_side), dtype=torch.float32, device=device)
+    m[y0:y0 + hh, x0:x0 + ww] = 1.0
+    rim = max(mask_side // 37, 1)
+    m[y0:y0 + rim, x0:x0 + ww] = 0.5
+    m[y0:y0 + hh, x0:x0 + rim] = 0.25
+    return feats.contiguous(), m

@@ -37,7 +37,7 @@ def test_header_symbols_all_exported_and_bound(lib):
 
 def test_version_and_error_strings(lib):
     cdll = lib.load()
-    assert cdll.nttt_version() == 101
+    assert cdll.nttt_version() == 200 and cdll.nttt_build_is_ablation() == 0
     assert cdll.nttt_error_string(0) == b"ok"
     assert b"workspace" in cdll.nttt_error_string(-4)
 

@@ -104,8 +104,9 @@ def test_similarity_neg_top1_entry():
 
 @pytest.mark.gpu
 def test_top1_nan_semantics_follow_torch():
-    """torch.topk treats NaN as the maximum and torch.clamp / torch.max propagate it; among NaNs (and among equal
-    values) the lowest index wins, which is what torch gives for rows of realistic width."""
+    """torch.topk treats NaN as the maximum and torch.clamp / torch.max propagate it.  Which of several NaNs (or of
+    several equal values) torch returns is unspecified — its CPU kernel gave column 17 or 31 row by row here — so the
+    contract is: the label is a NaN column whenever the row has one (ours: the lowest such column)."""
     ops = importlib.import_module("no-time-to-train_b200.ops")
     gen = torch.Generator().manual_seed(4)
     n, c, n_cls, l_neg = 70, 128, 40, 2
@@ -126,7 +127,8 @@ def test_top1_nan_semantics_follow_torch():
         assert torch.isnan(top_score.cpu()).all() and torch.isnan(want_v).all()
         lab = top_label.cpu()
         assert int(lab[5]) == 0 and (lab[torch.arange(n) != 5] == 17).all()
-        assert torch.equal(lab.long(), want_i.flatten()), "differs from torch.topk on NaN rows"
+        rows = torch.arange(n) != 5
+        assert set(want_i.flatten()[rows].tolist()) <= {17, 31}, "torch.topk itself must pick a NaN column"
     # a NaN only on the negative side propagates through max / clamp / exp as in torch
     neg_nan = neg.clone()
     neg_nan[2 * l_neg + 1] = float("nan")  # class 2, second negative slot
@@ -135,7 +137,7 @@ def test_top1_nan_semantics_follow_torch():
     sn = (obj @ neg_nan.t()).clamp(min=0).reshape(n, n_cls, l_neg).max(-1).values
     want = sp * torch.exp(-1.0 * (sn - sp).clamp(min=0) / 0.8)
     assert_close_rel(sim.cpu().numpy(), want.numpy(), what="sim_neg with NaN negatives")
-    assert torch.equal(top_label.cpu().long(), torch.topk(sim.cpu(), k=1).indices.flatten())
+    assert torch.isnan(sim.cpu()[:, 2]).all() and (top_label.cpu() == 2).all() and torch.isnan(top_score.cpu()).all()
 
 
 @pytest.mark.gpu
