@@ -67,6 +67,8 @@ def parse():
     ap.add_argument("--n-images", type=int, default=N_IMAGES, help="size of the sharded synthetic dataset")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from the host instead of replaying "
                     "the captured CUDA graph of the stage")
+    ap.add_argument("--tune", action="append", default=[], metavar="NAME=VALUE",
+                    help="context tunable for A/B runs (MatchingStage.TUNABLES), e.g. upsample_stage_bytes=0")
     ap.add_argument("--value-only", action="store_true", help="A/B helper: fill + `value` only, short line "
                     "(no e2e legs, no roofline / cpu_baseline) - not the driver's contract line")
     return ap.parse_args()
@@ -352,6 +354,9 @@ def main():
     stage = pkg.MatchingStage(dev, pkg.StageConfig(nms_thr=WORKLOAD["nms_thr"], num_out_instance=n_out,
                                                    enc_hw=(WORKLOAD["feat_hw"], WORKLOAD["feat_hw"])))
     stage.set_prototypes(bank.feats_ins_avg)
+    for item in args.tune:
+        name, val = item.split("=")
+        stage.tune(name, int(val))
     streams = [torch.cuda.Stream(dev) for _ in range(S)]
 
     def barrier():
@@ -434,7 +439,7 @@ def main():
         if rank == 0:
             print(json.dumps(dict(metric=METRIC, value_only=True, value=value, us_per_image=us_per_image, n_gpus=world,
                                   steps=args.steps, images_per_step_per_gpu=B, streams=S, clocks=clock_info,
-                                  ms_per_rank=ms_per_rank, fill=fill_record, env=nttt_env)))
+                                  ms_per_rank=ms_per_rank, fill=fill_record, env=nttt_env, tune=args.tune)))
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -642,7 +647,7 @@ def main():
                     dtype="f32", data="synthetic", config=config,
                     run=dict(streams=S, launch="cuda_graph_replay" if use_graph else "host_enqueue",
                              images_resident_per_gpu=len(distinct), timed_region_ms=ms_total, ms_per_rank=ms_per_rank,
-                             env=nttt_env),
+                             env=nttt_env, tune=args.tune),
                     us_per_image=us_per_image,
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              steps=e2e_steps, images_per_step_per_gpu=E2E_B),

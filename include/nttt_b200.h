@@ -56,6 +56,13 @@ const char* nttt_last_cuda_error(void);
 int nttt_ctx_create(nttt_ctx** out, int device);
 void nttt_ctx_destroy(nttt_ctx* ctx);
 
+/* Tunables of a context (defaults are the measured best on B200; results never depend on them):
+ *   NTTT_TUNE_UPSAMPLE_STAGE_BYTES  shared-memory budget per CTA of the full-resolution resize for staging the logit
+ *                                   tile under its row groups (0 = every tap is read from global memory; tiles that
+ *                                   do not fit take that path anyway).  Default 36 KB. */
+enum { NTTT_TUNE_UPSAMPLE_STAGE_BYTES = 1 };
+int nttt_ctx_tune(nttt_ctx* ctx, int what, long long value);
+
 /* number of kernels this library has launched in this process (bench.py's `gpu_launches`) */
 unsigned long long nttt_launch_count(void);
 

@@ -52,6 +52,7 @@ SIGNATURES = {
     "nttt_last_cuda_error": (c_char_p, []),
     "nttt_ctx_create": (c_int, [POINTER(c_void_p), c_int]),
     "nttt_ctx_destroy": (None, [c_void_p]),
+    "nttt_ctx_tune": (c_int, [c_void_p, c_int, ctypes.c_longlong]),
     "nttt_threshold_pack": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P]),
     "nttt_threshold_pack_stability": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P, _P]),
     "nttt_select_multimask": (c_int, [_P, c_int, c_int, c_int, POINTER(c_void_p), c_int, c_int, c_int, c_int, _P, _P, _P]),

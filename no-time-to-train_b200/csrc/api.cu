@@ -30,7 +30,7 @@ int launch_box_nms(const int32_t*, const float*, const int32_t*, const float*, i
                    int32_t*, int32_t*, void*, size_t, float, int, cudaStream_t);
 int launch_upsample_pack(const AxisTable&, const AxisTable&, const float*, const uint32_t*, const int32_t*,
                          const int32_t*, int, int, const int32_t*, const int32_t*, int, int, int, uint32_t*, int32_t*,
-                         int32_t*, int32_t*, int32_t*, const float* const*, cudaStream_t);
+                         int32_t*, int32_t*, int32_t*, const float* const*, cudaStream_t, int);
 size_t upsample_scratch_bytes(int max_sel);
 int launch_unpack_sparse(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, uint8_t*,
                          int32_t*, cudaStream_t);
@@ -201,6 +201,18 @@ static constexpr int kNumStages = sizeof(kStageNames) / sizeof(kStageNames[0]);
 
 int nttt_profile_num_stages(void) { return kNumStages; }
 const char* nttt_profile_stage_name(int i) { return (i >= 0 && i < kNumStages) ? kStageNames[i] : ""; }
+
+int nttt_ctx_tune(nttt_ctx* ctx, int what, long long value) {
+  if (!ctx) return NTTT_EINVAL;
+  switch (what) {
+    case NTTT_TUNE_UPSAMPLE_STAGE_BYTES:
+      if (value < 0 || value > 160 * 1024) return NTTT_EINVAL;
+      ctx->upsample_stage_floats = (int)(value / 4);
+      return NTTT_OK;
+    default:
+      return NTTT_EINVAL;
+  }
+}
 
 int nttt_ctx_profile(nttt_ctx* ctx, int enable) {
   if (!ctx) return NTTT_EINVAL;
@@ -456,7 +468,7 @@ static int upsample_entry(nttt_ctx* ctx, const float* logits, const float* const
   err = ensure_scratch(ctx, max_sel, &scratch);
   if (err) return err;
   return launch_upsample_pack(tx, ty, logits, bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, oh, ow,
-                              bits_full, rect, area_full, box_full, scratch, mask_ptr, s);
+                              bits_full, rect, area_full, box_full, scratch, mask_ptr, s, ctx->upsample_stage_floats);
 }
 
 int nttt_upsample_threshold_pack(nttt_ctx* ctx, const float* logits, const uint32_t* bits_lr, const int32_t* box_lr,
@@ -726,7 +738,7 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   // a12/a9
   NTTT_STEP(launch_upsample_pack(ux, uy, a->logits, L.bits_lr, L.box_lr, L.flags, a->lr_h, a->lr_w, L.sel,
                                  a->counts + 1, max_sel, a->ori_h, a->ori_w, L.bits_full, L.rect, L.area_full,
-                                 L.box_full, L.scratch, mask_ptr, s));
+                                 L.box_full, L.scratch, mask_ptr, s, ctx->upsample_stage_floats));
   // a13
   NTTT_STEP(launch_mask_ios(L.bits_full, L.rect, L.area_full, L.box_full, L.sel, a->counts + 1, max_sel, a->ori_h,
                             a->ori_w, L.top_label, obj_feats, a->c, L.ios, nullptr, L.ios_ws, false, s));

@@ -136,6 +136,8 @@ struct nttt_ctx {
   unsigned long long last_use[kMaxTables] = {};
   unsigned long long epoch = 0;  // bumped once per API call that takes tables
   int n_tables = 0;
+  // shared-memory budget of upsample_pack's logit tile, in floats (nttt_ctx_tune; 0 = read taps from global memory)
+  int upsample_stage_floats = 36 * 1024 / 4;
   int32_t* scratch = nullptr;  // per-mask statistics scratch of the stand-alone resize entry
   int scratch_cap = 0;
   // optional per-stage CUDA-event profile of nttt_match_image (off by default)

@@ -105,14 +105,27 @@ __device__ __forceinline__ int up_ctas_needed(int n_groups) {
 // All indices inside the loops are 32-bit (one 64-bit base per array): 64-bit index arithmetic was a third of the
 // instructions of an earlier version.
 #ifndef NTTT_UP_MINBLOCKS
-#define NTTT_UP_MINBLOCKS 8
+#define NTTT_UP_MINBLOCKS 5
 #endif
+// Logit tile staging: the taps of every boundary word of a CTA lie in the low-res rows [clr0, clr1) x the columns under
+// the mask's output words.  Read one by one from global memory they are chains of dependent DRAM accesses (pk_x record
+// -> logits -> pk_y record) and the kernel sat at 18 % issue utilisation; instead the CTA copies that tile into shared
+// memory once with 16-byte cp.async (no register is held while the copies are in flight, rows are contiguous
+// segments: full sectors, each logit of the box read at most once per CTA) and the evaluation reads LDS.
+// `stage_floats` = capacity of the tile area in floats (0: staging off); tiles that do not fit (very wide / tall
+// chunks, more than 256 row groups) and the > 3-tap configurations take the direct path, which stays bit-identical.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __global__ void __launch_bounds__(kUpThreads, NTTT_UP_MINBLOCKS)
 upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restrict__ meta, int ih, int iw,
                      const int32_t* __restrict__ n_sel, int max_sel, int oh, int ow, UpTables t,
                      uint32_t* __restrict__ bits_full, int32_t* __restrict__ area_full, int32_t* __restrict__ box_full,
-                     int32_t* __restrict__ scratch) {
-  extern __shared__ uint32_t s_lr[];  // packed low-res bits of this mask, rows [clr0, clr1) only
+                     int32_t* __restrict__ scratch, int stage_floats) {
+  extern __shared__ __align__(16) uint32_t s_lr[];  // packed low-res bits of this mask, rows [clr0, clr1) only; then the tile
   __shared__ int s_red[5];
   const int k = blockIdx.y;
   if (k >= min(*n_sel, max_sel)) return;
@@ -138,12 +151,36 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
   }
   const uint32_t* lr = bits_lr + ((size_t)mt.src * ih + clr0) * lr_wpr;
   const int n_lr = (clr1 - clr0) * lr_wpr;
+  const bool fast_cfg = t.pk_x != nullptr && t.pk_y != nullptr;  // <= 3 taps on both axes
+  const float* src = mt.logits;
+  // tile = low-res rows [clr0, clr1) x columns [tc0, tc0 + tstride) (4-float aligned), behind the bits (16-byte aligned)
+  float* tile = reinterpret_cast<float*>(s_lr + (((ih * lr_wpr + 1) + 3) & ~3));
+  int tc0 = 0, tstride = 0;
+  bool staged = false;
+  if (fast_cfg && one_chunk && chunk0 < mt.g1 && stage_floats > 0 && w1 > w0) {
+    const int xa = min(w0 << 5, ow - 1), xb = min((w1 << 5) - 1, ow - 1);
+    tc0 = t.xmin[xa] & ~3;
+    tstride = min((t.xmin[xb] + t.xsize[xb] + 3) & ~3, iw) - tc0;
+    staged = tstride > 0 && (clr1 - clr0) * tstride <= stage_floats;
+  }
+  if (staged) {
+    const int cpr = tstride >> 2;  // 16-byte chunks per tile row
+    const int n_chunks = (clr1 - clr0) * cpr;
+    const float* g0p = src + (size_t)clr0 * iw + tc0;
+    for (int i = threadIdx.x; i < n_chunks; i += kUpThreads) {
+      const int row = i / cpr, c4 = (i - row * cpr) << 2;
+      cp_async16(tile + row * tstride + c4, g0p + (size_t)row * iw + c4);
+    }
+  }
   for (int i = threadIdx.x; i < n_lr; i += kUpThreads) s_lr[i] = lr[i];
   if (threadIdx.x < 5) s_red[threadIdx.x] = 0;
-  const bool fast_cfg = t.pk_x != nullptr && t.pk_y != nullptr;  // <= 3 taps on both axes
   const bool safe = mt.safe != 0;
-  const float* src = mt.logits;
+  // taps are read at  tap_base[row * tap_stride + col - tap_c0]  (generic loads: global logits or the shared tile)
+  const float* tap_base = staged ? tile - clr0 * tstride : src;
+  const int tap_stride = staged ? tstride : iw;
+  const int tap_c0 = staged ? tc0 : 0;
   uint32_t* dst = bits_full + (size_t)k * oh * ow_words;
+  cp_async_wait_all();
   __syncthreads();
 
   int area = 0, minx = kBig, maxx = -1, miny = kBig, maxy = -1;
@@ -187,7 +224,7 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
           ry0 = t.ymin[ya];
           rys = t.ysize[ya];
         }
-        const int rb = ry0 * iw;                     // index of the group's first input row
+        const int rb = ry0 * tap_stride - tap_c0;    // index of the group's first input row at column 0
         const int lrb = (ry0 - clr0) * lr_wpr + cw0;  // this lane's first footprint word in s_lr
         uint32_t words[kGrpMax];
 #pragma unroll
@@ -257,12 +294,12 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
             for (int r = 0; r < 3; ++r) {
               float acc = 0.0f;
               if (r < s_rys) {  // (warp-uniform)
-                // records past the image width have cs = 0, cx = 0 and zero weights: their first tap reads a valid
-                // address and the lane's result is masked by `cs > 0` in the ballot
-                const float* pl = src + (uint32_t)(s_rb + cx + r * iw);
-                acc = __fmul_rn(__ldg(pl), xt.y);
-                if (cs > 1) acc = __fmaf_rn(__ldg(pl + 1), xt.z, acc);
-                if (cs > 2) acc = __fmaf_rn(__ldg(pl + 2), xt.w, acc);
+                // records past the image width have cs = 0, cx = 0 and zero weights: their first tap is clamped to
+                // the first column of the row (a valid address) and the lane's result is masked by `cs > 0`
+                const float* pl = tap_base + (s_rb + max(cx, tap_c0) + r * tap_stride);
+                acc = __fmul_rn(*pl, xt.y);
+                if (cs > 1) acc = __fmaf_rn(pl[1], xt.z, acc);
+                if (cs > 2) acc = __fmaf_rn(pl[2], xt.w, acc);
               }
               T[r] = acc;
             }
@@ -281,7 +318,7 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
           const bool inb = x < ow;
           const int cx = inb ? t.xmin[x] : 0, cs = inb ? t.xsize[x] : 1;
           const float* wx = t.wx + (size_t)(inb ? x : 0) * t.tx;
-          const float* p = src + (s_rb + cx);
+          const float* p = src + (s_rb + cx);  // (never staged here: tap_stride == iw, tap_c0 == 0)
           if (s_rys <= kTapsReg) {
             // horizontal pass once per group, vertical pass per row
             float T[kTapsReg];
@@ -371,11 +408,15 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
                          const int32_t* box_lr, const int32_t* flags_lr, int ih, int iw, const int32_t* sel,
                          const int32_t* n_sel, int max_sel, int oh, int ow, uint32_t* bits_full, int32_t* rect,
                          int32_t* area_full, int32_t* box_full, int32_t* scratch, const float* const* mask_ptr,
-                         cudaStream_t s) {
+                         cudaStream_t s, int stage_floats) {
   if (max_sel <= 0) return NTTT_OK;
   if (iw % 32 != 0) return NTTT_EUNSUPPORTED;
-  const size_t smem = ((size_t)ih * (iw / 32) + 1) * 4;  // + one spare word read (and masked off) by the footprint test
-  if (smem > 160 * 1024) return NTTT_EUNSUPPORTED;
+  // bits (+ one spare word read and masked off by the footprint test), padded to 16 bytes, then the logit tile
+  const size_t bits_bytes = ((((size_t)ih * (iw / 32) + 1) + 3) & ~(size_t)3) * 4;
+  if (bits_bytes > 160 * 1024) return NTTT_EUNSUPPORTED;
+  size_t stage_bytes = (size_t)(stage_floats > 0 ? stage_floats : 0) * 4;
+  if (bits_bytes + stage_bytes > 200 * 1024) stage_bytes = 0;
+  const size_t smem = bits_bytes + stage_bytes;
   if (smem > 48 * 1024)
     NTTT_CUDA(cudaFuncSetAttribute(upsample_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   UpTables t{tx.xmin, tx.xsize, tx.w, tx.taps, ty.xmin, ty.xsize, ty.w, ty.taps, tx.t_lo, tx.t_len, ty.t_lo, ty.t_len,
@@ -386,7 +427,7 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
   NTTT_LAUNCH_CHECK();
   dim3 grid(kUpMaxSplit, max_sel);
   upsample_pack_kernel<<<grid, kUpThreads, smem, s>>>(bits_lr, meta, ih, iw, n_sel, max_sel, oh, ow, t, bits_full,
-                                                      area_full, box_full, scratch);
+                                                      area_full, box_full, scratch, (int)(stage_bytes / 4));
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }

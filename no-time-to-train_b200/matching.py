@@ -224,6 +224,12 @@ class MatchingStage:
         return PendingResult(self, masks.view(torch.bool) if masks is not None else None, boxes, scores, labels, index,
                              counts, tap_t, (oh, ow), keepalive=(lr_masks, pred_ious, multi_ious, tar_feat, ws), rle=rle_t)
 
+    TUNABLES = {"upsample_stage_bytes": 1}  # include/nttt_b200.h: NTTT_TUNE_*
+
+    def tune(self, name: str, value: int) -> None:
+        """Set a performance tunable of this device's context (`nttt_ctx_tune`); results never depend on them."""
+        _lib.check(self.lib.nttt_ctx_tune(self.ctx, self.TUNABLES[name], int(value)), f"nttt_ctx_tune({name})")
+
     def profile(self, enable: bool) -> None:
         """Per-stage CUDA-event timing of the next `match_async` calls (see nttt_ctx_profile)."""
         _lib.check(self.lib.nttt_ctx_profile(self.ctx, int(enable)), "nttt_ctx_profile")

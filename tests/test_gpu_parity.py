@@ -315,9 +315,11 @@ def test_pipeline_not_ready(P):
 
 
 @pytest.mark.parametrize("n,c,n_cls,shots,ori_hw", [
-    (1024, 1024, 80, 10, (1024, 1024)),     # BASELINE config 2
-    (256, 1024, 1203, 10, (512, 512)),      # config 4 (LVIS-shape similarity)
-    (4096, 384, 80, 10, (1024, 1024)),      # config 5 (64x64 grid NMS / IoU stress)
+    (1024, 1024, 80, 10, (1024, 1024)),     # BASELINE config 2 / 3, full shape
+    (1024, 1024, 1203, 10, (1024, 1024)),   # config 4, full shape (LVIS-size bank: 1203 classes, ViT-L width)
+    (4096, 1024, 80, 10, (1024, 1024)),     # config 5, full shape (64x64 prompt grid: NMS / IoU stress)
+    (256, 1024, 1203, 10, (512, 512)),      # reduced variants kept for the odd shapes they exercise
+    (4096, 384, 80, 10, (1024, 1024)),
 ])
 def test_full_size_against_torch_port_on_gpu(P, synth, n, c, n_cls, shots, ori_hw):
     """BASELINE.json's full sizes: the CUDA path against the torch restatement run on the same GPU (the
