@@ -30,8 +30,8 @@ int launch_box_nms(const int32_t*, const float*, const int32_t*, const float*, i
                    int32_t*, int32_t*, void*, size_t, float, int, cudaStream_t);
 int launch_upsample_pack(const AxisTable&, const AxisTable&, const float*, const uint32_t*, const int32_t*,
                          const int32_t*, int, int, const int32_t*, const int32_t*, int, int, int, uint32_t*, int32_t*,
-                         int32_t*, int32_t*, int32_t*, const float* const*, cudaStream_t, int);
-size_t upsample_scratch_bytes(int max_sel);
+                         int32_t*, int32_t*, int32_t*, const float* const*, cudaStream_t, int, int);
+size_t upsample_scratch_bytes(int max_sel, int oh, int ow);
 int launch_unpack_sparse(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, uint8_t*,
                          int32_t*, cudaStream_t);
 int launch_unpack(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, uint8_t*,
@@ -436,13 +436,17 @@ int nttt_box_nms(const int32_t* box, const float* nms_scores, const int32_t* lab
 }
 
 // scratch for the cross-CTA per-mask statistics of the stand-alone resize entry is owned by the ctx
-static int ensure_scratch(nttt_ctx* ctx, int max_sel, int32_t** out) {
-  if (max_sel > ctx->scratch_cap) {
-    if (ctx->scratch) cudaFree(ctx->scratch);
+static int ensure_scratch(nttt_ctx* ctx, int max_sel, int oh, int ow, int32_t** out) {
+  const size_t need = upsample_scratch_bytes(max_sel, oh, ow);
+  if (need > ctx->scratch_cap) {
+    if (ctx->scratch) {
+      NTTT_CUDA(cudaDeviceSynchronize());  // kernels of earlier calls may still use it (rare: the need only grows)
+      cudaFree(ctx->scratch);
+    }
     ctx->scratch = nullptr;
     ctx->scratch_cap = 0;
-    NTTT_CUDA(cudaMalloc(&ctx->scratch, upsample_scratch_bytes(max_sel)));
-    ctx->scratch_cap = max_sel;
+    NTTT_CUDA(cudaMalloc(&ctx->scratch, need));
+    ctx->scratch_cap = need;
   }
   *out = ctx->scratch;
   return NTTT_OK;
@@ -465,10 +469,11 @@ static int upsample_entry(nttt_ctx* ctx, const float* logits, const float* const
   err = ctx->axis(ih, oh, s, &ty);
   if (err) return err;
   int32_t* scratch = nullptr;
-  err = ensure_scratch(ctx, max_sel, &scratch);
+  err = ensure_scratch(ctx, max_sel, oh, ow, &scratch);
   if (err) return err;
   return launch_upsample_pack(tx, ty, logits, bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, oh, ow,
-                              bits_full, rect, area_full, box_full, scratch, mask_ptr, s, ctx->upsample_stage_floats);
+                              bits_full, rect, area_full, box_full, scratch, mask_ptr, s, ctx->upsample_stage_floats,
+                              ctx->sm_count);
 }
 
 int nttt_upsample_threshold_pack(nttt_ctx* ctx, const float* logits, const uint32_t* bits_lr, const int32_t* box_lr,
@@ -618,7 +623,7 @@ static MatchLayout carve(void* ws, int n, int lr_h, int lr_w, int eh, int ew, in
   L.rect = cv.take<int32_t>((size_t)max_sel * 4);
   L.area_full = cv.take<int32_t>(max_sel > 0 ? max_sel : 1);
   L.box_full = cv.take<int32_t>((size_t)max_sel * 4);
-  L.scratch = cv.take<int32_t>(upsample_scratch_bytes(max_sel > 0 ? max_sel : 1) / sizeof(int32_t));
+  L.scratch = cv.take<int32_t>(upsample_scratch_bytes(max_sel > 0 ? max_sel : 1, oh, ow) / sizeof(int32_t) + 1);
   L.ios = cv.take<float>(max_sel > 0 ? max_sel : 1);
   L.ios_ws = cv.take<char>(ios_workspace_bytes(max_sel > 0 ? max_sel : 1));
   L.out_slot = cv.take<int32_t>(num_out > 0 ? num_out : 1);
@@ -738,7 +743,7 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   // a12/a9
   NTTT_STEP(launch_upsample_pack(ux, uy, a->logits, L.bits_lr, L.box_lr, L.flags, a->lr_h, a->lr_w, L.sel,
                                  a->counts + 1, max_sel, a->ori_h, a->ori_w, L.bits_full, L.rect, L.area_full,
-                                 L.box_full, L.scratch, mask_ptr, s, ctx->upsample_stage_floats));
+                                 L.box_full, L.scratch, mask_ptr, s, ctx->upsample_stage_floats, ctx->sm_count));
   // a13
   NTTT_STEP(launch_mask_ios(L.bits_full, L.rect, L.area_full, L.box_full, L.sel, a->counts + 1, max_sel, a->ori_h,
                             a->ori_w, L.top_label, obj_feats, a->c, L.ios, nullptr, L.ios_ws, false, s));

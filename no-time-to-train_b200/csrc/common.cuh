@@ -139,7 +139,7 @@ struct nttt_ctx {
   // shared-memory budget of upsample_pack's logit tile, in floats (nttt_ctx_tune; 0 = read taps from global memory)
   int upsample_stage_floats = 36 * 1024 / 4;
   int32_t* scratch = nullptr;  // per-mask statistics scratch of the stand-alone resize entry
-  int scratch_cap = 0;
+  size_t scratch_cap = 0;  // bytes
   // optional per-stage CUDA-event profile of nttt_match_image (off by default)
   static constexpr int kMaxStages = 16;
   bool profile = false;

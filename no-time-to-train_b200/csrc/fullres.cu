@@ -404,13 +404,414 @@ upsample_pack_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// v2 — the path every <= 3-tap configuration takes (all up-scaling, mild down-scaling)
+//
+// What v1 measured as (ncu, config 2): 18-33 % issue utilisation, top stall long-scoreboard on the chain
+// pk_x record -> logits -> pk_y record, 4 800 of 6 400 CTAs exiting after two dependent global loads, ~165 warp
+// instructions per boundary word.  v2 changes the organisation, not the arithmetic:
+//   * a PLAN kernel turns the selected masks into a compact list of work items (mask, 32 row groups, 8 word columns)
+//     with their geometry resolved; persistent CTAs pull items from it with one atomic — no empty CTAs;
+//   * everything an item reads is copied into shared memory up front with cp.async (no register held while in flight):
+//     the logit tile under its rows/columns, the packed low-res rows, the pk_x / pk_y records, the group boundaries.
+//     The evaluation loop then has no global load at all;
+//   * a warp owns a word COLUMN of the item: lane = row group for the footprint classification (32 groups at once),
+//     lane = pixel for the evaluation, so the pixel's x record is loaded once per column instead of once per word and
+//     group data are warp-uniform shared-memory reads instead of shuffles;
+//   * results go to a shared-memory tile; the epilogue writes them out in 32-byte row segments and derives area and box
+//     from the words (no per-row statistics inside the loops).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kUp2Threads = 128;
+constexpr int kUp2Groups = 32;                       // row groups per item = lanes of the classification
+constexpr int kUp2Cols = 8;                          // word columns per item
+constexpr int kUp2Rows = kUp2Groups * kGrpMax;       // output rows per item (<= 128)
+constexpr int kUp2OutStride = kUp2Rows + kUp2Rows / 32;  // column-major result tile, one pad word per 32 rows
+constexpr int kUp2CtasPerSm = 7;
+
+struct alignas(16) Up2Item {  // 32 bytes, written by the plan kernel
+  int k;                 // selected-mask slot
+  int g;                 // first group | n_groups << 16
+  int w;                 // first word  | n_words  << 16
+  int y;                 // first output row | n_rows << 16
+  int lr;                // first low-res row | n_lr_rows << 16
+  int tc;                // first tile column (multiple of 4) | tile stride << 16
+  int staged;            // 1: the logit tile fits the shared-memory budget
+  int pad;
+};
+
+// One CTA: per-mask geometry (as upsample_meta_kernel), then an exclusive scan of the items per mask and the item
+// records.  ctr[0] = number of items, ctr[1] = next item to hand out (zeroed here for the main kernel).
+__global__ void __launch_bounds__(1024)
+upsample_plan_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __restrict__ box_lr,
+                     const int32_t* __restrict__ flags_lr, int ih, int iw, const int32_t* __restrict__ sel,
+                     const int32_t* __restrict__ n_sel, int max_sel, UpTables t, UpMeta* __restrict__ meta,
+                     int32_t* __restrict__ rect, int32_t* __restrict__ scratch, const float* __restrict__ logits,
+                     const float* const* __restrict__ mask_ptr, Up2Item* __restrict__ items, int32_t* __restrict__ ctr,
+                     int32_t* __restrict__ area_full, int32_t* __restrict__ box_full, int ow, int tile_cap_floats) {
+  __shared__ int s_warp[33];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = min(*n_sel, max_sel);
+  int base = 0;
+  for (int k0 = 0; k0 < max_sel; k0 += 1024) {
+    const int k = k0 + tid;
+    int n_items = 0, rcs = 0, ccs = 0;
+    UpMeta m;
+    m.r0 = m.r1 = m.w0 = m.w1 = m.lr0 = m.lr1 = m.g0 = m.g1 = 0;
+    if (k < max_sel) {
+#pragma unroll
+      for (int q = 0; q < kScratchInts; ++q) scratch[(size_t)k * kScratchInts + q] = 0;
+    }
+    if (k < n) {
+      m.src = sel[k];
+      m.logits = mask_ptr ? mask_ptr[m.src] : logits + (size_t)m.src * ih * iw;
+      const int4 b = reinterpret_cast<const int4*>(box_lr)[m.src];
+      const bool lr_empty = (b.x | b.y | b.z | b.w) == 0 && (bits_lr[(size_t)m.src * ih * (iw >> 5)] & 1u) == 0;
+      if (!lr_empty) {
+        m.r0 = t.y_tlo[b.y];
+        m.r1 = t.y_tlo[b.w] + t.y_tlen[b.w];
+        const int c0 = t.x_tlo[b.x];
+        const int c1 = t.x_tlo[b.z] + t.x_tlen[b.z];
+        m.w0 = c0 >> 5;
+        m.w1 = (c1 + 31) >> 5;
+        if (m.r1 > m.r0) {
+          m.lr0 = t.ymin[m.r0];
+          m.lr1 = t.ymin[m.r1 - 1] + t.ysize[m.r1 - 1];
+          m.g0 = t.y_grp_of[m.r0];
+          m.g1 = t.y_grp_of[m.r1 - 1] + 1;
+        }
+      }
+      m.safe = flags_lr[m.src] & 1;
+      meta[k] = m;
+      reinterpret_cast<int4*>(rect)[k] = make_int4(m.r0, m.r1, m.w0, m.w1);
+      if (m.r1 > m.r0 && m.w1 > m.w0) {
+        rcs = (m.g1 - m.g0 + kUp2Groups - 1) / kUp2Groups;
+        ccs = (m.w1 - m.w0 + kUp2Cols - 1) / kUp2Cols;
+        n_items = rcs * ccs;
+        scratch[(size_t)k * kScratchInts + 6] = n_items;
+      } else {  // nothing to compute: publish the empty result here
+        area_full[k] = 0;
+        reinterpret_cast<int4*>(box_full)[k] = make_int4(0, 0, 0, 0);
+      }
+    }
+    // exclusive scan of n_items over the strip
+    int inc = n_items;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += up;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = s_warp[lane];
+      int winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(kFull, winc, o);
+        if (lane >= o) winc += up;
+      }
+      s_warp[lane] = winc - w;
+      if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    int off = base + s_warp[warp] + inc - n_items;
+    for (int i = 0; i < n_items; ++i, ++off) {
+      const int rc = i / ccs, cc = i - rc * ccs;
+      const int gA = m.g0 + rc * kUp2Groups, gB = min(gA + kUp2Groups, m.g1);
+      const int wA = m.w0 + cc * kUp2Cols, wB = min(wA + kUp2Cols, m.w1);
+      const int ya = min(max(t.y_grp_start[gA], m.r0), m.r1), yb = min(max(t.y_grp_start[gB], m.r0), m.r1);
+      const int l0 = t.ymin[ya], l1 = t.ymin[yb - 1] + t.ysize[yb - 1];
+      const int xa = min(wA << 5, ow - 1), xb = min((wB << 5) - 1, ow - 1);
+      const int tc0 = t.xmin[xa] & ~3;
+      const int tstride = min((t.xmin[xb] + t.xsize[xb] + 3) & ~3, iw) - tc0;
+      Up2Item it;
+      it.k = k;
+      it.g = gA | ((gB - gA) << 16);
+      it.w = wA | ((wB - wA) << 16);
+      it.y = ya | ((yb - ya) << 16);
+      it.lr = l0 | ((l1 - l0) << 16);
+      it.tc = tc0 | (tstride << 16);
+      it.staged = (l1 - l0) * tstride <= tile_cap_floats ? 1 : 0;
+      it.pad = 0;
+      items[off] = it;
+    }
+    base += s_warp[32];
+    __syncthreads();
+  }
+  if (tid == 0) { ctr[0] = base; ctr[1] = 0; }
+}
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+__global__ void __launch_bounds__(kUp2Threads, kUp2CtasPerSm)
+upsample_pack2_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restrict__ meta, int ih, int iw, int oh,
+                      int ow, UpTables t, uint32_t* __restrict__ bits_full, int32_t* __restrict__ area_full,
+                      int32_t* __restrict__ box_full, int32_t* __restrict__ scratch, const Up2Item* __restrict__ items,
+                      int32_t* __restrict__ ctr) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  float4* s_pkx = reinterpret_cast<float4*>(s_raw);                       // [kUp2Cols * 32]
+  float4* s_pky = s_pkx + kUp2Cols * 32;                                  // [kUp2Rows]
+  uint32_t* s_out = reinterpret_cast<uint32_t*>(s_pky + kUp2Rows);        // [kUp2Cols * kUp2OutStride]
+  int* s_gstart = reinterpret_cast<int*>(s_out + kUp2Cols * kUp2OutStride);  // [kUp2Groups + 4]
+  const int lr_wpr = iw >> 5;
+  uint32_t* s_lr = reinterpret_cast<uint32_t*>(s_gstart + kUp2Groups + 4);   // [ih * lr_wpr + 4] (one spare word is read)
+  float* tile = reinterpret_cast<float*>(s_lr + ((ih * lr_wpr + 4 + 3) & ~3));
+  __shared__ int s_item, s_unit;
+  __shared__ int s_red[5];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int ow_words = (ow + 31) >> 5;
+  const int total = ctr[0];
+  for (;;) {
+    __syncthreads();  // the previous item is completely done with shared memory
+    if (tid == 0) { s_item = atomicAdd(&ctr[1], 1); s_unit = 0; }
+    if (tid < 5) s_red[tid] = 0;
+    __syncthreads();
+    const int item = s_item;
+    if (item >= total) break;
+    const Up2Item it = items[item];
+    const int k = it.k;
+    const UpMeta mt = meta[k];
+    const int gA = it.g & 0xffff, ng = it.g >> 16;
+    const int wA = it.w & 0xffff, nw = it.w >> 16;
+    const int ya0 = it.y & 0xffff, n_rows = it.y >> 16;
+    const int clr0 = it.lr & 0xffff, tr = it.lr >> 16;
+    const int tc0 = it.tc & 0xffff, tstride = it.tc >> 16;
+    const bool staged = it.staged != 0;
+    const float* src = mt.logits;
+    // ---- stage everything the item reads
+    if (staged) {
+      const int cpr = tstride >> 2;
+      const int n_chunks = tr * cpr;
+      const float* g0p = src + (size_t)clr0 * iw + tc0;
+      for (int i = tid; i < n_chunks; i += kUp2Threads) {
+        const int row = i / cpr, c4 = (i - row * cpr) << 2;
+        cp_async16(tile + row * tstride + c4, g0p + (size_t)row * iw + c4);
+      }
+    }
+    {
+      const uint32_t* lr = bits_lr + ((size_t)mt.src * ih + clr0) * lr_wpr;
+      const int n_lr = tr * lr_wpr;
+      for (int i = tid; i < n_lr; i += kUp2Threads) cp_async4(s_lr + i, lr + i);
+      for (int i = tid; i < n_rows; i += kUp2Threads) cp_async16(s_pky + i, t.pk_y + ya0 + i);
+      const float4* px = t.pk_x + (wA << 5);
+      for (int i = tid; i < (nw << 5); i += kUp2Threads) cp_async16(s_pkx + i, px + i);
+      if (tid <= ng) s_gstart[tid] = min(max(t.y_grp_start[gA + tid], mt.r0), mt.r1);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // taps are read at  tap_base[row * tap_stride + max(col - tap_c0, 0)]
+    const float* tap_base = staged ? tile - clr0 * tstride : src;
+    const int tap_stride = staged ? tstride : iw;
+    const int tap_c0 = staged ? tc0 : 0;
+    const bool safe = mt.safe != 0;
+    // ---- columns of the item, handed out to the warps dynamically
+    for (;;) {
+      int u = 0;
+      if (lane == 0) u = atomicAdd(&s_unit, 1);
+      u = __shfl_sync(kFull, u, 0);
+      if (u >= nw) break;
+      const int wi = wA + u;
+      const int x0 = min(wi << 5, ow - 1);
+      const int x1 = min(x0 + 31, ow - 1);
+      const uint32_t valid = (x1 - x0 == 31) ? 0xffffffffu : ((1u << (x1 - x0 + 1)) - 1u);
+      const int p0 = __float_as_int(s_pkx[x0 - (wA << 5)].x), p1 = __float_as_int(s_pkx[x1 - (wA << 5)].x);
+      const int c0 = p0 & 0xffff;
+      const int c1 = (p1 & 0xffff) + (p1 >> 16);  // exclusive
+      const int cw0 = c0 >> 5;
+      const bool two_words = ((c1 - 1) >> 5) <= cw0 + 1;
+      uint32_t m0, m1 = 0;
+      {
+        const int lo = c0 - (cw0 << 5), hi = min(c1 - (cw0 << 5), 32);
+        m0 = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+        const int hi1 = c1 - ((cw0 + 1) << 5);
+        if (hi1 > 0) m1 = hi1 >= 32 ? 0xffffffffu : ((1u << hi1) - 1u);
+      }
+      // classification, lane = row group: 0 = all background, 1 = all foreground (and safe), 2 = boundary word
+      int cls = 0;
+      if (lane < ng) {
+        const int ya = s_gstart[lane], nrows = s_gstart[lane + 1] - ya;
+        if (nrows > 0) {
+          const int pky = __float_as_int(s_pky[ya - ya0].x);
+          const int ry0 = pky & 0xffff, rys = pky >> 16;
+          const int lrb = (ry0 - clr0) * lr_wpr + cw0;
+          bool all0 = true, all1 = true;
+          if (two_words) {
+            uint32_t any = 0, miss = 0;
+            for (int r = 0; r < rys; ++r) {
+              const uint32_t v0 = s_lr[lrb + r * lr_wpr] & m0;
+              const uint32_t v1 = s_lr[lrb + r * lr_wpr + 1] & m1;
+              any |= v0 | v1;
+              miss |= (v0 ^ m0) | (v1 ^ m1);
+            }
+            all0 = any == 0;
+            all1 = miss == 0;
+          } else {
+            for (int r = 0; r < rys; ++r) {
+              const uint32_t* row = s_lr + (lrb - cw0) + r * lr_wpr;
+              for (int cw = cw0; cw <= (c1 - 1) >> 5; ++cw) {
+                const int lo = max(c0 - (cw << 5), 0), hi = min(c1 - (cw << 5), 32);
+                const uint32_t m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+                const uint32_t v = row[cw] & m;
+                all0 = all0 && (v == 0);
+                all1 = all1 && (v == m);
+              }
+            }
+          }
+          cls = all0 ? 0 : ((all1 && safe) ? 1 : 2);
+          if (cls != 2) {
+            const uint32_t word = cls == 1 ? valid : 0u;
+            const int row = ya - ya0;
+            for (int j = 0; j < nrows; ++j) s_out[u * kUp2OutStride + (row + j) + ((row + j) >> 5)] = word;
+          }
+        }
+      }
+      uint32_t mixed = __ballot_sync(kFull, cls == 2);
+      if (mixed == 0) continue;
+      // evaluation, lane = pixel of the word
+      const float4 xt = s_pkx[(u << 5) + lane];
+      const int pk = __float_as_int(xt.x);
+      const int cx = pk & 0xffff, cs = pk >> 16;  // records past the image width: cs = 0, cx = 0, zero weights
+      const int colp = max(cx - tap_c0, 0);
+      while (mixed) {
+        const int gl = __ffs(mixed) - 1;
+        mixed &= mixed - 1;
+        const int ya = s_gstart[gl], nrows = s_gstart[gl + 1] - ya;
+        const float4 y0rec = s_pky[ya - ya0];
+        const int pky = __float_as_int(y0rec.x);
+        const int ry0 = pky & 0xffff, rys = pky >> 16;
+        // horizontal pass of the group's input rows: acc = s0*w0; acc = fma(s_j, w_j, acc) for j < cs.  Rows / taps
+        // beyond the span contribute fma(0, 0, acc), which leaves `acc > 0` unchanged.
+        const float* pl = tap_base + (ry0 * tap_stride + colp);
+        float T[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          float acc = 0.0f;
+          if (r < rys) {  // (warp-uniform)
+            const float* pr = pl + r * tap_stride;
+            acc = __fmul_rn(pr[0], xt.y);
+            if (cs > 1) acc = __fmaf_rn(pr[1], xt.z, acc);
+            if (cs > 2) acc = __fmaf_rn(pr[2], xt.w, acc);
+          }
+          T[r] = acc;
+        }
+        uint32_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < kGrpMax; ++j) {
+          // weights of row ya + j (rows past the group's last one repeat it and are dropped at the store)
+          const float4 wv = j == 0 ? y0rec : s_pky[min(ya + j, ya + nrows - 1) - ya0];
+          float acc = __fmul_rn(T[0], wv.y);
+          acc = __fmaf_rn(T[1], wv.z, acc);
+          acc = __fmaf_rn(T[2], wv.w, acc);
+          const uint32_t res = __ballot_sync(kFull, cs > 0 && acc > 0.0f);
+          if (lane == j) mine = res;
+        }
+        if (lane < nrows) {
+          const int row = ya - ya0 + lane;
+          s_out[u * kUp2OutStride + row + (row >> 5)] = mine;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- epilogue: result tile -> global in 32-byte row segments; area and box from the words
+    {
+      uint32_t* dst = bits_full + (size_t)k * oh * ow_words;
+      const int c = tid & (kUp2Cols - 1);
+      int area = 0, miny = kBig, maxy = -1;
+      uint32_t colbits = 0;
+      if (c < nw) {
+        for (int row = tid >> 3; row < n_rows; row += kUp2Threads / kUp2Cols) {
+          const uint32_t w = s_out[c * kUp2OutStride + row + (row >> 5)];
+          dst[(uint32_t)((ya0 + row) * ow_words + wA + c)] = w;
+          area += __popc(w);
+          colbits |= w;
+          if (w) { miny = min(miny, ya0 + row); maxy = max(maxy, ya0 + row); }
+        }
+      }
+      int minx = kBig, maxx = -1;
+      if (colbits) {
+        minx = ((wA + c) << 5) + __ffs(colbits) - 1;
+        maxx = ((wA + c) << 5) + 31 - __clz(colbits);
+      }
+      area = warp_sum(area);
+      minx = warp_min(minx); miny = warp_min(miny); maxx = warp_max(maxx); maxy = warp_max(maxy);
+      if (lane == 0) {
+        atomicAdd(&s_red[0], area);
+        atomicMax(&s_red[1], maxx + 1);
+        atomicMax(&s_red[2], maxy + 1);
+        atomicMax(&s_red[3], kBig - minx);
+        atomicMax(&s_red[4], kBig - miny);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int32_t* sc = scratch + (size_t)k * kScratchInts;
+      atomicAdd(&sc[0], s_red[0]);
+      atomicMax(&sc[1], s_red[1]);
+      atomicMax(&sc[2], s_red[2]);
+      atomicMax(&sc[3], s_red[3]);
+      atomicMax(&sc[4], s_red[4]);
+      __threadfence();
+      const int prev = atomicAdd(&sc[5], 1);
+      if (prev == sc[6] - 1) {  // last item of this mask publishes the final statistics
+        __threadfence();
+        const int a = atomicAdd(&sc[0], 0);
+        const int mx1 = atomicMax(&sc[1], 0), my1 = atomicMax(&sc[2], 0);
+        const int bx = atomicMax(&sc[3], 0), by = atomicMax(&sc[4], 0);
+        area_full[k] = a;
+        int4 o = make_int4(0, 0, 0, 0);
+        if (a > 0) o = make_int4(kBig - bx, kBig - by, mx1 - 1, my1 - 1);
+        reinterpret_cast<int4*>(box_full)[k] = o;
+      }
+    }
+  }
+}
+
+// shared-memory layout of upsample_pack2_kernel in bytes, without / with a logit tile of `tile_floats`
+static size_t up2_fixed_smem(int ih, int iw) {
+  const size_t lr_words = (((size_t)ih * (iw / 32) + 4) + 3) & ~(size_t)3;
+  return sizeof(float4) * (kUp2Cols * 32 + kUp2Rows) + 4 * ((size_t)kUp2Cols * kUp2OutStride + kUp2Groups + 4 + lr_words);
+}
+// items a selection can expand to: every mask at most ceil(groups / 32) x ceil(words / 8), groups <= output rows
+static size_t up2_max_items(int max_sel, int oh, int ow) {
+  return (size_t)max_sel * ((oh + kUp2Groups - 1) / kUp2Groups) * ((((ow + 31) / 32) + kUp2Cols - 1) / kUp2Cols);
+}
+
 int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* logits, const uint32_t* bits_lr,
                          const int32_t* box_lr, const int32_t* flags_lr, int ih, int iw, const int32_t* sel,
                          const int32_t* n_sel, int max_sel, int oh, int ow, uint32_t* bits_full, int32_t* rect,
                          int32_t* area_full, int32_t* box_full, int32_t* scratch, const float* const* mask_ptr,
-                         cudaStream_t s, int stage_floats) {
+                         cudaStream_t s, int stage_floats, int sm_count) {
   if (max_sel <= 0) return NTTT_OK;
   if (iw % 32 != 0) return NTTT_EUNSUPPORTED;
+  UpTables t{tx.xmin, tx.xsize, tx.w, tx.taps, ty.xmin, ty.xsize, ty.w, ty.taps, tx.t_lo, tx.t_len, ty.t_lo, ty.t_len,
+             ty.grp_of, ty.grp_start, tx.pk, ty.pk};
+  UpMeta* meta = reinterpret_cast<UpMeta*>(scratch + (size_t)kScratchInts * max_sel);
+  if (tx.pk && ty.pk && oh < 65536 && ow < 65536 && ih * (iw / 32) <= 16384) {
+    // v2: plan + persistent work-list kernel
+    int32_t* ctr = reinterpret_cast<int32_t*>(meta + max_sel);
+    Up2Item* items = reinterpret_cast<Up2Item*>(ctr + 4);
+    // tile budget: what an item of 32 groups x 8 words needs at this scale (+ slack), bounded by `stage_floats`
+    const double sy = (double)ih / oh, sx = (double)iw / ow;
+    long need = (long)((kUp2Rows * sy + 6)) * (long)(((kUp2Cols * 32) * sx + 12));
+    int tile_floats = (int)(need < stage_floats ? need : stage_floats);
+    if (tile_floats < 0) tile_floats = 0;
+    tile_floats = (tile_floats + 3) & ~3;
+    const size_t smem = up2_fixed_smem(ih, iw) + (size_t)tile_floats * 4;
+    if (smem > 200 * 1024) return NTTT_EUNSUPPORTED;
+    upsample_plan_kernel<<<1, 1024, 0, s>>>(bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, t, meta, rect, scratch,
+                                            logits, mask_ptr, items, ctr, area_full, box_full, ow, tile_floats);
+    NTTT_LAUNCH_CHECK();
+    if (smem > 48 * 1024)
+      NTTT_CUDA(cudaFuncSetAttribute(upsample_pack2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (sm_count > 0 ? sm_count : 148) * kUp2CtasPerSm;
+    upsample_pack2_kernel<<<grid, kUp2Threads, smem, s>>>(bits_lr, meta, ih, iw, oh, ow, t, bits_full, area_full, box_full,
+                                                          scratch, items, ctr);
+    NTTT_LAUNCH_CHECK();
+    return NTTT_OK;
+  }
   // bits (+ one spare word read and masked off by the footprint test), padded to 16 bytes, then the logit tile
   const size_t bits_bytes = ((((size_t)ih * (iw / 32) + 1) + 3) & ~(size_t)3) * 4;
   if (bits_bytes > 160 * 1024) return NTTT_EUNSUPPORTED;
@@ -419,9 +820,6 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
   const size_t smem = bits_bytes + stage_bytes;
   if (smem > 48 * 1024)
     NTTT_CUDA(cudaFuncSetAttribute(upsample_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  UpTables t{tx.xmin, tx.xsize, tx.w, tx.taps, ty.xmin, ty.xsize, ty.w, ty.taps, tx.t_lo, tx.t_len, ty.t_lo, ty.t_len,
-             ty.grp_of, ty.grp_start, tx.pk, ty.pk};
-  UpMeta* meta = reinterpret_cast<UpMeta*>(scratch + (size_t)kScratchInts * max_sel);
   upsample_meta_kernel<<<ceil_div(max_sel, 256), 256, 0, s>>>(bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, t,
                                                               meta, rect, scratch, logits, mask_ptr);
   NTTT_LAUNCH_CHECK();
@@ -431,8 +829,9 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }
-size_t upsample_scratch_bytes(int max_sel) {
-  return (sizeof(int32_t) * kScratchInts + sizeof(UpMeta)) * (size_t)max_sel;
+size_t upsample_scratch_bytes(int max_sel, int oh, int ow) {
+  return (sizeof(int32_t) * kScratchInts + sizeof(UpMeta)) * (size_t)max_sel + 16 +
+         sizeof(Up2Item) * up2_max_items(max_sel, oh, ow);
 }
 
 // ---------------------------------------------------------------------------------------------------

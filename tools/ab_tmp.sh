@@ -1,5 +1,3 @@
 set -x
-python tools/profile_stage.py > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 120 --csv --log-file gpurun_out/launches_r2a.csv python tools/profile_stage.py > gpurun_out/ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:upsample_pack_kernel -s 3 -c 2 -o gpurun_out/prof_upsample_staged python tools/profile_stage.py > gpurun_out/ncu2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:upsample_pack_kernel -s 3 -c 2 -o gpurun_out/prof_upsample_direct python tools/profile_stage.py --tune upsample_stage_bytes=0 > gpurun_out/ncu3.log 2>&1
-tail -3 gpurun_out/ncu2.log
+python -m pytest tests/test_gpu_parity.py tests/test_rle.py tests/test_filter_and_graph.py -x -q 2>&1 | tail -8
+python bench.py --value-only --steps 8 --n-images 64 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('v2 us/img', round(d['us_per_image'],2))"
