@@ -439,8 +439,10 @@ struct alignas(16) Up2Item {  // 32 bytes, written by the plan kernel
   int pad;
 };
 
-// One CTA: per-mask geometry (as upsample_meta_kernel), then an exclusive scan of the items per mask and the item
-// records.  ctr[0] = number of items, ctr[1] = next item to hand out (zeroed here for the main kernel).
+// One CTA.  Per strip of 1024 masks: thread per MASK resolves the geometry (as upsample_meta_kernel) and counts its
+// items, a block scan gives the item offsets, then thread per ITEM finds its mask by binary search over the offsets and
+// writes the item record — the dependent table reads of different items overlap instead of queueing in one thread.
+// ctr[0] = number of items, ctr[1] = next item to hand out (zeroed here for the main kernel).
 __global__ void __launch_bounds__(1024)
 upsample_plan_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __restrict__ box_lr,
                      const int32_t* __restrict__ flags_lr, int ih, int iw, const int32_t* __restrict__ sel,
@@ -449,19 +451,21 @@ upsample_plan_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
                      const float* const* __restrict__ mask_ptr, Up2Item* __restrict__ items, int32_t* __restrict__ ctr,
                      int32_t* __restrict__ area_full, int32_t* __restrict__ box_full, int ow, int tile_cap_floats) {
   __shared__ int s_warp[33];
+  __shared__ int s_off[1024];   // exclusive item offset of each mask of the strip
+  __shared__ int s_ccs[1024];   // column chunks of each mask (0: no items)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = min(*n_sel, max_sel);
   int base = 0;
   for (int k0 = 0; k0 < max_sel; k0 += 1024) {
     const int k = k0 + tid;
-    int n_items = 0, rcs = 0, ccs = 0;
-    UpMeta m;
-    m.r0 = m.r1 = m.w0 = m.w1 = m.lr0 = m.lr1 = m.g0 = m.g1 = 0;
+    int n_items = 0, ccs = 0;
     if (k < max_sel) {
 #pragma unroll
       for (int q = 0; q < kScratchInts; ++q) scratch[(size_t)k * kScratchInts + q] = 0;
     }
     if (k < n) {
+      UpMeta m;
+      m.r0 = m.r1 = m.w0 = m.w1 = m.lr0 = m.lr1 = m.g0 = m.g1 = 0;
       m.src = sel[k];
       m.logits = mask_ptr ? mask_ptr[m.src] : logits + (size_t)m.src * ih * iw;
       const int4 b = reinterpret_cast<const int4*>(box_lr)[m.src];
@@ -484,9 +488,8 @@ upsample_plan_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
       meta[k] = m;
       reinterpret_cast<int4*>(rect)[k] = make_int4(m.r0, m.r1, m.w0, m.w1);
       if (m.r1 > m.r0 && m.w1 > m.w0) {
-        rcs = (m.g1 - m.g0 + kUp2Groups - 1) / kUp2Groups;
         ccs = (m.w1 - m.w0 + kUp2Cols - 1) / kUp2Cols;
-        n_items = rcs * ccs;
+        n_items = ((m.g1 - m.g0 + kUp2Groups - 1) / kUp2Groups) * ccs;
         scratch[(size_t)k * kScratchInts + 6] = n_items;
       } else {  // nothing to compute: publish the empty result here
         area_full[k] = 0;
@@ -514,9 +517,23 @@ upsample_plan_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
       if (lane == 31) s_warp[32] = winc;
     }
     __syncthreads();
-    int off = base + s_warp[warp] + inc - n_items;
-    for (int i = 0; i < n_items; ++i, ++off) {
-      const int rc = i / ccs, cc = i - rc * ccs;
+    s_off[tid] = s_warp[warp] + inc - n_items;
+    s_ccs[tid] = ccs;
+    __syncthreads();  // (also publishes meta[] of this strip to the whole CTA: same-CTA global writes + barrier)
+    const int strip_items = s_warp[32];
+    for (int e = tid; e < strip_items; e += 1024) {
+      // last mask of the strip whose offset is <= e and that has items
+      int lo = 0, hi = 1023;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_off[mid] <= e) lo = mid; else hi = mid - 1;
+      }
+      // masks without items share the offset of their successor: the search lands on the LAST of equal offsets,
+      // which is the one that owns the item
+      const int km = k0 + lo;
+      const UpMeta m = meta[km];
+      const int i = e - s_off[lo], cc_n = s_ccs[lo];
+      const int rc = i / cc_n, cc = i - rc * cc_n;
       const int gA = m.g0 + rc * kUp2Groups, gB = min(gA + kUp2Groups, m.g1);
       const int wA = m.w0 + cc * kUp2Cols, wB = min(wA + kUp2Cols, m.w1);
       const int ya = min(max(t.y_grp_start[gA], m.r0), m.r1), yb = min(max(t.y_grp_start[gB], m.r0), m.r1);
@@ -525,7 +542,7 @@ upsample_plan_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
       const int tc0 = t.xmin[xa] & ~3;
       const int tstride = min((t.xmin[xb] + t.xsize[xb] + 3) & ~3, iw) - tc0;
       Up2Item it;
-      it.k = k;
+      it.k = km;
       it.g = gA | ((gB - gA) << 16);
       it.w = wA | ((wB - wA) << 16);
       it.y = ya | ((yb - ya) << 16);
@@ -533,9 +550,9 @@ upsample_plan_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
       it.tc = tc0 | (tstride << 16);
       it.staged = (l1 - l0) * tstride <= tile_cap_floats ? 1 : 0;
       it.pad = 0;
-      items[off] = it;
+      items[base + e] = it;
     }
-    base += s_warp[32];
+    base += strip_items;
     __syncthreads();
   }
   if (tid == 0) { ctr[0] = base; ctr[1] = 0; }
@@ -545,6 +562,75 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+
+// taps of one input row for this lane's pixel: acc = s0*w0; acc = fma(s_j, w_j, acc) for j < cs
+template <bool kStaged>
+__device__ __forceinline__ float up2_row(const float* __restrict__ gsrc, uint32_t saddr, int idx, const float4& xt, int cs) {
+  float a0, a1 = 0.0f, a2 = 0.0f;
+  if (kStaged) {
+    const uint32_t p = saddr + ((uint32_t)idx << 2);
+    a0 = lds_f32(p);
+    if (cs > 1) a1 = lds_f32(p + 4);
+    if (cs > 2) a2 = lds_f32(p + 8);
+  } else {
+    const float* p = gsrc + idx;
+    a0 = __ldg(p);
+    if (cs > 1) a1 = __ldg(p + 1);
+    if (cs > 2) a2 = __ldg(p + 2);
+  }
+  // absent taps: value 0 and weight 0 -> fma(0, 0, acc), which leaves `acc > 0` unchanged
+  float acc = __fmul_rn(a0, xt.y);
+  acc = __fmaf_rn(a1, xt.z, acc);
+  acc = __fmaf_rn(a2, xt.w, acc);
+  return acc;
+}
+
+// per-group record of an item (shared memory): output row offset, rows, first tile row index * stride, input rows
+struct alignas(16) Up2Group { int row, nrows, trow, rys; };
+
+template <bool kStaged>
+__device__ __forceinline__ void up2_evaluate(int warp, int lane, int n_list, const uint16_t* __restrict__ s_list,
+                                             const Up2Group* __restrict__ s_grp, const float4* __restrict__ s_pkx,
+                                             const float4* __restrict__ s_pky, uint32_t* __restrict__ s_out,
+                                             const float* __restrict__ gsrc, uint32_t tile_saddr, int tap_stride,
+                                             int tap_c0) {
+  constexpr int kWarps = kUp2Threads / 32;
+  for (int e = warp; e < n_list; e += kWarps) {
+    const int ent = s_list[e];
+    const int u = ent >> 5, gl = ent & 31;
+    const Up2Group g = s_grp[gl];
+    const float4 xt = s_pkx[(u << 5) + lane];
+    const int pk = __float_as_int(xt.x);
+    const int cx = pk & 0xffff, cs = pk >> 16;  // records past the image width: cs = 0, cx = 0, zero weights
+    const int idx = g.trow + max(cx - tap_c0, 0);
+    // horizontal pass of the group's (<= 3) input rows; rows beyond the span stay 0 and meet a zero weight
+    const float T0 = up2_row<kStaged>(gsrc, tile_saddr, idx, xt, cs);
+    float T1 = 0.0f, T2 = 0.0f;
+    if (g.rys > 1) T1 = up2_row<kStaged>(gsrc, tile_saddr, idx + tap_stride, xt, cs);
+    if (g.rys > 2) T2 = up2_row<kStaged>(gsrc, tile_saddr, idx + 2 * tap_stride, xt, cs);
+    // vertical pass of the group's rows (rows past its last one use whatever record follows and are dropped)
+    const float4* wy = s_pky + g.row;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < kGrpMax; ++j) {
+      const float4 wv = wy[j];
+      float acc = __fmul_rn(T0, wv.y);
+      acc = __fmaf_rn(T1, wv.z, acc);
+      acc = __fmaf_rn(T2, wv.w, acc);
+      const uint32_t res = __ballot_sync(kFull, cs > 0 && acc > 0.0f);
+      if (lane == j) mine = res;
+    }
+    if (lane < g.nrows) {
+      const int row = g.row + lane;
+      s_out[u * kUp2OutStride + row + (row >> 5)] = mine;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kUp2Threads, kUp2CtasPerSm)
 upsample_pack2_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restrict__ meta, int ih, int iw, int oh,
@@ -553,20 +639,25 @@ upsample_pack2_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __rest
                       int32_t* __restrict__ ctr) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   float4* s_pkx = reinterpret_cast<float4*>(s_raw);                       // [kUp2Cols * 32]
-  float4* s_pky = s_pkx + kUp2Cols * 32;                                  // [kUp2Rows]
-  uint32_t* s_out = reinterpret_cast<uint32_t*>(s_pky + kUp2Rows);        // [kUp2Cols * kUp2OutStride]
+  float4* s_pky = s_pkx + kUp2Cols * 32;                                  // [kUp2Rows + kGrpMax] (rows past the end are read)
+  Up2Group* s_grp = reinterpret_cast<Up2Group*>(s_pky + kUp2Rows + kGrpMax);  // [kUp2Groups]
+  uint32_t* s_out = reinterpret_cast<uint32_t*>(s_grp + kUp2Groups);      // [kUp2Cols * kUp2OutStride]
   int* s_gstart = reinterpret_cast<int*>(s_out + kUp2Cols * kUp2OutStride);  // [kUp2Groups + 4]
+  uint16_t* s_list = reinterpret_cast<uint16_t*>(s_gstart + kUp2Groups + 4);  // [kUp2Cols * kUp2Groups] boundary words
   const int lr_wpr = iw >> 5;
-  uint32_t* s_lr = reinterpret_cast<uint32_t*>(s_gstart + kUp2Groups + 4);   // [ih * lr_wpr + 4] (one spare word is read)
+  uint32_t* s_lr = reinterpret_cast<uint32_t*>(s_list + kUp2Cols * kUp2Groups);  // [ih * lr_wpr + 4] (one spare word is read)
   float* tile = reinterpret_cast<float*>(s_lr + ((ih * lr_wpr + 4 + 3) & ~3));
-  __shared__ int s_item, s_unit;
+  __shared__ int s_item;
   __shared__ int s_red[5];
-  const int tid = threadIdx.x, lane = tid & 31;
+  __shared__ uint32_t s_mix[kUp2Cols];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kUp2Threads / 32;
   const int ow_words = (ow + 31) >> 5;
   const int total = ctr[0];
+  const uint32_t tile_saddr = (uint32_t)__cvta_generic_to_shared(tile);
   for (;;) {
     __syncthreads();  // the previous item is completely done with shared memory
-    if (tid == 0) { s_item = atomicAdd(&ctr[1], 1); s_unit = 0; }
+    if (tid == 0) s_item = atomicAdd(&ctr[1], 1);
     if (tid < 5) s_red[tid] = 0;
     __syncthreads();
     const int item = s_item;
@@ -581,15 +672,12 @@ upsample_pack2_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __rest
     const int tc0 = it.tc & 0xffff, tstride = it.tc >> 16;
     const bool staged = it.staged != 0;
     const float* src = mt.logits;
-    // ---- stage everything the item reads
+    // ---- stage everything the item reads (cp.async: nothing is held in registers while in flight)
     if (staged) {
-      const int cpr = tstride >> 2;
-      const int n_chunks = tr * cpr;
+      const int cpr = tstride >> 2;  // 16-byte chunks per tile row
       const float* g0p = src + (size_t)clr0 * iw + tc0;
-      for (int i = tid; i < n_chunks; i += kUp2Threads) {
-        const int row = i / cpr, c4 = (i - row * cpr) << 2;
-        cp_async16(tile + row * tstride + c4, g0p + (size_t)row * iw + c4);
-      }
+      for (int row = warp; row < tr; row += kWarps)
+        for (int c = lane; c < cpr; c += 32) cp_async16(tile + row * tstride + (c << 2), g0p + (size_t)row * iw + (c << 2));
     }
     {
       const uint32_t* lr = bits_lr + ((size_t)mt.src * ih + clr0) * lr_wpr;
@@ -602,17 +690,30 @@ upsample_pack2_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __rest
     }
     cp_async_wait_all();
     __syncthreads();
-    // taps are read at  tap_base[row * tap_stride + max(col - tap_c0, 0)]
-    const float* tap_base = staged ? tile - clr0 * tstride : src;
+    // taps are read at index  trow + max(col - tap_c0, 0)  of the shared tile (staged) or of the global logits
     const int tap_stride = staged ? tstride : iw;
     const int tap_c0 = staged ? tc0 : 0;
     const bool safe = mt.safe != 0;
-    // ---- columns of the item, handed out to the warps dynamically
-    for (;;) {
-      int u = 0;
-      if (lane == 0) u = atomicAdd(&s_unit, 1);
-      u = __shfl_sync(kFull, u, 0);
-      if (u >= nw) break;
+    // ---- phase A: footprint classification, lane = row group, warp w takes the columns w, w + 4
+    int my_ya = 0, my_nrows = 0, my_ry0 = 0, my_rys = 0;
+    if (lane < ng) {
+      my_ya = s_gstart[lane];
+      my_nrows = s_gstart[lane + 1] - my_ya;
+      if (my_nrows > 0) {
+        const int pky = __float_as_int(s_pky[my_ya - ya0].x);
+        my_ry0 = pky & 0xffff;
+        my_rys = pky >> 16;
+      }
+      if (warp == 0) {
+        Up2Group g;
+        g.row = my_ya - ya0;
+        g.nrows = my_nrows;
+        g.trow = (staged ? my_ry0 - clr0 : my_ry0) * tap_stride;
+        g.rys = my_rys;
+        s_grp[lane] = g;
+      }
+    }
+    for (int u = warp; u < nw; u += kWarps) {
       const int wi = wA + u;
       const int x0 = min(wi << 5, ow - 1);
       const int x1 = min(x0 + 31, ow - 1);
@@ -629,91 +730,62 @@ upsample_pack2_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __rest
         const int hi1 = c1 - ((cw0 + 1) << 5);
         if (hi1 > 0) m1 = hi1 >= 32 ? 0xffffffffu : ((1u << hi1) - 1u);
       }
-      // classification, lane = row group: 0 = all background, 1 = all foreground (and safe), 2 = boundary word
+      // 0 = all background, 1 = all foreground (and safe), 2 = boundary word
       int cls = 0;
-      if (lane < ng) {
-        const int ya = s_gstart[lane], nrows = s_gstart[lane + 1] - ya;
-        if (nrows > 0) {
-          const int pky = __float_as_int(s_pky[ya - ya0].x);
-          const int ry0 = pky & 0xffff, rys = pky >> 16;
-          const int lrb = (ry0 - clr0) * lr_wpr + cw0;
-          bool all0 = true, all1 = true;
-          if (two_words) {
-            uint32_t any = 0, miss = 0;
-            for (int r = 0; r < rys; ++r) {
-              const uint32_t v0 = s_lr[lrb + r * lr_wpr] & m0;
-              const uint32_t v1 = s_lr[lrb + r * lr_wpr + 1] & m1;
-              any |= v0 | v1;
-              miss |= (v0 ^ m0) | (v1 ^ m1);
-            }
-            all0 = any == 0;
-            all1 = miss == 0;
-          } else {
-            for (int r = 0; r < rys; ++r) {
-              const uint32_t* row = s_lr + (lrb - cw0) + r * lr_wpr;
-              for (int cw = cw0; cw <= (c1 - 1) >> 5; ++cw) {
-                const int lo = max(c0 - (cw << 5), 0), hi = min(c1 - (cw << 5), 32);
-                const uint32_t m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-                const uint32_t v = row[cw] & m;
-                all0 = all0 && (v == 0);
-                all1 = all1 && (v == m);
-              }
+      if (my_nrows > 0) {
+        const int lrb = (my_ry0 - clr0) * lr_wpr + cw0;
+        bool all0 = true, all1 = true;
+        if (two_words) {
+          uint32_t any = 0, miss = 0;
+          for (int r = 0; r < my_rys; ++r) {
+            const uint32_t v0 = s_lr[lrb + r * lr_wpr] & m0;
+            const uint32_t v1 = s_lr[lrb + r * lr_wpr + 1] & m1;
+            any |= v0 | v1;
+            miss |= (v0 ^ m0) | (v1 ^ m1);
+          }
+          all0 = any == 0;
+          all1 = miss == 0;
+        } else {
+          for (int r = 0; r < my_rys; ++r) {
+            const uint32_t* row = s_lr + (lrb - cw0) + r * lr_wpr;
+            for (int cw = cw0; cw <= (c1 - 1) >> 5; ++cw) {
+              const int lo = max(c0 - (cw << 5), 0), hi = min(c1 - (cw << 5), 32);
+              const uint32_t m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+              const uint32_t v = row[cw] & m;
+              all0 = all0 && (v == 0);
+              all1 = all1 && (v == m);
             }
           }
-          cls = all0 ? 0 : ((all1 && safe) ? 1 : 2);
-          if (cls != 2) {
-            const uint32_t word = cls == 1 ? valid : 0u;
-            const int row = ya - ya0;
-            for (int j = 0; j < nrows; ++j) s_out[u * kUp2OutStride + (row + j) + ((row + j) >> 5)] = word;
-          }
+        }
+        cls = all0 ? 0 : ((all1 && safe) ? 1 : 2);
+        if (cls != 2) {
+          const uint32_t word = cls == 1 ? valid : 0u;
+          const int row = my_ya - ya0;
+          for (int j = 0; j < my_nrows; ++j) s_out[u * kUp2OutStride + (row + j) + ((row + j) >> 5)] = word;
         }
       }
-      uint32_t mixed = __ballot_sync(kFull, cls == 2);
-      if (mixed == 0) continue;
-      // evaluation, lane = pixel of the word
-      const float4 xt = s_pkx[(u << 5) + lane];
-      const int pk = __float_as_int(xt.x);
-      const int cx = pk & 0xffff, cs = pk >> 16;  // records past the image width: cs = 0, cx = 0, zero weights
-      const int colp = max(cx - tap_c0, 0);
-      while (mixed) {
-        const int gl = __ffs(mixed) - 1;
-        mixed &= mixed - 1;
-        const int ya = s_gstart[gl], nrows = s_gstart[gl + 1] - ya;
-        const float4 y0rec = s_pky[ya - ya0];
-        const int pky = __float_as_int(y0rec.x);
-        const int ry0 = pky & 0xffff, rys = pky >> 16;
-        // horizontal pass of the group's input rows: acc = s0*w0; acc = fma(s_j, w_j, acc) for j < cs.  Rows / taps
-        // beyond the span contribute fma(0, 0, acc), which leaves `acc > 0` unchanged.
-        const float* pl = tap_base + (ry0 * tap_stride + colp);
-        float T[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          float acc = 0.0f;
-          if (r < rys) {  // (warp-uniform)
-            const float* pr = pl + r * tap_stride;
-            acc = __fmul_rn(pr[0], xt.y);
-            if (cs > 1) acc = __fmaf_rn(pr[1], xt.z, acc);
-            if (cs > 2) acc = __fmaf_rn(pr[2], xt.w, acc);
-          }
-          T[r] = acc;
-        }
-        uint32_t mine = 0;
-#pragma unroll
-        for (int j = 0; j < kGrpMax; ++j) {
-          // weights of row ya + j (rows past the group's last one repeat it and are dropped at the store)
-          const float4 wv = j == 0 ? y0rec : s_pky[min(ya + j, ya + nrows - 1) - ya0];
-          float acc = __fmul_rn(T[0], wv.y);
-          acc = __fmaf_rn(T[1], wv.z, acc);
-          acc = __fmaf_rn(T[2], wv.w, acc);
-          const uint32_t res = __ballot_sync(kFull, cs > 0 && acc > 0.0f);
-          if (lane == j) mine = res;
-        }
-        if (lane < nrows) {
-          const int row = ya - ya0 + lane;
-          s_out[u * kUp2OutStride + row + (row >> 5)] = mine;
-        }
-      }
+      const uint32_t mixed = __ballot_sync(kFull, cls == 2);
+      if (lane == 0) s_mix[u] = mixed;
     }
+    __syncthreads();
+    // ---- the item's boundary words as one list, so that the warps share them evenly whatever their distribution
+    int n_list = 0;
+    {
+      int off = 0;  // every warp computes the (<= 8) offsets; warp w writes the entries of its columns
+      for (int u = 0; u < nw; ++u) {
+        const uint32_t mixed = s_mix[u];
+        if ((u & (kWarps - 1)) == warp && ((mixed >> lane) & 1u))
+          s_list[off + __popc(mixed & ((1u << lane) - 1u))] = (uint16_t)((u << 5) | lane);
+        off += __popc(mixed);
+      }
+      n_list = off;
+    }
+    __syncthreads();
+    // ---- phase B: evaluation, lane = pixel of the word
+    if (staged)
+      up2_evaluate<true>(warp, lane, n_list, s_list, s_grp, s_pkx, s_pky, s_out, src, tile_saddr, tap_stride, tap_c0);
+    else
+      up2_evaluate<false>(warp, lane, n_list, s_list, s_grp, s_pkx, s_pky, s_out, src, tile_saddr, tap_stride, tap_c0);
     __syncthreads();
     // ---- epilogue: result tile -> global in 32-byte row segments; area and box from the words
     {
@@ -772,7 +844,8 @@ upsample_pack2_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __rest
 // shared-memory layout of upsample_pack2_kernel in bytes, without / with a logit tile of `tile_floats`
 static size_t up2_fixed_smem(int ih, int iw) {
   const size_t lr_words = (((size_t)ih * (iw / 32) + 4) + 3) & ~(size_t)3;
-  return sizeof(float4) * (kUp2Cols * 32 + kUp2Rows) + 4 * ((size_t)kUp2Cols * kUp2OutStride + kUp2Groups + 4 + lr_words);
+  return sizeof(float4) * (kUp2Cols * 32 + kUp2Rows + kGrpMax + kUp2Groups) +
+         4 * ((size_t)kUp2Cols * kUp2OutStride + kUp2Groups + 4 + lr_words) + 2 * (size_t)kUp2Cols * kUp2Groups;
 }
 // items a selection can expand to: every mask at most ceil(groups / 32) x ceil(words / 8), groups <= output rows
 static size_t up2_max_items(int max_sel, int oh, int ow) {

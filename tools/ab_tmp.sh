@@ -1,3 +1,2 @@
-set -x
-python -m pytest tests/test_gpu_parity.py tests/test_rle.py tests/test_filter_and_graph.py -x -q 2>&1 | tail -8
-python bench.py --value-only --steps 8 --n-images 64 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('v2 us/img', round(d['us_per_image'],2))"
+python tools/profile_stage.py > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:upsample_pack2_kernel -s 3 -c 1 -o gpurun_out/prof_upsample_v2b python tools/profile_stage.py > gpurun_out/ncu2.log 2>&1
+tail -2 gpurun_out/ncu2.log
