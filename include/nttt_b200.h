@@ -60,7 +60,7 @@ void nttt_ctx_destroy(nttt_ctx* ctx);
  *   NTTT_TUNE_UPSAMPLE_STAGE_BYTES  shared-memory budget per CTA of the full-resolution resize for staging the logit
  *                                   tile under its row groups (0 = every tap is read from global memory; tiles that
  *                                   do not fit take that path anyway).  Default 36 KB. */
-enum { NTTT_TUNE_UPSAMPLE_STAGE_BYTES = 1 };
+enum { NTTT_TUNE_UPSAMPLE_STAGE_BYTES = 1, NTTT_TUNE_LOWRES_EXTRA_SMEM = 2 };
 int nttt_ctx_tune(nttt_ctx* ctx, int what, long long value);
 
 /* number of kernels this library has launched in this process (bench.py's `gpu_launches`) */

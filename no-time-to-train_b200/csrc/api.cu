@@ -15,12 +15,12 @@ int launch_multimask_select(const float*, int, int, int, const ChunkTable&, int,
                             cudaStream_t);
 int launch_project_masks(const AxisTable&, const AxisTable&, const uint32_t*, const int32_t*, int, int, int, int, int,
                          void*, int, bool, cudaStream_t);
-int launch_normalize_split(const float*, const int32_t*, int, int, int, float*, void*, bool, cudaStream_t);
+int launch_normalize_split(const float*, int, const int32_t*, int, int, int, float*, void*, bool, cudaStream_t);
 int launch_gemm_tc(const void*, int, const void*, int, float*, int, int, int, int, int, size_t, int*, cudaStream_t);
 int gemm_tc_pick_splits(int, int, int, int);
 int launch_split_rows(const float*, int, int, int, int, int, void*, cudaStream_t);
 int launch_split_transpose(const float*, int, int, int, int, int, void*, cudaStream_t);
-int launch_normalize_rows(const float*, const int32_t*, int, int, float*, bool, cudaStream_t);
+int launch_normalize_rows(const float*, int, const int32_t*, int, int, float*, bool, cudaStream_t);
 int launch_proto_prepare(const float*, int, int, int, float*, cudaStream_t);
 int launch_top1(const float*, int, size_t, float*, int, int, int, float*, int32_t*, cudaStream_t);
 int launch_neg_top1(const float*, int, size_t, const float*, int, size_t, int, int, int, float, float*, float*, int32_t*,
@@ -49,6 +49,7 @@ int launch_fill_scatter(const float*, const float*, const float*, const int32_t*
                         cudaStream_t);
 int launch_fill_finalize(const float*, const float*, int, int, int, float*, float*, cudaStream_t);
 
+extern int g_pack_extra_smem;  // lowres.cu
 static thread_local char g_cuda_err[512] = "";
 unsigned long long g_launches = 0;
 
@@ -76,24 +77,30 @@ inline int pad64(int k) { return (k + 63) / 64 * 64; }
 // sums[n, c] = proj[n, e] * feat[e, c] on the tensor cores (split-bf16, K' = 3 * pad64(e))
 // scratch: a_split [n, 3*ep] bf16, b_split [c, 3*ep] bf16
 // (proj == nullptr: a_split already holds the split projection, written by project_masks_kernel<true>)
+// The 128 x 128 output tiles of a 1024 x 1024 pooling GEMM occupy 64 of the 148 SMs, each pulling its operands through
+// its own L2 port: split K in kPoolSplits so that twice as many SMs share the same traffic.  The partial sums go to
+// sums[z] (stride n*c floats) and are added in a fixed order by the normalisation kernel that reads them anyway.
+constexpr int kPoolSplits = 1;  // measured: 2 halves the latency (25 -> 14 us) but costs throughput (100.7 -> 103.5 us/image with 16 images in flight: more SM-time in total)
 static int pool_contract(const float* proj, const float* feat, int n, int e, int c, float* sums, void* a_split,
-                         void* b_split, cudaStream_t s) {
+                         void* b_split, int* n_partials, cudaStream_t s) {
   const int ep = pad64(e);
   int err = proj ? launch_split_rows(proj, e, n, e, ep, 0, a_split, s) : NTTT_OK;
   if (err) return err;
   err = launch_split_transpose(feat, c, c, e, ep, 1, b_split, s);
   if (err) return err;
-  return launch_gemm_tc(a_split, 3 * ep, b_split, 3 * ep, sums, c, n, c, 3 * ep, 1, 0, nullptr, s);
+  return launch_gemm_tc(a_split, 3 * ep, b_split, 3 * ep, sums, c, n, c, 3 * ep, kPoolSplits, (size_t)n * c, n_partials, s);
 }
 
 // rows of `sums` -> /area -> L2-normalise -> obj_feats (+ split-bf16 copy when the vector path applies).
 // Returns through *split_done whether a_split now holds the similarity GEMM's A operand.
 // nan_empty: negative-reference scoring divides by the raw area (empty mask -> NaN row, as the reference does)
-static int normalize_rows(const float* sums, const int32_t* area, int n, int c, float* obj_feats, void* a_split,
-                          bool* split_done, bool nan_empty, cudaStream_t s) {
-  *split_done = a_split && launch_normalize_split(sums, area, n, c, pad64(c), obj_feats, a_split, nan_empty, s) == 1;
+// n_partials: split-K partial sums of the pooling GEMM, n*c floats apart, added in order
+static int normalize_rows(const float* sums, int n_partials, const int32_t* area, int n, int c, float* obj_feats,
+                          void* a_split, bool* split_done, bool nan_empty, cudaStream_t s) {
+  *split_done = a_split &&
+                launch_normalize_split(sums, n_partials, area, n, c, pad64(c), obj_feats, a_split, nan_empty, s) == 1;
   if (*split_done) return NTTT_OK;
-  return launch_normalize_rows(sums, area, n, c, obj_feats, nan_empty, s);
+  return launch_normalize_rows(sums, n_partials, area, n, c, obj_feats, nan_empty, s);
 }
 
 // the scatter tables hold kMaxScatter weights per encoder cell: enough while out/in <= ~11
@@ -205,6 +212,10 @@ const char* nttt_profile_stage_name(int i) { return (i >= 0 && i < kNumStages) ?
 int nttt_ctx_tune(nttt_ctx* ctx, int what, long long value) {
   if (!ctx) return NTTT_EINVAL;
   switch (what) {
+    case NTTT_TUNE_LOWRES_EXTRA_SMEM:
+      if (value < 0 || value > 128 * 1024) return NTTT_EINVAL;
+      nttt::g_pack_extra_smem = (int)value;
+      return NTTT_OK;
     case NTTT_TUNE_UPSAMPLE_STAGE_BYTES:
       if (value < 0 || value > 160 * 1024) return NTTT_EINVAL;
       ctx->upsample_stage_floats = (int)(value / 4);
@@ -351,7 +362,7 @@ int nttt_project_masks(nttt_ctx* ctx, const uint32_t* bits, const int32_t* box, 
 
 size_t nttt_pool_workspace_bytes(int n, int e, int c) {
   const size_t ep = pad64(e);
-  return align_up(sizeof(float) * (size_t)n * c, 256) + align_up(2 * (size_t)n * 3 * ep, 256) +
+  return align_up(sizeof(float) * (size_t)kPoolSplits * n * c, 256) + align_up(2 * (size_t)n * 3 * ep, 256) +
          align_up(2 * (size_t)c * 3 * ep, 256);
 }
 
@@ -364,12 +375,13 @@ int nttt_pool_normalize(nttt_ctx* ctx, const float* proj, const float* feat, con
   cudaStream_t s = (cudaStream_t)stream;
   char* ws = static_cast<char*>(workspace);
   float* sums = reinterpret_cast<float*>(ws);
-  char* a_split = ws + align_up(sizeof(float) * (size_t)n * c, 256);
+  char* a_split = ws + align_up(sizeof(float) * (size_t)kPoolSplits * n * c, 256);
   char* b_split = a_split + align_up(2 * (size_t)n * 3 * pad64(e), 256);
-  int err = pool_contract(proj, feat, n, e, c, sums, a_split, b_split, s);
+  int n_partials = 1;
+  int err = pool_contract(proj, feat, n, e, c, sums, a_split, b_split, &n_partials, s);
   if (err) return err;
   bool split_done;
-  return normalize_rows(sums, area, n, c, obj_feats, nullptr, &split_done, false, s);
+  return normalize_rows(sums, n_partials, area, n, c, obj_feats, nullptr, &split_done, false, s);
 }
 
 int nttt_proto_prepare(const float* feats_ins_avg, int n_cls, int shots, int c, float* proto, void* stream) {
@@ -601,7 +613,7 @@ static MatchLayout carve(void* ws, int n, int lr_h, int lr_w, int eh, int ew, in
   L.stab = cv.take<int32_t>((size_t)n * 2);
   L.flags = cv.take<int32_t>(n);
   L.proj = cv.take<float>((size_t)n * eh * ew);
-  L.sums = cv.take<float>((size_t)n * c);
+  L.sums = cv.take<float>((size_t)kPoolSplits * n * c);
   L.obj_feats = cv.take<float>((size_t)n * c);
   L.sim = cv.take<float>((size_t)n * n_cls);
   L.sim_part = cv.take<float>(sim_partial_floats(n, n_cls, c));
@@ -731,9 +743,11 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   if (!projection_supported(a->ew, a->lr_w) || !projection_supported(a->eh, a->lr_h)) return NTTT_EUNSUPPORTED;
   NTTT_STEP(launch_project_masks(px, py, L.bits_lr, L.box_lr, n, a->lr_h, a->lr_w, a->eh, a->ew, L.a_split, pad64(e),
                                  true, s));
-  NTTT_STEP(pool_contract(nullptr, a->tar_feat, n, e, a->c, L.sums, L.a_split, L.b_split, s));
+  int n_partials = 1;
+  NTTT_STEP(pool_contract(nullptr, a->tar_feat, n, e, a->c, L.sums, L.a_split, L.b_split, &n_partials, s));
   bool a_ready = false;
-  NTTT_STEP(normalize_rows(L.sums, L.area_lr, n, a->c, obj_feats, L.a_split, &a_ready, a->proto_neg != nullptr, s));
+  NTTT_STEP(normalize_rows(L.sums, n_partials, L.area_lr, n, a->c, obj_feats, L.a_split, &a_ready,
+                           a->proto_neg != nullptr, s));
   // a7/a8: similarity + top-1
   NTTT_STEP(sim_top1(obj_feats, a->proto, a->proto_neg, l_neg, a->sigma, n, a->c, a->n_cls, a->sim, L.sim_part,
                      L.sim_part_neg, L.top_score, L.top_label, L.a_split, L.b_split, a_ready, ctx->sm_count, s));

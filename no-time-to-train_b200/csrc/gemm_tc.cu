@@ -287,7 +287,7 @@ int launch_gemm_tc(const void* A, int lda, const void* B, int ldb, float* D, int
   if (splits_out) *splits_out = ceil_div(total_kb, kb_per);
   // wide outputs (the pooling GEMM, N = C) use 128 x 128 tiles: the kernel is bound by L2 -> shared-memory operand
   // traffic, which scales with 1/BM + 1/BN; narrow outputs (similarity, N = n_cls) keep 128 x 64 for more CTAs
-  if (N >= 512 && splits == 1)
+  if (N >= 512)
     return launch_tc<128, 5>(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(B), ldb, D,
                              ldd, M, N, K, splits, split_stride, s);
   return launch_tc<64, 6>(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(B), ldb, D, ldd,

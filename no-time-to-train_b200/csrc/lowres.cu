@@ -387,6 +387,9 @@ static int pack_mode() {
   return 0;
 #endif
 }
+// occupancy experiment knob (nttt_ctx_tune NTTT_TUNE_LOWRES_EXTRA_SMEM): extra dynamic shared memory per CTA of the
+// fast pack kernel, i.e. fewer resident CTAs per SM, leaving room for the other images' kernels
+int g_pack_extra_smem = 0;
 int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits,
                        int32_t* area, int32_t* box, int32_t* stab, int32_t* flags, const float* gate, float gate_min,
                        const float* const* mask_ptr, cudaStream_t s, float* stab_score) {
@@ -401,8 +404,9 @@ int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, floa
     lowres_pack_kernel<true><<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area, box,
                                                         stab, stab_score, flags, gate, gate_min, mask_ptr);
   } else if (pack_mode() <= 1) {
-    NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lowres_pack_fast_kernel<<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, bits, area, box, flags, gate, gate_min,
+    const size_t smem_fast = smem + (size_t)g_pack_extra_smem;
+    NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
+    lowres_pack_fast_kernel<<<n, kPackBlock, smem_fast, s>>>(src, (int)(p / 4), w / 32, bits, area, box, flags, gate, gate_min,
                                                         mask_ptr);
   } else {
     NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

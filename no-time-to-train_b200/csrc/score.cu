@@ -14,7 +14,7 @@ namespace nttt {
 // Sam2MatchingBaseline_noAMG.py:598-600): an empty mask divides 0 by 0 and its whole row is NaN, as in the reference.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-normalize_rows_kernel(const float* __restrict__ sums, const int32_t* __restrict__ area, int n, int c,
+normalize_rows_kernel(const float* __restrict__ sums, int n_partials, const int32_t* __restrict__ area, int n, int c,
                       float* __restrict__ out, bool nan_empty) {
   const int row = blockIdx.x * 8 + warp_id();
   if (row >= n) return;
@@ -22,12 +22,20 @@ normalize_rows_kernel(const float* __restrict__ sums, const int32_t* __restrict_
   float denom = 1.0f;
   if (area) { const int a = area[row]; denom = (a == 0 && !nan_empty) ? 1.0f : (float)a; }
   const float* src = sums + (size_t)row * c;
+  const size_t pstride = (size_t)n * c;  // split-K partials of the pooling GEMM, added in order
+  float* dst = out + (size_t)row * c;
   float ss = 0.0f;
-  for (int i = lane; i < c; i += 32) { const float v = __fdiv_rn(src[i], denom); ss = fmaf(v, v, ss); }
+  for (int i = lane; i < c; i += 32) {
+    float t = src[i];
+    for (int z = 1; z < n_partials; ++z) t += src[z * pstride + i];
+    const float v = __fdiv_rn(t, denom);
+    dst[i] = v;
+    ss = fmaf(v, v, ss);
+  }
   ss = warp_sum(ss);
   const float nrm = fmaxf(sqrtf(ss), 1e-12f);
-  float* dst = out + (size_t)row * c;
-  for (int i = lane; i < c; i += 32) dst[i] = __fdiv_rn(__fdiv_rn(src[i], denom), nrm);
+  __syncwarp();
+  for (int i = lane; i < c; i += 32) dst[i] = __fdiv_rn(dst[i], nrm);
 }
 
 // Vector path for encoder widths that are multiples of 128 (384, 768, 1024, 1536): one warp per row keeps the
@@ -35,7 +43,7 @@ normalize_rows_kernel(const float* __restrict__ sums, const int32_t* __restrict_
 // similarity GEMM so no separate conversion pass is needed.
 template <int kVec>  // float4 per lane, c = 128 * kVec
 __global__ void __launch_bounds__(256)
-normalize_split_kernel(const float* __restrict__ sums, const int32_t* __restrict__ area, int n, int cp,
+normalize_split_kernel(const float* __restrict__ sums, int n_partials, const int32_t* __restrict__ area, int n, int cp,
                        float* __restrict__ out, __nv_bfloat16* __restrict__ split, bool nan_empty) {
   constexpr int c = 128 * kVec;
   const int row = blockIdx.x * 8 + warp_id();
@@ -47,6 +55,14 @@ normalize_split_kernel(const float* __restrict__ sums, const int32_t* __restrict
   float4 v[kVec];
 #pragma unroll
   for (int i = 0; i < kVec; ++i) v[i] = src[i * 32 + lane];
+  for (int z = 1; z < n_partials; ++z) {  // split-K partials of the pooling GEMM, added in order
+    const float4* pz = src + z * ((size_t)n * c / 4);
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      const float4 t = pz[i * 32 + lane];
+      v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
+    }
+  }
   float ss = 0.0f;
 #pragma unroll
   for (int i = 0; i < kVec; ++i) {
@@ -86,17 +102,17 @@ normalize_split_kernel(const float* __restrict__ sums, const int32_t* __restrict
 }
 
 // returns 1 if the fused vector path ran (split written), 0 if the caller must use the generic kernels
-int launch_normalize_split(const float* sums, const int32_t* area, int n, int c, int cp, float* out, void* split,
-                           bool nan_empty, cudaStream_t s) {
+int launch_normalize_split(const float* sums, int n_partials, const int32_t* area, int n, int c, int cp, float* out,
+                           void* split, bool nan_empty, cudaStream_t s) {
   if (n <= 0) return 1;
   if (c % 128 != 0 || cp != c) return 0;
   const int grid = ceil_div(n, 8);
   __nv_bfloat16* sp = static_cast<__nv_bfloat16*>(split);
   switch (c / 128) {
-    case 3: normalize_split_kernel<3><<<grid, 256, 0, s>>>(sums, area, n, cp, out, sp, nan_empty); break;
-    case 6: normalize_split_kernel<6><<<grid, 256, 0, s>>>(sums, area, n, cp, out, sp, nan_empty); break;
-    case 8: normalize_split_kernel<8><<<grid, 256, 0, s>>>(sums, area, n, cp, out, sp, nan_empty); break;
-    case 12: normalize_split_kernel<12><<<grid, 256, 0, s>>>(sums, area, n, cp, out, sp, nan_empty); break;
+    case 3: normalize_split_kernel<3><<<grid, 256, 0, s>>>(sums, n_partials, area, n, cp, out, sp, nan_empty); break;
+    case 6: normalize_split_kernel<6><<<grid, 256, 0, s>>>(sums, n_partials, area, n, cp, out, sp, nan_empty); break;
+    case 8: normalize_split_kernel<8><<<grid, 256, 0, s>>>(sums, n_partials, area, n, cp, out, sp, nan_empty); break;
+    case 12: normalize_split_kernel<12><<<grid, 256, 0, s>>>(sums, n_partials, area, n, cp, out, sp, nan_empty); break;
     default: return 0;
   }
   ++g_launches;
@@ -104,10 +120,10 @@ int launch_normalize_split(const float* sums, const int32_t* area, int n, int c,
   return 1;
 }
 
-int launch_normalize_rows(const float* sums, const int32_t* area, int n, int c, float* out, bool nan_empty,
-                          cudaStream_t s) {
+int launch_normalize_rows(const float* sums, int n_partials, const int32_t* area, int n, int c, float* out,
+                          bool nan_empty, cudaStream_t s) {
   if (n <= 0) return NTTT_OK;
-  normalize_rows_kernel<<<ceil_div(n, 8), 256, 0, s>>>(sums, area, n, c, out, nan_empty);
+  normalize_rows_kernel<<<ceil_div(n, 8), 256, 0, s>>>(sums, n_partials, area, n, c, out, nan_empty);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }
