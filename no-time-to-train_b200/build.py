@@ -52,11 +52,13 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     ablate = os.environ.get("NTTT_BUILD_ABLATE", "0") not in ("", "0")
     flavour_file = os.path.join(OBJ, "flavour")
     flavour = "ablate" if ablate else "product"
+    extra = ["-DNTTT_ABLATE"] if ablate else []
+    extra += os.environ.get("NTTT_EXTRA_NVCC_FLAGS", "").split()  # A/B experiments (recorded in the flavour)
+    flavour += " " + " ".join(extra)
     if not os.path.exists(flavour_file) or open(flavour_file).read() != flavour:
         force = True
         with open(flavour_file, "w") as f:
             f.write(flavour)
-    extra = ["-DNTTT_ABLATE"] if ablate else []
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(PKG_DIR), "include", "nttt_b200.h"))
     headers.append(os.path.abspath(__file__))

@@ -28,6 +28,7 @@ def main() -> None:
     ap.add_argument("--streams", type=int, default=16)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--n-masks", type=int, default=1024)
+    ap.add_argument("--stops", default="", help="comma-separated stage numbers to measure (default: all, then 0 = whole)")
     args = ap.parse_args()
     pkg = importlib.import_module("no-time-to-train_b200")
     ops = importlib.import_module("no-time-to-train_b200.ops")
@@ -39,7 +40,10 @@ def main() -> None:
     resident = [(p.lr_masks.to(dev), p.pred_ious.to(dev), p.tar_feat.to(dev)) for p in pool]
     streams = [torch.cuda.Stream(dev) for _ in range(S)]
     prev = 0.0
-    for stop in list(range(1, len(STAGES) + 1)) + [0]:
+    stops = [int(x) for x in args.stops.split(",")] if args.stops else list(range(1, len(STAGES) + 1)) + [0]
+    if not pkg._lib.load().nttt_build_is_ablation():
+        raise SystemExit("tools/ablate.py needs the ablation build: NTTT_BUILD_ABLATE=1 python no-time-to-train_b200/build.py")
+    for stop in stops:
         os.environ["NTTT_STOP_AFTER"] = str(stop)
         ops._ctx_by_device.pop(dev.index, None)  # a fresh ctx reads the variable (the old one is leaked: tool only)
         stage = pkg.MatchingStage(dev, pkg.StageConfig(nms_thr=0.5, num_out_instance=100, enc_hw=(37, 37)))
