@@ -23,8 +23,11 @@ template <bool kReg>
 __global__ void __launch_bounds__(1024)
 nms_sort_kernel(const float* __restrict__ scores, const int32_t* __restrict__ box, const int32_t* __restrict__ labels,
                 int n, int n_pad, float min_score, int filter, int32_t* __restrict__ order,
-                float4* __restrict__ sorted_box, int32_t* __restrict__ sorted_label) {
+                float4* __restrict__ sorted_box, int32_t* __restrict__ sorted_label, uint32_t* __restrict__ nz,
+                int nz_total) {
   extern __shared__ unsigned long long s_keys[];
+  // (lists above 1024 boxes) clear the per-row summary of non-zero matrix words that nms_mask_kernel ORs into
+  for (int i = threadIdx.x; i < nz_total; i += blockDim.x) nz[i] = 0u;
   // filter: boxes whose score is not > min_score are not candidates at all (the reference drops them before the
   // stage, Sam2MatchingBaseline_noAMG.py:428-431): they sort last, get a unique negative label so that they never
   // match anything in the matrix, and the scan starts with them removed.
@@ -73,7 +76,7 @@ nms_sort_kernel(const float* __restrict__ scores, const int32_t* __restrict__ bo
 template <bool kByVictim>
 __global__ void __launch_bounds__(256)
 nms_mask_kernel(const float4* __restrict__ sorted_box, const int32_t* __restrict__ sorted_label, int n, float thr,
-                uint32_t* __restrict__ mask, int row_words) {
+                uint32_t* __restrict__ mask, int row_words, uint32_t* __restrict__ nz, int nz_words) {
   __shared__ float4 s_box[8][32];
   __shared__ int s_lab[8][32];
   const int i = blockIdx.y * 32 + threadIdx.x;  // sorted position of the row box
@@ -106,6 +109,8 @@ nms_mask_kernel(const float4* __restrict__ sorted_box, const int32_t* __restrict
   // by victim: word-major [cw][i] so that the scan's lanes (consecutive boxes) read consecutive addresses
   if (kByVictim) mask[(size_t)cw * (row_words * 32) + i] = bits;
   else mask[(size_t)i * row_words + cw] = bits;
+  // which words of row i hold suppressor bits at all (class-aware NMS: very few): lets the long-list scan touch only those
+  if (nz && bits) atomicOr(&nz[(size_t)i * nz_words + (cw >> 5)], 1u << (cw & 31));
 }
 
 // Greedy scan as a wavefront over 32-box chunks, one CTA of 32 warps, no CTA-wide barrier inside the scan.
@@ -117,7 +122,7 @@ nms_mask_kernel(const float4* __restrict__ sorted_box, const int32_t* __restrict
 //     unique greedy solution in (longest in-chunk chain + 1) ballots, usually 2-4 instead of a 32-step serial chain.
 // Then the warp publishes K[c] and sets the flag.  The critical path is one in-chunk resolve + one flag hand-off per
 // chunk.  All warps of the CTA are resident and a chunk only waits on lower chunks, so the spin-waits cannot deadlock.
-// Used for n <= 1024 (32 chunks = 32 warps, rows in registers); longer lists take the serial scan below.
+// Used for n <= 1024 (32 chunks = 32 warps, rows in registers); longer lists take nms_wave_sparse_kernel below.
 constexpr int kScanThreads = 1024;
 constexpr int kScanMaxN = 8192;
 
@@ -211,92 +216,107 @@ nms_wave_kernel(const uint32_t* __restrict__ mt, int row_words, const int32_t* _
   if (threadIdx.x == 0) { *n_keep = total_kept; *n_sel = s_pre[row_words]; }
 }
 
-// Serial greedy scan (lists longer than 1024 boxes; matrix stored by SUPPRESSOR, kByVictim = false) by one CTA of
-// 32 warps, 32 boxes (one chunk) per step:
-//   warp 0 resolves the in-chunk dependencies on the diagonal word and emits the survivors,
-//   then warp j ORs the suppression row of survivor j into the shared `removed` set (all rows in parallel).
-// The bit matrix is staged in shared memory when it fits (n <= ~1100), otherwise read from L2.
-
-template <bool kStaged>
-__global__ void __launch_bounds__(kScanThreads)
-nms_scan_kernel(const uint32_t* __restrict__ mask, int row_words, const int32_t* __restrict__ order,
-                const int32_t* __restrict__ sorted_label, const float* __restrict__ top_score, int n, int max_keep,
-                int32_t* __restrict__ keep,
-                int32_t* __restrict__ n_keep, int32_t* __restrict__ sel, int32_t* __restrict__ n_sel) {
-  extern __shared__ uint32_t s_dyn[];
-  __shared__ uint32_t s_removed[kScanMaxN / 32];
-  __shared__ uint32_t s_posbits[kScanMaxN / 32];  // bit i: top_score of sorted box i is > 0
-  __shared__ uint32_t s_keepbits;
-  __shared__ int s_stop;
+// The same wavefront for lists of up to kScanMaxN boxes (points_per_side 64: 4096 candidates).  A warp owns the chunks
+// c, c + 32, c + 64, ... and handles them in that order (a chunk only waits on lower chunks, which are either earlier
+// rounds or lower warps of the same round, all resident: no deadlock).  A row no longer fits in registers (128 words at
+// 4096 boxes), and almost all of it is zero, so the mask kernel leaves a per-row bitmap of its non-zero words (`nz`) and a
+// lane loads just those — the scan's work is proportional to the suppression pairs that exist, not to n^2 / 32.
+__global__ void __launch_bounds__(kScanThreads, 1)
+nms_wave_sparse_kernel(const uint32_t* __restrict__ mt, const uint32_t* __restrict__ nz, int nz_words, int row_words,
+                       const int32_t* __restrict__ order, const int32_t* __restrict__ sorted_label,
+                       const float* __restrict__ top_score, int n, int max_keep, int32_t* __restrict__ keep,
+                       int32_t* __restrict__ n_keep, int32_t* __restrict__ sel, int32_t* __restrict__ n_sel) {
+  __shared__ uint32_t s_K[kScanMaxN / 32];
+  __shared__ uint32_t s_S[kScanMaxN / 32];
+  __shared__ int s_pre[kScanMaxN / 32 + 1];
+  __shared__ volatile int s_ready[kScanMaxN / 32];
   const int lane = lane_id(), warp = warp_id();
-  const uint32_t* M = mask;
-  if (kStaged) {
-    const int total = n * row_words;
-    for (int i = threadIdx.x; i < total; i += kScanThreads) s_dyn[i] = mask[i];
-    M = s_dyn;
-  }
-  for (int base = 0; base < row_words * 32; base += kScanThreads) {  // per sorted box, one ballot per warp:
-    const int i = base + threadIdx.x;                               // positive-score flag, filtered-out flag
-    const bool pos = i < n && top_score[order[i]] > 0.0f;
-    const bool gone = i < n && sorted_label[i] < -1;
-    const uint32_t bits = __ballot_sync(kFull, pos);
-    const uint32_t gbits = __ballot_sync(kFull, gone);
-    if (lane == 0 && (i >> 5) < row_words) { s_posbits[i >> 5] = bits; s_removed[i >> 5] = gbits; }
-  }
-  if (threadIdx.x == 0) s_stop = 0;
+  for (int i = threadIdx.x; i < row_words; i += kScanThreads) s_ready[i] = 0;
   __syncthreads();
-  int kept = 0, selected = 0;  // tracked by warp 0
-  for (int c = 0; c < row_words; ++c) {
-    if (warp == 0) {
-      uint32_t cur = s_removed[c];
-      const int i = c * 32 + lane;
-      const uint32_t diag = i < n ? M[(size_t)i * row_words + c] : 0u;
-      const int n_here = min(32, n - c * 32);
-      uint32_t keepbits = 0;
-#pragma unroll
-      for (int b = 0; b < 32; ++b) {  // rows past n have diag == 0 and are masked out below
-        const uint32_t d = __shfl_sync(kFull, diag, b);
-        if (!((cur >> b) & 1u)) { keepbits |= 1u << b; cur |= d; }
-      }
-      if (n_here < 32) keepbits &= (1u << n_here) - 1u;
-      int cnt = __popc(keepbits);
-      if (kept + cnt > max_keep) {  // truncate to max_keep (= out_num)
-        int excess = kept + cnt - max_keep;
-        while (excess--) keepbits &= ~(1u << (31 - __clz(keepbits)));
-        cnt = max_keep - kept;
-      }
-      const bool mine = (keepbits >> lane) & 1u;
-      const uint32_t posbits = keepbits & s_posbits[c];
-      const bool pos = (posbits >> lane) & 1u;
-      if (mine) {
-        const int oi = order[i];
-        keep[kept + __popc(keepbits & ((1u << lane) - 1u))] = oi;
-        if (pos) sel[selected + __popc(posbits & ((1u << lane) - 1u))] = oi;
-      }
-      kept += cnt;
-      selected += __popc(posbits);
-      if (lane == 0) { s_keepbits = keepbits; s_stop = kept >= max_keep; }
-    }
-    __syncthreads();
-    const uint32_t kb = s_keepbits;
-    const int stop = s_stop;
-    if (stop) break;
-    if ((kb >> warp) & 1u) {
-      const uint32_t* row = M + (size_t)(c * 32 + warp) * row_words;
-      for (int w = c + 1 + lane; w < row_words; w += 32) {
-        const uint32_t v = row[w];
-        if (v) atomicOr(&s_removed[w], v);
+  const size_t stride = (size_t)row_words * 32;
+  for (int c = warp; c < row_words; c += kScanThreads / 32) {
+    const int j = c * 32 + lane;
+    const bool valid = j < n;
+    const bool gone = !valid || sorted_label[j] < -1;
+    const bool pos = valid && top_score[order[valid ? j : 0]] > 0.0f;
+    const uint32_t pbits = __ballot_sync(kFull, pos);
+    const uint32_t diag = valid ? __ldg(mt + (size_t)c * stride + j) : 0u;  // suppressors inside this chunk
+    uint32_t supp = 0;
+    if (valid) {
+      for (int q = 0; q < nz_words && q * 32 < c; ++q) {
+        uint32_t m = __ldg(nz + (size_t)j * nz_words + q);
+        if (q * 32 + 32 > c) m &= (1u << (c - q * 32)) - 1u;  // words of EARLIER chunks only
+        while (m) {
+          const int w = q * 32 + __ffs(m) - 1;
+          m &= m - 1;
+          const uint32_t r = __ldg(mt + (size_t)w * stride + j);
+          while (s_ready[w] == 0) {}
+          __threadfence_block();
+          supp |= r & s_K[w];
+        }
       }
     }
-    __syncthreads();
+    __syncwarp();
+    const bool cand = !gone && supp == 0;
+    uint32_t K = __ballot_sync(kFull, cand);
+    for (int it = 0; it < 33; ++it) {
+      const uint32_t K2 = __ballot_sync(kFull, cand && (diag & K) == 0);
+      if (K2 == K) break;
+      K = K2;
+    }
+    if (lane == 0) {
+      s_K[c] = K;
+      s_S[c] = pbits;
+      __threadfence_block();
+      s_ready[c] = 1;
+    }
   }
-  if (threadIdx.x == 0) { *n_keep = kept; *n_sel = selected; }
+  __syncthreads();
+  auto prefix = [&](const uint32_t* bits) {  // s_pre[w] = number of set bits in words < w (warp 0)
+    if (warp == 0) {
+      int run = 0;
+      for (int w0 = 0; w0 < row_words; w0 += 32) {
+        const int w = w0 + lane;
+        const int cnt = w < row_words ? __popc(bits[w]) : 0;
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(kFull, inc, o);
+          if (lane >= o) inc += up;
+        }
+        if (w < row_words) s_pre[w] = run + inc - cnt;
+        run += __shfl_sync(kFull, inc, 31);
+      }
+      if (lane == 0) s_pre[row_words] = run;
+    }
+    __syncthreads();
+  };
+  prefix(s_K);
+  for (int c = warp; c < row_words; c += kScanThreads / 32) {
+    const uint32_t kw = s_K[c];
+    const int rank = s_pre[c] + __popc(kw & ((1u << lane) - 1u));
+    const bool mine = ((kw >> lane) & 1u) && rank < max_keep;
+    if (mine) keep[rank] = order[c * 32 + lane];
+    const uint32_t mbits = __ballot_sync(kFull, mine);
+    __syncwarp();
+    if (lane == 0) { s_K[c] = mbits; s_S[c] &= mbits; }
+  }
+  const int total_kept = min(s_pre[row_words], max_keep);
+  __syncthreads();
+  prefix(s_S);
+  for (int c = warp; c < row_words; c += kScanThreads / 32) {
+    const uint32_t sw = s_S[c];
+    if ((sw >> lane) & 1u) sel[s_pre[c] + __popc(sw & ((1u << lane) - 1u))] = order[c * 32 + lane];
+  }
+  if (threadIdx.x == 0) { *n_keep = total_kept; *n_sel = s_pre[row_words]; }
 }
 
 size_t nms_workspace_bytes(int n) {
   const size_t row_words = (size_t)ceil_div(n, 32);
+  const size_t nz_words = (row_words + 31) / 32;
   return align_up(sizeof(int32_t) * (size_t)n, 256) + align_up(sizeof(uint32_t) * row_words * (row_words * 32), 256) +
-         align_up(sizeof(float4) * (size_t)n, 256) + align_up(sizeof(int32_t) * (size_t)n, 256);
+         align_up(sizeof(float4) * (size_t)n, 256) + align_up(sizeof(int32_t) * (size_t)n, 256) +
+         align_up(sizeof(uint32_t) * (size_t)n * nz_words, 256);
 }
 
 int launch_box_nms(const int32_t* box, const float* nms_scores, const int32_t* labels, const float* top_score, int n,
@@ -317,40 +337,35 @@ int launch_box_nms(const int32_t* box, const float* nms_scores, const int32_t* l
                                                  align_up(sizeof(uint32_t) * (size_t)row_words * (row_words * 32), 256));
   int32_t* sorted_label = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(sorted_box) +
                                                      align_up(sizeof(float4) * (size_t)n, 256));
+  const int nz_words = ceil_div(row_words, 32);
+  uint32_t* nz = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(sorted_label) + align_up(sizeof(int32_t) * (size_t)n, 256));
   int n_pad = 1;
   while (n_pad < n) n_pad <<= 1;
   if (n_pad <= 1024) {
     nms_sort_kernel<true><<<1, 1024, sizeof(unsigned long long) * 1024, s>>>(nms_scores, box, labels, n, 1024, min_score, filter, order,
-                                                                             sorted_box, sorted_label);
+                                                                             sorted_box, sorted_label, nullptr, 0);
   } else {
     const size_t smem = sizeof(unsigned long long) * (size_t)n_pad;
     if (smem > 48 * 1024)
       NTTT_CUDA(cudaFuncSetAttribute(nms_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nms_sort_kernel<false><<<1, 1024, smem, s>>>(nms_scores, box, labels, n, n_pad, min_score, filter, order, sorted_box,
-                                                 sorted_label);
+                                                 sorted_label, nz, n * nz_words);
   }
   NTTT_LAUNCH_CHECK();
   dim3 grid(ceil_div(row_words, 8), ceil_div(n, 32));
   if (n <= 1024) {
-    nms_mask_kernel<true><<<grid, dim3(32, 8), 0, s>>>(sorted_box, sorted_label, n, thr, mask, row_words);
+    nms_mask_kernel<true><<<grid, dim3(32, 8), 0, s>>>(sorted_box, sorted_label, n, thr, mask, row_words, nullptr, 0);
     NTTT_LAUNCH_CHECK();
     nms_wave_kernel<<<1, kScanThreads, 0, s>>>(mask, row_words, order, sorted_label, top_score, n, max_keep, keep, n_keep, sel,
                                                n_sel);
     NTTT_LAUNCH_CHECK();
     return NTTT_OK;
   }
-  nms_mask_kernel<false><<<grid, dim3(32, 8), 0, s>>>(sorted_box, sorted_label, n, thr, mask, row_words);
+  // longer lists: the same wavefront over the non-zero words of each row
+  nms_mask_kernel<true><<<grid, dim3(32, 8), 0, s>>>(sorted_box, sorted_label, n, thr, mask, row_words, nz, nz_words);
   NTTT_LAUNCH_CHECK();
-  const size_t stage_bytes = sizeof(uint32_t) * (size_t)n * row_words;
-  if (stage_bytes <= 160 * 1024) {
-    NTTT_CUDA(cudaFuncSetAttribute(nms_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)stage_bytes));
-    nms_scan_kernel<true><<<1, kScanThreads, stage_bytes, s>>>(mask, row_words, order, sorted_label, top_score, n, max_keep, keep,
-                                                              n_keep, sel, n_sel);
-  } else {
-    nms_scan_kernel<false><<<1, kScanThreads, 0, s>>>(mask, row_words, order, sorted_label, top_score, n, max_keep, keep, n_keep,
-                                                      sel, n_sel);
-  }
+  nms_wave_sparse_kernel<<<1, kScanThreads, 0, s>>>(mask, nz, nz_words, row_words, order, sorted_label, top_score, n, max_keep,
+                                                    keep, n_keep, sel, n_sel);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }

@@ -149,7 +149,7 @@ def test_proto_similarity_top1(ops, synth):
         assert abs(want[i, got_lab[i]] - want[i, wl[i]]) <= RTOL
 
 
-@pytest.mark.parametrize("n,n_cls", [(1, 1), (17, 2), (300, 4), (1000, 3), (4096, 80)])
+@pytest.mark.parametrize("n,n_cls", [(1, 1), (17, 2), (300, 4), (1000, 3), (4096, 80), (4096, 2), (2500, 1), (8192, 5)])
 def test_box_nms_matches_oracle_and_torchvision(ops, n, n_cls):
     from torchvision.ops import batched_nms
     gen = torch.Generator().manual_seed(n)
@@ -170,12 +170,23 @@ def test_box_nms_matches_oracle_and_torchvision(ops, n, n_cls):
     want = orc.box_nms(box.float().numpy(), scores.numpy(), labels.long().numpy(), 0.5)[:max_keep]
     assert np.array_equal(keep.cpu().numpy()[:nk], want)
     tv = batched_nms(box.float(), scores, labels.long(), 0.5)[:max_keep].numpy()
-    assert np.array_equal(want, tv)
+    if not np.array_equal(want, tv):
+        # torchvision sorts the scores with an UNSTABLE sort: among boxes with EQUAL scores its order is unspecified
+        # (ours and the oracle's: lower index first; torch.rand repeats values at these sizes).  Two tied boxes that do
+        # not suppress each other may swap places; of two tied boxes that do (the planted identical pair 2 / 3) either
+        # may be the survivor.  Nothing else may differ.
+        sc = scores.numpy()
+        assert len(want) == len(tv)
+        assert np.array_equal(sc[want], sc[tv]), "kept scores differ from torchvision beyond tie order"
+        for a, b in zip(want[want != tv].tolist(), tv[want != tv].tolist()):
+            assert sc[a] == sc[b]
+        only_ours, only_tv = set(want.tolist()) - set(tv.tolist()), set(tv.tolist()) - set(want.tolist())
+        assert only_ours | only_tv <= {2, 3}, (only_ours, only_tv)
     want_sel = want[top.numpy()[want] > 0]
     assert ns == len(want_sel) and np.array_equal(sel.cpu().numpy()[:ns], want_sel)
 
 
-@pytest.mark.parametrize("n,max_keep", [(1000, 800), (1024, 1024), (333, 50)])
+@pytest.mark.parametrize("n,max_keep", [(1000, 800), (1024, 1024), (333, 50), (4096, 800), (3000, 3000), (1025, 1025)])
 def test_box_nms_long_suppression_chain(ops, n, max_keep):
     """Worst case for the fixed-point scan: one class, boxes along a line, each overlapping only its neighbours with
     IoU > thr, so keep/suppress alternates along a dependency chain as long as the list (plus a random tail)."""

@@ -1,2 +1,1 @@
-ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,lts__t_bytes.sum,dram__bytes_read.sum,dram__bytes_write.sum,l1tex__t_bytes.sum,sm__warps_active.avg.pct_of_peak_sustained_active --cache-control none --clock-control none -k "regex:lowres|project|split|gemm|normalize|top1|nms|upsample|ios|decay|unpack" -s 24 -c 24 --csv --log-file gpurun_out/budget.csv python tools/profile_stage.py > gpurun_out/ncu1.log 2>&1
-echo done
+python -m pytest tests/test_gpu_parity.py -x -q -k "nms or full_size" 2>&1 | tail -4
