@@ -59,8 +59,12 @@ void nttt_ctx_destroy(nttt_ctx* ctx);
 /* Tunables of a context (defaults are the measured best on B200; results never depend on them):
  *   NTTT_TUNE_UPSAMPLE_STAGE_BYTES  shared-memory budget per CTA of the full-resolution resize for staging the logit
  *                                   tile under its row groups (0 = every tap is read from global memory; tiles that
- *                                   do not fit take that path anyway).  Default 36 KB. */
-enum { NTTT_TUNE_UPSAMPLE_STAGE_BYTES = 1, NTTT_TUNE_LOWRES_EXTRA_SMEM = 2 };
+ *                                   do not fit take that path anyway).  Default 36 KB.
+ *   NTTT_TUNE_LOWRES_EXTRA_SMEM     extra dynamic shared memory per CTA of the low-res pass (fewer resident CTAs per
+ *                                   SM; process-wide).  Default 0 — measured: leaving room for other kernels buys nothing.
+ *   NTTT_TUNE_GEMM_BN256_MIN_M      row count from which the pooling GEMM uses 128 x 256 tiles (process-wide).
+ *                                   Default 512 (measured: 32 fat CTAs beat 64 at 1024 rows, 97.9 vs 100.3 us/image). */
+enum { NTTT_TUNE_UPSAMPLE_STAGE_BYTES = 1, NTTT_TUNE_LOWRES_EXTRA_SMEM = 2, NTTT_TUNE_GEMM_BN256_MIN_M = 3 };
 int nttt_ctx_tune(nttt_ctx* ctx, int what, long long value);
 
 /* number of kernels this library has launched in this process (bench.py's `gpu_launches`) */

@@ -50,6 +50,7 @@ int launch_fill_scatter(const float*, const float*, const float*, const int32_t*
 int launch_fill_finalize(const float*, const float*, int, int, int, float*, float*, cudaStream_t);
 
 extern int g_pack_extra_smem;  // lowres.cu
+extern int g_gemm_bn256_min_m;  // gemm_tc.cu
 static thread_local char g_cuda_err[512] = "";
 unsigned long long g_launches = 0;
 
@@ -212,6 +213,10 @@ const char* nttt_profile_stage_name(int i) { return (i >= 0 && i < kNumStages) ?
 int nttt_ctx_tune(nttt_ctx* ctx, int what, long long value) {
   if (!ctx) return NTTT_EINVAL;
   switch (what) {
+    case NTTT_TUNE_GEMM_BN256_MIN_M:
+      if (value < 0) return NTTT_EINVAL;
+      nttt::g_gemm_bn256_min_m = (int)value;
+      return NTTT_OK;
     case NTTT_TUNE_LOWRES_EXTRA_SMEM:
       if (value < 0 || value > 128 * 1024) return NTTT_EINVAL;
       nttt::g_pack_extra_smem = (int)value;

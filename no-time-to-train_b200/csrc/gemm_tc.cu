@@ -274,6 +274,8 @@ static int launch_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, in
   return NTTT_OK;
 }
 
+int g_gemm_bn256_min_m = 512;  // nttt_ctx_tune(NTTT_TUNE_GEMM_BN256_MIN_M)
+
 // A [M, K] and B [N, K] bf16, K a multiple of 64, rows 16-byte aligned (lda, ldb multiples of 8)
 // splits > 1: split-K, partial tile z is written to D + z*split_stride (the caller sums the partials in a fixed
 // order); *splits_out receives the number of partials actually produced.
@@ -287,6 +289,12 @@ int launch_gemm_tc(const void* A, int lda, const void* B, int ldb, float* D, int
   if (splits_out) *splits_out = ceil_div(total_kb, kb_per);
   // wide outputs (the pooling GEMM, N = C) use 128 x 128 tiles: the kernel is bound by L2 -> shared-memory operand
   // traffic, which scales with 1/BM + 1/BN; narrow outputs (similarity, N = n_cls) keep 128 x 64 for more CTAs
+  // 128 x 256 tiles halve the CTA count and raise the flops per operand byte by a third.  With many images in flight
+  // the stage's throughput follows the SM-time a kernel consumes, not its latency: 32 CTAs x 38 us beat 64 CTAs x 25 us
+  // at 1024 rows (97.9 vs 100.3 us/image), and at 4096 rows one wave of 128 CTAs beats 1.7 waves of 256 (281 vs 292).
+  if (N >= 512 && N % 256 == 0 && M >= g_gemm_bn256_min_m)
+    return launch_tc<256, 4>(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(B), ldb, D,
+                             ldd, M, N, K, splits, split_stride, s);
   if (N >= 512)
     return launch_tc<128, 5>(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(B), ldb, D,
                              ldd, M, N, K, splits, split_stride, s);

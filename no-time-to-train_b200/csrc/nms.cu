@@ -94,7 +94,25 @@ nms_mask_kernel(const float4* __restrict__ sorted_box, const int32_t* __restrict
     const float4 a = sorted_box[i];
     const float area_a = __fmul_rn(a.z - a.x, a.w - a.y);
     const int la = sorted_label[i];
+    // Phase 1, branch-free: which of the 32 column boxes can suppress at all — same label, the right side of the
+    // diagonal, and a non-empty intersection (inter == 0 gives ovr == 0 or 0/0 = NaN, neither is > thr >= 0).  The
+    // lanes of a warp are 32 different rows, so a per-pair branch here made every warp walk the full IoU path.
+    uint32_t cand = 0;
+#pragma unroll 8
     for (int t = 0; t < 32; ++t) {
+      const float4 b = s_box[threadIdx.y][t];
+      const int j = cw * 32 + t;
+      const bool side = kByVictim ? (j < i) : (j > i && j < n);
+      const bool hit = side && s_lab[threadIdx.y][t] == la && fminf(a.z, b.z) > fmaxf(a.x, b.x) &&
+                       fminf(a.w, b.w) > fmaxf(a.y, b.y);
+      cand |= (uint32_t)hit << t;
+    }
+    // Phase 2: the exact fp32 IoU of torchvision's kernel on the few candidates
+    const bool thr_neg = thr < 0.0f;  // (a negative threshold is also exceeded by ovr == 0: take every pair)
+    if (thr_neg) cand = 0xffffffffu;
+    while (cand) {
+      const int t = __ffs(cand) - 1;
+      cand &= cand - 1;
       const int j = cw * 32 + t;
       if ((kByVictim ? j >= i : (j <= i || j >= n)) || s_lab[threadIdx.y][t] != la) continue;
       const float4 b = s_box[threadIdx.y][t];

@@ -149,6 +149,19 @@ def test_proto_similarity_top1(ops, synth):
         assert abs(want[i, got_lab[i]] - want[i, wl[i]]) <= RTOL
 
 
+def _assert_equal_up_to_score_ties(ours, tv, sc, planted=frozenset()):
+    """torchvision sorts the scores with an UNSTABLE sort: among boxes with EQUAL scores its order is unspecified
+    (ours and the oracle's: lower index first; torch.rand repeats values at these sizes).  Two tied boxes that do not
+    suppress each other may swap places; of two tied boxes that do (a planted identical pair) either may be the
+    survivor.  Nothing else may differ."""
+    if np.array_equal(ours, tv):
+        return
+    assert len(ours) == len(tv)
+    assert np.array_equal(sc[ours], sc[tv]), "kept scores differ from torchvision beyond tie order"
+    only_ours, only_tv = set(ours.tolist()) - set(tv.tolist()), set(tv.tolist()) - set(ours.tolist())
+    assert only_ours | only_tv <= set(planted), (only_ours, only_tv)
+
+
 @pytest.mark.parametrize("n,n_cls", [(1, 1), (17, 2), (300, 4), (1000, 3), (4096, 80), (4096, 2), (2500, 1), (8192, 5)])
 def test_box_nms_matches_oracle_and_torchvision(ops, n, n_cls):
     from torchvision.ops import batched_nms
@@ -170,18 +183,7 @@ def test_box_nms_matches_oracle_and_torchvision(ops, n, n_cls):
     want = orc.box_nms(box.float().numpy(), scores.numpy(), labels.long().numpy(), 0.5)[:max_keep]
     assert np.array_equal(keep.cpu().numpy()[:nk], want)
     tv = batched_nms(box.float(), scores, labels.long(), 0.5)[:max_keep].numpy()
-    if not np.array_equal(want, tv):
-        # torchvision sorts the scores with an UNSTABLE sort: among boxes with EQUAL scores its order is unspecified
-        # (ours and the oracle's: lower index first; torch.rand repeats values at these sizes).  Two tied boxes that do
-        # not suppress each other may swap places; of two tied boxes that do (the planted identical pair 2 / 3) either
-        # may be the survivor.  Nothing else may differ.
-        sc = scores.numpy()
-        assert len(want) == len(tv)
-        assert np.array_equal(sc[want], sc[tv]), "kept scores differ from torchvision beyond tie order"
-        for a, b in zip(want[want != tv].tolist(), tv[want != tv].tolist()):
-            assert sc[a] == sc[b]
-        only_ours, only_tv = set(want.tolist()) - set(tv.tolist()), set(tv.tolist()) - set(want.tolist())
-        assert only_ours | only_tv <= {2, 3}, (only_ours, only_tv)
+    _assert_equal_up_to_score_ties(want, tv, scores.numpy(), planted={2, 3})
     want_sel = want[top.numpy()[want] > 0]
     assert ns == len(want_sel) and np.array_equal(sel.cpu().numpy()[:ns], want_sel)
 
@@ -203,9 +205,11 @@ def test_box_nms_long_suppression_chain(ops, n, max_keep):
     top = torch.rand(n, generator=gen) - 0.3
     keep, sel, counts = ops.box_nms(box.to(DEV), scores.to(DEV), labels.to(DEV), top.to(DEV), 0.5, max_keep)
     nk, ns = counts.cpu().tolist()
-    want = batched_nms(box.float(), scores, labels.long(), 0.5)[:max_keep].numpy()
+    tv = batched_nms(box.float(), scores, labels.long(), 0.5)[:max_keep].numpy()
+    want = orc.box_nms(box.float().numpy(), scores.numpy(), labels.long().numpy(), 0.5)[:max_keep]
     assert want[:3].tolist() == [0, 2, 4]  # the chain alternates
     assert nk == len(want) and np.array_equal(keep.cpu().numpy()[:nk], want)
+    _assert_equal_up_to_score_ties(want, tv, scores.numpy())
     want_sel = want[top.numpy()[want] > 0]
     assert ns == len(want_sel) and np.array_equal(sel.cpu().numpy()[:ns], want_sel)
 
