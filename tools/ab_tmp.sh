@@ -1,3 +1,7 @@
-python -m pytest tests/test_gpu_parity.py -x -q -k "nms or full_size or pipeline" 2>&1 | tail -2
-for m in 2048 100000; do python bench.py --value-only --steps 6 --n-images 32 --n-masks 4096 --tune gemm_bn256_min_m=$m 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('config5 bn256_min_m', $m, 'us/img', round(d['us_per_image'],2))"; done
-for m in 1024 100000; do python bench.py --value-only --steps 8 --n-images 64 --tune gemm_bn256_min_m=$m 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('config2 bn256_min_m', $m, 'us/img', round(d['us_per_image'],2))"; done
+python bench.py --steps 6 --n-masks 4096 --n-images 64 --images-per-step 64 > gpurun_out/bench_config5.json 2> gpurun_out/bench_config5.err; tail -c 300 gpurun_out/bench_config5.err
+python bench.py --steps 10 --n-classes 1203 --n-images 64 --images-per-step 128 > gpurun_out/bench_config4.json 2> gpurun_out/bench_config4.err; tail -c 300 gpurun_out/bench_config4.err
+python -c "
+import json
+for f in ('gpurun_out/bench_config5.json','gpurun_out/bench_config4.json'):
+    d=json.load(open(f)); print(f, d['config']['workload'], round(d['value'],1), 'img/s', round(d['us_per_image'],1), 'us', 'e2e', round(d['e2e']['value'],1), 'fill ms', round(d['fill']['fill_ms'],2), 'roofline', round(d['roofline']['frac'],3))
+"
