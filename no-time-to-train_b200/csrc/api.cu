@@ -164,15 +164,20 @@ int nttt_ctx::axis(int in_size, int out_size, cudaStream_t s, nttt::AxisTable* o
       return NTTT_OK;
     }
   int slot = n_tables;
-  if (n_tables == kMaxTables) {
-    // evict the least recently used table that the current call has not taken; kernels of earlier calls
-    // (possibly on other streams) may still read it, so drain the device first.  Rare: sizes seldom change.
+  if (n_tables >= max_tables) {
+    // evict the least recently used table that the current call has not taken.  Kernels of earlier calls (possibly on
+    // other streams) may still read it, so it is only retired here; retired tables are freed kMaxRetired at a time
+    // behind ONE device synchronisation.
     slot = -1;
     for (int i = 0; i < n_tables; ++i)
       if (last_use[i] < epoch && (slot < 0 || last_use[i] < last_use[slot])) slot = i;
     if (slot < 0) return NTTT_EUNSUPPORTED;
-    NTTT_CUDA(cudaDeviceSynchronize());
-    free_axis_table(tables[slot]);
+    if (n_retired == kMaxRetired) {
+      NTTT_CUDA(cudaDeviceSynchronize());
+      for (int i = 0; i < n_retired; ++i) free_axis_table(retired[i]);
+      n_retired = 0;
+    }
+    retired[n_retired++] = tables[slot];
   }
   AxisTable t{};
   int err = build_axis_table(t, in_size, out_size, s);
@@ -213,6 +218,16 @@ const char* nttt_profile_stage_name(int i) { return (i >= 0 && i < kNumStages) ?
 int nttt_ctx_tune(nttt_ctx* ctx, int what, long long value) {
   if (!ctx) return NTTT_EINVAL;
   switch (what) {
+    case NTTT_TUNE_AXIS_CACHE_ENTRIES:
+      if (value < 8 || value > nttt_ctx::kMaxTables) return NTTT_EINVAL;
+      if (value < ctx->n_tables) {  // shrinking below what is held: drop the whole cache (behind a device sync)
+        NTTT_CUDA(cudaDeviceSynchronize());
+        for (int i = 0; i < ctx->n_tables; ++i) free_axis_table(ctx->tables[i]);
+        for (int i = 0; i < ctx->n_retired; ++i) free_axis_table(ctx->retired[i]);
+        ctx->n_tables = ctx->n_retired = 0;
+      }
+      ctx->max_tables = (int)value;
+      return NTTT_OK;
     case NTTT_TUNE_GEMM_BN256_MIN_M:
       if (value < 0) return NTTT_EINVAL;
       nttt::g_gemm_bn256_min_m = (int)value;
@@ -293,6 +308,7 @@ int nttt_ctx_create(nttt_ctx** out, int device) {
 void nttt_ctx_destroy(nttt_ctx* ctx) {
   if (!ctx) return;
   for (int i = 0; i < ctx->n_tables; ++i) free_axis_table(ctx->tables[i]);
+  for (int i = 0; i < ctx->n_retired; ++i) free_axis_table(ctx->retired[i]);
   if (ctx->scratch) cudaFree(ctx->scratch);
   for (int i = 0; i <= nttt_ctx::kMaxStages; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

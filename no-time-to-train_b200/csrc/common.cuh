@@ -93,6 +93,7 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
 // ---------------------------------------------------------------------------------------------------
 struct AxisTable {
   int in_size = 0, out_size = 0, taps = 0;
+  void* slab = nullptr;      // the one device allocation every array below points into
   int32_t* xmin = nullptr;   // [out]
   int32_t* xsize = nullptr;  // [out]
   float* w = nullptr;        // [out, taps]
@@ -130,10 +131,17 @@ void free_axis_table(AxisTable& t);
 struct nttt_ctx {
   int device = 0;
   int sm_count = 0;
-  // cache of antialias tables keyed by (in,out); least-recently-used entry of an EARLIER call is evicted
-  static constexpr int kMaxTables = 32;
+  // cache of antialias tables keyed by (in,out); least-recently-used entry of an EARLIER call is evicted.  An image
+  // takes two tables keyed by its height and its width (COCO / LVIS: a few hundred distinct values each), so the cache
+  // holds 1024 of them (~100 KB each); evicted tables are only RETIRED — kernels of earlier calls on other streams may
+  // still read them — and the retired ones are freed in batches behind one device synchronisation.
+  static constexpr int kMaxTables = 1024;
+  static constexpr int kMaxRetired = 64;
   nttt::AxisTable tables[kMaxTables];
   unsigned long long last_use[kMaxTables] = {};
+  nttt::AxisTable retired[kMaxRetired];
+  int n_retired = 0;
+  int max_tables = kMaxTables;  // nttt_ctx_tune(NTTT_TUNE_AXIS_CACHE_ENTRIES): smaller caches for tests
   unsigned long long epoch = 0;  // bumped once per API call that takes tables
   int n_tables = 0;
   // shared-memory budget of upsample_pack's logit tile, in floats (nttt_ctx_tune; 0 = read taps from global memory)

@@ -46,12 +46,28 @@ __device__ __forceinline__ void pk_mbar_wait(uint64_t* bar, uint32_t parity) {
   }
   __trap();
 }
-// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier
-__device__ __forceinline__ void pk_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier.  The logits are read exactly once per
+// image and are far larger than L2 (268 MB vs 126 MB): they are fetched with an evict-first L2 policy so that the
+// stream does not push the other kernels' working sets (packed masks, features, tables) out of the cache.
+__device__ __forceinline__ uint64_t pk_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void pk_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                             uint64_t policy) {
+#ifdef NTTT_PACK_NO_L2_HINT
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    pk_smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(pk_smem_u32(bar))
                : "memory");
+#else
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          pk_smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(pk_smem_u32(bar)), "l"(policy)
+      : "memory");
+#endif
 }
 
 // One CTA per mask.  A producer warp streams the 256 KB of logits through a 4-stage ring of 16 KB TMA bulk
@@ -103,12 +119,13 @@ lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mas
   if (warp == kPackThreads / 32) {
     // ===== producer warp =====
     if (lane == 0) {
+      const uint64_t l2_policy = pk_policy_evict_first();
       for (int st = 0; st < n_stages; ++st) {
         const int q = st % kPackStages;
         pk_mbar_wait(&s_empty[q], ((st / kPackStages) & 1) ^ 1);
         const int f4 = min(kPackStageF4, p4 - st * kPackStageF4);
         pk_mbar_expect_tx(&s_full[q], (uint32_t)f4 * 16u);
-        pk_bulk_load(s_stage + (size_t)q * kPackStageF4, src + (size_t)st * kPackStageF4, (uint32_t)f4 * 16u, &s_full[q]);
+        pk_bulk_load(s_stage + (size_t)q * kPackStageF4, src + (size_t)st * kPackStageF4, (uint32_t)f4 * 16u, &s_full[q], l2_policy);
       }
     }
   } else {
@@ -268,12 +285,13 @@ lowres_pack_fast_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 pe
   uint32_t unsafe = 0;
   if (warp == kPackThreads / 32) {
     if (lane == 0) {
+      const uint64_t l2_policy = pk_policy_evict_first();
       for (int st = 0; st < n_stages; ++st) {
         const int q = st % kPackStages;
         pk_mbar_wait(&s_empty[q], ((st / kPackStages) & 1) ^ 1);
         const int f4 = min(kPackStageF4, p4 - st * kPackStageF4);
         pk_mbar_expect_tx(&s_full[q], (uint32_t)f4 * 16u);
-        pk_bulk_load(s_stage + (size_t)q * kPackStageF4, src + (size_t)st * kPackStageF4, (uint32_t)f4 * 16u, &s_full[q]);
+        pk_bulk_load(s_stage + (size_t)q * kPackStageF4, src + (size_t)st * kPackStageF4, (uint32_t)f4 * 16u, &s_full[q], l2_policy);
       }
     }
   } else {
@@ -553,19 +571,36 @@ __global__ void aa_pack_kernel(int out_size, int out_pad, int taps, const int32_
   pk[i] = e;
 }
 
+// All arrays of a table live in ONE device allocation (`slab`): a table costs one cudaMalloc when a new (in, out) pair is
+// first seen and one cudaFree when it is retired, instead of ten of each.
 int build_axis_table(AxisTable& t, int in_size, int out_size, cudaStream_t s) {
   t.in_size = in_size;
   t.out_size = out_size;
   t.taps = aa_max_taps(in_size, out_size);
-  NTTT_CUDA(cudaMalloc(&t.xmin, sizeof(int32_t) * out_size));
-  NTTT_CUDA(cudaMalloc(&t.xsize, sizeof(int32_t) * out_size));
-  NTTT_CUDA(cudaMalloc(&t.w, sizeof(float) * (size_t)out_size * t.taps));
-  NTTT_CUDA(cudaMalloc(&t.t_lo, sizeof(int32_t) * in_size));
-  NTTT_CUDA(cudaMalloc(&t.t_len, sizeof(int32_t) * in_size));
-  NTTT_CUDA(cudaMalloc(&t.t_w, sizeof(float) * (size_t)in_size * kMaxScatter));
-  NTTT_CUDA(cudaMalloc(&t.t_cum, sizeof(float) * (size_t)in_size * (kMaxScatter + 1)));
-  NTTT_CUDA(cudaMalloc(&t.grp_of, sizeof(int32_t) * out_size));
-  NTTT_CUDA(cudaMalloc(&t.grp_start, sizeof(int32_t) * ((size_t)out_size + 1)));
+  const bool packed = t.taps <= 3 && in_size < 65536;
+  const int out_pad = (out_size + 31) / 32 * 32;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t o_xmin = take(sizeof(int32_t) * out_size), o_xsize = take(sizeof(int32_t) * out_size);
+  const size_t o_w = take(sizeof(float) * (size_t)out_size * t.taps);
+  const size_t o_tlo = take(sizeof(int32_t) * in_size), o_tlen = take(sizeof(int32_t) * in_size);
+  const size_t o_tw = take(sizeof(float) * (size_t)in_size * kMaxScatter);
+  const size_t o_tcum = take(sizeof(float) * (size_t)in_size * (kMaxScatter + 1));
+  const size_t o_gof = take(sizeof(int32_t) * out_size), o_gst = take(sizeof(int32_t) * ((size_t)out_size + 1));
+  const size_t o_pk = packed ? take(sizeof(float4) * (size_t)out_pad) : 0;
+  char* slab = nullptr;
+  NTTT_CUDA(cudaMalloc(&slab, off));
+  t.slab = slab;
+  t.xmin = reinterpret_cast<int32_t*>(slab + o_xmin);
+  t.xsize = reinterpret_cast<int32_t*>(slab + o_xsize);
+  t.w = reinterpret_cast<float*>(slab + o_w);
+  t.t_lo = reinterpret_cast<int32_t*>(slab + o_tlo);
+  t.t_len = reinterpret_cast<int32_t*>(slab + o_tlen);
+  t.t_w = reinterpret_cast<float*>(slab + o_tw);
+  t.t_cum = reinterpret_cast<float*>(slab + o_tcum);
+  t.grp_of = reinterpret_cast<int32_t*>(slab + o_gof);
+  t.grp_start = reinterpret_cast<int32_t*>(slab + o_gst);
+  t.pk = packed ? reinterpret_cast<float4*>(slab + o_pk) : nullptr;
   aa_table_kernel<<<ceil_div(out_size, 128), 128, 0, s>>>(in_size, out_size, t.taps, t.xmin, t.xsize, t.w);
   NTTT_LAUNCH_CHECK();
   aa_transpose_kernel<<<ceil_div(in_size, 128), 128, 0, s>>>(in_size, out_size, t.taps, t.xmin, t.xsize, t.w, t.t_lo,
@@ -573,9 +608,7 @@ int build_axis_table(AxisTable& t, int in_size, int out_size, cudaStream_t s) {
   NTTT_LAUNCH_CHECK();
   aa_group_kernel<<<1, 32, 0, s>>>(out_size, t.xmin, t.xsize, t.grp_of, t.grp_start);
   NTTT_LAUNCH_CHECK();
-  if (t.taps <= 3 && in_size < 65536) {
-    const int out_pad = (out_size + 31) / 32 * 32;
-    NTTT_CUDA(cudaMalloc(&t.pk, sizeof(float4) * (size_t)out_pad));
+  if (packed) {
     aa_pack_kernel<<<ceil_div(out_pad, 128), 128, 0, s>>>(out_size, out_pad, t.taps, t.xmin, t.xsize, t.w, t.pk);
     NTTT_LAUNCH_CHECK();
   }
@@ -583,9 +616,7 @@ int build_axis_table(AxisTable& t, int in_size, int out_size, cudaStream_t s) {
 }
 
 void free_axis_table(AxisTable& t) {
-  cudaFree(t.xmin); cudaFree(t.xsize); cudaFree(t.w); cudaFree(t.t_lo); cudaFree(t.t_len); cudaFree(t.t_w); cudaFree(t.t_cum);
-  cudaFree(t.grp_of); cudaFree(t.grp_start);
-  if (t.pk) cudaFree(t.pk);
+  if (t.slab) cudaFree(t.slab);
   t = AxisTable{};
 }
 

@@ -46,6 +46,11 @@ def context(device) -> int:
     return _ctx_by_device[idx]
 
 
+def tune(device, what: int, value: int) -> None:
+    """`nttt_ctx_tune` on the device's context (include/nttt_b200.h NTTT_TUNE_*)."""
+    _lib.check(_lib.load().nttt_ctx_tune(context(device), int(what), int(value)), "nttt_ctx_tune")
+
+
 def threshold_pack(logits: torch.Tensor, thr: float = 0.0, off: float = 1.0, out=None, want_stab: bool = True):
     """-> bits [n, h*w/32] int32 (bit pattern of uint32), area [n], box [n,4], stab [n,2], flags [n].
     `out` may carry the five preallocated outputs of an earlier call (no allocation inside a timed loop).

@@ -446,7 +446,9 @@ def test_model_boundary_modes(P, synth):
 
 
 def test_axis_table_cache_eviction(ops, synth):
-    """More distinct output sizes than the ctx's antialias-table cache holds: results stay bit-exact."""
+    """More distinct output sizes than the ctx's antialias-table cache holds (shrunk to 16 entries here; 84 tables are
+    needed, so tables are retired and, past 64 retired ones, freed in a batch): results stay bit-exact."""
+    ops.tune(DEV, 4, 16)  # NTTT_TUNE_AXIS_CACHE_ENTRIES
     gen = torch.Generator().manual_seed(99)
     logits = synth.make_masks(4, gen)
     d = logits.to(DEV)
@@ -459,3 +461,4 @@ def test_axis_table_cache_eviction(ops, synth):
         got = ops.unpack_masks(bits_full, rect, n_sel, hw).cpu().numpy()
         want = orc.aa_resize_threshold(logits.numpy(), hw).astype(bool)
         assert np.array_equal(got, want), hw
+    ops.tune(DEV, 4, 1024)
