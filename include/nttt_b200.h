@@ -334,6 +334,13 @@ typedef struct nttt_match_args {
   int32_t* rle_n_chars;
   int32_t rle_cap_counts;
   int32_t rle_cap_chars;
+  /* scheduling hint: 0 = throughput (many images in flight: every kernel is shaped for the least SM-time),
+   * 1 = low latency (one image at a time with a host synchronisation behind it, as the reference's bs=1 driver does,
+   * pl_wrapper/sam2matcher_pl.py:178-191: kernels are shaped for the shortest duration — the pooling GEMM runs
+   * split-K over twice the SMs).  The two modes add the fp32 partial sums of the pooling contraction in a different
+   * order: pooled features / similarities may differ in the last bit (far inside the 1e-3 bound); every integer
+   * result (masks, boxes, counts, keep lists) is computed identically. */
+  int32_t low_latency;
 } nttt_match_args;
 
 size_t nttt_match_workspace_bytes(int n, int lr_h, int lr_w, int eh, int ew, int c, int n_cls, int ori_h,

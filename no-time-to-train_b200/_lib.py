@@ -40,6 +40,7 @@ class MatchArgs(ctypes.Structure):
         ("logits_chunks_host", POINTER(c_void_p)), ("n_chunks", c_int32), ("chunk_prompts", c_int32),
         ("rle_counts", c_void_p), ("rle_n_counts", c_void_p), ("rle_chars", c_void_p), ("rle_n_chars", c_void_p),
         ("rle_cap_counts", c_int32), ("rle_cap_chars", c_int32),
+        ("low_latency", c_int32),
     ]
 
 

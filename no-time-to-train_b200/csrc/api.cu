@@ -16,7 +16,8 @@ int launch_multimask_select(const float*, int, int, int, const ChunkTable&, int,
 int launch_project_masks(const AxisTable&, const AxisTable&, const uint32_t*, const int32_t*, int, int, int, int, int,
                          void*, int, bool, cudaStream_t);
 int launch_normalize_split(const float*, int, const int32_t*, int, int, int, float*, void*, bool, cudaStream_t);
-int launch_gemm_tc(const void*, int, const void*, int, float*, int, int, int, int, int, size_t, int*, cudaStream_t);
+int launch_gemm_tc(const void*, int, const void*, int, float*, int, int, int, int, int, size_t, int*, cudaStream_t,
+                   bool low_latency = false);
 int gemm_tc_pick_splits(int, int, int, int);
 int launch_split_rows(const float*, int, int, int, int, int, void*, cudaStream_t);
 int launch_split_transpose(const float*, int, int, int, int, int, void*, cudaStream_t);
@@ -81,15 +82,20 @@ inline int pad64(int k) { return (k + 63) / 64 * 64; }
 // The 128 x 128 output tiles of a 1024 x 1024 pooling GEMM occupy 64 of the 148 SMs, each pulling its operands through
 // its own L2 port: split K in kPoolSplits so that twice as many SMs share the same traffic.  The partial sums go to
 // sums[z] (stride n*c floats) and are added in a fixed order by the normalisation kernel that reads them anyway.
+constexpr int kPoolSplitsMax = 2;  // workspace is sized for the low-latency mode
 constexpr int kPoolSplits = 1;  // measured: 2 halves the latency (25 -> 14 us) but costs throughput (100.7 -> 103.5 us/image with 16 images in flight: more SM-time in total)
+// low_latency (nttt_match_args.low_latency): one image at a time with a host synchronisation behind it — what counts
+// is the duration of each kernel, so the pooling GEMM spreads over twice the SMs (128 x 128 tiles, split-K 2: 14 us
+// instead of 25-38 us).
 static int pool_contract(const float* proj, const float* feat, int n, int e, int c, float* sums, void* a_split,
-                         void* b_split, int* n_partials, cudaStream_t s) {
+                         void* b_split, int* n_partials, cudaStream_t s, bool low_latency = false) {
   const int ep = pad64(e);
   int err = proj ? launch_split_rows(proj, e, n, e, ep, 0, a_split, s) : NTTT_OK;
   if (err) return err;
   err = launch_split_transpose(feat, c, c, e, ep, 1, b_split, s);
   if (err) return err;
-  return launch_gemm_tc(a_split, 3 * ep, b_split, 3 * ep, sums, c, n, c, 3 * ep, kPoolSplits, (size_t)n * c, n_partials, s);
+  return launch_gemm_tc(a_split, 3 * ep, b_split, 3 * ep, sums, c, n, c, 3 * ep, low_latency ? kPoolSplitsMax : kPoolSplits,
+                        (size_t)n * c, n_partials, s, low_latency);
 }
 
 // rows of `sums` -> /area -> L2-normalise -> obj_feats (+ split-bf16 copy when the vector path applies).
@@ -383,7 +389,7 @@ int nttt_project_masks(nttt_ctx* ctx, const uint32_t* bits, const int32_t* box, 
 
 size_t nttt_pool_workspace_bytes(int n, int e, int c) {
   const size_t ep = pad64(e);
-  return align_up(sizeof(float) * (size_t)kPoolSplits * n * c, 256) + align_up(2 * (size_t)n * 3 * ep, 256) +
+  return align_up(sizeof(float) * (size_t)kPoolSplitsMax * n * c, 256) + align_up(2 * (size_t)n * 3 * ep, 256) +
          align_up(2 * (size_t)c * 3 * ep, 256);
 }
 
@@ -396,7 +402,7 @@ int nttt_pool_normalize(nttt_ctx* ctx, const float* proj, const float* feat, con
   cudaStream_t s = (cudaStream_t)stream;
   char* ws = static_cast<char*>(workspace);
   float* sums = reinterpret_cast<float*>(ws);
-  char* a_split = ws + align_up(sizeof(float) * (size_t)kPoolSplits * n * c, 256);
+  char* a_split = ws + align_up(sizeof(float) * (size_t)kPoolSplitsMax * n * c, 256);
   char* b_split = a_split + align_up(2 * (size_t)n * 3 * pad64(e), 256);
   int n_partials = 1;
   int err = pool_contract(proj, feat, n, e, c, sums, a_split, b_split, &n_partials, s);
@@ -634,7 +640,7 @@ static MatchLayout carve(void* ws, int n, int lr_h, int lr_w, int eh, int ew, in
   L.stab = cv.take<int32_t>((size_t)n * 2);
   L.flags = cv.take<int32_t>(n);
   L.proj = cv.take<float>((size_t)n * eh * ew);
-  L.sums = cv.take<float>((size_t)kPoolSplits * n * c);
+  L.sums = cv.take<float>((size_t)kPoolSplitsMax * n * c);
   L.obj_feats = cv.take<float>((size_t)n * c);
   L.sim = cv.take<float>((size_t)n * n_cls);
   L.sim_part = cv.take<float>(sim_partial_floats(n, n_cls, c));
@@ -765,7 +771,8 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   NTTT_STEP(launch_project_masks(px, py, L.bits_lr, L.box_lr, n, a->lr_h, a->lr_w, a->eh, a->ew, L.a_split, pad64(e),
                                  true, s));
   int n_partials = 1;
-  NTTT_STEP(pool_contract(nullptr, a->tar_feat, n, e, a->c, L.sums, L.a_split, L.b_split, &n_partials, s));
+  NTTT_STEP(pool_contract(nullptr, a->tar_feat, n, e, a->c, L.sums, L.a_split, L.b_split, &n_partials, s,
+                          a->low_latency != 0));
   bool a_ready = false;
   NTTT_STEP(normalize_rows(L.sums, n_partials, L.area_lr, n, a->c, obj_feats, L.a_split, &a_ready,
                            a->proto_neg != nullptr, s));

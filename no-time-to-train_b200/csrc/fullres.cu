@@ -449,16 +449,38 @@ upsample_plan_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
                      const int32_t* __restrict__ n_sel, int max_sel, UpTables t, UpMeta* __restrict__ meta,
                      int32_t* __restrict__ rect, int32_t* __restrict__ scratch, const float* __restrict__ logits,
                      const float* const* __restrict__ mask_ptr, Up2Item* __restrict__ items, int32_t* __restrict__ ctr,
-                     int32_t* __restrict__ area_full, int32_t* __restrict__ box_full, int ow, int tile_cap_floats) {
+                     int32_t* __restrict__ area_full, int32_t* __restrict__ box_full, int oh, int ow, int tile_cap_floats,
+                     int stage_tables) {
+  extern __shared__ int32_t s_tab[];  // the span / group tables of both axes (stage_tables != 0)
   __shared__ int s_warp[33];
   __shared__ int s_off[1024];   // exclusive item offset of each mask of the strip
   __shared__ int s_ccs[1024];   // column chunks of each mask (0: no items)
+  __shared__ int4 s_geo[1024];  // {g0, g1, w0, w1} of each mask of the strip
+  __shared__ int2 s_rows[1024]; // {r0, r1}
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // Every table lookup below sits on a chain of dependent accesses (sel -> box -> spans -> groups -> spans ...).  The
+  // tables are a few tens of KB: copy them into shared memory once, coalesced, and chase them there.
+  const int32_t *y_tlo = t.y_tlo, *y_tlen = t.y_tlen, *x_tlo = t.x_tlo, *x_tlen = t.x_tlen, *ymin = t.ymin,
+                *ysize = t.ysize, *y_grp_of = t.y_grp_of, *y_grp_start = t.y_grp_start, *xmin = t.xmin, *xsize = t.xsize;
+  if (stage_tables) {
+    int32_t* p = s_tab;
+    auto stage = [&](const int32_t*& src, int count) {
+      for (int i = tid; i < count; i += 1024) p[i] = src[i];
+      src = p;
+      p += count;
+    };
+    stage(y_tlo, ih); stage(y_tlen, ih); stage(x_tlo, iw); stage(x_tlen, iw);
+    stage(ymin, oh); stage(ysize, oh); stage(y_grp_of, oh); stage(y_grp_start, oh + 1);
+    stage(xmin, ow); stage(xsize, ow);
+    __syncthreads();
+  }
   const int n = min(*n_sel, max_sel);
   int base = 0;
   for (int k0 = 0; k0 < max_sel; k0 += 1024) {
     const int k = k0 + tid;
     int n_items = 0, ccs = 0;
+    int4 geo = make_int4(0, 0, 0, 0);
+    int2 rows = make_int2(0, 0);
     if (k < max_sel) {
 #pragma unroll
       for (int q = 0; q < kScratchInts; ++q) scratch[(size_t)k * kScratchInts + q] = 0;
@@ -471,22 +493,24 @@ upsample_plan_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
       const int4 b = reinterpret_cast<const int4*>(box_lr)[m.src];
       const bool lr_empty = (b.x | b.y | b.z | b.w) == 0 && (bits_lr[(size_t)m.src * ih * (iw >> 5)] & 1u) == 0;
       if (!lr_empty) {
-        m.r0 = t.y_tlo[b.y];
-        m.r1 = t.y_tlo[b.w] + t.y_tlen[b.w];
-        const int c0 = t.x_tlo[b.x];
-        const int c1 = t.x_tlo[b.z] + t.x_tlen[b.z];
+        m.r0 = y_tlo[b.y];
+        m.r1 = y_tlo[b.w] + y_tlen[b.w];
+        const int c0 = x_tlo[b.x];
+        const int c1 = x_tlo[b.z] + x_tlen[b.z];
         m.w0 = c0 >> 5;
         m.w1 = (c1 + 31) >> 5;
         if (m.r1 > m.r0) {
-          m.lr0 = t.ymin[m.r0];
-          m.lr1 = t.ymin[m.r1 - 1] + t.ysize[m.r1 - 1];
-          m.g0 = t.y_grp_of[m.r0];
-          m.g1 = t.y_grp_of[m.r1 - 1] + 1;
+          m.lr0 = ymin[m.r0];
+          m.lr1 = ymin[m.r1 - 1] + ysize[m.r1 - 1];
+          m.g0 = y_grp_of[m.r0];
+          m.g1 = y_grp_of[m.r1 - 1] + 1;
         }
       }
       m.safe = flags_lr[m.src] & 1;
       meta[k] = m;
       reinterpret_cast<int4*>(rect)[k] = make_int4(m.r0, m.r1, m.w0, m.w1);
+      geo = make_int4(m.g0, m.g1, m.w0, m.w1);
+      rows = make_int2(m.r0, m.r1);
       if (m.r1 > m.r0 && m.w1 > m.w0) {
         ccs = (m.w1 - m.w0 + kUp2Cols - 1) / kUp2Cols;
         n_items = ((m.g1 - m.g0 + kUp2Groups - 1) / kUp2Groups) * ccs;
@@ -519,30 +543,31 @@ upsample_plan_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
     __syncthreads();
     s_off[tid] = s_warp[warp] + inc - n_items;
     s_ccs[tid] = ccs;
-    __syncthreads();  // (also publishes meta[] of this strip to the whole CTA: same-CTA global writes + barrier)
+    s_geo[tid] = geo;
+    s_rows[tid] = rows;
+    __syncthreads();
     const int strip_items = s_warp[32];
     for (int e = tid; e < strip_items; e += 1024) {
-      // last mask of the strip whose offset is <= e and that has items
+      // last mask of the strip whose offset is <= e: masks without items share the offset of their successor, so the
+      // LAST of equal offsets is the one that owns the item
       int lo = 0, hi = 1023;
       while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
         if (s_off[mid] <= e) lo = mid; else hi = mid - 1;
       }
-      // masks without items share the offset of their successor: the search lands on the LAST of equal offsets,
-      // which is the one that owns the item
-      const int km = k0 + lo;
-      const UpMeta m = meta[km];
+      const int4 g = s_geo[lo];
+      const int2 r = s_rows[lo];
       const int i = e - s_off[lo], cc_n = s_ccs[lo];
       const int rc = i / cc_n, cc = i - rc * cc_n;
-      const int gA = m.g0 + rc * kUp2Groups, gB = min(gA + kUp2Groups, m.g1);
-      const int wA = m.w0 + cc * kUp2Cols, wB = min(wA + kUp2Cols, m.w1);
-      const int ya = min(max(t.y_grp_start[gA], m.r0), m.r1), yb = min(max(t.y_grp_start[gB], m.r0), m.r1);
-      const int l0 = t.ymin[ya], l1 = t.ymin[yb - 1] + t.ysize[yb - 1];
+      const int gA = g.x + rc * kUp2Groups, gB = min(gA + kUp2Groups, g.y);
+      const int wA = g.z + cc * kUp2Cols, wB = min(wA + kUp2Cols, g.w);
+      const int ya = min(max(y_grp_start[gA], r.x), r.y), yb = min(max(y_grp_start[gB], r.x), r.y);
+      const int l0 = ymin[ya], l1 = ymin[yb - 1] + ysize[yb - 1];
       const int xa = min(wA << 5, ow - 1), xb = min((wB << 5) - 1, ow - 1);
-      const int tc0 = t.xmin[xa] & ~3;
-      const int tstride = min((t.xmin[xb] + t.xsize[xb] + 3) & ~3, iw) - tc0;
+      const int tc0 = xmin[xa] & ~3;
+      const int tstride = min((xmin[xb] + xsize[xb] + 3) & ~3, iw) - tc0;
       Up2Item it;
-      it.k = km;
+      it.k = k0 + lo;
       it.g = gA | ((gB - gA) << 16);
       it.w = wA | ((wB - wA) << 16);
       it.y = ya | ((yb - ya) << 16);
@@ -874,8 +899,14 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
     tile_floats = (tile_floats + 3) & ~3;
     const size_t smem = up2_fixed_smem(ih, iw) + (size_t)tile_floats * 4;
     if (smem > 200 * 1024) return NTTT_EUNSUPPORTED;
-    upsample_plan_kernel<<<1, 1024, 0, s>>>(bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, t, meta, rect, scratch,
-                                            logits, mask_ptr, items, ctr, area_full, box_full, ow, tile_floats);
+    size_t tab_bytes = sizeof(int32_t) * (size_t)(2 * ih + 2 * iw + 4 * oh + 1 + 2 * ow);
+    const int stage_tables = tab_bytes <= 96 * 1024;
+    if (!stage_tables) tab_bytes = 0;
+    if (tab_bytes > 0)  // (the kernel also holds 33 KB of static shared memory: opt in to more than 48 KB in total)
+      NTTT_CUDA(cudaFuncSetAttribute(upsample_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+    upsample_plan_kernel<<<1, 1024, tab_bytes, s>>>(bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, t, meta, rect,
+                                                    scratch, logits, mask_ptr, items, ctr, area_full, box_full, oh, ow,
+                                                    tile_floats, stage_tables);
     NTTT_LAUNCH_CHECK();
     if (smem > 48 * 1024)
       NTTT_CUDA(cudaFuncSetAttribute(upsample_pack2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -280,7 +280,7 @@ int g_gemm_bn256_min_m = 512;  // nttt_ctx_tune(NTTT_TUNE_GEMM_BN256_MIN_M)
 // splits > 1: split-K, partial tile z is written to D + z*split_stride (the caller sums the partials in a fixed
 // order); *splits_out receives the number of partials actually produced.
 int launch_gemm_tc(const void* A, int lda, const void* B, int ldb, float* D, int ldd, int M, int N, int K, int splits,
-                   size_t split_stride, int* splits_out, cudaStream_t s) {
+                   size_t split_stride, int* splits_out, cudaStream_t s, bool low_latency) {
   if (splits_out) *splits_out = 1;
   if (M <= 0 || N <= 0) return NTTT_OK;
   if (K <= 0 || K % kBK != 0 || lda % 8 != 0 || ldb % 8 != 0 || splits < 1) return NTTT_EINVAL;
@@ -292,7 +292,7 @@ int launch_gemm_tc(const void* A, int lda, const void* B, int ldb, float* D, int
   // 128 x 256 tiles halve the CTA count and raise the flops per operand byte by a third.  With many images in flight
   // the stage's throughput follows the SM-time a kernel consumes, not its latency: 32 CTAs x 38 us beat 64 CTAs x 25 us
   // at 1024 rows (97.9 vs 100.3 us/image), and at 4096 rows one wave of 128 CTAs beats 1.7 waves of 256 (281 vs 292).
-  if (N >= 512 && N % 256 == 0 && M >= g_gemm_bn256_min_m)
+  if (!low_latency && N >= 512 && N % 256 == 0 && M >= g_gemm_bn256_min_m)
     return launch_tc<256, 4>(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(B), ldb, D,
                              ldd, M, N, K, splits, split_stride, s);
   if (N >= 512)

@@ -128,7 +128,8 @@ class MatchingStage:
 
     def match_async(self, lr_masks: torch.Tensor, pred_ious: torch.Tensor, tar_feat: torch.Tensor, ori_hw,
                     taps: bool = False, slot=0, iou_thr=None, persistent_out=None, multi_ious=None,
-                    multi_first: int = 1, rle: bool = False, dense_masks: bool = True) -> PendingResult:
+                    multi_first: int = 1, rle: bool = False, dense_masks: bool = True,
+                    low_latency: bool = False) -> PendingResult:
         """Enqueue the whole stage for one image on the current stream.  `slot` selects which reusable
         workspace to use (callers that keep several images in flight on different streams use one slot per
         stream).  `iou_thr`, if given, fuses the reference's candidate filter (`scores_all > iou_thr`,
@@ -137,7 +138,9 @@ class MatchingStage:
         the decoder's raw output — one [n, m, 256, 256] tensor, or the LIST of per-batch tensors the decoder returned
         (each [testing_point_bs, m, 256, 256]; consumed in place, no `cat`) — and `pred_ious` is ignored (pass None).
         `rle=True` also emits the outputs as COCO compressed RLE (`PendingResult.rle_segmentations()`);
-        with `dense_masks=False` the bool masks are not produced at all (`binary_masks` is None)."""
+        with `dense_masks=False` the bool masks are not produced at all (`binary_masks` is None).
+        `low_latency=True` shapes the kernels for the shortest duration of ONE image (a caller that synchronises after
+        every image) instead of the least SM-time (many images in flight); float sums may differ in the last bit between the modes."""
         if self.proto is None:
             raise RuntimeError("Memory is not ready!")  # same text as Sam2MatchingBaseline_noAMG.py:752
         ops._need(tar_feat, torch.float32, "tar_feat")
@@ -219,6 +222,7 @@ class MatchingStage:
         a.l_neg, a.sigma = self.l_neg, float(self.cfg.neg_sigma)
         a.iou_thr, a.filter_iou = (float(iou_thr), 1) if iou_thr is not None else (0.0, 0)
         a.out_prev_rect = prev_rect.data_ptr() if prev_rect is not None else None
+        a.low_latency = 1 if low_latency else 0
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(self.lib.nttt_match_image(self.ctx, ctypes.byref(a), stream), "nttt_match_image")
         return PendingResult(self, masks.view(torch.bool) if masks is not None else None, boxes, scores, labels, index,
@@ -244,10 +248,12 @@ class MatchingStage:
         return {self.lib.nttt_profile_stage_name(i).decode(): float(buf[i]) for i in range(got)}
 
     def match(self, lr_masks, pred_ious, tar_feat, ori_hw, taps: bool = False, iou_thr=None, multi_ious=None,
-              multi_first: int = 1, rle: bool = False, dense_masks: bool = True, persistent_out=None) -> dict:
+              multi_first: int = 1, rle: bool = False, dense_masks: bool = True, persistent_out=None,
+              low_latency: bool = True) -> dict:
+        """One image, synchronously (the caller waits for the result): runs in low-latency mode by default."""
         pend = self.match_async(lr_masks, pred_ious, tar_feat, ori_hw, taps=taps, iou_thr=iou_thr,
                                 multi_ious=multi_ious, multi_first=multi_first, rle=rle, dense_masks=dense_masks,
-                                persistent_out=persistent_out)
+                                persistent_out=persistent_out, low_latency=low_latency)
         out = pend.get()
         if rle:
             out["segmentations"] = pend.rle_segmentations()

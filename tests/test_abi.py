@@ -55,7 +55,7 @@ def test_workspace_queries_are_pure_host(lib):
 
 def test_match_args_struct_layout(lib):
     """The ctypes mirror must have the size of the C struct as compiled."""
-    assert ctypes.sizeof(lib.MatchArgs) == lib.load().nttt_sizeof_match_args() == 264
+    assert ctypes.sizeof(lib.MatchArgs) == lib.load().nttt_sizeof_match_args() == 272
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

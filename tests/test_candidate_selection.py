@@ -106,7 +106,8 @@ def test_multimask_graph_replay_matches_eager(P, synth):
         g.tar_feat.copy_(feat.tar_feat)
         out = g.replay().get()
         lr, sc, _ = ref_torch.select_candidates([multi], [ious], 0.5)
-        eager = stage.match(lr.contiguous().to(DEV), sc.contiguous().to(DEV), feat.tar_feat.to(DEV), (480, 640))
+        eager = stage.match(lr.contiguous().to(DEV), sc.contiguous().to(DEV), feat.tar_feat.to(DEV), (480, 640),
+                            low_latency=False)  # same accumulation order as the captured (throughput-mode) graph
         assert out["counts"] == eager["counts"]
         assert torch.equal(torch.nan_to_num(out["scores"]), torch.nan_to_num(eager["scores"]))
         assert torch.equal(out["labels"], eager["labels"])

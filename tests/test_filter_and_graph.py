@@ -69,7 +69,8 @@ def test_graph_replay_matches_eager():
         g.pred_ious.copy_(cur.pred_ious)
         g.tar_feat.copy_(cur.tar_feat)
         out = g.replay().get()
-        eager = stage.match(cur.lr_masks.to(DEV), cur.pred_ious.to(DEV), cur.tar_feat.to(DEV), (1024, 1024), iou_thr=0.4)
+        eager = stage.match(cur.lr_masks.to(DEV), cur.pred_ious.to(DEV), cur.tar_feat.to(DEV), (1024, 1024), iou_thr=0.4,
+                            low_latency=False)  # same accumulation order as the captured (throughput-mode) graph
         assert out["counts"] == eager["counts"]
         assert torch.equal(torch.isnan(out["scores"]), torch.isnan(eager["scores"]))
         assert torch.equal(torch.nan_to_num(out["scores"]), torch.nan_to_num(eager["scores"]))
@@ -94,10 +95,27 @@ def test_persistent_outputs_are_exactly_the_dense_unpack():
         g.pred_ious.copy_(cur.pred_ious)
         g.tar_feat.copy_(cur.tar_feat)
         out = g.replay().get()
-        eager = stage.match(cur.lr_masks.to(DEV), cur.pred_ious.to(DEV), cur.tar_feat.to(DEV), (480, 640), iou_thr=0.4)
+        eager = stage.match(cur.lr_masks.to(DEV), cur.pred_ious.to(DEV), cur.tar_feat.to(DEV), (480, 640), iou_thr=0.4,
+                            low_latency=False)  # same accumulation order as the captured (throughput-mode) graph
         n_out = out["counts"]["n_out"]
         assert n_out == eager["counts"]["n_out"]
         full = g._out[0].view(torch.bool)
         assert torch.equal(full[:n_out], eager["binary_masks"])
         assert not bool(full[n_out:].any()), "stale pixels left in unused output slots"
     assert step == 3
+
+
+def test_low_latency_mode_changes_no_integer_result():
+    """`low_latency` only reshapes kernels (the pooling GEMM runs split-K): masks, boxes, labels and counts are
+    identical, float scores agree to the last few bits."""
+    P, inp = _case(n=128, c=384, n_cls=9, seed=91, ori_hw=(480, 640))
+    stage = P.MatchingStage(DEV, P.StageConfig(nms_thr=0.5, num_out_instance=20, enc_hw=(37, 37)))
+    stage.set_prototypes(inp.feats_ins_avg)
+    args = (inp.lr_masks.to(DEV), inp.pred_ious.to(DEV), inp.tar_feat.to(DEV), inp.ori_hw)
+    a = stage.match(*args, taps=True, low_latency=True)
+    b = stage.match(*args, taps=True, low_latency=False)
+    assert a["counts"] == b["counts"]
+    assert torch.equal(a["binary_masks"], b["binary_masks"]) and torch.equal(a["bboxes"], b["bboxes"])
+    assert torch.equal(a["labels"], b["labels"])
+    assert torch.allclose(a["taps"]["obj_feats"], b["taps"]["obj_feats"], rtol=0, atol=1e-6)
+    assert torch.allclose(torch.nan_to_num(a["scores"]), torch.nan_to_num(b["scores"]), rtol=1e-5, atol=1e-7)
