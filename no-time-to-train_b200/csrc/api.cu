@@ -31,7 +31,8 @@ int launch_box_nms(const int32_t*, const float*, const int32_t*, const float*, i
                    int32_t*, int32_t*, void*, size_t, float, int, cudaStream_t);
 int launch_upsample_pack(const AxisTable&, const AxisTable&, const float*, const uint32_t*, const int32_t*,
                          const int32_t*, int, int, const int32_t*, const int32_t*, int, int, int, uint32_t*, int32_t*,
-                         int32_t*, int32_t*, int32_t*, const float* const*, cudaStream_t, int, int);
+                         int32_t*, int32_t*, int32_t*, const float* const*, cudaStream_t, int, int, uint32_t* bits_t = nullptr,
+                         bool* wrote_t = nullptr);
 size_t upsample_scratch_bytes(int max_sel, int oh, int ow);
 int launch_unpack_sparse(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, uint8_t*,
                          int32_t*, cudaStream_t);
@@ -39,7 +40,8 @@ int launch_unpack(const uint32_t*, const int32_t*, const int32_t*, const int32_t
                   cudaStream_t);
 size_t ios_workspace_bytes(int max_sel);
 int launch_mask_ios(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
-                    int, int, int, const int32_t*, const float*, int, float*, int32_t*, void*, bool, cudaStream_t);
+                    int, int, int, const int32_t*, const float*, int, float*, int32_t*, void*, bool, cudaStream_t,
+                    const uint32_t* bits_t = nullptr);
 int launch_decay_rank(const float*, const int32_t*, const float*, const int32_t*, const int32_t*, int, int,
                       const int32_t*, const int32_t*, int64_t*, float*, int64_t*, int32_t*, int32_t*, int32_t*, float*,
                       cudaStream_t);
@@ -623,7 +625,7 @@ struct MatchLayout {
   float* proj; float* sums; float* obj_feats; float* sim; float* sim_part; float* sim_part_neg; float* top_score; int32_t* top_label;
   char* a_split; char* b_split;
   void* nms_ws; size_t nms_ws_bytes; int32_t* keep; int32_t* sel;
-  uint32_t* bits_full; int32_t* rect; int32_t* area_full; int32_t* box_full; int32_t* scratch;
+  uint32_t* bits_full; uint32_t* bits_t; int32_t* rect; int32_t* area_full; int32_t* box_full; int32_t* scratch;
   float* ios; void* ios_ws; int32_t* out_slot;
   const float** mask_ptr; float* plane_score;
   size_t total;
@@ -659,6 +661,7 @@ static MatchLayout carve(void* ws, int n, int lr_h, int lr_w, int eh, int ew, in
   L.keep = cv.take<int32_t>(max_sel > 0 ? max_sel : 1);
   L.sel = cv.take<int32_t>(max_sel > 0 ? max_sel : 1);
   L.bits_full = cv.take<uint32_t>((size_t)max_sel * oh * ((ow + 31) / 32));
+  L.bits_t = cv.take<uint32_t>((size_t)max_sel * oh * ((ow + 31) / 32));  // word-column-major copy for mask_ios
   L.rect = cv.take<int32_t>((size_t)max_sel * 4);
   L.area_full = cv.take<int32_t>(max_sel > 0 ? max_sel : 1);
   L.box_full = cv.take<int32_t>((size_t)max_sel * 4);
@@ -783,12 +786,15 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   NTTT_STEP(launch_box_nms(L.box_lr, pred_ious, L.top_label, L.top_score, n, a->nms_thr, max_sel, L.keep,
                            a->counts + 0, L.sel, a->counts + 1, L.nms_ws, L.nms_ws_bytes, a->iou_thr, a->filter_iou, s));
   // a12/a9
+  bool wrote_t = false;  // the resize also left the word-column-major copy of the packed masks (v2 path only)
   NTTT_STEP(launch_upsample_pack(ux, uy, a->logits, L.bits_lr, L.box_lr, L.flags, a->lr_h, a->lr_w, L.sel,
                                  a->counts + 1, max_sel, a->ori_h, a->ori_w, L.bits_full, L.rect, L.area_full,
-                                 L.box_full, L.scratch, mask_ptr, s, ctx->upsample_stage_floats, ctx->sm_count));
+                                 L.box_full, L.scratch, mask_ptr, s, ctx->upsample_stage_floats, ctx->sm_count, L.bits_t,
+                                 &wrote_t));
   // a13
   NTTT_STEP(launch_mask_ios(L.bits_full, L.rect, L.area_full, L.box_full, L.sel, a->counts + 1, max_sel, a->ori_h,
-                            a->ori_w, L.top_label, obj_feats, a->c, L.ios, nullptr, L.ios_ws, false, s));
+                            a->ori_w, L.top_label, obj_feats, a->c, L.ios, nullptr, L.ios_ws, false, s,
+                            wrote_t ? L.bits_t : nullptr));
   // a14
   NTTT_STEP(launch_decay_rank(L.top_score, L.top_label, L.ios, L.sel, a->counts + 1, max_sel, num_out, L.box_full,
                               L.area_full,

@@ -583,6 +583,11 @@ upsample_plan_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
   if (tid == 0) { ctr[0] = base; ctr[1] = 0; }
 }
 
+// 16-byte copy that allocates in L1: the pk_x / pk_y tables are a few KB shared by every item an SM processes
+__device__ __forceinline__ void cp_async16_ca(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -659,9 +664,9 @@ __device__ __forceinline__ void up2_evaluate(int warp, int lane, int n_list, con
 
 __global__ void __launch_bounds__(kUp2Threads, kUp2CtasPerSm)
 upsample_pack2_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restrict__ meta, int ih, int iw, int oh,
-                      int ow, UpTables t, uint32_t* __restrict__ bits_full, int32_t* __restrict__ area_full,
-                      int32_t* __restrict__ box_full, int32_t* __restrict__ scratch, const Up2Item* __restrict__ items,
-                      int32_t* __restrict__ ctr) {
+                      int ow, UpTables t, uint32_t* __restrict__ bits_full, uint32_t* __restrict__ bits_t,
+                      int32_t* __restrict__ area_full, int32_t* __restrict__ box_full, int32_t* __restrict__ scratch,
+                      const Up2Item* __restrict__ items, int32_t* __restrict__ ctr) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   float4* s_pkx = reinterpret_cast<float4*>(s_raw);                       // [kUp2Cols * 32]
   float4* s_pky = s_pkx + kUp2Cols * 32;                                  // [kUp2Rows + kGrpMax] (rows past the end are read)
@@ -708,9 +713,9 @@ upsample_pack2_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __rest
       const uint32_t* lr = bits_lr + ((size_t)mt.src * ih + clr0) * lr_wpr;
       const int n_lr = tr * lr_wpr;
       for (int i = tid; i < n_lr; i += kUp2Threads) cp_async4(s_lr + i, lr + i);
-      for (int i = tid; i < n_rows; i += kUp2Threads) cp_async16(s_pky + i, t.pk_y + ya0 + i);
+      for (int i = tid; i < n_rows; i += kUp2Threads) cp_async16_ca(s_pky + i, t.pk_y + ya0 + i);
       const float4* px = t.pk_x + (wA << 5);
-      for (int i = tid; i < (nw << 5); i += kUp2Threads) cp_async16(s_pkx + i, px + i);
+      for (int i = tid; i < (nw << 5); i += kUp2Threads) cp_async16_ca(s_pkx + i, px + i);
       if (tid <= ng) s_gstart[tid] = min(max(t.y_grp_start[gA + tid], mt.r0), mt.r1);
     }
     cp_async_wait_all();
@@ -812,6 +817,15 @@ upsample_pack2_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __rest
     else
       up2_evaluate<false>(warp, lane, n_list, s_list, s_grp, s_pkx, s_pky, s_out, src, tile_saddr, tap_stride, tap_c0);
     __syncthreads();
+    // ---- second copy, word-column major [k][word][row] (nullable): the overlap windows mask_ios walks are a few words
+    //      wide and hundreds of rows tall — 4 useful bytes per 32-byte sector in the row-major layout, contiguous here.
+    //      The result tile is column-major already: a warp writes 128 contiguous bytes per store.
+    if (bits_t) {
+      uint32_t* dt = bits_t + (size_t)k * oh * ow_words;
+      for (int c = warp; c < nw; c += kWarps)
+        for (int row = lane; row < n_rows; row += 32)
+          dt[(uint32_t)((wA + c) * oh + ya0 + row)] = s_out[c * kUp2OutStride + row + (row >> 5)];
+    }
     // ---- epilogue: result tile -> global in 32-byte row segments; area and box from the words
     {
       uint32_t* dst = bits_full + (size_t)k * oh * ow_words;
@@ -881,7 +895,8 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
                          const int32_t* box_lr, const int32_t* flags_lr, int ih, int iw, const int32_t* sel,
                          const int32_t* n_sel, int max_sel, int oh, int ow, uint32_t* bits_full, int32_t* rect,
                          int32_t* area_full, int32_t* box_full, int32_t* scratch, const float* const* mask_ptr,
-                         cudaStream_t s, int stage_floats, int sm_count) {
+                         cudaStream_t s, int stage_floats, int sm_count, uint32_t* bits_t, bool* wrote_t) {
+  if (wrote_t) *wrote_t = false;
   if (max_sel <= 0) return NTTT_OK;
   if (iw % 32 != 0) return NTTT_EUNSUPPORTED;
   UpTables t{tx.xmin, tx.xsize, tx.w, tx.taps, ty.xmin, ty.xsize, ty.w, ty.taps, tx.t_lo, tx.t_len, ty.t_lo, ty.t_len,
@@ -911,9 +926,10 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
     if (smem > 48 * 1024)
       NTTT_CUDA(cudaFuncSetAttribute(upsample_pack2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (sm_count > 0 ? sm_count : 148) * kUp2CtasPerSm;
-    upsample_pack2_kernel<<<grid, kUp2Threads, smem, s>>>(bits_lr, meta, ih, iw, oh, ow, t, bits_full, area_full, box_full,
-                                                          scratch, items, ctr);
+    upsample_pack2_kernel<<<grid, kUp2Threads, smem, s>>>(bits_lr, meta, ih, iw, oh, ow, t, bits_full, bits_t, area_full,
+                                                          box_full, scratch, items, ctr);
     NTTT_LAUNCH_CHECK();
+    if (wrote_t) *wrote_t = bits_t != nullptr;
     return NTTT_OK;
   }
   // bits (+ one spare word read and masked off by the footprint test), padded to 16 bytes, then the logit tile

@@ -6,6 +6,8 @@
 // The reference casts [K,H*W] bool to fp32 and runs one SGEMM per class; the counts it produces are exact
 // integers, so AND+popcount over the packed words gives the same numbers.  Only same-label pairs whose
 // full-res boxes overlap can intersect, and only inside the intersection of their rects.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace nttt {
@@ -98,8 +100,12 @@ ios_pairs_kernel(const IosMeta* __restrict__ meta, const int32_t* __restrict__ l
 // feature dot product, both reduced with shuffles — no shared memory, no CTA barrier.  (One CTA per pair spent most of
 // its instructions on per-thread set-up and the block reduction: a typical window is ~150 words.)  A window is walked
 // row-major with the lanes along the words when it is wide and along the rows when it is narrow.
+// bits_t (nullable): the word-column-major copy [k][word][row] written by upsample_pack2_kernel.  A window is a few words
+// wide and hundreds of rows tall: in the row-major layout every word sits in its own 32-byte sector (ncu: 80 MB through L1
+// for 10 MB of words); in the column-major copy a warp reads 128 contiguous bytes per word column.
 __global__ void __launch_bounds__(kIosThreads)
-ios_eval_kernel(const uint32_t* __restrict__ bits_full, const IosMeta* __restrict__ meta,
+ios_eval_kernel(const uint32_t* __restrict__ bits_full, const uint32_t* __restrict__ bits_t,
+                const IosMeta* __restrict__ meta,
                 const int2* __restrict__ pairs, const int32_t* __restrict__ n_pairs, int max_pairs, int max_sel, int oh,
                 int ow, const float* __restrict__ obj_feats, int c, float* __restrict__ ios,
                 int32_t* __restrict__ inter_out) {
@@ -120,7 +126,23 @@ ios_eval_kernel(const uint32_t* __restrict__ bits_full, const IosMeta* __restric
     const uint32_t* mi = bits_full + (size_t)i * mask_words;
     const uint32_t* pj = bits_full + (size_t)j * mask_words;
     int inter = 0;
-    if (nw > 0 && nr > 0) {
+    if (bits_t && nw > 0 && nr > 0) {
+      // column-major copy: lanes along the rows of one word column, four row chunks in flight
+      const uint32_t* ti = bits_t + (size_t)i * mask_words;
+      const uint32_t* tj = bits_t + (size_t)j * mask_words;
+      for (int w = wlo; w < whi; ++w) {
+        const uint32_t base = (uint32_t)w * (uint32_t)oh;
+        int y = ylo + lane;
+        for (; y + 96 < yhi; y += 128) {
+          const uint32_t a0 = __ldg(ti + base + y), b0 = __ldg(tj + base + y);
+          const uint32_t a1 = __ldg(ti + base + y + 32), b1 = __ldg(tj + base + y + 32);
+          const uint32_t a2 = __ldg(ti + base + y + 64), b2 = __ldg(tj + base + y + 64);
+          const uint32_t a3 = __ldg(ti + base + y + 96), b3 = __ldg(tj + base + y + 96);
+          inter += __popc(a0 & b0) + __popc(a1 & b1) + __popc(a2 & b2) + __popc(a3 & b3);
+        }
+        for (; y < yhi; y += 32) inter += __popc(__ldg(ti + base + y) & __ldg(tj + base + y));
+      }
+    } else if (nw > 0 && nr > 0) {
       // lanes tile the window: tx over words (next pow2 >= nw, <= 32), ty over rows
       int txn = 1;
       while (txn < nw && txn < 32) txn <<= 1;
@@ -258,7 +280,7 @@ ios_finalize_kernel(const int32_t* __restrict__ area_full, const int32_t* __rest
 int launch_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_t* area_full, const int32_t* box_full,
                     const int32_t* sel, const int32_t* n_sel, int max_sel, int oh, int ow, const int32_t* labels,
                     const float* obj_feats, int c, float* ios, int32_t* inter_out, void* ws, bool finalize,
-                    cudaStream_t s) {
+                    cudaStream_t s, const uint32_t* bits_t) {
   if (max_sel <= 0) return NTTT_OK;
   if (inter_out) NTTT_CUDA(cudaMemsetAsync(inter_out, 0, sizeof(int32_t) * (size_t)max_sel * max_sel, s));
   char* w8 = static_cast<char*>(ws);
@@ -267,14 +289,23 @@ int launch_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_
   int2* pairs = reinterpret_cast<int2*>(reinterpret_cast<char*>(label_sel) + align_up(sizeof(int32_t) * (size_t)max_sel, 256));
   const int max_pairs = (int)ios_max_pairs(max_sel);
   int32_t* n_pairs = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(pairs) + align_up(sizeof(int2) * (size_t)max_pairs, 256));
+#ifdef NTTT_ABLATE
+  // ablation builds: NTTT_IOS_STOP=<k> ends this stage after its k-th kernel (marginal cost of each of the four)
+  static const int ios_stop = [] { const char* e = getenv("NTTT_IOS_STOP"); return e ? atoi(e) : 0; }();
+#else
+  constexpr int ios_stop = 0;
+#endif
   ios_meta_kernel<<<ceil_div(max_sel, 256), 256, 0, s>>>(rect, area_full, box_full, sel, n_sel, max_sel, labels, meta,
                                                          label_sel, ios, n_pairs);
   NTTT_LAUNCH_CHECK();
+  if (ios_stop == 1) return NTTT_OK;
   ios_pairs_kernel<<<max_sel, 256, 0, s>>>(meta, label_sel, n_sel, max_sel, pairs, n_pairs, max_pairs);
   NTTT_LAUNCH_CHECK();
-  ios_eval_kernel<<<148 * 4, kIosThreads, 0, s>>>(bits_full, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats,
+  if (ios_stop == 2) return NTTT_OK;
+  ios_eval_kernel<<<148 * 4, kIosThreads, 0, s>>>(bits_full, bits_t, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats,
                                                   c, ios, inter_out);
   NTTT_LAUNCH_CHECK();
+  if (ios_stop == 3) return NTTT_OK;
   ios_eval_big_kernel<<<148, kIosThreads, 0, s>>>(bits_full, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats, c,
                                                   ios, inter_out);
   NTTT_LAUNCH_CHECK();
