@@ -32,12 +32,12 @@ int launch_box_nms(const int32_t*, const float*, const int32_t*, const float*, i
 int launch_upsample_pack(const AxisTable&, const AxisTable&, const float*, const uint32_t*, const int32_t*,
                          const int32_t*, int, int, const int32_t*, const int32_t*, int, int, int, uint32_t*, int32_t*,
                          int32_t*, int32_t*, int32_t*, const float* const*, cudaStream_t, int, int, uint32_t* bits_t = nullptr,
-                         bool* wrote_t = nullptr);
+                         bool* wrote_t = nullptr, bool t_only = false);
 size_t upsample_scratch_bytes(int max_sel, int oh, int ow);
 int launch_unpack_sparse(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, uint8_t*,
-                         int32_t*, cudaStream_t);
+                         int32_t*, cudaStream_t, bool tr = false);
 int launch_unpack(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, uint8_t*,
-                  cudaStream_t);
+                  cudaStream_t, bool tr = false);
 size_t ios_workspace_bytes(int max_sel);
 int launch_mask_ios(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
                     int, int, int, const int32_t*, const float*, int, float*, int32_t*, void*, bool, cudaStream_t,
@@ -46,7 +46,7 @@ int launch_decay_rank(const float*, const int32_t*, const float*, const int32_t*
                       const int32_t*, const int32_t*, int64_t*, float*, int64_t*, int32_t*, int32_t*, int32_t*, float*,
                       cudaStream_t);
 int launch_rle_encode(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, int, uint32_t*,
-                      int32_t*, uint8_t*, int32_t*, cudaStream_t);
+                      int32_t*, uint8_t*, int32_t*, cudaStream_t, bool tr = false);
 int launch_fill_pool(const float*, const float*, int, int, int, int, int, int, float*, float*, float*, int, cudaStream_t);
 int launch_fill_scatter(const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*, float*,
                         cudaStream_t);
@@ -790,7 +790,9 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   NTTT_STEP(launch_upsample_pack(ux, uy, a->logits, L.bits_lr, L.box_lr, L.flags, a->lr_h, a->lr_w, L.sel,
                                  a->counts + 1, max_sel, a->ori_h, a->ori_w, L.bits_full, L.rect, L.area_full,
                                  L.box_full, L.scratch, mask_ptr, s, ctx->upsample_stage_floats, ctx->sm_count, L.bits_t,
-                                 &wrote_t));
+                                 &wrote_t, /*t_only=*/true));
+  // the packed full-resolution masks from here on: word-column major when the v2 resize ran, row-major otherwise
+  const uint32_t* packed = wrote_t ? L.bits_t : L.bits_full;
   // a13
   NTTT_STEP(launch_mask_ios(L.bits_full, L.rect, L.area_full, L.box_full, L.sel, a->counts + 1, max_sel, a->ori_h,
                             a->ori_w, L.top_label, obj_feats, a->c, L.ios, nullptr, L.ios_ws, false, s,
@@ -803,16 +805,16 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   if (!a->out_masks)
     NTTT_MARK();  // RLE-only output: the dense bool masks are never produced
   else if (a->out_prev_rect)
-    NTTT_STEP(launch_unpack_sparse(L.bits_full, L.rect, L.out_slot, a->counts + 2, num_out, a->ori_h, a->ori_w,
-                                   a->out_masks, a->out_prev_rect, s));
+    NTTT_STEP(launch_unpack_sparse(packed, L.rect, L.out_slot, a->counts + 2, num_out, a->ori_h, a->ori_w,
+                                   a->out_masks, a->out_prev_rect, s, wrote_t));
   else
-    NTTT_STEP(launch_unpack(L.bits_full, L.rect, L.out_slot, a->counts + 2, num_out, a->ori_h, a->ori_w, a->out_masks,
-                            s));
+    NTTT_STEP(launch_unpack(packed, L.rect, L.out_slot, a->counts + 2, num_out, a->ori_h, a->ori_w, a->out_masks,
+                            s, wrote_t));
   // §8f rank 1: COCO RLE of the outputs straight from the packed words
   if (want_rle)
-    NTTT_STEP(launch_rle_encode(L.bits_full, L.rect, L.out_slot, a->counts + 2, num_out, a->ori_h, a->ori_w,
+    NTTT_STEP(launch_rle_encode(packed, L.rect, L.out_slot, a->counts + 2, num_out, a->ori_h, a->ori_w,
                                 a->rle_cap_counts, a->rle_cap_chars, a->rle_counts, a->rle_n_counts, a->rle_chars,
-                                a->rle_n_chars, s));
+                                a->rle_n_chars, s, wrote_t));
   else
     NTTT_MARK();
 #undef NTTT_STEP

@@ -828,14 +828,14 @@ upsample_pack2_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __rest
     }
     // ---- epilogue: result tile -> global in 32-byte row segments; area and box from the words
     {
-      uint32_t* dst = bits_full + (size_t)k * oh * ow_words;
+      uint32_t* dst = bits_full ? bits_full + (size_t)k * oh * ow_words : nullptr;  // (row-major copy: optional)
       const int c = tid & (kUp2Cols - 1);
       int area = 0, miny = kBig, maxy = -1;
       uint32_t colbits = 0;
       if (c < nw) {
         for (int row = tid >> 3; row < n_rows; row += kUp2Threads / kUp2Cols) {
           const uint32_t w = s_out[c * kUp2OutStride + row + (row >> 5)];
-          dst[(uint32_t)((ya0 + row) * ow_words + wA + c)] = w;
+          if (dst) dst[(uint32_t)((ya0 + row) * ow_words + wA + c)] = w;
           area += __popc(w);
           colbits |= w;
           if (w) { miny = min(miny, ya0 + row); maxy = max(maxy, ya0 + row); }
@@ -895,7 +895,9 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
                          const int32_t* box_lr, const int32_t* flags_lr, int ih, int iw, const int32_t* sel,
                          const int32_t* n_sel, int max_sel, int oh, int ow, uint32_t* bits_full, int32_t* rect,
                          int32_t* area_full, int32_t* box_full, int32_t* scratch, const float* const* mask_ptr,
-                         cudaStream_t s, int stage_floats, int sm_count, uint32_t* bits_t, bool* wrote_t) {
+                         cudaStream_t s, int stage_floats, int sm_count, uint32_t* bits_t, bool* wrote_t, bool t_only) {
+  // bits_t (nullable): also write the word-column-major copy [k][word][row]; t_only: and skip the row-major one
+  // (every consumer of the fused pipeline reads the transposed layout).  *wrote_t tells whether the v2 path ran.
   if (wrote_t) *wrote_t = false;
   if (max_sel <= 0) return NTTT_OK;
   if (iw % 32 != 0) return NTTT_EUNSUPPORTED;
@@ -926,7 +928,8 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
     if (smem > 48 * 1024)
       NTTT_CUDA(cudaFuncSetAttribute(upsample_pack2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (sm_count > 0 ? sm_count : 148) * kUp2CtasPerSm;
-    upsample_pack2_kernel<<<grid, kUp2Threads, smem, s>>>(bits_lr, meta, ih, iw, oh, ow, t, bits_full, bits_t, area_full,
+    upsample_pack2_kernel<<<grid, kUp2Threads, smem, s>>>(bits_lr, meta, ih, iw, oh, ow, t,
+                                                          (bits_t && t_only) ? nullptr : bits_full, bits_t, area_full,
                                                           box_full, scratch, items, ctr);
     NTTT_LAUNCH_CHECK();
     if (wrote_t) *wrote_t = bits_t != nullptr;
@@ -967,7 +970,7 @@ constexpr int kUnpackUnroll = 4;  // words per thread in flight
 __global__ void __launch_bounds__(256)
 unpack_masks_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restrict__ rect,
                     const int32_t* __restrict__ index, const int32_t* __restrict__ count, int max_count, int oh, int ow,
-                    uint8_t* __restrict__ out) {
+                    uint8_t* __restrict__ out, bool tr /* packed words are [word][row] instead of [row][word] */) {
   const int j = blockIdx.y;
   if (j >= min(*count, max_count)) return;
   const int k = index ? index[j] : j;
@@ -990,7 +993,7 @@ unpack_masks_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __res
       ww[u] = it - ry * ow_words;
       word[u] = 0;
       if (it < total && yy[u] >= rc.x && yy[u] < rc.y && ww[u] >= rc.z && ww[u] < rc.w)
-        word[u] = __ldg(src + (size_t)yy[u] * ow_words + ww[u]);
+        word[u] = __ldg(tr ? src + (size_t)ww[u] * oh + yy[u] : src + (size_t)yy[u] * ow_words + ww[u]);
     }
 #pragma unroll
     for (int u = 0; u < kUnpackUnroll; ++u) {
@@ -1021,7 +1024,7 @@ unpack_masks_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __res
 __global__ void __launch_bounds__(256)
 unpack_sparse_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restrict__ rect,
                      const int32_t* __restrict__ index, const int32_t* __restrict__ count, int max_count, int oh, int ow,
-                     uint8_t* __restrict__ out, int32_t* __restrict__ prev_rect) {
+                     uint8_t* __restrict__ out, int32_t* __restrict__ prev_rect, bool tr) {
   const int j = blockIdx.y;
   const int ow_words = (ow + 31) >> 5;
   const bool live = j < min(*count, max_count);
@@ -1033,6 +1036,7 @@ unpack_sparse_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __re
   if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<int4*>(prev_rect)[j] = has_new ? nr : make_int4(0, 0, 0, 0);
   if (!has_new && !has_old) return;
   const int old_w = has_old ? pr.w - pr.z : 0, new_w = has_new ? nr.w - nr.z : 0;
+  const int old_h = has_old ? pr.y - pr.x : 0, new_h = has_new ? nr.y - nr.x : 0;
   const int n_old = has_old ? (pr.y - pr.x) * old_w : 0;
   const int total = n_old + (has_new ? (nr.y - nr.x) * new_w : 0);
   const uint32_t* src = bits_full + (size_t)k * oh * ow_words;
@@ -1041,16 +1045,17 @@ unpack_sparse_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __re
   for (int it = blockIdx.x * 256 + threadIdx.x; it < total; it += gridDim.x * 256) {
     int y, wi;
     uint32_t w = 0;
+    // (transposed source: consecutive threads take consecutive ROWS of one word column, so the reads are contiguous;
+    //  a thread writes a whole 32-byte sector either way)
     if (it < n_old) {  // clearing pass: old words the new rect will not rewrite
-      const int ry = it / old_w;
-      y = pr.x + ry;
-      wi = pr.z + (it - ry * old_w);
+      if (tr) { const int cw = it / old_h; wi = pr.z + cw; y = pr.x + (it - cw * old_h); }
+      else    { const int ry = it / old_w; y = pr.x + ry; wi = pr.z + (it - ry * old_w); }
       if (has_new && y >= nr.x && y < nr.y && wi >= nr.z && wi < nr.w) continue;
     } else {           // writing pass
-      const int q = it - n_old, ry = q / new_w;
-      y = nr.x + ry;
-      wi = nr.z + (q - ry * new_w);
-      w = __ldg(src + (size_t)y * ow_words + wi);
+      const int q = it - n_old;
+      if (tr) { const int cw = q / new_h; wi = nr.z + cw; y = nr.x + (q - cw * new_h); }
+      else    { const int ry = q / new_w; y = nr.x + ry; wi = nr.z + (q - ry * new_w); }
+      w = __ldg(tr ? src + (size_t)wi * oh + y : src + (size_t)y * ow_words + wi);
     }
     const int x = wi << 5;
     uint8_t* p = dst + (size_t)y * ow + x;
@@ -1067,19 +1072,19 @@ unpack_sparse_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __re
 }
 
 int launch_unpack_sparse(const uint32_t* bits_full, const int32_t* rect, const int32_t* index, const int32_t* count,
-                         int max_count, int oh, int ow, uint8_t* out, int32_t* prev_rect, cudaStream_t s) {
+                         int max_count, int oh, int ow, uint8_t* out, int32_t* prev_rect, cudaStream_t s, bool tr) {
   if (max_count <= 0) return NTTT_OK;
   dim3 grid(1, max_count);  // one CTA per slot: prev_rect[j] is read and rewritten by the same CTA
-  unpack_sparse_kernel<<<grid, 256, 0, s>>>(bits_full, rect, index, count, max_count, oh, ow, out, prev_rect);
+  unpack_sparse_kernel<<<grid, 256, 0, s>>>(bits_full, rect, index, count, max_count, oh, ow, out, prev_rect, tr);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }
 
 int launch_unpack(const uint32_t* bits_full, const int32_t* rect, const int32_t* index, const int32_t* count,
-                  int max_count, int oh, int ow, uint8_t* out, cudaStream_t s) {
+                  int max_count, int oh, int ow, uint8_t* out, cudaStream_t s, bool tr) {
   if (max_count <= 0) return NTTT_OK;
   dim3 grid(ceil_div(oh, kUnpackRows), max_count);
-  unpack_masks_kernel<<<grid, 256, 0, s>>>(bits_full, rect, index, count, max_count, oh, ow, out);
+  unpack_masks_kernel<<<grid, 256, 0, s>>>(bits_full, rect, index, count, max_count, oh, ow, out, tr);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }

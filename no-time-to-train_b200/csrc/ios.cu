@@ -196,7 +196,8 @@ ios_eval_kernel(const uint32_t* __restrict__ bits_full, const uint32_t* __restri
 // grows from the back of the pair buffer): the window is spread over all threads with four load pairs in flight,
 // one block reduction.  A single warp would take tens of microseconds on a 1000 x 32-word window.
 __global__ void __launch_bounds__(kIosThreads)
-ios_eval_big_kernel(const uint32_t* __restrict__ bits_full, const IosMeta* __restrict__ meta,
+ios_eval_big_kernel(const uint32_t* __restrict__ bits_full, const uint32_t* __restrict__ bits_t,
+                const IosMeta* __restrict__ meta,
                 const int2* __restrict__ pairs, const int32_t* __restrict__ n_pairs, int max_pairs, int max_sel, int oh,
                 int ow, const float* __restrict__ obj_feats, int c, float* __restrict__ ios,
                 int32_t* __restrict__ inter_out) {
@@ -215,8 +216,10 @@ ios_eval_big_kernel(const uint32_t* __restrict__ bits_full, const IosMeta* __res
     const int wlo = max(max(me.rect.z, mj.rect.z), x0 >> 5), whi = min(min(me.rect.w, mj.rect.w), (x1 >> 5) + 1);
     const int ylo = max(max(me.rect.x, mj.rect.x), y0), yhi = min(min(me.rect.y, mj.rect.y), y1 + 1);
     const int nw = whi - wlo;
-    const uint32_t* mi = bits_full + (size_t)i * oh * ow_words;
-    const uint32_t* pj = bits_full + (size_t)j * oh * ow_words;
+    const bool tr = bits_t != nullptr;  // word-column-major copy: word (y, w) at w * oh + y
+    const uint32_t* mi = (tr ? bits_t : bits_full) + (size_t)i * oh * ow_words;
+    const uint32_t* pj = (tr ? bits_t : bits_full) + (size_t)j * oh * ow_words;
+    const size_t sy = tr ? 1 : (size_t)ow_words, sw = tr ? (size_t)oh : 1;
     int inter = 0;
     if (nw > 0 && yhi > ylo) {
       // threads tile the window: tx over words (next pow2 >= nw, <= 32), ty over rows
@@ -226,14 +229,14 @@ ios_eval_big_kernel(const uint32_t* __restrict__ bits_full, const IosMeta* __res
       for (int w = wlo + tx; w < whi; w += txn) {
         int y = ylo + ty;
         for (; y + 3 * tyn < yhi; y += 4 * tyn) {
-          const size_t o0 = (size_t)y * ow_words + w, o1 = o0 + (size_t)tyn * ow_words;
-          const size_t o2 = o1 + (size_t)tyn * ow_words, o3 = o2 + (size_t)tyn * ow_words;
+          const size_t o0 = (size_t)y * sy + (size_t)w * sw, o1 = o0 + (size_t)tyn * sy;
+          const size_t o2 = o1 + (size_t)tyn * sy, o3 = o2 + (size_t)tyn * sy;
           const uint32_t a0 = __ldg(mi + o0), b0 = __ldg(pj + o0), a1 = __ldg(mi + o1), b1 = __ldg(pj + o1);
           const uint32_t a2 = __ldg(mi + o2), b2 = __ldg(pj + o2), a3 = __ldg(mi + o3), b3 = __ldg(pj + o3);
           inter += __popc(a0 & b0) + __popc(a1 & b1) + __popc(a2 & b2) + __popc(a3 & b3);
         }
         for (; y < yhi; y += tyn) {
-          const size_t o = (size_t)y * ow_words + w;
+          const size_t o = (size_t)y * sy + (size_t)w * sw;
           inter += __popc(__ldg(mi + o) & __ldg(pj + o));
         }
       }
@@ -306,7 +309,7 @@ int launch_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_
                                                   c, ios, inter_out);
   NTTT_LAUNCH_CHECK();
   if (ios_stop == 3) return NTTT_OK;
-  ios_eval_big_kernel<<<148, kIosThreads, 0, s>>>(bits_full, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats, c,
+  ios_eval_big_kernel<<<148, kIosThreads, 0, s>>>(bits_full, bits_t, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats, c,
                                                   ios, inter_out);
   NTTT_LAUNCH_CHECK();
   if (finalize) {

@@ -80,6 +80,10 @@ __device__ __forceinline__ int rle_nchars(long long x) {
 struct RleGeom {
   const uint32_t* src;  // packed words of this mask
   int oh, ow_words, r0, r1, w0, w1, rend, n_strips;
+  bool tr;              // words are stored [word][row] (word-column major) instead of [row][word]
+  __device__ __forceinline__ uint32_t word(int y, int w) const {
+    return __ldg(tr ? src + (size_t)w * oh + y : src + (size_t)y * ow_words + w);
+  }
 };
 
 // run boundaries of the 32 columns of strip `st`, rows [r0 + 32*b, +32): returns the boundary bits of this lane's
@@ -88,7 +92,7 @@ __device__ __forceinline__ uint32_t rle_block_edges(const RleGeom& g, int st, in
   const int wi = g.w0 + st;
   const int y = g.r0 + 32 * b + lane;
   uint32_t word = 0;
-  if (y < g.r1 && wi < g.w1) word = __ldg(g.src + (size_t)y * g.ow_words + wi);
+  if (y < g.r1 && wi < g.w1) word = g.word(y, wi);
   const uint32_t col = transpose32(word, lane);
   uint32_t d = col ^ ((col << 1) | carry);
   carry = col >> 31;
@@ -103,7 +107,7 @@ __device__ __forceinline__ uint32_t rle_prev_column_last(const RleGeom& g, int x
   if (x == 0 || g.r1 < g.oh) return 0u;
   const int xp = x - 1, wp = xp >> 5;
   if (wp < g.w0 || wp >= g.w1) return 0u;
-  return (__ldg(g.src + (size_t)(g.oh - 1) * g.ow_words + wp) >> (xp & 31)) & 1u;
+  return (g.word(g.oh - 1, wp) >> (xp & 31)) & 1u;
 }
 
 // value of the pixel that precedes (x, r0) in column-major order, for the first block of a column: the wrap from the
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(kRleThreads)
 rle_encode_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restrict__ rect,
                   const int32_t* __restrict__ slot, const int32_t* __restrict__ count, int max_count, int oh, int ow,
                   int cap_counts, int cap_chars, uint32_t* __restrict__ counts_out, int32_t* __restrict__ n_counts,
-                  uint8_t* __restrict__ chars_out, int32_t* __restrict__ n_chars) {
+                  uint8_t* __restrict__ chars_out, int32_t* __restrict__ n_chars, bool tr) {
   extern __shared__ int s_col[];  // boundaries per visited column, then their exclusive prefix
   __shared__ int s_warp[kRleWarps + 1];
   const int j = blockIdx.x;
@@ -135,6 +139,7 @@ rle_encode_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restr
   const int4 rc = reinterpret_cast<const int4*>(rect)[k];
   RleGeom g;
   g.oh = oh;
+  g.tr = tr;
   g.ow_words = (ow + 31) >> 5;
   g.src = bits_full + (size_t)k * oh * g.ow_words;
   g.r0 = rc.x; g.r1 = rc.y; g.w0 = rc.z; g.w1 = rc.w;
@@ -239,7 +244,7 @@ rle_encode_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restr
 
 int launch_rle_encode(const uint32_t* bits_full, const int32_t* rect, const int32_t* slot, const int32_t* count,
                       int max_count, int oh, int ow, int cap_counts, int cap_chars, uint32_t* counts_out,
-                      int32_t* n_counts, uint8_t* chars_out, int32_t* n_chars, cudaStream_t s) {
+                      int32_t* n_counts, uint8_t* chars_out, int32_t* n_chars, cudaStream_t s, bool tr) {
   if (max_count <= 0) return NTTT_OK;
   if ((unsigned long long)oh * ow > 0xffffffffull) return NTTT_EUNSUPPORTED;
   const size_t smem = sizeof(int) * (size_t)(((ow + 31) / 32 + 1) * 32);
@@ -247,7 +252,7 @@ int launch_rle_encode(const uint32_t* bits_full, const int32_t* rect, const int3
   if (smem > 48 * 1024)
     NTTT_CUDA(cudaFuncSetAttribute(rle_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   rle_encode_kernel<<<max_count, kRleThreads, smem, s>>>(bits_full, rect, slot, count, max_count, oh, ow, cap_counts,
-                                                        cap_chars, counts_out, n_counts, chars_out, n_chars);
+                                                        cap_chars, counts_out, n_counts, chars_out, n_chars, tr);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }
