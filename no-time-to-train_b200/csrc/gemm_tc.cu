@@ -295,7 +295,11 @@ int launch_gemm_tc(const void* A, int lda, const void* B, int ldb, float* D, int
   if (!low_latency && N >= 512 && N % 256 == 0 && M >= g_gemm_bn256_min_m)
     return launch_tc<256, 4>(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(B), ldb, D,
                              ldd, M, N, K, splits, split_stride, s);
+#ifndef NTTT_SIM_NO_BN128
+  if (N >= 512 || (N > 64 && N <= 128))  // 65..128 columns: ONE 128-wide tile reads the A operand once instead of twice
+#else
   if (N >= 512)
+#endif
     return launch_tc<128, 5>(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(B), ldb, D,
                              ldd, M, N, K, splits, split_stride, s);
   return launch_tc<64, 6>(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(B), ldb, D, ldd,
