@@ -62,12 +62,16 @@ void nttt_ctx_destroy(nttt_ctx* ctx);
  *                                   do not fit take that path anyway).  Default 36 KB.
  *   NTTT_TUNE_LOWRES_EXTRA_SMEM     extra dynamic shared memory per CTA of the low-res pass (fewer resident CTAs per
  *                                   SM; process-wide).  Default 0 — measured: leaving room for other kernels buys nothing.
+ *   NTTT_TUNE_LOWRES_PERSISTENT     0 (default): the low-res pass runs one CTA per mask, three resident per SM; 1: persistent,
+ *                                   one CTA per SM with a 7-stage TMA ring; 2: persistent, two CTAs per SM with 4 stages
+ *                                   (process-wide).  Bit-identical; measured equal in throughput (92.6 / 93.8 / 92.7
+ *                                   us/image): the stage is bound by L2 tag throughput, which co-residency does not create.
  *   NTTT_TUNE_AXIS_CACHE_ENTRIES    capacity of the antialias-table cache (8..1024; shrinking below the number
  *                                   held drops the cache behind a device synchronisation).  Default 1024: an image takes one table per distinct height and width.
  *   NTTT_TUNE_GEMM_BN256_MIN_M      row count from which the pooling GEMM uses 128 x 256 tiles (process-wide).
  *                                   Default 512 (measured: 32 fat CTAs beat 64 at 1024 rows, 97.9 vs 100.3 us/image). */
 enum { NTTT_TUNE_UPSAMPLE_STAGE_BYTES = 1, NTTT_TUNE_LOWRES_EXTRA_SMEM = 2, NTTT_TUNE_GEMM_BN256_MIN_M = 3,
-       NTTT_TUNE_AXIS_CACHE_ENTRIES = 4 };
+       NTTT_TUNE_AXIS_CACHE_ENTRIES = 4, NTTT_TUNE_LOWRES_PERSISTENT = 5 };
 int nttt_ctx_tune(nttt_ctx* ctx, int what, long long value);
 
 /* number of kernels this library has launched in this process (bench.py's `gpu_launches`) */

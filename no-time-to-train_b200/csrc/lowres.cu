@@ -392,6 +392,187 @@ lowres_pack_fast_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 pe
   }
 }
 
+// K1c: persistent form of K1b — ONE CTA per SM, a 7-stage ring, CTA b takes masks b, b + grid, b + 2*grid, ...
+//
+// With images in flight the stage is a queue of kernels competing for SMs, and K1b (one CTA per mask, three CTAs per
+// SM to keep enough bytes in flight) owns every register and all shared memory of an SM while it runs: the other
+// kernels of the other images — which hardly touch HBM — cannot run beside the one kernel that is bound by it
+// (tools/ablate.py: the marginal costs of the stages ADD UP, 39 us of HBM time + 76 us of everything else).
+// Here one CTA per SM with a 7-stage ring (or two with 4 stages each) keeps 112 KB of bulk copies in flight (HBM needs
+// ~55 KB per SM), the producer runs ahead
+// into the next mask while the consumers finish the current one, and two thirds of the SM's registers and ~100 KB of
+// its shared memory stay free for the kernels of the other images.
+// The packed words are double-buffered so that one consumer barrier per mask is enough; the warp that finishes the
+// mask's statistics last combines and publishes them.
+// ---------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void pk_consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kPackThreads) : "memory"); }
+
+// (min-blocks 3 only caps the registers at 72 per thread: the shared-memory request admits one CTA per SM, and the
+// registers this kernel does not take are what the kernels of the other images run in)
+template <int kPersistStages>
+__global__ void __launch_bounds__(kPackBlock, 3)
+lowres_pack_persistent_kernel(const float4* __restrict__ logits, int n_masks, int p4 /* pixels/4 per mask */,
+                              int words_per_row, uint32_t* __restrict__ bits, int32_t* __restrict__ area,
+                              int32_t* __restrict__ box, int32_t* __restrict__ flags, const float* __restrict__ gate,
+                              float gate_min, const float* const* __restrict__ mask_ptr) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  uint4* s_stage = reinterpret_cast<uint4*>(s_raw);
+  const int n_words = p4 >> 3;
+  uint32_t* s_bits0 = reinterpret_cast<uint32_t*>(s_raw + (size_t)kPersistStages * kPackStageBytes);  // 2 x n_words
+  __shared__ uint64_t s_full[kPersistStages], s_empty[kPersistStages];
+  __shared__ int s_part[2][kPackThreads / 32][8];  // per warp: area, unsafe, minx, miny, maxx, maxy
+  __shared__ int s_done[2];
+  const int lane = lane_id(), warp = warp_id();
+  const int n_stages = (p4 + kPackStageF4 - 1) / kPackStageF4;
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < kPersistStages; ++q) { pk_mbar_init(&s_full[q], 1); pk_mbar_init(&s_empty[q], kPackThreads / 32); }
+    s_done[0] = 0; s_done[1] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kPackThreads / 32) {
+    // ===== producer warp: streams the stages of all of this CTA's (non-gated) masks back to back =====
+    if (lane == 0) {
+      const uint64_t l2_policy = pk_policy_evict_first();
+      int sg = 0;  // stages issued so far (ring position)
+      for (int n = blockIdx.x; n < n_masks; n += gridDim.x) {
+        if (gate && !(gate[n] > gate_min)) continue;
+        const float4* src = mask_ptr ? reinterpret_cast<const float4*>(mask_ptr[n]) : logits + (size_t)n * p4;
+        for (int st = 0; st < n_stages; ++st, ++sg) {
+          const int q = sg % kPersistStages;
+          pk_mbar_wait(&s_empty[q], ((sg / kPersistStages) & 1) ^ 1);
+          const int f4 = min(kPackStageF4, p4 - st * kPackStageF4);
+          pk_mbar_expect_tx(&s_full[q], (uint32_t)f4 * 16u);
+          pk_bulk_load(s_stage + (size_t)q * kPackStageF4, src + (size_t)st * kPackStageF4, (uint32_t)f4 * 16u, &s_full[q], l2_policy);
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps =====
+  const int g = lane & 7;
+  const int ustar = ((g >> 2) << 1) | (g & 1);
+  const int grp = threadIdx.x & ~7;
+  int off[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int u = j ^ ustar;
+    off[j] = u * kPackThreads + grp + (g ^ (u & 1));
+  }
+  const uint32_t sel_a = (g & 4) ? 0x04u : 0x40u;
+  const uint32_t sel_c = (g & 2) ? 0x1504u : 0x5140u;
+  const int word_slot = ustar * (kPackThreads / 8) + (threadIdx.x >> 3);
+  int sg = 0, it = 0;
+  for (int n = blockIdx.x; n < n_masks; n += gridDim.x) {
+    uint4* dst = reinterpret_cast<uint4*>(bits + (size_t)n * n_words);
+    if (gate && !(gate[n] > gate_min)) {  // filtered-out candidate: its logits are never read
+      for (int i = threadIdx.x; i < (n_words >> 2); i += kPackThreads) dst[i] = make_uint4(0, 0, 0, 0);
+      if (threadIdx.x == 0) {
+        area[n] = 0;
+        flags[n] = 1;
+        reinterpret_cast<int4*>(box)[n] = make_int4(0, 0, 0, 0);
+      }
+      continue;
+    }
+    const int buf = it & 1;
+    ++it;
+    uint32_t* s_bits = s_bits0 + (size_t)buf * n_words;
+    uint32_t unsafe = 0;
+    int mx = (int)0x80000000;
+    uint32_t mn = 0xffffffffu;
+    bool exact = false;
+    for (int st = 0; st < n_stages; ++st, ++sg) {
+      const int q = sg % kPersistStages;
+      pk_mbar_wait(&s_full[q], (sg / kPersistStages) & 1);
+      const uint4* sbuf = s_stage + (size_t)q * kPackStageF4;
+      const int f0 = st * kPackStageF4;
+      uint4 v[4];
+      if (f0 + kPackStageF4 <= p4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = sbuf[off[j]];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          v[j] = (f0 + (off[j] & ~7) < p4) ? sbuf[off[j]] : make_uint4(0xbf800000u, 0xbf800000u, 0xbf800000u, 0xbf800000u);
+      }
+      __syncwarp();
+      if (lane == 0) pk_mbar_arrive(&s_empty[q]);
+      uint32_t a01 = 0, a23 = 0;
+      if (!exact) {
+        a01 = pk_sign_chain(pk_sign_chain(0u, v[1]), v[0]);
+        a23 = pk_sign_chain(pk_sign_chain(0u, v[3]), v[2]);
+        int mx1 = mx;
+        uint32_t mn1 = mn;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          mx1 = __vimax3_s32(mx1, (int)v[j].x, (int)v[j].y);
+          mx1 = __vimax3_s32(mx1, (int)v[j].z, (int)v[j].w);
+          mn1 = __vimin3_u32(mn1, v[j].x, v[j].y);
+          mn1 = __vimin3_u32(mn1, v[j].z, v[j].w);
+        }
+        if (mn1 == 0u || mx1 > 0x7f800000) exact = true;
+        else { mx = mx1; mn = mn1; }
+      }
+      if (exact) {
+        a01 = pk_exact_negbits(v[0], unsafe) | (pk_exact_negbits(v[1], unsafe) << 4);
+        a23 = pk_exact_negbits(v[2], unsafe) | (pk_exact_negbits(v[3], unsafe) << 4);
+      }
+      const uint32_t r = __shfl_xor_sync(kFull, a23, 4);
+      const uint32_t y = __byte_perm(a01, r, sel_a);
+      const uint32_t z = __shfl_xor_sync(kFull, y, 1);
+      const uint32_t hv = ~((y & 0x0F0Fu) | (z & 0xF0F0u));
+      const uint32_t z2 = __shfl_xor_sync(kFull, hv, 2);
+      const uint32_t word = __byte_perm(hv, z2, sel_c);
+      if (!(g & 2) && f0 + ustar * kPackThreads + grp < p4) s_bits[st * (kPackStageF4 / 8) + word_slot] = word;
+    }
+    unsafe |= (uint32_t)(mx >= 0x71800000 || mn < 0x0D800001u);
+    pk_consumer_barrier();  // the mask's words are complete (and everybody has left the previous use of the other buffer)
+    int a = 0, minx = 0x7fffffff, miny = 0x7fffffff, maxx = -1, maxy = -1;
+    for (int wi = threadIdx.x; wi < n_words; wi += kPackThreads) {
+      const uint32_t word = s_bits[wi];
+      if (word) {
+        a += __popc(word);
+        const int row = wi / words_per_row;
+        const int x0 = (wi - row * words_per_row) * 32;
+        minx = min(minx, x0 + __ffs(word) - 1);
+        maxx = max(maxx, x0 + 31 - __clz(word));
+        miny = min(miny, row);
+        maxy = max(maxy, row);
+      }
+    }
+    const uint4* s4 = reinterpret_cast<const uint4*>(s_bits);
+    for (int i = threadIdx.x; i < (n_words >> 2); i += kPackThreads) dst[i] = s4[i];
+    a = warp_sum(a);
+    unsafe = (uint32_t)warp_max((int)unsafe);
+    minx = warp_min(minx); miny = warp_min(miny); maxx = warp_max(maxx); maxy = warp_max(maxy);
+    int last = 0;
+    if (lane == 0) {
+      int* pw = s_part[buf][warp];
+      pw[0] = a; pw[1] = (int)unsafe; pw[2] = minx; pw[3] = miny; pw[4] = maxx; pw[5] = maxy;
+      __threadfence_block();
+      last = atomicAdd(&s_done[buf], 1) == kPackThreads / 32 - 1;
+      if (last) {
+        __threadfence_block();
+        int ta = 0, tu = 0, tminx = 0x7fffffff, tminy = 0x7fffffff, tmaxx = -1, tmaxy = -1;
+#pragma unroll
+        for (int w = 0; w < kPackThreads / 32; ++w) {
+          const volatile int* q = s_part[buf][w];
+          ta += q[0]; tu |= q[1];
+          tminx = min(tminx, q[2]); tminy = min(tminy, q[3]); tmaxx = max(tmaxx, q[4]); tmaxy = max(tmaxy, q[5]);
+        }
+        s_done[buf] = 0;  // (next use of this buffer is two masks away, behind a consumer barrier)
+        area[n] = ta;
+        flags[n] = tu ? 0 : 1;
+        const bool empty = tmaxx < tminx || tmaxy < tminy;
+        reinterpret_cast<int4*>(box)[n] = empty ? make_int4(0, 0, 0, 0) : make_int4(tminx, tminy, tmaxx, tmaxy);
+      }
+    }
+  }
+}
+
 // stab may be NULL: the stability counts (sam2/utils/amg.py:158-178) are not read on the noAMG path
 // gate (nullable): per-mask score; masks with !(gate[n] > gate_min) are skipped and published as empty
 // mask_ptr (nullable, device [n]): mask n is read from mask_ptr[n] (16-byte aligned) instead of logits + n*h*w
@@ -408,6 +589,9 @@ static int pack_mode() {
 // occupancy experiment knob (nttt_ctx_tune NTTT_TUNE_LOWRES_EXTRA_SMEM): extra dynamic shared memory per CTA of the
 // fast pack kernel, i.e. fewer resident CTAs per SM, leaving room for the other images' kernels
 int g_pack_extra_smem = 0;
+// nttt_ctx_tune(NTTT_TUNE_LOWRES_PERSISTENT): 0 = one CTA per mask (3 resident per SM), 1 = persistent, one CTA per SM with
+// a 7-stage ring, 2 = persistent, two CTAs per SM with 4 stages each
+int g_pack_persistent = 0;
 int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits,
                        int32_t* area, int32_t* box, int32_t* stab, int32_t* flags, const float* gate, float gate_min,
                        const float* const* mask_ptr, cudaStream_t s, float* stab_score) {
@@ -421,6 +605,21 @@ int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, floa
     NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lowres_pack_kernel<true><<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area, box,
                                                         stab, stab_score, flags, gate, gate_min, mask_ptr);
+  } else if (pack_mode() <= 1 && g_pack_persistent > 0) {
+    int sm_count = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+    const size_t bits_bytes = 2 * (size_t)(p / 32) * sizeof(uint32_t);
+    if (g_pack_persistent == 1) {
+      const size_t sm = 7 * (size_t)kPackStageBytes + bits_bytes;
+      NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_persistent_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      lowres_pack_persistent_kernel<7><<<min(n, sm_count), kPackBlock, sm, s>>>(src, n, (int)(p / 4), w / 32, bits, area, box,
+                                                                               flags, gate, gate_min, mask_ptr);
+    } else {
+      const size_t sm = 4 * (size_t)kPackStageBytes + bits_bytes;
+      NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_persistent_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      lowres_pack_persistent_kernel<4><<<min(n, 2 * sm_count), kPackBlock, sm, s>>>(src, n, (int)(p / 4), w / 32, bits, area,
+                                                                                   box, flags, gate, gate_min, mask_ptr);
+    }
   } else if (pack_mode() <= 1) {
     const size_t smem_fast = smem + (size_t)g_pack_extra_smem;
     NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));

@@ -228,7 +228,7 @@ class MatchingStage:
         return PendingResult(self, masks.view(torch.bool) if masks is not None else None, boxes, scores, labels, index,
                              counts, tap_t, (oh, ow), keepalive=(lr_masks, pred_ious, multi_ious, tar_feat, ws), rle=rle_t)
 
-    TUNABLES = {"upsample_stage_bytes": 1, "lowres_extra_smem": 2, "gemm_bn256_min_m": 3, "axis_cache_entries": 4}  # include/nttt_b200.h: NTTT_TUNE_*
+    TUNABLES = {"upsample_stage_bytes": 1, "lowres_extra_smem": 2, "gemm_bn256_min_m": 3, "axis_cache_entries": 4, "lowres_persistent": 5}  # include/nttt_b200.h: NTTT_TUNE_*
 
     def tune(self, name: str, value: int) -> None:
         """Set a performance tunable of this device's context (`nttt_ctx_tune`); results never depend on them."""

@@ -113,6 +113,30 @@ def test_stability_score_value_matches_reference(ops, name):
         assert got.shape == (2, 4) and np.array_equal(got.cpu().numpy(), want.numpy(), equal_nan=True)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_threshold_pack_persistent_variants_are_bit_identical(ops, synth, mode):
+    """NTTT_TUNE_LOWRES_PERSISTENT: the persistent forms of the low-res pass (one CTA per SM with a 7-stage ring, two
+    with 4 stages) give exactly the outputs of the default one-CTA-per-mask kernel, special values and gated masks
+    included (they are A/B options: measured equal in throughput)."""
+    gen = torch.Generator().manual_seed(41 + mode)
+    n = 333  # more masks than CTAs in flight: every CTA loops over several masks
+    logits = synth.make_masks(n, gen)
+    synth.inject_degenerate_cases(logits, torch.zeros(2, 2, 4))
+    logits[9, 17, 33] = float("nan")
+    logits[10, 200, 5] = float("inf")
+    logits[11] = 0.0
+    d = logits.to(DEV)
+    want = ops.threshold_pack(d, want_stab=False)
+    try:
+        ops.tune(DEV, 5, mode)
+        got = ops.threshold_pack(d, want_stab=False)
+    finally:
+        ops.tune(DEV, 5, 0)
+    for name, a, b in zip(("bits", "area", "box", "stab", "flags"), want, got):
+        if name != "stab":
+            assert torch.equal(a, b), name
+
+
 def test_threshold_pack_empty_batch(ops):
     bits, area, *_ = ops.threshold_pack(torch.zeros((0, 256, 256), device=DEV))
     assert bits.shape[0] == 0 and area.shape[0] == 0
