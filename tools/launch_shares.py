@@ -10,7 +10,8 @@ import re
 import sys
 from collections import OrderedDict
 
-SETUP = ("aa_table_kernel", "aa_transpose_kernel", "aa_group_kernel", "aa_pack_kernel", "proto_prepare_kernel")
+SETUP = ("aa_table_kernel", "aa_transpose_kernel", "aa_group_kernel", "aa_pack_kernel", "proto_prepare_kernel",
+         "fill_pool_kernel", "fill_scatter_kernel", "fill_finalize_kernel", "unpack_masks_kernel")  # (+ the fill phase)
 
 
 def short(name: str) -> str:
