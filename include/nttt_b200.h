@@ -244,6 +244,12 @@ int nttt_unpack_masks(const uint32_t* bits_full, const int32_t* rect, const int3
 int nttt_rle_encode(const uint32_t* bits_full, const int32_t* rect, const int32_t* slot, const int32_t* count,
                     int max_count, int oh, int ow, int cap_counts, int cap_chars, uint32_t* counts, int32_t* n_counts,
                     uint8_t* chars, int32_t* n_chars, void* stream);
+/* Packs the strings of outputs 0..n_masks-1 back to back for one small D2H read: mask j goes to
+ * out[sum_{i<j} len_i ...], len_i = n_chars[i] (a length outside [0, cap_chars] — an overflowed mask — counts as 0).
+ * Replaces the per-mask `rle["counts"].decode("utf-8")` host loop's input (dataset/coco_ref_dataset.py:603-604).
+ * Nothing is written past out_cap. */
+int nttt_rle_compact(const uint8_t* chars, const int32_t* n_chars, int n_masks, int cap_chars, uint8_t* out,
+                     int64_t out_cap, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * a2 / a5 — memory-bank fill and post-process

@@ -47,6 +47,7 @@ int launch_decay_rank(const float*, const int32_t*, const float*, const int32_t*
                       cudaStream_t);
 int launch_rle_encode(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, int, uint32_t*,
                       int32_t*, uint8_t*, int32_t*, cudaStream_t, bool tr = false);
+int launch_rle_compact(const uint8_t*, const int32_t*, int, int, uint8_t*, long long, cudaStream_t);
 int launch_fill_pool(const float*, const float*, int, int, int, int, int, int, float*, float*, float*, int, cudaStream_t);
 int launch_fill_scatter(const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*, float*,
                         cudaStream_t);
@@ -56,7 +57,7 @@ extern int g_pack_extra_smem;  // lowres.cu
 extern int g_pack_persistent;  // lowres.cu
 extern int g_gemm_bn256_min_m;  // gemm_tc.cu
 static thread_local char g_cuda_err[512] = "";
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 int cuda_fail(cudaError_t e, const char* what) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
@@ -215,7 +216,7 @@ int nttt_build_is_ablation(void) {
 
 size_t nttt_sizeof_match_args(void) { return sizeof(nttt_match_args); }
 
-unsigned long long nttt_launch_count(void) { return g_launches; }
+unsigned long long nttt_launch_count(void) { return g_launches.load(); }
 
 static const char* const kStageNames[] = {"lowres_pack", "project_masks", "pool_gemm", "normalize_rows", "sim_top1",
                                           "box_nms", "upsample_pack", "mask_ios", "decay_rank", "unpack", "rle_encode"};
@@ -589,6 +590,14 @@ int nttt_rle_encode(const uint32_t* bits_full, const int32_t* rect, const int32_
   if (!bits_full || !rect || !count || !counts || !n_counts || !chars || !n_chars) return NTTT_EINVAL;
   return launch_rle_encode(bits_full, rect, slot, count, max_count, oh, ow, cap_counts, cap_chars, counts, n_counts, chars,
                            n_chars, (cudaStream_t)stream);
+}
+
+int nttt_rle_compact(const uint8_t* chars, const int32_t* n_chars, int n_masks, int cap_chars, uint8_t* out,
+                     int64_t out_cap, void* stream) {
+  if (n_masks < 0 || cap_chars <= 0 || out_cap < 0) return NTTT_EINVAL;
+  if (n_masks == 0) return NTTT_OK;
+  if (!chars || !n_chars || !out) return NTTT_EINVAL;
+  return launch_rle_compact(chars, n_chars, n_masks, cap_chars, out, (long long)out_cap, (cudaStream_t)stream);
 }
 
 int nttt_fill_pool_accumulate(const float* feat, const float* soft_mask, int mh, int mw, int eh, int ew, int c,

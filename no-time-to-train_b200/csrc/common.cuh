@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/nttt_b200.h"
 
 namespace nttt {
@@ -19,7 +21,7 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_e != cudaSuccess) return ::nttt::cuda_fail(_e, #expr); \
   } while (0)
 // every kernel launch of the library passes through here; the counter backs nttt_launch_count()
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;  // (host threads of different contexts may launch concurrently)
 #define NTTT_LAUNCH_CHECK()          \
   do {                               \
     ++::nttt::g_launches;            \

@@ -257,4 +257,39 @@ int launch_rle_encode(const uint32_t* bits_full, const int32_t* rect, const int3
   return NTTT_OK;
 }
 
+// Packs the strings of the first n_masks outputs back to back (mask j at offset sum_{i<j} len_i) so the host reads
+// sum(len) bytes instead of n_masks * max(len).  One CTA per mask; a length outside [0, cap_chars] counts as 0.
+__global__ void __launch_bounds__(256)
+rle_compact_kernel(const uint8_t* __restrict__ chars, const int32_t* __restrict__ n_chars, int n_masks, int cap_chars,
+                   uint8_t* __restrict__ out, long long out_cap) {
+  __shared__ long long s_off;
+  const int j = blockIdx.x;
+  if (threadIdx.x < 32) {
+    long long acc = 0;
+    for (int i = threadIdx.x; i < j; i += 32) {
+      const int len = n_chars[i];
+      acc += (len < 0 || len > cap_chars) ? 0 : len;
+    }
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (threadIdx.x == 0) s_off = acc;
+  }
+  __syncthreads();
+  int len = n_chars[j];
+  if (len < 0 || len > cap_chars) len = 0;
+  const long long off = s_off;
+  if (off + len > out_cap) return;
+  const uint8_t* src = chars + (size_t)j * cap_chars;
+  uint8_t* dst = out + off;
+  // (a few KB per mask and an arbitrary destination alignment: plain coalesced byte copies)
+  for (int i = threadIdx.x; i < len; i += blockDim.x) dst[i] = src[i];
+}
+
+int launch_rle_compact(const uint8_t* chars, const int32_t* n_chars, int n_masks, int cap_chars, uint8_t* out,
+                       long long out_cap, cudaStream_t s) {
+  if (n_masks <= 0) return NTTT_OK;
+  rle_compact_kernel<<<n_masks, 256, 0, s>>>(chars, n_chars, n_masks, cap_chars, out, out_cap);
+  NTTT_LAUNCH_CHECK();
+  return NTTT_OK;
+}
+
 }  // namespace nttt

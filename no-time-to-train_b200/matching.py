@@ -30,10 +30,12 @@ class StageConfig:
 class PendingResult:
     """Device-side result of one image; `.get()` does the single D2H read of the counts and slices."""
 
-    def __init__(self, stage, masks, boxes, scores, labels, index, counts, taps, ori_hw, keepalive, rle=None):
+    def __init__(self, stage, masks, boxes, scores, labels, index, counts, taps, ori_hw, keepalive, rle=None, meta=None):
         self._stage = stage
         self.masks, self.boxes, self.scores, self.labels, self.index = masks, boxes, scores, labels, index
         self.counts = counts
+        self._meta_dev = meta if meta is not None else counts
+        self._meta = None  # host copy of counts (+ the RLE lengths, which share the counts' allocation): ONE D2H read
         self.taps = taps
         self.ori_hw = ori_hw
         self._keepalive = keepalive
@@ -45,22 +47,44 @@ class PendingResult:
         (`dataset/coco_ref_dataset.py:601-604`).  One small D2H read instead of the dense masks."""
         if self.rle is None:
             raise RuntimeError("the stage was not asked for RLE output (match_async(..., rle=True))")
-        n_out = int(self.counts.cpu()[2])
+        meta = self._host_meta()
+        n_out = int(meta[2])
         _, n_counts, chars, n_chars = self.rle
-        lens = n_chars[:n_out].cpu().tolist()
-        need = n_counts[:n_out].cpu().tolist()
+        k = n_chars.shape[0]
+        need, lens = meta[4:4 + n_out], meta[4 + k:4 + k + n_out]
         cap = chars.shape[1]
         for j, ln in enumerate(lens):
             if ln < 0 or ln > cap:
                 raise RuntimeError(f"RLE of output {j} does not fit (runs needed {need[j]}, bytes needed {ln}): raise "
                                    "StageConfig.rle_cap_counts / rle_cap_chars")
-        width = max(lens) if lens else 0
-        host = chars[:n_out, :width].cpu().numpy() if width else None
+        total = sum(lens)
         oh, ow = self.ori_hw
-        return [dict(size=[oh, ow], counts=host[j, :lens[j]].tobytes().decode("ascii")) for j in range(n_out)]
+        if not total:
+            return [dict(size=[oh, ow], counts="") for _ in range(n_out)]
+        # the strings, packed back to back on the device and read with ONE copy of sum(len) bytes into the stage's
+        # pinned staging buffer (a pageable `.cpu()` of the strided [n_out, max(len)] view costs ~0.5 ms)
+        st = self._stage
+        packed = st._workspace("rle_compact", chars.numel())
+        _lib.check(st.lib.nttt_rle_compact(chars.data_ptr(), n_chars.data_ptr(), n_out, cap, packed.data_ptr(),
+                                           packed.numel(), torch.cuda.current_stream(chars.device).cuda_stream),
+                   "nttt_rle_compact")
+        host = st._pinned_bytes(total)[:total]
+        host.copy_(packed[:total], non_blocking=True)
+        torch.cuda.current_stream(chars.device).synchronize()
+        raw = host.numpy().tobytes().decode("ascii")
+        out, off = [], 0
+        for ln in lens:
+            out.append(dict(size=[oh, ow], counts=raw[off:off + ln]))
+            off += ln
+        return out
+
+    def _host_meta(self) -> list:
+        if self._meta is None:
+            self._meta = self._meta_dev.cpu().tolist()  # synchronises with the producing stream
+        return self._meta
 
     def get(self) -> dict:
-        counts = self.counts.cpu()  # synchronises with the producing stream
+        counts = self._host_meta()
         n_keep, n_sel, n_out = int(counts[0]), int(counts[1]), int(counts[2])
         dev = self.boxes.device
         oh, ow = self.ori_hw
@@ -187,7 +211,9 @@ class MatchingStage:
         scores = torch.empty((max(num_out, 1),), dtype=torch.float32, device=dev)
         labels = torch.empty((max(num_out, 1),), dtype=torch.int64, device=dev)
         index = torch.empty((max(num_out, 1),), dtype=torch.int32, device=dev)
-        counts = torch.empty((4,), dtype=torch.int32, device=dev)
+        k_rle = max(num_out, 1) if rle else 0
+        meta = torch.empty((4 + 2 * k_rle,), dtype=torch.int32, device=dev)  # counts | rle n_counts | rle n_chars
+        counts = meta[:4]
         tap_t = {}
         if taps:
             tap_t["sim"] = torch.empty((n, self.n_cls), dtype=torch.float32, device=dev)
@@ -210,8 +236,8 @@ class MatchingStage:
         rle_t = None
         if rle:
             k, cc, ch = max(num_out, 1), int(self.cfg.rle_cap_counts), int(self.cfg.rle_cap_chars)
-            rle_t = (torch.empty((k, cc), dtype=torch.int32, device=dev), torch.empty((k,), dtype=torch.int32, device=dev),
-                     torch.empty((k, ch), dtype=torch.uint8, device=dev), torch.empty((k,), dtype=torch.int32, device=dev))
+            rle_t = (torch.empty((k, cc), dtype=torch.int32, device=dev), meta[4:4 + k],
+                     torch.empty((k, ch), dtype=torch.uint8, device=dev), meta[4 + k:])
             a.rle_counts, a.rle_n_counts, a.rle_chars, a.rle_n_chars = (t.data_ptr() for t in rle_t)
             a.rle_cap_counts, a.rle_cap_chars = cc, ch
         a.out_index, a.counts = index.data_ptr(), counts.data_ptr()
@@ -226,7 +252,16 @@ class MatchingStage:
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(self.lib.nttt_match_image(self.ctx, ctypes.byref(a), stream), "nttt_match_image")
         return PendingResult(self, masks.view(torch.bool) if masks is not None else None, boxes, scores, labels, index,
-                             counts, tap_t, (oh, ow), keepalive=(lr_masks, pred_ious, multi_ious, tar_feat, ws), rle=rle_t)
+                             counts, tap_t, (oh, ow), keepalive=(lr_masks, pred_ious, multi_ious, tar_feat, ws), rle=rle_t,
+                             meta=meta)
+
+    def _pinned_bytes(self, nbytes: int) -> torch.Tensor:
+        """Pinned host staging for result reads (grown on demand, reused call after call)."""
+        buf = self._ws.get("pinned")
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty((max(nbytes, 1 << 20),), dtype=torch.uint8).pin_memory()
+            self._ws["pinned"] = buf
+        return buf
 
     TUNABLES = {"upsample_stage_bytes": 1, "lowres_extra_smem": 2, "gemm_bn256_min_m": 3, "axis_cache_entries": 4, "lowres_persistent": 5}  # include/nttt_b200.h: NTTT_TUNE_*
 
@@ -330,4 +365,5 @@ class GraphedMatch:
         if self.graph is None:
             self.capture()
         self.graph.replay()
+        self.pending._meta = None  # the static buffers now hold a new image's result
         return self.pending

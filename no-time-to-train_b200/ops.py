@@ -340,6 +340,20 @@ def rle_encode(bits_full, rect, slot, count, ori_hw, cap_counts: int = 16384, ca
     return counts, n_counts, chars, n_chars
 
 
+def rle_compact(chars, n_chars, n_masks: int, out=None):
+    """The strings of outputs 0..n_masks-1 packed back to back (`nttt_rle_compact`): -> uint8 [>= sum(len)] on the
+    device; mask j starts at sum_{i<j} len_i.  Lengths outside [0, cap_chars] (overflowed masks) count as 0."""
+    _need(chars, torch.uint8, "chars")
+    _need(n_chars, torch.int32, "n_chars")
+    if out is None:
+        out = torch.empty((max(n_masks, 1) * chars.shape[1],), dtype=torch.uint8, device=chars.device)
+    _need(out, torch.uint8, "out")
+    lib = _lib.load()
+    _lib.check(lib.nttt_rle_compact(_ptr(chars), _ptr(n_chars), int(n_masks), int(chars.shape[1]), _ptr(out),
+                                    out.numel(), _stream(chars.device)), "nttt_rle_compact")
+    return out
+
+
 def fill_pool_accumulate(feat, soft_mask, enc_hw, sum_slot, wsum_slot, mask_slot=None):
     """One shot pooled straight INTO a bank slot: sum_slot [c], wsum_slot [1] and mask_slot [e] (nullable) are views of
     the bank's buffers and are accumulated in place (`+=`, as the reference's slot writes at :482-484)."""

@@ -198,6 +198,29 @@ def test_gpu_rle_large_random_and_overflow():
 
 
 @pytest.mark.gpu
+def test_gpu_rle_compact_packs_strings_back_to_back():
+    """nttt_rle_compact: string j at offset sum_{i<j} len_i, overflowed rows (len < 0 or > cap) skipped, nothing
+    written past the output capacity."""
+    ops = importlib.import_module("no-time-to-train_b200").ops
+    g = torch.Generator().manual_seed(5)
+    k, cap = 37, 512
+    chars = torch.randint(48, 112, (k, cap), dtype=torch.uint8, generator=g)
+    lens = torch.randint(0, cap + 1, (k,), dtype=torch.int32, generator=g)
+    lens[3], lens[11], lens[20], lens[21] = -1, cap + 9, 0, cap
+    want = b"".join(chars[j, :int(lens[j])].numpy().tobytes() for j in range(k) if 0 <= int(lens[j]) <= cap)
+    out = ops.rle_compact(chars.cuda(), lens.cuda(), k)
+    assert out[:len(want)].cpu().numpy().tobytes() == want
+    # a prefix only, into an output with room for the first five strings: the sixth must not be written
+    room = sum(int(lens[j]) for j in range(5) if 0 <= int(lens[j]) <= cap)
+    small = torch.full((room + 64,), 7, dtype=torch.uint8, device="cuda")
+    ops.rle_compact(chars.cuda(), lens.cuda(), 5, out=small[:room])
+    assert small[:room].cpu().numpy().tobytes() == want[:room] and bool((small[room:] == 7).all())
+    tiny = torch.full((8,), 7, dtype=torch.uint8, device="cuda")
+    ops.rle_compact(chars.cuda(), lens.cuda(), k, out=tiny[:4])
+    assert bool((tiny[4:] == 7).all())
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", ["stage_a_1024_degenerate", "stage_f_truncate_333x500", "stage_d_200x180_downscale",
                                   "stage_h_borders_640x480", "stage_i_borders_1024"])
 def test_stage_rle_output_matches_dense_masks(name):
