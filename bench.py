@@ -76,6 +76,15 @@ def parse():
 
 def configure_workload(args, world):
     shots = 10 if world == 1 else 30
+    # every rank keeps its shard resident: bound it to 42 % of the GPU's memory (config 2: 256 x 268 MB = 38 %), the rest
+    # is workspaces, outputs and the e2e legs.  A workload with bigger images (config 5: 1.07 GB each) gets a smaller
+    # dataset instead of an out-of-memory box; the line says so.
+    per_image = 4 * args.n_masks * 65536 + 4 * 1369 * 1024
+    total = torch.cuda.get_device_properties(0).total_memory if torch.cuda.is_available() else 192 << 30
+    fit = max(16, int(0.42 * total / per_image) // 16 * 16)
+    if -(-args.n_images // world) > fit:
+        WORKLOAD["n_images_requested"] = args.n_images
+        args.n_images = fit * world
     WORKLOAD.update(n_classes=args.n_classes, n_masks=args.n_masks, shots=shots, n_images=args.n_images)
     WORKLOAD["workload"] = (f"coco{args.n_classes}x{shots}_sam2L_dinov2L_{args.n_masks}masks_1024x1024_"
                             f"{args.n_images}img_sharded")

@@ -69,9 +69,14 @@ void nttt_ctx_destroy(nttt_ctx* ctx);
  *   NTTT_TUNE_AXIS_CACHE_ENTRIES    capacity of the antialias-table cache (8..1024; shrinking below the number
  *                                   held drops the cache behind a device synchronisation).  Default 1024: an image takes one table per distinct height and width.
  *   NTTT_TUNE_GEMM_BN256_MIN_M      row count from which the pooling GEMM uses 128 x 256 tiles (process-wide).
- *                                   Default 512 (measured: 32 fat CTAs beat 64 at 1024 rows, 97.9 vs 100.3 us/image). */
+ *                                   Default 512 (measured: 32 fat CTAs beat 64 at 1024 rows, 97.9 vs 100.3 us/image).
+ *   NTTT_TUNE_GEMM_SHARED_SEGMENTS  0 (default): the split-bf16 GEMMs stream all three K-segments of both operands; 1: they
+ *                                   load each k-block's four distinct operand tiles (A_hi, A_lo, B_hi, B_lo) once and
+ *                                   multiply them three ways (a third less L2 traffic; same products, summed in a
+ *                                   different order — float results may differ in the last bit).  Measured equal in
+ *                                   throughput: the kernel is bound by its SM's tensor pipe.  Process-wide. */
 enum { NTTT_TUNE_UPSAMPLE_STAGE_BYTES = 1, NTTT_TUNE_LOWRES_EXTRA_SMEM = 2, NTTT_TUNE_GEMM_BN256_MIN_M = 3,
-       NTTT_TUNE_AXIS_CACHE_ENTRIES = 4, NTTT_TUNE_LOWRES_PERSISTENT = 5 };
+       NTTT_TUNE_AXIS_CACHE_ENTRIES = 4, NTTT_TUNE_LOWRES_PERSISTENT = 5, NTTT_TUNE_GEMM_SHARED_SEGMENTS = 6 };
 int nttt_ctx_tune(nttt_ctx* ctx, int what, long long value);
 
 /* number of kernels this library has launched in this process (bench.py's `gpu_launches`) */

@@ -56,6 +56,7 @@ int launch_fill_finalize(const float*, const float*, int, int, int, float*, floa
 extern int g_pack_extra_smem;  // lowres.cu
 extern int g_pack_persistent;  // lowres.cu
 extern int g_gemm_bn256_min_m;  // gemm_tc.cu
+extern int g_gemm_shared_segments;
 static thread_local char g_cuda_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 
@@ -241,6 +242,10 @@ int nttt_ctx_tune(nttt_ctx* ctx, int what, long long value) {
     case NTTT_TUNE_GEMM_BN256_MIN_M:
       if (value < 0) return NTTT_EINVAL;
       nttt::g_gemm_bn256_min_m = (int)value;
+      return NTTT_OK;
+    case NTTT_TUNE_GEMM_SHARED_SEGMENTS:
+      if (value < 0 || value > 1) return NTTT_EINVAL;
+      nttt::g_gemm_shared_segments = (int)value;
       return NTTT_OK;
     case NTTT_TUNE_LOWRES_PERSISTENT:
       if (value < 0 || value > 2) return NTTT_EINVAL;

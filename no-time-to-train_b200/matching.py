@@ -263,7 +263,8 @@ class MatchingStage:
             self._ws["pinned"] = buf
         return buf
 
-    TUNABLES = {"upsample_stage_bytes": 1, "lowres_extra_smem": 2, "gemm_bn256_min_m": 3, "axis_cache_entries": 4, "lowres_persistent": 5}  # include/nttt_b200.h: NTTT_TUNE_*
+    TUNABLES = {"upsample_stage_bytes": 1, "lowres_extra_smem": 2, "gemm_bn256_min_m": 3, "axis_cache_entries": 4, "lowres_persistent": 5,
+                "gemm_shared_segments": 6}  # include/nttt_b200.h: NTTT_TUNE_*
 
     def tune(self, name: str, value: int) -> None:
         """Set a performance tunable of this device's context (`nttt_ctx_tune`); results never depend on them."""

@@ -337,6 +337,27 @@ def test_pipeline_matches_c_oracle(P, name):
                            masks=ref["binary_masks"].astype(bool), index=ref_index), what=name + " vs C oracle")
 
 
+@pytest.mark.parametrize("name", STAGE_CASES[:3])
+def test_pipeline_with_shared_segment_gemm(P, ops, name):
+    """NTTT_TUNE_GEMM_SHARED_SEGMENTS = 1 (`gemm_split3_kernel`: four operand tiles per k-block multiplied three ways
+    instead of three streamed K-segments) computes the same products in a different order: the same golden parity, and
+    every integer result of the default kernel."""
+    g, inp, cfg = load_case(name)
+    base = _run_stage(P, inp, cfg["num_out_instance"])
+    try:
+        ops.tune(DEV, 6, 1)
+        out = _run_stage(P, inp, cfg["num_out_instance"])
+    finally:
+        ops.tune(DEV, 6, 0)
+    assert_close_rel(out["taps"]["sim"].cpu().numpy(), g["sim"], what="sim")
+    assert_close_rel(out["taps"]["obj_feats"].cpu().numpy(), g["obj_feats"], what="obj_feats")
+    assert out["counts"] == base["counts"]
+    assert_rows_match(dict(scores=out["scores"], labels=out["labels"], bboxes=out["bboxes"], masks=out["binary_masks"]),
+                      dict(scores=base["scores"].cpu().numpy(), labels=base["labels"].cpu().numpy(),
+                           bboxes=base["bboxes"].cpu().numpy(), masks=base["binary_masks"].cpu().numpy()),
+                      what=name + " shared-segment GEMM vs default")
+
+
 def test_pipeline_empty_selection(P, synth):
     """All scores <= 0 -> the reference's empty early return (float32 zero boxes, :647-655)."""
     inp = synth.make_stage_inputs(n=16, c=64, n_cls=2, shots=1, ori_hw=(64, 96), seed=41)

@@ -1,2 +1,2 @@
-python -m pytest tests/test_rle.py tests/test_runner_and_fill.py tests/test_sam2_seam.py tests/test_filter_and_graph.py -m gpu -x -q 2>&1 | tail -3
-python tools/forward_timing.py 2>&1 | tail -8
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "shared_segment or golden" 2>&1 | tail -3
+python bench.py --value-only --n-masks 4096 --tune gemm_shared_segments=1 2>&1 | tail -5 | cut -c1-600
