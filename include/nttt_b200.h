@@ -74,9 +74,12 @@ void nttt_ctx_destroy(nttt_ctx* ctx);
  *                                   load each k-block's four distinct operand tiles (A_hi, A_lo, B_hi, B_lo) once and
  *                                   multiply them three ways (a third less L2 traffic; same products, summed in a
  *                                   different order — float results may differ in the last bit).  Measured equal in
- *                                   throughput: the kernel is bound by its SM's tensor pipe.  Process-wide. */
+ *                                   throughput: the kernel is bound by its SM's tensor pipe.  Process-wide.
+ *   NTTT_TUNE_GEMM_BN256_STAGES     2..4 (default 3): TMA ring depth of the 128 x 256 pooling GEMM (48 KB per stage); fewer
+ *                                   stages leave shared memory to co-resident CTAs of other kernels.  Process-wide. */
 enum { NTTT_TUNE_UPSAMPLE_STAGE_BYTES = 1, NTTT_TUNE_LOWRES_EXTRA_SMEM = 2, NTTT_TUNE_GEMM_BN256_MIN_M = 3,
-       NTTT_TUNE_AXIS_CACHE_ENTRIES = 4, NTTT_TUNE_LOWRES_PERSISTENT = 5, NTTT_TUNE_GEMM_SHARED_SEGMENTS = 6 };
+       NTTT_TUNE_AXIS_CACHE_ENTRIES = 4, NTTT_TUNE_LOWRES_PERSISTENT = 5, NTTT_TUNE_GEMM_SHARED_SEGMENTS = 6,
+       NTTT_TUNE_GEMM_BN256_STAGES = 7 };
 int nttt_ctx_tune(nttt_ctx* ctx, int what, long long value);
 
 /* number of kernels this library has launched in this process (bench.py's `gpu_launches`) */

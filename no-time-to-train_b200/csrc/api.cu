@@ -32,7 +32,7 @@ int launch_box_nms(const int32_t*, const float*, const int32_t*, const float*, i
 int launch_upsample_pack(const AxisTable&, const AxisTable&, const float*, const uint32_t*, const int32_t*,
                          const int32_t*, int, int, const int32_t*, const int32_t*, int, int, int, uint32_t*, int32_t*,
                          int32_t*, int32_t*, int32_t*, const float* const*, cudaStream_t, int, int, uint32_t* bits_t = nullptr,
-                         bool* wrote_t = nullptr, bool t_only = false);
+                         bool* wrote_t = nullptr, bool t_only = false, bool low_latency = false);
 size_t upsample_scratch_bytes(int max_sel, int oh, int ow);
 int launch_unpack_sparse(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, uint8_t*,
                          int32_t*, cudaStream_t, bool tr = false);
@@ -57,8 +57,12 @@ extern int g_pack_extra_smem;  // lowres.cu
 extern int g_pack_persistent;  // lowres.cu
 extern int g_gemm_bn256_min_m;  // gemm_tc.cu
 extern int g_gemm_shared_segments;
+extern int g_gemm_bn256_stages;
+extern int g_up2_ctas_per_sm;
 static thread_local char g_cuda_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+int g_exp[8] = {};
+thread_local bool t_low_latency = false;
 
 int cuda_fail(cudaError_t e, const char* what) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
@@ -247,8 +251,16 @@ int nttt_ctx_tune(nttt_ctx* ctx, int what, long long value) {
       if (value < 0 || value > 1) return NTTT_EINVAL;
       nttt::g_gemm_shared_segments = (int)value;
       return NTTT_OK;
+    case NTTT_TUNE_GEMM_BN256_STAGES:
+      if (value < 2 || value > 4) return NTTT_EINVAL;
+      nttt::g_gemm_bn256_stages = (int)value;
+      return NTTT_OK;
+    case 8:
+      if (value < 1 || value > 7) return NTTT_EINVAL;
+      nttt::g_up2_ctas_per_sm = (int)value;
+      return NTTT_OK;
     case NTTT_TUNE_LOWRES_PERSISTENT:
-      if (value < 0 || value > 2) return NTTT_EINVAL;
+      if (value < 0 || value > 49) return NTTT_EINVAL;
       nttt::g_pack_persistent = (int)value;
       return NTTT_OK;
     case NTTT_TUNE_LOWRES_EXTRA_SMEM:
@@ -260,6 +272,10 @@ int nttt_ctx_tune(nttt_ctx* ctx, int what, long long value) {
       ctx->upsample_stage_floats = (int)(value / 4);
       return NTTT_OK;
     default:
+      if (what >= 100 && what < 108 && value >= 0 && value <= (1 << 20)) {
+        nttt::g_exp[what - 100] = (int)value;
+        return NTTT_OK;
+      }
       return NTTT_EINVAL;
   }
 }
@@ -738,6 +754,11 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   if (a->workspace_bytes < L.total) return NTTT_EWORKSPACE;
   float* obj_feats = a->obj_feats ? a->obj_feats : L.obj_feats;
   float* sim = a->sim ? a->sim : L.sim;
+  struct LaunchMode {  // the launch shapes of this call (common.cuh: t_low_latency), restored on every return path
+    bool prev;
+    explicit LaunchMode(bool v) : prev(nttt::t_low_latency) { nttt::t_low_latency = v; }
+    ~LaunchMode() { nttt::t_low_latency = prev; }
+  } launch_mode(a->low_latency != 0);
   ++ctx->epoch;
   AxisTable px, py, ux, uy;
   int err = ctx->axis(a->ew, a->lr_w, s, &px);
@@ -809,7 +830,7 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   NTTT_STEP(launch_upsample_pack(ux, uy, a->logits, L.bits_lr, L.box_lr, L.flags, a->lr_h, a->lr_w, L.sel,
                                  a->counts + 1, max_sel, a->ori_h, a->ori_w, L.bits_full, L.rect, L.area_full,
                                  L.box_full, L.scratch, mask_ptr, s, ctx->upsample_stage_floats, ctx->sm_count, L.bits_t,
-                                 &wrote_t, /*t_only=*/true));
+                                 &wrote_t, /*t_only=*/true, a->low_latency != 0));
   // the packed full-resolution masks from here on: word-column major when the v2 resize ran, row-major otherwise
   const uint32_t* packed = wrote_t ? L.bits_t : L.bits_full;
   // a13

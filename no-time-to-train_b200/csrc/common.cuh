@@ -21,6 +21,11 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_e != cudaSuccess) return ::nttt::cuda_fail(_e, #expr); \
   } while (0)
 // every kernel launch of the library passes through here; the counter backs nttt_launch_count()
+// Set by nttt_match_image for the duration of the call (launchers run on the calling thread): kernels take the launch
+// shape with the shortest duration of ONE image instead of the thin persistent shape that costs the least when many
+// images are in flight (nttt_match_args.low_latency).  Results do not depend on it.
+extern thread_local bool t_low_latency;
+extern int g_exp[8];  // launch-shape experiments (nttt_ctx_tune ids 100..107); 0 = the built-in default
 extern std::atomic<unsigned long long> g_launches;  // (host threads of different contexts may launch concurrently)
 #define NTTT_LAUNCH_CHECK()          \
   do {                               \

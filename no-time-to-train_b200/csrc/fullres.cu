@@ -427,6 +427,7 @@ constexpr int kUp2Cols = 8;                          // word columns per item
 constexpr int kUp2Rows = kUp2Groups * kGrpMax;       // output rows per item (<= 128)
 constexpr int kUp2OutStride = kUp2Rows + kUp2Rows / 32;  // column-major result tile, one pad word per 32 rows
 constexpr int kUp2CtasPerSm = 7;
+int g_up2_ctas_per_sm = 1;
 
 struct alignas(16) Up2Item {  // 32 bytes, written by the plan kernel
   int k;                 // selected-mask slot
@@ -895,7 +896,8 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
                          const int32_t* box_lr, const int32_t* flags_lr, int ih, int iw, const int32_t* sel,
                          const int32_t* n_sel, int max_sel, int oh, int ow, uint32_t* bits_full, int32_t* rect,
                          int32_t* area_full, int32_t* box_full, int32_t* scratch, const float* const* mask_ptr,
-                         cudaStream_t s, int stage_floats, int sm_count, uint32_t* bits_t, bool* wrote_t, bool t_only) {
+                         cudaStream_t s, int stage_floats, int sm_count, uint32_t* bits_t, bool* wrote_t, bool t_only,
+                         bool low_latency) {
   // bits_t (nullable): also write the word-column-major copy [k][word][row]; t_only: and skip the row-major one
   // (every consumer of the fused pipeline reads the transposed layout).  *wrote_t tells whether the v2 path ran.
   if (wrote_t) *wrote_t = false;
@@ -927,7 +929,7 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
     NTTT_LAUNCH_CHECK();
     if (smem > 48 * 1024)
       NTTT_CUDA(cudaFuncSetAttribute(upsample_pack2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (sm_count > 0 ? sm_count : 148) * kUp2CtasPerSm;
+    const int grid = (sm_count > 0 ? sm_count : 148) * (low_latency ? kUp2CtasPerSm : g_up2_ctas_per_sm);
     upsample_pack2_kernel<<<grid, kUp2Threads, smem, s>>>(bits_lr, meta, ih, iw, oh, ow, t,
                                                           (bits_t && t_only) ? nullptr : bits_full, bits_t, area_full,
                                                           box_full, scratch, items, ctr);

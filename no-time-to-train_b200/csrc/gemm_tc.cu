@@ -421,6 +421,10 @@ static int launch_tc3(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, i
   return NTTT_OK;
 }
 
+// nttt_ctx_tune(NTTT_TUNE_GEMM_BN256_STAGES): TMA ring depth of the 128 x 256 kernel.  The kernel is tensor-pipe bound, so
+// three 48 KB stages feed it as well as four and leave 83 KB of the SM's shared memory to CTAs of the other kernels of
+// the images in flight (measured 91.8 vs 92.3 us/image; two stages: 92.0).
+int g_gemm_bn256_stages = 3;
 int g_gemm_bn256_min_m = 512;  // nttt_ctx_tune(NTTT_TUNE_GEMM_BN256_MIN_M)
 // nttt_ctx_tune(NTTT_TUNE_GEMM_SHARED_SEGMENTS): 1 = gemm_split3_kernel.  Off by default — measured equal at config 2
 // (92.5 vs 92.5 us/image) and 1.5 us/image slower at 1 203 classes: a CTA's 264 MMAs of 128 x 256 x 16 take 25 of its
@@ -457,6 +461,8 @@ int launch_gemm_tc(const void* A, int lda, const void* B, int ldb, float* D, int
     if (bn128) return launch_tc3<128, 6>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s);
     return launch_tc3<64, 8>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s);
   }
+  if (bn256 && g_gemm_bn256_stages == 2) return launch_tc<256, 2>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s);
+  if (bn256 && g_gemm_bn256_stages == 3) return launch_tc<256, 3>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s);
   if (bn256) return launch_tc<256, 4>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s);
   if (bn128) return launch_tc<128, 5>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s);
   return launch_tc<64, 6>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s);

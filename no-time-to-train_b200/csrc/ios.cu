@@ -63,12 +63,11 @@ __global__ void __launch_bounds__(256)
 ios_pairs_kernel(const IosMeta* __restrict__ meta, const int32_t* __restrict__ label_sel,
                  const int32_t* __restrict__ n_sel, int max_sel, int2* __restrict__ pairs,
                  int32_t* __restrict__ n_pairs, int max_pairs) {
-  const int i = blockIdx.x;
   const int nsel = min(*n_sel, max_sel);
-  if (i >= nsel) return;
-  const IosMeta me = meta[i];
-  if (me.area == 0) return;
   const int lane = lane_id();
+  for (int i = blockIdx.x; i < nsel; i += gridDim.x) {  // (row i has nsel - i - 1 partners: striding balances the CTAs)
+  const IosMeta me = meta[i];
+  if (me.area == 0) continue;
   for (int base = i + 1; base < nsel; base += 256) {
     const int j = base + threadIdx.x;
     bool hit = false, big = false;
@@ -93,6 +92,7 @@ ios_pairs_kernel(const IosMeta* __restrict__ meta, const int32_t* __restrict__ l
       slot = __shfl_sync(kFull, slot, 0) + __popc(mb & ((1u << lane) - 1u));
       if (big) pairs[max_pairs - 1 - slot] = make_int2(i, j);
     }
+  }
   }
 }
 
@@ -302,14 +302,15 @@ int launch_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_
                                                          label_sel, ios, n_pairs);
   NTTT_LAUNCH_CHECK();
   if (ios_stop == 1) return NTTT_OK;
-  ios_pairs_kernel<<<max_sel, 256, 0, s>>>(meta, label_sel, n_sel, max_sel, pairs, n_pairs, max_pairs);
+  ios_pairs_kernel<<<g_exp[3] > 0 ? min(max_sel, g_exp[3]) : max_sel, 256, 0, s>>>(meta, label_sel, n_sel, max_sel, pairs, n_pairs, max_pairs);
   NTTT_LAUNCH_CHECK();
   if (ios_stop == 2) return NTTT_OK;
-  ios_eval_kernel<<<148 * 4, kIosThreads, 0, s>>>(bits_full, bits_t, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats,
+  // one CTA per SM when many images are in flight (measured 89.4 vs 90.0 us/image with four), four for one image alone
+  ios_eval_kernel<<<g_exp[0] > 0 ? g_exp[0] : (t_low_latency ? 148 * 4 : 148), kIosThreads, 0, s>>>(bits_full, bits_t, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats,
                                                   c, ios, inter_out);
   NTTT_LAUNCH_CHECK();
   if (ios_stop == 3) return NTTT_OK;
-  ios_eval_big_kernel<<<148, kIosThreads, 0, s>>>(bits_full, bits_t, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats, c,
+  ios_eval_big_kernel<<<g_exp[1] > 0 ? g_exp[1] : 148, kIosThreads, 0, s>>>(bits_full, bits_t, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats, c,
                                                   ios, inter_out);
   NTTT_LAUNCH_CHECK();
   if (finalize) {

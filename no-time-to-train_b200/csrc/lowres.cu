@@ -589,9 +589,25 @@ static int pack_mode() {
 // occupancy experiment knob (nttt_ctx_tune NTTT_TUNE_LOWRES_EXTRA_SMEM): extra dynamic shared memory per CTA of the
 // fast pack kernel, i.e. fewer resident CTAs per SM, leaving room for the other images' kernels
 int g_pack_extra_smem = 0;
-// nttt_ctx_tune(NTTT_TUNE_LOWRES_PERSISTENT): 0 = one CTA per mask (3 resident per SM), 1 = persistent, one CTA per SM with
-// a 7-stage ring, 2 = persistent, two CTAs per SM with 4 stages each
-int g_pack_persistent = 0;
+
+// SM count of the current device (queried once per device)
+static int current_sm_count() {
+  static int cache[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+  int count = 148;
+  cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev);
+  if (dev >= 0 && dev < 64) cache[dev] = count;
+  return count;
+}
+
+// nttt_ctx_tune(NTTT_TUNE_LOWRES_PERSISTENT): 0 = one CTA per mask (3 resident per SM; always used in low-latency mode),
+// otherwise persistent CTAs that loop over masks: 10 * CTAs-per-SM + ring stages (1 and 2 = the round-2a shapes 17 / 24).
+// Measured with 16 images in flight (us/image): one CTA per mask 88.2 | 17: 90.6 | 24: 87.5 | 23: 86.7 | 22: 88.2 |
+// 33: 87.7 | 32: 89.5 | 25: 87.9 | 42: 89.1 — the thinnest shape that still covers the HBM latency wins, because what it
+// does not occupy runs the other images' kernels.
+int g_pack_persistent = 23;
 int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, float off, uint32_t* bits,
                        int32_t* area, int32_t* box, int32_t* stab, int32_t* flags, const float* gate, float gate_min,
                        const float* const* mask_ptr, cudaStream_t s, float* stab_score) {
@@ -605,21 +621,29 @@ int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, floa
     NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lowres_pack_kernel<true><<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area, box,
                                                         stab, stab_score, flags, gate, gate_min, mask_ptr);
-  } else if (pack_mode() <= 1 && g_pack_persistent > 0) {
-    int sm_count = 148;
-    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+  } else if (pack_mode() <= 1 && g_pack_persistent > 0 && !t_low_latency) {
+    const int sm_count = current_sm_count();
     const size_t bits_bytes = 2 * (size_t)(p / 32) * sizeof(uint32_t);
-    if (g_pack_persistent == 1) {
-      const size_t sm = 7 * (size_t)kPackStageBytes + bits_bytes;
-      NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_persistent_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      lowres_pack_persistent_kernel<7><<<min(n, sm_count), kPackBlock, sm, s>>>(src, n, (int)(p / 4), w / 32, bits, area, box,
-                                                                               flags, gate, gate_min, mask_ptr);
-    } else {
-      const size_t sm = 4 * (size_t)kPackStageBytes + bits_bytes;
-      NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_persistent_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      lowres_pack_persistent_kernel<4><<<min(n, 2 * sm_count), kPackBlock, sm, s>>>(src, n, (int)(p / 4), w / 32, bits, area,
-                                                                                   box, flags, gate, gate_min, mask_ptr);
+    // modes 1 and 2 are the named ones; 10 * CTAs-per-SM + stages selects any other shape (experiments)
+    const int shape = g_pack_persistent == 1 ? 17 : g_pack_persistent == 2 ? 24 : g_pack_persistent;
+    const int per_sm = shape / 10, stages = shape % 10;
+    const size_t sm = (size_t)stages * kPackStageBytes + bits_bytes;
+    const int grid = min(n, per_sm * sm_count);
+#define NTTT_PERSIST_CASE(S)                                                                                            \
+  case S:                                                                                                               \
+    NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_persistent_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    lowres_pack_persistent_kernel<S><<<grid, kPackBlock, sm, s>>>(src, n, (int)(p / 4), w / 32, bits, area, box, flags, gate, \
+                                                                  gate_min, mask_ptr);                                  \
+    break;
+    switch (stages) {
+      NTTT_PERSIST_CASE(2)
+      NTTT_PERSIST_CASE(3)
+      NTTT_PERSIST_CASE(4)
+      NTTT_PERSIST_CASE(5)
+      NTTT_PERSIST_CASE(7)
+      default: return NTTT_EINVAL;
     }
+#undef NTTT_PERSIST_CASE
   } else if (pack_mode() <= 1) {
     const size_t smem_fast = smem + (size_t)g_pack_extra_smem;
     NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
@@ -863,12 +887,12 @@ __device__ __forceinline__ void warp_range(int n, F flag, int& lo, int& hi) {
 
 template <bool kSplit>
 __global__ void __launch_bounds__(kProjThreads)
-project_masks_kernel(const uint32_t* __restrict__ bits, const int32_t* __restrict__ box, int h, int words_per_row,
-                     int eh, int ew, ProjTables t, void* __restrict__ out, int stride_or_kp) {
+project_masks_kernel(const uint32_t* __restrict__ bits, const int32_t* __restrict__ box, int n_masks, int h,
+                     int words_per_row, int eh, int ew, ProjTables t, void* __restrict__ out, int stride_or_kp) {
   extern __shared__ uint32_t smem[];
   // layout: x_lo[ew] x_len[ew] y_lo[eh] y_len[eh] | bits[rc*wpr] | row[rc*ew] | acc[eh*ew]     (rc = min(h, kProjRows))
   // (the weight tables — running column sums, row weights — are the same for every mask and are read through L1
-  // from the prebuilt global tables instead of being re-staged by each CTA)
+  // from the prebuilt global tables)
   const int rc = min(h, kProjRows);
   int* s_xlo = reinterpret_cast<int*>(smem);
   int* s_xlen = s_xlo + ew;
@@ -877,9 +901,14 @@ project_masks_kernel(const uint32_t* __restrict__ bits, const int32_t* __restric
   uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_ylen + eh);
   float* s_row = reinterpret_cast<float*>(s_bits + rc * words_per_row);
   float* s_acc = s_row + rc * ew;
-  const int n = blockIdx.x;
   const int lane = lane_id(), warp = warp_id();
   constexpr int kWarps = kProjThreads / 32;
+  if (eh > 64 || ew > 64) return;  // (checked by the launcher)
+  // the span tables are the same for every mask: staged once per CTA, which then walks masks blockIdx.x, +gridDim.x, ...
+  for (int i = threadIdx.x; i < ew; i += kProjThreads) { s_xlo[i] = t.x_lo[i]; s_xlen[i] = min(t.x_len[i], kMaxScatter); }
+  for (int i = threadIdx.x; i < eh; i += kProjThreads) { s_ylo[i] = t.y_lo[i]; s_ylen[i] = min(t.y_len[i], kMaxScatter); }
+  for (int n = blockIdx.x; n < n_masks; n += gridDim.x) {
+  __syncthreads();  // tables staged / the previous mask's accumulators and rows are no longer read
   const int4 b = reinterpret_cast<const int4*>(box)[n];
   const uint32_t* src = bits + (size_t)n * h * words_per_row;
   const bool empty = (b.x | b.y | b.z | b.w) == 0 && (src[0] & 1u) == 0;
@@ -896,18 +925,14 @@ project_masks_kernel(const uint32_t* __restrict__ bits, const int32_t* __restric
       for (int i = threadIdx.x; i < (int)(row_bytes >> 2); i += kProjThreads) reinterpret_cast<uint32_t*>(o)[i] = 0;
     }
   }
-  if (empty || eh > 64 || ew > 64) return;  // (eh, ew <= 64 is checked by the launcher)
-
-  for (int i = threadIdx.x; i < ew; i += kProjThreads) { s_xlo[i] = t.x_lo[i]; s_xlen[i] = min(t.x_len[i], kMaxScatter); }
-  for (int i = threadIdx.x; i < eh; i += kProjThreads) { s_ylo[i] = t.y_lo[i]; s_ylen[i] = min(t.y_len[i], kMaxScatter); }
+  if (empty) continue;  // (CTA-uniform)
   const int nrows = bottom - top + 1;
-  __syncthreads();
   // encoder cells whose spans touch the box
   int ex_lo, ex_hi, ey_lo, ey_hi;
   warp_range(ew, [&](int e) { return s_xlo[e] <= right && s_xlo[e] + s_xlen[e] > left; }, ex_lo, ex_hi);
   warp_range(eh, [&](int e) { return s_ylo[e] <= bottom && s_ylo[e] + s_ylen[e] > top; }, ey_lo, ey_hi);
   const int nex = ex_hi - ex_lo + 1;
-  if (nex <= 0 || ey_hi < ey_lo) return;
+  if (nex <= 0 || ey_hi < ey_lo) continue;  // (CTA-uniform)
   // every cell (ey, ex) has ONE owner thread for the whole kernel: warp = (ey - ey_lo) % kWarps, lane = (ex - ex_lo) % 32
   for (int ey = ey_lo + warp; ey <= ey_hi; ey += kWarps)
     for (int ex = ex_lo + lane; ex <= ex_hi; ex += 32) s_acc[ey * ew + ex] = 0.0f;
@@ -971,6 +996,7 @@ project_masks_kernel(const uint32_t* __restrict__ bits, const int32_t* __restric
       }
     }
   }
+  }  // masks of this CTA
 }
 
 static size_t project_smem_bytes(int h, int w, int eh, int ew) {
@@ -987,14 +1013,20 @@ int launch_project_masks(const AxisTable& tx, const AxisTable& ty, const uint32_
   const size_t smem = project_smem_bytes(h, w, eh, ew);
   if (smem > 200 * 1024) return NTTT_EUNSUPPORTED;
   ProjTables t{tx.t_lo, tx.t_len, tx.t_cum, ty.t_lo, ty.t_len, ty.t_w};
+  // throughput mode: two persistent CTAs per SM walk the masks (measured 88.1 vs 89.4 us/image with one CTA per mask:
+  // the span tables are staged once per CTA and 1024 CTA launches become 296); low-latency mode: one CTA per mask
+  int grid = n;
+  if (!t_low_latency) {
+    grid = min(n, g_exp[2] > 0 ? g_exp[2] : 2 * current_sm_count());
+  }
   if (split) {
     if (smem > 48 * 1024)
       NTTT_CUDA(cudaFuncSetAttribute(project_masks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    project_masks_kernel<true><<<n, kProjThreads, smem, s>>>(bits, box, h, w / 32, eh, ew, t, out, out_stride);
+    project_masks_kernel<true><<<grid, kProjThreads, smem, s>>>(bits, box, n, h, w / 32, eh, ew, t, out, out_stride);
   } else {
     if (smem > 48 * 1024)
       NTTT_CUDA(cudaFuncSetAttribute(project_masks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    project_masks_kernel<false><<<n, kProjThreads, smem, s>>>(bits, box, h, w / 32, eh, ew, t, out, out_stride);
+    project_masks_kernel<false><<<grid, kProjThreads, smem, s>>>(bits, box, n, h, w / 32, eh, ew, t, out, out_stride);
   }
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
