@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -63,6 +64,26 @@ static thread_local char g_cuda_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 int g_exp[8] = {};
 thread_local bool t_low_latency = false;
+
+cudaError_t set_dyn_smem_impl(const void* fn, int bytes) {
+  struct Entry { const void* fn; int dev; int bytes; };
+  static std::mutex mu;
+  static Entry table[256];
+  static int n = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  Entry* hit = nullptr;
+  for (int i = 0; i < n; ++i)
+    if (table[i].fn == fn && table[i].dev == dev) { hit = &table[i]; break; }
+  if (hit && hit->bytes >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  if (hit) hit->bytes = bytes;
+  else if (n < 256) table[n++] = Entry{fn, dev, bytes};
+  return cudaSuccess;
+}
 
 int cuda_fail(cudaError_t e, const char* what) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
@@ -148,6 +169,9 @@ static int sim_top1(const float* obj_feats, const float* proto, const float* pro
   if (err) return err;
   int want = gemm_tc_pick_splits(n, n_cls, 3 * cp, sm_count < 148 ? sm_count : 148);
   if (want > kMaxSimSplits) want = kMaxSimSplits;
+  // with many images in flight the partial tiles of a split-K cost more SM-time (8 x the prologues, epilogues and
+  // partial sums) than the one long CTA per tile they shorten: measured 84.0 (no split) / 84.6 (2) / 85.1 (4) / 86.8 (8)
+  if (!t_low_latency) want = 1;
   const size_t stride = (size_t)n * n_cls;
   int splits = 1;
   err = launch_gemm_tc(a_split, 3 * cp, b_split, 3 * cp, partials, n_cls, n, n_cls, 3 * cp, want, stride, &splits, s);
@@ -158,6 +182,7 @@ static int sim_top1(const float* obj_feats, const float* proto, const float* pro
   if (err) return err;
   int want_n = gemm_tc_pick_splits(n, cols, 3 * cp, sm_count < 148 ? sm_count : 148);
   if (want_n > kMaxSimSplits) want_n = kMaxSimSplits;
+  if (!t_low_latency) want_n = 1;
   const size_t stride_n = (size_t)n * cols;
   int splits_n = 1;
   err = launch_gemm_tc(a_split, 3 * cp, b_split, 3 * cp, partials_neg, cols, n, cols, 3 * cp, want_n, stride_n, &splits_n,

@@ -20,6 +20,11 @@ int cuda_fail(cudaError_t e, const char* what);
     cudaError_t _e = (expr);                                   \
     if (_e != cudaSuccess) return ::nttt::cuda_fail(_e, #expr); \
   } while (0)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel, size reached): the call costs several
+// microseconds of host time, which a caller that launches one image at a time pays on every kernel
+cudaError_t set_dyn_smem_impl(const void* fn, int bytes);
+template <typename F>
+inline cudaError_t set_dyn_smem(F* fn, int bytes) { return set_dyn_smem_impl(reinterpret_cast<const void*>(fn), bytes); }
 // every kernel launch of the library passes through here; the counter backs nttt_launch_count()
 // Set by nttt_match_image for the duration of the call (launchers run on the calling thread): kernels take the launch
 // shape with the shortest duration of ONE image instead of the thin persistent shape that costs the least when many

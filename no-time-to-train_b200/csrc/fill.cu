@@ -94,7 +94,7 @@ int launch_fill_pool(const float* feat, const float* soft_mask, int b, int mh, i
   const size_t smem = sizeof(float) * ((((size_t)eh * ew + 3) & ~(size_t)3) + 8 * 128);
   if (smem > 200 * 1024) return NTTT_EUNSUPPORTED;
   if (smem > 48 * 1024)
-    NTTT_CUDA(cudaFuncSetAttribute(fill_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NTTT_CUDA(set_dyn_smem(fill_pool_kernel, (int)smem));
   fill_pool_kernel<<<dim3(ceil_div(c, 128), b), 256, smem, s>>>(feat, soft_mask, mh, mw, eh, ew, c, sums, wsums, mask_out,
                                                                 accumulate);
   NTTT_LAUNCH_CHECK();

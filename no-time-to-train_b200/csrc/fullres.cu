@@ -922,13 +922,13 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
     const int stage_tables = tab_bytes <= 96 * 1024;
     if (!stage_tables) tab_bytes = 0;
     if (tab_bytes > 0)  // (the kernel also holds 33 KB of static shared memory: opt in to more than 48 KB in total)
-      NTTT_CUDA(cudaFuncSetAttribute(upsample_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+      NTTT_CUDA(set_dyn_smem(upsample_plan_kernel, (int)tab_bytes));
     upsample_plan_kernel<<<1, 1024, tab_bytes, s>>>(bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, t, meta, rect,
                                                     scratch, logits, mask_ptr, items, ctr, area_full, box_full, oh, ow,
                                                     tile_floats, stage_tables);
     NTTT_LAUNCH_CHECK();
     if (smem > 48 * 1024)
-      NTTT_CUDA(cudaFuncSetAttribute(upsample_pack2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      NTTT_CUDA(set_dyn_smem(upsample_pack2_kernel, (int)smem));
     const int grid = (sm_count > 0 ? sm_count : 148) * (low_latency ? kUp2CtasPerSm : g_up2_ctas_per_sm);
     upsample_pack2_kernel<<<grid, kUp2Threads, smem, s>>>(bits_lr, meta, ih, iw, oh, ow, t,
                                                           (bits_t && t_only) ? nullptr : bits_full, bits_t, area_full,
@@ -944,7 +944,7 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
   if (bits_bytes + stage_bytes > 200 * 1024) stage_bytes = 0;
   const size_t smem = bits_bytes + stage_bytes;
   if (smem > 48 * 1024)
-    NTTT_CUDA(cudaFuncSetAttribute(upsample_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NTTT_CUDA(set_dyn_smem(upsample_pack_kernel, (int)smem));
   upsample_meta_kernel<<<ceil_div(max_sel, 256), 256, 0, s>>>(bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, t,
                                                               meta, rect, scratch, logits, mask_ptr);
   NTTT_LAUNCH_CHECK();

@@ -391,7 +391,7 @@ static int launch_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, in
   if (err) return err;
   const size_t smem = sizeof(GemmSmem<BN, STAGES>) + 1024;
   auto kern = gemm_tc_kernel<BN, STAGES>;
-  NTTT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NTTT_CUDA(set_dyn_smem(kern, (int)smem));
   const int total_kb = K / kBK;
   const int kb_per = ceil_div(total_kb, splits);
   dim3 grid(ceil_div(N, BN), ceil_div(M, kBM), ceil_div(total_kb, kb_per));
@@ -411,7 +411,7 @@ static int launch_tc3(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, i
   if (err) return err;
   const size_t smem = sizeof(Gemm3Smem<BN, SLOTS>) + 1024;
   auto kern = gemm_split3_kernel<BN, SLOTS>;
-  NTTT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NTTT_CUDA(set_dyn_smem(kern, (int)smem));
   const int kp = K / 3;
   const int total_kb = kp / kBK;
   const int kb_per = ceil_div(total_kb, splits);
@@ -510,27 +510,31 @@ __global__ void __launch_bounds__(256)
 split_transpose_kernel(const float* __restrict__ X, int ld, int rows, int k, int kp, int mode,
                        __nv_bfloat16* __restrict__ out) {
   __shared__ float tile[64][33];
-  const int k0 = blockIdx.x * 64, r0 = blockIdx.y * 32;
+  const int tiles_k = kp / 64, tiles_r = (rows + 31) / 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int tile_id = blockIdx.x; tile_id < tiles_k * tiles_r; tile_id += gridDim.x) {  // (a few tiles per CTA)
+    const int k0 = (tile_id % tiles_k) * 64, r0 = (tile_id / tiles_k) * 32;
+    if (tile_id != (int)blockIdx.x) __syncthreads();  // the previous tile has been written out
 #pragma unroll
-  for (int j = ty; j < 64; j += 8) {
-    const int kk = k0 + j, rr = r0 + tx;
-    tile[j][tx] = (kk < k && rr < rows) ? X[(size_t)kk * ld + rr] : 0.0f;
-  }
-  __syncthreads();
-  const int kk = k0 + 2 * tx;
+    for (int j = ty; j < 64; j += 8) {
+      const int kk = k0 + j, rr = r0 + tx;
+      tile[j][tx] = (kk < k && rr < rows) ? X[(size_t)kk * ld + rr] : 0.0f;
+    }
+    __syncthreads();
+    const int kk = k0 + 2 * tx;
 #pragma unroll
-  for (int j = ty; j < 32; j += 8) {
-    const int rr = r0 + j;
-    if (rr < rows && kk + 1 < kp) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(tile[2 * tx][j], h0, l0);
-      split_bf16(tile[2 * tx + 1][j], h1, l1);
-      const __nv_bfloat162 hi = __halves2bfloat162(h0, h1), lo = __halves2bfloat162(l0, l1);
-      __nv_bfloat16* dst = out + (size_t)rr * 3 * kp + kk;
-      *reinterpret_cast<__nv_bfloat162*>(dst) = hi;
-      *reinterpret_cast<__nv_bfloat162*>(dst + kp) = mode == 0 ? hi : lo;
-      *reinterpret_cast<__nv_bfloat162*>(dst + 2 * kp) = mode == 0 ? lo : hi;
+    for (int j = ty; j < 32; j += 8) {
+      const int rr = r0 + j;
+      if (rr < rows && kk + 1 < kp) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(tile[2 * tx][j], h0, l0);
+        split_bf16(tile[2 * tx + 1][j], h1, l1);
+        const __nv_bfloat162 hi = __halves2bfloat162(h0, h1), lo = __halves2bfloat162(l0, l1);
+        __nv_bfloat16* dst = out + (size_t)rr * 3 * kp + kk;
+        *reinterpret_cast<__nv_bfloat162*>(dst) = hi;
+        *reinterpret_cast<__nv_bfloat162*>(dst + kp) = mode == 0 ? hi : lo;
+        *reinterpret_cast<__nv_bfloat162*>(dst + 2 * kp) = mode == 0 ? lo : hi;
+      }
     }
   }
 }
@@ -546,7 +550,8 @@ int launch_split_rows(const float* X, int ld, int rows, int k, int kp, int mode,
 int launch_split_transpose(const float* X, int ld, int rows, int k, int kp, int mode, void* out, cudaStream_t s) {
   if (rows <= 0) return NTTT_OK;
   if (kp % 64 != 0) return NTTT_EINVAL;  // (callers pad K to 64: the GEMM's K block)
-  dim3 grid(kp / 64, ceil_div(rows, 32));
+  const int tiles = (kp / 64) * ceil_div(rows, 32);
+  const int grid = g_exp[5] > 0 ? min(tiles, g_exp[5]) : (t_low_latency ? tiles : min(tiles, 148));
   split_transpose_kernel<<<grid, 256, 0, s>>>(X, ld, rows, k, kp, mode, static_cast<__nv_bfloat16*>(out));
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;

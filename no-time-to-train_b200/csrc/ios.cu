@@ -302,7 +302,7 @@ int launch_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_
                                                          label_sel, ios, n_pairs);
   NTTT_LAUNCH_CHECK();
   if (ios_stop == 1) return NTTT_OK;
-  ios_pairs_kernel<<<g_exp[3] > 0 ? min(max_sel, g_exp[3]) : max_sel, 256, 0, s>>>(meta, label_sel, n_sel, max_sel, pairs, n_pairs, max_pairs);
+  ios_pairs_kernel<<<g_exp[3] > 0 ? min(max_sel, g_exp[3]) : (t_low_latency ? max_sel : min(max_sel, 148)), 256, 0, s>>>(meta, label_sel, n_sel, max_sel, pairs, n_pairs, max_pairs);
   NTTT_LAUNCH_CHECK();
   if (ios_stop == 2) return NTTT_OK;
   // one CTA per SM when many images are in flight (measured 89.4 vs 90.0 us/image with four), four for one image alone
@@ -404,7 +404,7 @@ int launch_decay_rank(const float* top_score, const int32_t* labels, const float
   const size_t smem = (sizeof(unsigned long long) + sizeof(float)) * (size_t)n_pad;
   if (smem > 200 * 1024) return NTTT_EUNSUPPORTED;
   if (smem > 48 * 1024)
-    NTTT_CUDA(cudaFuncSetAttribute(decay_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NTTT_CUDA(set_dyn_smem(decay_rank_kernel, (int)smem));
   decay_rank_kernel<<<1, 1024, smem, s>>>(top_score, labels, ios, sel, n_sel, max_sel, n_pad, num_out, box_full,
                                           area_full, out_boxes, out_scores, out_labels, out_index, out_slot, n_out, decayed_out);
   NTTT_LAUNCH_CHECK();

@@ -618,7 +618,7 @@ int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, floa
   const size_t smem = (size_t)kPackStages * kPackStageBytes + (size_t)(p / 32) * sizeof(uint32_t);
   const float4* src = reinterpret_cast<const float4*>(logits);
   if (stab) {
-    NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NTTT_CUDA(set_dyn_smem(lowres_pack_kernel<true>, (int)smem));
     lowres_pack_kernel<true><<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area, box,
                                                         stab, stab_score, flags, gate, gate_min, mask_ptr);
   } else if (pack_mode() <= 1 && g_pack_persistent > 0 && !t_low_latency) {
@@ -631,7 +631,7 @@ int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, floa
     const int grid = min(n, per_sm * sm_count);
 #define NTTT_PERSIST_CASE(S)                                                                                            \
   case S:                                                                                                               \
-    NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_persistent_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    NTTT_CUDA(set_dyn_smem(lowres_pack_persistent_kernel<S>, (int)sm)); \
     lowres_pack_persistent_kernel<S><<<grid, kPackBlock, sm, s>>>(src, n, (int)(p / 4), w / 32, bits, area, box, flags, gate, \
                                                                   gate_min, mask_ptr);                                  \
     break;
@@ -646,11 +646,11 @@ int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, floa
 #undef NTTT_PERSIST_CASE
   } else if (pack_mode() <= 1) {
     const size_t smem_fast = smem + (size_t)g_pack_extra_smem;
-    NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
+    NTTT_CUDA(set_dyn_smem(lowres_pack_fast_kernel, (int)smem_fast));
     lowres_pack_fast_kernel<<<n, kPackBlock, smem_fast, s>>>(src, (int)(p / 4), w / 32, bits, area, box, flags, gate, gate_min,
                                                         mask_ptr);
   } else {
-    NTTT_CUDA(cudaFuncSetAttribute(lowres_pack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NTTT_CUDA(set_dyn_smem(lowres_pack_kernel<false>, (int)smem));
     lowres_pack_kernel<false><<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area,
                                                          box, stab, nullptr, flags, gate, gate_min, mask_ptr);
   }
@@ -1021,11 +1021,11 @@ int launch_project_masks(const AxisTable& tx, const AxisTable& ty, const uint32_
   }
   if (split) {
     if (smem > 48 * 1024)
-      NTTT_CUDA(cudaFuncSetAttribute(project_masks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      NTTT_CUDA(set_dyn_smem(project_masks_kernel<true>, (int)smem));
     project_masks_kernel<true><<<grid, kProjThreads, smem, s>>>(bits, box, n, h, w / 32, eh, ew, t, out, out_stride);
   } else {
     if (smem > 48 * 1024)
-      NTTT_CUDA(cudaFuncSetAttribute(project_masks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      NTTT_CUDA(set_dyn_smem(project_masks_kernel<false>, (int)smem));
     project_masks_kernel<false><<<grid, kProjThreads, smem, s>>>(bits, box, n, h, w / 32, eh, ew, t, out, out_stride);
   }
   NTTT_LAUNCH_CHECK();

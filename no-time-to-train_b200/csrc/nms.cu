@@ -365,7 +365,7 @@ int launch_box_nms(const int32_t* box, const float* nms_scores, const int32_t* l
   } else {
     const size_t smem = sizeof(unsigned long long) * (size_t)n_pad;
     if (smem > 48 * 1024)
-      NTTT_CUDA(cudaFuncSetAttribute(nms_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      NTTT_CUDA(set_dyn_smem(nms_sort_kernel<false>, (int)smem));
     nms_sort_kernel<false><<<1, 1024, smem, s>>>(nms_scores, box, labels, n, n_pad, min_score, filter, order, sorted_box,
                                                  sorted_label, nz, n * nz_words);
   }

@@ -250,7 +250,7 @@ int launch_rle_encode(const uint32_t* bits_full, const int32_t* rect, const int3
   const size_t smem = sizeof(int) * (size_t)(((ow + 31) / 32 + 1) * 32);
   if (smem > 160 * 1024) return NTTT_EUNSUPPORTED;
   if (smem > 48 * 1024)
-    NTTT_CUDA(cudaFuncSetAttribute(rle_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NTTT_CUDA(set_dyn_smem(rle_encode_kernel, (int)smem));
   rle_encode_kernel<<<max_count, kRleThreads, smem, s>>>(bits_full, rect, slot, count, max_count, oh, ow, cap_counts,
                                                         cap_chars, counts_out, n_counts, chars_out, n_chars, tr);
   NTTT_LAUNCH_CHECK();

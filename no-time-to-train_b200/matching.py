@@ -297,13 +297,16 @@ class MatchingStage:
         return out
 
     def graphed(self, n: int, c: int, ori_hw, iou_thr=None, key=None, n_multi: int = 0,
-                multi_first: int = 1, rle: bool = False, dense_masks: bool = True, persistent_out=None) -> "GraphedMatch":
+                multi_first: int = 1, rle: bool = False, dense_masks: bool = True, persistent_out=None,
+                low_latency: bool = False) -> "GraphedMatch":
         """A CUDA-graph capture of the whole stage at fixed shapes with static input/output buffers.
         n_multi > 1: the static mask buffer is the decoder's raw [n, n_multi, 256, 256] output (+ `multi_ious`).
         rle / dense_masks: as in `match_async`.  `key` names the workspace slot and `persistent_out` the
         (masks, prev_rect) output buffers: graphs that are replayed on the SAME stream may share both (a caller
-        holding one graph per resident image passes the stream's slot)."""
-        return GraphedMatch(self, n, c, ori_hw, iou_thr, key, n_multi, multi_first, rle, dense_masks, persistent_out)
+        holding one graph per resident image passes the stream's slot).  `low_latency`: capture the launch shapes
+        for one image at a time (a caller that waits for each result) instead of many images in flight."""
+        return GraphedMatch(self, n, c, ori_hw, iou_thr, key, n_multi, multi_first, rle, dense_masks, persistent_out,
+                            low_latency)
 
 
 class GraphedMatch:
@@ -316,7 +319,8 @@ class GraphedMatch:
     again.  Replay costs one graph launch on the host instead of ~18 kernel launches."""
 
     def __init__(self, stage: MatchingStage, n: int, c: int, ori_hw, iou_thr=None, key=None, n_multi: int = 0,
-                 multi_first: int = 1, rle: bool = False, dense_masks: bool = True, persistent_out=None):
+                 multi_first: int = 1, rle: bool = False, dense_masks: bool = True, persistent_out=None,
+                 low_latency: bool = False):
         dev = stage.device
         eh, ew = stage.cfg.enc_hw
         self.stage = stage
@@ -329,7 +333,7 @@ class GraphedMatch:
             self.pred_ious = torch.zeros((n,), dtype=torch.float32, device=dev)
             self.multi_ious = None
         self.multi_first = multi_first
-        self._kw = dict(rle=rle, dense_masks=dense_masks)
+        self._kw = dict(rle=rle, dense_masks=dense_masks, low_latency=low_latency)
         self.tar_feat = torch.zeros((eh * ew, c), dtype=torch.float32, device=dev)
         self.ori_hw = (int(ori_hw[0]), int(ori_hw[1]))
         self.iou_thr = iou_thr

@@ -22,6 +22,8 @@ def main() -> None:
     ap.add_argument("--n-masks", type=int, default=1024)
     ap.add_argument("--n-classes", type=int, default=80)
     ap.add_argument("--tune", action="append", default=[])
+    ap.add_argument("--latency", action="store_true", help="time ONE image at a time: a CUDA-graph replay of the stage "
+                    "in both launch modes (CUDA events, device idle before every replay) and the per-stage event profile")
     args = ap.parse_args()
     pkg = importlib.import_module("no-time-to-train_b200")
     synth = pkg.synth
@@ -44,6 +46,32 @@ def main() -> None:
             p = stage.match_async(*img, (1024, 1024), slot=0, persistent_out=outs)
     torch.cuda.synchronize(dev)
     print("n_out", p.get()["counts"])
+    if args.latency:
+        for low in (False, True):
+            g = stage.graphed(args.n_masks, c, (1024, 1024), key=("lat", low), low_latency=low)
+            g.lr_masks.copy_(images[0][0]); g.pred_ious.copy_(images[0][1]); g.tar_feat.copy_(images[0][2])
+            g.capture()
+            times = []
+            for rep in range(24):
+                img = images[rep % len(images)]
+                g.lr_masks.copy_(img[0]); g.pred_ious.copy_(img[1]); g.tar_feat.copy_(img[2])
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); g.replay(); e1.record()
+                torch.cuda.synchronize(dev)
+                times.append(1e3 * e0.elapsed_time(e1))
+            times = sorted(times[4:])
+            print(f"graph replay, low_latency={low}: median {times[len(times) // 2]:.1f} us, min {times[0]:.1f} us per image")
+        stage.profile(True)
+        acc = {}
+        for rep in range(12):
+            p = stage.match_async(*images[rep % len(images)], (1024, 1024), slot=0, persistent_out=outs, low_latency=True)
+            torch.cuda.synchronize(dev)
+            if rep >= 2:
+                for k, v in stage.profile_read().items():
+                    acc[k] = acc.get(k, 0.0) + 1e3 * v / 10
+        stage.profile(False)
+        print("per-stage (eager, low-latency, includes host launch gaps): " + "  ".join(f"{k} {v:.1f}" for k, v in acc.items()))
 
 
 if __name__ == "__main__":
