@@ -624,19 +624,23 @@ def main():
         alg_bytes = 4 * args.n_masks * WORKLOAD["lowres"] ** 2
         peak, peak_src = measured_peak()
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        traffic, traffic_src = None, None
+        traffic, traffic_src, prof_kernel = None, None, None
         try:  # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel at this shape
             with open(os.path.join(ROOT, "profiles", "lowres_pack_ncu.json")) as f:
                 prof = json.load(f)
+            prof_kernel = prof.get("kernel")
             if args.n_masks == 1024:
                 traffic, traffic_src = prof["traffic_bytes_per_launch"], "profiles/lowres_pack_ncu.json (ncu --set full capture)"
         except Exception:
             pass
-        roofline = dict(bound="hbm", kernel="lowres_pack_fast_kernel", achieved=achieved, peak=peak, unit="GB/s",
+        persistent = not any(t.split("=") == ["lowres_persistent", "0"] for t in args.tune)
+        roofline = dict(bound="hbm", kernel=prof_kernel if persistent and prof_kernel else
+                        ("lowres_pack_persistent_kernel<3>" if persistent else "lowres_pack_fast_kernel"), achieved=achieved, peak=peak, unit="GB/s",
                         frac=achieved / peak, traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
                         alg_bytes_per_launch=alg_bytes, us_per_launch=1e3 * k_ms,
-                        note="peak is the driver's copy bandwidth (read+write); a read-only stream of the same 268 MB "
-                             "through torch.sum reaches 5.45 TB/s on this part (scratch measurement, DESIGN.md §5)")
+                        note="launches back to back on one stream over rotating images; peak is the driver's COPY "
+                             "bandwidth (read+write) - a read-only stream can exceed it (frac > 1 at 4096 masks, where "
+                             "the persistent kernel's 296 CTAs run 14 masks each)")
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle's torch port on a bounded sample -------------------------
     cpu_baseline = None

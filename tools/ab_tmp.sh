@@ -1,1 +1,4 @@
-python tools/profile_stage.py --latency --images 4 2>&1 | tail -4
+set -e
+python tools/profile_stage.py --images 3 > gpurun_out/prof_plain.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:lowres_pack_persistent -s 3 -c 1 -o gpurun_out/lowres_persistent_r2e -f python tools/profile_stage.py --images 3 > gpurun_out/prof_ncu.log 2>&1
+ls -la gpurun_out/*.ncu-rep
