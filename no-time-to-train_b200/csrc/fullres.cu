@@ -440,89 +440,97 @@ struct alignas(16) Up2Item {  // 32 bytes, written by the plan kernel
   int pad;
 };
 
-// One CTA.  Per strip of 1024 masks: thread per MASK resolves the geometry (as upsample_meta_kernel) and counts its
-// items, a block scan gives the item offsets, then thread per ITEM finds its mask by binary search over the offsets and
-// writes the item record — the dependent table reads of different items overlap instead of queueing in one thread.
-// ctr[0] = number of items, ctr[1] = next item to hand out (zeroed here for the main kernel).
-__global__ void __launch_bounds__(1024)
+// A few CTAs (gridDim.x = P), no table staging, no atomics.  Per strip of 1024 masks EVERY CTA resolves the geometry of
+// every mask of the strip (four per thread, all loads read-only so that they overlap) and runs the same block scan of the
+// item counts — a few hundred redundant table reads are cheaper than a cross-CTA scan or a counter that somebody has to
+// zero — and then writes its share of the item records (item e belongs to CTA e mod P ... in blocks of 256): thread per ITEM,
+// the mask found by binary search over the offsets.  CTA (k / 256) mod P owns the per-mask outputs (meta, rect, scratch).
+// The single-CTA form of this kernel spent 18 us on ~7 dependent access rounds of 1024 threads each; this one is a
+// handful of L2 round trips long.  ctr[0] = number of items, ctr[1] = next item to hand out (zeroed for the main kernel).
+constexpr int kPlanThreads = 256;
+constexpr int kPlanPerThread = 1024 / kPlanThreads;
+
+__global__ void __launch_bounds__(kPlanThreads)
 upsample_plan_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __restrict__ box_lr,
                      const int32_t* __restrict__ flags_lr, int ih, int iw, const int32_t* __restrict__ sel,
                      const int32_t* __restrict__ n_sel, int max_sel, UpTables t, UpMeta* __restrict__ meta,
                      int32_t* __restrict__ rect, int32_t* __restrict__ scratch, const float* __restrict__ logits,
                      const float* const* __restrict__ mask_ptr, Up2Item* __restrict__ items, int32_t* __restrict__ ctr,
-                     int32_t* __restrict__ area_full, int32_t* __restrict__ box_full, int oh, int ow, int tile_cap_floats,
-                     int stage_tables) {
-  extern __shared__ int32_t s_tab[];  // the span / group tables of both axes (stage_tables != 0)
-  __shared__ int s_warp[33];
+                     int32_t* __restrict__ area_full, int32_t* __restrict__ box_full, int oh, int ow, int tile_cap_floats) {
+  __shared__ int s_warp[kPlanThreads / 32 + 1];
   __shared__ int s_off[1024];   // exclusive item offset of each mask of the strip
   __shared__ int s_ccs[1024];   // column chunks of each mask (0: no items)
   __shared__ int4 s_geo[1024];  // {g0, g1, w0, w1} of each mask of the strip
   __shared__ int2 s_rows[1024]; // {r0, r1}
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // Every table lookup below sits on a chain of dependent accesses (sel -> box -> spans -> groups -> spans ...).  The
-  // tables are a few tens of KB: copy them into shared memory once, coalesced, and chase them there.
-  const int32_t *y_tlo = t.y_tlo, *y_tlen = t.y_tlen, *x_tlo = t.x_tlo, *x_tlen = t.x_tlen, *ymin = t.ymin,
-                *ysize = t.ysize, *y_grp_of = t.y_grp_of, *y_grp_start = t.y_grp_start, *xmin = t.xmin, *xsize = t.xsize;
-  if (stage_tables) {
-    int32_t* p = s_tab;
-    auto stage = [&](const int32_t*& src, int count) {
-      for (int i = tid; i < count; i += 1024) p[i] = src[i];
-      src = p;
-      p += count;
-    };
-    stage(y_tlo, ih); stage(y_tlen, ih); stage(x_tlo, iw); stage(x_tlen, iw);
-    stage(ymin, oh); stage(ysize, oh); stage(y_grp_of, oh); stage(y_grp_start, oh + 1);
-    stage(xmin, ow); stage(xsize, ow);
-    __syncthreads();
-  }
-  const int n = min(*n_sel, max_sel);
+  const int n = min(__ldg(n_sel), max_sel);
+  const int words_lr = ih * (iw >> 5);
   int base = 0;
   for (int k0 = 0; k0 < max_sel; k0 += 1024) {
-    const int k = k0 + tid;
-    int n_items = 0, ccs = 0;
-    int4 geo = make_int4(0, 0, 0, 0);
-    int2 rows = make_int2(0, 0);
-    if (k < max_sel) {
+    // ---- geometry of masks k0 + tid * kPlanPerThread + q (consecutive masks per thread: the scan below is then a
+    //      thread-local prefix + one block scan of the thread totals)
+    int cnt[kPlanPerThread];
+    int thread_items = 0;
 #pragma unroll
-      for (int q = 0; q < kScratchInts; ++q) scratch[(size_t)k * kScratchInts + q] = 0;
-    }
-    if (k < n) {
-      UpMeta m;
-      m.r0 = m.r1 = m.w0 = m.w1 = m.lr0 = m.lr1 = m.g0 = m.g1 = 0;
-      m.src = sel[k];
-      m.logits = mask_ptr ? mask_ptr[m.src] : logits + (size_t)m.src * ih * iw;
-      const int4 b = reinterpret_cast<const int4*>(box_lr)[m.src];
-      const bool lr_empty = (b.x | b.y | b.z | b.w) == 0 && (bits_lr[(size_t)m.src * ih * (iw >> 5)] & 1u) == 0;
-      if (!lr_empty) {
-        m.r0 = y_tlo[b.y];
-        m.r1 = y_tlo[b.w] + y_tlen[b.w];
-        const int c0 = x_tlo[b.x];
-        const int c1 = x_tlo[b.z] + x_tlen[b.z];
-        m.w0 = c0 >> 5;
-        m.w1 = (c1 + 31) >> 5;
-        if (m.r1 > m.r0) {
-          m.lr0 = ymin[m.r0];
-          m.lr1 = ymin[m.r1 - 1] + ysize[m.r1 - 1];
-          m.g0 = y_grp_of[m.r0];
-          m.g1 = y_grp_of[m.r1 - 1] + 1;
+    for (int q = 0; q < kPlanPerThread; ++q) {
+      const int idx = tid * kPlanPerThread + q;
+      const int k = k0 + idx;
+      const bool owner = ((k >> 8) % gridDim.x) == blockIdx.x;
+      int n_items = 0, ccs = 0;
+      int4 geo = make_int4(0, 0, 0, 0);
+      int2 rows = make_int2(0, 0);
+      if (k < max_sel && owner) {
+#pragma unroll
+        for (int z = 0; z < kScratchInts; ++z) scratch[(size_t)k * kScratchInts + z] = 0;
+      }
+      if (k < n) {
+        UpMeta m;
+        m.r0 = m.r1 = m.w0 = m.w1 = m.lr0 = m.lr1 = m.g0 = m.g1 = 0;
+        m.src = __ldg(sel + k);
+        m.logits = mask_ptr ? mask_ptr[m.src] : logits + (size_t)m.src * ih * iw;
+        const int4 b = __ldg(reinterpret_cast<const int4*>(box_lr) + m.src);
+        const bool lr_empty = (b.x | b.y | b.z | b.w) == 0 && (__ldg(bits_lr + (size_t)m.src * words_lr) & 1u) == 0;
+        if (!lr_empty) {
+          m.r0 = __ldg(t.y_tlo + b.y);
+          m.r1 = __ldg(t.y_tlo + b.w) + __ldg(t.y_tlen + b.w);
+          const int c0 = __ldg(t.x_tlo + b.x);
+          const int c1 = __ldg(t.x_tlo + b.z) + __ldg(t.x_tlen + b.z);
+          m.w0 = c0 >> 5;
+          m.w1 = (c1 + 31) >> 5;
+          if (m.r1 > m.r0) {
+            m.lr0 = __ldg(t.ymin + m.r0);
+            m.lr1 = __ldg(t.ymin + m.r1 - 1) + __ldg(t.ysize + m.r1 - 1);
+            m.g0 = __ldg(t.y_grp_of + m.r0);
+            m.g1 = __ldg(t.y_grp_of + m.r1 - 1) + 1;
+          }
+        }
+        m.safe = __ldg(flags_lr + m.src) & 1;
+        geo = make_int4(m.g0, m.g1, m.w0, m.w1);
+        rows = make_int2(m.r0, m.r1);
+        const bool has = m.r1 > m.r0 && m.w1 > m.w0;
+        if (has) {
+          ccs = (m.w1 - m.w0 + kUp2Cols - 1) / kUp2Cols;
+          n_items = ((m.g1 - m.g0 + kUp2Groups - 1) / kUp2Groups) * ccs;
+        }
+        if (owner) {
+          meta[k] = m;
+          reinterpret_cast<int4*>(rect)[k] = make_int4(m.r0, m.r1, m.w0, m.w1);
+          if (has) {
+            scratch[(size_t)k * kScratchInts + 6] = n_items;
+          } else {  // nothing to compute: publish the empty result here
+            area_full[k] = 0;
+            reinterpret_cast<int4*>(box_full)[k] = make_int4(0, 0, 0, 0);
+          }
         }
       }
-      m.safe = flags_lr[m.src] & 1;
-      meta[k] = m;
-      reinterpret_cast<int4*>(rect)[k] = make_int4(m.r0, m.r1, m.w0, m.w1);
-      geo = make_int4(m.g0, m.g1, m.w0, m.w1);
-      rows = make_int2(m.r0, m.r1);
-      if (m.r1 > m.r0 && m.w1 > m.w0) {
-        ccs = (m.w1 - m.w0 + kUp2Cols - 1) / kUp2Cols;
-        n_items = ((m.g1 - m.g0 + kUp2Groups - 1) / kUp2Groups) * ccs;
-        scratch[(size_t)k * kScratchInts + 6] = n_items;
-      } else {  // nothing to compute: publish the empty result here
-        area_full[k] = 0;
-        reinterpret_cast<int4*>(box_full)[k] = make_int4(0, 0, 0, 0);
-      }
+      cnt[q] = n_items;
+      thread_items += n_items;
+      s_ccs[idx] = ccs;
+      s_geo[idx] = geo;
+      s_rows[idx] = rows;
     }
-    // exclusive scan of n_items over the strip
-    int inc = n_items;
+    // ---- exclusive scan of the item counts over the strip
+    int inc = thread_items;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int up = __shfl_up_sync(kFull, inc, o);
@@ -531,24 +539,30 @@ upsample_plan_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-      const int w = s_warp[lane];
+      const int w = lane < kPlanThreads / 32 ? s_warp[lane] : 0;
       int winc = w;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int up = __shfl_up_sync(kFull, winc, o);
         if (lane >= o) winc += up;
       }
-      s_warp[lane] = winc - w;
-      if (lane == 31) s_warp[32] = winc;
+      __syncwarp();
+      if (lane < kPlanThreads / 32) s_warp[lane] = winc - w;
+      if (lane == 31) s_warp[kPlanThreads / 32] = winc;
     }
     __syncthreads();
-    s_off[tid] = s_warp[warp] + inc - n_items;
-    s_ccs[tid] = ccs;
-    s_geo[tid] = geo;
-    s_rows[tid] = rows;
+    {
+      int off = s_warp[warp] + inc - thread_items;
+#pragma unroll
+      for (int q = 0; q < kPlanPerThread; ++q) {
+        s_off[tid * kPlanPerThread + q] = off;
+        off += cnt[q];
+      }
+    }
     __syncthreads();
-    const int strip_items = s_warp[32];
-    for (int e = tid; e < strip_items; e += 1024) {
+    const int strip_items = s_warp[kPlanThreads / 32];
+    // ---- item records: blocks of kPlanThreads consecutive items go round-robin over the CTAs
+    for (int e = blockIdx.x * kPlanThreads + tid; e < strip_items; e += gridDim.x * kPlanThreads) {
       // last mask of the strip whose offset is <= e: masks without items share the offset of their successor, so the
       // LAST of equal offsets is the one that owns the item
       int lo = 0, hi = 1023;
@@ -562,11 +576,11 @@ upsample_plan_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
       const int rc = i / cc_n, cc = i - rc * cc_n;
       const int gA = g.x + rc * kUp2Groups, gB = min(gA + kUp2Groups, g.y);
       const int wA = g.z + cc * kUp2Cols, wB = min(wA + kUp2Cols, g.w);
-      const int ya = min(max(y_grp_start[gA], r.x), r.y), yb = min(max(y_grp_start[gB], r.x), r.y);
-      const int l0 = ymin[ya], l1 = ymin[yb - 1] + ysize[yb - 1];
+      const int ya = min(max(__ldg(t.y_grp_start + gA), r.x), r.y), yb = min(max(__ldg(t.y_grp_start + gB), r.x), r.y);
+      const int l0 = __ldg(t.ymin + ya), l1 = __ldg(t.ymin + yb - 1) + __ldg(t.ysize + yb - 1);
       const int xa = min(wA << 5, ow - 1), xb = min((wB << 5) - 1, ow - 1);
-      const int tc0 = xmin[xa] & ~3;
-      const int tstride = min((xmin[xb] + xsize[xb] + 3) & ~3, iw) - tc0;
+      const int tc0 = __ldg(t.xmin + xa) & ~3;
+      const int tstride = min((__ldg(t.xmin + xb) + __ldg(t.xsize + xb) + 3) & ~3, iw) - tc0;
       Up2Item it;
       it.k = k0 + lo;
       it.g = gA | ((gB - gA) << 16);
@@ -579,9 +593,9 @@ upsample_plan_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
       items[base + e] = it;
     }
     base += strip_items;
-    __syncthreads();
+    __syncthreads();  // the strip's shared arrays are rewritten by the next strip
   }
-  if (tid == 0) { ctr[0] = base; ctr[1] = 0; }
+  if (blockIdx.x == 0 && tid == 0) { ctr[0] = base; ctr[1] = 0; }
 }
 
 // 16-byte copy that allocates in L1: the pk_x / pk_y tables are a few KB shared by every item an SM processes
@@ -918,14 +932,10 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
     tile_floats = (tile_floats + 3) & ~3;
     const size_t smem = up2_fixed_smem(ih, iw) + (size_t)tile_floats * 4;
     if (smem > 200 * 1024) return NTTT_EUNSUPPORTED;
-    size_t tab_bytes = sizeof(int32_t) * (size_t)(2 * ih + 2 * iw + 4 * oh + 1 + 2 * ow);
-    const int stage_tables = tab_bytes <= 96 * 1024;
-    if (!stage_tables) tab_bytes = 0;
-    if (tab_bytes > 0)  // (the kernel also holds 33 KB of static shared memory: opt in to more than 48 KB in total)
-      NTTT_CUDA(set_dyn_smem(upsample_plan_kernel, (int)tab_bytes));
-    upsample_plan_kernel<<<1, 1024, tab_bytes, s>>>(bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, t, meta, rect,
+    // (eight CTAs: the geometry pass is redundant per CTA, the item records are shared out)
+    upsample_plan_kernel<<<8, kPlanThreads, 0, s>>>(bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, t, meta, rect,
                                                     scratch, logits, mask_ptr, items, ctr, area_full, box_full, oh, ow,
-                                                    tile_floats, stage_tables);
+                                                    tile_floats);
     NTTT_LAUNCH_CHECK();
     if (smem > 48 * 1024)
       NTTT_CUDA(set_dyn_smem(upsample_pack2_kernel, (int)smem));

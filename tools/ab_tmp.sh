@@ -1,4 +1,8 @@
-set -e
-python tools/profile_stage.py --images 3 > gpurun_out/prof_plain.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:lowres_pack_persistent -s 3 -c 1 -o gpurun_out/lowres_persistent_r2e -f python tools/profile_stage.py --images 3 > gpurun_out/prof_ncu.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python tools/profile_stage.py --latency --images 4 2>&1 | tail -3
+python bench.py --value-only 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value us/img', round(1e6/d['value'],2), d['clocks']['sm_mhz'])"
+python bench.py --value-only --n-masks 4096 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('cfg5 us/img', round(1e6/d['value'],2), d['clocks']['sm_mhz'])"

@@ -16,8 +16,10 @@ def main():
     ap.add_argument("report")
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--file", default=None, help="only lines of source files whose path contains this")
+    ap.add_argument("--kernel", default=None, help="only launches of this kernel (ncu -k)")
     args = ap.parse_args()
-    txt = subprocess.run(["ncu", "-i", args.report, "--page", "source", "--print-source", "cuda,sass", "--csv"],
+    txt = subprocess.run(["ncu", "-i", args.report, "--page", "source", "--print-source", "cuda,sass", "--csv"] +
+                         (["-k", args.kernel] if args.kernel else []),
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     cur_file, hdr, lines, launches = None, None, {}, 0
