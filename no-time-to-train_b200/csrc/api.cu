@@ -118,11 +118,11 @@ constexpr int kPoolSplits = 1;  // measured: 2 halves the latency (25 -> 14 us) 
 // is the duration of each kernel, so the pooling GEMM spreads over twice the SMs (128 x 128 tiles, split-K 2: 14 us
 // instead of 25-38 us).
 static int pool_contract(const float* proj, const float* feat, int n, int e, int c, float* sums, void* a_split,
-                         void* b_split, int* n_partials, cudaStream_t s, bool low_latency = false) {
+                         void* b_split, int* n_partials, cudaStream_t s, bool low_latency = false, bool b_ready = false) {
   const int ep = pad64(e);
   int err = proj ? launch_split_rows(proj, e, n, e, ep, 0, a_split, s) : NTTT_OK;
   if (err) return err;
-  err = launch_split_transpose(feat, c, c, e, ep, 1, b_split, s);
+  err = b_ready ? NTTT_OK : launch_split_transpose(feat, c, c, e, ep, 1, b_split, s);  // (b_ready: done on the side stream)
   if (err) return err;
   return launch_gemm_tc(a_split, 3 * ep, b_split, 3 * ep, sums, c, n, c, 3 * ep, low_latency ? kPoolSplitsMax : kPoolSplits,
                         (size_t)n * c, n_partials, s, low_latency);
@@ -161,11 +161,15 @@ static size_t sim_partial_floats(int n, int cols, int c) {
 // class-level average, proto_neg [n_cls * l_neg, c] the normalised negative instance averages.
 static int sim_top1(const float* obj_feats, const float* proto, const float* proto_neg, int l_neg, float sigma, int n,
                     int c, int n_cls, float* sim, float* partials, float* partials_neg, float* top_score,
-                    int32_t* top_label, void* a_split, void* b_split, bool a_ready, int sm_count, cudaStream_t s) {
+                    int32_t* top_label, void* a_split, void* b_split, bool a_ready, int sm_count, cudaStream_t s,
+                    void* p_split = nullptr, bool p_ready = false) {
+  // p_split (nullable): a buffer of its own for the split prototypes, so that they can be prepared before b_split is free
+  // (p_ready: already done, on the side stream of the low-latency mode); without it they go through b_split
   const int cp = pad64(c);
   int err = a_ready ? NTTT_OK : launch_split_rows(obj_feats, c, n, c, cp, 0, a_split, s);
   if (err) return err;
-  err = launch_split_rows(proto, c, n_cls, c, cp, 1, b_split, s);
+  void* pb = p_split ? p_split : b_split;
+  err = p_ready ? NTTT_OK : launch_split_rows(proto, c, n_cls, c, cp, 1, pb, s);
   if (err) return err;
   int want = gemm_tc_pick_splits(n, n_cls, 3 * cp, sm_count < 148 ? sm_count : 148);
   if (want > kMaxSimSplits) want = kMaxSimSplits;
@@ -174,7 +178,7 @@ static int sim_top1(const float* obj_feats, const float* proto, const float* pro
   if (!t_low_latency) want = 1;
   const size_t stride = (size_t)n * n_cls;
   int splits = 1;
-  err = launch_gemm_tc(a_split, 3 * cp, b_split, 3 * cp, partials, n_cls, n, n_cls, 3 * cp, want, stride, &splits, s);
+  err = launch_gemm_tc(a_split, 3 * cp, pb, 3 * cp, partials, n_cls, n, n_cls, 3 * cp, want, stride, &splits, s);
   if (err) return err;
   if (!proto_neg) return launch_top1(partials, splits, stride, sim, n_cls, n, n_cls, top_score, top_label, s);
   const int cols = n_cls * l_neg;
@@ -367,6 +371,9 @@ int nttt_ctx_create(nttt_ctx** out, int device) {
 
 void nttt_ctx_destroy(nttt_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   for (int i = 0; i < ctx->n_tables; ++i) free_axis_table(ctx->tables[i]);
   for (int i = 0; i < ctx->n_retired; ++i) free_axis_table(ctx->retired[i]);
   if (ctx->scratch) cudaFree(ctx->scratch);
@@ -683,7 +690,7 @@ int nttt_fill_finalize(const float* sum, const float* wsum, int n_cls, int shots
 struct MatchLayout {
   uint32_t* bits_lr; int32_t* area_lr; int32_t* box_lr; int32_t* stab; int32_t* flags;
   float* proj; float* sums; float* obj_feats; float* sim; float* sim_part; float* sim_part_neg; float* top_score; int32_t* top_label;
-  char* a_split; char* b_split;
+  char* a_split; char* b_split; char* p_split;
   void* nms_ws; size_t nms_ws_bytes; int32_t* keep; int32_t* sel;
   uint32_t* bits_full; uint32_t* bits_t; int32_t* rect; int32_t* area_full; int32_t* box_full; int32_t* scratch;
   float* ios; void* ios_ws; int32_t* out_slot;
@@ -713,6 +720,7 @@ static MatchLayout carve(void* ws, int n, int lr_h, int lr_w, int eh, int ew, in
     if ((size_t)n_cls * (l_neg > 0 ? l_neg : 0) > rows_b) rows_b = (size_t)n_cls * l_neg;
     L.a_split = cv.take<char>(2 * (size_t)n * kmax);
     L.b_split = cv.take<char>(2 * rows_b * kmax);
+    L.p_split = cv.take<char>(2 * (size_t)n_cls * 3 * pad64(c));  // split prototypes (prepared off the critical path)
   }
   L.top_score = cv.take<float>(n);
   L.top_label = cv.take<int32_t>(n);
@@ -830,6 +838,18 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
     pred_ious = L.plane_score;
   }
   NTTT_MARK();
+  // low-latency mode: the two operand preparations that do not depend on the masks (features -> transposed split
+  // operand, prototypes -> split operand) run on the context's side stream while the main stream reads the logits
+  const bool forked = a->low_latency != 0 && ctx->side_ready();
+  if (forked) {
+    NTTT_CUDA(cudaEventRecord(ctx->ev_fork, s));
+    NTTT_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    err = launch_split_transpose(a->tar_feat, a->c, a->c, e, pad64(e), 1, L.b_split, ctx->side);
+    if (err) return err;
+    err = launch_split_rows(a->proto, a->c, a->n_cls, a->c, pad64(a->c), 1, L.p_split, ctx->side);
+    if (err) return err;
+    NTTT_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+  }
   // a6/a9/a15: one pass over the logits
   // (the stability counts of a15 are not read on this path, so the pipeline does not pay for them)
   NTTT_STEP(launch_lowres_pack(a->logits, n, a->lr_h, a->lr_w, 0.0f, 1.0f, L.bits_lr, L.area_lr, L.box_lr, nullptr,
@@ -839,14 +859,16 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   NTTT_STEP(launch_project_masks(px, py, L.bits_lr, L.box_lr, n, a->lr_h, a->lr_w, a->eh, a->ew, L.a_split, pad64(e),
                                  true, s));
   int n_partials = 1;
+  if (forked) NTTT_CUDA(cudaStreamWaitEvent(s, ctx->ev_join, 0));
   NTTT_STEP(pool_contract(nullptr, a->tar_feat, n, e, a->c, L.sums, L.a_split, L.b_split, &n_partials, s,
-                          a->low_latency != 0));
+                          a->low_latency != 0, forked));
   bool a_ready = false;
   NTTT_STEP(normalize_rows(L.sums, n_partials, L.area_lr, n, a->c, obj_feats, L.a_split, &a_ready,
                            a->proto_neg != nullptr, s));
   // a7/a8: similarity + top-1
   NTTT_STEP(sim_top1(obj_feats, a->proto, a->proto_neg, l_neg, a->sigma, n, a->c, a->n_cls, a->sim, L.sim_part,
-                     L.sim_part_neg, L.top_score, L.top_label, L.a_split, L.b_split, a_ready, ctx->sm_count, s));
+                     L.sim_part_neg, L.top_score, L.top_label, L.a_split, L.b_split, a_ready, ctx->sm_count, s, L.p_split,
+                     forked));
   // a10/a11
   NTTT_STEP(launch_box_nms(L.box_lr, pred_ious, L.top_label, L.top_score, n, a->nms_thr, max_sel, L.keep,
                            a->counts + 0, L.sel, a->counts + 1, L.nms_ws, L.nms_ws_bytes, a->iou_thr, a->filter_iou, s));

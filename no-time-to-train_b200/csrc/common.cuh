@@ -166,6 +166,20 @@ struct nttt_ctx {
   int stop_after = 0;  // debugging/profiling: stop nttt_match_image after this many stages (0 = run all)
   cudaEvent_t ev[kMaxStages + 1] = {};
   int n_ev = 0;
+  // side stream of the low-latency mode (created on first use; the context is not thread-safe, see the header)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool side_ready() {
+    if (side) return true;
+    if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) { side = nullptr; return false; }
+    if (cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaStreamDestroy(side);
+      side = nullptr;
+      return false;
+    }
+    return true;
+  }
   // returns the table BY VALUE (device pointers stay valid until evicted by a later call)
   int axis(int in_size, int out_size, cudaStream_t s, nttt::AxisTable* out);
 };

@@ -96,6 +96,87 @@ ios_pairs_kernel(const IosMeta* __restrict__ meta, const int32_t* __restrict__ l
   }
 }
 
+// Pairs with a LARGE overlap window (> kIosBigWords words): one CTA per pair (grid-stride over the big list, which
+// grows from the back of the pair buffer): the window is spread over all threads with four load pairs in flight,
+// one block reduction.  A single warp would take tens of microseconds on a 1000 x 32-word window.  Runs as the tail of
+// ios_eval_kernel (every thread of the CTA arrives here): the list is usually empty, and a launch of its own put ~4 us of
+// launch latency on the chain of a single image.
+__device__ __forceinline__ void
+ios_eval_big_pairs(const uint32_t* __restrict__ bits_full, const uint32_t* __restrict__ bits_t,
+                const IosMeta* __restrict__ meta,
+                const int2* __restrict__ pairs, const int32_t* __restrict__ n_pairs, int max_pairs, int max_sel, int oh,
+                int ow, const float* __restrict__ obj_feats, int c, float* __restrict__ ios,
+                int32_t* __restrict__ inter_out) {
+  __shared__ int s_inter[kIosThreads / 32];
+  __shared__ float s_dot[kIosThreads / 32];
+  const int lane = lane_id(), warp = warp_id();
+  constexpr int kWarps = kIosThreads / 32;
+  const int ow_words = (ow + 31) >> 5;
+  const int np = min(n_pairs[1], max_pairs);
+  for (int p = blockIdx.x; p < np; p += gridDim.x) {
+    const int2 pr = pairs[max_pairs - 1 - p];
+    const int i = pr.x, j = pr.y;
+    const IosMeta me = meta[i], mj = meta[j];
+    const int x0 = max(me.box.x, mj.box.x), x1 = min(me.box.z, mj.box.z);
+    const int y0 = max(me.box.y, mj.box.y), y1 = min(me.box.w, mj.box.w);
+    const int wlo = max(max(me.rect.z, mj.rect.z), x0 >> 5), whi = min(min(me.rect.w, mj.rect.w), (x1 >> 5) + 1);
+    const int ylo = max(max(me.rect.x, mj.rect.x), y0), yhi = min(min(me.rect.y, mj.rect.y), y1 + 1);
+    const int nw = whi - wlo;
+    const bool tr = bits_t != nullptr;  // word-column-major copy: word (y, w) at w * oh + y
+    const uint32_t* mi = (tr ? bits_t : bits_full) + (size_t)i * oh * ow_words;
+    const uint32_t* pj = (tr ? bits_t : bits_full) + (size_t)j * oh * ow_words;
+    const size_t sy = tr ? 1 : (size_t)ow_words, sw = tr ? (size_t)oh : 1;
+    int inter = 0;
+    if (nw > 0 && yhi > ylo) {
+      // threads tile the window: tx over words (next pow2 >= nw, <= 32), ty over rows
+      int txn = 1;
+      while (txn < nw && txn < 32) txn <<= 1;
+      const int tx = threadIdx.x & (txn - 1), ty = threadIdx.x / txn, tyn = kIosThreads / txn;
+      for (int w = wlo + tx; w < whi; w += txn) {
+        int y = ylo + ty;
+        for (; y + 3 * tyn < yhi; y += 4 * tyn) {
+          const size_t o0 = (size_t)y * sy + (size_t)w * sw, o1 = o0 + (size_t)tyn * sy;
+          const size_t o2 = o1 + (size_t)tyn * sy, o3 = o2 + (size_t)tyn * sy;
+          const uint32_t a0 = __ldg(mi + o0), b0 = __ldg(pj + o0), a1 = __ldg(mi + o1), b1 = __ldg(pj + o1);
+          const uint32_t a2 = __ldg(mi + o2), b2 = __ldg(pj + o2), a3 = __ldg(mi + o3), b3 = __ldg(pj + o3);
+          inter += __popc(a0 & b0) + __popc(a1 & b1) + __popc(a2 & b2) + __popc(a3 & b3);
+        }
+        for (; y < yhi; y += tyn) {
+          const size_t o = (size_t)y * sy + (size_t)w * sw;
+          inter += __popc(__ldg(mi + o) & __ldg(pj + o));
+        }
+      }
+    }
+    const float* fi = obj_feats + (size_t)me.src * c;
+    const float* fj = obj_feats + (size_t)mj.src * c;
+    float dot = 0.0f;
+    for (int e = threadIdx.x; e < c; e += kIosThreads) dot = fmaf(__ldg(fi + e), __ldg(fj + e), dot);
+    inter = warp_sum(inter);
+    dot = warp_sum(dot);
+    if (lane == 0) { s_inter[warp] = inter; s_dot[warp] = dot; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int it = 0;
+      float dt = 0.0f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) { it += s_inter[w]; dt += s_dot[w]; }
+      if (inter_out) {
+        inter_out[(size_t)i * max_sel + j] = it;
+        inter_out[(size_t)j * max_sel + i] = it;
+      }
+      if (it > 0) {
+        const float sim = fmaxf(dt, 0.0f);
+        // ((inter * s) / area) * s  — the reference's association, for both rows of the pair; all values are
+        // >= 0, so the row max is an integer atomicMax on the float bits
+        const float num = __fmul_rn((float)it, sim);
+        atomicMax(reinterpret_cast<int*>(ios + i), __float_as_int(__fmul_rn(__fdiv_rn(num, (float)me.area), sim)));
+        atomicMax(reinterpret_cast<int*>(ios + j), __float_as_int(__fmul_rn(__fdiv_rn(num, (float)mj.area), sim)));
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Pair evaluation: one WARP per pair (warp-stride over the list): popcount of the AND over the overlap window and the
 // feature dot product, both reduced with shuffles — no shared memory, no CTA barrier.  (One CTA per pair spent most of
 // its instructions on per-thread set-up and the block reduction: a typical window is ~150 words.)  A window is walked
@@ -190,85 +271,7 @@ ios_eval_kernel(const uint32_t* __restrict__ bits_full, const uint32_t* __restri
       }
     }
   }
-}
-
-// Pairs with a LARGE overlap window (> kIosBigWords words): one CTA per pair (grid-stride over the big list, which
-// grows from the back of the pair buffer): the window is spread over all threads with four load pairs in flight,
-// one block reduction.  A single warp would take tens of microseconds on a 1000 x 32-word window.
-__global__ void __launch_bounds__(kIosThreads)
-ios_eval_big_kernel(const uint32_t* __restrict__ bits_full, const uint32_t* __restrict__ bits_t,
-                const IosMeta* __restrict__ meta,
-                const int2* __restrict__ pairs, const int32_t* __restrict__ n_pairs, int max_pairs, int max_sel, int oh,
-                int ow, const float* __restrict__ obj_feats, int c, float* __restrict__ ios,
-                int32_t* __restrict__ inter_out) {
-  __shared__ int s_inter[kIosThreads / 32];
-  __shared__ float s_dot[kIosThreads / 32];
-  const int lane = lane_id(), warp = warp_id();
-  constexpr int kWarps = kIosThreads / 32;
-  const int ow_words = (ow + 31) >> 5;
-  const int np = min(n_pairs[1], max_pairs);
-  for (int p = blockIdx.x; p < np; p += gridDim.x) {
-    const int2 pr = pairs[max_pairs - 1 - p];
-    const int i = pr.x, j = pr.y;
-    const IosMeta me = meta[i], mj = meta[j];
-    const int x0 = max(me.box.x, mj.box.x), x1 = min(me.box.z, mj.box.z);
-    const int y0 = max(me.box.y, mj.box.y), y1 = min(me.box.w, mj.box.w);
-    const int wlo = max(max(me.rect.z, mj.rect.z), x0 >> 5), whi = min(min(me.rect.w, mj.rect.w), (x1 >> 5) + 1);
-    const int ylo = max(max(me.rect.x, mj.rect.x), y0), yhi = min(min(me.rect.y, mj.rect.y), y1 + 1);
-    const int nw = whi - wlo;
-    const bool tr = bits_t != nullptr;  // word-column-major copy: word (y, w) at w * oh + y
-    const uint32_t* mi = (tr ? bits_t : bits_full) + (size_t)i * oh * ow_words;
-    const uint32_t* pj = (tr ? bits_t : bits_full) + (size_t)j * oh * ow_words;
-    const size_t sy = tr ? 1 : (size_t)ow_words, sw = tr ? (size_t)oh : 1;
-    int inter = 0;
-    if (nw > 0 && yhi > ylo) {
-      // threads tile the window: tx over words (next pow2 >= nw, <= 32), ty over rows
-      int txn = 1;
-      while (txn < nw && txn < 32) txn <<= 1;
-      const int tx = threadIdx.x & (txn - 1), ty = threadIdx.x / txn, tyn = kIosThreads / txn;
-      for (int w = wlo + tx; w < whi; w += txn) {
-        int y = ylo + ty;
-        for (; y + 3 * tyn < yhi; y += 4 * tyn) {
-          const size_t o0 = (size_t)y * sy + (size_t)w * sw, o1 = o0 + (size_t)tyn * sy;
-          const size_t o2 = o1 + (size_t)tyn * sy, o3 = o2 + (size_t)tyn * sy;
-          const uint32_t a0 = __ldg(mi + o0), b0 = __ldg(pj + o0), a1 = __ldg(mi + o1), b1 = __ldg(pj + o1);
-          const uint32_t a2 = __ldg(mi + o2), b2 = __ldg(pj + o2), a3 = __ldg(mi + o3), b3 = __ldg(pj + o3);
-          inter += __popc(a0 & b0) + __popc(a1 & b1) + __popc(a2 & b2) + __popc(a3 & b3);
-        }
-        for (; y < yhi; y += tyn) {
-          const size_t o = (size_t)y * sy + (size_t)w * sw;
-          inter += __popc(__ldg(mi + o) & __ldg(pj + o));
-        }
-      }
-    }
-    const float* fi = obj_feats + (size_t)me.src * c;
-    const float* fj = obj_feats + (size_t)mj.src * c;
-    float dot = 0.0f;
-    for (int e = threadIdx.x; e < c; e += kIosThreads) dot = fmaf(__ldg(fi + e), __ldg(fj + e), dot);
-    inter = warp_sum(inter);
-    dot = warp_sum(dot);
-    if (lane == 0) { s_inter[warp] = inter; s_dot[warp] = dot; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int it = 0;
-      float dt = 0.0f;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) { it += s_inter[w]; dt += s_dot[w]; }
-      if (inter_out) {
-        inter_out[(size_t)i * max_sel + j] = it;
-        inter_out[(size_t)j * max_sel + i] = it;
-      }
-      if (it > 0) {
-        const float sim = fmaxf(dt, 0.0f);
-        // ((inter * s) / area) * s  — the reference's association, for both rows of the pair; all values are
-        // >= 0, so the row max is an integer atomicMax on the float bits
-        const float num = __fmul_rn((float)it, sim);
-        atomicMax(reinterpret_cast<int*>(ios + i), __float_as_int(__fmul_rn(__fdiv_rn(num, (float)me.area), sim)));
-        atomicMax(reinterpret_cast<int*>(ios + j), __float_as_int(__fmul_rn(__fdiv_rn(num, (float)mj.area), sim)));
-      }
-    }
-    __syncthreads();
-  }
+  ios_eval_big_pairs(bits_full, bits_t, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats, c, ios, inter_out);
 }
 
 // rows of empty full-res masks: 0/0 on the diagonal -> NaN, and torch.max propagates it
@@ -308,10 +311,6 @@ int launch_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_
   // one CTA per SM when many images are in flight (measured 89.4 vs 90.0 us/image with four), four for one image alone
   ios_eval_kernel<<<g_exp[0] > 0 ? g_exp[0] : (t_low_latency ? 148 * 4 : 148), kIosThreads, 0, s>>>(bits_full, bits_t, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats,
                                                   c, ios, inter_out);
-  NTTT_LAUNCH_CHECK();
-  if (ios_stop == 3) return NTTT_OK;
-  ios_eval_big_kernel<<<g_exp[1] > 0 ? g_exp[1] : 148, kIosThreads, 0, s>>>(bits_full, bits_t, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats, c,
-                                                  ios, inter_out);
   NTTT_LAUNCH_CHECK();
   if (finalize) {
     ios_finalize_kernel<<<ceil_div(max_sel, 256), 256, 0, s>>>(area_full, n_sel, max_sel, ios);
