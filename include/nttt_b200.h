@@ -76,10 +76,16 @@ void nttt_ctx_destroy(nttt_ctx* ctx);
  *                                   different order — float results may differ in the last bit).  Measured equal in
  *                                   throughput: the kernel is bound by its SM's tensor pipe.  Process-wide.
  *   NTTT_TUNE_GEMM_BN256_STAGES     2..4 (default 3): TMA ring depth of the 128 x 256 pooling GEMM (48 KB per stage); fewer
- *                                   stages leave shared memory to co-resident CTAs of other kernels.  Process-wide. */
+ *                                   stages leave shared memory to co-resident CTAs of other kernels.  Process-wide.
+ *   NTTT_TUNE_UPSAMPLE_CTAS_PER_SM  1..7 (default 1): persistent CTAs per SM of the full-resolution resize when many images
+ *                                   are in flight (low-latency mode always uses 7).  Measured 89.8 (1) / 90.7 (2) / 91.2 (3) /
+ *                                   91.9 (7) us/image.  Process-wide.
+ *   NTTT_TUNE_EXPERIMENT + i        (i = 0..7) launch-shape experiment slots used by tools/ and `bench.py --tune expI=V`
+ *                                   for A/B runs (grid sizes of single kernels, programmatic dependent launch off);
+ *                                   0 = the built-in default.  Results never depend on them. */
 enum { NTTT_TUNE_UPSAMPLE_STAGE_BYTES = 1, NTTT_TUNE_LOWRES_EXTRA_SMEM = 2, NTTT_TUNE_GEMM_BN256_MIN_M = 3,
        NTTT_TUNE_AXIS_CACHE_ENTRIES = 4, NTTT_TUNE_LOWRES_PERSISTENT = 5, NTTT_TUNE_GEMM_SHARED_SEGMENTS = 6,
-       NTTT_TUNE_GEMM_BN256_STAGES = 7 };
+       NTTT_TUNE_GEMM_BN256_STAGES = 7, NTTT_TUNE_UPSAMPLE_CTAS_PER_SM = 8, NTTT_TUNE_EXPERIMENT = 100 };
 int nttt_ctx_tune(nttt_ctx* ctx, int what, long long value);
 
 /* number of kernels this library has launched in this process (bench.py's `gpu_launches`) */
@@ -352,12 +358,15 @@ typedef struct nttt_match_args {
   int32_t* rle_n_chars;
   int32_t rle_cap_counts;
   int32_t rle_cap_chars;
-  /* scheduling hint: 0 = throughput (many images in flight: every kernel is shaped for the least SM-time),
+  /* scheduling hint: 0 = throughput (many images in flight on several streams: every kernel takes the launch shape that
+   * costs the least SM-time — thin persistent grids of one or two CTAs per SM, no split-K — so that the kernels of
+   * different images overlap: 83 us/image at 16 in flight, 330 us for one image alone);
    * 1 = low latency (one image at a time with a host synchronisation behind it, as the reference's bs=1 driver does,
-   * pl_wrapper/sam2matcher_pl.py:178-191: kernels are shaped for the shortest duration — the pooling GEMM runs
-   * split-K over twice the SMs).  The two modes add the fp32 partial sums of the pooling contraction in a different
-   * order: pooled features / similarities may differ in the last bit (far inside the 1e-3 bound); every integer
-   * result (masks, boxes, counts, keep lists) is computed identically. */
+   * pl_wrapper/sam2matcher_pl.py:178-191: wide grids, split-K GEMMs, the mask-independent operand preparation forked
+   * onto a side stream of the context, programmatic dependent launch along the kernel chain: 204 us for one image).
+   * The two modes add the fp32 partial sums of the two contractions in a different order: pooled features /
+   * similarities may differ in the last bit (far inside the 1e-3 bound); every integer result (masks, boxes, counts,
+   * keep lists) is computed identically. */
   int32_t low_latency;
 } nttt_match_args;
 

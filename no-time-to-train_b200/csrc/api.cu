@@ -284,7 +284,7 @@ int nttt_ctx_tune(nttt_ctx* ctx, int what, long long value) {
       if (value < 2 || value > 4) return NTTT_EINVAL;
       nttt::g_gemm_bn256_stages = (int)value;
       return NTTT_OK;
-    case 8:
+    case NTTT_TUNE_UPSAMPLE_CTAS_PER_SM:
       if (value < 1 || value > 7) return NTTT_EINVAL;
       nttt::g_up2_ctas_per_sm = (int)value;
       return NTTT_OK;
@@ -301,8 +301,8 @@ int nttt_ctx_tune(nttt_ctx* ctx, int what, long long value) {
       ctx->upsample_stage_floats = (int)(value / 4);
       return NTTT_OK;
     default:
-      if (what >= 100 && what < 108 && value >= 0 && value <= (1 << 20)) {
-        nttt::g_exp[what - 100] = (int)value;
+      if (what >= NTTT_TUNE_EXPERIMENT && what < NTTT_TUNE_EXPERIMENT + 8 && value >= 0 && value <= (1 << 20)) {
+        nttt::g_exp[what - NTTT_TUNE_EXPERIMENT] = (int)value;
         return NTTT_OK;
       }
       return NTTT_EINVAL;

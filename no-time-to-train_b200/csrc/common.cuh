@@ -38,6 +38,35 @@ extern std::atomic<unsigned long long> g_launches;  // (host threads of differen
     NTTT_CUDA(cudaGetLastError());   \
   } while (0)
 
+// Launch of a kernel on the main chain of nttt_match_image.  In low-latency mode (one image at a time) the launch carries
+// the programmatic-stream-serialization attribute: the kernel may be scheduled while its predecessor's last CTAs are
+// still running, and its `chain_wait()` — the first statement of every chain kernel — holds it until the predecessor
+// has completed and its writes are visible.  What overlaps is the launch latency and the CTA ramp-up, 2-3 us per kernel
+// boundary of an 18-kernel chain.  Without the attribute (many images in flight: other streams fill the gaps anyway)
+// chain_wait() returns immediately.  g_exp[6] = 1 switches the attribute off (A/B).
+template <typename... KArgs, typename... Args>
+inline void launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (t_low_latency && g_exp[6] != 1) ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // (the error is picked up by NTTT_LAUNCH_CHECK)
+}
+#ifdef __CUDACC__
+// first statement of every chain kernel, in every CTA and on every path: wait for the predecessor grid (and, through it,
+// for every earlier one), then let the successor be scheduled once all CTAs of this grid have got here
+__device__ __forceinline__ void chain_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -457,6 +457,7 @@ upsample_plan_kernel(const uint32_t* __restrict__ bits_lr, const int32_t* __rest
                      int32_t* __restrict__ rect, int32_t* __restrict__ scratch, const float* __restrict__ logits,
                      const float* const* __restrict__ mask_ptr, Up2Item* __restrict__ items, int32_t* __restrict__ ctr,
                      int32_t* __restrict__ area_full, int32_t* __restrict__ box_full, int oh, int ow, int tile_cap_floats) {
+  chain_wait();
   __shared__ int s_warp[kPlanThreads / 32 + 1];
   __shared__ int s_off[1024];   // exclusive item offset of each mask of the strip
   __shared__ int s_ccs[1024];   // column chunks of each mask (0: no items)
@@ -682,6 +683,7 @@ upsample_pack2_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __rest
                       int ow, UpTables t, uint32_t* __restrict__ bits_full, uint32_t* __restrict__ bits_t,
                       int32_t* __restrict__ area_full, int32_t* __restrict__ box_full, int32_t* __restrict__ scratch,
                       const Up2Item* __restrict__ items, int32_t* __restrict__ ctr) {
+  chain_wait();
   extern __shared__ __align__(16) unsigned char s_raw[];
   float4* s_pkx = reinterpret_cast<float4*>(s_raw);                       // [kUp2Cols * 32]
   float4* s_pky = s_pkx + kUp2Cols * 32;                                  // [kUp2Rows + kGrpMax] (rows past the end are read)
@@ -933,14 +935,14 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
     const size_t smem = up2_fixed_smem(ih, iw) + (size_t)tile_floats * 4;
     if (smem > 200 * 1024) return NTTT_EUNSUPPORTED;
     // (eight CTAs: the geometry pass is redundant per CTA, the item records are shared out)
-    upsample_plan_kernel<<<8, kPlanThreads, 0, s>>>(bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, t, meta, rect,
+    launch_chain(upsample_plan_kernel, 8, kPlanThreads, 0, s, bits_lr, box_lr, flags_lr, ih, iw, sel, n_sel, max_sel, t, meta, rect,
                                                     scratch, logits, mask_ptr, items, ctr, area_full, box_full, oh, ow,
                                                     tile_floats);
     NTTT_LAUNCH_CHECK();
     if (smem > 48 * 1024)
       NTTT_CUDA(set_dyn_smem(upsample_pack2_kernel, (int)smem));
     const int grid = (sm_count > 0 ? sm_count : 148) * (low_latency ? kUp2CtasPerSm : g_up2_ctas_per_sm);
-    upsample_pack2_kernel<<<grid, kUp2Threads, smem, s>>>(bits_lr, meta, ih, iw, oh, ow, t,
+    launch_chain(upsample_pack2_kernel, grid, kUp2Threads, smem, s, bits_lr, meta, ih, iw, oh, ow, t,
                                                           (bits_t && t_only) ? nullptr : bits_full, bits_t, area_full,
                                                           box_full, scratch, items, ctr);
     NTTT_LAUNCH_CHECK();
@@ -1037,6 +1039,7 @@ __global__ void __launch_bounds__(256)
 unpack_sparse_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restrict__ rect,
                      const int32_t* __restrict__ index, const int32_t* __restrict__ count, int max_count, int oh, int ow,
                      uint8_t* __restrict__ out, int32_t* __restrict__ prev_rect, bool tr) {
+  chain_wait();
   const int j = blockIdx.y;
   const int ow_words = (ow + 31) >> 5;
   const bool live = j < min(*count, max_count);
@@ -1087,7 +1090,7 @@ int launch_unpack_sparse(const uint32_t* bits_full, const int32_t* rect, const i
                          int max_count, int oh, int ow, uint8_t* out, int32_t* prev_rect, cudaStream_t s, bool tr) {
   if (max_count <= 0) return NTTT_OK;
   dim3 grid(1, max_count);  // one CTA per slot: prev_rect[j] is read and rewritten by the same CTA
-  unpack_sparse_kernel<<<grid, 256, 0, s>>>(bits_full, rect, index, count, max_count, oh, ow, out, prev_rect, tr);
+  launch_chain(unpack_sparse_kernel, grid, 256, 0, s, bits_full, rect, index, count, max_count, oh, ow, out, prev_rect, tr);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }

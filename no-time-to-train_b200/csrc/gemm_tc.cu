@@ -180,6 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_acc = sm.tmem_base;
+  chain_wait();  // (barriers, TMEM and tensor-map prefetch are set up while the producer of the operands drains)
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -289,6 +290,7 @@ gemm_split3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_acc = sm.tmem_base;
+  chain_wait();  // (barriers, TMEM and tensor-map prefetch are set up while the producer of the operands drains)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -395,7 +397,7 @@ static int launch_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, in
   const int total_kb = K / kBK;
   const int kb_per = ceil_div(total_kb, splits);
   dim3 grid(ceil_div(N, BN), ceil_div(M, kBM), ceil_div(total_kb, kb_per));
-  kern<<<grid, kGemmThreads, smem, s>>>(ma, mb, D, ldd, M, N, total_kb, kb_per, split_stride);
+  launch_chain(kern, grid, kGemmThreads, smem, s, ma, mb, D, ldd, M, N, total_kb, kb_per, split_stride);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }

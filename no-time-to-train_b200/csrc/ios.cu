@@ -41,6 +41,7 @@ ios_meta_kernel(const int32_t* __restrict__ rect, const int32_t* __restrict__ ar
                 const int32_t* __restrict__ n_sel, int max_sel, const int32_t* __restrict__ labels,
                 IosMeta* __restrict__ meta, int32_t* __restrict__ label_sel, float* __restrict__ ios,
                 int32_t* __restrict__ n_pairs) {
+  chain_wait();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j == 0) { n_pairs[0] = 0; n_pairs[1] = 0; }  // small list (front of the buffer), big list (back)
   if (j >= max_sel) return;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(256)
 ios_pairs_kernel(const IosMeta* __restrict__ meta, const int32_t* __restrict__ label_sel,
                  const int32_t* __restrict__ n_sel, int max_sel, int2* __restrict__ pairs,
                  int32_t* __restrict__ n_pairs, int max_pairs) {
+  chain_wait();
   const int nsel = min(*n_sel, max_sel);
   const int lane = lane_id();
   for (int i = blockIdx.x; i < nsel; i += gridDim.x) {  // (row i has nsel - i - 1 partners: striding balances the CTAs)
@@ -190,6 +192,7 @@ ios_eval_kernel(const uint32_t* __restrict__ bits_full, const uint32_t* __restri
                 const int2* __restrict__ pairs, const int32_t* __restrict__ n_pairs, int max_pairs, int max_sel, int oh,
                 int ow, const float* __restrict__ obj_feats, int c, float* __restrict__ ios,
                 int32_t* __restrict__ inter_out) {
+  chain_wait();
   const int lane = lane_id();
   constexpr int kWarps = kIosThreads / 32;
   const int ow_words = (ow + 31) >> 5;
@@ -301,15 +304,15 @@ int launch_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_
 #else
   constexpr int ios_stop = 0;
 #endif
-  ios_meta_kernel<<<ceil_div(max_sel, 256), 256, 0, s>>>(rect, area_full, box_full, sel, n_sel, max_sel, labels, meta,
+  launch_chain(ios_meta_kernel, ceil_div(max_sel, 256), 256, 0, s, rect, area_full, box_full, sel, n_sel, max_sel, labels, meta,
                                                          label_sel, ios, n_pairs);
   NTTT_LAUNCH_CHECK();
   if (ios_stop == 1) return NTTT_OK;
-  ios_pairs_kernel<<<g_exp[3] > 0 ? min(max_sel, g_exp[3]) : (t_low_latency ? max_sel : min(max_sel, 148)), 256, 0, s>>>(meta, label_sel, n_sel, max_sel, pairs, n_pairs, max_pairs);
+  launch_chain(ios_pairs_kernel, g_exp[3] > 0 ? min(max_sel, g_exp[3]) : (t_low_latency ? max_sel : min(max_sel, 148)), 256, 0, s, meta, label_sel, n_sel, max_sel, pairs, n_pairs, max_pairs);
   NTTT_LAUNCH_CHECK();
   if (ios_stop == 2) return NTTT_OK;
   // one CTA per SM when many images are in flight (measured 89.4 vs 90.0 us/image with four), four for one image alone
-  ios_eval_kernel<<<g_exp[0] > 0 ? g_exp[0] : (t_low_latency ? 148 * 4 : 148), kIosThreads, 0, s>>>(bits_full, bits_t, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats,
+  launch_chain(ios_eval_kernel, g_exp[0] > 0 ? g_exp[0] : (t_low_latency ? 148 * 4 : 148), kIosThreads, 0, s, bits_full, bits_t, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats,
                                                   c, ios, inter_out);
   NTTT_LAUNCH_CHECK();
   if (finalize) {
@@ -339,6 +342,7 @@ decay_rank_kernel(const float* __restrict__ top_score, const int32_t* __restrict
                   int64_t* __restrict__ out_boxes, float* __restrict__ out_scores, int64_t* __restrict__ out_labels,
                   int32_t* __restrict__ out_index, int32_t* __restrict__ out_slot, int32_t* __restrict__ n_out,
                   float* __restrict__ decayed_out) {
+  chain_wait();
   extern __shared__ unsigned long long s_keys[];
   float* s_val = reinterpret_cast<float*>(s_keys + n_pad);
   const int nsel = min(*n_sel, max_sel);
@@ -404,7 +408,7 @@ int launch_decay_rank(const float* top_score, const int32_t* labels, const float
   if (smem > 200 * 1024) return NTTT_EUNSUPPORTED;
   if (smem > 48 * 1024)
     NTTT_CUDA(set_dyn_smem(decay_rank_kernel, (int)smem));
-  decay_rank_kernel<<<1, 1024, smem, s>>>(top_score, labels, ios, sel, n_sel, max_sel, n_pad, num_out, box_full,
+  launch_chain(decay_rank_kernel, 1, 1024, smem, s, top_score, labels, ios, sel, n_sel, max_sel, n_pad, num_out, box_full,
                                           area_full, out_boxes, out_scores, out_labels, out_index, out_slot, n_out, decayed_out);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;

@@ -255,6 +255,7 @@ lowres_pack_fast_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 pe
                         uint32_t* __restrict__ bits, int32_t* __restrict__ area, int32_t* __restrict__ box,
                         int32_t* __restrict__ flags, const float* __restrict__ gate, float gate_min,
                         const float* const* __restrict__ mask_ptr) {
+  chain_wait();
   extern __shared__ __align__(128) unsigned char s_raw[];
   if (gate && !(gate[blockIdx.x] > gate_min)) {
     const int nw = p4 >> 3;
@@ -621,7 +622,7 @@ int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, floa
     NTTT_CUDA(set_dyn_smem(lowres_pack_kernel<true>, (int)smem));
     lowres_pack_kernel<true><<<n, kPackBlock, smem, s>>>(src, (int)(p / 4), w / 32, thr + off, thr - off, bits, area, box,
                                                         stab, stab_score, flags, gate, gate_min, mask_ptr);
-  } else if (pack_mode() <= 1 && g_pack_persistent > 0 && !t_low_latency) {
+  } else if (pack_mode() <= 1 && g_pack_persistent > 0 && (!t_low_latency || g_exp[7] == 1)) {
     const int sm_count = current_sm_count();
     const size_t bits_bytes = 2 * (size_t)(p / 32) * sizeof(uint32_t);
     // modes 1 and 2 are the named ones; 10 * CTAs-per-SM + stages selects any other shape (experiments)
@@ -647,6 +648,7 @@ int launch_lowres_pack(const float* logits, int n, int h, int w, float thr, floa
   } else if (pack_mode() <= 1) {
     const size_t smem_fast = smem + (size_t)g_pack_extra_smem;
     NTTT_CUDA(set_dyn_smem(lowres_pack_fast_kernel, (int)smem_fast));
+    // (first kernel of the chain, behind the fork event of the low-latency mode: an ordinary launch)
     lowres_pack_fast_kernel<<<n, kPackBlock, smem_fast, s>>>(src, (int)(p / 4), w / 32, bits, area, box, flags, gate, gate_min,
                                                         mask_ptr);
   } else {
@@ -889,6 +891,7 @@ template <bool kSplit>
 __global__ void __launch_bounds__(kProjThreads)
 project_masks_kernel(const uint32_t* __restrict__ bits, const int32_t* __restrict__ box, int n_masks, int h,
                      int words_per_row, int eh, int ew, ProjTables t, void* __restrict__ out, int stride_or_kp) {
+  chain_wait();
   extern __shared__ uint32_t smem[];
   // layout: x_lo[ew] x_len[ew] y_lo[eh] y_len[eh] | bits[rc*wpr] | row[rc*ew] | acc[eh*ew]     (rc = min(h, kProjRows))
   // (the weight tables — running column sums, row weights — are the same for every mask and are read through L1
@@ -1022,7 +1025,7 @@ int launch_project_masks(const AxisTable& tx, const AxisTable& ty, const uint32_
   if (split) {
     if (smem > 48 * 1024)
       NTTT_CUDA(set_dyn_smem(project_masks_kernel<true>, (int)smem));
-    project_masks_kernel<true><<<grid, kProjThreads, smem, s>>>(bits, box, n, h, w / 32, eh, ew, t, out, out_stride);
+    launch_chain(project_masks_kernel<true>, grid, kProjThreads, smem, s, bits, box, n, h, w / 32, eh, ew, t, out, out_stride);
   } else {
     if (smem > 48 * 1024)
       NTTT_CUDA(set_dyn_smem(project_masks_kernel<false>, (int)smem));

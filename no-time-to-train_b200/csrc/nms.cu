@@ -25,6 +25,7 @@ nms_sort_kernel(const float* __restrict__ scores, const int32_t* __restrict__ bo
                 int n, int n_pad, float min_score, int filter, int32_t* __restrict__ order,
                 float4* __restrict__ sorted_box, int32_t* __restrict__ sorted_label, uint32_t* __restrict__ nz,
                 int nz_total) {
+  chain_wait();
   extern __shared__ unsigned long long s_keys[];
   // (lists above 1024 boxes) clear the per-row summary of non-zero matrix words that nms_mask_kernel ORs into
   for (int i = threadIdx.x; i < nz_total; i += blockDim.x) nz[i] = 0u;
@@ -77,6 +78,7 @@ template <bool kByVictim>
 __global__ void __launch_bounds__(256)
 nms_mask_kernel(const float4* __restrict__ sorted_box, const int32_t* __restrict__ sorted_label, int n, float thr,
                 uint32_t* __restrict__ mask, int row_words, uint32_t* __restrict__ nz, int nz_words) {
+  chain_wait();
   __shared__ float4 s_box[8][32];
   __shared__ int s_lab[8][32];
   const int i = blockIdx.y * 32 + threadIdx.x;  // sorted position of the row box
@@ -150,6 +152,7 @@ nms_wave_kernel(const uint32_t* __restrict__ mt, int row_words, const int32_t* _
                 const int32_t* __restrict__ sorted_label, const float* __restrict__ top_score, int n, int max_keep,
                 int32_t* __restrict__ keep, int32_t* __restrict__ n_keep, int32_t* __restrict__ sel,
                 int32_t* __restrict__ n_sel) {
+  chain_wait();
   __shared__ uint32_t s_K[kScanMaxN / 32];    // keep bits per chunk, then truncated to max_keep
   __shared__ uint32_t s_S[kScanMaxN / 32];    // positive-score flags, then `sel` bits
   __shared__ int s_pre[kScanMaxN / 32 + 1];   // exclusive prefix of popc over the words
@@ -257,6 +260,7 @@ nms_wave_sparse_kernel(const uint32_t* __restrict__ mt, const uint32_t* __restri
                        const int32_t* __restrict__ order, const int32_t* __restrict__ sorted_label,
                        const float* __restrict__ top_score, int n, int max_keep, int32_t* __restrict__ keep,
                        int32_t* __restrict__ n_keep, int32_t* __restrict__ sel, int32_t* __restrict__ n_sel) {
+  chain_wait();
   __shared__ uint32_t s_K[kScanMaxN / 32];
   __shared__ uint32_t s_S[kScanMaxN / 32];
   __shared__ int s_pre[kScanMaxN / 32 + 1];
@@ -379,29 +383,29 @@ int launch_box_nms(const int32_t* box, const float* nms_scores, const int32_t* l
   int n_pad = 1;
   while (n_pad < n) n_pad <<= 1;
   if (n_pad <= 1024) {
-    nms_sort_kernel<true><<<1, 1024, sizeof(unsigned long long) * 1024, s>>>(nms_scores, box, labels, n, 1024, min_score, filter, order,
+    launch_chain(nms_sort_kernel<true>, 1, 1024, sizeof(unsigned long long) * 1024, s, nms_scores, box, labels, n, 1024, min_score, filter, order,
                                                                              sorted_box, sorted_label, nullptr, 0);
   } else {
     const size_t smem = sizeof(unsigned long long) * (size_t)n_pad;
     if (smem > 48 * 1024)
       NTTT_CUDA(set_dyn_smem(nms_sort_kernel<false>, (int)smem));
-    nms_sort_kernel<false><<<1, 1024, smem, s>>>(nms_scores, box, labels, n, n_pad, min_score, filter, order, sorted_box,
+    launch_chain(nms_sort_kernel<false>, 1, 1024, smem, s, nms_scores, box, labels, n, n_pad, min_score, filter, order, sorted_box,
                                                  sorted_label, nz, n * nz_words);
   }
   NTTT_LAUNCH_CHECK();
   dim3 grid(ceil_div(row_words, 8), ceil_div(n, 32));
   if (n <= 1024) {
-    nms_mask_kernel<true><<<grid, dim3(32, 8), 0, s>>>(sorted_box, sorted_label, n, thr, mask, row_words, nullptr, 0);
+    launch_chain(nms_mask_kernel<true>, grid, dim3(32, 8), 0, s, sorted_box, sorted_label, n, thr, mask, row_words, nullptr, 0);
     NTTT_LAUNCH_CHECK();
-    nms_wave_kernel<<<1, kScanThreads, 0, s>>>(mask, row_words, order, sorted_label, top_score, n, max_keep, keep, n_keep, sel,
+    launch_chain(nms_wave_kernel, 1, kScanThreads, 0, s, mask, row_words, order, sorted_label, top_score, n, max_keep, keep, n_keep, sel,
                                                n_sel);
     NTTT_LAUNCH_CHECK();
     return NTTT_OK;
   }
   // longer lists: the same wavefront over the non-zero words of each row
-  nms_mask_kernel<true><<<grid, dim3(32, 8), 0, s>>>(sorted_box, sorted_label, n, thr, mask, row_words, nz, nz_words);
+  launch_chain(nms_mask_kernel<true>, grid, dim3(32, 8), 0, s, sorted_box, sorted_label, n, thr, mask, row_words, nz, nz_words);
   NTTT_LAUNCH_CHECK();
-  nms_wave_sparse_kernel<<<1, kScanThreads, 0, s>>>(mask, nz, nz_words, row_words, order, sorted_label, top_score, n, max_keep,
+  launch_chain(nms_wave_sparse_kernel, 1, kScanThreads, 0, s, mask, nz, nz_words, row_words, order, sorted_label, top_score, n, max_keep,
                                                     keep, n_keep, sel, n_sel);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;

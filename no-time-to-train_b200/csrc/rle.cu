@@ -127,6 +127,7 @@ rle_encode_kernel(const uint32_t* __restrict__ bits_full, const int32_t* __restr
                   const int32_t* __restrict__ slot, const int32_t* __restrict__ count, int max_count, int oh, int ow,
                   int cap_counts, int cap_chars, uint32_t* __restrict__ counts_out, int32_t* __restrict__ n_counts,
                   uint8_t* __restrict__ chars_out, int32_t* __restrict__ n_chars, bool tr) {
+  chain_wait();
   extern __shared__ int s_col[];  // boundaries per visited column, then their exclusive prefix
   __shared__ int s_warp[kRleWarps + 1];
   const int j = blockIdx.x;
@@ -251,7 +252,7 @@ int launch_rle_encode(const uint32_t* bits_full, const int32_t* rect, const int3
   if (smem > 160 * 1024) return NTTT_EUNSUPPORTED;
   if (smem > 48 * 1024)
     NTTT_CUDA(set_dyn_smem(rle_encode_kernel, (int)smem));
-  rle_encode_kernel<<<max_count, kRleThreads, smem, s>>>(bits_full, rect, slot, count, max_count, oh, ow, cap_counts,
+  launch_chain(rle_encode_kernel, max_count, kRleThreads, smem, s, bits_full, rect, slot, count, max_count, oh, ow, cap_counts,
                                                         cap_chars, counts_out, n_counts, chars_out, n_chars, tr);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;

@@ -45,6 +45,7 @@ template <int kVec>  // float4 per lane, c = 128 * kVec
 __global__ void __launch_bounds__(256)
 normalize_split_kernel(const float* __restrict__ sums, int n_partials, const int32_t* __restrict__ area, int n, int cp,
                        float* __restrict__ out, __nv_bfloat16* __restrict__ split, bool nan_empty) {
+  chain_wait();
   constexpr int c = 128 * kVec;
   const int row = blockIdx.x * 8 + warp_id();
   if (row >= n) return;
@@ -109,10 +110,10 @@ int launch_normalize_split(const float* sums, int n_partials, const int32_t* are
   const int grid = ceil_div(n, 8);
   __nv_bfloat16* sp = static_cast<__nv_bfloat16*>(split);
   switch (c / 128) {
-    case 3: normalize_split_kernel<3><<<grid, 256, 0, s>>>(sums, n_partials, area, n, cp, out, sp, nan_empty); break;
-    case 6: normalize_split_kernel<6><<<grid, 256, 0, s>>>(sums, n_partials, area, n, cp, out, sp, nan_empty); break;
-    case 8: normalize_split_kernel<8><<<grid, 256, 0, s>>>(sums, n_partials, area, n, cp, out, sp, nan_empty); break;
-    case 12: normalize_split_kernel<12><<<grid, 256, 0, s>>>(sums, n_partials, area, n, cp, out, sp, nan_empty); break;
+    case 3: launch_chain(normalize_split_kernel<3>, grid, 256, 0, s, sums, n_partials, area, n, cp, out, sp, nan_empty); break;
+    case 6: launch_chain(normalize_split_kernel<6>, grid, 256, 0, s, sums, n_partials, area, n, cp, out, sp, nan_empty); break;
+    case 8: launch_chain(normalize_split_kernel<8>, grid, 256, 0, s, sums, n_partials, area, n, cp, out, sp, nan_empty); break;
+    case 12: launch_chain(normalize_split_kernel<12>, grid, 256, 0, s, sums, n_partials, area, n, cp, out, sp, nan_empty); break;
     default: return 0;
   }
   ++g_launches;
@@ -175,6 +176,7 @@ __device__ __forceinline__ float clamp_min0(float x) { return x < 0.0f ? 0.0f : 
 __global__ void __launch_bounds__(256)
 top1_kernel(const float* __restrict__ part, int n_splits, size_t split_stride, float* __restrict__ sim, int ld, int n,
             int n_cls, float* __restrict__ top_score, int32_t* __restrict__ top_label) {
+  chain_wait();
   const int row = blockIdx.x * 8 + warp_id();
   if (row >= n) return;
   const int lane = lane_id();
@@ -203,7 +205,7 @@ top1_kernel(const float* __restrict__ part, int n_splits, size_t split_stride, f
 int launch_top1(const float* part, int n_splits, size_t split_stride, float* sim, int ld, int n, int n_cls,
                 float* top_score, int32_t* top_label, cudaStream_t s) {
   if (n <= 0) return NTTT_OK;
-  top1_kernel<<<ceil_div(n, 8), 256, 0, s>>>(part, n_splits, split_stride, sim, ld, n, n_cls, top_score, top_label);
+  launch_chain(top1_kernel, ceil_div(n, 8), 256, 0, s, part, n_splits, split_stride, sim, ld, n, n_cls, top_score, top_label);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }
@@ -216,6 +218,7 @@ __global__ void __launch_bounds__(256)
 neg_top1_kernel(const float* __restrict__ part_pos, int splits_pos, size_t stride_pos,
                 const float* __restrict__ part_neg, int splits_neg, size_t stride_neg, int n, int n_cls, int l_neg,
                 float sigma, float* __restrict__ sim, float* __restrict__ top_score, int32_t* __restrict__ top_label) {
+  chain_wait();
   const int row = blockIdx.x * 8 + warp_id();
   if (row >= n) return;
   const int lane = lane_id();
@@ -254,7 +257,7 @@ int launch_neg_top1(const float* part_pos, int splits_pos, size_t stride_pos, co
                     size_t stride_neg, int n, int n_cls, int l_neg, float sigma, float* sim, float* top_score,
                     int32_t* top_label, cudaStream_t s) {
   if (n <= 0) return NTTT_OK;
-  neg_top1_kernel<<<ceil_div(n, 8), 256, 0, s>>>(part_pos, splits_pos, stride_pos, part_neg, splits_neg, stride_neg, n,
+  launch_chain(neg_top1_kernel, ceil_div(n, 8), 256, 0, s, part_pos, splits_pos, stride_pos, part_neg, splits_neg, stride_neg, n,
                                                  n_cls, l_neg, sigma, sim, top_score, top_label);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;

@@ -1,6 +1,3 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-python tools/profile_stage.py --latency --images 4 2>&1 | tail -3
-python bench.py --value-only 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value us/img', round(1e6/d['value'],2), d['clocks']['sm_mhz'])"
-python tools/forward_timing.py 2>&1 | grep "2nd\|segment\|C call" | cut -c1-70
+for t in "exp7=0" "exp7=1" "exp7=1 --tune lowres_persistent=24" "exp7=1 --tune lowres_persistent=33" "exp0=1184" "exp0=296"; do
+echo "== $t"; timeout 300 python tools/profile_stage.py --latency --images 4 --tune $t 2>&1 | grep "low_latency=True"
+done
