@@ -590,6 +590,31 @@ def main():
                                 "gathered with sharding.collect_results; encoders replaced by resident synthetic tensors")
     del model, runner
 
+    # ---- latency of ONE image (rank 0): the whole stage as one CUDA-graph replay in low-latency mode, the device idle
+    #      before every replay, CUDA events around it; the throughput-mode shapes beside it for comparison ---------------
+    latency = None
+    if rank == 0:
+        latency = {}
+        for low in (True, False):
+            g = stage.graphed(args.n_masks, WORKLOAD["feat_dim"], ori_hw, key=("latency", low), low_latency=low)
+            first = resident[distinct[0]]
+            g.lr_masks.copy_(first[0]); g.pred_ious.copy_(first[1]); g.tar_feat.copy_(first[2])
+            g.capture()
+            times = []
+            for rep in range(28):
+                img = resident[distinct[rep % min(8, len(distinct))]]
+                g.lr_masks.copy_(img[0]); g.pred_ious.copy_(img[1]); g.tar_feat.copy_(img[2])
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); g.replay(); e1.record()
+                torch.cuda.synchronize(dev)
+                times.append(1e3 * e0.elapsed_time(e1))
+            times = sorted(times[4:])
+            latency["low_latency_us" if low else "throughput_shapes_us"] = dict(median=times[len(times) // 2], min=times[0])
+            del g
+        latency["note"] = ("one image alone on an idle device, whole stage = one CUDA-graph replay (nttt_match_args."
+                           "low_latency = 1 / 0), CUDA events; inputs in HBM")
+
     # ---- per-stage share (single stream, CUDA events between the stage's kernels) and the roofline kernel --
     stage_ms = {}
     roofline = None
@@ -667,7 +692,7 @@ def main():
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              steps=e2e_steps, images_per_step_per_gpu=E2E_B),
                     e2e_rle=e2e_rle, fill=fill_record, forward_api=forward_api, gpu_launches=int(launches),
-                    clocks=clock_info, roofline=roofline, cpu_baseline=cpu_baseline,
+                    clocks=clock_info, roofline=roofline, cpu_baseline=cpu_baseline, latency=latency,
                     stage_us_per_image={k: 1e3 * v for k, v in stage_ms.items()},
                     stage_roofline=stage_floor(args.n_masks, us_per_image))
         print(json.dumps(line))

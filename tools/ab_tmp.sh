@@ -1,3 +1,8 @@
-for t in "exp7=0" "exp7=1" "exp7=1 --tune lowres_persistent=24" "exp7=1 --tune lowres_persistent=33" "exp0=1184" "exp0=296"; do
-echo "== $t"; timeout 300 python tools/profile_stage.py --latency --images 4 --tune $t 2>&1 | grep "low_latency=True"
-done
+mkdir -p gpurun_out
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 4 --steps 20 --warmup 3 > gpurun_out/bench_r2f_n4.json 2> gpurun_out/bench_r2f_n4.err
+tail -c 400 gpurun_out/bench_r2f_n4.err
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/bench_r2f_n4.json").read().strip().splitlines()[-1])
+print(round(d["value"],1), "per gpu us/img", round(4e6/d["value"],2), "e2e", round(d["e2e"]["value"],1), d["fill"]["fill_ms"], d["fill"]["allreduce_us"], d["fill"]["bit_identical_across_world"], d["run"]["ms_per_rank"], d["clocks"])
+PY
