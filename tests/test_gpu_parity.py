@@ -277,6 +277,29 @@ def test_upsample_threshold_pack_bit_exact(ops, synth, ori_hw):
         assert diff <= max(4, got.size // 5_000_000)
 
 
+def test_upsample_more_selected_masks_than_one_plan_strip(ops, synth):
+    """The plan kernel works in strips of 1024 selected masks (every CTA scans the whole strip, the item records are
+    shared out): 2 500 selected masks (num_out_instance > 128 gives max_sel > 1024) = two full strips and a partial one,
+    with repeated sources, empty masks and an unused tail of the selection."""
+    ori_hw = (300, 280)
+    inp = synth.make_stage_inputs(n=40, c=64, n_cls=3, shots=2, ori_hw=ori_hw, seed=77, degenerate=True)
+    d = inp.lr_masks.to(DEV)
+    bits, area, box, stab, flags = ops.threshold_pack(d)
+    gen = torch.Generator().manual_seed(78)
+    k, max_sel = 2500, 2600
+    sel_host = torch.randint(0, 40, (max_sel,), generator=gen).int()
+    n_sel = torch.tensor([k], dtype=torch.int32, device=DEV)
+    bits_full, rect, area_full, box_full = ops.upsample_threshold_pack(d, bits, box, flags, sel_host.to(DEV), n_sel, max_sel,
+                                                                       ori_hw)
+    got = ops.unpack_masks(bits_full, rect, n_sel, ori_hw)[:k].cpu().numpy()
+    want_src = orc.aa_resize_threshold(inp.lr_masks.numpy(), ori_hw).astype(bool)
+    idx = sel_host[:k].long().numpy()
+    assert np.array_equal(got, want_src[idx])
+    o_box, o_area = orc.mask_boxes(want_src.astype(np.uint8))
+    assert np.array_equal(area_full.cpu().numpy()[:k], o_area[idx])
+    assert np.array_equal(box_full.cpu().numpy()[:k].astype(np.int64), o_box[idx])
+
+
 def test_mask_ios_counts_bit_exact(ops, synth):
     inp = synth.make_stage_inputs(n=48, c=64, n_cls=3, shots=2, ori_hw=(333, 500), seed=31, degenerate=True)
     d = inp.lr_masks.to(DEV)
