@@ -1,4 +1,4 @@
-set -e
-python tools/profile_stage.py --images 3 > gpurun_out/prof_plain.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:upsample_pack2 -s 3 -c 1 -o gpurun_out/upsample_r2f -f python tools/profile_stage.py --images 3 > gpurun_out/prof_ncu.log 2>&1
-ls -la gpurun_out/upsample_r2f.ncu-rep
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "upsample or pipeline" 2>&1 | tail -2
+for i in 1 2; do python bench.py --value-only 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value us/img', round(1e6/d['value'],2), d['clocks']['sm_mhz'])"; done
