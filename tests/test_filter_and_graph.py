@@ -78,6 +78,59 @@ def test_graph_replay_matches_eager():
         assert torch.equal(out["binary_masks"], eager["binary_masks"]) and torch.equal(out["bboxes"], eager["bboxes"])
 
 
+def test_low_latency_graph_replay_matches_eager():
+    """The low-latency launch mode under stream capture: the side-stream fork (feature / prototype operand preparation)
+    and the programmatic dependent launches along the kernel chain become graph edges.  Every replay — new inputs in the
+    static buffers, several replays back to back without a host synchronisation in between — gives bit for bit what
+    the eager low-latency call gives, with RLE output and persistent masks."""
+    P, inp = _case(n=128, c=384, n_cls=9, seed=171, ori_hw=(640, 480))
+    stage = P.MatchingStage(DEV, P.StageConfig(nms_thr=0.5, num_out_instance=20, enc_hw=(37, 37)))
+    stage.set_prototypes(inp.feats_ins_avg)
+    g = stage.graphed(128, 384, (640, 480), iou_thr=0.4, rle=True, low_latency=True).capture()
+    for seed in (171, 172, 173, 174):
+        _, cur = _case(n=128, c=384, n_cls=9, seed=seed, ori_hw=(640, 480))
+        g.lr_masks.copy_(cur.lr_masks)
+        g.pred_ious.copy_(cur.pred_ious)
+        g.tar_feat.copy_(cur.tar_feat)
+        for _ in range(3):  # the same image three times: a replay must not depend on what the previous one left behind
+            pend = g.replay()
+        out = pend.get()
+        segs = pend.rle_segmentations()
+        eager = stage.match(cur.lr_masks.to(DEV), cur.pred_ious.to(DEV), cur.tar_feat.to(DEV), (640, 480), iou_thr=0.4,
+                            rle=True, low_latency=True)
+        assert out["counts"] == eager["counts"]
+        assert torch.equal(torch.nan_to_num(out["scores"]), torch.nan_to_num(eager["scores"]))
+        assert torch.equal(out["labels"], eager["labels"]) and torch.equal(out["bboxes"], eager["bboxes"])
+        assert torch.equal(out["binary_masks"], eager["binary_masks"])
+        assert segs == eager["segmentations"]
+
+
+def test_low_latency_chain_is_deterministic_over_many_calls():
+    """Race check of the overlapped kernel chain (programmatic dependent launch: a kernel may be scheduled while its
+    predecessor is finishing, and waits for it before its first read): 60 back-to-back calls on two alternating images
+    give the same bits every time, and the taps written by the middle of the chain as well."""
+    P, a = _case(n=192, c=384, n_cls=9, seed=181, ori_hw=(512, 768))
+    _, b = _case(n=192, c=384, n_cls=9, seed=182, ori_hw=(512, 768))
+    stage = P.MatchingStage(DEV, P.StageConfig(nms_thr=0.5, num_out_instance=30, enc_hw=(37, 37)))
+    stage.set_prototypes(a.feats_ins_avg)
+    dev_in = [(x.lr_masks.to(DEV), x.pred_ious.to(DEV), x.tar_feat.to(DEV)) for x in (a, b)]
+    first = [None, None]
+    for rep in range(60):
+        pend = stage.match_async(*dev_in[rep % 2], (512, 768), taps=True, iou_thr=0.3, low_latency=True)
+        if rep % 7 == 3:
+            torch.cuda.synchronize()  # (some calls start on an idle device, most behind the previous image's tail)
+        out = pend.get()
+        cur = (out["counts"], out["scores"].clone(), out["labels"].clone(), out["bboxes"].clone(),
+               out["binary_masks"].clone(), out["taps"]["sim"].clone(), out["taps"]["obj_feats"].clone())
+        if first[rep % 2] is None:
+            first[rep % 2] = cur
+            continue
+        ref = first[rep % 2]
+        assert cur[0] == ref[0], rep
+        for x, y in zip(cur[1:], ref[1:]):
+            assert torch.equal(torch.nan_to_num(x.float()), torch.nan_to_num(y.float())), rep
+
+
 def test_persistent_outputs_are_exactly_the_dense_unpack():
     """Sparse unpack into persistent buffers: after every replay the WHOLE mask buffer (used and unused slots)
     equals what a dense unpack into a fresh buffer gives, also when the number of outputs shrinks to zero."""
