@@ -411,8 +411,11 @@ __device__ __forceinline__ void pk_consumer_barrier() { asm volatile("bar.sync 1
 
 // (min-blocks 3 only caps the registers at 72 per thread: the shared-memory request admits one CTA per SM, and the
 // registers this kernel does not take are what the kernels of the other images run in)
+#ifndef NTTT_PERSIST_MINBLOCKS
+#define NTTT_PERSIST_MINBLOCKS 3
+#endif
 template <int kPersistStages>
-__global__ void __launch_bounds__(kPackBlock, 3)
+__global__ void __launch_bounds__(kPackBlock, NTTT_PERSIST_MINBLOCKS)
 lowres_pack_persistent_kernel(const float4* __restrict__ logits, int n_masks, int p4 /* pixels/4 per mask */,
                               int words_per_row, uint32_t* __restrict__ bits, int32_t* __restrict__ area,
                               int32_t* __restrict__ box, int32_t* __restrict__ flags, const float* __restrict__ gate,
