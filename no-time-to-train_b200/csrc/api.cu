@@ -64,6 +64,7 @@ static thread_local char g_cuda_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 int g_exp[8] = {};
 thread_local bool t_low_latency = false;
+thread_local bool t_chain_break = false;
 
 cudaError_t set_dyn_smem_impl(const void* fn, int bytes) {
   struct Entry { const void* fn; int dev; int bytes; };
@@ -859,7 +860,10 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   NTTT_STEP(launch_project_masks(px, py, L.bits_lr, L.box_lr, n, a->lr_h, a->lr_w, a->eh, a->ew, L.a_split, pad64(e),
                                  true, s));
   int n_partials = 1;
-  if (forked) NTTT_CUDA(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+  if (forked) {
+    NTTT_CUDA(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    nttt::t_chain_break = true;  // the pooling GEMM depends on the side stream as well: launched the ordinary way
+  }
   NTTT_STEP(pool_contract(nullptr, a->tar_feat, n, e, a->c, L.sums, L.a_split, L.b_split, &n_partials, s,
                           a->low_latency != 0, forked));
   bool a_ready = false;

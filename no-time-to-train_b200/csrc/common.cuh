@@ -30,6 +30,9 @@ inline cudaError_t set_dyn_smem(F* fn, int bytes) { return set_dyn_smem_impl(rei
 // shape with the shortest duration of ONE image instead of the thin persistent shape that costs the least when many
 // images are in flight (nttt_match_args.low_latency).  Results do not depend on it.
 extern thread_local bool t_low_latency;
+// set after a cross-stream event wait: the next chain launch is an ordinary one (its predecessor in the stream is the
+// wait, not a kernel that triggers), then the flag clears itself
+extern thread_local bool t_chain_break;
 extern int g_exp[8];  // launch-shape experiments (nttt_ctx_tune ids 100..107); 0 = the built-in default
 extern std::atomic<unsigned long long> g_launches;  // (host threads of different contexts may launch concurrently)
 #define NTTT_LAUNCH_CHECK()          \
@@ -55,7 +58,8 @@ inline void launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (t_low_latency && g_exp[6] != 1) ? 1 : 0;
+  cfg.numAttrs = (t_low_latency && g_exp[6] != 1 && !t_chain_break) ? 1 : 0;
+  t_chain_break = false;
   (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // (the error is picked up by NTTT_LAUNCH_CHECK)
 }
 #ifdef __CUDACC__
