@@ -15,13 +15,15 @@ int launch_lowres_pack(const float*, int, int, int, float, float, uint32_t*, int
 int launch_multimask_select(const float*, int, int, int, const ChunkTable&, int, size_t, const float**, float*,
                             cudaStream_t);
 int launch_project_masks(const AxisTable&, const AxisTable&, const uint32_t*, const int32_t*, int, int, int, int, int,
-                         void*, int, bool, cudaStream_t);
-int launch_normalize_split(const float*, int, const int32_t*, int, int, int, float*, void*, bool, cudaStream_t);
+                         void*, int, bool, cudaStream_t, const int32_t* perm = nullptr, uint32_t* active = nullptr);
+int launch_pool_order(const int32_t*, int, int, int32_t*, cudaStream_t);
+int launch_normalize_split(const float*, int, const int32_t*, int, int, int, float*, void*, bool, cudaStream_t,
+                           const int32_t* perm = nullptr);
 int launch_gemm_tc(const void*, int, const void*, int, float*, int, int, int, int, int, size_t, int*, cudaStream_t,
-                   bool low_latency = false);
+                   bool low_latency = false, const uint32_t* a_active = nullptr, const uint8_t* b_nonfinite = nullptr);
 int gemm_tc_pick_splits(int, int, int, int);
 int launch_split_rows(const float*, int, int, int, int, int, void*, cudaStream_t);
-int launch_split_transpose(const float*, int, int, int, int, int, void*, cudaStream_t);
+int launch_split_transpose(const float*, int, int, int, int, int, void*, cudaStream_t, uint8_t* nonfinite = nullptr);
 int launch_normalize_rows(const float*, int, const int32_t*, int, int, float*, bool, cudaStream_t);
 int launch_proto_prepare(const float*, int, int, int, float*, cudaStream_t);
 int launch_top1(const float*, int, size_t, float*, int, int, int, float*, int32_t*, cudaStream_t);
@@ -119,14 +121,17 @@ constexpr int kPoolSplits = 1;  // measured: 2 halves the latency (25 -> 14 us) 
 // is the duration of each kernel, so the pooling GEMM spreads over twice the SMs (128 x 128 tiles, split-K 2: 14 us
 // instead of 25-38 us).
 static int pool_contract(const float* proj, const float* feat, int n, int e, int c, float* sums, void* a_split,
-                         void* b_split, int* n_partials, cudaStream_t s, bool low_latency = false, bool b_ready = false) {
+                         void* b_split, int* n_partials, cudaStream_t s, bool low_latency = false, bool b_ready = false,
+                         const uint32_t* a_active = nullptr, uint8_t* b_nonfinite = nullptr) {
+  // a_active / b_nonfinite (both or neither): the A operand's rows are spatially ordered and carry their non-zero k-block
+  // masks; the GEMM skips the k-blocks a tile does not touch (gemm_tc_kernel), unless the features are not finite there
   const int ep = pad64(e);
   int err = proj ? launch_split_rows(proj, e, n, e, ep, 0, a_split, s) : NTTT_OK;
   if (err) return err;
-  err = b_ready ? NTTT_OK : launch_split_transpose(feat, c, c, e, ep, 1, b_split, s);  // (b_ready: done on the side stream)
+  err = b_ready ? NTTT_OK : launch_split_transpose(feat, c, c, e, ep, 1, b_split, s, a_active ? b_nonfinite : nullptr);  // (b_ready: done on the side stream)
   if (err) return err;
   return launch_gemm_tc(a_split, 3 * ep, b_split, 3 * ep, sums, c, n, c, 3 * ep, low_latency ? kPoolSplitsMax : kPoolSplits,
-                        (size_t)n * c, n_partials, s, low_latency);
+                        (size_t)n * c, n_partials, s, low_latency, a_active, a_active ? b_nonfinite : nullptr);
 }
 
 // rows of `sums` -> /area -> L2-normalise -> obj_feats (+ split-bf16 copy when the vector path applies).
@@ -134,10 +139,11 @@ static int pool_contract(const float* proj, const float* feat, int n, int e, int
 // nan_empty: negative-reference scoring divides by the raw area (empty mask -> NaN row, as the reference does)
 // n_partials: split-K partial sums of the pooling GEMM, n*c floats apart, added in order
 static int normalize_rows(const float* sums, int n_partials, const int32_t* area, int n, int c, float* obj_feats,
-                          void* a_split, bool* split_done, bool nan_empty, cudaStream_t s) {
+                          void* a_split, bool* split_done, bool nan_empty, cudaStream_t s, const int32_t* perm = nullptr) {
   *split_done = a_split &&
-                launch_normalize_split(sums, n_partials, area, n, c, pad64(c), obj_feats, a_split, nan_empty, s) == 1;
+                launch_normalize_split(sums, n_partials, area, n, c, pad64(c), obj_feats, a_split, nan_empty, s, perm) == 1;
   if (*split_done) return NTTT_OK;
+  if (perm) return NTTT_EINVAL;  // (callers order the rows only when the vector path applies)
   return launch_normalize_rows(sums, n_partials, area, n, c, obj_feats, nan_empty, s);
 }
 
@@ -692,6 +698,7 @@ struct MatchLayout {
   uint32_t* bits_lr; int32_t* area_lr; int32_t* box_lr; int32_t* stab; int32_t* flags;
   float* proj; float* sums; float* obj_feats; float* sim; float* sim_part; float* sim_part_neg; float* top_score; int32_t* top_label;
   char* a_split; char* b_split; char* p_split;
+  int32_t* pool_perm; uint32_t* pool_active; uint8_t* b_nonfinite;
   void* nms_ws; size_t nms_ws_bytes; int32_t* keep; int32_t* sel;
   uint32_t* bits_full; uint32_t* bits_t; int32_t* rect; int32_t* area_full; int32_t* box_full; int32_t* scratch;
   float* ios; void* ios_ws; int32_t* out_slot;
@@ -722,6 +729,9 @@ static MatchLayout carve(void* ws, int n, int lr_h, int lr_w, int eh, int ew, in
     L.a_split = cv.take<char>(2 * (size_t)n * kmax);
     L.b_split = cv.take<char>(2 * rows_b * kmax);
     L.p_split = cv.take<char>(2 * (size_t)n_cls * 3 * pad64(c));  // split prototypes (prepared off the critical path)
+    L.pool_perm = cv.take<int32_t>(n > 0 ? n : 1);       // spatial row order of the pooling GEMM (pool_order_kernel)
+    L.pool_active = cv.take<uint32_t>(n > 0 ? n : 1);    // per operand row: its non-zero k-blocks
+    L.b_nonfinite = cv.take<uint8_t>((size_t)(pad64(eh * ew) / 64) * ((c + 31) / 32));
   }
   L.top_score = cv.take<float>(n);
   L.top_label = cv.take<int32_t>(n);
@@ -816,6 +826,11 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
 #else
 #define NTTT_STOP_CHECK() (void)0
 #endif
+#define NTTT_STEP_QUIET(call) \
+  do {                        \
+    err = (call);             \
+    if (err) return err;      \
+  } while (0)
 #define NTTT_STEP(call)                                        \
   do {                                                         \
     err = (call);                                              \
@@ -857,18 +872,23 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
                                L.flags, a->filter_iou ? pred_ious : nullptr, a->iou_thr, mask_ptr, s));
   // a6/a7: projection + pooling contraction + normalisation
   if (!projection_supported(a->ew, a->lr_w) || !projection_supported(a->eh, a->lr_h)) return NTTT_EUNSUPPORTED;
+  // Many images in flight: the pooling GEMM runs on spatially ordered rows and skips the k-blocks a tile of masks does
+  // not touch (~45 % of them).  Needs the vector normalisation path (it undoes the order) and <= 32 k-blocks per segment.
+  const bool ordered = !a->low_latency && g_exp[1] != 1 && n > 128 && n <= 8192 && pad64(e) / 64 <= 32 &&
+                       (a->c == 384 || a->c == 768 || a->c == 1024 || a->c == 1536);
+  if (ordered) NTTT_STEP_QUIET(launch_pool_order(L.box_lr, n, a->lr_h, L.pool_perm, s));
   NTTT_STEP(launch_project_masks(px, py, L.bits_lr, L.box_lr, n, a->lr_h, a->lr_w, a->eh, a->ew, L.a_split, pad64(e),
-                                 true, s));
+                                 true, s, ordered ? L.pool_perm : nullptr, ordered ? L.pool_active : nullptr));
   int n_partials = 1;
   if (forked) {
     NTTT_CUDA(cudaStreamWaitEvent(s, ctx->ev_join, 0));
     nttt::t_chain_break = true;  // the pooling GEMM depends on the side stream as well: launched the ordinary way
   }
   NTTT_STEP(pool_contract(nullptr, a->tar_feat, n, e, a->c, L.sums, L.a_split, L.b_split, &n_partials, s,
-                          a->low_latency != 0, forked));
+                          a->low_latency != 0, forked, ordered ? L.pool_active : nullptr, L.b_nonfinite));
   bool a_ready = false;
   NTTT_STEP(normalize_rows(L.sums, n_partials, L.area_lr, n, a->c, obj_feats, L.a_split, &a_ready,
-                           a->proto_neg != nullptr, s));
+                           a->proto_neg != nullptr, s, ordered ? L.pool_perm : nullptr));
   // a7/a8: similarity + top-1
   NTTT_STEP(sim_top1(obj_feats, a->proto, a->proto_neg, l_neg, a->sigma, n, a->c, a->n_cls, a->sim, L.sim_part,
                      L.sim_part_neg, L.top_score, L.top_label, L.a_split, L.b_split, a_ready, ctx->sm_count, s, L.p_split,

@@ -146,13 +146,20 @@ struct GemmSmem {
   alignas(8) uint64_t empty[STAGES];
   alignas(8) uint64_t acc_ready;
   uint32_t tmem_base;
+  uint32_t act;  // k-blocks of one operand segment that this tile has to multiply (skipping mode)
 };
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                float* __restrict__ D, int ldd, int M, int N, int total_k_blocks, int kb_per_split,
-               size_t split_stride) {
+               size_t split_stride, const uint32_t* __restrict__ a_active, const uint8_t* __restrict__ b_nonfinite,
+               int nkb_seg) {
+  // Skipping mode (a_active != nullptr; no split-K): K' is nseg = total_k_blocks / nkb_seg segments of nkb_seg k-blocks
+  // (the split-bf16 layout: 3), a_active[row] has bit kb set if row `row` of A holds anything but zeros in k-block kb of a
+  // segment, b_nonfinite[r-tile * nkb_seg + kb] is 1 if rows 32 r-tile .. +31 of B hold an inf / NaN there.  A k-block in
+  // which all 128 rows of the A tile are zero and the B tile is finite adds exact zeros: it is neither loaded nor
+  // multiplied.  (The pooling operand is a mask's projection onto the encoder grid: a quarter of the k-blocks per mask.)
   extern __shared__ uint8_t smem_raw[];
   auto& sm = *reinterpret_cast<GemmSmem<BN, STAGES>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -182,23 +189,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_acc = sm.tmem_base;
   chain_wait();  // (barriers, TMEM and tensor-map prefetch are set up while the producer of the operands drains)
 
+  const bool skipping = a_active != nullptr && nkb_seg > 0 && nkb_seg <= 32 && gridDim.z == 1;
+  uint32_t act = 0;
+  if (skipping) {
+    if (threadIdx.x == 0) sm.act = 0u;
+    __syncthreads();
+    uint32_t m = 0;
+    for (int r = threadIdx.x; r < kBM && m0 + r < M; r += kGemmThreads) m |= a_active[m0 + r];
+    if (b_nonfinite) {
+      const int rt0 = n0 >> 5, rt1 = min((n0 + BN + 31) >> 5, (N + 31) >> 5);
+      for (int i = threadIdx.x; i < (rt1 - rt0) * nkb_seg; i += kGemmThreads) {
+        const int rt = rt0 + i / nkb_seg, kb = i - (i / nkb_seg) * nkb_seg;
+        if (b_nonfinite[rt * nkb_seg + kb]) m |= 1u << kb;
+      }
+    }
+    m = __reduce_or_sync(0xffffffffu, m);
+    if (lane == 0 && m) atomicOr(&sm.act, m);
+    __syncthreads();
+    act = sm.act & (nkb_seg >= 32 ? 0xffffffffu : ((1u << nkb_seg) - 1u));
+    if (act == 0u) act = 1u;  // (an all-zero tile still has to write its zeros)
+  }
+  const int per_seg = skipping ? __popc(act) : 0;
+  const int n_exec = skipping ? per_seg * (total_k_blocks / nkb_seg) : num_k_blocks;
+  // global k-block index of the it-th executed one
+  auto kb_index = [&](int it) -> int {
+    if (!skipping) return kb0 + it;
+    const int seg = it / per_seg;
+    return seg * nkb_seg + (int)__fns(act, 0, it - seg * per_seg + 1);
+  };
+
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
+      for (int kb = 0; kb < n_exec; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
+        const int col = kb_index(kb) * kBK;
         mbar_wait(&sm.empty[s], ph ^ 1);
         mbar_expect_tx(&sm.full[s], kStageBytes);
-        tma_load_2d(sm.a[s], &map_a, &sm.full[s], (kb0 + kb) * kBK, m0);
-        tma_load_2d(sm.b[s], &map_b, &sm.full[s], (kb0 + kb) * kBK, n0);
+        tma_load_2d(sm.a[s], &map_a, &sm.full[s], col, m0);
+        tma_load_2d(sm.b[s], &map_b, &sm.full[s], col, n0);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(BN);
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
+      for (int kb = 0; kb < n_exec; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&sm.full[s], ph);
@@ -385,7 +422,8 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int k, int ld,
 
 template <int BN, int STAGES>
 static int launch_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, float* D, int ldd, int M, int N,
-                     int K, int splits, size_t split_stride, cudaStream_t s) {
+                     int K, int splits, size_t split_stride, cudaStream_t s, const uint32_t* a_active = nullptr,
+                     const uint8_t* b_nonfinite = nullptr) {
   CUtensorMap ma, mb;
   int err = make_map(&ma, A, M, K, lda, kBM);
   if (err) return err;
@@ -397,7 +435,9 @@ static int launch_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, in
   const int total_kb = K / kBK;
   const int kb_per = ceil_div(total_kb, splits);
   dim3 grid(ceil_div(N, BN), ceil_div(M, kBM), ceil_div(total_kb, kb_per));
-  launch_chain(kern, grid, kGemmThreads, smem, s, ma, mb, D, ldd, M, N, total_kb, kb_per, split_stride);
+  const int nkb_seg = (a_active && K % (3 * kBK) == 0) ? K / 3 / kBK : 0;
+  launch_chain(kern, grid, kGemmThreads, smem, s, ma, mb, D, ldd, M, N, total_kb, kb_per, split_stride, a_active, b_nonfinite,
+               nkb_seg);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }
@@ -437,11 +477,12 @@ int g_gemm_shared_segments = 0;
 // splits > 1: split-K, partial tile z is written to D + z*split_stride (the caller sums the partials in a fixed
 // order); *splits_out receives the number of partials actually produced.
 int launch_gemm_tc(const void* A, int lda, const void* B, int ldb, float* D, int ldd, int M, int N, int K, int splits,
-                   size_t split_stride, int* splits_out, cudaStream_t s, bool low_latency) {
+                   size_t split_stride, int* splits_out, cudaStream_t s, bool low_latency, const uint32_t* a_active,
+                   const uint8_t* b_nonfinite) {
   if (splits_out) *splits_out = 1;
   if (M <= 0 || N <= 0) return NTTT_OK;
   if (K <= 0 || K % kBK != 0 || lda % 8 != 0 || ldb % 8 != 0 || splits < 1) return NTTT_EINVAL;
-  const bool shared = g_gemm_shared_segments != 0 && K % (3 * kBK) == 0;
+  const bool shared = g_gemm_shared_segments != 0 && K % (3 * kBK) == 0 && !a_active;
   const int total_kb = shared ? K / 3 / kBK : K / kBK;
   const int kb_per = ceil_div(total_kb, splits);
   if (splits_out) *splits_out = ceil_div(total_kb, kb_per);
@@ -463,11 +504,11 @@ int launch_gemm_tc(const void* A, int lda, const void* B, int ldb, float* D, int
     if (bn128) return launch_tc3<128, 6>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s);
     return launch_tc3<64, 8>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s);
   }
-  if (bn256 && g_gemm_bn256_stages == 2) return launch_tc<256, 2>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s);
-  if (bn256 && g_gemm_bn256_stages == 3) return launch_tc<256, 3>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s);
-  if (bn256) return launch_tc<256, 4>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s);
-  if (bn128) return launch_tc<128, 5>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s);
-  return launch_tc<64, 6>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s);
+  if (bn256 && g_gemm_bn256_stages == 2) return launch_tc<256, 2>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s, a_active, b_nonfinite);
+  if (bn256 && g_gemm_bn256_stages == 3) return launch_tc<256, 3>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s, a_active, b_nonfinite);
+  if (bn256) return launch_tc<256, 4>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s, a_active, b_nonfinite);
+  if (bn128) return launch_tc<128, 5>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s, a_active, b_nonfinite);
+  return launch_tc<64, 6>(a, lda, b, ldb, D, ldd, M, N, K, splits, split_stride, s, a_active, b_nonfinite);
 }
 
 // how many K splits fill the machine for an M x N output of 128 x 64 tiles (1 when the tiles already do)
@@ -510,19 +551,25 @@ split_rows_kernel(const float* __restrict__ X, int ld, int rows, int k, int kp, 
 // bf16x2, so a warp stores 128 contiguous bytes per segment (kp is a multiple of 64).
 __global__ void __launch_bounds__(256)
 split_transpose_kernel(const float* __restrict__ X, int ld, int rows, int k, int kp, int mode,
-                       __nv_bfloat16* __restrict__ out) {
+                       __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ nonfinite) {
+  // nonfinite (nullable) [kp / 64, ceil(rows / 32)]: 1 where the tile holds an inf or a NaN — a GEMM that skips k-blocks
+  // whose OTHER operand is all zeros must not skip those (0 * inf = NaN in the reference's dense product)
   __shared__ float tile[64][33];
   const int tiles_k = kp / 64, tiles_r = (rows + 31) / 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (int tile_id = blockIdx.x; tile_id < tiles_k * tiles_r; tile_id += gridDim.x) {  // (a few tiles per CTA)
     const int k0 = (tile_id % tiles_k) * 64, r0 = (tile_id / tiles_k) * 32;
     if (tile_id != (int)blockIdx.x) __syncthreads();  // the previous tile has been written out
+    int bad = 0;
 #pragma unroll
     for (int j = ty; j < 64; j += 8) {
       const int kk = k0 + j, rr = r0 + tx;
-      tile[j][tx] = (kk < k && rr < rows) ? X[(size_t)kk * ld + rr] : 0.0f;
+      const float v = (kk < k && rr < rows) ? X[(size_t)kk * ld + rr] : 0.0f;
+      bad |= (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u;
+      tile[j][tx] = v;
     }
-    __syncthreads();
+    bad = __syncthreads_or(bad);
+    if (nonfinite && threadIdx.x == 0) nonfinite[tile_id] = (uint8_t)(bad != 0);  // tile_id = r-tile * tiles_k + k-tile
     const int kk = k0 + 2 * tx;
 #pragma unroll
     for (int j = ty; j < 32; j += 8) {
@@ -549,12 +596,13 @@ int launch_split_rows(const float* X, int ld, int rows, int k, int kp, int mode,
   return NTTT_OK;
 }
 
-int launch_split_transpose(const float* X, int ld, int rows, int k, int kp, int mode, void* out, cudaStream_t s) {
+int launch_split_transpose(const float* X, int ld, int rows, int k, int kp, int mode, void* out, cudaStream_t s,
+                           uint8_t* nonfinite) {
   if (rows <= 0) return NTTT_OK;
   if (kp % 64 != 0) return NTTT_EINVAL;  // (callers pad K to 64: the GEMM's K block)
   const int tiles = (kp / 64) * ceil_div(rows, 32);
   const int grid = g_exp[5] > 0 ? min(tiles, g_exp[5]) : (t_low_latency ? tiles : min(tiles, 148));
-  split_transpose_kernel<<<grid, 256, 0, s>>>(X, ld, rows, k, kp, mode, static_cast<__nv_bfloat16*>(out));
+  split_transpose_kernel<<<grid, 256, 0, s>>>(X, ld, rows, k, kp, mode, static_cast<__nv_bfloat16*>(out), nonfinite);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }

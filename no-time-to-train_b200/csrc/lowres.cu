@@ -893,7 +893,8 @@ __device__ __forceinline__ void warp_range(int n, F flag, int& lo, int& hi) {
 template <bool kSplit>
 __global__ void __launch_bounds__(kProjThreads)
 project_masks_kernel(const uint32_t* __restrict__ bits, const int32_t* __restrict__ box, int n_masks, int h,
-                     int words_per_row, int eh, int ew, ProjTables t, void* __restrict__ out, int stride_or_kp) {
+                     int words_per_row, int eh, int ew, ProjTables t, void* __restrict__ out, int stride_or_kp,
+                     const int32_t* __restrict__ perm, uint32_t* __restrict__ active) {
   chain_wait();
   extern __shared__ uint32_t smem[];
   // layout: x_lo[ew] x_len[ew] y_lo[eh] y_len[eh] | bits[rc*wpr] | row[rc*ew] | acc[eh*ew]     (rc = min(h, kProjRows))
@@ -918,12 +919,15 @@ project_masks_kernel(const uint32_t* __restrict__ bits, const int32_t* __restric
   const int4 b = reinterpret_cast<const int4*>(box)[n];
   const uint32_t* src = bits + (size_t)n * h * words_per_row;
   const bool empty = (b.x | b.y | b.z | b.w) == 0 && (src[0] & 1u) == 0;
+  // perm (nullable): output row of mask n (the pooling GEMM then runs on spatially ordered rows, see pool_order_kernel);
+  // active (nullable): per OUTPUT row, the 64-wide k-blocks of the operand that hold anything but zeros
+  const int orow = perm ? perm[n] : n;
   const int top = b.y, bottom = b.w, left = b.x, right = b.z;
 
   // zero the whole output row first (128-bit stores); the cells the box reaches are overwritten below
   {
     const size_t row_bytes = kSplit ? (size_t)3 * stride_or_kp * 2 : (size_t)stride_or_kp * 4;
-    char* o = static_cast<char*>(out) + (size_t)n * row_bytes;
+    char* o = static_cast<char*>(out) + (size_t)orow * row_bytes;
     if ((row_bytes & 15) == 0) {
       for (int i = threadIdx.x; i < (int)(row_bytes >> 4); i += kProjThreads)
         reinterpret_cast<uint4*>(o)[i] = make_uint4(0, 0, 0, 0);
@@ -931,14 +935,33 @@ project_masks_kernel(const uint32_t* __restrict__ bits, const int32_t* __restric
       for (int i = threadIdx.x; i < (int)(row_bytes >> 2); i += kProjThreads) reinterpret_cast<uint32_t*>(o)[i] = 0;
     }
   }
-  if (empty) continue;  // (CTA-uniform)
+  if (empty) {  // (CTA-uniform)
+    if (active && threadIdx.x == 0) active[orow] = 0u;
+    continue;
+  }
   const int nrows = bottom - top + 1;
   // encoder cells whose spans touch the box
   int ex_lo, ex_hi, ey_lo, ey_hi;
   warp_range(ew, [&](int e) { return s_xlo[e] <= right && s_xlo[e] + s_xlen[e] > left; }, ex_lo, ex_hi);
   warp_range(eh, [&](int e) { return s_ylo[e] <= bottom && s_ylo[e] + s_ylen[e] > top; }, ey_lo, ey_hi);
   const int nex = ex_hi - ex_lo + 1;
-  if (nex <= 0 || ey_hi < ey_lo) continue;  // (CTA-uniform)
+  if (nex <= 0 || ey_hi < ey_lo) {  // (CTA-uniform)
+    if (active && threadIdx.x == 0) active[orow] = 0u;
+    continue;
+  }
+  if (active && warp == 0) {  // k-blocks touched by the cells [ey_lo, ey_hi] x [ex_lo, ex_hi] (cell index ey * ew + ex)
+    uint32_t m = 0;
+    if (eh * ew > 32 * 64) {
+      m = 0xffffffffu;  // more k-blocks than bits: everything counts as active
+    } else {
+      for (int ey = ey_lo + lane; ey <= ey_hi; ey += 32) {
+        const int k0 = (ey * ew + ex_lo) >> 6, k1 = (ey * ew + ex_hi) >> 6;
+        m |= (k1 - k0 >= 31 ? 0xffffffffu : ((2u << (k1 - k0)) - 1u)) << k0;
+      }
+    }
+    m = __reduce_or_sync(kFull, m);
+    if (lane == 0) active[orow] = m;
+  }
   // every cell (ey, ex) has ONE owner thread for the whole kernel: warp = (ey - ey_lo) % kWarps, lane = (ex - ex_lo) % 32
   for (int ey = ey_lo + warp; ey <= ey_hi; ey += kWarps)
     for (int ex = ex_lo + lane; ex <= ex_hi; ex += 32) s_acc[ey * ew + ex] = 0.0f;
@@ -993,12 +1016,12 @@ project_masks_kernel(const uint32_t* __restrict__ bits, const int32_t* __restric
       if (kSplit) {
         __nv_bfloat16 hi, lo16;
         split_bf16_pair(acc, hi, lo16);
-        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + (size_t)n * 3 * stride_or_kp;
+        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + (size_t)orow * 3 * stride_or_kp;
         o[item] = hi;
         o[stride_or_kp + item] = hi;
         o[2 * stride_or_kp + item] = lo16;
       } else {
-        static_cast<float*>(out)[(size_t)n * stride_or_kp + item] = acc;
+        static_cast<float*>(out)[(size_t)orow * stride_or_kp + item] = acc;
       }
     }
   }
@@ -1013,7 +1036,8 @@ static size_t project_smem_bytes(int h, int w, int eh, int ew) {
 
 // split=false: out = float [n, out_stride];  split=true: out = bf16 [n, 3*out_stride] with out_stride = kp
 int launch_project_masks(const AxisTable& tx, const AxisTable& ty, const uint32_t* bits, const int32_t* box, int n,
-                         int h, int w, int eh, int ew, void* out, int out_stride, bool split, cudaStream_t s) {
+                         int h, int w, int eh, int ew, void* out, int out_stride, bool split, cudaStream_t s,
+                         const int32_t* perm, uint32_t* active) {
   if (n <= 0) return NTTT_OK;
   if (w % 32 != 0 || eh > 64 || ew > 64) return NTTT_EUNSUPPORTED;
   const size_t smem = project_smem_bytes(h, w, eh, ew);
@@ -1028,12 +1052,87 @@ int launch_project_masks(const AxisTable& tx, const AxisTable& ty, const uint32_
   if (split) {
     if (smem > 48 * 1024)
       NTTT_CUDA(set_dyn_smem(project_masks_kernel<true>, (int)smem));
-    launch_chain(project_masks_kernel<true>, grid, kProjThreads, smem, s, bits, box, n, h, w / 32, eh, ew, t, out, out_stride);
+    launch_chain(project_masks_kernel<true>, grid, kProjThreads, smem, s, bits, box, n, h, w / 32, eh, ew, t, out, out_stride, perm,
+                 active);
   } else {
     if (smem > 48 * 1024)
       NTTT_CUDA(set_dyn_smem(project_masks_kernel<false>, (int)smem));
-    project_masks_kernel<false><<<grid, kProjThreads, smem, s>>>(bits, box, n, h, w / 32, eh, ew, t, out, out_stride);
+    project_masks_kernel<false><<<grid, kProjThreads, smem, s>>>(bits, box, n, h, w / 32, eh, ew, t, out, out_stride, perm, active);
   }
+  NTTT_LAUNCH_CHECK();
+  return NTTT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Spatial order of the masks for the pooling GEMM.  A projected mask touches only the encoder cells around its box —
+// a quarter of the operand's 64-wide k-blocks on average — but a 128-row tile of masks in arbitrary order touches all
+// of them.  Rows ordered by (bottom edge, top edge) of the low-res box make the union of a tile ~55 % of the k-blocks,
+// and gemm_tc_kernel skips the rest (zeros times anything finite).  One CTA: counting sort over 64 x 64 bins of
+// (bottom >> 2, top >> 2); ranks inside a bin are handed out by an atomic, so the order inside a bin is arbitrary — the
+// row a mask lands in changes nothing in its result.  perm[n] = row of mask n.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kOrderBins = 64 * 64;
+__global__ void __launch_bounds__(1024)
+pool_order_kernel(const int32_t* __restrict__ box, int n, int h, int32_t* __restrict__ perm) {
+  chain_wait();
+  __shared__ int s_hist[kOrderBins];
+  __shared__ int s_warp[33];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kOrderBins; i += 1024) s_hist[i] = 0;
+  __syncthreads();
+  const int shift = 32 - __clz((h - 1) >> 6);  // rows -> at most 64 bins (h = 256: >> 2)
+  constexpr int kMaxPer = 8;  // n <= 8192
+  int key[kMaxPer], rank[kMaxPer];
+#pragma unroll
+  for (int q = 0; q < kMaxPer; ++q) {
+    const int i = q * 1024 + tid;
+    key[q] = -1;
+    if (i < n) {
+      const int4 b = reinterpret_cast<const int4*>(box)[i];
+      key[q] = min(b.w >> shift, 63) * 64 + min(b.y >> shift, 63);
+      rank[q] = atomicAdd(&s_hist[key[q]], 1);
+    }
+  }
+  __syncthreads();
+  // exclusive scan of the 4096 bins: four consecutive bins per thread
+  int c0 = s_hist[4 * tid], c1 = s_hist[4 * tid + 1], c2 = s_hist[4 * tid + 2], c3 = s_hist[4 * tid + 3];
+  const int mine = c0 + c1 + c2 + c3;
+  int inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += up;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = s_warp[lane];
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(kFull, winc, o);
+      if (lane >= o) winc += up;
+    }
+    s_warp[lane] = winc - w;
+  }
+  __syncthreads();
+  const int base = s_warp[warp] + inc - mine;
+  s_hist[4 * tid] = base;
+  s_hist[4 * tid + 1] = base + c0;
+  s_hist[4 * tid + 2] = base + c0 + c1;
+  s_hist[4 * tid + 3] = base + c0 + c1 + c2;
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < kMaxPer; ++q) {
+    const int i = q * 1024 + tid;
+    if (i < n) perm[i] = s_hist[key[q]] + rank[q];
+  }
+}
+
+int launch_pool_order(const int32_t* box, int n, int h, int32_t* perm, cudaStream_t s) {
+  if (n <= 0) return NTTT_OK;
+  if (n > 8192) return NTTT_EUNSUPPORTED;
+  launch_chain(pool_order_kernel, 1, 1024, 0, s, box, n, h, perm);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }

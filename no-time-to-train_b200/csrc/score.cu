@@ -44,7 +44,8 @@ normalize_rows_kernel(const float* __restrict__ sums, int n_partials, const int3
 template <int kVec>  // float4 per lane, c = 128 * kVec
 __global__ void __launch_bounds__(256)
 normalize_split_kernel(const float* __restrict__ sums, int n_partials, const int32_t* __restrict__ area, int n, int cp,
-                       float* __restrict__ out, __nv_bfloat16* __restrict__ split, bool nan_empty) {
+                       float* __restrict__ out, __nv_bfloat16* __restrict__ split, bool nan_empty,
+                       const int32_t* __restrict__ perm) {
   chain_wait();
   constexpr int c = 128 * kVec;
   const int row = blockIdx.x * 8 + warp_id();
@@ -52,7 +53,8 @@ normalize_split_kernel(const float* __restrict__ sums, int n_partials, const int
   const int lane = lane_id();
   float denom = 1.0f;
   if (area) { const int a = area[row]; denom = (a == 0 && !nan_empty) ? 1.0f : (float)a; }
-  const float4* src = reinterpret_cast<const float4*>(sums + (size_t)row * c);
+  // perm (nullable): the pooling GEMM ran on spatially ordered rows; mask `row` sits at sums row perm[row]
+  const float4* src = reinterpret_cast<const float4*>(sums + (size_t)(perm ? perm[row] : row) * c);
   float4 v[kVec];
 #pragma unroll
   for (int i = 0; i < kVec; ++i) v[i] = src[i * 32 + lane];
@@ -104,16 +106,16 @@ normalize_split_kernel(const float* __restrict__ sums, int n_partials, const int
 
 // returns 1 if the fused vector path ran (split written), 0 if the caller must use the generic kernels
 int launch_normalize_split(const float* sums, int n_partials, const int32_t* area, int n, int c, int cp, float* out,
-                           void* split, bool nan_empty, cudaStream_t s) {
+                           void* split, bool nan_empty, cudaStream_t s, const int32_t* perm) {
   if (n <= 0) return 1;
   if (c % 128 != 0 || cp != c) return 0;
   const int grid = ceil_div(n, 8);
   __nv_bfloat16* sp = static_cast<__nv_bfloat16*>(split);
   switch (c / 128) {
-    case 3: launch_chain(normalize_split_kernel<3>, grid, 256, 0, s, sums, n_partials, area, n, cp, out, sp, nan_empty); break;
-    case 6: launch_chain(normalize_split_kernel<6>, grid, 256, 0, s, sums, n_partials, area, n, cp, out, sp, nan_empty); break;
-    case 8: launch_chain(normalize_split_kernel<8>, grid, 256, 0, s, sums, n_partials, area, n, cp, out, sp, nan_empty); break;
-    case 12: launch_chain(normalize_split_kernel<12>, grid, 256, 0, s, sums, n_partials, area, n, cp, out, sp, nan_empty); break;
+    case 3: launch_chain(normalize_split_kernel<3>, grid, 256, 0, s, sums, n_partials, area, n, cp, out, sp, nan_empty, perm); break;
+    case 6: launch_chain(normalize_split_kernel<6>, grid, 256, 0, s, sums, n_partials, area, n, cp, out, sp, nan_empty, perm); break;
+    case 8: launch_chain(normalize_split_kernel<8>, grid, 256, 0, s, sums, n_partials, area, n, cp, out, sp, nan_empty, perm); break;
+    case 12: launch_chain(normalize_split_kernel<12>, grid, 256, 0, s, sums, n_partials, area, n, cp, out, sp, nan_empty, perm); break;
     default: return 0;
   }
   ++g_launches;
