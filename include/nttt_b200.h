@@ -81,7 +81,8 @@ void nttt_ctx_destroy(nttt_ctx* ctx);
  *                                   are in flight (low-latency mode always uses 7).  Measured 89.8 (1) / 90.7 (2) / 91.2 (3) /
  *                                   91.9 (7) us/image.  Process-wide.
  *   NTTT_TUNE_EXPERIMENT + i        (i = 0..7) launch-shape experiment slots used by tools/ and `bench.py --tune expI=V`
- *                                   for A/B runs (grid sizes of single kernels, programmatic dependent launch off);
+ *                                   for A/B runs (grid sizes of single kernels, slot 1 = 1: pooling GEMM on unordered rows
+ *                                   without k-block skipping, slot 6 = 1: programmatic dependent launch off);
  *                                   0 = the built-in default.  Results never depend on them. */
 enum { NTTT_TUNE_UPSAMPLE_STAGE_BYTES = 1, NTTT_TUNE_LOWRES_EXTRA_SMEM = 2, NTTT_TUNE_GEMM_BN256_MIN_M = 3,
        NTTT_TUNE_AXIS_CACHE_ENTRIES = 4, NTTT_TUNE_LOWRES_PERSISTENT = 5, NTTT_TUNE_GEMM_SHARED_SEGMENTS = 6,
