@@ -24,23 +24,27 @@ __device__ __forceinline__ uint32_t pk_smem_u32(const void* p) { return (uint32_
 __device__ __forceinline__ void pk_mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pk_smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void pk_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pk_smem_u32(bar)), "r"(bytes) : "memory");
+// (the barrier helpers of the streaming loops take SHARED-SPACE ADDRESSES computed once per kernel: converting the generic
+//  pointer on every call was 11 % of the low-res pass's instructions)
+__device__ __forceinline__ void pk_mbar_expect_tx(uint32_t bar_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void pk_mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pk_smem_u32(bar)) : "memory");
+__device__ __forceinline__ void pk_mbar_arrive(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
-// bounded wait: a lost arrive traps (CUDA error) instead of hanging the GPU
-__device__ __forceinline__ void pk_mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = pk_smem_u32(bar);
-  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+// Bounded wait: a lost arrive traps (CUDA error) instead of hanging the GPU.  The try_wait carries a suspend-time hint:
+// the warp sleeps in the instruction until the phase completes (or ~4 us pass) instead of coming back after the short
+// default limit — the kernel is HBM-bound, its consumer warps wait most of the time, and every spin of the old loop was
+// seven issue slots taken from the other kernels on the SM (a third of this kernel's 18 M warp instructions).
+__device__ __forceinline__ void pk_mbar_wait(uint32_t bar_addr, uint32_t parity) {
+  for (uint32_t spin = 0; spin < (1u << 20); ++spin) {
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(bar_addr), "r"(parity), "r"(4000u)
         : "memory");
     if (done) return;
   }
@@ -54,18 +58,18 @@ __device__ __forceinline__ uint64_t pk_policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
-__device__ __forceinline__ void pk_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+__device__ __forceinline__ void pk_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar_addr,
                                              uint64_t policy) {
 #ifdef NTTT_PACK_NO_L2_HINT
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    pk_smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(pk_smem_u32(bar))
+               "l"(gsrc), "r"(bytes), "r"(bar_addr)
                : "memory");
 #else
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
           pk_smem_u32(smem_dst)),
-      "l"(gsrc), "r"(bytes), "r"(pk_smem_u32(bar)), "l"(policy)
+      "l"(gsrc), "r"(bytes), "r"(bar_addr), "l"(policy)
       : "memory");
 #endif
 }
@@ -101,6 +105,7 @@ lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mas
   float4* s_stage = reinterpret_cast<float4*>(s_raw);                                        // ring
   uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_raw + (size_t)kPackStages * kPackStageBytes);  // p4/8 words
   __shared__ uint64_t s_full[kPackStages], s_empty[kPackStages];
+  const uint32_t full_a = pk_smem_u32(s_full), empty_a = pk_smem_u32(s_empty);
   __shared__ int s_red[8];  // area, hi, lo, unsafe, minx, miny, maxx, maxy
   const int n = blockIdx.x;
   // mask_ptr (nullable): where the decoder left mask n's logits (multimask_select_kernel); else the dense [n,h,w] array
@@ -122,10 +127,10 @@ lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mas
       const uint64_t l2_policy = pk_policy_evict_first();
       for (int st = 0; st < n_stages; ++st) {
         const int q = st % kPackStages;
-        pk_mbar_wait(&s_empty[q], ((st / kPackStages) & 1) ^ 1);
+        pk_mbar_wait(empty_a + 8u * q, ((st / kPackStages) & 1) ^ 1);
         const int f4 = min(kPackStageF4, p4 - st * kPackStageF4);
-        pk_mbar_expect_tx(&s_full[q], (uint32_t)f4 * 16u);
-        pk_bulk_load(s_stage + (size_t)q * kPackStageF4, src + (size_t)st * kPackStageF4, (uint32_t)f4 * 16u, &s_full[q], l2_policy);
+        pk_mbar_expect_tx(full_a + 8u * q, (uint32_t)f4 * 16u);
+        pk_bulk_load(s_stage + (size_t)q * kPackStageF4, src + (size_t)st * kPackStageF4, (uint32_t)f4 * 16u, full_a + 8u * q, l2_policy);
       }
     }
   } else {
@@ -134,7 +139,7 @@ lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mas
     constexpr uint32_t kLoBits = 0x0D800000u, kSpan = 0x71800000u - 0x0D800001u;
     for (int st = 0; st < n_stages; ++st) {
       const int q = st % kPackStages;
-      pk_mbar_wait(&s_full[q], (st / kPackStages) & 1);
+      pk_mbar_wait(full_a + 8u * q, (st / kPackStages) & 1);
       const float4* buf = s_stage + (size_t)q * kPackStageF4;
       float4 v[4];
 #pragma unroll
@@ -142,7 +147,7 @@ lowres_pack_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 per mas
         v[u] = (st * kPackStageF4 + u * kPackThreads + (int)threadIdx.x < p4) ? buf[u * kPackThreads + threadIdx.x]
                                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
       __syncwarp();
-      if (lane == 0) pk_mbar_arrive(&s_empty[q]);  // this warp has copied its share out of the slot
+      if (lane == 0) pk_mbar_arrive(empty_a + 8u * q);  // this warp has copied its share out of the slot
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int qi = st * kPackStageF4 + u * kPackThreads + threadIdx.x;
@@ -271,6 +276,7 @@ lowres_pack_fast_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 pe
   uint4* s_stage = reinterpret_cast<uint4*>(s_raw);
   uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_raw + (size_t)kPackStages * kPackStageBytes);
   __shared__ uint64_t s_full[kPackStages], s_empty[kPackStages];
+  const uint32_t full_a = pk_smem_u32(s_full), empty_a = pk_smem_u32(s_empty);
   __shared__ int s_red[8];  // area, -, -, unsafe, minx, miny, maxx, maxy
   const int n = blockIdx.x;
   const float4* src = mask_ptr ? reinterpret_cast<const float4*>(mask_ptr[n]) : logits + (size_t)n * p4;
@@ -289,10 +295,10 @@ lowres_pack_fast_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 pe
       const uint64_t l2_policy = pk_policy_evict_first();
       for (int st = 0; st < n_stages; ++st) {
         const int q = st % kPackStages;
-        pk_mbar_wait(&s_empty[q], ((st / kPackStages) & 1) ^ 1);
+        pk_mbar_wait(empty_a + 8u * q, ((st / kPackStages) & 1) ^ 1);
         const int f4 = min(kPackStageF4, p4 - st * kPackStageF4);
-        pk_mbar_expect_tx(&s_full[q], (uint32_t)f4 * 16u);
-        pk_bulk_load(s_stage + (size_t)q * kPackStageF4, src + (size_t)st * kPackStageF4, (uint32_t)f4 * 16u, &s_full[q], l2_policy);
+        pk_mbar_expect_tx(full_a + 8u * q, (uint32_t)f4 * 16u);
+        pk_bulk_load(s_stage + (size_t)q * kPackStageF4, src + (size_t)st * kPackStageF4, (uint32_t)f4 * 16u, full_a + 8u * q, l2_policy);
       }
     }
   } else {
@@ -313,7 +319,7 @@ lowres_pack_fast_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 pe
     bool exact = false;
     for (int st = 0; st < n_stages; ++st) {
       const int q = st % kPackStages;
-      pk_mbar_wait(&s_full[q], (st / kPackStages) & 1);
+      pk_mbar_wait(full_a + 8u * q, (st / kPackStages) & 1);
       const uint4* buf = s_stage + (size_t)q * kPackStageF4;
       const int f0 = st * kPackStageF4;
       uint4 v[4];
@@ -326,7 +332,7 @@ lowres_pack_fast_kernel(const float4* __restrict__ logits, int p4 /* pixels/4 pe
           v[j] = (f0 + (off[j] & ~7) < p4) ? buf[off[j]] : make_uint4(0xbf800000u, 0xbf800000u, 0xbf800000u, 0xbf800000u);
       }
       __syncwarp();
-      if (lane == 0) pk_mbar_arrive(&s_empty[q]);
+      if (lane == 0) pk_mbar_arrive(empty_a + 8u * q);
       uint32_t a01 = 0, a23 = 0;  // sign bits: slot 0 in bits 0-3, slot 1 in bits 4-7 (resp. slots 2, 3)
       if (!exact) {
         a01 = pk_sign_chain(pk_sign_chain(0u, v[1]), v[0]);
@@ -425,6 +431,7 @@ lowres_pack_persistent_kernel(const float4* __restrict__ logits, int n_masks, in
   const int n_words = p4 >> 3;
   uint32_t* s_bits0 = reinterpret_cast<uint32_t*>(s_raw + (size_t)kPersistStages * kPackStageBytes);  // 2 x n_words
   __shared__ uint64_t s_full[kPersistStages], s_empty[kPersistStages];
+  const uint32_t full_a = pk_smem_u32(s_full), empty_a = pk_smem_u32(s_empty);
   __shared__ int s_part[2][kPackThreads / 32][8];  // per warp: area, unsafe, minx, miny, maxx, maxy
   __shared__ int s_done[2];
   const int lane = lane_id(), warp = warp_id();
@@ -446,10 +453,10 @@ lowres_pack_persistent_kernel(const float4* __restrict__ logits, int n_masks, in
         const float4* src = mask_ptr ? reinterpret_cast<const float4*>(mask_ptr[n]) : logits + (size_t)n * p4;
         for (int st = 0; st < n_stages; ++st, ++sg) {
           const int q = sg % kPersistStages;
-          pk_mbar_wait(&s_empty[q], ((sg / kPersistStages) & 1) ^ 1);
+          pk_mbar_wait(empty_a + 8u * q, ((sg / kPersistStages) & 1) ^ 1);
           const int f4 = min(kPackStageF4, p4 - st * kPackStageF4);
-          pk_mbar_expect_tx(&s_full[q], (uint32_t)f4 * 16u);
-          pk_bulk_load(s_stage + (size_t)q * kPackStageF4, src + (size_t)st * kPackStageF4, (uint32_t)f4 * 16u, &s_full[q], l2_policy);
+          pk_mbar_expect_tx(full_a + 8u * q, (uint32_t)f4 * 16u);
+          pk_bulk_load(s_stage + (size_t)q * kPackStageF4, src + (size_t)st * kPackStageF4, (uint32_t)f4 * 16u, full_a + 8u * q, l2_policy);
         }
       }
     }
@@ -490,7 +497,7 @@ lowres_pack_persistent_kernel(const float4* __restrict__ logits, int n_masks, in
     bool exact = false;
     for (int st = 0; st < n_stages; ++st, ++sg) {
       const int q = sg % kPersistStages;
-      pk_mbar_wait(&s_full[q], (sg / kPersistStages) & 1);
+      pk_mbar_wait(full_a + 8u * q, (sg / kPersistStages) & 1);
       const uint4* sbuf = s_stage + (size_t)q * kPackStageF4;
       const int f0 = st * kPackStageF4;
       uint4 v[4];
@@ -503,7 +510,7 @@ lowres_pack_persistent_kernel(const float4* __restrict__ logits, int n_masks, in
           v[j] = (f0 + (off[j] & ~7) < p4) ? sbuf[off[j]] : make_uint4(0xbf800000u, 0xbf800000u, 0xbf800000u, 0xbf800000u);
       }
       __syncwarp();
-      if (lane == 0) pk_mbar_arrive(&s_empty[q]);
+      if (lane == 0) pk_mbar_arrive(empty_a + 8u * q);
       uint32_t a01 = 0, a23 = 0;
       if (!exact) {
         a01 = pk_sign_chain(pk_sign_chain(0u, v[1]), v[0]);
