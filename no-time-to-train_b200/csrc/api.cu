@@ -35,7 +35,8 @@ int launch_box_nms(const int32_t*, const float*, const int32_t*, const float*, i
 int launch_upsample_pack(const AxisTable&, const AxisTable&, const float*, const uint32_t*, const int32_t*,
                          const int32_t*, int, int, const int32_t*, const int32_t*, int, int, int, uint32_t*, int32_t*,
                          int32_t*, int32_t*, int32_t*, const float* const*, cudaStream_t, int, int, uint32_t* bits_t = nullptr,
-                         bool* wrote_t = nullptr, bool t_only = false, bool low_latency = false);
+                         bool* wrote_t = nullptr, bool t_only = false, bool low_latency = false, int32_t* zero2 = nullptr);
+int32_t* ios_pair_counters(void* ws, int max_sel);
 size_t upsample_scratch_bytes(int max_sel, int oh, int ow);
 int launch_unpack_sparse(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, uint8_t*,
                          int32_t*, cudaStream_t, bool tr = false);
@@ -44,7 +45,7 @@ int launch_unpack(const uint32_t*, const int32_t*, const int32_t*, const int32_t
 size_t ios_workspace_bytes(int max_sel);
 int launch_mask_ios(const uint32_t*, const int32_t*, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
                     int, int, int, const int32_t*, const float*, int, float*, int32_t*, void*, bool, cudaStream_t,
-                    const uint32_t* bits_t = nullptr);
+                    const uint32_t* bits_t = nullptr, bool counters_zeroed = false);
 int launch_decay_rank(const float*, const int32_t*, const float*, const int32_t*, const int32_t*, int, int,
                       const int32_t*, const int32_t*, int64_t*, float*, int64_t*, int32_t*, int32_t*, int32_t*, float*,
                       cudaStream_t);
@@ -901,13 +902,14 @@ int nttt_match_image(nttt_ctx* ctx, const nttt_match_args* a, void* stream) {
   NTTT_STEP(launch_upsample_pack(ux, uy, a->logits, L.bits_lr, L.box_lr, L.flags, a->lr_h, a->lr_w, L.sel,
                                  a->counts + 1, max_sel, a->ori_h, a->ori_w, L.bits_full, L.rect, L.area_full,
                                  L.box_full, L.scratch, mask_ptr, s, ctx->upsample_stage_floats, ctx->sm_count, L.bits_t,
-                                 &wrote_t, /*t_only=*/true, a->low_latency != 0));
+                                 &wrote_t, /*t_only=*/true, a->low_latency != 0, ios_pair_counters(L.ios_ws, max_sel)));
   // the packed full-resolution masks from here on: word-column major when the v2 resize ran, row-major otherwise
   const uint32_t* packed = wrote_t ? L.bits_t : L.bits_full;
   // a13
   NTTT_STEP(launch_mask_ios(L.bits_full, L.rect, L.area_full, L.box_full, L.sel, a->counts + 1, max_sel, a->ori_h,
                             a->ori_w, L.top_label, obj_feats, a->c, L.ios, nullptr, L.ios_ws, false, s,
-                            wrote_t ? L.bits_t : nullptr));
+                            wrote_t ? L.bits_t : nullptr, /*counters_zeroed=*/wrote_t && a->low_latency != 0 && g_exp[4] != 1));  // (folding the metadata
+  // kernel into the pair kernel takes 1 us off a single image's chain and costs 0.3 us/image with images in flight)
   // a14
   NTTT_STEP(launch_decay_rank(L.top_score, L.top_label, L.ios, L.sel, a->counts + 1, max_sel, num_out, L.box_full,
                               L.area_full,

@@ -682,8 +682,10 @@ __global__ void __launch_bounds__(kUp2Threads, kUp2CtasPerSm)
 upsample_pack2_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __restrict__ meta, int ih, int iw, int oh,
                       int ow, UpTables t, uint32_t* __restrict__ bits_full, uint32_t* __restrict__ bits_t,
                       int32_t* __restrict__ area_full, int32_t* __restrict__ box_full, int32_t* __restrict__ scratch,
-                      const Up2Item* __restrict__ items, int32_t* __restrict__ ctr) {
+                      const Up2Item* __restrict__ items, int32_t* __restrict__ ctr, int32_t* __restrict__ zero2) {
   chain_wait();
+  // (nullable) two counters of the NEXT stage, zeroed here so that its first kernel can append to them right away
+  if (zero2 && blockIdx.x == 0 && threadIdx.x == 0) { zero2[0] = 0; zero2[1] = 0; }
   extern __shared__ __align__(16) unsigned char s_raw[];
   float4* s_pkx = reinterpret_cast<float4*>(s_raw);                       // [kUp2Cols * 32]
   float4* s_pky = s_pkx + kUp2Cols * 32;                                  // [kUp2Rows + kGrpMax] (rows past the end are read)
@@ -919,7 +921,7 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
                          const int32_t* n_sel, int max_sel, int oh, int ow, uint32_t* bits_full, int32_t* rect,
                          int32_t* area_full, int32_t* box_full, int32_t* scratch, const float* const* mask_ptr,
                          cudaStream_t s, int stage_floats, int sm_count, uint32_t* bits_t, bool* wrote_t, bool t_only,
-                         bool low_latency) {
+                         bool low_latency, int32_t* zero2) {
   // bits_t (nullable): also write the word-column-major copy [k][word][row]; t_only: and skip the row-major one
   // (every consumer of the fused pipeline reads the transposed layout).  *wrote_t tells whether the v2 path ran.
   if (wrote_t) *wrote_t = false;
@@ -950,7 +952,7 @@ int launch_upsample_pack(const AxisTable& tx, const AxisTable& ty, const float* 
     const int grid = (sm_count > 0 ? sm_count : 148) * (low_latency ? kUp2CtasPerSm : g_up2_ctas_per_sm);
     launch_chain(upsample_pack2_kernel, grid, kUp2Threads, smem, s, bits_lr, meta, ih, iw, oh, ow, t,
                                                           (bits_t && t_only) ? nullptr : bits_full, bits_t, area_full,
-                                                          box_full, scratch, items, ctr);
+                                                          box_full, scratch, items, ctr, zero2);
     NTTT_LAUNCH_CHECK();
     if (wrote_t) *wrote_t = bits_t != nullptr;
     return NTTT_OK;

@@ -98,6 +98,65 @@ ios_pairs_kernel(const IosMeta* __restrict__ meta, const int32_t* __restrict__ l
   }
 }
 
+// The same pair generation with the metadata kernel folded in (nttt_match_image: one launch less on the chain of a single
+// image).  n_pairs was zeroed by the resize kernel that ran before.  Nothing a CTA reads here is written by another CTA of
+// this launch: partners are described from the raw arrays (sel -> labels, area_full, box_full), and the compacted
+// records `meta[]` that the evaluation kernel reads are written on the side, each by the thread that owns the row.
+__global__ void __launch_bounds__(256)
+ios_pairs_fused_kernel(const int32_t* __restrict__ rect, const int32_t* __restrict__ area_full,
+                       const int32_t* __restrict__ box_full, const int32_t* __restrict__ sel,
+                       const int32_t* __restrict__ n_sel, int max_sel, const int32_t* __restrict__ labels,
+                       IosMeta* __restrict__ meta, float* __restrict__ ios, int2* __restrict__ pairs,
+                       int32_t* __restrict__ n_pairs, int max_pairs) {
+  chain_wait();
+  const int nsel = min(*n_sel, max_sel);
+  const int lane = lane_id();
+  for (int j = blockIdx.x * 256 + threadIdx.x; j < max_sel; j += gridDim.x * 256) {
+    ios[j] = 0.0f;  // identity of the row max (the zeroed diagonal, area > 0 case)
+    if (j < nsel) {
+      IosMeta m;
+      m.src = sel[j];
+      m.label = labels[m.src];
+      m.area = area_full[j];
+      m.box = reinterpret_cast<const int4*>(box_full)[j];
+      m.rect = reinterpret_cast<const int4*>(rect)[j];
+      m.pad = 0;
+      meta[j] = m;
+    }
+  }
+  for (int i = blockIdx.x; i < nsel; i += gridDim.x) {  // (row i has nsel - i - 1 partners: striding balances the CTAs)
+    const int my_area = area_full[i];
+    if (my_area == 0) continue;
+    const int my_label = labels[sel[i]];
+    const int4 my_box = reinterpret_cast<const int4*>(box_full)[i];
+    for (int base = i + 1; base < nsel; base += 256) {
+      const int j = base + threadIdx.x;
+      bool hit = false, big = false;
+      if (j < nsel && labels[sel[j]] == my_label) {
+        const int4 bj = reinterpret_cast<const int4*>(box_full)[j];
+        const int x0 = max(my_box.x, bj.x), x1 = min(my_box.z, bj.z);
+        const int y0 = max(my_box.y, bj.y), y1 = min(my_box.w, bj.w);
+        hit = area_full[j] > 0 && x0 <= x1 && y0 <= y1;
+        big = hit && ((x1 >> 5) - (x0 >> 5) + 1) * (y1 - y0 + 1) > kIosBigWords;
+      }
+      const uint32_t mb = __ballot_sync(kFull, big);
+      const uint32_t m = __ballot_sync(kFull, hit) & ~mb;
+      if (m) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(&n_pairs[0], __popc(m));
+        slot = __shfl_sync(kFull, slot, 0) + __popc(m & ((1u << lane) - 1u));
+        if (hit && !big) pairs[slot] = make_int2(i, j);
+      }
+      if (mb) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(&n_pairs[1], __popc(mb));
+        slot = __shfl_sync(kFull, slot, 0) + __popc(mb & ((1u << lane) - 1u));
+        if (big) pairs[max_pairs - 1 - slot] = make_int2(i, j);
+      }
+    }
+  }
+}
+
 // Pairs with a LARGE overlap window (> kIosBigWords words): one CTA per pair (grid-stride over the big list, which
 // grows from the back of the pair buffer): the window is spread over all threads with four load pairs in flight,
 // one block reduction.  A single warp would take tens of microseconds on a 1000 x 32-word window.  Runs as the tail of
@@ -285,11 +344,20 @@ ios_finalize_kernel(const int32_t* __restrict__ area_full, const int32_t* __rest
   if (j < min(*n_sel, max_sel) && area_full[j] == 0) ios[j] = __int_as_float(0x7fc00000);
 }
 
+// the two pair counters inside the workspace (small list, big list)
+int32_t* ios_pair_counters(void* ws, int max_sel) {
+  char* w8 = static_cast<char*>(ws);
+  char* pairs = w8 + align_up(sizeof(IosMeta) * (size_t)max_sel, 256) + align_up(sizeof(int32_t) * (size_t)max_sel, 256);
+  return reinterpret_cast<int32_t*>(pairs + align_up(sizeof(int2) * ios_max_pairs(max_sel), 256));
+}
+
 // finalize=false leaves the NaN rows to the consumer (decay_rank_kernel applies the same rule)
 int launch_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_t* area_full, const int32_t* box_full,
                     const int32_t* sel, const int32_t* n_sel, int max_sel, int oh, int ow, const int32_t* labels,
                     const float* obj_feats, int c, float* ios, int32_t* inter_out, void* ws, bool finalize,
-                    cudaStream_t s, const uint32_t* bits_t) {
+                    cudaStream_t s, const uint32_t* bits_t, bool counters_zeroed) {
+  // counters_zeroed: the pair counters (ios_pair_counters(ws, max_sel)) were set to zero by an earlier kernel of the
+  // same stream — the metadata kernel is then folded into the pair kernel
   if (max_sel <= 0) return NTTT_OK;
   if (inter_out) NTTT_CUDA(cudaMemsetAsync(inter_out, 0, sizeof(int32_t) * (size_t)max_sel * max_sel, s));
   char* w8 = static_cast<char*>(ws);
@@ -304,12 +372,19 @@ int launch_mask_ios(const uint32_t* bits_full, const int32_t* rect, const int32_
 #else
   constexpr int ios_stop = 0;
 #endif
-  launch_chain(ios_meta_kernel, ceil_div(max_sel, 256), 256, 0, s, rect, area_full, box_full, sel, n_sel, max_sel, labels, meta,
-                                                         label_sel, ios, n_pairs);
-  NTTT_LAUNCH_CHECK();
-  if (ios_stop == 1) return NTTT_OK;
-  launch_chain(ios_pairs_kernel, g_exp[3] > 0 ? min(max_sel, g_exp[3]) : (t_low_latency ? max_sel : min(max_sel, 148)), 256, 0, s, meta, label_sel, n_sel, max_sel, pairs, n_pairs, max_pairs);
-  NTTT_LAUNCH_CHECK();
+  const int pair_grid = g_exp[3] > 0 ? min(max_sel, g_exp[3]) : (t_low_latency ? max_sel : min(max_sel, 148));
+  if (counters_zeroed && ios_stop == 0) {
+    launch_chain(ios_pairs_fused_kernel, pair_grid, 256, 0, s, rect, area_full, box_full, sel, n_sel, max_sel, labels, meta, ios,
+                 pairs, n_pairs, max_pairs);
+    NTTT_LAUNCH_CHECK();
+  } else {
+    launch_chain(ios_meta_kernel, ceil_div(max_sel, 256), 256, 0, s, rect, area_full, box_full, sel, n_sel, max_sel, labels, meta,
+                 label_sel, ios, n_pairs);
+    NTTT_LAUNCH_CHECK();
+    if (ios_stop == 1) return NTTT_OK;
+    launch_chain(ios_pairs_kernel, pair_grid, 256, 0, s, meta, label_sel, n_sel, max_sel, pairs, n_pairs, max_pairs);
+    NTTT_LAUNCH_CHECK();
+  }
   if (ios_stop == 2) return NTTT_OK;
   // one CTA per SM when many images are in flight (measured 89.4 vs 90.0 us/image with four), four for one image alone
   launch_chain(ios_eval_kernel, g_exp[0] > 0 ? g_exp[0] : (t_low_latency ? 148 * 4 : 148), kIosThreads, 0, s, bits_full, bits_t, meta, pairs, n_pairs, max_pairs, max_sel, oh, ow, obj_feats,
