@@ -493,7 +493,9 @@ int launch_gemm_tc(const void* A, int lda, const void* B, int ldb, float* D, int
   // 128 x 256 tiles halve the CTA count and raise the flops per operand byte by a third.  With many images in flight
   // the stage's throughput follows the SM-time a kernel consumes, not its latency: 32 CTAs x 38 us beat 64 CTAs x 25 us
   // at 1024 rows (97.9 vs 100.3 us/image), and at 4096 rows one wave of 128 CTAs beats 1.7 waves of 256 (281 vs 292).
-  const bool bn256 = !low_latency && N >= 512 && N % 256 == 0 && M >= g_gemm_bn256_min_m;
+  // (N need not be a multiple of 256: TMA zero-fills the rows past N and the epilogue bounds its stores; g_exp[7] = 2
+  //  restores the former N % 256 == 0 rule for A/B runs)
+  const bool bn256 = !low_latency && N >= 512 && (N % 256 == 0 || g_exp[7] != 2) && M >= g_gemm_bn256_min_m;
 #ifndef NTTT_SIM_NO_BN128
   const bool bn128 = N >= 512 || (N > 64 && N <= 128);  // 65..128 columns: ONE 128-wide tile reads the A operand once instead of twice
 #else
