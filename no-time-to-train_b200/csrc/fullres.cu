@@ -737,7 +737,12 @@ upsample_pack2_kernel(const uint32_t* __restrict__ bits_lr, const UpMeta* __rest
     {
       const uint32_t* lr = bits_lr + ((size_t)mt.src * ih + clr0) * lr_wpr;
       const int n_lr = tr * lr_wpr;
-      for (int i = tid; i < n_lr; i += kUp2Threads) cp_async4(s_lr + i, lr + i);
+      // (rows of iw / 32 words: 16-byte chunks when the row length allows, which every multiple of 128 pixels does)
+      if ((lr_wpr & 3) == 0 && (reinterpret_cast<uintptr_t>(lr) & 15) == 0) {
+        for (int i = tid; i < (n_lr >> 2); i += kUp2Threads) cp_async16_ca(s_lr + 4 * i, lr + 4 * i);
+      } else {
+        for (int i = tid; i < n_lr; i += kUp2Threads) cp_async4(s_lr + i, lr + i);
+      }
       for (int i = tid; i < n_rows; i += kUp2Threads) cp_async16_ca(s_pky + i, t.pk_y + ya0 + i);
       const float4* px = t.pk_x + (wA << 5);
       for (int i = tid; i < (nw << 5); i += kUp2Threads) cp_async16_ca(s_pkx + i, px + i);
