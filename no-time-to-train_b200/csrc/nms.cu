@@ -71,14 +71,57 @@ nms_sort_kernel(const float* __restrict__ scores, const int32_t* __restrict__ bo
   for (int i = threadIdx.x; i < n; i += blockDim.x) emit(i, s_keys[i]);
 }
 
+// Long lists (n > 1024): a second order, by (label, score rank).  Class-aware suppression only acts inside a label, so in
+// this order the suppression matrix is block diagonal and nms_mask_kernel skips everything else.  Single CTA, bitonic sort
+// of 32-bit keys (label + bias) << 13 | score position; gathers boxes and labels into the new order and leaves the map
+// class position -> score position for the scan's epilogue.
+constexpr int kClassKeyBias = 8194;  // labels of filtered boxes go down to -2 - 8191
+__global__ void __launch_bounds__(1024)
+nms_class_sort_kernel(const float4* __restrict__ sorted_box, const int32_t* __restrict__ sorted_label, int n, int n_pad,
+                      int32_t* __restrict__ c2s, float4* __restrict__ cbox, int32_t* __restrict__ clabel) {
+  chain_wait();
+  extern __shared__ unsigned long long s_keys[];
+  uint32_t* keys = reinterpret_cast<uint32_t*>(s_keys);
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x)
+    keys[i] = i < n ? (((uint32_t)(sorted_label[i] + kClassKeyBias) << 13) | (uint32_t)i) : 0xffffffffu;
+  __syncthreads();
+  for (int k = 2; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint32_t a = keys[i], b = keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int ps = (int)(keys[i] & 8191u);
+    c2s[i] = ps;
+    cbox[i] = sorted_box[ps];
+    clabel[i] = sorted_label[ps];
+  }
+}
+
 // suppression bit matrix in sorted order.  kByVictim: bit i of row j set iff i < j, same label, IoU(i,j) > thr — row j
 // lists the earlier boxes that would suppress j if they are kept (wavefront scan).  Otherwise by suppressor: bit j of
 // row i set iff j > i (serial scan).  The IoU arithmetic is symmetric in its two boxes (float additions commute exactly).
 template <bool kByVictim>
 __global__ void __launch_bounds__(256)
 nms_mask_kernel(const float4* __restrict__ sorted_box, const int32_t* __restrict__ sorted_label, int n, float thr,
-                uint32_t* __restrict__ mask, int row_words, uint32_t* __restrict__ nz, int nz_words) {
+                uint32_t* __restrict__ mask, int row_words, uint32_t* __restrict__ nz, int nz_words, int class_sorted) {
   chain_wait();
+  // class_sorted (by-victim form with the nz summary only): the boxes are ordered by (label, score) and the labels
+  // ascend, so a block whose last column box has a smaller label than its first row box holds no same-label pair at all.
+  // It writes nothing — the scan only reads the words flagged in `nz` — and with 80 classes that is all but the two or
+  // three word tiles next to the diagonal of each row chunk.
+  if (class_sorted && kByVictim) {
+    const int r0 = blockIdx.y * 32, jl = min(n - 1, blockIdx.x * 256 + 255);
+    if (r0 >= n || blockIdx.x * 256 > r0 + 31 || sorted_label[jl] < sorted_label[r0]) return;  // (or no column precedes a row)
+  }
   __shared__ float4 s_box[8][32];
   __shared__ int s_lab[8][32];
   const int i = blockIdx.y * 32 + threadIdx.x;  // sorted position of the row box
@@ -259,7 +302,12 @@ __global__ void __launch_bounds__(kScanThreads, 1)
 nms_wave_sparse_kernel(const uint32_t* __restrict__ mt, const uint32_t* __restrict__ nz, int nz_words, int row_words,
                        const int32_t* __restrict__ order, const int32_t* __restrict__ sorted_label,
                        const float* __restrict__ top_score, int n, int max_keep, int32_t* __restrict__ keep,
-                       int32_t* __restrict__ n_keep, int32_t* __restrict__ sel, int32_t* __restrict__ n_sel) {
+                       int32_t* __restrict__ n_keep, int32_t* __restrict__ sel, int32_t* __restrict__ n_sel,
+                       const int32_t* __restrict__ c2s) {
+  // c2s (nullable): the matrix, `nz` and `sorted_label` are in CLASS order (nms_class_sort_kernel) and c2s maps a position
+  // there to the box's position in score order, which is what `order` and the output lists are in: the wavefront runs in
+  // class order (any order that keeps same-label boxes in score order gives the same greedy result), its keep bits are
+  // scattered to score order before the compaction.
   chain_wait();
   __shared__ uint32_t s_K[kScanMaxN / 32];
   __shared__ uint32_t s_S[kScanMaxN / 32];
@@ -274,7 +322,7 @@ nms_wave_sparse_kernel(const uint32_t* __restrict__ mt, const uint32_t* __restri
     const int j = c * 32 + lane;
     const bool valid = j < n;
     const bool gone = !valid || sorted_label[j] < -1;
-    const bool pos = valid && top_score[order[valid ? j : 0]] > 0.0f;
+    const bool pos = valid && top_score[order[valid ? (c2s ? c2s[j] : j) : 0]] > 0.0f;
     const uint32_t pbits = __ballot_sync(kFull, pos);
     const uint32_t diag = valid ? __ldg(mt + (size_t)c * stride + j) : 0u;  // suppressors inside this chunk
     const bool any_diag = __any_sync(kFull, diag != 0u);
@@ -313,6 +361,23 @@ nms_wave_sparse_kernel(const uint32_t* __restrict__ mt, const uint32_t* __restri
     }
   }
   __syncthreads();
+  if (c2s) {  // class order -> score order (s_pub is free now: its low and high halves take the two bit vectors)
+    uint32_t* k2 = reinterpret_cast<uint32_t*>(s_pub);
+    uint32_t* s2 = k2 + kScanMaxN / 32;
+    for (int i = threadIdx.x; i < 2 * (kScanMaxN / 32); i += kScanThreads) k2[i] = 0u;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += kScanThreads) {
+      const uint32_t kb = (s_K[j >> 5] >> (j & 31)) & 1u, sb = (s_S[j >> 5] >> (j & 31)) & 1u;
+      if (kb | sb) {
+        const int ps = c2s[j];
+        if (kb) atomicOr(&k2[ps >> 5], 1u << (ps & 31));
+        if (sb) atomicOr(&s2[ps >> 5], 1u << (ps & 31));
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < row_words; i += kScanThreads) { s_K[i] = k2[i]; s_S[i] = s2[i]; }
+    __syncthreads();
+  }
   auto prefix = [&](const uint32_t* bits) {  // s_pre[w] = number of set bits in words < w (warp 0)
     if (warp == 0) {
       int run = 0;
@@ -357,7 +422,9 @@ size_t nms_workspace_bytes(int n) {
   const size_t nz_words = (row_words + 31) / 32;
   return align_up(sizeof(int32_t) * (size_t)n, 256) + align_up(sizeof(uint32_t) * row_words * (row_words * 32), 256) +
          align_up(sizeof(float4) * (size_t)n, 256) + align_up(sizeof(int32_t) * (size_t)n, 256) +
-         align_up(sizeof(uint32_t) * (size_t)n * nz_words, 256);
+         align_up(sizeof(uint32_t) * (size_t)n * nz_words, 256) +
+         // class order of long lists: boxes, labels, class position -> score position
+         align_up(sizeof(float4) * (size_t)n, 256) + 2 * align_up(sizeof(int32_t) * (size_t)n, 256);
 }
 
 int launch_box_nms(const int32_t* box, const float* nms_scores, const int32_t* labels, const float* top_score, int n,
@@ -395,18 +462,29 @@ int launch_box_nms(const int32_t* box, const float* nms_scores, const int32_t* l
   NTTT_LAUNCH_CHECK();
   dim3 grid(ceil_div(row_words, 8), ceil_div(n, 32));
   if (n <= 1024) {
-    launch_chain(nms_mask_kernel<true>, grid, dim3(32, 8), 0, s, sorted_box, sorted_label, n, thr, mask, row_words, nullptr, 0);
+    launch_chain(nms_mask_kernel<true>, grid, dim3(32, 8), 0, s, sorted_box, sorted_label, n, thr, mask, row_words, nullptr, 0, 0);
     NTTT_LAUNCH_CHECK();
     launch_chain(nms_wave_kernel, 1, kScanThreads, 0, s, mask, row_words, order, sorted_label, top_score, n, max_keep, keep, n_keep, sel,
                                                n_sel);
     NTTT_LAUNCH_CHECK();
     return NTTT_OK;
   }
-  // longer lists: the same wavefront over the non-zero words of each row
-  launch_chain(nms_mask_kernel<true>, grid, dim3(32, 8), 0, s, sorted_box, sorted_label, n, thr, mask, row_words, nz, nz_words);
+  // longer lists: boxes re-ordered by (label, score rank), block-diagonal matrix, the same wavefront over the non-zero
+  // words of each row; g_exp[1] = 2 keeps the score order (A/B)
+  const bool by_class = g_exp[1] != 2;
+  float4* cbox = reinterpret_cast<float4*>(reinterpret_cast<char*>(nz) + align_up(sizeof(uint32_t) * (size_t)n * nz_words, 256));
+  int32_t* clabel = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(cbox) + align_up(sizeof(float4) * (size_t)n, 256));
+  int32_t* c2s = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(clabel) + align_up(sizeof(int32_t) * (size_t)n, 256));
+  if (by_class) {
+    launch_chain(nms_class_sort_kernel, 1, 1024, sizeof(uint32_t) * (size_t)n_pad, s, sorted_box, sorted_label, n, n_pad, c2s, cbox,
+                 clabel);
+    NTTT_LAUNCH_CHECK();
+  }
+  launch_chain(nms_mask_kernel<true>, grid, dim3(32, 8), 0, s, by_class ? cbox : sorted_box, by_class ? clabel : sorted_label, n,
+               thr, mask, row_words, nz, nz_words, by_class ? 1 : 0);
   NTTT_LAUNCH_CHECK();
-  launch_chain(nms_wave_sparse_kernel, 1, kScanThreads, 0, s, mask, nz, nz_words, row_words, order, sorted_label, top_score, n, max_keep,
-                                                    keep, n_keep, sel, n_sel);
+  launch_chain(nms_wave_sparse_kernel, 1, kScanThreads, 0, s, mask, nz, nz_words, row_words, order,
+               by_class ? clabel : sorted_label, top_score, n, max_keep, keep, n_keep, sel, n_sel, by_class ? c2s : nullptr);
   NTTT_LAUNCH_CHECK();
   return NTTT_OK;
 }
